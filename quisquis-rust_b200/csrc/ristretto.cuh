@@ -1,0 +1,109 @@
+// Ristretto255 decode / encode (RFC 9496 4.3.1 / 4.3.2) on top of fe25519.cuh / ge25519.cuh.
+//
+// Replaces curve25519-dalek 3.x `ristretto.rs` CompressedRistretto::decompress and RistrettoPoint::compress, which
+// the reference calls on every API entry/exit (e.g. src/ristretto/keys.rs:278-281, src/elgamal/elgamal.rs:47-52,
+// src/accounts/verifier.rs:95-98).  Branch-free; the reject rules are part of parity.
+#pragma once
+#include "ge25519.cuh"
+
+namespace qq {
+
+// invsqrt(v) = sqrt_ratio_i(1, v) with the multiplications by u = 1 removed.
+QQ_HD u32 fe_invsqrt(fe& r, const fe& v) {
+    fe v3, v7, t, check, one, mone, monei;
+    fe_sq(v3, v);
+    fe_mul(v3, v3, v);
+    fe_sq(v7, v3);
+    fe_mul(v7, v7, v);
+    fe_pow22523(t, v7);
+    fe_mul(r, v3, t);
+    fe_sq(check, r);
+    fe_mul(check, v, check);
+    fe_1(one);
+    fe_neg(mone, one);
+    fe_carry(mone, mone);
+    fe_neg(monei, fe_sqrt_m1());
+    fe_carry(monei, monei);
+    u32 correct = fe_eq(check, one);
+    u32 flipped = fe_eq(check, mone);
+    u32 flipped_i = fe_eq(check, monei);
+    fe ri;
+    fe_mul(ri, r, fe_sqrt_m1());
+    fe_cmov(r, ri, flipped | flipped_i);
+    fe_abs(r);
+    return correct | flipped;
+}
+
+// 32 little-endian bytes (as 8 words) -> extended point with Z = 1.  Returns 1 if the encoding is valid.
+QQ_HD u32 ristretto_decompress(ge_p3& p, const u32 w[8]) {
+    fe s, ss, u1, u2, u1s, u2s, v, I, dx, dy, t;
+    fe_fromwords(s, w);
+    u32 cw[8];
+    fe_towords(cw, s);
+    u32 diff = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) diff |= cw[i] ^ w[i];
+    u32 canonical = diff == 0 ? 1u : 0u;       // rejects s >= p and bit 255 set
+    u32 s_neg = w[0] & 1u;
+    fe_sq(ss, s);
+    fe one;
+    fe_1(one);
+    fe_sub(u1, one, ss);                         // 2T
+    fe_add(u2, one, ss);                         // T+1
+    fe_sq(u2s, u2);
+    fe_sq(u1s, u1);
+    fe_mul(t, u1s, fe_d());
+    fe_neg(v, t);                                // 2T
+    fe_sub(v, v, u2s);                           // 4T  (f-side only below)
+    fe_mul(t, v, u2s);
+    u32 ok = fe_invsqrt(I, t);
+    fe_mul(dx, I, u2);
+    fe_mul(t, I, dx);
+    fe_mul(dy, v, t);
+    fe_add(t, s, s);
+    fe_mul(p.X, t, dx);
+    fe_abs(p.X);
+    fe_carry(p.X, p.X);
+    fe_mul(p.Y, u1, dy);
+    fe_1(p.Z);
+    fe_mul(p.T, p.X, p.Y);
+    u32 t_neg = fe_isnegative(p.T);
+    u32 y_zero = fe_iszero(p.Y);
+    return canonical & (s_neg ^ 1u) & ok & (t_neg ^ 1u) & (y_zero ^ 1u);
+}
+
+// extended point -> canonical 32-byte encoding (8 words)
+QQ_HD void ristretto_compress(u32 w[8], const ge_p3& p) {
+    fe u1, u2, t, inv, i1, i2, zinv, deninv, ix, iy, ed, x, y, zy;
+    fe_add(u1, p.Z, p.Y);                        // 2T
+    fe_sub(t, p.Z, p.Y);                         // 3T
+    fe_mul(u1, u1, t);
+    fe_mul(u2, p.X, p.Y);
+    fe_sq(t, u2);
+    fe_mul(t, u1, t);
+    fe_invsqrt(inv, t);                          // always square for valid points
+    fe_mul(i1, inv, u1);
+    fe_mul(i2, inv, u2);
+    fe_mul(t, i1, i2);
+    fe_mul(zinv, t, p.T);
+    fe_mul(ix, p.X, fe_sqrt_m1());
+    fe_mul(iy, p.Y, fe_sqrt_m1());
+    fe_mul(ed, i1, fe_invsqrt_a_minus_d());
+    fe_mul(t, p.T, zinv);
+    u32 rotate = fe_isnegative(t);
+    x = p.X;
+    y = p.Y;
+    deninv = i2;
+    fe_cmov(x, iy, rotate);
+    fe_cmov(y, ix, rotate);
+    fe_cmov(deninv, ed, rotate);
+    fe_mul(t, x, zinv);
+    fe yc = y;                                   // tight (p.Y or a product)
+    fe_cneg(yc, fe_isnegative(t));
+    fe_sub(zy, p.Z, yc);                         // yc <= 2p limb-wise after cneg
+    fe_mul(t, zy, deninv);
+    fe_abs(t);
+    fe_towords(w, t);
+}
+
+}  // namespace qq

@@ -1,0 +1,204 @@
+// Scalar multiplication building blocks shared by the kernels (and by the host-compiled unit tests).
+//
+//  * variable base: signed radix-16 fixed window, 9-entry projective-Niels table {0,1..8}P kept in memory
+//    (global scratch on the GPU), 63 x (3 dbl-noT + 1 dbl) + 64 table additions, uniform control flow.
+//    Same algorithm family as curve25519-dalek 3.x backend/serial/scalar_mul/variable_base.rs, which the reference
+//    reaches through `&Scalar * &RistrettoPoint` (src/ristretto/keys.rs:279-280, src/elgamal/elgamal.rs:47,50).
+//  * fixed base: signed radix-2^W windows over a precomputed affine-Niels table
+//    tbl[k][j] = j * 2^(W k) * Base, j = 0..2^(W-1); NW madds, no doublings.  Replaces
+//    `&Scalar * &RISTRETTO_BASEPOINT_TABLE` (src/elgamal/elgamal.rs:49,85) and the reference's variable-base use of
+//    the constants B, H in create_delta_and_epsilon_accounts (src/accounts/accounts.rs:214).
+#pragma once
+#include "ge25519.cuh"
+#include "sc25519.cuh"
+
+namespace qq {
+
+struct alignas(16) u32x4 {
+    u32 x, y, z, w;
+};
+
+#define QQ_VB_ENTRIES 9
+#define QQ_VB_TABLE_WORDS (QQ_VB_ENTRIES * 40)
+
+QQ_HD void fe_store4(u32x4* dst, int& o, const fe& a, const fe& b) {
+    // two field elements = 20 words = 5 x 128-bit
+    u32x4 q;
+    q.x = a.v[0]; q.y = a.v[1]; q.z = a.v[2]; q.w = a.v[3]; dst[o++] = q;
+    q.x = a.v[4]; q.y = a.v[5]; q.z = a.v[6]; q.w = a.v[7]; dst[o++] = q;
+    q.x = a.v[8]; q.y = a.v[9]; q.z = b.v[0]; q.w = b.v[1]; dst[o++] = q;
+    q.x = b.v[2]; q.y = b.v[3]; q.z = b.v[4]; q.w = b.v[5]; dst[o++] = q;
+    q.x = b.v[6]; q.y = b.v[7]; q.z = b.v[8]; q.w = b.v[9]; dst[o++] = q;
+}
+QQ_HD void fe_load4(const u32x4* src, int& o, fe& a, fe& b) {
+    u32x4 q;
+    q = src[o++]; a.v[0] = q.x; a.v[1] = q.y; a.v[2] = q.z; a.v[3] = q.w;
+    q = src[o++]; a.v[4] = q.x; a.v[5] = q.y; a.v[6] = q.z; a.v[7] = q.w;
+    q = src[o++]; a.v[8] = q.x; a.v[9] = q.y; b.v[0] = q.z; b.v[1] = q.w;
+    q = src[o++]; b.v[2] = q.x; b.v[3] = q.y; b.v[4] = q.z; b.v[5] = q.w;
+    q = src[o++]; b.v[6] = q.x; b.v[7] = q.y; b.v[8] = q.z; b.v[9] = q.w;
+}
+QQ_HD void ge_cached_store(u32x4* dst, const ge_cached& c) {
+    int o = 0;
+    fe_store4(dst, o, c.YpX, c.YmX);
+    fe_store4(dst, o, c.Z, c.T2d);
+}
+QQ_HD void ge_cached_load(ge_cached& c, const u32x4* src) {
+    int o = 0;
+    fe_load4(src, o, c.YpX, c.YmX);
+    fe_load4(src, o, c.Z, c.T2d);
+}
+QQ_HD void ge_p3_store(u32x4* dst, const ge_p3& p) {
+    int o = 0;
+    fe_store4(dst, o, p.X, p.Y);
+    fe_store4(dst, o, p.Z, p.T);
+}
+QQ_HD void ge_p3_load(ge_p3& p, const u32x4* src) {
+    int o = 0;
+    fe_load4(src, o, p.X, p.Y);
+    fe_load4(src, o, p.Z, p.T);
+}
+
+// Build the 9-entry table {0P, 1P, ..., 8P} (cached form) into tbl (9 x 10 x u32x4 = 1440 B).
+QQ_HD void vb_build_table(u32x4* tbl, const ge_p3& p) {
+    ge_cached c0, c;
+    ge_p3 id, q;
+    ge_identity(id);
+    ge_to_cached(c, id);
+    ge_cached_store(tbl, c);
+    ge_to_cached(c0, p);
+    ge_cached_store(tbl + 10, c0);
+    q = p;
+    for (int i = 2; i <= 8; i++) {
+        ge_add(q, q, c0);
+        ge_to_cached(c, q);
+        ge_cached_store(tbl + 10 * i, c);
+    }
+}
+
+// r = s * P using a table built by vb_build_table.  s: 8 little-endian words, s < 2^253.
+QQ_HD void vb_scalarmult(ge_p3& r, const u32x4* tbl, const u32 s[8]) {
+    u32 rr[9];
+    sc_recode_bias<4, 64>(rr, s);        // rr[8] == 0 for s < 2^253
+    u32 w[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = rr[i];
+    ge_identity(r);
+    for (int k = 63; k >= 0; k--) {
+        if (k != 63) {
+            ge_dbl<false>(r, r);
+            ge_dbl<false>(r, r);
+            ge_dbl<false>(r, r);
+            ge_dbl<true>(r, r);
+        }
+        int d = (int)(w[7] >> 28) - 8;    // signed digit in [-8, 8)
+        // shift the 256-bit register left by one nibble
+#pragma unroll
+        for (int i = 7; i > 0; i--) w[i] = (w[i] << 4) | (w[i - 1] >> 28);
+        w[0] <<= 4;
+        u32 neg = d < 0 ? 1u : 0u;
+        u32 idx = (u32)(d < 0 ? -d : d);
+        ge_cached c;
+        ge_cached_load(c, tbl + 10 * idx);
+        ge_cached_cneg(c, neg);
+        ge_add(r, r, c);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Fixed-base tables.  Layout: entry (k, j) at tbl[(k * (2^(W-1) + 1) + j) * 30 .. +30] words:
+// ypx[10], ymx[10], xy2d[10].  j = 0 is the identity (1, 1, 0).
+// ---------------------------------------------------------------------------------------------------------
+#define QQ_NIELS_WORDS 30
+
+QQ_HD int fb_num_windows(int w) { return (256 + w - 1) / w; }   // W*NW >= 256 keeps the recoding carry-free
+QQ_HD int fb_entries(int w) { return (1 << (w - 1)) + 1; }
+
+QQ_HD void ge_niels_load(ge_niels& n, const u32* src) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        n.ypx.v[i] = src[i];
+        n.ymx.v[i] = src[10 + i];
+        n.xy2d.v[i] = src[20 + i];
+    }
+}
+
+// r = s * Base from table (W-bit signed windows).  tbl may point to shared or global memory.
+template <int W>
+QQ_HD void fb_scalarmult(ge_p3& r, const u32* tbl, const u32 s[8]) {
+    const int NW = (256 + W - 1) / W;
+    const int ENT = (1 << (W - 1)) + 1;
+    u32 rr[9];
+    sc_recode_bias<W, NW>(rr, s);
+    ge_identity(r);
+#pragma unroll 1
+    for (int k = 0; k < NW; k++) {
+        // extract digit k: shift-free approach needs dynamic word index -> read via small switchless funnel
+        int bit = W * k;
+        int wi = bit >> 5, sh = bit & 31;
+        u32 lo = 0, hi = 0;
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            lo = (i == wi) ? rr[i] : lo;
+            hi = (i == wi + 1) ? rr[i] : hi;
+        }
+        u64 two = (u64)lo | ((u64)hi << 32);
+        int d = (int)((u32)(two >> sh) & ((1u << W) - 1u)) - (1 << (W - 1));
+        u32 neg = d < 0 ? 1u : 0u;
+        u32 idx = (u32)(d < 0 ? -d : d);
+        ge_niels n;
+        ge_niels_load(n, tbl + (size_t)(k * ENT + idx) * QQ_NIELS_WORDS);
+        ge_niels_cneg(n, neg);
+        ge_madd(r, r, n);
+    }
+}
+
+// Field inversion z^(p-2) (used only when normalising precomputed tables; not on the hot path).
+QQ_HD void fe_invert(fe& out, const fe& z) {
+    // z^(p-2) = z^(2^255 - 21) = (z^(2^252-3))^8 * z^3
+    fe t, z2, z3;
+    fe_pow22523(t, z);      // z^(2^252-3)
+    fe_sqn(t, t, 3);        // z^(2^255-24)
+    fe_sq(z2, z);
+    fe_mul(z3, z2, z);
+    fe_mul(out, t, z3);     // z^(2^255-21)
+}
+
+// Table entry (k, j) = (j << (W k)) * base by plain double-and-add (table construction only, one-off).
+QQ_HD void fb_build_entry(u32* dst, const ge_p3& base, int W, int k, int j);
+
+// Convert an extended point to affine Niels (one inversion).  For table construction only.
+QQ_HD void ge_to_niels_affine(u32* dst, const ge_p3& p) {
+    fe zi, x, y, t;
+    fe_invert(zi, p.Z);
+    fe_mul(x, p.X, zi);
+    fe_mul(y, p.Y, zi);
+    fe ypx, ymx, xy2d;
+    fe_add(t, y, x);
+    fe_carry(ypx, t);
+    fe_sub(t, y, x);
+    fe_carry(ymx, t);
+    fe_mul(t, x, y);
+    fe_mul(xy2d, t, fe_2d());
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        dst[i] = ypx.v[i];
+        dst[10 + i] = ymx.v[i];
+        dst[20 + i] = xy2d.v[i];
+    }
+}
+
+QQ_HD void fb_build_entry(u32* dst, const ge_p3& base, int W, int k, int j) {
+    ge_p3 r;
+    ge_identity(r);
+    ge_cached cb;
+    ge_to_cached(cb, base);
+    for (int b = W - 1; b >= 0; b--) {
+        ge_dbl<true>(r, r);
+        if ((j >> b) & 1) ge_add(r, r, cb);
+    }
+    for (int i = 0; i < W * k; i++) ge_dbl<true>(r, r);
+    ge_to_niels_affine(dst, r);
+}
+
+}  // namespace qq

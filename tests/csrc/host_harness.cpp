@@ -1,0 +1,190 @@
+// TEST INFRASTRUCTURE: compiles the device arithmetic headers (fe25519/ge25519/ristretto/scalarmult .cuh) for the
+// host with g++, so that tests/test_host_arith.py can check the exact limb arithmetic the kernels run against
+// the oracle without a GPU.  This object is never linked into libqq_b200.so and is not a CPU fallback.
+#include <cstring>
+#include <vector>
+#include "../../quisquis-rust_b200/csrc/ristretto.cuh"
+#include "../../quisquis-rust_b200/csrc/scalarmult.cuh"
+
+using namespace qq;
+
+static void load_words(u32 w[8], const uint8_t* b) { memcpy(w, b, 32); }
+static void store_words(uint8_t* b, const u32 w[8]) { memcpy(b, w, 32); }
+
+extern "C" {
+
+void hh_fe_mul_limbs(u32* out, const u32* f, const u32* g) {
+    fe a, b, c;
+    memcpy(a.v, f, 40);
+    memcpy(b.v, g, 40);
+    fe_mul(c, a, b);
+    memcpy(out, c.v, 40);
+}
+void hh_fe_sq_limbs(u32* out, const u32* f) {
+    fe a, c;
+    memcpy(a.v, f, 40);
+    fe_sq(c, a);
+    memcpy(out, c.v, 40);
+}
+void hh_fe_carry_limbs(u32* out, const u32* f) {
+    fe a, c;
+    memcpy(a.v, f, 40);
+    fe_carry(c, a);
+    memcpy(out, c.v, 40);
+}
+void hh_fe_tobytes_limbs(uint8_t* out, const u32* f) {
+    fe a;
+    memcpy(a.v, f, 40);
+    u32 w[8];
+    fe_towords(w, a);
+    store_words(out, w);
+}
+void hh_fe_frombytes(u32* out, const uint8_t* in) {
+    u32 w[8];
+    load_words(w, in);
+    fe a;
+    fe_fromwords(a, w);
+    memcpy(out, a.v, 40);
+}
+void hh_fe_const(int which, uint8_t* out) {
+    fe c = which == 0 ? fe_d() : which == 1 ? fe_2d() : which == 2 ? fe_sqrt_m1() : which == 3 ? fe_invsqrt_a_minus_d()
+         : which == 4 ? fe_sqrt_ad_minus_one() : which == 5 ? fe_one_minus_d_sq() : fe_d_minus_one_sq();
+    u32 w[8];
+    fe_towords(w, c);
+    store_words(out, w);
+}
+int hh_sqrt_ratio_i(uint8_t* out, const uint8_t* u, const uint8_t* v) {
+    u32 w[8];
+    fe fu, fv, r;
+    load_words(w, u);
+    fe_fromwords(fu, w);
+    load_words(w, v);
+    fe_fromwords(fv, w);
+    int ok = (int)fe_sqrt_ratio_i(r, fu, fv);
+    fe_towords(w, r);
+    store_words(out, w);
+    return ok;
+}
+void hh_fe_invert(uint8_t* out, const uint8_t* z) {
+    u32 w[8];
+    fe a, r;
+    load_words(w, z);
+    fe_fromwords(a, w);
+    fe_invert(r, a);
+    fe_towords(w, r);
+    store_words(out, w);
+}
+// decompress: returns ok; xyzt = 4 x 32 canonical bytes
+int hh_decompress(uint8_t* xyzt, const uint8_t* in) {
+    u32 w[8];
+    load_words(w, in);
+    ge_p3 p;
+    int ok = (int)ristretto_decompress(p, w);
+    fe_towords(w, p.X); store_words(xyzt, w);
+    fe_towords(w, p.Y); store_words(xyzt + 32, w);
+    fe_towords(w, p.Z); store_words(xyzt + 64, w);
+    fe_towords(w, p.T); store_words(xyzt + 96, w);
+    return ok;
+}
+static void p3_from_bytes(ge_p3& p, const uint8_t* xyzt) {
+    u32 w[8];
+    load_words(w, xyzt); fe_fromwords(p.X, w);
+    load_words(w, xyzt + 32); fe_fromwords(p.Y, w);
+    load_words(w, xyzt + 64); fe_fromwords(p.Z, w);
+    load_words(w, xyzt + 96); fe_fromwords(p.T, w);
+}
+void hh_compress_xyzt(uint8_t* out, const uint8_t* xyzt) {
+    ge_p3 p;
+    p3_from_bytes(p, xyzt);
+    u32 w[8];
+    ristretto_compress(w, p);
+    store_words(out, w);
+}
+int hh_add(uint8_t* out, const uint8_t* a, const uint8_t* b) {
+    u32 w[8];
+    ge_p3 p, q, r;
+    load_words(w, a);
+    int ok = (int)ristretto_decompress(p, w);
+    load_words(w, b);
+    ok &= (int)ristretto_decompress(q, w);
+    ge_cached c;
+    ge_to_cached(c, q);
+    ge_add(r, p, c);
+    ristretto_compress(w, r);
+    store_words(out, w);
+    return ok;
+}
+int hh_sub_madd(uint8_t* out, const uint8_t* a, const uint8_t* b) {  // a - b via negated affine Niels
+    u32 w[8];
+    ge_p3 p, q, r;
+    load_words(w, a);
+    int ok = (int)ristretto_decompress(p, w);
+    load_words(w, b);
+    ok &= (int)ristretto_decompress(q, w);
+    ge_niels n;
+    ge_to_niels_z1(n, q);
+    ge_niels_cneg(n, 1);
+    ge_madd(r, p, n);
+    ristretto_compress(w, r);
+    store_words(out, w);
+    return ok;
+}
+int hh_dbl(uint8_t* out, const uint8_t* a, int n) {
+    u32 w[8];
+    ge_p3 p;
+    load_words(w, a);
+    int ok = (int)ristretto_decompress(p, w);
+    for (int i = 0; i < n; i++) {
+        if (i == n - 1) ge_dbl<true>(p, p);
+        else ge_dbl<false>(p, p);
+    }
+    ristretto_compress(w, p);
+    store_words(out, w);
+    return ok;
+}
+int hh_eq(const uint8_t* a, const uint8_t* b) {
+    u32 w[8];
+    ge_p3 p, q;
+    load_words(w, a);
+    ristretto_decompress(p, w);
+    load_words(w, b);
+    ristretto_decompress(q, w);
+    return (int)ge_ristretto_eq(p, q) | ((int)ge_ristretto_is_identity(p) << 1);
+}
+int hh_scalarmult(uint8_t* out, const uint8_t* scalar, const uint8_t* point) {
+    u32 w[8], s[8];
+    ge_p3 p, r;
+    load_words(w, point);
+    int ok = (int)ristretto_decompress(p, w);
+    load_words(s, scalar);
+    std::vector<u32x4> tbl(QQ_VB_ENTRIES * 10);
+    vb_build_table(tbl.data(), p);
+    vb_scalarmult(r, tbl.data(), s);
+    ristretto_compress(w, r);
+    store_words(out, w);
+    return ok | ((int)sc_is_canonical(s) << 1);
+}
+// fixed base: W in {4,5,6,8}; builds the table on each call into caller-provided buffer (words)
+size_t hh_fb_table_words(int W) { return (size_t)fb_num_windows(W) * fb_entries(W) * QQ_NIELS_WORDS; }
+int hh_fb_build(u32* tbl, int W, const uint8_t* base) {
+    u32 w[8];
+    ge_p3 p;
+    load_words(w, base);
+    int ok = (int)ristretto_decompress(p, w);
+    for (int k = 0; k < fb_num_windows(W); k++)
+        for (int j = 0; j < fb_entries(W); j++)
+            fb_build_entry(tbl + ((size_t)k * fb_entries(W) + j) * QQ_NIELS_WORDS, p, W, k, j);
+    return ok;
+}
+void hh_fb_mult(uint8_t* out, const u32* tbl, int W, const uint8_t* scalar) {
+    u32 s[8], w[8];
+    load_words(s, scalar);
+    ge_p3 r;
+    if (W == 4) fb_scalarmult<4>(r, tbl, s);
+    else if (W == 5) fb_scalarmult<5>(r, tbl, s);
+    else if (W == 6) fb_scalarmult<6>(r, tbl, s);
+    else fb_scalarmult<8>(r, tbl, s);
+    ristretto_compress(w, r);
+    store_words(out, w);
+}
+}
