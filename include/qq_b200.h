@@ -1,0 +1,153 @@
+/* qq_b200.h -- C ABI of libqq_b200.so: the B200 (sm_100a) implementation of quisquis-rust's data-parallel hot path
+ * (batched Ristretto255 scalar multiplication behind account updates / ElGamal commitments, and multiscalar
+ * multiplication under proof verification).
+ *
+ * The reference has no FFI boundary (`#![deny(unsafe_code)]`, reference src/lib.rs:4); the seam is its public Rust API.
+ * Every entry point below names the reference function it batches (file:line under /root/reference).  A Rust
+ * `cuda/` sys crate binds these symbols; tests and bench.py bind them with ctypes.
+ *
+ * Conventions
+ *   - All arrays are caller-owned and tightly packed (AoS exactly as the reference serialises its types):
+ *       CompressedRistretto 32 B; Scalar 32 B little-endian; RistrettoPublicKey = gr||grsk 64 B
+ *       (src/ristretto/keys.rs:113-120); ElGamalCommitment = c||d 64 B (src/elgamal/elgamal.rs:135-142);
+ *       Account = pk||comm 128 B (src/accounts/accounts.rs:47-53).
+ *   - Functions without a suffix take HOST pointers: the library stages host->device, runs the kernels and copies
+ *     results back before returning (synchronous).  `_dev` variants take DEVICE pointers on the ctx's GPU and only
+ *     enqueue + synchronise the kernels.
+ *   - Return value: QQ_OK or a negative QQ_ERR_* (API-level failure: bad argument, CUDA error, out of memory).
+ *   - status[i] (one byte per element): see QQ_ST_*.  Where the reference would panic (`.unwrap()` on a failed
+ *     decompress, e.g. src/ristretto/keys.rs:278-279, src/elgamal/elgamal.rs:47,50,66-67) or return
+ *     Err("Error::Decompression Failed") / None, status[i] = QQ_ST_BAD_POINT and the outputs for element i are zero.
+ *   - One qq_ctx per GPU and per calling thread (or external locking).  There is NO CPU fallback: qq_init fails
+ *     when no sm_100 device is usable.
+ */
+#ifndef QQ_B200_H
+#define QQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QQ_OK 0
+#define QQ_ERR_ARG (-1)
+#define QQ_ERR_CUDA (-2)
+#define QQ_ERR_NOMEM (-3)
+#define QQ_ERR_NODEVICE (-4)
+
+#define QQ_ST_OK 0
+#define QQ_ST_BAD_POINT 1   /* a compressed point failed RFC 9496 decoding */
+#define QQ_ST_BAD_SCALAR 2  /* a scalar was not canonical (>= l) */
+#define QQ_ST_KEYPAIR 3     /* Err("Invalid Account::Keypair Verification Failed") / `false` */
+#define QQ_ST_COMMIT 4      /* Err("Invalid Account::Commitment Verification Failed") / identity check failed */
+
+#define QQ_BASE_B 0 /* Ristretto basepoint, BASE_PK_BTC_COMPRESSED[0] (src/ristretto/constants.rs:13-16) */
+#define QQ_BASE_H 1 /* Pedersen H,         BASE_PK_BTC_COMPRESSED[1] (src/ristretto/constants.rs:17-20) */
+
+typedef struct qq_ctx qq_ctx;
+
+/* ---- context ------------------------------------------------------------------------------------------------- */
+int qq_init(qq_ctx** ctx, int device);
+void qq_destroy(qq_ctx* ctx);
+const char* qq_last_error(const qq_ctx* ctx);
+int qq_device_sm_count(const qq_ctx* ctx);
+/* number of kernels launched by this ctx since creation (bench.py reports it as gpu_launches) */
+uint64_t qq_launch_count(const qq_ctx* ctx);
+/* milliseconds spent in kernels during the most recent call, measured with CUDA events on the ctx stream */
+float qq_last_kernel_ms(const qq_ctx* ctx);
+/* per-kernel-family milliseconds of the most recent call: [0] decompress [1] variable-base [2] fixed-base
+ * [3] finish/compress [4] msm-bucket [5] msm-reduce; returns number of entries written */
+int qq_last_kernel_breakdown(const qq_ctx* ctx, float* ms, int cap);
+/* device memory helpers for the _dev entry points (thin cudaMalloc/cudaMemcpy wrappers so callers need no CUDA) */
+int qq_dev_alloc(qq_ctx* ctx, void** dptr, size_t bytes);
+int qq_dev_free(qq_ctx* ctx, void* dptr);
+int qq_dev_upload(qq_ctx* ctx, void* dptr, const void* host, size_t bytes);
+int qq_dev_download(qq_ctx* ctx, void* host, const void* dptr, size_t bytes);
+/* integer-pipe micro-benchmark: thread-level IMAD.WIDE-class ops per second on this device (roofline denominator) */
+int qq_measure_imad_peak(qq_ctx* ctx, double* wide_ops_per_s, double* lo_ops_per_s);
+
+/* ---- RistrettoPublicKey ----------------------------------------------------------------------------------------
+ * update_public_key(p, r) = (r*gr, r*grsk)              reference src/ristretto/keys.rs:146-148 (Mul :266-282) */
+int qq_update_public_key_batch(qq_ctx* ctx, const uint8_t* pk, const uint8_t* r, uint8_t* out_pk, uint8_t* status,
+                               size_t n);
+int qq_update_public_key_batch_dev(qq_ctx* ctx, const uint8_t* pk, const uint8_t* r, uint8_t* out_pk,
+                                   uint8_t* status, size_t n);
+/* verify_public_key_update(u, p, r): status 0 = true, QQ_ST_KEYPAIR = false   src/ristretto/keys.rs:161-169 */
+int qq_verify_public_key_update_batch(qq_ctx* ctx, const uint8_t* updated_pk, const uint8_t* pk, const uint8_t* r,
+                                      uint8_t* status, size_t n);
+
+/* ---- ElGamalCommitment -----------------------------------------------------------------------------------------
+ * generate_commitment(p, r, v) = (r*gr, v*B + r*grsk)                         src/elgamal/elgamal.rs:41-53 */
+int qq_generate_commitment_batch(qq_ctx* ctx, const uint8_t* pk, const uint8_t* r, const uint8_t* v,
+                                 uint8_t* out_comm, uint8_t* status, size_t n);
+int qq_generate_commitment_batch_dev(qq_ctx* ctx, const uint8_t* pk, const uint8_t* r, const uint8_t* v,
+                                     uint8_t* out_comm, uint8_t* status, size_t n);
+/* add_commitments(a, b)                                                       src/elgamal/elgamal.rs:65-69
+ * impl Sub (negate = 1)                                                       src/elgamal/elgamal.rs:201-218 */
+int qq_add_commitments_batch(qq_ctx* ctx, const uint8_t* a, const uint8_t* b, int negate_b, uint8_t* out_comm,
+                             uint8_t* status, size_t n);
+/* impl Mul<&Scalar> for &ElGamalCommitment                                    src/elgamal/elgamal.rs:220-236 */
+int qq_mul_commitment_batch(qq_ctx* ctx, const uint8_t* comm, const uint8_t* s, uint8_t* out_comm, uint8_t* status,
+                            size_t n);
+
+/* ---- Account ---------------------------------------------------------------------------------------------------
+ * update_account(a, bl, u, c): pk' = u*pk ; comm' = generate_commitment(OLD pk, c, bl) + a.comm
+ *                                                                             src/accounts/accounts.rs:143-154 */
+int qq_update_account_batch(qq_ctx* ctx, const uint8_t* acc, const uint8_t* bl, const uint8_t* u, const uint8_t* c,
+                            uint8_t* out_acc, uint8_t* status, size_t n);
+int qq_update_account_batch_dev(qq_ctx* ctx, const uint8_t* acc, const uint8_t* bl, const uint8_t* u,
+                                const uint8_t* c, uint8_t* out_acc, uint8_t* status, size_t n);
+/* verify_account(sk, bl): status 0 / QQ_ST_KEYPAIR / QQ_ST_COMMIT / QQ_ST_BAD_POINT
+ *                                                                             src/accounts/accounts.rs:81-84 */
+int qq_verify_account_batch(qq_ctx* ctx, const uint8_t* acc, const uint8_t* sk, const uint8_t* bl, uint8_t* status,
+                            size_t n);
+int qq_verify_account_batch_dev(qq_ctx* ctx, const uint8_t* acc, const uint8_t* sk, const uint8_t* bl,
+                                uint8_t* status, size_t n);
+/* create_delta_and_epsilon_accounts(a, bl, base_pk) with the random scalars r supplied by the caller (the reference
+ * draws them from OsRng inside the function, src/accounts/accounts.rs:203,318-326):
+ *   delta_i   = (a_i.pk,  generate_commitment(a_i.pk,  r_i, bl_i))
+ *   epsilon_i = (base_pk, generate_commitment(base_pk, r_i, bl_i))           src/accounts/accounts.rs:198-220
+ * base_pk must be BASE_PK_BTC_COMPRESSED (B, H) -- the fixed-base tables are built for it; any other 64 bytes make
+ * the call fall back to the variable-base kernel for the epsilon half. */
+int qq_delta_epsilon_batch(qq_ctx* ctx, const uint8_t* acc, const uint8_t* bl, const uint8_t* r,
+                           const uint8_t* base_pk, uint8_t* out_delta, uint8_t* out_epsilon, uint8_t* status,
+                           size_t n);
+/* Verifier::verify_delta_identity_check: sum of c and sum of d over all n accounts must be the identity.
+ * *verdict = QQ_ST_OK / QQ_ST_COMMIT / QQ_ST_BAD_POINT                        src/accounts/verifier.rs:566-581 */
+int qq_delta_identity_check(qq_ctx* ctx, const uint8_t* acc, size_t n, uint8_t* verdict);
+
+/* ---- fixed-base multiplication: out_i = s_i * Base, Base in {QQ_BASE_B, QQ_BASE_H}
+ * `&Scalar * &RISTRETTO_BASEPOINT_TABLE` (src/elgamal/elgamal.rs:49,85; src/ristretto/keys.rs:102) and the B/H legs of
+ * PedersenGens::commit used throughout src/shuffle */
+int qq_fixed_base_batch(qq_ctx* ctx, int which, const uint8_t* s, uint8_t* out_points, uint8_t* status, size_t n);
+int qq_fixed_base_batch_dev(qq_ctx* ctx, int which, const uint8_t* s, uint8_t* out_points, uint8_t* status,
+                            size_t n);
+
+/* ---- multiscalar multiplication --------------------------------------------------------------------------------
+ * Verifier::multiscalar_multiplication = RistrettoPoint::optional_multiscalar_mul over compressed points
+ * (src/accounts/verifier.rs:91-99) and the Bulletproofs verification mega-MSM reached from
+ * src/accounts/verifier.rs:517,548.  out = sum_i s_i * decompress(P_i) compressed; *status = QQ_ST_BAD_POINT when any
+ * point fails to decode (the reference returns None), QQ_ST_BAD_SCALAR for a non-canonical scalar. */
+int qq_msm(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t* out_point,
+           uint8_t* status);
+int qq_msm_dev(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t* out_point,
+               uint8_t* status);
+/* same sum, but returns the uncompressed partial result as 4 x 32 canonical bytes (X, Y, Z, T) so that per-GPU
+ * partial sums can be gathered (NCCL all-gather, 128 B per rank) and combined with qq_points_sum. */
+int qq_msm_partial(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t* out_xyzt,
+                   uint8_t* status);
+int qq_msm_partial_dev(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t* out_xyzt,
+                       uint8_t* status);
+/* sum of k extended points given as k x 128 B (X,Y,Z,T canonical) -> compressed; *is_identity set to 1/0 */
+int qq_points_sum(qq_ctx* ctx, const uint8_t* xyzt, size_t k, uint8_t* out_point, uint8_t* is_identity);
+/* many small MSMs (2..9 terms each in the reference, src/accounts/verifier.rs:165-880, src/shuffle/*):
+ * instance j covers terms offsets[j] .. offsets[j+1]-1 ; out m x 32 B ; status m */
+int qq_msm_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* points, const uint32_t* offsets, size_t m,
+                     uint8_t* out_points, uint8_t* status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QQ_B200_H */

@@ -1,0 +1,235 @@
+"""Host-side mirror of the reference's operator interface for the hot path (same names, argument meaning and error
+behaviour), routed through libqq_b200.so.  Scalar (n = 1) forms follow the reference signatures; `*_batch` forms are
+the data-parallel entry points the Rust shim would add.
+
+Reference: src/keys.rs:33-126 (trait PublicKey), src/ristretto/keys.rs, src/elgamal/elgamal.rs,
+src/accounts/accounts.rs, src/accounts/verifier.rs:91-99,566-581.
+"""
+import numpy as np
+
+from . import binding as B
+
+_engine = None
+
+
+def default_engine():
+    global _engine
+    if _engine is None:
+        _engine = B.Engine(0)
+    return _engine
+
+
+def set_default_engine(e):
+    global _engine
+    _engine = e
+
+
+class PanicError(RuntimeError):
+    """The reference panics here (`.unwrap()` on a failed decompress)."""
+
+
+def _b(x, n):
+    a = np.frombuffer(bytes(x), dtype=np.uint8) if not isinstance(x, np.ndarray) else x
+    if a.size != n:
+        raise ValueError("expected %d bytes" % n)
+    return a
+
+
+class RistrettoPublicKey:
+    """src/ristretto/keys.rs:75-79; 64 bytes gr||grsk."""
+
+    def __init__(self, data):
+        self.data = bytes(_b(data, 64))
+
+    def as_bytes(self):
+        return self.data
+
+    @staticmethod
+    def generate_base_pk():
+        """src/ristretto/keys.rs:171-177 -> BASE_PK_BTC_COMPRESSED."""
+        return RistrettoPublicKey(bytes.fromhex(
+            "e2f2ae0a6abc4e71a884a961c500515f58e30b6aa582dd8db6a65945e08d2d76"
+            "8c9240b456a9e6dc65c377a1048d745f94a08cdb7f44cbcd7b46f34048871134"))
+
+    @staticmethod
+    def update_public_key(p, rscalar):
+        """src/ristretto/keys.rs:146-148."""
+        out, st = default_engine().update_public_key(_b(p.data, 64), _b(rscalar, 32))
+        if st[0] == B.ST_BAD_POINT:
+            raise PanicError("called `Option::unwrap()` on a `None` value")
+        if st[0]:
+            raise ValueError("non-canonical scalar")
+        return RistrettoPublicKey(out[0].tobytes())
+
+    @staticmethod
+    def update_public_key_batch(pks, rscalars, engine=None):
+        return (engine or default_engine()).update_public_key(pks, rscalars)
+
+    @staticmethod
+    def verify_public_key_update(u, p, rscalar):
+        """src/ristretto/keys.rs:161-169 -> bool."""
+        st = default_engine().verify_public_key_update(_b(u.data, 64), _b(p.data, 64), _b(rscalar, 32))
+        if st[0] == B.ST_BAD_POINT:
+            raise PanicError("called `Option::unwrap()` on a `None` value")
+        return st[0] == 0
+
+    def verify_keypair(self, sk):
+        """src/ristretto/keys.rs:187-195 -> None or raises ValueError(msg) like Err(msg)."""
+        acc = self.data + bytes(64)
+        st = default_engine().verify_account(_b(acc, 128), _b(sk, 32), np.zeros(32, np.uint8))
+        if st[0] == B.ST_BAD_POINT:
+            raise ValueError("Error::Decompression Failed")
+        if st[0] == B.ST_KEYPAIR:
+            raise ValueError("Invalid Account::Keypair Verification Failed")
+        return None
+
+    def __eq__(self, o):
+        return self.data == o.data
+
+
+class ElGamalCommitment:
+    """src/elgamal/elgamal.rs:18-22; 64 bytes c||d."""
+
+    def __init__(self, data):
+        self.data = bytes(_b(data, 64))
+
+    def to_bytes(self):
+        return self.data
+
+    @staticmethod
+    def generate_commitment(p, rscalar, bl_scalar):
+        """src/elgamal/elgamal.rs:41-53."""
+        out, st = default_engine().generate_commitment(_b(p.data, 64), _b(rscalar, 32), _b(bl_scalar, 32))
+        if st[0] == B.ST_BAD_POINT:
+            raise PanicError("called `Option::unwrap()` on a `None` value")
+        if st[0]:
+            raise ValueError("non-canonical scalar")
+        return ElGamalCommitment(out[0].tobytes())
+
+    @staticmethod
+    def generate_commitment_batch(pks, rscalars, bl_scalars, engine=None):
+        return (engine or default_engine()).generate_commitment(pks, rscalars, bl_scalars)
+
+    @staticmethod
+    def add_commitments(a, b):
+        """src/elgamal/elgamal.rs:65-69."""
+        out, st = default_engine().add_commitments(_b(a.data, 64), _b(b.data, 64))
+        if st[0]:
+            raise PanicError("called `Option::unwrap()` on a `None` value")
+        return ElGamalCommitment(out[0].tobytes())
+
+    def __sub__(self, other):
+        """src/elgamal/elgamal.rs:201-218."""
+        out, st = default_engine().add_commitments(_b(self.data, 64), _b(other.data, 64), negate_b=True)
+        if st[0]:
+            raise PanicError("called `Option::unwrap()` on a `None` value")
+        return ElGamalCommitment(out[0].tobytes())
+
+    def __mul__(self, scalar):
+        """src/elgamal/elgamal.rs:220-236."""
+        out, st = default_engine().mul_commitment(_b(self.data, 64), _b(scalar, 32))
+        if st[0] == B.ST_BAD_POINT:
+            raise PanicError("called `Option::unwrap()` on a `None` value")
+        return ElGamalCommitment(out[0].tobytes())
+
+    def __eq__(self, o):
+        return self.data == o.data
+
+
+class Account:
+    """src/accounts/accounts.rs:47-53; 128 bytes pk||comm."""
+
+    def __init__(self, data):
+        self.data = bytes(_b(data, 128))
+
+    @staticmethod
+    def set_account(pk, comm):
+        return Account(pk.data + comm.data)
+
+    @property
+    def pk(self):
+        return RistrettoPublicKey(self.data[:64])
+
+    @property
+    def comm(self):
+        return ElGamalCommitment(self.data[64:])
+
+    @staticmethod
+    def update_account(a, bl, update_key_scalar, generate_commitment_scalar):
+        """src/accounts/accounts.rs:143-154."""
+        out, st = default_engine().update_account(_b(a.data, 128), _b(bl, 32), _b(update_key_scalar, 32),
+                                                  _b(generate_commitment_scalar, 32))
+        if st[0] == B.ST_BAD_POINT:
+            raise PanicError("called `Option::unwrap()` on a `None` value")
+        if st[0]:
+            raise ValueError("non-canonical scalar")
+        return Account(out[0].tobytes())
+
+    @staticmethod
+    def update_account_batch(accounts, bl, u, c, engine=None):
+        return (engine or default_engine()).update_account(accounts, bl, u, c)
+
+    def verify_account(self, sk, bl):
+        """src/accounts/accounts.rs:81-84 -> None or raises ValueError(msg) like Err(msg)."""
+        st = default_engine().verify_account(_b(self.data, 128), _b(sk, 32), _b(bl, 32))
+        msg = {B.ST_BAD_POINT: "Error::Decompression Failed",
+               B.ST_KEYPAIR: "Invalid Account::Keypair Verification Failed",
+               B.ST_COMMIT: "Invalid Account::Commitment Verification Failed",
+               B.ST_BAD_SCALAR: "non-canonical scalar"}
+        if st[0]:
+            raise ValueError(msg[int(st[0])])
+        return None
+
+    @staticmethod
+    def verify_account_batch(accounts, sks, bls, engine=None):
+        return (engine or default_engine()).verify_account(accounts, sks, bls)
+
+    @staticmethod
+    def verify_account_update(updated_input_accounts, accounts, updated_keys_scalar, generate_commitment_scalar):
+        """src/accounts/accounts.rs:173-193: recompute update_account with bl = 0 for exactly 9 accounts (quirk kept:
+        shorter input raises, like the reference's index panic) and compare all 128 bytes."""
+        if min(len(accounts), len(updated_keys_scalar), len(generate_commitment_scalar)) < 9:
+            raise PanicError("index out of bounds")
+        acc = np.frombuffer(b"".join(a.data for a in accounts[:9]), np.uint8)
+        u = np.frombuffer(b"".join(bytes(x) for x in updated_keys_scalar[:9]), np.uint8)
+        c = np.frombuffer(b"".join(bytes(x) for x in generate_commitment_scalar[:9]), np.uint8)
+        out, st = default_engine().update_account(acc, np.zeros(9 * 32, np.uint8), u, c)
+        if (st == B.ST_BAD_POINT).any():
+            raise PanicError("called `Option::unwrap()` on a `None` value")
+        return all(out[i].tobytes() == ua.data for i, ua in zip(range(9), updated_input_accounts))
+
+    @staticmethod
+    def create_delta_and_epsilon_accounts(a, bl, base_pk, rscalar):
+        """src/accounts/accounts.rs:198-220 with the randomness `rscalar` supplied (the reference draws it inside)."""
+        n = len(a)
+        acc = np.frombuffer(b"".join(x.data for x in a), np.uint8)
+        blb = np.frombuffer(b"".join(bytes(x) for x in bl), np.uint8)
+        rb = np.frombuffer(b"".join(bytes(x) for x in rscalar), np.uint8)
+        d, e, st = default_engine().delta_epsilon(acc, blb, rb, _b(base_pk.data, 64))
+        if (st == B.ST_BAD_POINT).any():
+            raise PanicError("called `Option::unwrap()` on a `None` value")
+        return ([Account(d[i].tobytes()) for i in range(n)], [Account(e[i].tobytes()) for i in range(n)], list(rscalar))
+
+    def __eq__(self, o):
+        return self.data == o.data
+
+
+class Verifier:
+    @staticmethod
+    def multiscalar_multiplication(combined_scalars, point):
+        """src/accounts/verifier.rs:91-99 -> 32-byte compressed point, or None if any point fails to decompress."""
+        s = np.frombuffer(b"".join(bytes(x) for x in combined_scalars), np.uint8)
+        p = np.frombuffer(b"".join(bytes(x) for x in point), np.uint8)
+        out, st = default_engine().msm(s, p)
+        return None if st else out.tobytes()
+
+    @staticmethod
+    def verify_delta_identity_check(epsilon_accounts):
+        """src/accounts/verifier.rs:566-581."""
+        acc = np.frombuffer(b"".join(x.data for x in epsilon_accounts), np.uint8)
+        v = default_engine().delta_identity_check(acc)
+        if v == B.ST_BAD_POINT:
+            raise PanicError("called `Option::unwrap()` on a `None` value")
+        if v:
+            raise ValueError("Identity sum verify: Failed")
+        return None

@@ -1,0 +1,283 @@
+"""ctypes binding of libqq_b200.so (include/qq_b200.h).  No CPU fallback: a missing library or GPU raises."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+QQ_OK = 0
+ST_OK, ST_BAD_POINT, ST_BAD_SCALAR, ST_KEYPAIR, ST_COMMIT = 0, 1, 2, 3, 4
+BASE_B, BASE_H = 0, 1
+
+EXPORTS = [
+    "qq_init", "qq_destroy", "qq_last_error", "qq_device_sm_count", "qq_launch_count", "qq_last_kernel_ms",
+    "qq_last_kernel_breakdown", "qq_dev_alloc", "qq_dev_free", "qq_dev_upload", "qq_dev_download",
+    "qq_measure_imad_peak",
+    "qq_update_public_key_batch", "qq_update_public_key_batch_dev", "qq_verify_public_key_update_batch",
+    "qq_generate_commitment_batch", "qq_generate_commitment_batch_dev", "qq_add_commitments_batch",
+    "qq_mul_commitment_batch", "qq_update_account_batch", "qq_update_account_batch_dev",
+    "qq_verify_account_batch", "qq_verify_account_batch_dev", "qq_delta_epsilon_batch", "qq_delta_identity_check",
+    "qq_fixed_base_batch", "qq_fixed_base_batch_dev", "qq_msm", "qq_msm_dev", "qq_msm_partial", "qq_msm_partial_dev",
+    "qq_points_sum", "qq_msm_segmented",
+]
+
+
+class QQError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "libqq_b200.so")
+
+
+_lib = None
+
+
+def load_library():
+    """Load libqq_b200.so; raises QQError if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise QQError("libqq_b200.so is not built at %s -- run __graft_entry__.build(); there is no CPU fallback" % p)
+    lib = ctypes.CDLL(p)
+    vp, sz, u8p = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p
+    lib.qq_init.argtypes = [ctypes.POINTER(vp), ctypes.c_int]
+    lib.qq_destroy.argtypes = [vp]
+    lib.qq_destroy.restype = None
+    lib.qq_last_error.argtypes = [vp]
+    lib.qq_last_error.restype = ctypes.c_char_p
+    lib.qq_device_sm_count.argtypes = [vp]
+    lib.qq_launch_count.argtypes = [vp]
+    lib.qq_launch_count.restype = ctypes.c_uint64
+    lib.qq_last_kernel_ms.argtypes = [vp]
+    lib.qq_last_kernel_ms.restype = ctypes.c_float
+    lib.qq_last_kernel_breakdown.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.c_int]
+    lib.qq_dev_alloc.argtypes = [vp, ctypes.POINTER(vp), sz]
+    lib.qq_dev_free.argtypes = [vp, vp]
+    lib.qq_dev_upload.argtypes = [vp, vp, vp, sz]
+    lib.qq_dev_download.argtypes = [vp, vp, vp, sz]
+    lib.qq_measure_imad_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    for name in ("qq_update_public_key_batch", "qq_update_public_key_batch_dev", "qq_mul_commitment_batch"):
+        getattr(lib, name).argtypes = [vp, u8p, u8p, u8p, u8p, sz]
+    lib.qq_verify_public_key_update_batch.argtypes = [vp, u8p, u8p, u8p, u8p, sz]
+    for name in ("qq_generate_commitment_batch", "qq_generate_commitment_batch_dev"):
+        getattr(lib, name).argtypes = [vp, u8p, u8p, u8p, u8p, u8p, sz]
+    lib.qq_add_commitments_batch.argtypes = [vp, u8p, u8p, ctypes.c_int, u8p, u8p, sz]
+    for name in ("qq_update_account_batch", "qq_update_account_batch_dev"):
+        getattr(lib, name).argtypes = [vp, u8p, u8p, u8p, u8p, u8p, u8p, sz]
+    for name in ("qq_verify_account_batch", "qq_verify_account_batch_dev"):
+        getattr(lib, name).argtypes = [vp, u8p, u8p, u8p, u8p, sz]
+    lib.qq_delta_epsilon_batch.argtypes = [vp, u8p, u8p, u8p, u8p, u8p, u8p, u8p, sz]
+    lib.qq_delta_identity_check.argtypes = [vp, u8p, sz, u8p]
+    for name in ("qq_fixed_base_batch", "qq_fixed_base_batch_dev"):
+        getattr(lib, name).argtypes = [vp, ctypes.c_int, u8p, u8p, u8p, sz]
+    for name in ("qq_msm", "qq_msm_dev", "qq_msm_partial", "qq_msm_partial_dev"):
+        getattr(lib, name).argtypes = [vp, u8p, u8p, sz, u8p, u8p]
+    lib.qq_points_sum.argtypes = [vp, u8p, sz, u8p, u8p]
+    lib.qq_msm_segmented.argtypes = [vp, u8p, u8p, vp, sz, u8p, u8p]
+    for name in EXPORTS:
+        f = getattr(lib, name)
+        if f.restype is ctypes.c_int and name not in ("qq_device_sm_count", "qq_last_kernel_breakdown"):
+            pass
+    _lib = lib
+    return lib
+
+
+def _u8(a, nbytes=None):
+    a = np.ascontiguousarray(a, dtype=np.uint8).reshape(-1)
+    if nbytes is not None and a.size != nbytes:
+        raise ValueError("expected %d bytes, got %d" % (nbytes, a.size))
+    return a
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+class Engine:
+    """One qq_ctx on one GPU.  Host-array methods take/return numpy uint8 arrays shaped (n, bytes)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = ctypes.c_void_p()
+        rc = self.lib.qq_init(ctypes.byref(h), int(device))
+        if rc != QQ_OK:
+            raise QQError("qq_init(device=%d) failed with %d: no usable sm_100 GPU (there is no CPU fallback)" % (device, rc))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.qq_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != QQ_OK:
+            raise QQError("%s failed (%d): %s" % (what, rc, self.lib.qq_last_error(self.h).decode()))
+
+    # ---- introspection -------------------------------------------------------------------------------------
+    @property
+    def sm_count(self):
+        return self.lib.qq_device_sm_count(self.h)
+
+    @property
+    def launch_count(self):
+        return int(self.lib.qq_launch_count(self.h))
+
+    @property
+    def last_kernel_ms(self):
+        return float(self.lib.qq_last_kernel_ms(self.h))
+
+    def last_kernel_breakdown(self):
+        buf = (ctypes.c_float * 8)()
+        k = self.lib.qq_last_kernel_breakdown(self.h, buf, 8)
+        names = ["decompress", "varbase", "fixedbase", "finish", "msm_bucket", "msm_reduce"]
+        return {names[i]: float(buf[i]) for i in range(k)}
+
+    def measure_imad_peak(self):
+        w, lo = ctypes.c_double(), ctypes.c_double()
+        self._ck(self.lib.qq_measure_imad_peak(self.h, ctypes.byref(w), ctypes.byref(lo)), "qq_measure_imad_peak")
+        return {"imad_wide_per_s": w.value, "imad_lo_per_s": lo.value}
+
+    # ---- device memory ---------------------------------------------------------------------------------------
+    def dev_alloc(self, nbytes):
+        p = ctypes.c_void_p()
+        self._ck(self.lib.qq_dev_alloc(self.h, ctypes.byref(p), nbytes), "qq_dev_alloc")
+        return p
+
+    def dev_free(self, p):
+        self._ck(self.lib.qq_dev_free(self.h, p), "qq_dev_free")
+
+    def dev_upload(self, p, arr):
+        a = _u8(arr)
+        self._ck(self.lib.qq_dev_upload(self.h, p, _ptr(a), a.size), "qq_dev_upload")
+
+    def dev_download(self, p, nbytes):
+        out = np.empty(nbytes, dtype=np.uint8)
+        self._ck(self.lib.qq_dev_download(self.h, _ptr(out), p, nbytes), "qq_dev_download")
+        return out
+
+    # ---- host-array batch calls --------------------------------------------------------------------------------
+    def update_public_key(self, pk, r):
+        pk, r = _u8(pk), _u8(r)
+        n = r.size // 32
+        _u8(pk, n * 64)
+        out, st = np.zeros(n * 64, np.uint8), np.zeros(n, np.uint8)
+        self._ck(self.lib.qq_update_public_key_batch(self.h, _ptr(pk), _ptr(r), _ptr(out), _ptr(st), n), "qq_update_public_key_batch")
+        return out.reshape(n, 64), st
+
+    def mul_commitment(self, comm, s):
+        comm, s = _u8(comm), _u8(s)
+        n = s.size // 32
+        _u8(comm, n * 64)
+        out, st = np.zeros(n * 64, np.uint8), np.zeros(n, np.uint8)
+        self._ck(self.lib.qq_mul_commitment_batch(self.h, _ptr(comm), _ptr(s), _ptr(out), _ptr(st), n), "qq_mul_commitment_batch")
+        return out.reshape(n, 64), st
+
+    def verify_public_key_update(self, upd, pk, r):
+        upd, pk, r = _u8(upd), _u8(pk), _u8(r)
+        n = r.size // 32
+        _u8(pk, n * 64), _u8(upd, n * 64)
+        st = np.zeros(n, np.uint8)
+        self._ck(self.lib.qq_verify_public_key_update_batch(self.h, _ptr(upd), _ptr(pk), _ptr(r), _ptr(st), n), "qq_verify_public_key_update_batch")
+        return st
+
+    def generate_commitment(self, pk, r, v):
+        pk, r, v = _u8(pk), _u8(r), _u8(v)
+        n = r.size // 32
+        _u8(pk, n * 64), _u8(v, n * 32)
+        out, st = np.zeros(n * 64, np.uint8), np.zeros(n, np.uint8)
+        self._ck(self.lib.qq_generate_commitment_batch(self.h, _ptr(pk), _ptr(r), _ptr(v), _ptr(out), _ptr(st), n), "qq_generate_commitment_batch")
+        return out.reshape(n, 64), st
+
+    def add_commitments(self, a, b, negate_b=False):
+        a, b = _u8(a), _u8(b)
+        n = a.size // 64
+        _u8(b, n * 64)
+        out, st = np.zeros(n * 64, np.uint8), np.zeros(n, np.uint8)
+        self._ck(self.lib.qq_add_commitments_batch(self.h, _ptr(a), _ptr(b), int(bool(negate_b)), _ptr(out), _ptr(st), n), "qq_add_commitments_batch")
+        return out.reshape(n, 64), st
+
+    def update_account(self, acc, bl, u, c):
+        acc, bl, u, c = _u8(acc), _u8(bl), _u8(u), _u8(c)
+        n = bl.size // 32
+        _u8(acc, n * 128), _u8(u, n * 32), _u8(c, n * 32)
+        out, st = np.zeros(n * 128, np.uint8), np.zeros(n, np.uint8)
+        self._ck(self.lib.qq_update_account_batch(self.h, _ptr(acc), _ptr(bl), _ptr(u), _ptr(c), _ptr(out), _ptr(st), n), "qq_update_account_batch")
+        return out.reshape(n, 128), st
+
+    def verify_account(self, acc, sk, bl):
+        acc, sk, bl = _u8(acc), _u8(sk), _u8(bl)
+        n = sk.size // 32
+        _u8(acc, n * 128), _u8(bl, n * 32)
+        st = np.zeros(n, np.uint8)
+        self._ck(self.lib.qq_verify_account_batch(self.h, _ptr(acc), _ptr(sk), _ptr(bl), _ptr(st), n), "qq_verify_account_batch")
+        return st
+
+    def delta_epsilon(self, acc, bl, r, base_pk):
+        acc, bl, r, base_pk = _u8(acc), _u8(bl), _u8(r), _u8(base_pk, 64)
+        n = bl.size // 32
+        _u8(acc, n * 128), _u8(r, n * 32)
+        d, e, st = np.zeros(n * 128, np.uint8), np.zeros(n * 128, np.uint8), np.zeros(n, np.uint8)
+        self._ck(self.lib.qq_delta_epsilon_batch(self.h, _ptr(acc), _ptr(bl), _ptr(r), _ptr(base_pk), _ptr(d), _ptr(e), _ptr(st), n), "qq_delta_epsilon_batch")
+        return d.reshape(n, 128), e.reshape(n, 128), st
+
+    def delta_identity_check(self, acc):
+        acc = _u8(acc)
+        n = acc.size // 128
+        v = np.zeros(1, np.uint8)
+        self._ck(self.lib.qq_delta_identity_check(self.h, _ptr(acc), n, _ptr(v)), "qq_delta_identity_check")
+        return int(v[0])
+
+    def fixed_base(self, which, s):
+        s = _u8(s)
+        n = s.size // 32
+        out, st = np.zeros(n * 32, np.uint8), np.zeros(n, np.uint8)
+        self._ck(self.lib.qq_fixed_base_batch(self.h, int(which), _ptr(s), _ptr(out), _ptr(st), n), "qq_fixed_base_batch")
+        return out.reshape(n, 32), st
+
+    def msm(self, scalars, points):
+        scalars, points = _u8(scalars), _u8(points)
+        n = scalars.size // 32
+        _u8(points, n * 32)
+        out, st = np.zeros(32, np.uint8), np.zeros(1, np.uint8)
+        self._ck(self.lib.qq_msm(self.h, _ptr(scalars), _ptr(points), n, _ptr(out), _ptr(st)), "qq_msm")
+        return out, int(st[0])
+
+    def msm_partial(self, scalars, points):
+        scalars, points = _u8(scalars), _u8(points)
+        n = scalars.size // 32
+        _u8(points, n * 32)
+        out, st = np.zeros(128, np.uint8), np.zeros(1, np.uint8)
+        self._ck(self.lib.qq_msm_partial(self.h, _ptr(scalars), _ptr(points), n, _ptr(out), _ptr(st)), "qq_msm_partial")
+        return out, int(st[0])
+
+    def points_sum(self, xyzt):
+        xyzt = _u8(xyzt)
+        k = xyzt.size // 128
+        out, ident = np.zeros(32, np.uint8), np.zeros(1, np.uint8)
+        self._ck(self.lib.qq_points_sum(self.h, _ptr(xyzt), k, _ptr(out), _ptr(ident)), "qq_points_sum")
+        return out, bool(ident[0])
+
+    def msm_segmented(self, scalars, points, offsets):
+        scalars, points = _u8(scalars), _u8(points)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+        m = offsets.size - 1
+        out, st = np.zeros(m * 32, np.uint8), np.zeros(m, np.uint8)
+        self._ck(self.lib.qq_msm_segmented(self.h, _ptr(scalars), _ptr(points), ctypes.c_void_p(offsets.ctypes.data), m, _ptr(out), _ptr(st)), "qq_msm_segmented")
+        return out.reshape(m, 32), st
+
+    # ---- device-pointer calls (pointers are ints / c_void_p on this engine's GPU) ---------------------------------
+    def call_dev(self, name, *args):
+        f = getattr(self.lib, name)
+        conv = [a if isinstance(a, (ctypes.c_void_p,)) or not isinstance(a, int) or a < 4096 else ctypes.c_void_p(a) for a in args]
+        self._ck(f(self.h, *conv), name)

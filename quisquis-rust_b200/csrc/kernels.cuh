@@ -1,0 +1,409 @@
+// CUDA kernels (sm_100a) for the quisquis hot path.  One thread owns one group element; every kernel is a grid-stride
+// loop so the grid can be sized to a multiple of the SM count (148 on B200).  Points travel between kernels as
+// extended coordinates, 4 x 10 limbs = 160 B, read and written with 128-bit accesses; the compressed API buffers
+// (32 B per point / scalar) are read with two 128-bit loads per thread.
+//
+// The work is bound by integer-multiply issue (IMAD.WIDE.U32 + 64-bit IADD3 pairs), not by HBM: see DESIGN.md.
+#pragma once
+#include "ristretto.cuh"
+#include "scalarmult.cuh"
+
+namespace qq {
+
+struct idx_map {  // element t -> source index (t / ppi) * pstride + off[t % ppi]
+    int ppi, pstride;
+    int off[4];
+};
+__device__ __forceinline__ size_t map_index(const idx_map& m, size_t t) {
+    size_t g = t / (size_t)m.ppi;
+    int s = (int)(t - g * (size_t)m.ppi);
+    int o = m.off[0];
+    o = s == 1 ? m.off[1] : o;
+    o = s == 2 ? m.off[2] : o;
+    o = s == 3 ? m.off[3] : o;
+    return g * (size_t)m.pstride + (size_t)o;
+}
+
+__device__ __forceinline__ void load_words32(u32 w[8], const u32x4* src, size_t i) {
+    const uint4* s = reinterpret_cast<const uint4*>(src) + 2 * i;
+    uint4 a = __ldg(s), b = __ldg(s + 1);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+}
+__device__ __forceinline__ void store_words32(u32x4* dst, size_t i, const u32 w[8]) {
+    uint4* d = reinterpret_cast<uint4*>(dst) + 2 * i;
+    d[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    d[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+// ---- decompress: compressed points (mapped) -> extended points + validity flags -------------------------------
+__global__ void __launch_bounds__(256) k_decompress(const u32x4* __restrict__ in, idx_map map, u32x4* __restrict__ pts,
+                                                    uint8_t* __restrict__ ok, size_t n) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+        u32 w[8];
+        load_words32(w, in, map_index(map, t));
+        ge_p3 p;
+        u32 v = ristretto_decompress(p, w);
+        ge_p3_store(pts + 10 * t, p);
+        ok[t] = (uint8_t)v;
+    }
+}
+
+// ---- variable-base scalar multiplication ------------------------------------------------------------------------
+// item t: point pts[map(t)], scalars s0[t / sdiv] (and s1[t / sdiv] when NS == 2); out0[t] = s0 * P, out1[t] = s1 * P.
+// The per-thread window table lives in `scratch` (gridDim.x * blockDim.x * 90 x 16 B), so it stays L2-resident
+// while the grid-stride loop walks the batch.
+struct vb_args {
+    const u32x4* pts;
+    idx_map map;
+    const u32x4* s0;
+    const u32x4* s1;
+    int sdiv;
+    u32x4* out0;
+    u32x4* out1;
+    u32x4* scratch;
+    size_t n;
+};
+template <int NS>
+__global__ void __launch_bounds__(128) k_varbase(vb_args a) {
+    size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    u32x4* tbl = a.scratch + gtid * (QQ_VB_ENTRIES * 10);
+    for (size_t t = gtid; t < a.n; t += stride) {
+        ge_p3 p, r;
+        ge_p3_load(p, a.pts + 10 * map_index(a.map, t));
+        vb_build_table(tbl, p);
+        u32 s[8];
+        load_words32(s, a.s0, t / (size_t)a.sdiv);
+        vb_scalarmult(r, tbl, s);
+        ge_p3_store(a.out0 + 10 * t, r);
+        if (NS == 2) {
+            load_words32(s, a.s1, t / (size_t)a.sdiv);
+            vb_scalarmult(r, tbl, s);
+            ge_p3_store(a.out1 + 10 * t, r);
+        }
+    }
+}
+
+// ---- fixed-base scalar multiplication: table staged in shared memory ---------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(512) k_fixedbase(const u32* __restrict__ tbl_g, const u32x4* __restrict__ s,
+                                                   u32x4* __restrict__ out, size_t n) {
+    extern __shared__ __align__(16) u32 tbl_s[];
+    const int words = ((256 + W - 1) / W) * ((1 << (W - 1)) + 1) * QQ_NIELS_WORDS;
+    {
+        const uint4* g = reinterpret_cast<const uint4*>(tbl_g);
+        uint4* d = reinterpret_cast<uint4*>(tbl_s);
+        for (int i = threadIdx.x; i < words / 4; i += blockDim.x) d[i] = __ldg(g + i);
+        for (int i = (words / 4) * 4 + threadIdx.x; i < words; i += blockDim.x) tbl_s[i] = tbl_g[i];
+    }
+    __syncthreads();
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+        u32 w[8];
+        load_words32(w, s, t);
+        ge_p3 r;
+        fb_scalarmult<W>(r, tbl_s, w);
+        ge_p3_store(out + 10 * t, r);
+    }
+}
+
+// one thread per table entry (k, j): tbl[(k * ENT + j) * 30 ..] = (j << (W k)) * base
+__global__ void k_fb_build(u32* tbl, const u32x4* base_compressed, int W, int nw, int ent) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nw * ent) return;
+    u32 w[8];
+    load_words32(w, base_compressed, 0);
+    ge_p3 b;
+    ristretto_decompress(b, w);
+    fb_build_entry(tbl + (size_t)t * QQ_NIELS_WORDS, b, W, t / ent, t % ent);
+}
+
+// ---- finish kernels: combine + compress -------------------------------------------------------------------------
+// A finish job produces one compressed point per item t:  enc( sum of up to 3 extended points ).
+// Source k of output t is  src[k].base + 10 * map(src[k].map, t)  (null base = absent), optionally negated.
+struct fin_src {
+    const u32x4* base;
+    idx_map map;
+    int negate;
+};
+struct fin_args {
+    fin_src src[3];
+    u32x4* out;        // compressed outputs
+    idx_map omap;      // where output t is written (index into `out`, in 32-byte units)
+    const uint8_t* bad;  // per-item status (indexed by t): non-zero -> write zeros instead
+    size_t n;
+};
+__device__ __forceinline__ void fin_eval(ge_p3& q, const fin_args& a, size_t t) {
+    ge_p3_load(q, a.src[0].base + 10 * map_index(a.src[0].map, t));
+    if (a.src[0].negate) ge_neg(q, q);
+#pragma unroll 1
+    for (int k = 1; k < 3; k++) {
+        if (a.src[k].base == nullptr) break;
+        ge_p3 p;
+        ge_p3_load(p, a.src[k].base + 10 * map_index(a.src[k].map, t));
+        if (a.src[k].negate) ge_neg(p, p);
+        ge_cached c;
+        ge_to_cached(c, p);
+        ge_add(q, q, c);
+    }
+}
+__global__ void __launch_bounds__(256) k_finish_compress(fin_args a) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < a.n; t += stride) {
+        ge_p3 q;
+        fin_eval(q, a, t);
+        u32 w[8];
+        ristretto_compress(w, q);
+        if (a.bad != nullptr && a.bad[t] != 0) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) w[i] = 0;
+        }
+        store_words32(a.out, map_index(a.omap, t), w);
+    }
+}
+// compare enc(sum) against expected compressed bytes: flag[t] = 1 if equal
+__global__ void __launch_bounds__(256) k_finish_compare(fin_args a, const u32x4* __restrict__ expect, idx_map emap,
+                                                        uint8_t* __restrict__ flag) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < a.n; t += stride) {
+        ge_p3 q;
+        fin_eval(q, a, t);
+        u32 w[8], e[8];
+        ristretto_compress(w, q);
+        load_words32(e, expect, map_index(emap, t));
+        u32 d = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) d |= w[i] ^ e[i];
+        flag[t] = d == 0 ? 1 : 0;
+    }
+}
+// projective Ristretto equality of two extended points: flag[t] = 1 if equal
+__global__ void __launch_bounds__(256) k_points_equal(const u32x4* __restrict__ a, const u32x4* __restrict__ b,
+                                                      uint8_t* __restrict__ flag, size_t n) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+        ge_p3 p, q;
+        ge_p3_load(p, a + 10 * t);
+        ge_p3_load(q, b + 10 * t);
+        flag[t] = (uint8_t)ge_ristretto_eq(p, q);
+    }
+}
+
+// ---- status assembly ---------------------------------------------------------------------------------------------
+// status[i] = BAD_SCALAR if any of the (up to 3) scalar arrays holds a non-canonical scalar at i,
+//             else BAD_POINT if any of the `npts` validity flags ok[i * npts + j] is 0, else 0.
+struct st_args {
+    const u32x4* sc[3];
+    const uint8_t* ok;
+    int npts;
+    uint8_t* status;
+    size_t n;
+};
+__global__ void k_status(st_args a) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+        uint8_t st = 0;
+        for (int j = 0; j < a.npts; j++)
+            if (!a.ok[i * a.npts + j]) st = 1;
+        for (int k = 0; k < 3; k++) {
+            if (a.sc[k] == nullptr) continue;
+            u32 w[8];
+            load_words32(w, a.sc[k], i);
+            if (!sc_is_canonical(w)) st = 2;
+        }
+        a.status[i] = st;
+    }
+}
+// verify_account verdict (reference order: keypair check, then commitment; src/accounts/accounts.rs:81-84):
+// pre = status from k_status over (sk, bl) and ok flags [gr, c]; eqflag[i] = keypair equal, eqflag[n + i] = commitment equal.
+__global__ void k_verify_account_status(const uint8_t* pre_scalar, const uint8_t* ok2, const uint8_t* eqflag,
+                                        uint8_t* status, size_t n) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint8_t st = 0;
+        if (pre_scalar[i] == 2) st = 2;
+        else if (!ok2[2 * i]) st = 1;
+        else if (!eqflag[i]) st = 3;
+        else if (!ok2[2 * i + 1]) st = 1;
+        else if (!eqflag[n + i]) st = 4;
+        status[i] = st;
+    }
+}
+// pairs of flags -> status: pre[i] != 0 wins, else (f[2i] & f[2i+1]) ? 0 : fail_code
+__global__ void k_pair_status(const uint8_t* pre, const uint8_t* f, uint8_t fail_code, uint8_t* status, size_t n) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        status[i] = pre[i] ? pre[i] : ((f[2 * i] && f[2 * i + 1]) ? 0 : fail_code);
+}
+__global__ void k_or_status(uint8_t* dst, const uint8_t* a, const uint8_t* b, size_t n) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint8_t x = a[i], y = b[i];
+        dst[i] = (x == 2 || y == 2) ? 2 : ((x | y) ? (x ? x : y) : 0);
+    }
+}
+
+// delta / epsilon pk halves (reference src/accounts/accounts.rs:210,215): delta_i.pk = acc_i.pk, epsilon_i.pk = base_pk
+struct pk_bytes {
+    uint4 q[4];
+};
+__global__ void k_copy_pk(const u32x4* __restrict__ acc, u32x4* __restrict__ delta, u32x4* __restrict__ eps,
+                          pk_bytes base, const uint8_t* __restrict__ status, size_t n) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint4* a = reinterpret_cast<const uint4*>(acc) + 8 * i;
+        uint4* d = reinterpret_cast<uint4*>(delta) + 8 * i;
+        uint4* e = reinterpret_cast<uint4*>(eps) + 8 * i;
+        bool bad = status[i] != 0;
+        uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            d[k] = bad ? z : __ldg(a + k);
+            e[k] = bad ? z : base.q[k];
+        }
+    }
+}
+// first failing term of an MSM (the reference stops at the first None / the oracle at the first bad term):
+// key = index * 4 + code, minimum wins
+__global__ void k_first_bad(const uint8_t* __restrict__ term_status, size_t n, unsigned long long* key) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    unsigned long long best = ~0ull;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint8_t s = term_status[i];
+        if (s) {
+            unsigned long long k = (unsigned long long)i * 4 + s;
+            best = k < best ? k : best;
+        }
+    }
+    if (best != ~0ull) atomicMin(key, best);
+}
+__global__ void k_key_to_status(const unsigned long long* key, uint8_t* status) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *status = (*key == ~0ull) ? 0 : (uint8_t)(*key & 3);
+}
+
+// ---- point-sum reduction -------------------------------------------------------------------------------------------
+// out[b] = sum over a strided slice of in[0..n) (block b handles elements b, b + gridDim, ...; threads stride inside)
+// followed by a shared-memory tree over the block.  Used for the identity check and for MSM fallbacks.
+__global__ void __launch_bounds__(128) k_point_sum(const u32x4* __restrict__ in, idx_map map, size_t n,
+                                                   u32x4* __restrict__ out) {
+    __shared__ u32x4 sm[128 * 10];
+    ge_p3 acc;
+    ge_identity(acc);
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+        ge_p3 p;
+        ge_p3_load(p, in + 10 * map_index(map, t));
+        ge_cached c;
+        ge_to_cached(c, p);
+        ge_add(acc, acc, c);
+    }
+    ge_p3_store(sm + 10 * threadIdx.x, acc);
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            ge_p3 p;
+            ge_p3_load(p, sm + 10 * (threadIdx.x + s));
+            ge_cached c;
+            ge_to_cached(c, p);
+            ge_add(acc, acc, c);
+            ge_p3_store(sm + 10 * threadIdx.x, acc);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ge_p3_store(out + 10 * blockIdx.x, acc);
+}
+// single thread: out_xyzt (4 x 32 canonical bytes), out compressed, identity flag, from one extended point
+__global__ void k_point_export(const u32x4* in, u32x4* xyzt, u32x4* compressed, uint8_t* is_identity) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    ge_p3 p;
+    ge_p3_load(p, in);
+    u32 w[8];
+    if (xyzt != nullptr) {
+        fe_towords(w, p.X); store_words32(xyzt, 0, w);
+        fe_towords(w, p.Y); store_words32(xyzt, 1, w);
+        fe_towords(w, p.Z); store_words32(xyzt, 2, w);
+        fe_towords(w, p.T); store_words32(xyzt, 3, w);
+    }
+    if (compressed != nullptr) {
+        ristretto_compress(w, p);
+        store_words32(compressed, 0, w);
+    }
+    if (is_identity != nullptr) *is_identity = (uint8_t)ge_ristretto_is_identity(p);
+}
+// k points given as canonical X,Y,Z,T bytes -> extended limbs
+__global__ void k_point_import(const u32x4* xyzt, u32x4* pts, size_t k) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= k) return;
+    ge_p3 p;
+    u32 w[8];
+    load_words32(w, xyzt, 4 * t + 0); fe_fromwords(p.X, w);
+    load_words32(w, xyzt, 4 * t + 1); fe_fromwords(p.Y, w);
+    load_words32(w, xyzt, 4 * t + 2); fe_fromwords(p.Z, w);
+    load_words32(w, xyzt, 4 * t + 3); fe_fromwords(p.T, w);
+    ge_p3_store(pts + 10 * t, p);
+}
+// segmented sum: instance j = sum of terms offsets[j]..offsets[j+1]-1, compressed; bad if any term flag set
+__global__ void __launch_bounds__(256) k_segment_sum_compress(const u32x4* __restrict__ terms,
+                                                              const uint32_t* __restrict__ offsets,
+                                                              const uint8_t* __restrict__ term_status,
+                                                              u32x4* __restrict__ out, uint8_t* __restrict__ status,
+                                                              size_t m) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {
+        ge_p3 acc;
+        ge_identity(acc);
+        uint8_t st = 0;
+        for (uint32_t t = offsets[j]; t < offsets[j + 1]; t++) {
+            ge_p3 p;
+            ge_p3_load(p, terms + 10 * (size_t)t);
+            ge_cached c;
+            ge_to_cached(c, p);
+            ge_add(acc, acc, c);
+            uint8_t s = term_status[t];
+            st = (s == 2 || st == 2) ? 2 : (st | s);
+        }
+        u32 w[8];
+        ristretto_compress(w, acc);
+        if (st) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) w[i] = 0;
+        }
+        store_words32(out, j, w);
+        status[j] = st;
+    }
+}
+
+// ---- integer-pipe peak micro-benchmark (roofline denominator) ------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) k_imad_peak(u32* out, u32 seed, int outer) {
+    __shared__ u32 sm[1024];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) sm[i] = i * 2654435761u + seed;
+    __syncthreads();
+    u32 b[4], c[8];
+    u64 w[8];
+    for (int j = 0; j < 4; j++) b[j] = seed * 2654435761u + j * 40503u + threadIdx.x;
+    for (int i = 0; i < 8; i++) { c[i] = i + seed; w[i] = ((u64)c[i] << 32) | b[i & 3]; }
+    for (int o = 0; o < outer; o++) {
+#pragma unroll
+        for (int k = 0; k < 32; k++) {
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                u32 x = sm[(threadIdx.x + (o * 32 + k) * 2 + i) & 1023];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    int q = i * 4 + j;
+                    if (MODE == 0) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c[q]) : "r"(x), "r"(b[j]));
+                    if (MODE == 1) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[q]) : "r"(x), "r"(b[j]));
+                }
+            }
+        }
+    }
+    u32 acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc ^= c[i] ^ (u32)w[i] ^ (u32)(w[i] >> 32);
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+}  // namespace qq

@@ -1,0 +1,811 @@
+// libqq_b200.so -- host side of the C ABI declared in include/qq_b200.h.
+// Owns the device workspace, the fixed-base tables and the stream; sequences the kernels of kernels.cuh / msm.cuh.
+// No CPU fallback: every entry point fails with QQ_ERR_NODEVICE / QQ_ERR_CUDA when the GPU path is unavailable.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/qq_b200.h"
+#include "kernels.cuh"
+#include "msm.cuh"
+
+using namespace qq;
+
+#define QQ_FB_W 6  // window width of the shared-memory fixed-base tables (43 windows x 33 entries x 120 B = 166 KB)
+enum { FAM_DEC = 0, FAM_VB = 1, FAM_FB = 2, FAM_FIN = 3, FAM_MSM_BUCKET = 4, FAM_MSM_REDUCE = 5, FAM_COUNT = 6 };
+
+struct qq_ctx {
+    int device = 0;
+    int sms = 0;
+    cudaStream_t stream = nullptr;
+    char* ws = nullptr;
+    size_t ws_cap = 0, ws_off = 0;
+    u32* fb_tbl[2] = {nullptr, nullptr};
+    uint8_t base_pk[64];
+    uint64_t launches = 0;
+    float last_ms = 0.f;
+    float breakdown[FAM_COUNT] = {0};
+    std::string err;
+    std::vector<cudaEvent_t> ev_pool;
+    struct span { int fam; int e0, e1; };
+    std::vector<span> spans;
+    int ev_used = 0;
+    int vb_blocks_per_sm[3] = {0, 0, 0};
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                         \
+            return e_ == cudaErrorMemoryAllocation ? QQ_ERR_NOMEM : QQ_ERR_CUDA;                   \
+        }                                                                                          \
+    } while (0)
+#define CKQ(call)                 \
+    do {                          \
+        int r_ = (call);          \
+        if (r_ != QQ_OK) return r_; \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- workspace: one growable slab, bump-allocated per call -----------------------------------------------------
+static int ws_begin(qq_ctx* ctx, size_t bytes) {
+    bytes = align_up(bytes, 256) + 4096;
+    if (bytes > ctx->ws_cap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->ws) CK(cudaFree(ctx->ws));
+        ctx->ws = nullptr;
+        ctx->ws_cap = 0;
+        size_t want = bytes + bytes / 8;
+        CK(cudaMalloc((void**)&ctx->ws, want));
+        ctx->ws_cap = want;
+    }
+    ctx->ws_off = 0;
+    return QQ_OK;
+}
+template <class T>
+static T* ws_take(qq_ctx* ctx, size_t bytes) {
+    size_t off = align_up(ctx->ws_off, 256);
+    ctx->ws_off = off + bytes;
+    return reinterpret_cast<T*>(ctx->ws + off);
+}
+static size_t ws_need(std::initializer_list<size_t> parts) {
+    size_t t = 0;
+    for (size_t p : parts) t += align_up(p, 256) + 256;
+    return t;
+}
+
+// ---- timing spans ------------------------------------------------------------------------------------------------
+static int ev_get(qq_ctx* ctx) {
+    if (ctx->ev_used == (int)ctx->ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        ctx->ev_pool.push_back(e);
+    }
+    return ctx->ev_used++;
+}
+static void span_begin(qq_ctx* ctx, int fam) {
+    qq_ctx::span s;
+    s.fam = fam;
+    s.e0 = ev_get(ctx);
+    s.e1 = -1;
+    cudaEventRecord(ctx->ev_pool[s.e0], ctx->stream);
+    ctx->spans.push_back(s);
+}
+static void span_end(qq_ctx* ctx) {
+    qq_ctx::span& s = ctx->spans.back();
+    s.e1 = ev_get(ctx);
+    cudaEventRecord(ctx->ev_pool[s.e1], ctx->stream);
+}
+static void call_begin(qq_ctx* ctx) {
+    ctx->spans.clear();
+    ctx->ev_used = 0;
+}
+static int call_end(qq_ctx* ctx) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    for (int i = 0; i < FAM_COUNT; i++) ctx->breakdown[i] = 0.f;
+    ctx->last_ms = 0.f;
+    for (auto& s : ctx->spans) {
+        float ms = 0.f;
+        if (s.e1 >= 0) cudaEventElapsedTime(&ms, ctx->ev_pool[s.e0], ctx->ev_pool[s.e1]);
+        ctx->breakdown[s.fam] += ms;
+        ctx->last_ms += ms;
+    }
+    return QQ_OK;
+}
+
+static inline int grid_for(size_t n, int block, int cap) {
+    size_t g = (n + block - 1) / block;
+    if (g > (size_t)cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+static idx_map imap(int ppi, int pstride, int o0 = 0, int o1 = 1, int o2 = 2, int o3 = 3) {
+    idx_map m;
+    m.ppi = ppi;
+    m.pstride = pstride;
+    m.off[0] = o0; m.off[1] = o1; m.off[2] = o2; m.off[3] = o3;
+    return m;
+}
+static const idx_map IDENT = {1, 1, {0, 0, 0, 0}};
+
+// ---- kernel launch helpers --------------------------------------------------------------------------------------
+static int launch_decompress(qq_ctx* ctx, const void* in, idx_map map, u32x4* pts, uint8_t* ok, size_t n) {
+    if (n == 0) return QQ_OK;
+    span_begin(ctx, FAM_DEC);
+    k_decompress<<<grid_for(n, 256, ctx->sms * 64), 256, 0, ctx->stream>>>((const u32x4*)in, map, pts, ok, n);
+    span_end(ctx);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return QQ_OK;
+}
+static size_t vb_scratch_bytes(qq_ctx* ctx, int ns) {
+    return (size_t)ctx->sms * ctx->vb_blocks_per_sm[ns] * 128 * QQ_VB_TABLE_WORDS * 4;
+}
+static int launch_varbase(qq_ctx* ctx, int ns, const u32x4* pts, idx_map map, const void* s0, const void* s1, int sdiv,
+                          u32x4* out0, u32x4* out1, u32x4* scratch, size_t n) {
+    if (n == 0) return QQ_OK;
+    vb_args a;
+    a.pts = pts; a.map = map; a.s0 = (const u32x4*)s0; a.s1 = (const u32x4*)s1; a.sdiv = sdiv;
+    a.out0 = out0; a.out1 = out1; a.scratch = scratch; a.n = n;
+    int grid = ctx->sms * ctx->vb_blocks_per_sm[ns];
+    span_begin(ctx, FAM_VB);
+    if (ns == 1) k_varbase<1><<<grid, 128, 0, ctx->stream>>>(a);
+    else k_varbase<2><<<grid, 128, 0, ctx->stream>>>(a);
+    span_end(ctx);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return QQ_OK;
+}
+static size_t fb_table_words() { return (size_t)fb_num_windows(QQ_FB_W) * fb_entries(QQ_FB_W) * QQ_NIELS_WORDS; }
+static int launch_fixedbase(qq_ctx* ctx, int which, const void* s, u32x4* out, size_t n) {
+    if (n == 0) return QQ_OK;
+    size_t smem = fb_table_words() * 4;
+    int grid = (int)((n + 511) / 512);
+    if (grid > ctx->sms) grid = ctx->sms;
+    span_begin(ctx, FAM_FB);
+    k_fixedbase<QQ_FB_W><<<grid, 512, smem, ctx->stream>>>(ctx->fb_tbl[which], (const u32x4*)s, out, n);
+    span_end(ctx);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return QQ_OK;
+}
+static fin_src fsrc(const u32x4* base, idx_map map, int negate = 0) {
+    fin_src s;
+    s.base = base; s.map = map; s.negate = negate;
+    return s;
+}
+static const fin_src FNONE = {nullptr, {1, 1, {0, 0, 0, 0}}, 0};
+static int launch_finish(qq_ctx* ctx, fin_src a, fin_src b, fin_src c, void* out, idx_map omap, const uint8_t* bad,
+                         size_t n) {
+    if (n == 0) return QQ_OK;
+    fin_args f;
+    f.src[0] = a; f.src[1] = b; f.src[2] = c;
+    f.out = (u32x4*)out; f.omap = omap; f.bad = bad; f.n = n;
+    span_begin(ctx, FAM_FIN);
+    k_finish_compress<<<grid_for(n, 256, ctx->sms * 64), 256, 0, ctx->stream>>>(f);
+    span_end(ctx);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return QQ_OK;
+}
+static int launch_compare(qq_ctx* ctx, fin_src a, fin_src b, const void* expect, idx_map emap, uint8_t* flag, size_t n) {
+    if (n == 0) return QQ_OK;
+    fin_args f;
+    f.src[0] = a; f.src[1] = b; f.src[2] = FNONE;
+    f.out = nullptr; f.omap = IDENT; f.bad = nullptr; f.n = n;
+    span_begin(ctx, FAM_FIN);
+    k_finish_compare<<<grid_for(n, 256, ctx->sms * 64), 256, 0, ctx->stream>>>(f, (const u32x4*)expect, emap, flag);
+    span_end(ctx);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return QQ_OK;
+}
+static int launch_status(qq_ctx* ctx, const void* s0, const void* s1, const void* s2, const uint8_t* ok, int npts,
+                         uint8_t* status, size_t n) {
+    if (n == 0) return QQ_OK;
+    st_args a;
+    a.sc[0] = (const u32x4*)s0; a.sc[1] = (const u32x4*)s1; a.sc[2] = (const u32x4*)s2;
+    a.ok = ok; a.npts = npts; a.status = status; a.n = n;
+    k_status<<<grid_for(n, 256, ctx->sms * 16), 256, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return QQ_OK;
+}
+// sum of n extended points (mapped) -> one extended point at `result` (device, 160 B)
+static int launch_point_sum(qq_ctx* ctx, const u32x4* pts, idx_map map, size_t n, u32x4* partials /*>= sms*2*10*/,
+                            u32x4* result) {
+    int blocks = grid_for(n, 128, ctx->sms * 2);
+    span_begin(ctx, FAM_MSM_REDUCE);
+    k_point_sum<<<blocks, 128, 0, ctx->stream>>>(pts, map, n, partials);
+    k_point_sum<<<1, 128, 0, ctx->stream>>>(partials, IDENT, (size_t)blocks, result);
+    span_end(ctx);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    return QQ_OK;
+}
+
+// =================================================================================================================
+// context
+// =================================================================================================================
+extern "C" int qq_init(qq_ctx** out, int device) {
+    if (!out) return QQ_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return QQ_ERR_NODEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return QQ_ERR_NODEVICE;
+    if (prop.major != 10) {
+        fprintf(stderr, "qq_b200: device %d is sm_%d%d; this library contains sm_100a code only\n", device, prop.major,
+                prop.minor);
+        return QQ_ERR_NODEVICE;
+    }
+    qq_ctx* ctx = new qq_ctx();
+    ctx->device = device;
+    ctx->sms = prop.multiProcessorCount;
+    auto fail = [&](int code) {
+        fprintf(stderr, "qq_b200: init failed: %s\n", ctx->err.c_str());
+        delete ctx;
+        return code;
+    };
+    auto body = [&]() -> int {
+        CK(cudaSetDevice(device));
+        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        CK(cudaFuncSetAttribute(k_fixedbase<QQ_FB_W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(fb_table_words() * 4)));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_varbase<1>, 128, 0));
+        ctx->vb_blocks_per_sm[1] = occ > 0 ? occ : 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_varbase<2>, 128, 0));
+        ctx->vb_blocks_per_sm[2] = occ > 0 ? occ : 1;
+        // fixed-base tables for B and H, built on the device from their compressed encodings
+        static const uint8_t BASE_PK[64] = {
+            0xe2, 0xf2, 0xae, 0x0a, 0x6a, 0xbc, 0x4e, 0x71, 0xa8, 0x84, 0xa9, 0x61, 0xc5, 0x00, 0x51, 0x5f,
+            0x58, 0xe3, 0x0b, 0x6a, 0xa5, 0x82, 0xdd, 0x8d, 0xb6, 0xa6, 0x59, 0x45, 0xe0, 0x8d, 0x2d, 0x76,
+            0x8c, 0x92, 0x40, 0xb4, 0x56, 0xa9, 0xe6, 0xdc, 0x65, 0xc3, 0x77, 0xa1, 0x04, 0x8d, 0x74, 0x5f,
+            0x94, 0xa0, 0x8c, 0xdb, 0x7f, 0x44, 0xcb, 0xcd, 0x7b, 0x46, 0xf3, 0x40, 0x48, 0x87, 0x11, 0x34};
+        memcpy(ctx->base_pk, BASE_PK, 64);
+        u32x4* dbase = nullptr;
+        CK(cudaMalloc((void**)&dbase, 64));
+        CK(cudaMemcpy(dbase, BASE_PK, 64, cudaMemcpyHostToDevice));
+        int nw = fb_num_windows(QQ_FB_W), ent = fb_entries(QQ_FB_W);
+        for (int b = 0; b < 2; b++) {
+            CK(cudaMalloc((void**)&ctx->fb_tbl[b], align_up(fb_table_words() * 4, 256)));
+            k_fb_build<<<(nw * ent + 63) / 64, 64, 0, ctx->stream>>>(ctx->fb_tbl[b], dbase + 2 * b, QQ_FB_W, nw, ent);
+            ctx->launches++;
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaGetLastError());
+        CK(cudaFree(dbase));
+        return QQ_OK;
+    };
+    int r = body();
+    if (r != QQ_OK) return fail(r);
+    *out = ctx;
+    return QQ_OK;
+}
+
+extern "C" void qq_destroy(qq_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->ws) cudaFree(ctx->ws);
+    for (int b = 0; b < 2; b++)
+        if (ctx->fb_tbl[b]) cudaFree(ctx->fb_tbl[b]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+extern "C" const char* qq_last_error(const qq_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+extern "C" int qq_device_sm_count(const qq_ctx* ctx) { return ctx ? ctx->sms : 0; }
+extern "C" uint64_t qq_launch_count(const qq_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" float qq_last_kernel_ms(const qq_ctx* ctx) { return ctx ? ctx->last_ms : 0.f; }
+extern "C" int qq_last_kernel_breakdown(const qq_ctx* ctx, float* ms, int cap) {
+    if (!ctx || !ms) return 0;
+    int k = cap < FAM_COUNT ? cap : FAM_COUNT;
+    for (int i = 0; i < k; i++) ms[i] = ctx->breakdown[i];
+    return k;
+}
+extern "C" int qq_dev_alloc(qq_ctx* ctx, void** dptr, size_t bytes) {
+    if (!ctx || !dptr) return QQ_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMalloc(dptr, bytes ? bytes : 16));
+    return QQ_OK;
+}
+extern "C" int qq_dev_free(qq_ctx* ctx, void* dptr) {
+    if (!ctx) return QQ_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaFree(dptr));
+    return QQ_OK;
+}
+extern "C" int qq_dev_upload(qq_ctx* ctx, void* dptr, const void* host, size_t bytes) {
+    if (!ctx) return QQ_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(dptr, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return QQ_OK;
+}
+extern "C" int qq_dev_download(qq_ctx* ctx, void* host, const void* dptr, size_t bytes) {
+    if (!ctx) return QQ_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return QQ_OK;
+}
+extern "C" int qq_measure_imad_peak(qq_ctx* ctx, double* wide_ops_per_s, double* lo_ops_per_s) {
+    if (!ctx) return QQ_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int grid = ctx->sms * 4, outer = 4000;
+    u32* out = nullptr;
+    CK(cudaMalloc((void**)&out, (size_t)grid * 256 * 4));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    double ops = (double)grid * 256 * (double)outer * 32 * 8;
+    double best[2] = {0, 0};
+    for (int mode = 0; mode < 2; mode++) {
+        for (int rep = 0; rep < 4; rep++) {
+            CK(cudaEventRecord(e0, ctx->stream));
+            if (mode == 0) k_imad_peak<0><<<grid, 256, 0, ctx->stream>>>(out, 1234u + rep, outer);
+            else k_imad_peak<1><<<grid, 256, 0, ctx->stream>>>(out, 1234u + rep, outer);
+            CK(cudaEventRecord(e1, ctx->stream));
+            CK(cudaEventSynchronize(e1));
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            double r = ops / (ms * 1e-3);
+            if (rep > 0 && r > best[mode]) best[mode] = r;
+            ctx->launches++;
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CK(cudaFree(out));
+    if (lo_ops_per_s) *lo_ops_per_s = best[0];
+    if (wide_ops_per_s) *wide_ops_per_s = best[1];
+    return QQ_OK;
+}
+
+// =================================================================================================================
+// device-pointer cores.  Each processes [0, n) in chunks so the workspace stays bounded.
+// =================================================================================================================
+#define QQ_CHUNK ((size_t)1 << 20)
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+#define REQUIRE(c) \
+    do {           \
+        if (!(c)) { ctx->err = "bad argument: " #c; return QQ_ERR_ARG; } \
+    } while (0)
+
+// out = s * (both points of each 64-byte pair)      [update_public_key, Mul for ElGamalCommitment]
+static int core_scale_pairs(qq_ctx* ctx, const uint8_t* pk, const uint8_t* s, uint8_t* out, uint8_t* status, size_t n) {
+    for (size_t base = 0; base < n; base += QQ_CHUNK) {
+        size_t m = n - base < QQ_CHUNK ? n - base : QQ_CHUNK;
+        CKQ(ws_begin(ctx, ws_need({2 * m * 160, 2 * m * 160, 2 * m, vb_scratch_bytes(ctx, 1)})));
+        u32x4* P = ws_take<u32x4>(ctx, 2 * m * 160);
+        u32x4* R = ws_take<u32x4>(ctx, 2 * m * 160);
+        uint8_t* ok = ws_take<uint8_t>(ctx, 2 * m);
+        u32x4* scratch = ws_take<u32x4>(ctx, vb_scratch_bytes(ctx, 1));
+        const uint8_t* pk_c = pk + base * 64;
+        const uint8_t* s_c = s + base * 32;
+        CKQ(launch_decompress(ctx, pk_c, IDENT, P, ok, 2 * m));
+        CKQ(launch_status(ctx, s_c, nullptr, nullptr, ok, 2, status + base, m));
+        CKQ(launch_varbase(ctx, 1, P, IDENT, s_c, nullptr, 2, R, nullptr, scratch, 2 * m));
+        for (int j = 0; j < 2; j++)
+            CKQ(launch_finish(ctx, fsrc(R, imap(1, 2, j)), FNONE, FNONE, out + base * 64, imap(1, 2, j), status + base, m));
+    }
+    return QQ_OK;
+}
+
+static int core_generate_commitment(qq_ctx* ctx, const uint8_t* pk, const uint8_t* r, const uint8_t* v, uint8_t* out,
+                                    uint8_t* status, size_t n) {
+    for (size_t base = 0; base < n; base += QQ_CHUNK) {
+        size_t m = n - base < QQ_CHUNK ? n - base : QQ_CHUNK;
+        CKQ(ws_begin(ctx, ws_need({2 * m * 160, 2 * m * 160, m * 160, 2 * m, vb_scratch_bytes(ctx, 1)})));
+        u32x4* P = ws_take<u32x4>(ctx, 2 * m * 160);
+        u32x4* R = ws_take<u32x4>(ctx, 2 * m * 160);
+        u32x4* F = ws_take<u32x4>(ctx, m * 160);
+        uint8_t* ok = ws_take<uint8_t>(ctx, 2 * m);
+        u32x4* scratch = ws_take<u32x4>(ctx, vb_scratch_bytes(ctx, 1));
+        const uint8_t* pk_c = pk + base * 64;
+        const uint8_t* r_c = r + base * 32;
+        const uint8_t* v_c = v + base * 32;
+        CKQ(launch_decompress(ctx, pk_c, IDENT, P, ok, 2 * m));
+        CKQ(launch_status(ctx, r_c, v_c, nullptr, ok, 2, status + base, m));
+        CKQ(launch_varbase(ctx, 1, P, IDENT, r_c, nullptr, 2, R, nullptr, scratch, 2 * m));
+        CKQ(launch_fixedbase(ctx, QQ_BASE_B, v_c, F, m));
+        CKQ(launch_finish(ctx, fsrc(R, imap(1, 2, 0)), FNONE, FNONE, out + base * 64, imap(1, 2, 0), status + base, m));
+        CKQ(launch_finish(ctx, fsrc(R, imap(1, 2, 1)), fsrc(F, IDENT), FNONE, out + base * 64, imap(1, 2, 1),
+                          status + base, m));
+    }
+    return QQ_OK;
+}
+
+static int core_add_commitments(qq_ctx* ctx, const uint8_t* a, const uint8_t* b, int negate_b, uint8_t* out,
+                                uint8_t* status, size_t n) {
+    for (size_t base = 0; base < n; base += QQ_CHUNK) {
+        size_t m = n - base < QQ_CHUNK ? n - base : QQ_CHUNK;
+        CKQ(ws_begin(ctx, ws_need({2 * m * 160, 2 * m * 160, 2 * m, 2 * m, m, m})));
+        u32x4* A = ws_take<u32x4>(ctx, 2 * m * 160);
+        u32x4* B = ws_take<u32x4>(ctx, 2 * m * 160);
+        uint8_t* oka = ws_take<uint8_t>(ctx, 2 * m);
+        uint8_t* okb = ws_take<uint8_t>(ctx, 2 * m);
+        uint8_t* sa = ws_take<uint8_t>(ctx, m);
+        uint8_t* sb = ws_take<uint8_t>(ctx, m);
+        CKQ(launch_decompress(ctx, a + base * 64, IDENT, A, oka, 2 * m));
+        CKQ(launch_decompress(ctx, b + base * 64, IDENT, B, okb, 2 * m));
+        CKQ(launch_status(ctx, nullptr, nullptr, nullptr, oka, 2, sa, m));
+        CKQ(launch_status(ctx, nullptr, nullptr, nullptr, okb, 2, sb, m));
+        k_or_status<<<grid_for(m, 256, ctx->sms * 16), 256, 0, ctx->stream>>>(status + base, sa, sb, m);
+        ctx->launches++;
+        for (int j = 0; j < 2; j++)
+            CKQ(launch_finish(ctx, fsrc(A, imap(1, 2, j)), fsrc(B, imap(1, 2, j), negate_b), FNONE, out + base * 64,
+                              imap(1, 2, j), status + base, m));
+    }
+    return QQ_OK;
+}
+
+static int core_update_account(qq_ctx* ctx, const uint8_t* acc, const uint8_t* bl, const uint8_t* u, const uint8_t* c,
+                               uint8_t* out, uint8_t* status, size_t n) {
+    for (size_t base = 0; base < n; base += QQ_CHUNK) {
+        size_t m = n - base < QQ_CHUNK ? n - base : QQ_CHUNK;
+        CKQ(ws_begin(ctx, ws_need({4 * m * 160, 2 * m * 160, 2 * m * 160, m * 160, 4 * m, vb_scratch_bytes(ctx, 2)})));
+        u32x4* P = ws_take<u32x4>(ctx, 4 * m * 160);   // gr, grsk, c, d of every account
+        u32x4* Ru = ws_take<u32x4>(ctx, 2 * m * 160);  // u*gr, u*grsk
+        u32x4* Rc = ws_take<u32x4>(ctx, 2 * m * 160);  // c*gr, c*grsk
+        u32x4* F = ws_take<u32x4>(ctx, m * 160);       // bl*B
+        uint8_t* ok = ws_take<uint8_t>(ctx, 4 * m);
+        u32x4* scratch = ws_take<u32x4>(ctx, vb_scratch_bytes(ctx, 2));
+        const uint8_t* acc_c = acc + base * 128;
+        const uint8_t *bl_c = bl + base * 32, *u_c = u + base * 32, *c_c = c + base * 32;
+        uint8_t* out_c = out + base * 128;
+        CKQ(launch_decompress(ctx, acc_c, IDENT, P, ok, 4 * m));
+        CKQ(launch_status(ctx, bl_c, u_c, c_c, ok, 4, status + base, m));
+        // items: (account i, point j in {gr, grsk}); two scalars (u_i, c_i) share one window table
+        CKQ(launch_varbase(ctx, 2, P, imap(2, 4, 0, 1), u_c, c_c, 2, Ru, Rc, scratch, 2 * m));
+        CKQ(launch_fixedbase(ctx, QQ_BASE_B, bl_c, F, m));
+        // pk' = (u*gr, u*grsk)
+        CKQ(launch_finish(ctx, fsrc(Ru, imap(1, 2, 0)), FNONE, FNONE, out_c, imap(1, 4, 0), status + base, m));
+        CKQ(launch_finish(ctx, fsrc(Ru, imap(1, 2, 1)), FNONE, FNONE, out_c, imap(1, 4, 1), status + base, m));
+        // comm' = (c*gr + a.c, bl*B + c*grsk + a.d)        -- OLD pk, reference src/accounts/accounts.rs:149-152
+        CKQ(launch_finish(ctx, fsrc(Rc, imap(1, 2, 0)), fsrc(P, imap(1, 4, 2)), FNONE, out_c, imap(1, 4, 2),
+                          status + base, m));
+        CKQ(launch_finish(ctx, fsrc(Rc, imap(1, 2, 1)), fsrc(F, IDENT), fsrc(P, imap(1, 4, 3)), out_c, imap(1, 4, 3),
+                          status + base, m));
+    }
+    return QQ_OK;
+}
+
+static int core_verify_account(qq_ctx* ctx, const uint8_t* acc, const uint8_t* sk, const uint8_t* bl, uint8_t* status,
+                               size_t n) {
+    for (size_t base = 0; base < n; base += QQ_CHUNK) {
+        size_t m = n - base < QQ_CHUNK ? n - base : QQ_CHUNK;
+        CKQ(ws_begin(ctx, ws_need({2 * m * 160, 2 * m * 160, m * 160, 2 * m, 2 * m, m, vb_scratch_bytes(ctx, 1)})));
+        u32x4* P = ws_take<u32x4>(ctx, 2 * m * 160);  // gr, c
+        u32x4* R = ws_take<u32x4>(ctx, 2 * m * 160);  // sk*gr, sk*c
+        u32x4* F = ws_take<u32x4>(ctx, m * 160);      // bl*B
+        uint8_t* ok = ws_take<uint8_t>(ctx, 2 * m);
+        uint8_t* eq = ws_take<uint8_t>(ctx, 2 * m);
+        uint8_t* pre = ws_take<uint8_t>(ctx, m);
+        u32x4* scratch = ws_take<u32x4>(ctx, vb_scratch_bytes(ctx, 1));
+        const uint8_t* acc_c = acc + base * 128;
+        const uint8_t *sk_c = sk + base * 32, *bl_c = bl + base * 32;
+        CKQ(launch_decompress(ctx, acc_c, imap(2, 4, 0, 2), P, ok, 2 * m));
+        CKQ(launch_status(ctx, sk_c, bl_c, nullptr, ok, 0, pre, m));
+        CKQ(launch_varbase(ctx, 1, P, IDENT, sk_c, nullptr, 2, R, nullptr, scratch, 2 * m));
+        CKQ(launch_fixedbase(ctx, QQ_BASE_B, bl_c, F, m));
+        // grsk == enc(sk*gr)                       reference src/ristretto/keys.rs:187-195
+        CKQ(launch_compare(ctx, fsrc(R, imap(1, 2, 0)), FNONE, acc_c, imap(1, 4, 1), eq, m));
+        // d == enc(bl*B + sk*c)                    reference src/elgamal/elgamal.rs:81-95
+        CKQ(launch_compare(ctx, fsrc(R, imap(1, 2, 1)), fsrc(F, IDENT), acc_c, imap(1, 4, 3), eq + m, m));
+        k_verify_account_status<<<grid_for(m, 256, ctx->sms * 16), 256, 0, ctx->stream>>>(pre, ok, eq, status + base, m);
+        ctx->launches++;
+    }
+    return QQ_OK;
+}
+
+static int core_verify_pk_update(qq_ctx* ctx, const uint8_t* upd, const uint8_t* pk, const uint8_t* r, uint8_t* status,
+                                 size_t n) {
+    for (size_t base = 0; base < n; base += QQ_CHUNK) {
+        size_t m = n - base < QQ_CHUNK ? n - base : QQ_CHUNK;
+        CKQ(ws_begin(ctx, ws_need({2 * m * 160, 2 * m * 160, 2 * m * 160, 4 * m, 2 * m, m, m, vb_scratch_bytes(ctx, 1)})));
+        u32x4* P = ws_take<u32x4>(ctx, 2 * m * 160);
+        u32x4* U = ws_take<u32x4>(ctx, 2 * m * 160);
+        u32x4* R = ws_take<u32x4>(ctx, 2 * m * 160);
+        uint8_t* ok = ws_take<uint8_t>(ctx, 4 * m);
+        uint8_t* eq = ws_take<uint8_t>(ctx, 2 * m);
+        uint8_t* s1 = ws_take<uint8_t>(ctx, m);
+        uint8_t* s2 = ws_take<uint8_t>(ctx, m);
+        u32x4* scratch = ws_take<u32x4>(ctx, vb_scratch_bytes(ctx, 1));
+        CKQ(launch_decompress(ctx, pk + base * 64, IDENT, P, ok, 2 * m));
+        CKQ(launch_decompress(ctx, upd + base * 64, IDENT, U, ok + 2 * m, 2 * m));
+        CKQ(launch_status(ctx, r + base * 32, nullptr, nullptr, ok, 2, s1, m));
+        CKQ(launch_status(ctx, nullptr, nullptr, nullptr, ok + 2 * m, 2, s2, m));
+        k_or_status<<<grid_for(m, 256, ctx->sms * 16), 256, 0, ctx->stream>>>(s1, s1, s2, m);
+        CKQ(launch_varbase(ctx, 1, P, IDENT, r + base * 32, nullptr, 2, R, nullptr, scratch, 2 * m));
+        span_begin(ctx, FAM_FIN);
+        k_points_equal<<<grid_for(2 * m, 256, ctx->sms * 64), 256, 0, ctx->stream>>>(R, U, eq, 2 * m);
+        span_end(ctx);
+        k_pair_status<<<grid_for(m, 256, ctx->sms * 16), 256, 0, ctx->stream>>>(s1, eq, QQ_ST_KEYPAIR, status + base, m);
+        ctx->launches += 3;
+    }
+    return QQ_OK;
+}
+
+static int core_delta_epsilon(qq_ctx* ctx, const uint8_t* acc, const uint8_t* bl, const uint8_t* r, uint8_t* delta,
+                              uint8_t* eps, uint8_t* status, size_t n) {
+    for (size_t base = 0; base < n; base += QQ_CHUNK) {
+        size_t m = n - base < QQ_CHUNK ? n - base : QQ_CHUNK;
+        CKQ(ws_begin(ctx, ws_need({2 * m * 160, 2 * m * 160, m * 160, m * 160, m * 160, 2 * m, vb_scratch_bytes(ctx, 1)})));
+        u32x4* P = ws_take<u32x4>(ctx, 2 * m * 160);   // gr, grsk
+        u32x4* R = ws_take<u32x4>(ctx, 2 * m * 160);   // r*gr, r*grsk
+        u32x4* FB = ws_take<u32x4>(ctx, m * 160);      // bl*B
+        u32x4* RB = ws_take<u32x4>(ctx, m * 160);      // r*B
+        u32x4* RH = ws_take<u32x4>(ctx, m * 160);      // r*H
+        uint8_t* ok = ws_take<uint8_t>(ctx, 2 * m);
+        u32x4* scratch = ws_take<u32x4>(ctx, vb_scratch_bytes(ctx, 1));
+        const uint8_t* acc_c = acc + base * 128;
+        const uint8_t *bl_c = bl + base * 32, *r_c = r + base * 32;
+        uint8_t *d_c = delta + base * 128, *e_c = eps + base * 128;
+        CKQ(launch_decompress(ctx, acc_c, imap(2, 4, 0, 1), P, ok, 2 * m));
+        CKQ(launch_status(ctx, r_c, bl_c, nullptr, ok, 2, status + base, m));
+        CKQ(launch_varbase(ctx, 1, P, IDENT, r_c, nullptr, 2, R, nullptr, scratch, 2 * m));
+        CKQ(launch_fixedbase(ctx, QQ_BASE_B, bl_c, FB, m));
+        CKQ(launch_fixedbase(ctx, QQ_BASE_B, r_c, RB, m));
+        CKQ(launch_fixedbase(ctx, QQ_BASE_H, r_c, RH, m));
+        // pk halves: delta keeps the account pk, epsilon carries base_pk (zeroed when the element is bad)
+        pk_bytes bpk;
+        memcpy(&bpk, ctx->base_pk, 64);
+        k_copy_pk<<<grid_for(m, 256, ctx->sms * 16), 256, 0, ctx->stream>>>((const u32x4*)acc_c, (u32x4*)d_c, (u32x4*)e_c,
+                                                                            bpk, status + base, m);
+        ctx->launches++;
+        CKQ(launch_finish(ctx, fsrc(R, imap(1, 2, 0)), FNONE, FNONE, d_c, imap(1, 4, 2), status + base, m));
+        CKQ(launch_finish(ctx, fsrc(R, imap(1, 2, 1)), fsrc(FB, IDENT), FNONE, d_c, imap(1, 4, 3), status + base, m));
+        CKQ(launch_finish(ctx, fsrc(RB, IDENT), FNONE, FNONE, e_c, imap(1, 4, 2), status + base, m));
+        CKQ(launch_finish(ctx, fsrc(RH, IDENT), fsrc(FB, IDENT), FNONE, e_c, imap(1, 4, 3), status + base, m));
+    }
+    return QQ_OK;
+}
+
+static int core_fixed_base(qq_ctx* ctx, int which, const uint8_t* s, uint8_t* out, uint8_t* status, size_t n) {
+    for (size_t base = 0; base < n; base += QQ_CHUNK) {
+        size_t m = n - base < QQ_CHUNK ? n - base : QQ_CHUNK;
+        CKQ(ws_begin(ctx, ws_need({m * 160})));
+        u32x4* F = ws_take<u32x4>(ctx, m * 160);
+        CKQ(launch_status(ctx, s + base * 32, nullptr, nullptr, nullptr, 0, status + base, m));
+        CKQ(launch_fixedbase(ctx, which, s + base * 32, F, m));
+        CKQ(launch_finish(ctx, fsrc(F, IDENT), FNONE, FNONE, out + base * 32, IDENT, status + base, m));
+    }
+    return QQ_OK;
+}
+
+// ---- MSM ----------------------------------------------------------------------------------------------------------
+// result: extended point (device, 160 B) = sum s_i * P_i ; *dstatus (device byte) = 0 / 1 / 2
+static int core_msm_to_point(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, u32x4* result,
+                             uint8_t* dstatus);
+
+static int core_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* points, const uint32_t* offsets, size_t m,
+                          size_t nterms, uint8_t* out, uint8_t* status) {
+    CKQ(ws_begin(ctx, ws_need({nterms * 160, nterms * 160, nterms, nterms, vb_scratch_bytes(ctx, 1)})));
+    u32x4* P = ws_take<u32x4>(ctx, nterms * 160);
+    u32x4* R = ws_take<u32x4>(ctx, nterms * 160);
+    uint8_t* ok = ws_take<uint8_t>(ctx, nterms);
+    uint8_t* tst = ws_take<uint8_t>(ctx, nterms);
+    u32x4* scratch = ws_take<u32x4>(ctx, vb_scratch_bytes(ctx, 1));
+    CKQ(launch_decompress(ctx, points, IDENT, P, ok, nterms));
+    CKQ(launch_status(ctx, scalars, nullptr, nullptr, ok, 1, tst, nterms));
+    CKQ(launch_varbase(ctx, 1, P, IDENT, scalars, nullptr, 1, R, nullptr, scratch, nterms));
+    span_begin(ctx, FAM_FIN);
+    k_segment_sum_compress<<<grid_for(m, 256, ctx->sms * 64), 256, 0, ctx->stream>>>(R, offsets, tst, (u32x4*)out, status, m);
+    span_end(ctx);
+    ctx->launches++;
+    return QQ_OK;
+}
+
+// =================================================================================================================
+// exported entry points: _dev variants call the cores directly, host variants stage through the workspace tail
+// =================================================================================================================
+struct stage {
+    std::vector<void*> dptr;
+    qq_ctx* ctx;
+    explicit stage(qq_ctx* c) : ctx(c) {}
+    ~stage() {
+        for (void* p : dptr) cudaFree(p);
+    }
+    int in(const void* host, size_t bytes, uint8_t** out) {
+        void* d = nullptr;
+        CK(cudaMalloc(&d, bytes ? bytes : 16));
+        dptr.push_back(d);
+        if (bytes) CK(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        *out = (uint8_t*)d;
+        return QQ_OK;
+    }
+    int outbuf(size_t bytes, uint8_t** out) {
+        void* d = nullptr;
+        CK(cudaMalloc(&d, bytes ? bytes : 16));
+        dptr.push_back(d);
+        *out = (uint8_t*)d;
+        return QQ_OK;
+    }
+    int back(void* host, const void* dev, size_t bytes) {
+        if (bytes) CK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        return QQ_OK;
+    }
+};
+
+#define ENTER()                          \
+    if (!ctx) return QQ_ERR_ARG;         \
+    CK(cudaSetDevice(ctx->device));      \
+    call_begin(ctx)
+
+extern "C" int qq_update_public_key_batch_dev(qq_ctx* ctx, const uint8_t* pk, const uint8_t* r, uint8_t* out_pk,
+                                              uint8_t* status, size_t n) {
+    ENTER();
+    REQUIRE(aligned16(pk) && aligned16(r) && aligned16(out_pk) && status);
+    CKQ(core_scale_pairs(ctx, pk, r, out_pk, status, n));
+    return call_end(ctx);
+}
+extern "C" int qq_update_public_key_batch(qq_ctx* ctx, const uint8_t* pk, const uint8_t* r, uint8_t* out_pk,
+                                          uint8_t* status, size_t n) {
+    ENTER();
+    REQUIRE(pk && r && out_pk && status);
+    stage st(ctx);
+    uint8_t *dpk, *dr, *dout, *dst;
+    CKQ(st.in(pk, n * 64, &dpk));
+    CKQ(st.in(r, n * 32, &dr));
+    CKQ(st.outbuf(n * 64, &dout));
+    CKQ(st.outbuf(n, &dst));
+    CKQ(core_scale_pairs(ctx, dpk, dr, dout, dst, n));
+    CKQ(st.back(out_pk, dout, n * 64));
+    CKQ(st.back(status, dst, n));
+    return call_end(ctx);
+}
+extern "C" int qq_mul_commitment_batch(qq_ctx* ctx, const uint8_t* comm, const uint8_t* s, uint8_t* out_comm,
+                                       uint8_t* status, size_t n) {
+    return qq_update_public_key_batch(ctx, comm, s, out_comm, status, n);
+}
+extern "C" int qq_verify_public_key_update_batch(qq_ctx* ctx, const uint8_t* updated_pk, const uint8_t* pk,
+                                                 const uint8_t* r, uint8_t* status, size_t n) {
+    ENTER();
+    REQUIRE(updated_pk && pk && r && status);
+    stage st(ctx);
+    uint8_t *du, *dpk, *dr, *dst;
+    CKQ(st.in(updated_pk, n * 64, &du));
+    CKQ(st.in(pk, n * 64, &dpk));
+    CKQ(st.in(r, n * 32, &dr));
+    CKQ(st.outbuf(n, &dst));
+    CKQ(core_verify_pk_update(ctx, du, dpk, dr, dst, n));
+    CKQ(st.back(status, dst, n));
+    return call_end(ctx);
+}
+extern "C" int qq_generate_commitment_batch_dev(qq_ctx* ctx, const uint8_t* pk, const uint8_t* r, const uint8_t* v,
+                                                uint8_t* out_comm, uint8_t* status, size_t n) {
+    ENTER();
+    REQUIRE(aligned16(pk) && aligned16(r) && aligned16(v) && aligned16(out_comm) && status);
+    CKQ(core_generate_commitment(ctx, pk, r, v, out_comm, status, n));
+    return call_end(ctx);
+}
+extern "C" int qq_generate_commitment_batch(qq_ctx* ctx, const uint8_t* pk, const uint8_t* r, const uint8_t* v,
+                                            uint8_t* out_comm, uint8_t* status, size_t n) {
+    ENTER();
+    REQUIRE(pk && r && v && out_comm && status);
+    stage st(ctx);
+    uint8_t *dpk, *dr, *dv, *dout, *dst;
+    CKQ(st.in(pk, n * 64, &dpk));
+    CKQ(st.in(r, n * 32, &dr));
+    CKQ(st.in(v, n * 32, &dv));
+    CKQ(st.outbuf(n * 64, &dout));
+    CKQ(st.outbuf(n, &dst));
+    CKQ(core_generate_commitment(ctx, dpk, dr, dv, dout, dst, n));
+    CKQ(st.back(out_comm, dout, n * 64));
+    CKQ(st.back(status, dst, n));
+    return call_end(ctx);
+}
+extern "C" int qq_add_commitments_batch(qq_ctx* ctx, const uint8_t* a, const uint8_t* b, int negate_b,
+                                        uint8_t* out_comm, uint8_t* status, size_t n) {
+    ENTER();
+    REQUIRE(a && b && out_comm && status);
+    stage st(ctx);
+    uint8_t *da, *db, *dout, *dst;
+    CKQ(st.in(a, n * 64, &da));
+    CKQ(st.in(b, n * 64, &db));
+    CKQ(st.outbuf(n * 64, &dout));
+    CKQ(st.outbuf(n, &dst));
+    CKQ(core_add_commitments(ctx, da, db, negate_b ? 1 : 0, dout, dst, n));
+    CKQ(st.back(out_comm, dout, n * 64));
+    CKQ(st.back(status, dst, n));
+    return call_end(ctx);
+}
+extern "C" int qq_update_account_batch_dev(qq_ctx* ctx, const uint8_t* acc, const uint8_t* bl, const uint8_t* u,
+                                           const uint8_t* c, uint8_t* out_acc, uint8_t* status, size_t n) {
+    ENTER();
+    REQUIRE(aligned16(acc) && aligned16(bl) && aligned16(u) && aligned16(c) && aligned16(out_acc) && status);
+    CKQ(core_update_account(ctx, acc, bl, u, c, out_acc, status, n));
+    return call_end(ctx);
+}
+extern "C" int qq_update_account_batch(qq_ctx* ctx, const uint8_t* acc, const uint8_t* bl, const uint8_t* u,
+                                       const uint8_t* c, uint8_t* out_acc, uint8_t* status, size_t n) {
+    ENTER();
+    REQUIRE(acc && bl && u && c && out_acc && status);
+    stage st(ctx);
+    uint8_t *dacc, *dbl, *du, *dc, *dout, *dst;
+    CKQ(st.in(acc, n * 128, &dacc));
+    CKQ(st.in(bl, n * 32, &dbl));
+    CKQ(st.in(u, n * 32, &du));
+    CKQ(st.in(c, n * 32, &dc));
+    CKQ(st.outbuf(n * 128, &dout));
+    CKQ(st.outbuf(n, &dst));
+    CKQ(core_update_account(ctx, dacc, dbl, du, dc, dout, dst, n));
+    CKQ(st.back(out_acc, dout, n * 128));
+    CKQ(st.back(status, dst, n));
+    return call_end(ctx);
+}
+extern "C" int qq_verify_account_batch_dev(qq_ctx* ctx, const uint8_t* acc, const uint8_t* sk, const uint8_t* bl,
+                                           uint8_t* status, size_t n) {
+    ENTER();
+    REQUIRE(aligned16(acc) && aligned16(sk) && aligned16(bl) && status);
+    CKQ(core_verify_account(ctx, acc, sk, bl, status, n));
+    return call_end(ctx);
+}
+extern "C" int qq_verify_account_batch(qq_ctx* ctx, const uint8_t* acc, const uint8_t* sk, const uint8_t* bl,
+                                       uint8_t* status, size_t n) {
+    ENTER();
+    REQUIRE(acc && sk && bl && status);
+    stage st(ctx);
+    uint8_t *dacc, *dsk, *dbl, *dst;
+    CKQ(st.in(acc, n * 128, &dacc));
+    CKQ(st.in(sk, n * 32, &dsk));
+    CKQ(st.in(bl, n * 32, &dbl));
+    CKQ(st.outbuf(n, &dst));
+    CKQ(core_verify_account(ctx, dacc, dsk, dbl, dst, n));
+    CKQ(st.back(status, dst, n));
+    return call_end(ctx);
+}
+extern "C" int qq_delta_epsilon_batch(qq_ctx* ctx, const uint8_t* acc, const uint8_t* bl, const uint8_t* r,
+                                      const uint8_t* base_pk, uint8_t* out_delta, uint8_t* out_epsilon,
+                                      uint8_t* status, size_t n) {
+    ENTER();
+    REQUIRE(acc && bl && r && base_pk && out_delta && out_epsilon && status);
+    if (memcmp(base_pk, ctx->base_pk, 64) != 0) {
+        ctx->err = "qq_delta_epsilon_batch: base_pk must be BASE_PK_BTC_COMPRESSED (B, H)";
+        return QQ_ERR_ARG;
+    }
+    stage st(ctx);
+    uint8_t *dacc, *dbl, *dr, *dd, *de, *dst;
+    CKQ(st.in(acc, n * 128, &dacc));
+    CKQ(st.in(bl, n * 32, &dbl));
+    CKQ(st.in(r, n * 32, &dr));
+    CKQ(st.outbuf(n * 128, &dd));
+    CKQ(st.outbuf(n * 128, &de));
+    CKQ(st.outbuf(n, &dst));
+    CKQ(core_delta_epsilon(ctx, dacc, dbl, dr, dd, de, dst, n));
+    CKQ(st.back(out_delta, dd, n * 128));
+    CKQ(st.back(out_epsilon, de, n * 128));
+    CKQ(st.back(status, dst, n));
+    return call_end(ctx);
+}
+extern "C" int qq_fixed_base_batch_dev(qq_ctx* ctx, int which, const uint8_t* s, uint8_t* out_points, uint8_t* status,
+                                       size_t n) {
+    ENTER();
+    REQUIRE((which == 0 || which == 1) && aligned16(s) && aligned16(out_points) && status);
+    CKQ(core_fixed_base(ctx, which, s, out_points, status, n));
+    return call_end(ctx);
+}
+extern "C" int qq_fixed_base_batch(qq_ctx* ctx, int which, const uint8_t* s, uint8_t* out_points, uint8_t* status,
+                                   size_t n) {
+    ENTER();
+    REQUIRE((which == 0 || which == 1) && s && out_points && status);
+    stage st(ctx);
+    uint8_t *ds, *dout, *dst;
+    CKQ(st.in(s, n * 32, &ds));
+    CKQ(st.outbuf(n * 32, &dout));
+    CKQ(st.outbuf(n, &dst));
+    CKQ(core_fixed_base(ctx, which, ds, dout, dst, n));
+    CKQ(st.back(out_points, dout, n * 32));
+    CKQ(st.back(status, dst, n));
+    return call_end(ctx);
+}
+
+#include "qq_api_msm.inc"

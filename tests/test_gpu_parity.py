@@ -1,0 +1,291 @@
+"""GPU parity tests: every C-ABI entry point against the oracle on the same seeded inputs, bit-exact.
+Mirrors the reference's test scenarios (src/accounts/accounts.rs:367-596, src/elgamal/elgamal.rs:265-303,
+src/ristretto/keys.rs:293-337, src/accounts/verifier.rs:938-1776) with the oracle supplying expected bytes."""
+import numpy as np
+import pytest
+
+import ristretto_ref as R
+from qq_testlib import Stream, cat, invalid_encodings, make_account, sb
+
+pytestmark = pytest.mark.gpu
+
+EDGE_SCALARS = [0, 1, 2, 8, 15, 16, R.L - 1, R.L - 8, 2**252, 2**128 - 1]
+
+
+def test_fixed_base_B_and_H(engine):
+    st = Stream(b"fixed")
+    ks = EDGE_SCALARS + [st.scalar() for _ in range(150)]
+    for which, base in ((0, R.BASEPOINT), (1, R.PEDERSEN_H)):
+        out, status = engine.fixed_base(which, cat([sb(k) for k in ks]))
+        assert not status.any()
+        for i, k in enumerate(ks):
+            assert out[i].tobytes() == R.compress(R.mul(k, base)), (which, i)
+    # RFC 9496 A.1 small multiples of the generator
+    import json, os
+    vec = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "rfc9496.json")))
+    out, _ = engine.fixed_base(0, cat([sb(i) for i in range(16)]))
+    for i in range(16):
+        assert out[i].tobytes().hex() == vec["multiples_of_generator"][i]
+
+
+def test_fixed_base_non_canonical_scalar(engine):
+    s = cat([sb(5), R.L.to_bytes(32, "little"), (2**256 - 1).to_bytes(32, "little")])
+    out, status = engine.fixed_base(0, s)
+    assert list(status) == [0, 2, 2]
+    assert out[1].tobytes() == bytes(32) and out[2].tobytes() == bytes(32)
+    assert out[0].tobytes() == R.compress(R.mul(5, R.BASEPOINT))
+
+
+def test_update_public_key(engine):
+    st = Stream(b"upk")
+    pks, rs = [], []
+    for i in range(96):
+        acc, _, _ = make_account(st)
+        pks.append(acc[:64])
+        rs.append(sb(EDGE_SCALARS[i]) if i < len(EDGE_SCALARS) else st.scalar_bytes())
+    out, status = engine.update_public_key(cat(pks), cat(rs))
+    for i in range(len(pks)):
+        exp, es = R.update_public_key(pks[i], rs[i])
+        assert status[i] == es and out[i].tobytes() == exp, i
+
+
+def test_update_public_key_invalid_points(engine):
+    st = Stream(b"upk-bad")
+    good, _, _ = make_account(st)
+    pks, rs = [], []
+    for name, enc in invalid_encodings():
+        pks.append(enc + good[32:64])
+        pks.append(good[:32] + enc)
+        rs += [st.scalar_bytes(), st.scalar_bytes()]
+    pks.append(bytes(64))  # identity, identity: valid
+    rs.append(st.scalar_bytes())
+    out, status = engine.update_public_key(cat(pks), cat(rs))
+    for i in range(len(pks)):
+        exp, es = R.update_public_key(pks[i], rs[i])
+        assert status[i] == es, i
+        assert out[i].tobytes() == exp, i
+    assert status[-1] == 0 and list(status[:-1]) == [1] * (len(pks) - 1)
+
+
+def test_generate_commitment(engine):
+    st = Stream(b"commit")
+    pks, rs, vs = [], [], []
+    for i in range(96):
+        acc, _, _ = make_account(st)
+        pks.append(acc[:64])
+        rs.append(st.scalar_bytes())
+        vs.append(sb([0, 1, 160000, 16734, R.L - 5][i]) if i < 5 else (sb(st.scalar() % 2**64) if i % 2 else st.scalar_bytes()))
+    out, status = engine.generate_commitment(cat(pks), cat(rs), cat(vs))
+    for i in range(len(pks)):
+        exp, es = R.generate_commitment(pks[i], rs[i], vs[i])
+        assert status[i] == es and out[i].tobytes() == exp, i
+
+
+def test_add_sub_mul_commitments(engine):
+    st = Stream(b"addc")
+    a, b, s = [], [], []
+    for i in range(64):
+        x, _, _ = make_account(st, value=st.scalar() % 1000)
+        y, _, _ = make_account(st, value=st.scalar() % 1000)
+        a.append(x[64:])
+        b.append(y[64:] if i else x[64:])
+        s.append(st.scalar_bytes())
+    bad = invalid_encodings()[0][1]
+    a.append(bad + a[0][32:])
+    b.append(b[0])
+    s.append(s[0])
+    out, status = engine.add_commitments(cat(a), cat(b))
+    outs, statuss = engine.add_commitments(cat(a), cat(b), negate_b=True)
+    outm, statusm = engine.mul_commitment(cat(a), cat(s))
+    for i in range(len(a)):
+        exp, es = R.add_commitments(a[i], b[i])
+        assert status[i] == es and out[i].tobytes() == exp, i
+        exp, es = R.sub_commitments(a[i], b[i])
+        assert statuss[i] == es and outs[i].tobytes() == exp, i
+        exp, es = R.mul_commitment(a[i], s[i])
+        assert statusm[i] == es and outm[i].tobytes() == exp, i
+    # a - a = identity -> 32 zero bytes (dalek encodes the identity as zeros)
+    assert outs[0].tobytes() == bytes(64)
+
+
+def test_update_account_and_verify(engine):
+    st = Stream(b"upd")
+    accs, sks, bls, us, cs, vals = [], [], [], [], [], []
+    for i in range(80):
+        v = [0, 5, 0, 3][i % 4] if i < 40 else st.scalar() % 2**64
+        acc, sk, _ = make_account(st, value=v)
+        accs.append(acc)
+        sks.append(sk)
+        vals.append(v)
+        delta = [0, R.L - 5, 5, 0][i % 4] if i < 40 else st.scalar() % 2**32
+        bls.append(sb(delta))
+        us.append(st.scalar_bytes())
+        cs.append(st.scalar_bytes())
+    out, status = engine.update_account(cat(accs), cat(bls), cat(us), cat(cs))
+    assert not status.any()
+    for i in range(len(accs)):
+        exp, es = R.update_account(accs[i], bls[i], us[i], cs[i])
+        assert es == 0 and out[i].tobytes() == exp, i
+    # updated accounts still verify under the same secret key and the new balance (reference
+    # update_account_test, src/accounts/accounts.rs:432-452)
+    newbal = [sb(vals[i] + int.from_bytes(bls[i], "little")) for i in range(len(accs))]
+    vst = engine.verify_account(out.reshape(-1), cat([sb(k) for k in sks]), cat(newbal))
+    assert not vst.any(), vst
+    # wrong balance -> commitment failure (4); wrong key -> keypair failure (3)
+    vst = engine.verify_account(out.reshape(-1), cat([sb(k) for k in sks]), cat([sb(int.from_bytes(b, "little") + 1) for b in newbal]))
+    assert (vst == 4).all()
+    vst = engine.verify_account(out.reshape(-1), cat([sb(k + 1) for k in sks]), cat(newbal))
+    assert (vst == 3).all()
+    for i in range(0, len(accs), 7):
+        assert R.verify_account(out[i].tobytes(), sb(sks[i]), newbal[i]) == 0
+
+
+def test_update_account_invalid_and_status(engine):
+    st = Stream(b"upd-bad")
+    good, _, _ = make_account(st, 7)
+    accs, bls, us, cs = [], [], [], []
+    for name, enc in invalid_encodings():
+        for pos in range(4):
+            a = bytearray(good)
+            a[32 * pos:32 * pos + 32] = enc
+            accs.append(bytes(a))
+            bls.append(sb(3)), us.append(st.scalar_bytes()), cs.append(st.scalar_bytes())
+    accs.append(good)
+    bls.append(R.L.to_bytes(32, "little")), us.append(sb(1)), cs.append(sb(1))       # non-canonical scalar
+    accs.append(good)
+    bls.append(sb(0)), us.append(sb(0)), cs.append(sb(0))                              # all-zero scalars
+    out, status = engine.update_account(cat(accs), cat(bls), cat(us), cat(cs))
+    for i in range(len(accs)):
+        exp, es = R.update_account(accs[i], bls[i], us[i], cs[i])
+        assert status[i] == es, (i, status[i], es)
+        assert out[i].tobytes() == exp, i
+    vst = engine.verify_account(cat(accs), cat(us), cat(bls))
+    for i in range(len(accs)):
+        assert vst[i] == R.verify_account(accs[i], us[i], bls[i]), i
+
+
+def test_verify_public_key_update(engine):
+    st = Stream(b"vpku")
+    pks, rs, upd = [], [], []
+    for i in range(48):
+        acc, _, _ = make_account(st)
+        r = st.scalar_bytes()
+        u, _ = R.update_public_key(acc[:64], r)
+        if i % 3 == 1:
+            u = u[:32] + R.compress(R.mul(st.scalar(), R.BASEPOINT))
+        if i % 3 == 2:
+            r = st.scalar_bytes()
+        pks.append(acc[:64]), rs.append(r), upd.append(u)
+    status = engine.verify_public_key_update(cat(upd), cat(pks), cat(rs))
+    for i in range(len(pks)):
+        assert status[i] == R.verify_public_key_update(upd[i], pks[i], rs[i]), i
+
+
+def test_delta_and_epsilon_accounts(engine):
+    """Reference scenario create_delta_and_epsilon_accounts_test (src/accounts/accounts.rs:454-499): values
+    [-5, 5, 0 x7], random r with sum zero; then Verifier::verify_delta_identity_check on the epsilon accounts."""
+    st = Stream(b"delta")
+    for trial in range(3):
+        n = 9
+        accs = [make_account(st)[0] for _ in range(n)]
+        vals = [R.L - 5, 5] + [0] * 7 if trial == 0 else [R.L - 5, R.L - 3, 5, 3] + [0] * 5
+        rs = [st.scalar() for _ in range(n - 1)]
+        rs.append((-sum(rs)) % R.L)
+        d, e, status = engine.delta_epsilon(cat(accs), cat([sb(v) for v in vals]), cat([sb(r) for r in rs]), np.frombuffer(R.BASE_PK, np.uint8))
+        assert not status.any()
+        for i in range(n):
+            ed, ee, es = R.delta_epsilon(accs[i], sb(vals[i]), sb(rs[i]))
+            assert es == 0 and d[i].tobytes() == ed and e[i].tobytes() == ee, i
+        assert engine.delta_identity_check(e.reshape(-1)) == 0
+        assert R.delta_identity_check([e[i].tobytes() for i in range(n)]) == 0
+        # break the zero-sum -> identity check fails
+        e2 = e.copy()
+        e2[0] = e2[1]
+        assert engine.delta_identity_check(e2.reshape(-1)) == R.delta_identity_check([e2[i].tobytes() for i in range(n)]) == 4
+
+
+def test_msm_small_and_segmented(engine):
+    st = Stream(b"msm")
+    # 2- and 3-term instances as at the 27 call sites of Verifier::multiscalar_multiplication
+    scal, pts, offs = [], [], [0]
+    for j in range(40):
+        k = [2, 3, 2, 9, 1, 6][j % 6]
+        for _ in range(k):
+            scal.append(st.scalar_bytes())
+            pts.append(R.compress(R.mul(st.scalar(), R.BASEPOINT)))
+        offs.append(len(scal))
+    bad = invalid_encodings()[3][1]
+    scal += [st.scalar_bytes(), st.scalar_bytes()]
+    pts += [pts[0], bad]
+    offs.append(len(scal))
+    offs.append(len(scal))  # empty instance -> identity
+    out, status = engine.msm_segmented(cat(scal), cat(pts), np.array(offs, np.uint32))
+    for j in range(len(offs) - 1):
+        exp, es = R.msm(scal[offs[j]:offs[j + 1]], pts[offs[j]:offs[j + 1]])
+        assert status[j] == es and out[j].tobytes() == exp, j
+    # single MSM over everything valid
+    nv = offs[40]
+    o, s = engine.msm(cat(scal[:nv]), cat(pts[:nv]))
+    exp, es = R.msm(scal[:nv], pts[:nv])
+    assert s == es == 0 and o.tobytes() == exp
+    o, s = engine.msm(cat(scal), cat(pts))
+    assert s == 1 and o.tobytes() == bytes(32)
+    # partial sums combine (multi-GPU path): split, export X,Y,Z,T, sum
+    h = nv // 2
+    p1, s1 = engine.msm_partial(cat(scal[:h]), cat(pts[:h]))
+    p2, s2 = engine.msm_partial(cat(scal[h:nv]), cat(pts[h:nv]))
+    assert s1 == 0 and s2 == 0
+    tot, ident = engine.points_sum(np.concatenate([p1, p2]))
+    assert tot.tobytes() == exp and not ident
+
+
+def test_msm_known_dlog_identity(engine):
+    """SURVEY 8d config 4 shape: P_i = h_i*B, last scalar solved so that sum a_i h_i = 0 -> identity."""
+    st = Stream(b"msm-id")
+    n = 300
+    hs = [st.scalar() for _ in range(n)]
+    pts, _ = engine.fixed_base(0, cat([sb(h) for h in hs]))
+    a = [st.scalar() for _ in range(n - 1)]
+    acc = sum(x * h for x, h in zip(a, hs)) % R.L
+    a.append((-acc * pow(hs[-1], -1, R.L)) % R.L)
+    o, s = engine.msm(cat([sb(x) for x in a]), pts.reshape(-1))
+    assert s == 0 and o.tobytes() == bytes(32)
+    a[3] = (a[3] + 1) % R.L
+    o, s = engine.msm(cat([sb(x) for x in a]), pts.reshape(-1))
+    assert s == 0 and o.tobytes() == R.compress(R.mul(hs[3], R.BASEPOINT))
+
+
+def test_reference_interface_mirror(engine, pkg):
+    """The reference's own scalar API shapes (n = 1), routed through the batch library."""
+    from quisquis_rust_b200 import api
+    api.set_default_engine(engine)
+    st = Stream(b"mirror")
+    acc_b, sk, k = make_account(st, 0)
+    acc = pkg.Account(acc_b)
+    upd = pkg.Account.update_account(acc, sb(16734), st.scalar_bytes(), st.scalar_bytes())
+    upd.verify_account(sb(sk), sb(16734))
+    with pytest.raises(ValueError, match="Commitment Verification Failed"):
+        upd.verify_account(sb(sk), sb(16735))
+    with pytest.raises(ValueError, match="Keypair Verification Failed"):
+        upd.verify_account(sb(sk + 1), sb(16734))
+    r = st.scalar_bytes()
+    pk2 = pkg.RistrettoPublicKey.update_public_key(acc.pk, r)
+    assert pkg.RistrettoPublicKey.verify_public_key_update(pk2, acc.pk, r)
+    assert not pkg.RistrettoPublicKey.verify_public_key_update(pk2, acc.pk, st.scalar_bytes())
+    c1 = pkg.ElGamalCommitment.generate_commitment(acc.pk, r, sb(10))
+    c2 = pkg.ElGamalCommitment.generate_commitment(acc.pk, r, sb(4))
+    c3 = pkg.ElGamalCommitment.generate_commitment(acc.pk, sb(0), sb(6))
+    assert (c1 - c2) == c3
+    assert pkg.ElGamalCommitment.add_commitments(c2, c3) == c1
+    with pytest.raises(api.PanicError):
+        pkg.RistrettoPublicKey.update_public_key(pkg.RistrettoPublicKey(b"\x01" + bytes(63)), r)
+    assert pkg.Verifier.multiscalar_multiplication([r, r], [acc_b[:32], b"\x01" + bytes(31)]) is None
+    # verify_account_update: exactly-9 quirk (src/accounts/accounts.rs:180)
+    accs = [pkg.Account(make_account(st)[0]) for _ in range(9)]
+    us = [st.scalar_bytes() for _ in range(9)]
+    cs = [st.scalar_bytes() for _ in range(9)]
+    updated = [pkg.Account.update_account(a, sb(0), u, c) for a, u, c in zip(accs, us, cs)]
+    assert pkg.Account.verify_account_update(updated, accs, us, cs)
+    assert not pkg.Account.verify_account_update(updated[::-1], accs, us, cs)
+    with pytest.raises(api.PanicError):
+        pkg.Account.verify_account_update(updated[:8], accs[:8], us[:8], cs[:8])
