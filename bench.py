@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""Benchmark of the quisquis hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, libqq_b200.so)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path on the host cores
+
+A "step" = Account::update_account over one batch of 2^20 synthetic accounts per GPU (BASELINE.json configs[1]);
+the JSON line also carries the 2^20-point MSM (configs[3]) as `msm`.  Metric: account updates / s (whole job).
+
+Timing: W warm-up steps, then exactly K steps bracketed by barrier + synchronize; device time is taken with CUDA
+events recorded on the library's own stream (qq_event_record), max over ranks.  Inputs (224 MB) and outputs (128 MB)
+per step exceed the 126 MB L2, so no L2 flush is needed between steps.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic work per unit (SURVEY.md App. B / BASELINE.md section 4), in thread-level IMAD instructions
+# (a 32x32->64 product = 2: IMAD.WIDE and IMAD.HI issue at half the IMAD rate on sm_100a, measured)
+IMAD_PER_UPDATE_ACCOUNT = 1_438_000
+IMAD_PER_VARBASE = 289_000
+IMAD_PER_MSM_POINT = 43_900        # compressed input, n = 2^20, c = 16
+BYTES_PER_UPDATE_ACCOUNT = 224 + 128 + 1
+L = 2**252 + 27742317777372353535851937790883648493
+
+
+def rand_scalars(rng, n):
+    raw = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    raw[:, 31] &= 0x0f          # < 2^252 < l: canonical, uniform over 252 bits ("worst case" distribution A)
+    return raw
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for nme, v in zip(names, s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]),
+                "power_w_max": max(float(s[2]) for s in self.samples), "reasons": sorted(reasons),
+                "samples": len(self.samples)}
+
+
+def dist_setup(n_gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return world, rank, local
+
+
+# =====================================================================================================================
+# reference arm: the reference's own CPU implementation of the path = curve25519-dalek's algorithms, restated in
+# oracle/qq_oracle.c (dalek cannot be built here: no cargo/rustc, not vendored), all host threads.
+# =====================================================================================================================
+def run_reference(args):
+    world, rank, local = dist_setup(args.gpus)
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import c_oracle as C
+    cores = C.threads()
+    rng = np.random.default_rng(1234)
+    # calibrate a bounded sample: ~2 s of all-core work per step
+    m0 = 64 * cores
+    cols = [C.fixed_base(0, rand_scalars(rng, m0))[0] for _ in range(4)]
+    acc0 = np.concatenate(cols, axis=1).copy()
+    t = time.time()
+    C.update_account(acc0, rand_scalars(rng, m0), rand_scalars(rng, m0), rand_scalars(rng, m0))
+    rate0 = m0 / (time.time() - t)
+    m = int(max(m0, min(1 << 20, rate0 * args.ref_seconds_per_step)))
+    reps = (m + m0 - 1) // m0
+    acc = np.tile(acc0, (reps, 1))[:m].copy()
+    bl, u, c = rand_scalars(rng, m), rand_scalars(rng, m), rand_scalars(rng, m)
+    for _ in range(args.warmup):
+        C.update_account(acc[:m0], bl[:m0], u[:m0], c[:m0])
+    t = time.time()
+    for _ in range(args.steps):
+        out, st = C.update_account(acc, bl, u, c)
+    dt = time.time() - t
+    assert not st.any()
+    value = m * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "account_updates_per_sec", "value": value, "unit": "accounts/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (radix-2^51 limbs, 128-bit products)",
+        "data": "synthetic",
+        "config": {"workload": "Account::update_account, 2^20 accounts per GPU (BASELINE.json configs[1]); this arm times "
+                               "a bounded sample of %d accounts per step" % m,
+                   "scalars": "uniform 252-bit"},
+        "cpu_baseline": {"value": value, "unit": "accounts/s", "cores": cores, "kind": "port",
+                         "sample": "%d accounts x %d steps, OpenMP over %d host threads; oracle/qq_oracle.c restates "
+                                   "curve25519-dalek 3.2.1's algorithms (dalek itself is not buildable here: no "
+                                   "cargo/rustc, crate not vendored)" % (m, args.steps, cores)},
+        "e2e": {"value": value, "unit": "accounts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# =====================================================================================================================
+# our arm
+# =====================================================================================================================
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    world, rank, local = dist_setup(args.gpus)
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = g.load_package()
+    eng = pkg.Engine(local)
+    dev = torch.device("cuda", local)
+    n = args.accounts
+    rng = np.random.default_rng(1000 + rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- synthetic inputs: valid accounts with known discrete logs, built with the fixed-base kernel ------------
+    cols = [eng.fixed_base(0, rand_scalars(rng, n))[0] for _ in range(4)]
+    acc_h = np.concatenate(cols, axis=1).copy()
+    bl_h, u_h, c_h = rand_scalars(rng, n), rand_scalars(rng, n), rand_scalars(rng, n)
+    # pinned host buffers for the end-to-end leg
+    pin = {k: torch.from_numpy(v).pin_memory() for k, v in (("acc", acc_h), ("bl", bl_h), ("u", u_h), ("c", c_h))}
+    out_pin = torch.empty(n * 128, dtype=torch.uint8).pin_memory()
+    st_pin = torch.empty(n, dtype=torch.uint8).pin_memory()
+    # device-resident copies for the kernel-only leg (torch owns the memory; the library gets raw pointers)
+    d = {k: v.to(dev) for k, v in pin.items()}
+    out_d = torch.empty(n * 128, dtype=torch.uint8, device=dev)
+    st_d = torch.empty(n, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize(dev)
+    import ctypes
+    vp = ctypes.c_void_p
+
+    def step_dev():
+        eng.call_dev("qq_update_account_batch_dev", vp(d["acc"].data_ptr()), vp(d["bl"].data_ptr()),
+                     vp(d["u"].data_ptr()), vp(d["c"].data_ptr()), vp(out_d.data_ptr()), vp(st_d.data_ptr()),
+                     ctypes.c_size_t(n))
+
+    def step_e2e():
+        rc = eng.lib.qq_update_account_batch(eng.h, vp(pin["acc"].data_ptr()), vp(pin["bl"].data_ptr()),
+                                             vp(pin["u"].data_ptr()), vp(pin["c"].data_ptr()), vp(out_pin.data_ptr()),
+                                             vp(st_pin.data_ptr()), ctypes.c_size_t(n))
+        if rc != 0:
+            raise RuntimeError("qq_update_account_batch failed: %d" % rc)
+
+    peak = eng.measure_imad_peak()
+
+    # ---- kernel-only leg (inputs resident in HBM) -----------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_dev()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    launches0 = eng.launch_count
+    eng.event_record(0)
+    t0 = time.time()
+    vb_ms = 0.0
+    breakdown = {}
+    for _ in range(args.steps):
+        step_dev()
+        bd = eng.last_kernel_breakdown()
+        vb_ms += bd["varbase"]
+        for k_, v_ in bd.items():
+            breakdown[k_] = breakdown.get(k_, 0.0) + v_
+    eng.event_record(1)
+    dev_ms = eng.event_elapsed_ms(0, 1)
+    barrier()
+    wall_ms = (time.time() - t0) * 1e3
+    launches = eng.launch_count - launches0
+    sampler.stop_flag = True
+    sampler.join(2)
+    assert int(st_d.max().item()) == 0
+
+    # ---- end-to-end leg: host buffers in, host buffers out, through the public C ABI ----------------------------
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    t0 = time.time()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_ms = (time.time() - t0) * 1e3
+    assert int(st_pin.max().item()) == 0
+    same = bool(torch.equal(out_pin, out_d.cpu()))
+
+    # ---- MSM 2^20 (configs[3]): known-dlog points, last scalar solved so the sum is the identity ------------------
+    msm = None
+    if args.msm_points > 0:
+        m = args.msm_points
+        hs = rand_scalars(rng, m)
+        pts_h, _ = eng.fixed_base(0, hs)
+        a = rand_scalars(rng, m)
+        pts_d = torch.from_numpy(pts_h.reshape(-1)).to(dev)
+        a_d = torch.from_numpy(a.reshape(-1)).to(dev)
+        small = torch.zeros(256, dtype=torch.uint8, device=dev)
+        for _ in range(2):
+            eng.call_dev("qq_msm_dev", vp(a_d.data_ptr()), vp(pts_d.data_ptr()), ctypes.c_size_t(m),
+                         vp(small.data_ptr()), vp(small.data_ptr() + 64))
+        barrier()
+        eng.event_record(2)
+        reps = max(2, args.steps)
+        bdm = {}
+        for _ in range(reps):
+            eng.call_dev("qq_msm_dev", vp(a_d.data_ptr()), vp(pts_d.data_ptr()), ctypes.c_size_t(m),
+                         vp(small.data_ptr()), vp(small.data_ptr() + 64))
+            for k_, v_ in eng.last_kernel_breakdown().items():
+                bdm[k_] = bdm.get(k_, 0.0) + v_ / reps
+        eng.event_record(3)
+        msm_ms = eng.event_elapsed_ms(2, 3) / reps
+        barrier()
+        res = small.cpu().numpy()
+        # correctness at full size: sum a_i h_i * B computed on the host with big ints, one fixed-base mult on the GPU
+        tot = 0
+        ai = [int.from_bytes(a[i].tobytes(), "little") for i in range(0, m)] if m <= (1 << 20) else None
+        if ai is not None:
+            hi_ = [int.from_bytes(hs[i].tobytes(), "little") for i in range(0, m)]
+            tot = sum(x * y for x, y in zip(ai, hi_)) % L
+            exp, _ = eng.fixed_base(0, np.frombuffer(tot.to_bytes(32, "little"), np.uint8))
+            msm_ok = bool((exp[0] == res[:32]).all()) and int(res[64]) == 0
+        else:
+            msm_ok = None
+        msm = {"points": m, "ms": msm_ms, "points_per_sec_per_gpu": m / (msm_ms * 1e-3),
+               "breakdown_ms": bdm, "matches_known_dlog": msm_ok,
+               "imad_frac": m * IMAD_PER_MSM_POINT / (msm_ms * 1e-3) / peak["imad_lo_per_s"]}
+
+    # ---- reduce over ranks ----------------------------------------------------------------------------------------
+    def maxr(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    dev_ms_max, wall_ms_max, e2e_ms_max = maxr(dev_ms), maxr(wall_ms), maxr(e2e_ms)
+    msm_ms_max = maxr(msm["ms"]) if msm else None
+    total_accounts = n * world * args.steps
+    value = total_accounts / (wall_ms_max * 1e-3)
+    e2e_value = total_accounts / (e2e_ms_max * 1e-3)
+
+    # ---- CPU baseline on rank 0 (bounded sample) ------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import c_oracle as C
+        cores = C.threads()
+        m0 = 64 * cores
+        t = time.time()
+        eo, es = C.update_account(acc_h[:m0], bl_h[:m0], u_h[:m0], c_h[:m0])
+        r0 = m0 / (time.time() - t)
+        ms_ = int(max(m0, min(n, r0 * args.cpu_seconds)))
+        t = time.time()
+        eo, es = C.update_account(acc_h[:ms_], bl_h[:ms_], u_h[:ms_], c_h[:ms_])
+        dtc = time.time() - t
+        same_cpu = bool((eo.reshape(-1) == out_pin.numpy()[:ms_ * 128]).all())
+        cpu = {"value": ms_ / dtc, "unit": "accounts/s", "cores": cores, "kind": "port",
+               "sample": "first %d accounts of the same batch, OpenMP over %d host threads; oracle/qq_oracle.c restates "
+                         "curve25519-dalek 3.2.1's algorithms (radix-2^51 field, radix-16 variable-base, table "
+                         "fixed-base); dalek itself cannot be built here" % (ms_, cores),
+               "gpu_output_matches_cpu_on_sample": same_cpu}
+
+    if rank == 0:
+        clocks = sampler.summary()
+        vb_avg_ms = vb_ms / args.steps
+        vb_work = 4 * IMAD_PER_VARBASE * n                       # 4 variable-base mults per account in one launch
+        achieved = vb_work / (vb_avg_ms * 1e-3)
+        step_frac = (IMAD_PER_UPDATE_ACCOUNT * n) / (dev_ms / args.steps * 1e-3) / peak["imad_lo_per_s"]
+        line = {
+            "metric": "account_updates_per_sec", "value": value, "unit": "accounts/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 limbs (radix 2^25.5), 64-bit products", "data": "synthetic",
+            "config": {"workload": "Account::update_account over 2^20 accounts per GPU (BASELINE.json configs[1])"
+                       if n == (1 << 20) else "Account::update_account over %d accounts per GPU" % n,
+                       "accounts_per_gpu": n, "scalars": "uniform 252-bit (worst case)",
+                       "l2": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2; no flush needed" % (n * 352 / 1e6),
+                       "sharding": "independent contiguous account slices per GPU, no data-path collective"},
+            "device_ms_per_step": dev_ms_max / args.steps,
+            "e2e": {"value": e2e_value, "unit": "accounts/s", "h2d_bytes_per_step": n * 224, "d2h_bytes_per_step": n * 129,
+                    "ms_per_step": e2e_ms_max / args.steps, "api": "qq_update_account_batch (host pointers, pinned)",
+                    "matches_device_path": same},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "imad", "kernel": "k_varbase<2> (4 variable-base scalar mults per account)",
+                         "achieved": achieved / 1e12, "peak": peak["imad_lo_per_s"] / 1e12,
+                         "unit": "Tera thread-IMAD/s (32x32->64 product = 2)", "frac": achieved / peak["imad_lo_per_s"],
+                         "peak_source": "measured live by qq_measure_imad_peak (independent mad.lo.u32 chains, all SMs)",
+                         "peak_theoretical": 148 * 64 * 1.965e9 / 1e12,
+                         "whole_step_frac": step_frac, "kernel_ms_per_launch": vb_avg_ms,
+                         "kernel_share_of_step": vb_avg_ms / (dev_ms / args.steps),
+                         "breakdown_ms_per_step": {k_: v_ / args.steps for k_, v_ in breakdown.items()},
+                         "traffic": None,
+                         "hbm": {"algorithmic_bytes_per_step": n * BYTES_PER_UPDATE_ACCOUNT,
+                                 "achieved_GBps": n * BYTES_PER_UPDATE_ACCOUNT / (dev_ms / args.steps * 1e-3) / 1e9,
+                                 "peak_GBps": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+                                 if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0}},
+            "cpu_baseline": cpu,
+        }
+        if msm:
+            msm["points_per_sec"] = msm["points"] * world / (msm_ms_max * 1e-3)
+            msm["note"] = "each GPU runs a full %d-point MSM (weak scaling); compressed input, decompression included" % msm["points"]
+            line["msm"] = msm
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    eng.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--accounts", type=int, default=1 << 20, help="accounts per GPU per step")
+    ap.add_argument("--msm-points", type=int, default=1 << 20)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--ref-seconds-per-step", type=float, default=4.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

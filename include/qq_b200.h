@@ -60,6 +60,10 @@ float qq_last_kernel_ms(const qq_ctx* ctx);
 /* per-kernel-family milliseconds of the most recent call: [0] decompress [1] variable-base [2] fixed-base
  * [3] finish/compress [4] msm-bucket [5] msm-reduce; returns number of entries written */
 int qq_last_kernel_breakdown(const qq_ctx* ctx, float* ms, int cap);
+/* CUDA events on the ctx stream (the stream every kernel of this ctx is launched on), so callers can time a
+ * sequence of _dev calls on the device: record slot a, run, record slot b, read elapsed.  slots 0..7 */
+int qq_event_record(qq_ctx* ctx, int slot);
+int qq_event_elapsed_ms(qq_ctx* ctx, int slot_a, int slot_b, float* ms);
 /* device memory helpers for the _dev entry points (thin cudaMalloc/cudaMemcpy wrappers so callers need no CUDA) */
 int qq_dev_alloc(qq_ctx* ctx, void** dptr, size_t bytes);
 int qq_dev_free(qq_ctx* ctx, void* dptr);
@@ -109,8 +113,9 @@ int qq_verify_account_batch_dev(qq_ctx* ctx, const uint8_t* acc, const uint8_t* 
  * draws them from OsRng inside the function, src/accounts/accounts.rs:203,318-326):
  *   delta_i   = (a_i.pk,  generate_commitment(a_i.pk,  r_i, bl_i))
  *   epsilon_i = (base_pk, generate_commitment(base_pk, r_i, bl_i))           src/accounts/accounts.rs:198-220
- * base_pk must be BASE_PK_BTC_COMPRESSED (B, H) -- the fixed-base tables are built for it; any other 64 bytes make
- * the call fall back to the variable-base kernel for the epsilon half. */
+ * base_pk must be BASE_PK_BTC_COMPRESSED (B, H) = RistrettoPublicKey::generate_base_pk() (src/ristretto/keys.rs:171-177),
+ * the only base key the reference defines; the fixed-base tables are built for it and any other value returns
+ * QQ_ERR_ARG. */
 int qq_delta_epsilon_batch(qq_ctx* ctx, const uint8_t* acc, const uint8_t* bl, const uint8_t* r,
                            const uint8_t* base_pk, uint8_t* out_delta, uint8_t* out_epsilon, uint8_t* status,
                            size_t n);

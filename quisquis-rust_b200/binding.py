@@ -13,7 +13,7 @@ BASE_B, BASE_H = 0, 1
 EXPORTS = [
     "qq_init", "qq_destroy", "qq_last_error", "qq_device_sm_count", "qq_launch_count", "qq_last_kernel_ms",
     "qq_last_kernel_breakdown", "qq_dev_alloc", "qq_dev_free", "qq_dev_upload", "qq_dev_download",
-    "qq_measure_imad_peak",
+    "qq_measure_imad_peak", "qq_event_record", "qq_event_elapsed_ms",
     "qq_update_public_key_batch", "qq_update_public_key_batch_dev", "qq_verify_public_key_update_batch",
     "qq_generate_commitment_batch", "qq_generate_commitment_batch_dev", "qq_add_commitments_batch",
     "qq_mul_commitment_batch", "qq_update_account_batch", "qq_update_account_batch_dev",
@@ -59,6 +59,8 @@ def load_library():
     lib.qq_dev_free.argtypes = [vp, vp]
     lib.qq_dev_upload.argtypes = [vp, vp, vp, sz]
     lib.qq_dev_download.argtypes = [vp, vp, vp, sz]
+    lib.qq_event_record.argtypes = [vp, ctypes.c_int]
+    lib.qq_event_elapsed_ms.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
     lib.qq_measure_imad_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     for name in ("qq_update_public_key_batch", "qq_update_public_key_batch_dev", "qq_mul_commitment_batch"):
         getattr(lib, name).argtypes = [vp, u8p, u8p, u8p, u8p, sz]
@@ -147,6 +149,14 @@ class Engine:
         w, lo = ctypes.c_double(), ctypes.c_double()
         self._ck(self.lib.qq_measure_imad_peak(self.h, ctypes.byref(w), ctypes.byref(lo)), "qq_measure_imad_peak")
         return {"imad_wide_per_s": w.value, "imad_lo_per_s": lo.value}
+
+    def event_record(self, slot):
+        self._ck(self.lib.qq_event_record(self.h, slot), "qq_event_record")
+
+    def event_elapsed_ms(self, a, b):
+        ms = ctypes.c_float()
+        self._ck(self.lib.qq_event_elapsed_ms(self.h, a, b, ctypes.byref(ms)), "qq_event_elapsed_ms")
+        return float(ms.value)
 
     # ---- device memory ---------------------------------------------------------------------------------------
     def dev_alloc(self, nbytes):
@@ -278,6 +288,5 @@ class Engine:
 
     # ---- device-pointer calls (pointers are ints / c_void_p on this engine's GPU) ---------------------------------
     def call_dev(self, name, *args):
-        f = getattr(self.lib, name)
-        conv = [a if isinstance(a, (ctypes.c_void_p,)) or not isinstance(a, int) or a < 4096 else ctypes.c_void_p(a) for a in args]
-        self._ck(f(self.h, *conv), name)
+        """Call a `_dev` entry point; args are ctypes values (c_void_p device pointers, c_size_t counts, ints)."""
+        self._ck(getattr(self.lib, name)(self.h, *args), name)

@@ -288,7 +288,7 @@ QQ_HD void fe_cneg(fe& h, u32 b) {
 }
 QQ_HD void fe_abs(fe& h) { fe_cneg(h, fe_isnegative(h)); }
 
-// ---- constants (values verified against oracle/ristretto_ref.py by tests/test_host_arith.py) ----
+// ---- constants (generated by tools/gen_consts.py; checked numerically by tests/test_host_arith.py) ----
 #define QQ_FE_CONST(name, a0, a1, a2, a3, a4, a5, a6, a7, a8, a9) \
     QQ_HD fe name() {                                             \
         fe r = {{a0, a1, a2, a3, a4, a5, a6, a7, a8, a9}};        \

@@ -22,6 +22,9 @@ struct qq_ctx {
     cudaStream_t stream = nullptr;
     char* ws = nullptr;
     size_t ws_cap = 0, ws_off = 0;
+    char* io = nullptr;      // staging slab for the host-pointer entry points (grow-only)
+    size_t io_cap = 0;
+    cudaEvent_t user_ev[8] = {nullptr};
     u32* fb_tbl[2] = {nullptr, nullptr};
     uint8_t base_pk[64];
     uint64_t launches = 0;
@@ -295,6 +298,9 @@ extern "C" void qq_destroy(qq_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->io) cudaFree(ctx->io);
+    for (int i = 0; i < 8; i++)
+        if (ctx->user_ev[i]) cudaEventDestroy(ctx->user_ev[i]);
     for (int b = 0; b < 2; b++)
         if (ctx->fb_tbl[b]) cudaFree(ctx->fb_tbl[b]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -334,6 +340,21 @@ extern "C" int qq_dev_download(qq_ctx* ctx, void* host, const void* dptr, size_t
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return QQ_OK;
+}
+extern "C" int qq_event_record(qq_ctx* ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= 8) return QQ_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->user_ev[slot]) CK(cudaEventCreate(&ctx->user_ev[slot]));
+    CK(cudaEventRecord(ctx->user_ev[slot], ctx->stream));
+    return QQ_OK;
+}
+extern "C" int qq_event_elapsed_ms(qq_ctx* ctx, int slot_a, int slot_b, float* ms) {
+    if (!ctx || !ms || slot_a < 0 || slot_a >= 8 || slot_b < 0 || slot_b >= 8) return QQ_ERR_ARG;
+    if (!ctx->user_ev[slot_a] || !ctx->user_ev[slot_b]) return QQ_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(ctx->user_ev[slot_b]));
+    CK(cudaEventElapsedTime(ms, ctx->user_ev[slot_a], ctx->user_ev[slot_b]));
     return QQ_OK;
 }
 extern "C" int qq_measure_imad_peak(qq_ctx* ctx, double* wide_ops_per_s, double* lo_ops_per_s) {
@@ -608,26 +629,45 @@ static int core_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* po
 // exported entry points: _dev variants call the cores directly, host variants stage through the workspace tail
 // =================================================================================================================
 struct stage {
-    std::vector<void*> dptr;
+    // Device staging for the host-pointer entry points, carved from a grow-only slab owned by the ctx.
+    // plan() must be called once with every buffer size before in()/outbuf().
     qq_ctx* ctx;
+    size_t off = 0;
     explicit stage(qq_ctx* c) : ctx(c) {}
-    ~stage() {
-        for (void* p : dptr) cudaFree(p);
+    int plan(std::initializer_list<size_t> sizes) {
+        size_t total = 0;
+        for (size_t b : sizes) total += align_up(b ? b : 16, 256);
+        if (total > ctx->io_cap) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (ctx->io) CK(cudaFree(ctx->io));
+            ctx->io = nullptr;
+            ctx->io_cap = 0;
+            CK(cudaMalloc((void**)&ctx->io, total));
+            ctx->io_cap = total;
+        }
+        off = 0;
+        return QQ_OK;
+    }
+    uint8_t* take(size_t bytes) {
+        uint8_t* p = (uint8_t*)ctx->io + off;
+        off += align_up(bytes ? bytes : 16, 256);
+        return p;
     }
     int in(const void* host, size_t bytes, uint8_t** out) {
-        void* d = nullptr;
-        CK(cudaMalloc(&d, bytes ? bytes : 16));
-        dptr.push_back(d);
+        if (off + align_up(bytes ? bytes : 16, 256) > ctx->io_cap) CKQ(grow(bytes));
+        uint8_t* d = take(bytes);
         if (bytes) CK(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
-        *out = (uint8_t*)d;
+        *out = d;
         return QQ_OK;
     }
     int outbuf(size_t bytes, uint8_t** out) {
-        void* d = nullptr;
-        CK(cudaMalloc(&d, bytes ? bytes : 16));
-        dptr.push_back(d);
-        *out = (uint8_t*)d;
+        if (off + align_up(bytes ? bytes : 16, 256) > ctx->io_cap) CKQ(grow(bytes));
+        *out = take(bytes);
         return QQ_OK;
+    }
+    int grow(size_t) {
+        ctx->err = "internal: staging plan too small";
+        return QQ_ERR_ARG;
     }
     int back(void* host, const void* dev, size_t bytes) {
         if (bytes) CK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -652,6 +692,7 @@ extern "C" int qq_update_public_key_batch(qq_ctx* ctx, const uint8_t* pk, const 
     ENTER();
     REQUIRE(pk && r && out_pk && status);
     stage st(ctx);
+    CKQ(st.plan({(size_t)(n * 64), (size_t)(n * 32), (size_t)(n * 64), (size_t)(n)}));
     uint8_t *dpk, *dr, *dout, *dst;
     CKQ(st.in(pk, n * 64, &dpk));
     CKQ(st.in(r, n * 32, &dr));
@@ -671,6 +712,7 @@ extern "C" int qq_verify_public_key_update_batch(qq_ctx* ctx, const uint8_t* upd
     ENTER();
     REQUIRE(updated_pk && pk && r && status);
     stage st(ctx);
+    CKQ(st.plan({(size_t)(n * 64), (size_t)(n * 64), (size_t)(n * 32), (size_t)(n)}));
     uint8_t *du, *dpk, *dr, *dst;
     CKQ(st.in(updated_pk, n * 64, &du));
     CKQ(st.in(pk, n * 64, &dpk));
@@ -692,6 +734,7 @@ extern "C" int qq_generate_commitment_batch(qq_ctx* ctx, const uint8_t* pk, cons
     ENTER();
     REQUIRE(pk && r && v && out_comm && status);
     stage st(ctx);
+    CKQ(st.plan({(size_t)(n * 64), (size_t)(n * 32), (size_t)(n * 32), (size_t)(n * 64), (size_t)(n)}));
     uint8_t *dpk, *dr, *dv, *dout, *dst;
     CKQ(st.in(pk, n * 64, &dpk));
     CKQ(st.in(r, n * 32, &dr));
@@ -708,6 +751,7 @@ extern "C" int qq_add_commitments_batch(qq_ctx* ctx, const uint8_t* a, const uin
     ENTER();
     REQUIRE(a && b && out_comm && status);
     stage st(ctx);
+    CKQ(st.plan({(size_t)(n * 64), (size_t)(n * 64), (size_t)(n * 64), (size_t)(n)}));
     uint8_t *da, *db, *dout, *dst;
     CKQ(st.in(a, n * 64, &da));
     CKQ(st.in(b, n * 64, &db));
@@ -730,6 +774,7 @@ extern "C" int qq_update_account_batch(qq_ctx* ctx, const uint8_t* acc, const ui
     ENTER();
     REQUIRE(acc && bl && u && c && out_acc && status);
     stage st(ctx);
+    CKQ(st.plan({(size_t)(n * 128), (size_t)(n * 32), (size_t)(n * 32), (size_t)(n * 32), (size_t)(n * 128), (size_t)(n)}));
     uint8_t *dacc, *dbl, *du, *dc, *dout, *dst;
     CKQ(st.in(acc, n * 128, &dacc));
     CKQ(st.in(bl, n * 32, &dbl));
@@ -754,6 +799,7 @@ extern "C" int qq_verify_account_batch(qq_ctx* ctx, const uint8_t* acc, const ui
     ENTER();
     REQUIRE(acc && sk && bl && status);
     stage st(ctx);
+    CKQ(st.plan({(size_t)(n * 128), (size_t)(n * 32), (size_t)(n * 32), (size_t)(n)}));
     uint8_t *dacc, *dsk, *dbl, *dst;
     CKQ(st.in(acc, n * 128, &dacc));
     CKQ(st.in(sk, n * 32, &dsk));
@@ -773,6 +819,7 @@ extern "C" int qq_delta_epsilon_batch(qq_ctx* ctx, const uint8_t* acc, const uin
         return QQ_ERR_ARG;
     }
     stage st(ctx);
+    CKQ(st.plan({(size_t)(n * 128), (size_t)(n * 32), (size_t)(n * 32), (size_t)(n * 128), (size_t)(n * 128), (size_t)(n)}));
     uint8_t *dacc, *dbl, *dr, *dd, *de, *dst;
     CKQ(st.in(acc, n * 128, &dacc));
     CKQ(st.in(bl, n * 32, &dbl));
@@ -798,6 +845,7 @@ extern "C" int qq_fixed_base_batch(qq_ctx* ctx, int which, const uint8_t* s, uin
     ENTER();
     REQUIRE((which == 0 || which == 1) && s && out_points && status);
     stage st(ctx);
+    CKQ(st.plan({(size_t)(n * 32), (size_t)(n * 32), (size_t)(n)}));
     uint8_t *ds, *dout, *dst;
     CKQ(st.in(s, n * 32, &ds));
     CKQ(st.outbuf(n * 32, &dout));

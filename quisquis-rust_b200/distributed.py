@@ -1,0 +1,53 @@
+"""Multi-GPU plumbing: one process per GPU (torch.distributed, NCCL over NVLink on the GPU box, gloo in CPU tests).
+
+Account batches and segmented MSMs shard into independent contiguous slices -- no data-path collective.
+One large MSM has a single exchange step: every rank's partial sum (extended point, 4 x 32 canonical bytes = 128 B)
+is all-gathered and the ranks' points are added (Edwards addition is not an NCCL reduce op, so
+"all-reduce-to-root" = all-gather of 128 B + a local sum).  SURVEY.md section 8e.
+"""
+import numpy as np
+
+
+def shard_range(n, rank, world):
+    """Contiguous slice [lo, hi) of n items owned by `rank`."""
+    lo = n * rank // world
+    hi = n * (rank + 1) // world
+    return lo, hi
+
+
+def gather_partials(partial_xyzt, status, device=None):
+    """All-gather the 128-byte partial sums and the per-rank status byte.  Returns (world x 128 uint8, world uint8)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    buf = np.zeros(132, np.uint8)
+    buf[:128] = np.asarray(partial_xyzt, dtype=np.uint8).reshape(-1)
+    buf[128] = int(status)
+    if world == 1:
+        return buf[:128].reshape(1, 128).copy(), buf[128:129].copy()
+    t = torch.from_numpy(buf)
+    if device is not None:
+        t = t.to(device)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    allb = torch.stack(out).cpu().numpy()
+    return allb[:, :128].copy(), allb[:, 128].copy()
+
+
+def msm_sharded(partial_fn, sum_fn, scalars, points, device=None):
+    """Large MSM across ranks.  `partial_fn(scalars, points) -> (xyzt 128 B, status)` runs on this rank's slice,
+    `sum_fn(k x 128 B) -> (32 B compressed, is_identity)` adds the gathered partial sums.
+    Every rank returns the same (compressed point, status)."""
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    scalars = np.asarray(scalars, dtype=np.uint8).reshape(-1, 32)
+    points = np.asarray(points, dtype=np.uint8).reshape(-1, 32)
+    lo, hi = shard_range(scalars.shape[0], rank, world)
+    part, st = partial_fn(scalars[lo:hi], points[lo:hi])
+    parts, sts = gather_partials(part, st, device)
+    bad = [int(s) for s in sts if s]
+    if bad:
+        return np.zeros(32, np.uint8), bad[0]   # lowest rank = earliest slice = first failing term
+    out, ident = sum_fn(parts.reshape(-1))
+    return out, 0

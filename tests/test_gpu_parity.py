@@ -289,3 +289,105 @@ def test_reference_interface_mirror(engine, pkg):
     assert not pkg.Account.verify_account_update(updated[::-1], accs, us, cs)
     with pytest.raises(api.PanicError):
         pkg.Account.verify_account_update(updated[:8], accs[:8], us[:8], cs[:8])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# larger batches: the C restatement (oracle/qq_oracle.c) is the checker
+# ---------------------------------------------------------------------------------------------------------------------
+def _rand_scalars(rng, n):
+    raw = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    raw[:, 31] &= 0x0f
+    return raw
+
+
+@pytest.mark.parametrize("n", [256, 1000, 4096, 20000])
+def test_msm_pippenger_vs_c_oracle(engine, n):
+    import c_oracle as C
+    rng = np.random.default_rng(n)
+    pts, _ = engine.fixed_base(0, _rand_scalars(rng, n))
+    sc = _rand_scalars(rng, n)
+    # protocol-like mix: a quarter of the scalars are small (64-bit balances), a few are 0 / 1 / l-1
+    sc[::4, 8:] = 0
+    sc[1] = 0
+    sc[2] = np.frombuffer(sb(1), np.uint8)
+    sc[3] = np.frombuffer(sb(R.L - 1), np.uint8)
+    o, s = engine.msm(sc, pts)
+    eo, es = C.msm(sc, pts)
+    assert s == es == 0 and o.tobytes() == eo.tobytes()
+    # a bad point anywhere -> None (status 1), first failure decides
+    pts2 = pts.copy()
+    pts2[n // 2] = np.frombuffer(invalid_encodings()[0][1], np.uint8)
+    sc2 = sc.copy()
+    sc2[n - 1] = np.frombuffer(R.L.to_bytes(32, "little"), np.uint8)
+    o, s = engine.msm(sc2, pts2)
+    eo, es = C.msm(sc2, pts2)
+    assert s == es == 1 and o.tobytes() == bytes(32)
+
+
+def test_msm_all_points_in_one_bucket(engine):
+    """Adversarial distribution for the bucket kernel: identical scalars."""
+    import c_oracle as C
+    rng = np.random.default_rng(99)
+    n = 3000
+    pts, _ = engine.fixed_base(0, _rand_scalars(rng, n))
+    sc = np.tile(_rand_scalars(rng, 1), (n, 1))
+    o, s = engine.msm(sc, pts)
+    eo, es = C.msm(sc, pts)
+    assert s == es == 0 and o.tobytes() == eo.tobytes()
+
+
+def test_update_account_16k_vs_c_oracle(engine):
+    import c_oracle as C
+    rng = np.random.default_rng(2024)
+    n = 1 << 14
+    cols = [engine.fixed_base(0, _rand_scalars(rng, n))[0] for _ in range(4)]
+    acc = np.concatenate(cols, axis=1).copy()
+    bl, u, c = _rand_scalars(rng, n), _rand_scalars(rng, n), _rand_scalars(rng, n)
+    bl[::3, 8:] = 0       # protocol-like small balances
+    bl[1::9] = 0          # bl = 0 as in Shuffle::input_shuffle
+    out, st = engine.update_account(acc, bl, u, c)
+    eout, est = C.update_account(acc, bl, u, c)
+    assert (st == est).all() and not st.any()
+    assert (out == eout).all()
+    vs = engine.verify_account(acc, u, bl)
+    assert (vs == C.verify_account(acc, u, bl)).all()
+    gc, gs = engine.generate_commitment(acc[:, :64].copy(), u, bl)
+    egc, egs = C.generate_commitment(acc[:, :64].copy(), u, bl)
+    assert (gc == egc).all() and (gs == egs).all()
+    d, e, ds = engine.delta_epsilon(acc[:4096], bl[:4096], u[:4096], np.frombuffer(R.BASE_PK, np.uint8))
+    ed, ee, eds = C.delta_epsilon(acc[:4096], bl[:4096], u[:4096], np.frombuffer(R.BASE_PK, np.uint8))
+    assert (d == ed).all() and (e == ee).all() and (ds == eds).all()
+
+
+def test_update_account_properties_at_scale(engine):
+    """Size-independent property at 2^17: updating with (bl, u, c) then with (-bl, u^-1, -c*u^-1 ... ) is checked
+    through linearity instead: update(acc, bl1+bl2, u, c1+c2).comm == update(update(acc, bl1, 1, c1), bl2, u, c2).comm
+    and pk' depends only on u."""
+    rng = np.random.default_rng(7)
+    n = 1 << 17
+    cols = [engine.fixed_base(0, _rand_scalars(rng, n))[0] for _ in range(4)]
+    acc = np.concatenate(cols, axis=1).copy()
+    one = np.tile(np.frombuffer(sb(1), np.uint8), (n, 1))
+    bl1, bl2, c1, c2, u = (_rand_scalars(rng, n) for _ in range(5))
+    bl1[:, 16:] = 0
+    bl2[:, 16:] = 0
+    c1[:, 31] &= 0x07
+    c2[:, 31] &= 0x07
+
+    def add_scalars(a, b):  # both < 2^251 -> sum < 2^252 < l, plain 256-bit addition
+        x = a.astype(np.uint16).reshape(n, 32) + b.reshape(n, 32)
+        out = np.zeros((n, 32), np.uint8)
+        carry = np.zeros(n, np.uint16)
+        for j in range(32):
+            t = x[:, j] + carry
+            out[:, j] = t & 0xff
+            carry = t >> 8
+        return out
+    a1, s1 = engine.update_account(acc, bl1, one, c1)
+    a2, s2 = engine.update_account(a1, bl2, u, c2)
+    a3, s3 = engine.update_account(acc, add_scalars(bl1, bl2), u, add_scalars(c1, c2))
+    assert not s1.any() and not s2.any() and not s3.any()
+    assert (a1[:, :64] == acc[:, :64]).all()          # u = 1 leaves the key unchanged
+    assert (a2[:, :64] == a3[:, :64]).all()           # pk' = u * pk either way
+    # commitments: second update of a2 used pk (unchanged by u = 1), so both routes give the same commitment
+    assert (a2[:, 64:] == a3[:, 64:]).all()

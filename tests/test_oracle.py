@@ -1,0 +1,143 @@
+"""CPU tests (no GPU): pin the oracle.  (1) RFC 9496 Appendix A vectors, (2) the reference's only fixed point bytes
+BASE_PK_BTC_COMPRESSED (src/ristretto/constants.rs:12-21), (3) libsodium 1.0.20 as an independent implementation,
+(4) the C restatement (oracle/qq_oracle.c) against the big-int restatement on every batch entry point."""
+import ctypes
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+import c_oracle as C
+import ristretto_ref as R
+from qq_testlib import Stream, cat, invalid_encodings, make_account, sb
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "rfc9496.json")))
+
+
+def _sodium():
+    cands = glob.glob("/opt/prime-rl/.venv/lib/python3.12/site-packages/pyzmq.libs/libsodium*.so*")
+    if not cands:
+        return None
+    try:
+        return ctypes.CDLL(cands[0])
+    except OSError:
+        return None
+
+
+def test_rfc9496_generator_multiples():
+    for i, h in enumerate(GOLD["multiples_of_generator"]):
+        assert R.compress(R.mul(i, R.BASEPOINT)).hex() == h
+        out, st = C.fixed_base(0, np.frombuffer(sb(i), np.uint8))
+        assert st[0] == 0 and out[0].tobytes().hex() == h
+
+
+def test_rfc9496_invalid_encodings():
+    for h in GOLD["invalid_encodings"]:
+        assert R.decompress(bytes.fromhex(h)) is None
+        assert C.lib().oq_decompress_check(bytes.fromhex(h)) == 0
+    for name, enc in invalid_encodings():
+        assert R.decompress(enc) is None, name
+        assert C.lib().oq_decompress_check(enc) == 0, name
+    names = {n for n, _ in invalid_encodings()}
+    assert {"non_square", "negative_t", "negative_s", "bit255_set", "non_canonical_p"} <= names
+
+
+def test_reference_base_pk_constants():
+    """src/ristretto/constants.rs:12-21: [0] = enc(B), [1] = from_uniform_bytes(SHA3-512(enc(B))) = Pedersen H."""
+    assert R.BASEPOINT_COMPRESSED.hex() == GOLD["base_pk_btc_compressed"][0] == bytes(
+        [226, 242, 174, 10, 106, 188, 78, 113, 168, 132, 169, 97, 197, 0, 81, 95, 88, 227, 11, 106, 165, 130, 221, 141,
+         182, 166, 89, 69, 224, 141, 45, 118]).hex()
+    assert R.PEDERSEN_H_COMPRESSED.hex() == GOLD["base_pk_btc_compressed"][1] == bytes(
+        [140, 146, 64, 180, 86, 169, 230, 220, 101, 195, 119, 161, 4, 141, 116, 95, 148, 160, 140, 219, 127, 68, 203, 205,
+         123, 70, 243, 64, 72, 135, 17, 52]).hex()
+
+
+def test_against_libsodium():
+    so = _sodium()
+    if so is None:
+        pytest.skip("libsodium not present in this image")
+    st = Stream(b"sodium")
+    for i in range(60):
+        k, k2 = st.scalar(), st.scalar()
+        o1, o2, o3 = (ctypes.create_string_buffer(32) for _ in range(3))
+        assert so.crypto_scalarmult_ristretto255_base(o1, sb(k)) == 0
+        assert o1.raw == R.compress(R.mul(k, R.BASEPOINT))
+        assert so.crypto_scalarmult_ristretto255(o2, sb(k2), o1.raw) == 0
+        assert o2.raw == R.compress(R.mul(k2, R.decompress(o1.raw)))
+        assert so.crypto_core_ristretto255_add(o3, o1.raw, o2.raw) == 0
+        assert o3.raw == R.compress(R.add(R.decompress(o1.raw), R.decompress(o2.raw)))
+        u = st.bytes(64)
+        assert so.crypto_core_ristretto255_from_hash(o3, u) == 0
+        assert o3.raw == R.compress(R.from_uniform_bytes(u))
+    rng = np.random.default_rng(5)
+    for i in range(1500):
+        b = bytearray(rng.bytes(32))
+        if i % 2:
+            b[31] &= 0x7f
+            b[0] &= 0xfe
+        assert (so.crypto_core_ristretto255_is_valid_point(bytes(b)) == 1) == (R.decompress(bytes(b)) is not None)
+
+
+def test_c_oracle_matches_bigint_account_ops():
+    st = Stream(b"c-vs-py")
+    n = 40
+    accs, sks, bls, us, cs = [], [], [], [], []
+    for i in range(n):
+        a, sk, _ = make_account(st, i % 5)
+        accs.append(a), sks.append(sb(sk)), bls.append(sb(st.scalar() % 2**40))
+        us.append(st.scalar_bytes()), cs.append(st.scalar_bytes())
+    bad = invalid_encodings()
+    for j, (name, enc) in enumerate(bad):
+        a = bytearray(accs[j])
+        a[32 * (j % 4):32 * (j % 4) + 32] = enc
+        accs[j] = bytes(a)
+    us[n - 1] = R.L.to_bytes(32, "little")
+    A, BL, U, CC, SK = cat(accs), cat(bls), cat(us), cat(cs), cat(sks)
+    out, stt = C.update_account(A, BL, U, CC)
+    vst = C.verify_account(A, SK, cat([sb(i % 5) for i in range(n)]))
+    pk, pst = C.update_public_key(A.reshape(n, 128)[:, :64].copy(), U)
+    gc, gst = C.generate_commitment(A.reshape(n, 128)[:, :64].copy(), CC, BL)
+    d, e, dst = C.delta_epsilon(A, BL, CC, np.frombuffer(R.BASE_PK, np.uint8))
+    for i in range(n):
+        exp, es = R.update_account(accs[i], bls[i], us[i], cs[i])
+        assert stt[i] == es and out[i].tobytes() == exp, i
+        assert vst[i] == R.verify_account(accs[i], sks[i], sb(i % 5)), i
+        exp, es = R.update_public_key(accs[i][:64], us[i])
+        assert pst[i] == es and pk[i].tobytes() == exp, i
+        exp, es = R.generate_commitment(accs[i][:64], cs[i], bls[i])
+        assert gst[i] == es and gc[i].tobytes() == exp, i
+        ed, ee, es = R.delta_epsilon(accs[i], bls[i], cs[i])
+        assert dst[i] == es and d[i].tobytes() == ed and e[i].tobytes() == ee, i
+
+
+def test_c_oracle_msm_straus_and_pippenger():
+    st = Stream(b"c-msm")
+    for n in (0, 1, 2, 3, 9, 189, 190, 520, 810):
+        hs = [st.scalar() for _ in range(n)]
+        a = [st.scalar() for _ in range(n)]
+        pts, _ = C.fixed_base(0, cat([sb(h) for h in hs])) if n else (np.zeros((0, 32), np.uint8), None)
+        out, s = C.msm(cat([sb(x) for x in a]) if n else np.zeros(0, np.uint8), pts)
+        tot = sum(x * h for x, h in zip(a, hs)) % R.L
+        assert s == 0 and out.tobytes() == R.compress(R.mul(tot, R.BASEPOINT)), n
+    # first failing term decides the status; output zero
+    pts2 = pts.copy()
+    pts2[5] = np.frombuffer(invalid_encodings()[0][1], np.uint8)
+    out, s = C.msm(cat([sb(x) for x in a]), pts2)
+    assert s == 1 and out.tobytes() == bytes(32)
+
+
+def test_quirks_of_the_reference_are_kept():
+    st = Stream(b"quirks")
+    acc, sk, k = make_account(st, 3)
+    # update_account commits under the OLD public key (src/accounts/accounts.rs:149-151)
+    bl, u, c = sb(4), st.scalar_bytes(), st.scalar_bytes()
+    out, s = R.update_account(acc, bl, u, c)
+    new_comm, _ = R.generate_commitment(acc[:64], c, bl)
+    exp_comm, _ = R.add_commitments(new_comm, acc[64:])
+    assert out[64:] == exp_comm
+    assert R.verify_account(out, sb(sk), sb(7)) == 0
+    # identity encodes as 32 zero bytes (dalek), e.g. a - a
+    z, s = R.sub_commitments(acc[64:], acc[64:])
+    assert z == bytes(64) and s == 0
