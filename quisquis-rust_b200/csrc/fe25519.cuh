@@ -122,7 +122,7 @@ QQ_HD void fe_reduce64(fe& h, u64 t[10]) {
 }
 
 // h = f * g.  Preconditions: 19*g.v[j] < 2^32 for all j (g <= 3.3T); see header for magnitude budget.
-QQ_HD void fe_mul(fe& h, const fe& f, const fe& g) {
+QQ_HD void fe_mul_inl(fe& h, const fe& f, const fe& g) {
     u32 g19[10], f2[10];
 #pragma unroll
     for (int i = 1; i < 10; i++) g19[i] = g.v[i] * 19u;
@@ -148,7 +148,7 @@ QQ_HD void fe_mul(fe& h, const fe& f, const fe& g) {
 }
 
 // h = f^2.  Precondition: 19*f.v[j] < 2^32 (f <= 3.3T).
-QQ_HD void fe_sq(fe& h, const fe& f) {
+QQ_HD void fe_sq_inl(fe& h, const fe& f) {
     u32 f2[10], f4[10], f19[10];
 #pragma unroll
     for (int i = 0; i < 10; i++) {
@@ -177,6 +177,37 @@ QQ_HD void fe_sq(fe& h, const fe& f) {
         t[k] = acc;
     }
     fe_reduce64(h, t);
+}
+
+// Out-of-line copies for the device build: the big kernels call fe_mul / fe_sq thousands of times per thread, and
+// inlining every call produced 150-370 KB of straight-line SASS per kernel (instruction-cache misses showed up as
+// `no_instruction` stalls in ncu).  Arguments and result travel in registers (by-value ABI), so a call costs only
+// CALL + RET + a few moves.  Define QQ_INLINE_FIELD_OPS to get the fully inlined code back.
+#if defined(__CUDACC__) && !defined(QQ_INLINE_FIELD_OPS)
+static __device__ __noinline__ fe fe_mul_ool(fe f, fe g) {
+    fe h;
+    fe_mul_inl(h, f, g);
+    return h;
+}
+static __device__ __noinline__ fe fe_sq_ool(fe f) {
+    fe h;
+    fe_sq_inl(h, f);
+    return h;
+}
+#endif
+QQ_HD void fe_mul(fe& h, const fe& f, const fe& g) {
+#if defined(__CUDA_ARCH__) && !defined(QQ_INLINE_FIELD_OPS)
+    h = fe_mul_ool(f, g);
+#else
+    fe_mul_inl(h, f, g);
+#endif
+}
+QQ_HD void fe_sq(fe& h, const fe& f) {
+#if defined(__CUDA_ARCH__) && !defined(QQ_INLINE_FIELD_OPS)
+    h = fe_sq_ool(f);
+#else
+    fe_sq_inl(h, f);
+#endif
 }
 
 QQ_HD void fe_sqn(fe& h, const fe& f, int n) {

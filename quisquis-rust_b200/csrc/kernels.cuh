@@ -65,8 +65,10 @@ struct vb_args {
     u32x4* scratch;
     size_t n;
 };
+// 2 blocks/SM (<= 255 regs) measured faster than 3 or 4 (tools/vb_bench.cu): the kernel is FMA-pipe bound, not
+// latency bound, and a tighter register cap only adds moves.
 template <int NS>
-__global__ void __launch_bounds__(128) k_varbase(vb_args a) {
+__global__ void __launch_bounds__(128, 2) k_varbase(vb_args a) {
     size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     u32x4* tbl = a.scratch + gtid * (QQ_VB_ENTRIES * 10);

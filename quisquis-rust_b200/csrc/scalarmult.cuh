@@ -77,19 +77,27 @@ QQ_HD void vb_build_table(u32x4* tbl, const ge_p3& p) {
 }
 
 // r = s * P using a table built by vb_build_table.  s: 8 little-endian words, s < 2^253.
-QQ_HD void vb_scalarmult(ge_p3& r, const u32x4* tbl, const u32 s[8]) {
+// ROLLED keeps one copy of the doubling body (smaller instruction footprint; T is computed by every doubling).
+template <bool ROLLED>
+QQ_HD void vb_scalarmult_t(ge_p3& r, const u32x4* tbl, const u32 s[8]) {
     u32 rr[9];
     sc_recode_bias<4, 64>(rr, s);        // rr[8] == 0 for s < 2^253
     u32 w[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) w[i] = rr[i];
     ge_identity(r);
+#pragma unroll 1
     for (int k = 63; k >= 0; k--) {
         if (k != 63) {
-            ge_dbl<false>(r, r);
-            ge_dbl<false>(r, r);
-            ge_dbl<false>(r, r);
-            ge_dbl<true>(r, r);
+            if (ROLLED) {
+#pragma unroll 1
+                for (int d = 0; d < 4; d++) ge_dbl<true>(r, r);
+            } else {
+                ge_dbl<false>(r, r);
+                ge_dbl<false>(r, r);
+                ge_dbl<false>(r, r);
+                ge_dbl<true>(r, r);
+            }
         }
         int d = (int)(w[7] >> 28) - 8;    // signed digit in [-8, 8)
         // shift the 256-bit register left by one nibble
@@ -104,6 +112,7 @@ QQ_HD void vb_scalarmult(ge_p3& r, const u32x4* tbl, const u32 s[8]) {
         ge_add(r, r, c);
     }
 }
+QQ_HD void vb_scalarmult(ge_p3& r, const u32x4* tbl, const u32 s[8]) { vb_scalarmult_t<false>(r, tbl, s); }
 
 // ---------------------------------------------------------------------------------------------------------
 // Fixed-base tables.  Layout: entry (k, j) at tbl[(k * (2^(W-1) + 1) + j) * 30 .. +30] words:

@@ -1,0 +1,64 @@
+//! Raw + safe bindings of libqq_b200.so (include/qq_b200.h).  NOT BUILT IN THIS ENVIRONMENT (no cargo/rustc).
+//! All `unsafe` lives here so that quisquislib can keep `#![deny(unsafe_code)]` (reference src/lib.rs:4).
+use std::os::raw::{c_char, c_int};
+
+#[repr(C)]
+pub struct QqCtx {
+    _private: [u8; 0],
+}
+
+extern "C" {
+    pub fn qq_init(ctx: *mut *mut QqCtx, device: c_int) -> c_int;
+    pub fn qq_destroy(ctx: *mut QqCtx);
+    pub fn qq_last_error(ctx: *const QqCtx) -> *const c_char;
+    pub fn qq_update_public_key_batch(ctx: *mut QqCtx, pk: *const u8, r: *const u8, out_pk: *mut u8, status: *mut u8, n: usize) -> c_int;
+    pub fn qq_verify_public_key_update_batch(ctx: *mut QqCtx, upd: *const u8, pk: *const u8, r: *const u8, status: *mut u8, n: usize) -> c_int;
+    pub fn qq_generate_commitment_batch(ctx: *mut QqCtx, pk: *const u8, r: *const u8, v: *const u8, out: *mut u8, status: *mut u8, n: usize) -> c_int;
+    pub fn qq_add_commitments_batch(ctx: *mut QqCtx, a: *const u8, b: *const u8, negate_b: c_int, out: *mut u8, status: *mut u8, n: usize) -> c_int;
+    pub fn qq_mul_commitment_batch(ctx: *mut QqCtx, comm: *const u8, s: *const u8, out: *mut u8, status: *mut u8, n: usize) -> c_int;
+    pub fn qq_update_account_batch(ctx: *mut QqCtx, acc: *const u8, bl: *const u8, u: *const u8, c: *const u8, out: *mut u8, status: *mut u8, n: usize) -> c_int;
+    pub fn qq_verify_account_batch(ctx: *mut QqCtx, acc: *const u8, sk: *const u8, bl: *const u8, status: *mut u8, n: usize) -> c_int;
+    pub fn qq_delta_epsilon_batch(ctx: *mut QqCtx, acc: *const u8, bl: *const u8, r: *const u8, base_pk: *const u8, delta: *mut u8, eps: *mut u8, status: *mut u8, n: usize) -> c_int;
+    pub fn qq_delta_identity_check(ctx: *mut QqCtx, acc: *const u8, n: usize, verdict: *mut u8) -> c_int;
+    pub fn qq_fixed_base_batch(ctx: *mut QqCtx, which: c_int, s: *const u8, out: *mut u8, status: *mut u8, n: usize) -> c_int;
+    pub fn qq_msm(ctx: *mut QqCtx, scalars: *const u8, points: *const u8, n: usize, out: *mut u8, status: *mut u8) -> c_int;
+    pub fn qq_msm_partial(ctx: *mut QqCtx, scalars: *const u8, points: *const u8, n: usize, out_xyzt: *mut u8, status: *mut u8) -> c_int;
+    pub fn qq_points_sum(ctx: *mut QqCtx, xyzt: *const u8, k: usize, out: *mut u8, is_identity: *mut u8) -> c_int;
+    pub fn qq_msm_segmented(ctx: *mut QqCtx, scalars: *const u8, points: *const u8, offsets: *const u32, m: usize, out: *mut u8, status: *mut u8) -> c_int;
+}
+
+pub const ST_BAD_POINT: u8 = 1;
+
+/// Owning handle of one GPU context.
+pub struct Gpu(*mut QqCtx);
+
+impl Gpu {
+    pub fn new(device: i32) -> Result<Gpu, i32> {
+        let mut p: *mut QqCtx = std::ptr::null_mut();
+        let rc = unsafe { qq_init(&mut p, device) };
+        if rc == 0 { Ok(Gpu(p)) } else { Err(rc) }
+    }
+    /// `Account::update_account` over n accounts (128 B each); panics where the reference's `.unwrap()` would.
+    pub fn update_account(&self, acc: &[u8], bl: &[u8], u: &[u8], c: &[u8]) -> Vec<u8> {
+        let n = bl.len() / 32;
+        assert!(acc.len() == n * 128 && u.len() == n * 32 && c.len() == n * 32);
+        let mut out = vec![0u8; n * 128];
+        let mut st = vec![0u8; n];
+        let rc = unsafe { qq_update_account_batch(self.0, acc.as_ptr(), bl.as_ptr(), u.as_ptr(), c.as_ptr(), out.as_mut_ptr(), st.as_mut_ptr(), n) };
+        assert_eq!(rc, 0, "qq_update_account_batch failed");
+        if st.iter().any(|&s| s == ST_BAD_POINT) { panic!("called `Option::unwrap()` on a `None` value"); }
+        out
+    }
+    /// `Verifier::multiscalar_multiplication`: None if any point fails to decompress.
+    pub fn msm(&self, scalars: &[u8], points: &[u8]) -> Option<[u8; 32]> {
+        let n = scalars.len() / 32;
+        assert!(points.len() == n * 32);
+        let (mut out, mut st) = ([0u8; 32], 0u8);
+        let rc = unsafe { qq_msm(self.0, scalars.as_ptr(), points.as_ptr(), n, out.as_mut_ptr(), &mut st) };
+        assert_eq!(rc, 0, "qq_msm failed");
+        if st == 0 { Some(out) } else { None }
+    }
+}
+impl Drop for Gpu {
+    fn drop(&mut self) { unsafe { qq_destroy(self.0) } }
+}

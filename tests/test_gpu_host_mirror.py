@@ -1,0 +1,32 @@
+"""GPU test: the C++ host mirror of the reference interface (quisquis-rust_b200/host/quisquis.hpp) compiled against
+libqq_b200.so and run on fixtures whose expected bytes come from the oracle."""
+import os
+import subprocess
+
+import pytest
+
+import ristretto_ref as R
+from qq_testlib import Stream, make_account, sb
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cpp_host_mirror(tmp_path, pkg):
+    st = Stream(b"cpp-mirror")
+    rec = b""
+    for i in range(9):
+        v = [0, 5, 0, 3, 7, 0, 0, 1, 2][i]
+        acc, sk, _ = make_account(st, v)
+        bl, u, c = sb(st.scalar() % 2**40), st.scalar_bytes(), st.scalar_bytes()
+        exp, es = R.update_account(acc, bl, u, c)
+        assert es == 0
+        rec += acc + sb(sk) + sb(v) + bl + u + c + exp
+    fx = tmp_path / "fixture.bin"
+    fx.write_bytes(rec)
+    exe = tmp_path / "host_api_test"
+    libdir = os.path.join(ROOT, "quisquis-rust_b200")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", str(exe), os.path.join(ROOT, "tests", "csrc", "host_api_test.cpp"),
+                           "-L" + libdir, "-lqq_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe), str(fx)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "HOST_API_TEST OK" in out.stdout, out.stdout + out.stderr

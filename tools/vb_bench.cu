@@ -1,0 +1,76 @@
+// Tuning harness for the variable-base kernel: register cap (min blocks per SM) x rolled/unrolled doubling body.
+// Arithmetic is data-independent, so random limbs are fine for timing.
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#include "kernels.cuh"
+using namespace qq;
+
+template <int NS, int MINB, bool ROLLED>
+__global__ void __launch_bounds__(128, MINB) k_vb(vb_args a) {
+    size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    u32x4* tbl = a.scratch + gtid * (QQ_VB_ENTRIES * 10);
+    for (size_t t = gtid; t < a.n; t += stride) {
+        ge_p3 p, r;
+        ge_p3_load(p, a.pts + 10 * map_index(a.map, t));
+        vb_build_table(tbl, p);
+        u32 s[8];
+        load_words32(s, a.s0, t / (size_t)a.sdiv);
+        vb_scalarmult_t<ROLLED>(r, tbl, s);
+        ge_p3_store(a.out0 + 10 * t, r);
+        if (NS == 2) {
+            load_words32(s, a.s1, t / (size_t)a.sdiv);
+            vb_scalarmult_t<ROLLED>(r, tbl, s);
+            ge_p3_store(a.out1 + 10 * t, r);
+        }
+    }
+}
+
+template <int MINB, bool ROLLED>
+static void run(size_t n, int sms) {
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_vb<2, MINB, ROLLED>, 128, 0);
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, k_vb<2, MINB, ROLLED>);
+    int grid = sms * occ;
+    u32x4 *pts, *s0, *s1, *o0, *o1, *scratch;
+    cudaMalloc(&pts, n * 160); cudaMalloc(&s0, n * 32); cudaMalloc(&s1, n * 32);
+    cudaMalloc(&o0, n * 160); cudaMalloc(&o1, n * 160);
+    cudaMalloc(&scratch, (size_t)grid * 128 * QQ_VB_TABLE_WORDS * 4);
+    size_t words = n * 40;
+    u32* h = (u32*)malloc(words * 4);
+    for (size_t i = 0; i < words; i++) h[i] = (u32)(rand()) & 0x1ffffff;
+    cudaMemcpy(pts, h, words * 4, cudaMemcpyHostToDevice);
+    for (size_t i = 0; i < n * 8; i++) h[i] = (u32)rand() * 2654435761u;
+    for (size_t i = 7; i < n * 8; i += 8) h[i] &= 0x0fffffff;
+    cudaMemcpy(s0, h, n * 32, cudaMemcpyHostToDevice);
+    cudaMemcpy(s1, h + 8, n * 32 - 32, cudaMemcpyHostToDevice);
+    vb_args a;
+    a.pts = pts; a.map = idx_map{1, 1, {0, 0, 0, 0}}; a.s0 = s0; a.s1 = s1; a.sdiv = 1; a.out0 = o0; a.out1 = o1; a.scratch = scratch; a.n = n;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k_vb<2, MINB, ROLLED><<<grid, 128>>>(a);
+    cudaDeviceSynchronize();
+    float best = 1e30f;
+    for (int r = 0; r < 2; r++) {
+        cudaEventRecord(e0);
+        k_vb<2, MINB, ROLLED><<<grid, 128>>>(a);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    printf("{\"variant\": \"minb%d_%s\", \"regs\": %d, \"local_bytes\": %zu, \"blocks_per_sm\": %d, \"n_items\": %zu, \"ms\": %.3f, \"scalar_mults_per_s\": %.4e, \"err\": \"%s\"}\n",
+           MINB, ROLLED ? "rolled" : "unrolled", fa.numRegs, (size_t)fa.localSizeBytes, occ, n, best, 2.0 * n / (best * 1e-3), cudaGetErrorString(cudaGetLastError()));
+    cudaFree(pts); cudaFree(s0); cudaFree(s1); cudaFree(o0); cudaFree(o1); cudaFree(scratch); free(h);
+}
+int main() {
+    cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+    size_t n = 1 << 18;
+    run<2, false>(n, p.multiProcessorCount);
+    run<2, true>(n, p.multiProcessorCount);
+    run<3, false>(n, p.multiProcessorCount);
+    run<3, true>(n, p.multiProcessorCount);
+    run<4, false>(n, p.multiProcessorCount);
+    run<4, true>(n, p.multiProcessorCount);
+    return 0;
+}
