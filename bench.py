@@ -113,6 +113,7 @@ def run_reference(args):
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import c_oracle as C
+    C.set_threads(len(os.sched_getaffinity(0)))   # torchrun exports OMP_NUM_THREADS=1; the baseline uses every host core
     cores = C.threads()
     rng = np.random.default_rng(1234)
     # calibrate a bounded sample: ~2 s of all-core work per step
@@ -303,6 +304,7 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import c_oracle as C
+        C.set_threads(len(os.sched_getaffinity(0)))
         cores = C.threads()
         m0 = 64 * cores
         t = time.time()

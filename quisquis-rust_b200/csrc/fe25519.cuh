@@ -61,6 +61,19 @@ QQ_HD u64 mad_wide(u32 a, u32 b, u64 c) {
 #endif
 }
 
+// x << K for x < 2^(32-K), written as a rotate so that ptxas keeps it on the ALU pipe (SHF) instead of emitting
+// IMAD.SHL / IMAD.IADD on the FMA pipe, which is the bottleneck pipe of every kernel here.
+template <int K>
+QQ_HD u32 shl_alu(u32 x) {
+#if defined(__CUDA_ARCH__)
+    u32 r;
+    asm("shf.l.wrap.b32 %0, %1, %1, %2;" : "=r"(r) : "r"(x), "n"(K));
+    return r;
+#else
+    return x << K;
+#endif
+}
+
 QQ_HD void fe_0(fe& h) {
 #pragma unroll
     for (int i = 0; i < 10; i++) h.v[i] = 0;
@@ -127,22 +140,31 @@ QQ_HD void fe_mul_inl(fe& h, const fe& f, const fe& g) {
 #pragma unroll
     for (int i = 1; i < 10; i++) g19[i] = g.v[i] * 19u;
 #pragma unroll
-    for (int i = 1; i < 10; i += 2) f2[i] = f.v[i] * 2u;
+    for (int i = 1; i < 10; i += 2) f2[i] = shl_alu<1>(f.v[i]);
+    // Products are accumulated in chains of two (mul.wide + mad.wide) and the five partial sums of a column are then
+    // added: ptxas keeps a 2-long chain as IMAD.WIDE with a 64-bit addend, whereas it rewrites longer chains into
+    // IMAD.WIDE ..., RZ plus one 64-bit add per product (measured: 114 instead of 155 non-multiply instructions).
     u64 t[10];
 #pragma unroll
     for (int k = 0; k < 10; k++) {
-        u64 acc = 0;
+        u64 part[5];
 #pragma unroll
-        for (int i = 0; i < 10; i++) {
-            int j = k - i;
-            bool wrap = false;
-            if (j < 0) { j += 10; wrap = true; }
-            bool both_odd = (i & 1) && (j & 1);
-            u32 a = both_odd ? f2[i] : f.v[i];
-            u32 b = wrap ? g19[j] : g.v[j];
-            acc = (i == 0) ? mul_wide(a, b) : mad_wide(a, b, acc);
+        for (int q = 0; q < 5; q++) {
+            u64 acc = 0;
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                int i = 2 * q + e;
+                int j = k - i;
+                bool wrap = false;
+                if (j < 0) { j += 10; wrap = true; }
+                bool both_odd = (i & 1) && (j & 1);
+                u32 a = both_odd ? f2[i] : f.v[i];
+                u32 b = wrap ? g19[j] : g.v[j];
+                acc = (e == 0) ? mul_wide(a, b) : mad_wide(a, b, acc);
+            }
+            part[q] = acc;
         }
-        t[k] = acc;
+        t[k] = ((part[0] + part[1]) + part[2]) + (part[3] + part[4]);
     }
     fe_reduce64(h, t);
 }
@@ -152,15 +174,16 @@ QQ_HD void fe_sq_inl(fe& h, const fe& f) {
     u32 f2[10], f4[10], f19[10];
 #pragma unroll
     for (int i = 0; i < 10; i++) {
-        f2[i] = f.v[i] * 2u;
-        f4[i] = f.v[i] * 4u;
+        f2[i] = shl_alu<1>(f.v[i]);
+        f4[i] = shl_alu<2>(f.v[i]);
         f19[i] = f.v[i] * 19u;
     }
     u64 t[10];
 #pragma unroll
     for (int k = 0; k < 10; k++) {
-        u64 acc = 0;
-        bool first = true;
+        // chains of two products (see fe_mul_inl); a column of the square has 5 or 6 distinct products
+        u64 tot = 0, acc = 0;
+        int len = 0, nparts = 0;
 #pragma unroll
         for (int i = 0; i < 10; i++) {
             int j = k - i;
@@ -171,10 +194,16 @@ QQ_HD void fe_sq_inl(fe& h, const fe& f) {
             int coef = (i == j ? 1 : 2) * (both_odd ? 2 : 1);  // 1, 2 or 4 on the i side; 19 on the j side
             u32 a = coef == 4 ? f4[i] : (coef == 2 ? f2[i] : f.v[i]);
             u32 b = wrap ? f19[j] : f.v[j];
-            acc = first ? mul_wide(a, b) : mad_wide(a, b, acc);
-            first = false;
+            acc = (len == 0) ? mul_wide(a, b) : mad_wide(a, b, acc);
+            len++;
+            if (len == 2) {
+                tot = (nparts == 0) ? acc : tot + acc;
+                nparts++;
+                len = 0;
+            }
         }
-        t[k] = acc;
+        if (len) tot = (nparts == 0) ? acc : tot + acc;
+        t[k] = tot;
     }
     fe_reduce64(h, t);
 }
@@ -194,6 +223,17 @@ static __device__ __noinline__ fe fe_sq_ool(fe f) {
     fe_sq_inl(h, f);
     return h;
 }
+// n >= 1 squarings with the loop inside the callee: the square-root chains (254 squarings per decompress / compress)
+// then pay the call marshalling once per run instead of once per squaring
+static __device__ __noinline__ fe fe_sqn_ool(fe f, int n) {
+#pragma unroll 1
+    for (int i = 0; i < n; i++) {
+        fe h;
+        fe_sq_inl(h, f);
+        f = h;
+    }
+    return f;
+}
 #endif
 QQ_HD void fe_mul(fe& h, const fe& f, const fe& g) {
 #if defined(__CUDA_ARCH__) && !defined(QQ_INLINE_FIELD_OPS)
@@ -211,8 +251,12 @@ QQ_HD void fe_sq(fe& h, const fe& f) {
 }
 
 QQ_HD void fe_sqn(fe& h, const fe& f, int n) {
+#if defined(__CUDA_ARCH__) && !defined(QQ_INLINE_FIELD_OPS)
+    h = fe_sqn_ool(f, n);
+#else
     fe_sq(h, f);
     for (int i = 1; i < n; i++) fe_sq(h, h);
+#endif
 }
 
 // z^(2^252 - 3) = z^((p-5)/8)   (dalek field.rs pow_p58 / ref10 pow22523 addition chain: 251 S + 11 M)

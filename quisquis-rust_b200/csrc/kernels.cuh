@@ -377,28 +377,107 @@ __global__ void __launch_bounds__(256) k_segment_sum_compress(const u32x4* __res
     }
 }
 
+// ---- Straus (interleaved windows) for many small MSMs -----------------------------------------------------------------
+// One thread per instance: the 2..9 terms of an instance (reference call sites: src/accounts/verifier.rs:165-880,
+// src/shuffle/*.rs) share ONE doubling chain -- 252 doublings + 64 table additions per term instead of
+// 252 doublings per term.  Per-term window tables and recoded scalars live in a per-thread global scratch slab
+// (QQ_STRAUS_KMAX terms x 92 x 16 B); instances with more terms are processed in chunks of QQ_STRAUS_KMAX.
+// dalek counterpart: backend/serial/scalar_mul/straus.rs.
+#define QQ_STRAUS_KMAX 10
+#define QQ_STRAUS_TERM_Q 92   // 90 x 16 B table + 2 x 16 B recoded scalar
+struct straus_args {
+    const u32x4* pts;          // decompressed terms
+    const u32x4* scalars;
+    const uint32_t* offsets;   // m + 1
+    const uint8_t* term_status;
+    u32x4* out;                // m compressed points
+    uint8_t* status;           // m
+    u32x4* scratch;
+    size_t m;
+};
+__global__ void __launch_bounds__(128, 2) k_straus(straus_args a) {
+    size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    u32x4* slab = a.scratch + gtid * (size_t)(QQ_STRAUS_KMAX * QQ_STRAUS_TERM_Q);
+    for (size_t j = gtid; j < a.m; j += stride) {
+        uint32_t lo = a.offsets[j], hi = a.offsets[j + 1];
+        ge_p3 total;
+        ge_identity(total);
+        uint8_t st = 0;
+        for (uint32_t c0 = lo; c0 < hi; c0 += QQ_STRAUS_KMAX) {
+            int k = (int)((hi - c0) < QQ_STRAUS_KMAX ? (hi - c0) : QQ_STRAUS_KMAX);
+            for (int t = 0; t < k; t++) {
+                ge_p3 p;
+                ge_p3_load(p, a.pts + 10 * (size_t)(c0 + t));
+                u32x4* tb = slab + (size_t)t * QQ_STRAUS_TERM_Q;
+                vb_build_table(tb, p);
+                u32 s[8], rr[9];
+                load_words32(s, a.scalars, c0 + t);
+                sc_recode_bias<4, 64>(rr, s);
+                store_words32(tb + 90, 0, rr);
+                uint8_t ts = a.term_status[c0 + t];
+                st = (ts == 2 || st == 2) ? 2 : (st | ts);
+            }
+            ge_p3 r;
+            ge_identity(r);
+#pragma unroll 1
+            for (int w = 63; w >= 0; w--) {
+                if (w != 63) {
+                    ge_dbl<false>(r, r);
+                    ge_dbl<false>(r, r);
+                    ge_dbl<false>(r, r);
+                    ge_dbl<true>(r, r);
+                }
+#pragma unroll 1
+                for (int t = 0; t < k; t++) {
+                    const u32x4* tb = slab + (size_t)t * QQ_STRAUS_TERM_Q;
+                    u32 word = reinterpret_cast<const u32*>(tb + 90)[w >> 3];
+                    int d = (int)((word >> ((w & 7) * 4)) & 15u) - 8;
+                    u32 neg = d < 0 ? 1u : 0u;
+                    u32 idx = (u32)(d < 0 ? -d : d);
+                    ge_cached c;
+                    ge_cached_load(c, tb + 10 * idx);
+                    ge_cached_cneg(c, neg);
+                    ge_add(r, r, c);
+                }
+            }
+            ge_cached cr;
+            ge_to_cached(cr, r);
+            ge_add(total, total, cr);
+        }
+        u32 wds[8];
+        ristretto_compress(wds, total);
+        if (st) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) wds[i] = 0;
+        }
+        store_words32(a.out, j, wds);
+        a.status[j] = st;
+    }
+}
+
 // ---- integer-pipe peak micro-benchmark (roofline denominator) ------------------------------------------------------
+// 8 independent dependent chains per thread and nothing else in the loop body:
+//   MODE 0: c = c * a + b          -> IMAD          (32-bit multiply-add, the "IMAD unit" of the cost model)
+//   MODE 1: w = lo(w) * a + w      -> IMAD.WIDE.U32 (32x32->64 product; issues at half the IMAD rate)
 template <int MODE>
 __global__ void __launch_bounds__(256) k_imad_peak(u32* out, u32 seed, int outer) {
-    __shared__ u32 sm[1024];
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) sm[i] = i * 2654435761u + seed;
-    __syncthreads();
-    u32 b[4], c[8];
+    u32 a[8], b[8], c[8];
     u64 w[8];
-    for (int j = 0; j < 4; j++) b[j] = seed * 2654435761u + j * 40503u + threadIdx.x;
-    for (int i = 0; i < 8; i++) { c[i] = i + seed; w[i] = ((u64)c[i] << 32) | b[i & 3]; }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        a[i] = (seed * 2654435761u + i * 40503u + threadIdx.x) | 1u;
+        b[i] = seed + i * 7919u + blockIdx.x;
+        c[i] = i + seed;
+        w[i] = ((u64)c[i] << 32) | b[i];
+    }
     for (int o = 0; o < outer; o++) {
 #pragma unroll
         for (int k = 0; k < 32; k++) {
 #pragma unroll
-            for (int i = 0; i < 2; i++) {
-                u32 x = sm[(threadIdx.x + (o * 32 + k) * 2 + i) & 1023];
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    int q = i * 4 + j;
-                    if (MODE == 0) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c[q]) : "r"(x), "r"(b[j]));
-                    if (MODE == 1) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[q]) : "r"(x), "r"(b[j]));
-                }
+            for (int i = 0; i < 8; i++) {
+                if (MODE == 0) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(c[i]) : "r"(a[i]), "r"(b[i]));
+                if (MODE == 1) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"((u32)(w[i] >> 32)), "r"(a[i]));
             }
         }
     }

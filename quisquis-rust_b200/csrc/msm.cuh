@@ -109,27 +109,49 @@ __global__ void __launch_bounds__(256) k_msm_prepare(const u32x4* __restrict__ p
     }
 }
 
-// exclusive scan of `total` counters by one block of 1024 threads (total <= 2^20 here)
+// exclusive scan of `total` counters by one block of 1024 threads, tile by tile (coalesced loads, warp-shuffle scan)
 __global__ void __launch_bounds__(1024) k_scan_exclusive(const unsigned int* __restrict__ in,
                                                          unsigned int* __restrict__ out, size_t total) {
-    __shared__ unsigned int sm[1024];
-    size_t chunk = (total + 1023) / 1024;
-    size_t lo = (size_t)threadIdx.x * chunk, hi = lo + chunk < total ? lo + chunk : total;
-    unsigned int s = 0;
-    for (size_t i = lo; i < hi; i++) s += in[i];
-    sm[threadIdx.x] = s;
+    __shared__ unsigned int warp_sums[32];
+    __shared__ unsigned int carry_s;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-        unsigned int v = threadIdx.x >= off ? sm[threadIdx.x - off] : 0;
+    for (size_t base = 0; base < total; base += 4096) {
+        // each thread owns 4 consecutive counters of the tile
+        size_t i0 = base + (size_t)threadIdx.x * 4;
+        unsigned int v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = (i0 + j < total) ? in[i0 + j] : 0u;
+        unsigned int tsum = v[0] + v[1] + v[2] + v[3];
+        unsigned int x = tsum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            unsigned int y = __shfl_up_sync(0xffffffffu, x, off);
+            if (lane >= off) x += y;
+        }
+        if (lane == 31) warp_sums[wid] = x;
         __syncthreads();
-        sm[threadIdx.x] += v;
+        if (wid == 0) {
+            unsigned int w = warp_sums[lane];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                unsigned int y = __shfl_up_sync(0xffffffffu, w, off);
+                if (lane >= off) w += y;
+            }
+            warp_sums[lane] = w;  // inclusive over warps
+        }
         __syncthreads();
-    }
-    unsigned int run = sm[threadIdx.x] - s;
-    for (size_t i = lo; i < hi; i++) {
-        unsigned int v = in[i];
-        out[i] = run;
-        run += v;
+        unsigned int carry = carry_s;
+        unsigned int excl = carry + (wid ? warp_sums[wid - 1] : 0u) + (x - tsum);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (i0 + j < total) out[i0 + j] = excl;
+            excl += v[j];
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + warp_sums[31];
+        __syncthreads();
     }
 }
 

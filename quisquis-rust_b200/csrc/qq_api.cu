@@ -609,19 +609,27 @@ static int core_msm_to_point(qq_ctx* ctx, const uint8_t* scalars, const uint8_t*
 
 static int core_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* points, const uint32_t* offsets, size_t m,
                           size_t nterms, uint8_t* out, uint8_t* status) {
-    CKQ(ws_begin(ctx, ws_need({nterms * 160, nterms * 160, nterms, nterms, vb_scratch_bytes(ctx, 1)})));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_straus, 128, 0));
+    if (occ < 1) occ = 1;
+    size_t grid = (m + 127) / 128;
+    if (grid > (size_t)ctx->sms * occ) grid = (size_t)ctx->sms * occ;
+    size_t scratch_bytes = grid * 128 * (size_t)QQ_STRAUS_KMAX * QQ_STRAUS_TERM_Q * 16;
+    CKQ(ws_begin(ctx, ws_need({nterms * 160, nterms, nterms, scratch_bytes})));
     u32x4* P = ws_take<u32x4>(ctx, nterms * 160);
-    u32x4* R = ws_take<u32x4>(ctx, nterms * 160);
     uint8_t* ok = ws_take<uint8_t>(ctx, nterms);
     uint8_t* tst = ws_take<uint8_t>(ctx, nterms);
-    u32x4* scratch = ws_take<u32x4>(ctx, vb_scratch_bytes(ctx, 1));
+    u32x4* scratch = ws_take<u32x4>(ctx, scratch_bytes);
     CKQ(launch_decompress(ctx, points, IDENT, P, ok, nterms));
     CKQ(launch_status(ctx, scalars, nullptr, nullptr, ok, 1, tst, nterms));
-    CKQ(launch_varbase(ctx, 1, P, IDENT, scalars, nullptr, 1, R, nullptr, scratch, nterms));
-    span_begin(ctx, FAM_FIN);
-    k_segment_sum_compress<<<grid_for(m, 256, ctx->sms * 64), 256, 0, ctx->stream>>>(R, offsets, tst, (u32x4*)out, status, m);
+    straus_args a;
+    a.pts = P; a.scalars = (const u32x4*)scalars; a.offsets = offsets; a.term_status = tst;
+    a.out = (u32x4*)out; a.status = status; a.scratch = scratch; a.m = m;
+    span_begin(ctx, FAM_VB);
+    k_straus<<<(unsigned)grid, 128, 0, ctx->stream>>>(a);
     span_end(ctx);
     ctx->launches++;
+    CK(cudaGetLastError());
     return QQ_OK;
 }
 

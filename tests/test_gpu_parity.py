@@ -391,3 +391,29 @@ def test_update_account_properties_at_scale(engine):
     assert (a2[:, :64] == a3[:, :64]).all()           # pk' = u * pk either way
     # commitments: second update of a2 used pk (unchanged by u = 1), so both routes give the same commitment
     assert (a2[:, 64:] == a3[:, 64:]).all()
+
+
+def test_msm_segmented_many_shapes_vs_c_oracle(engine):
+    """Shuffle-proof-shaped workload: thousands of 0..25-term MSMs, Straus kernel vs the C oracle."""
+    import c_oracle as C
+    rng = np.random.default_rng(4242)
+    m = 3000
+    ks = rng.choice([2, 3, 2, 3, 4, 6, 7, 9, 9, 1, 0, 11, 25], size=m)
+    offs = np.zeros(m + 1, np.uint32)
+    offs[1:] = np.cumsum(ks)
+    nt = int(offs[-1])
+    pts, _ = engine.fixed_base(0, _rand_scalars(rng, nt))
+    sc = _rand_scalars(rng, nt)
+    sc[::5, 8:] = 0
+    sc[7] = 0
+    # a few invalid terms
+    bad = np.frombuffer(invalid_encodings()[0][1], np.uint8)
+    for j in (5, 77, 1234):
+        if ks[j]:
+            pts[offs[j] + ks[j] // 2] = bad
+    sc[offs[200]] = np.frombuffer(R.L.to_bytes(32, "little"), np.uint8)
+    out, st = engine.msm_segmented(sc, pts, offs)
+    eout, est = C.msm_segmented(sc, pts, offs)
+    assert (st == est).all()
+    assert (out == eout).all()
+    assert st[5] == 1 and st[200] == 2
