@@ -393,13 +393,19 @@ struct straus_args {
     u32x4* out;                // m compressed points
     uint8_t* status;           // m
     u32x4* scratch;
+    const unsigned int* order; // instances sorted by term count (descending) so a warp's lanes do equal work
     size_t m;
 };
+__global__ void k_seg_counts(const uint32_t* __restrict__ offsets, size_t m, unsigned int* __restrict__ counts) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) counts[j] = offsets[j + 1] - offsets[j];
+}
 __global__ void __launch_bounds__(128, 2) k_straus(straus_args a) {
     size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     u32x4* slab = a.scratch + gtid * (size_t)(QQ_STRAUS_KMAX * QQ_STRAUS_TERM_Q);
-    for (size_t j = gtid; j < a.m; j += stride) {
+    for (size_t jj = gtid; jj < a.m; jj += stride) {
+        size_t j = a.order[jj];
         uint32_t lo = a.offsets[j], hi = a.offsets[j + 1];
         ge_p3 total;
         ge_identity(total);
