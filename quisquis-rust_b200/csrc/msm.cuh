@@ -7,7 +7,7 @@
 //
 // Pipeline for n terms, signed c-bit windows, K = ceil(256 / c) windows, NB = 2^(c-1) buckets per window:
 //   k_msm_prepare     decompress point -> affine Niels (128 B, Z = 1), status, K signed digits, bucket histogram
-//   k_scan_exclusive  bucket offsets
+//   k_scan_*          bucket offsets (tile totals, scan of totals, apply)
 //   k_msm_scatter     counting sort of (term, sign) pairs by (window, bucket)
 //   k_msm_order_*     buckets ordered by population (descending) so the lanes of a warp get equal work
 //   k_msm_accumulate  one thread per bucket: mixed additions (7 M) of its points, 128-bit gathers of Niels points
@@ -109,50 +109,83 @@ __global__ void __launch_bounds__(256) k_msm_prepare(const u32x4* __restrict__ p
     }
 }
 
-// exclusive scan of `total` counters by one block of 1024 threads, tile by tile (coalesced loads, warp-shuffle scan)
-__global__ void __launch_bounds__(1024) k_scan_exclusive(const unsigned int* __restrict__ in,
-                                                         unsigned int* __restrict__ out, size_t total) {
-    __shared__ unsigned int warp_sums[32];
-    __shared__ unsigned int carry_s;
+// ---- exclusive scan of `total` counters -----------------------------------------------------------------------------
+// Tile = 4096 counters per 1024-thread block (4 per thread, warp-shuffle scan).  PASS 0 writes each tile's total,
+// PASS 1 (one block) scans the tile totals in place, PASS 2 rescans every tile and adds its tile offset.
+__device__ __forceinline__ unsigned int block_scan_1024(unsigned int tsum, unsigned int* warp_sums, unsigned int& block_total) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (size_t base = 0; base < total; base += 4096) {
-        // each thread owns 4 consecutive counters of the tile
-        size_t i0 = base + (size_t)threadIdx.x * 4;
-        unsigned int v[4];
+    unsigned int x = tsum;
 #pragma unroll
-        for (int j = 0; j < 4; j++) v[j] = (i0 + j < total) ? in[i0 + j] : 0u;
-        unsigned int tsum = v[0] + v[1] + v[2] + v[3];
-        unsigned int x = tsum;
+    for (int off = 1; off < 32; off <<= 1) {
+        unsigned int y = __shfl_up_sync(0xffffffffu, x, off);
+        if (lane >= off) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned int w = warp_sums[lane];
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
-            unsigned int y = __shfl_up_sync(0xffffffffu, x, off);
-            if (lane >= off) x += y;
+            unsigned int y = __shfl_up_sync(0xffffffffu, w, off);
+            if (lane >= off) w += y;
         }
-        if (lane == 31) warp_sums[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            unsigned int w = warp_sums[lane];
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                unsigned int y = __shfl_up_sync(0xffffffffu, w, off);
-                if (lane >= off) w += y;
-            }
-            warp_sums[lane] = w;  // inclusive over warps
-        }
-        __syncthreads();
-        unsigned int carry = carry_s;
-        unsigned int excl = carry + (wid ? warp_sums[wid - 1] : 0u) + (x - tsum);
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (i0 + j < total) out[i0 + j] = excl;
-            excl += v[j];
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = carry + warp_sums[31];
-        __syncthreads();
+        warp_sums[lane] = w;
     }
+    __syncthreads();
+    block_total = warp_sums[31];
+    unsigned int excl = (wid ? warp_sums[wid - 1] : 0u) + (x - tsum);
+    __syncthreads();
+    return excl;  // exclusive prefix of this thread's tsum within the block
+}
+__global__ void __launch_bounds__(1024) k_scan_tile_totals(const unsigned int* __restrict__ in, size_t total,
+                                                           unsigned int* __restrict__ tile_tot) {
+    __shared__ unsigned int warp_sums[32];
+    size_t i0 = (size_t)blockIdx.x * 4096 + (size_t)threadIdx.x * 4;
+    unsigned int tsum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) tsum += (i0 + j < total) ? in[i0 + j] : 0u;
+    unsigned int bt;
+    block_scan_1024(tsum, warp_sums, bt);
+    if (threadIdx.x == 0) tile_tot[blockIdx.x] = bt;
+}
+// single block: exclusive scan of up to 4096 values in place
+__global__ void __launch_bounds__(1024) k_scan_small(unsigned int* __restrict__ v, size_t n) {
+    __shared__ unsigned int warp_sums[32];
+    size_t i0 = (size_t)threadIdx.x * 4;
+    unsigned int x[4], tsum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { x[j] = (i0 + j < n) ? v[i0 + j] : 0u; tsum += x[j]; }
+    unsigned int bt;
+    unsigned int excl = block_scan_1024(tsum, warp_sums, bt);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if (i0 + j < n) v[i0 + j] = excl;
+        excl += x[j];
+    }
+}
+__global__ void __launch_bounds__(1024) k_scan_apply(const unsigned int* __restrict__ in, size_t total,
+                                                     const unsigned int* __restrict__ tile_off,
+                                                     unsigned int* __restrict__ out) {
+    __shared__ unsigned int warp_sums[32];
+    size_t i0 = (size_t)blockIdx.x * 4096 + (size_t)threadIdx.x * 4;
+    unsigned int x[4], tsum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { x[j] = (i0 + j < total) ? in[i0 + j] : 0u; tsum += x[j]; }
+    unsigned int bt;
+    unsigned int excl = block_scan_1024(tsum, warp_sums, bt) + tile_off[blockIdx.x];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if (i0 + j < total) out[i0 + j] = excl;
+        excl += x[j];
+    }
+}
+// host-side helper: exclusive scan of `total` <= 4096 * 4096 counters; tile_tmp holds ceil(total / 4096) words
+static inline void launch_scan_exclusive(const unsigned int* in, unsigned int* out, size_t total, unsigned int* tile_tmp,
+                                         cudaStream_t st) {
+    unsigned tiles = (unsigned)((total + 4095) / 4096);
+    k_scan_tile_totals<<<tiles, 1024, 0, st>>>(in, total, tile_tmp);
+    k_scan_small<<<1, 1024, 0, st>>>(tile_tmp, tiles);
+    k_scan_apply<<<tiles, 1024, 0, st>>>(in, total, tile_tmp, out);
 }
 
 __global__ void __launch_bounds__(256) k_msm_scatter(const int16_t* __restrict__ digits, size_t n, msm_geom g,
@@ -285,21 +318,69 @@ __global__ void __launch_bounds__(128) k_point_sum_rows(const u32x4* __restrict_
     }
     if (threadIdx.x == 0) ge_p3_store(out + 10 * blockIdx.x, acc);
 }
-// result = sum_k 2^(c k) win[k]
-__global__ void k_msm_horner(const u32x4* __restrict__ win, msm_geom g, u32x4* __restrict__ result) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+// result = sum_k 2^(c k) win[k].  A chain of c (K - 1) = 240 dependent doublings: latency, not throughput.  Four lanes of one
+// warp cooperate on every doubling -- lane l squares one of (X, Y, Z, X + Y), the four squares are exchanged through
+// shared memory, every lane forms the completed-point terms and multiplies out one output coordinate -- so a doubling
+// costs one squaring + one multiplication of latency instead of four + four.
+__global__ void __launch_bounds__(32) k_msm_horner(const u32x4* __restrict__ win, msm_geom g, u32x4* __restrict__ result) {
+    __shared__ fe sq_s[4];
+    __shared__ fe co_s[4];
+    const int lane = threadIdx.x;
+    if (blockIdx.x != 0 || lane >= 4) return;
+    const unsigned mask = 0xfu;
     ge_p3 acc;
     ge_p3_load(acc, win + 10 * (size_t)(g.K - 1));
+    // lane l keeps coordinate l of the running point in `mine` (0: X, 1: Y, 2: Z, 3: T)
+    fe mine = lane == 0 ? acc.X : (lane == 1 ? acc.Y : (lane == 2 ? acc.Z : acc.T));
     for (int k = g.K - 2; k >= 0; k--) {
-        for (int i = 0; i < g.c - 1; i++) ge_dbl<false>(acc, acc);
-        ge_dbl<true>(acc, acc);
-        ge_p3 p;
-        ge_p3_load(p, win + 10 * (size_t)k);
-        ge_cached c;
-        ge_to_cached(c, p);
-        ge_add(acc, acc, c);
+        for (int i = 0; i < g.c; i++) {
+            co_s[lane] = mine;
+            __syncwarp(mask);
+            fe in;
+            if (lane == 3) fe_add(in, co_s[0], co_s[1]);   // X + Y (2T)
+            else in = mine;
+            fe sq;
+            fe_sq(sq, in);
+            sq_s[lane] = sq;
+            __syncwarp(mask);
+            fe xx = sq_s[0], yy = sq_s[1], zz = sq_s[2], s = sq_s[3];
+            fe cx, cy, cz, ct, t;
+            fe_add(cy, yy, xx);
+            fe_sub(cz, yy, xx);
+            fe_sub4(cx, s, cy);
+            fe_add(t, zz, zz);
+            fe_add(t, t, xx);
+            fe_sub(t, t, yy);
+            fe_carry(ct, t);
+            // X3 = cx ct, Y3 = cy cz, Z3 = cz ct, T3 = cx cy
+            fe a = (lane == 0 || lane == 3) ? cx : (lane == 1 ? cy : cz);
+            fe b = (lane == 0 || lane == 2) ? ct : (lane == 1 ? cz : cy);
+            fe_mul(mine, a, b);
+            __syncwarp(mask);
+        }
+        // add window k: lane 0 gathers the point, performs the addition, and redistributes
+        co_s[lane] = mine;
+        __syncwarp(mask);
+        if (lane == 0) {
+            ge_p3 r, p;
+            r.X = co_s[0]; r.Y = co_s[1]; r.Z = co_s[2]; r.T = co_s[3];
+            ge_p3_load(p, win + 10 * (size_t)k);
+            ge_cached c;
+            ge_to_cached(c, p);
+            ge_add(r, r, c);
+            co_s[0] = r.X; co_s[1] = r.Y; co_s[2] = r.Z; co_s[3] = r.T;
+        }
+        __syncwarp(mask);
+        mine = co_s[lane];
+        __syncwarp(mask);
     }
-    ge_p3_store(result, acc);
+    co_s[lane] = mine;
+    __syncwarp(mask);
+    if (lane == 0) {
+        ge_p3 r;
+        r.X = co_s[0]; r.Y = co_s[1]; r.Z = co_s[2]; r.T = co_s[3];
+        ge_p3_store(result, r);
+    }
 }
 
 }  // namespace qq

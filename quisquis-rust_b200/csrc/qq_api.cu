@@ -616,12 +616,13 @@ static int core_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* po
     if (grid > (size_t)ctx->sms * occ) grid = (size_t)ctx->sms * occ;
     size_t scratch_bytes = grid * 128 * (size_t)QQ_STRAUS_KMAX * QQ_STRAUS_TERM_Q * 16;
     CKQ(ws_begin(ctx, ws_need({nterms * 160, nterms, nterms, scratch_bytes, m * 4, m * 4, QQ_ORDER_BINS * 4, QQ_ORDER_BINS * 4,
-                               QQ_ORDER_BINS * 4})));
+                               QQ_ORDER_BINS * 4, 4096 * 4})));
     unsigned int* counts = ws_take<unsigned int>(ctx, m * 4);
     unsigned int* order = ws_take<unsigned int>(ctx, m * 4);
     unsigned int* ohist = ws_take<unsigned int>(ctx, QQ_ORDER_BINS * 4);
     unsigned int* ooff = ws_take<unsigned int>(ctx, QQ_ORDER_BINS * 4);
     unsigned int* ocur = ws_take<unsigned int>(ctx, QQ_ORDER_BINS * 4);
+    unsigned int* scan_tmp = ws_take<unsigned int>(ctx, 4096 * 4);
     u32x4* P = ws_take<u32x4>(ctx, nterms * 160);
     uint8_t* ok = ws_take<uint8_t>(ctx, nterms);
     uint8_t* tst = ws_take<uint8_t>(ctx, nterms);
@@ -633,9 +634,9 @@ static int core_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* po
     CK(cudaMemsetAsync(ocur, 0, QQ_ORDER_BINS * 4, ctx->stream));
     k_seg_counts<<<grid_for(m, 256, ctx->sms * 8), 256, 0, ctx->stream>>>(offsets, m, counts);
     k_msm_order_hist<<<grid_for(m, 256, ctx->sms * 8), 256, 0, ctx->stream>>>(counts, m, ohist);
-    k_scan_exclusive<<<1, 1024, 0, ctx->stream>>>(ohist, ooff, QQ_ORDER_BINS);
+    launch_scan_exclusive(ohist, ooff, QQ_ORDER_BINS, scan_tmp, ctx->stream);
     k_msm_order_scatter<<<grid_for(m, 256, ctx->sms * 8), 256, 0, ctx->stream>>>(counts, m, ooff, ocur, order);
-    ctx->launches += 4;
+    ctx->launches += 6;
     straus_args a;
     a.pts = P; a.scalars = (const u32x4*)scalars; a.offsets = offsets; a.term_status = tst;
     a.out = (u32x4*)out; a.status = status; a.scratch = scratch; a.order = order; a.m = m;
