@@ -331,7 +331,7 @@ def run_b200(args):
             "metric": "account_updates_per_sec", "value": value, "unit": "accounts/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32 limbs (radix 2^25.5), 64-bit products", "data": "synthetic",
+            "dtype": "u32 (8 saturated 32-bit limbs, 32x32->64 IMAD.WIDE carry chains)", "data": "synthetic",
             "config": {"workload": "Account::update_account over 2^20 accounts per GPU (BASELINE.json configs[1])"
                        if n == (1 << 20) else "Account::update_account over %d accounts per GPU" % n,
                        "accounts_per_gpu": n, "scalars": "uniform 252-bit (worst case)",

@@ -1,24 +1,25 @@
-// GF(2^255-19) arithmetic for sm_100a.
+// GF(2^255-19) arithmetic for sm_100a -- saturated representation.
 //
-// Representation: 10 unsigned limbs, radix 2^25.5 (limb i has 26 bits for even i, 25 bits for odd i), one limb per
-// 32-bit register.  Every 32x32->64 partial product is one IMAD.WIDE.U32; the 19-fold for 2^255 = 19 is applied to
-// one operand before the products, so a multiplication is 100 wide products + 9 small IMADs and needs NO carry
-// propagation between partial products (all column sums stay below 2^64).  ptxas pairs the products into
-// 3-input 64-bit adds (IADD3 + IADD3.X on the ALU pipe), which balances the FMA-pipe and ALU-pipe issue slots.
+// Representation: 8 unsigned 32-bit limbs, little-endian, value in [0, 2^256) (NOT necessarily reduced mod p;
+// 2^256 = 38 mod p).  Every function accepts and returns the full range, so there are no magnitude budgets to
+// track at the call sites.
+//
+// Why saturated limbs: the multiply pipe is the bound of every kernel here.  On sm_100a a
+// 32x32->64 product is one IMAD.WIDE.U32 (measured 0.7-0.8e13 thread-ops/s per GPU, ~2.6x slower than a plain
+// IMAD), and nothing else on the SM multiplies integers faster.  The radix-2^25.5 form needs 100 products per
+// multiplication; this form needs 64, and one level of subtractive Karatsuba brings that to 48, plus 8 products by
+// the constant 38 for the reduction: 56 IMAD.WIDE per multiplication, 44 per squaring.  Accumulation is free:
+// each product is a (mad.lo.cc, madc.hi.cc) PTX pair that ptxas fuses into one IMAD.WIDE.U32.X with the carry in a
+// predicate register (verified in SASS), see tools/gen_field_ops.py for the even/odd accumulator scheme.
+// Additions, subtractions and the Karatsuba glue are carry chains on the ALU pipe (IADD3.X), which has 5x the
+// throughput and runs beside the multiply pipe.
 //
 // Replaces (for the hot path) curve25519-dalek 3.x `backend/serial/u64/field.rs` + `field.rs`
 // (FieldElement51::{mul,square,pow_p58,sqrt_ratio_i,to_bytes,from_bytes}); dalek is a dependency of the
 // reference (Cargo.toml:42) and not vendored, so this restates the published arithmetic (RFC 9496 / RFC 7748).
 //
-// Bounds (T = "tight" = output of fe_mul/fe_sq/fe_carry): even limbs < 2^26, odd limbs < 2^25 + 2^18.
-//   fe_add(tight,tight)        -> <= 2T   ("loose")
-//   fe_sub(any<=3T, tight)     -> a + 2p - b
-//   fe_mul(f,g): g limbs must satisfy 19*g < 2^32 (g <= 3.3T); f*g magnitude product <= ~30 T^2 per limb pair.
-//   fe_sq(f):   f <= 3.3T.
-// All call sites in ge25519.cuh / ristretto.cuh are annotated with the bound they rely on.
-//
-// The file compiles for the host too (QQ_HD empty, plain C multiply) so tests/ can unit-test the exact device
-// arithmetic on CPU against the oracle; the host build is test infrastructure and is never linked into the library.
+// The file compiles for the host too (carry flag emulated in a thread-local) so tests/ can unit-test the exact
+// device algorithms on CPU against the oracle; the host build is test infrastructure, never linked into the library.
 #pragma once
 #include <stdint.h>
 
@@ -35,183 +36,219 @@ namespace qq {
 typedef uint32_t u32;
 typedef uint64_t u64;
 
+#define QQ_FE_LIMBS 8
+
 struct fe {
-    u32 v[10];
+    u32 v[QQ_FE_LIMBS];
 };
 
-#define QQ_M26 0x3ffffffu
-#define QQ_M25 0x1ffffffu
+// ---------------------------------------------------------------------------------------------------------
+// Carry-flag primitives.  Device: PTX extended-precision instructions (the flag lives in CC.CF / a predicate).
+// Host: the same semantics with the flag in a thread-local, so the host unit tests run the identical algorithm.
+// ---------------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+#define QQ_ASM2(name, ins)                                                  \
+    QQ_HD u32 name(u32 a, u32 b) {                                          \
+        u32 r;                                                              \
+        asm volatile(ins " %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));        \
+        return r;                                                           \
+    }
+#define QQ_ASM3(name, ins)                                                          \
+    QQ_HD u32 name(u32 a, u32 b, u32 c) {                                           \
+        u32 r;                                                                      \
+        asm volatile(ins " %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));    \
+        return r;                                                                   \
+    }
+QQ_ASM2(add_cc, "add.cc.u32")
+QQ_ASM2(addc_cc, "addc.cc.u32")
+QQ_ASM2(addc, "addc.u32")
+QQ_ASM2(sub_cc, "sub.cc.u32")
+QQ_ASM2(subc_cc, "subc.cc.u32")
+QQ_ASM2(subc, "subc.u32")
+QQ_ASM2(mul_lo, "mul.lo.u32")
+QQ_ASM2(mul_hi, "mul.hi.u32")
+QQ_ASM3(mad_lo_cc, "mad.lo.cc.u32")
+QQ_ASM3(madc_lo_cc, "madc.lo.cc.u32")
+QQ_ASM3(madc_hi_cc, "madc.hi.cc.u32")
+QQ_ASM3(madc_hi, "madc.hi.u32")
+#undef QQ_ASM2
+#undef QQ_ASM3
+#else
+static thread_local u32 qq_cf = 0;
+inline u32 add_cc(u32 a, u32 b) { u64 s = (u64)a + b; qq_cf = (u32)(s >> 32); return (u32)s; }
+inline u32 addc_cc(u32 a, u32 b) { u64 s = (u64)a + b + qq_cf; qq_cf = (u32)(s >> 32); return (u32)s; }
+inline u32 addc(u32 a, u32 b) { return a + b + qq_cf; }
+inline u32 sub_cc(u32 a, u32 b) { u64 s = (u64)a - b; qq_cf = (u32)(s >> 63); return (u32)s; }
+inline u32 subc_cc(u32 a, u32 b) { u64 s = (u64)a - b - qq_cf; qq_cf = (u32)(s >> 63); return (u32)s; }
+inline u32 subc(u32 a, u32 b) { return a - b - qq_cf; }
+inline u32 mul_lo(u32 a, u32 b) { return (u32)((u64)a * b); }
+inline u32 mul_hi(u32 a, u32 b) { return (u32)(((u64)a * b) >> 32); }
+inline u32 mad_lo_cc(u32 a, u32 b, u32 c) { return add_cc(mul_lo(a, b), c); }
+inline u32 madc_lo_cc(u32 a, u32 b, u32 c) { return addc_cc(mul_lo(a, b), c); }
+inline u32 madc_hi_cc(u32 a, u32 b, u32 c) { return addc_cc(mul_hi(a, b), c); }
+inline u32 madc_hi(u32 a, u32 b, u32 c) { return addc(mul_hi(a, b), c); }
+#endif
 
-QQ_HD u64 mul_wide(u32 a, u32 b) {
-#if defined(__CUDA_ARCH__)
-    u64 r;
-    asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b));
-    return r;
-#else
-    return (u64)a * b;
-#endif
-}
-QQ_HD u64 mad_wide(u32 a, u32 b, u64 c) {
-#if defined(__CUDA_ARCH__)
-    u64 r;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
-    return r;
-#else
-    return (u64)a * b + c;
-#endif
-}
-
-// x << K for x < 2^(32-K), written as a rotate so that ptxas keeps it on the ALU pipe (SHF) instead of emitting
-// IMAD.SHL / IMAD.IADD on the FMA pipe, which is the bottleneck pipe of every kernel here.
-template <int K>
-QQ_HD u32 shl_alu(u32 x) {
-#if defined(__CUDA_ARCH__)
-    u32 r;
-    asm("shf.l.wrap.b32 %0, %1, %1, %2;" : "=r"(r) : "r"(x), "n"(K));
-    return r;
-#else
-    return x << K;
-#endif
-}
+#include "fe25519_mp.inc"
 
 QQ_HD void fe_0(fe& h) {
 #pragma unroll
-    for (int i = 0; i < 10; i++) h.v[i] = 0;
+    for (int i = 0; i < 8; i++) h.v[i] = 0;
 }
 QQ_HD void fe_1(fe& h) {
     h.v[0] = 1;
 #pragma unroll
-    for (int i = 1; i < 10; i++) h.v[i] = 0;
+    for (int i = 1; i < 8; i++) h.v[i] = 0;
 }
+
+// h = f + g.  Two folds of the carry (2^256 = 38): after the first the value can wrap once more only if it is
+// within 38 of 2^256, in which case the wrapped value is < 38 and the last correction cannot carry.
 QQ_HD void fe_add(fe& h, const fe& f, const fe& g) {
+    u32 r[8];
+    r[0] = add_cc(f.v[0], g.v[0]);
 #pragma unroll
-    for (int i = 0; i < 10; i++) h.v[i] = f.v[i] + g.v[i];
+    for (int i = 1; i < 8; i++) r[i] = addc_cc(f.v[i], g.v[i]);
+    u32 k = addc(0u, 0u);
+    r[0] = add_cc(r[0], (0u - k) & 38u);
+#pragma unroll
+    for (int i = 1; i < 8; i++) r[i] = addc_cc(r[i], 0u);
+    k = addc(0u, 0u);
+    r[0] += (0u - k) & 38u;
+#pragma unroll
+    for (int i = 0; i < 8; i++) h.v[i] = r[i];
 }
-// 2p in this radix
-QQ_HD u32 fe_2p_limb(int i) { return i == 0 ? 0x7ffffdau : ((i & 1) ? 0x3fffffeu : 0x7fffffeu); }
-// h = f - g (mod p), computed as f + 2p - g.  g must be tight (limb-wise <= 2p).
+// h = f - g (mod p)
 QQ_HD void fe_sub(fe& h, const fe& f, const fe& g) {
+    u32 r[8];
+    r[0] = sub_cc(f.v[0], g.v[0]);
 #pragma unroll
-    for (int i = 0; i < 10; i++) h.v[i] = f.v[i] + fe_2p_limb(i) - g.v[i];
-}
-// h = f - g with g up to 2T (limb-wise <= 4p): f + 4p - g
-QQ_HD void fe_sub4(fe& h, const fe& f, const fe& g) {
+    for (int i = 1; i < 8; i++) r[i] = subc_cc(f.v[i], g.v[i]);
+    u32 m = subc(0u, 0u);  // all-ones when the subtraction borrowed
+    r[0] = sub_cc(r[0], m & 38u);
 #pragma unroll
-    for (int i = 0; i < 10; i++) h.v[i] = f.v[i] + 2u * fe_2p_limb(i) - g.v[i];
+    for (int i = 1; i < 8; i++) r[i] = subc_cc(r[i], 0u);
+    m = subc(0u, 0u);
+    r[0] -= m & 38u;
+#pragma unroll
+    for (int i = 0; i < 8; i++) h.v[i] = r[i];
 }
+QQ_HD void fe_sub4(fe& h, const fe& f, const fe& g) { fe_sub(h, f, g); }
 QQ_HD void fe_neg(fe& h, const fe& f) {
+    // 2p - f = (2^256 - 38) - f  >= 0 whenever f <= 2^256 - 38; the borrow path covers the last 37 values
+    fe z;
+    fe_0(z);
+    fe_sub(h, z, f);
+}
+// identity in this representation (kept so that the group-law code reads the same as before)
+QQ_HD void fe_carry(fe& h, const fe& f) { h = f; }
+
+// 16 limbs -> 8 limbs: h = t[0..7] + 38 * t[8..15] (mod p), folded into [0, 2^256).
+QQ_HD void fe_reduce512(fe& h, const u32* t) {
+    u32 E[8], O[8], r[8];
+    // even positions accumulate on top of the low half, odd positions are fresh
+    E[0] = mad_lo_cc(t[8], 38u, t[0]);
+    E[1] = madc_hi_cc(t[8], 38u, t[1]);
+    E[2] = madc_lo_cc(t[10], 38u, t[2]);
+    E[3] = madc_hi_cc(t[10], 38u, t[3]);
+    E[4] = madc_lo_cc(t[12], 38u, t[4]);
+    E[5] = madc_hi_cc(t[12], 38u, t[5]);
+    E[6] = madc_lo_cc(t[14], 38u, t[6]);
+    E[7] = madc_hi_cc(t[14], 38u, t[7]);
+    u32 ce = addc(0u, 0u);
 #pragma unroll
-    for (int i = 0; i < 10; i++) h.v[i] = fe_2p_limb(i) - f.v[i];
+    for (int k = 0; k < 4; k++) {
+        O[2 * k] = mul_lo(t[9 + 2 * k], 38u);
+        O[2 * k + 1] = mul_hi(t[9 + 2 * k], 38u);
+    }
+    r[0] = E[0];
+    r[1] = add_cc(E[1], O[0]);
+#pragma unroll
+    for (int k = 2; k < 8; k++) r[k] = addc_cc(E[k], O[k - 1]);
+    u32 top = addc(ce, O[7]);  // total < 39 * 2^256  =>  top <= 38
+    r[0] = add_cc(r[0], top * 38u);
+#pragma unroll
+    for (int k = 1; k < 8; k++) r[k] = addc_cc(r[k], 0u);
+    u32 k2 = addc(0u, 0u);
+    r[0] += (0u - k2) & 38u;  // wrapped value is < 38*39, cannot carry
+#pragma unroll
+    for (int i = 0; i < 8; i++) h.v[i] = r[i];
 }
 
-// Parallel (single-step) weak reduction: every limb hands its excess to the next limb at once.
-// Input limbs < 2^31; output is tight.  ~31 ALU ops, no serial chain.
-QQ_HD void fe_carry(fe& h, const fe& f) {
-    u32 c[10];
-#pragma unroll
-    for (int i = 0; i < 10; i++) c[i] = (i & 1) ? (f.v[i] >> 25) : (f.v[i] >> 26);
-    h.v[0] = (f.v[0] & QQ_M26) + 19u * c[9];
-#pragma unroll
-    for (int i = 1; i < 10; i++) h.v[i] = (f.v[i] & ((i & 1) ? QQ_M25 : QQ_M26)) + c[i - 1];
+// |x - y| on 4 limbs; returns the all-ones mask when x < y.
+QQ_HD u32 mp_absdiff4(u32* d, const u32* x, const u32* y) {
+    u32 t[4];
+    t[0] = sub_cc(x[0], y[0]);
+    t[1] = subc_cc(x[1], y[1]);
+    t[2] = subc_cc(x[2], y[2]);
+    t[3] = subc_cc(x[3], y[3]);
+    u32 m = subc(0u, 0u);
+    d[0] = sub_cc(t[0] ^ m, m);
+    d[1] = subc_cc(t[1] ^ m, m);
+    d[2] = subc_cc(t[2] ^ m, m);
+    d[3] = subc(t[3] ^ m, m);
+    return m;
 }
 
-// Carry chain on ten 64-bit column sums -> tight limbs.
-QQ_HD void fe_reduce64(fe& h, u64 t[10]) {
-    u64 c;
-    c = t[0] >> 26; t[1] += c; t[0] &= QQ_M26;
-    c = t[4] >> 26; t[5] += c; t[4] &= QQ_M26;
-    c = t[1] >> 25; t[2] += c; t[1] &= QQ_M25;
-    c = t[5] >> 25; t[6] += c; t[5] &= QQ_M25;
-    c = t[2] >> 26; t[3] += c; t[2] &= QQ_M26;
-    c = t[6] >> 26; t[7] += c; t[6] &= QQ_M26;
-    c = t[3] >> 25; t[4] += c; t[3] &= QQ_M25;
-    c = t[7] >> 25; t[8] += c; t[7] &= QQ_M25;
-    c = t[4] >> 26; t[5] += c; t[4] &= QQ_M26;
-    c = t[8] >> 26; t[9] += c; t[8] &= QQ_M26;
-    c = t[9] >> 25; t[0] += c * 19u; t[9] &= QQ_M25;
-    c = t[0] >> 26; t[1] += c; t[0] &= QQ_M26;
-#pragma unroll
-    for (int i = 0; i < 10; i++) h.v[i] = (u32)t[i];
-}
-
-// h = f * g.  Preconditions: 19*g.v[j] < 2^32 for all j (g <= 3.3T); see header for magnitude budget.
+// h = f * g: one level of subtractive Karatsuba over 128-bit halves (3 x 16 products) + reduction (8 products).
+//   f*g = z0 + (z0 + z2 + (f0 - f1)(g1 - g0)) 2^128 + z2 2^256
 QQ_HD void fe_mul_inl(fe& h, const fe& f, const fe& g) {
-    u32 g19[10], f2[10];
+    u32 t[16], zm[8], df[4], dg[4], z1[9];
+    mp_mul4(t, f.v, g.v);
+    mp_mul4(t + 8, f.v + 4, g.v + 4);
+    u32 sf = mp_absdiff4(df, f.v, f.v + 4);
+    u32 sg = mp_absdiff4(dg, g.v + 4, g.v);
+    mp_mul4(zm, df, dg);
+    u32 s = sf ^ sg;  // all-ones: the middle product is negative
+    z1[0] = add_cc(t[0], t[8]);
 #pragma unroll
-    for (int i = 1; i < 10; i++) g19[i] = g.v[i] * 19u;
+    for (int i = 1; i < 8; i++) z1[i] = addc_cc(t[i], t[8 + i]);
+    z1[8] = addc(0u, 0u);
+    // z1 += s ? -zm : zm   (two's complement over 9 limbs; carry-in = s & 1)
+    add_cc(s, s);
 #pragma unroll
-    for (int i = 1; i < 10; i += 2) f2[i] = shl_alu<1>(f.v[i]);
-    // Products are accumulated in chains of two (mul.wide + mad.wide) and the five partial sums of a column are then
-    // added: ptxas keeps a 2-long chain as IMAD.WIDE with a 64-bit addend, whereas it rewrites longer chains into
-    // IMAD.WIDE ..., RZ plus one 64-bit add per product (measured: 114 instead of 155 non-multiply instructions).
-    u64 t[10];
+    for (int i = 0; i < 8; i++) z1[i] = addc_cc(z1[i], zm[i] ^ s);
+    z1[8] = addc(z1[8], s);
+    t[4] = add_cc(t[4], z1[0]);
 #pragma unroll
-    for (int k = 0; k < 10; k++) {
-        u64 part[5];
-#pragma unroll
-        for (int q = 0; q < 5; q++) {
-            u64 acc = 0;
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                int i = 2 * q + e;
-                int j = k - i;
-                bool wrap = false;
-                if (j < 0) { j += 10; wrap = true; }
-                bool both_odd = (i & 1) && (j & 1);
-                u32 a = both_odd ? f2[i] : f.v[i];
-                u32 b = wrap ? g19[j] : g.v[j];
-                acc = (e == 0) ? mul_wide(a, b) : mad_wide(a, b, acc);
-            }
-            part[q] = acc;
-        }
-        t[k] = ((part[0] + part[1]) + part[2]) + (part[3] + part[4]);
-    }
-    fe_reduce64(h, t);
+    for (int i = 1; i < 9; i++) t[4 + i] = addc_cc(t[4 + i], z1[i]);
+    t[13] = addc_cc(t[13], 0u);
+    t[14] = addc_cc(t[14], 0u);
+    t[15] = addc(t[15], 0u);
+    fe_reduce512(h, t);
+}
+// schoolbook variant (64 + 8 products), kept for the bake-off in tools/fe_bench.cu
+QQ_HD void fe_mul_school(fe& h, const fe& f, const fe& g) {
+    u32 t[16];
+    mp_mul8(t, f.v, g.v);
+    fe_reduce512(h, t);
 }
 
-// h = f^2.  Precondition: 19*f.v[j] < 2^32 (f <= 3.3T).
+// t[2n] = 2 * off[2n] + diag(a)   (n = 8)
 QQ_HD void fe_sq_inl(fe& h, const fe& f) {
-    u32 f2[10], f4[10], f19[10];
+    u32 off[16], t[16];
+    mp_sqoff8(off, f.v);
+    // double: funnel shifts (ALU pipe)
+    u32 d[16];
+    d[0] = 0;
 #pragma unroll
-    for (int i = 0; i < 10; i++) {
-        f2[i] = shl_alu<1>(f.v[i]);
-        f4[i] = shl_alu<2>(f.v[i]);
-        f19[i] = f.v[i] * 19u;
+    for (int k = 1; k < 16; k++) {
+#if defined(__CUDA_ARCH__)
+        asm("shf.l.wrap.b32 %0, %1, %2, 1;" : "=r"(d[k]) : "r"(off[k - 1]), "r"(off[k]));
+#else
+        d[k] = (off[k] << 1) | (off[k - 1] >> 31);
+#endif
     }
-    u64 t[10];
+    // add the diagonal a[i]^2 at limbs (2i, 2i+1)
+    t[0] = mad_lo_cc(f.v[0], f.v[0], d[0]);
+    t[1] = madc_hi_cc(f.v[0], f.v[0], d[1]);
 #pragma unroll
-    for (int k = 0; k < 10; k++) {
-        // chains of two products (see fe_mul_inl); a column of the square has 5 or 6 distinct products
-        u64 tot = 0, acc = 0;
-        int len = 0, nparts = 0;
-#pragma unroll
-        for (int i = 0; i < 10; i++) {
-            int j = k - i;
-            bool wrap = false;
-            if (j < 0) { j += 10; wrap = true; }
-            if (j < i) continue;  // each unordered pair once
-            bool both_odd = (i & 1) && (j & 1);
-            int coef = (i == j ? 1 : 2) * (both_odd ? 2 : 1);  // 1, 2 or 4 on the i side; 19 on the j side
-            u32 a = coef == 4 ? f4[i] : (coef == 2 ? f2[i] : f.v[i]);
-            u32 b = wrap ? f19[j] : f.v[j];
-            acc = (len == 0) ? mul_wide(a, b) : mad_wide(a, b, acc);
-            len++;
-            if (len == 2) {
-                tot = (nparts == 0) ? acc : tot + acc;
-                nparts++;
-                len = 0;
-            }
-        }
-        if (len) tot = (nparts == 0) ? acc : tot + acc;
-        t[k] = tot;
+    for (int i = 1; i < 8; i++) {
+        t[2 * i] = madc_lo_cc(f.v[i], f.v[i], d[2 * i]);
+        t[2 * i + 1] = (i == 7) ? madc_hi(f.v[i], f.v[i], d[2 * i + 1]) : madc_hi_cc(f.v[i], f.v[i], d[2 * i + 1]);
     }
-    fe_reduce64(h, t);
+    fe_reduce512(h, t);
 }
 
-// Out-of-line copies for the device build: the big kernels call fe_mul / fe_sq thousands of times per thread, and
-// inlining every call produced 150-370 KB of straight-line SASS per kernel (instruction-cache misses showed up as
-// `no_instruction` stalls in ncu).  Arguments and result travel in registers (by-value ABI), so a call costs only
-// CALL + RET + a few moves.  Define QQ_INLINE_FIELD_OPS to get the fully inlined code back.
 #if defined(__CUDACC__) && !defined(QQ_INLINE_FIELD_OPS)
 static __device__ __noinline__ fe fe_mul_ool(fe f, fe g) {
     fe h;
@@ -223,8 +260,6 @@ static __device__ __noinline__ fe fe_sq_ool(fe f) {
     fe_sq_inl(h, f);
     return h;
 }
-// n >= 1 squarings with the loop inside the callee: the square-root chains (254 squarings per decompress / compress)
-// then pay the call marshalling once per run instead of once per squaring
 static __device__ __noinline__ fe fe_sqn_ool(fe f, int n) {
 #pragma unroll 1
     for (int i = 0; i < n; i++) {
@@ -249,7 +284,6 @@ QQ_HD void fe_sq(fe& h, const fe& f) {
     fe_sq_inl(h, f);
 #endif
 }
-
 QQ_HD void fe_sqn(fe& h, const fe& f, int n) {
 #if defined(__CUDA_ARCH__) && !defined(QQ_INLINE_FIELD_OPS)
     h = fe_sqn_ool(f, n);
@@ -286,49 +320,37 @@ QQ_HD void fe_pow22523(fe& out, const fe& z) {
     fe_mul(out, t0, z);        // 2^252-3
 }
 
-// Canonical little-endian bytes as 8 x u32 words (fully reduced mod p).  Input: limbs < 2^31.
+// Canonical little-endian bytes as 8 x u32 words (fully reduced mod p).  Any input in [0, 2^256).
 QQ_HD void fe_towords(u32 w[8], const fe& f) {
-    fe t;
-    fe_carry(t, f);
-    fe_carry(t, t);  // now every limb within its width except possibly +small on limb 1; value < 2^255 + eps
-    u32 h[10];
+    u32 r[8], q[8];
 #pragma unroll
-    for (int i = 0; i < 10; i++) h[i] = t.v[i];
-    // q = floor((h + 19) / 2^255) in {0,1}: decides whether h >= p
-    u32 q = (19u + h[0]) >> 26;
+    for (int i = 0; i < 8; i++) r[i] = f.v[i];
+    // fold bit 255 twice (2^255 = 19): after the first fold r < 2^255 + 19, after the second r < 2^255
 #pragma unroll
-    for (int i = 1; i < 10; i++) q = (h[i] + q) >> ((i & 1) ? 25 : 26);
-    h[0] += 19u * q;
-    u32 c;
+    for (int pass = 0; pass < 2; pass++) {
+        u32 top = r[7] >> 31;
+        r[7] &= 0x7fffffffu;
+        r[0] = add_cc(r[0], (0u - top) & 19u);
 #pragma unroll
-    for (int i = 0; i < 9; i++) {
-        c = h[i] >> ((i & 1) ? 25 : 26);
-        h[i + 1] += c;
-        h[i] &= (i & 1) ? QQ_M25 : QQ_M26;
+        for (int i = 1; i < 7; i++) r[i] = addc_cc(r[i], 0u);
+        r[7] = addc(r[7], 0u);
     }
-    h[9] &= QQ_M25;  // drop 2^255 * q
-    w[0] = h[0] | (h[1] << 26);
-    w[1] = (h[1] >> 6) | (h[2] << 19);
-    w[2] = (h[2] >> 13) | (h[3] << 13);
-    w[3] = (h[3] >> 19) | (h[4] << 6);
-    w[4] = h[5] | (h[6] << 25);
-    w[5] = (h[6] >> 7) | (h[7] << 19);
-    w[6] = (h[7] >> 13) | (h[8] << 12);
-    w[7] = (h[8] >> 20) | (h[9] << 6);
+    // r in [0, 2^255): r >= p  <=>  r + 19 >= 2^255
+    q[0] = add_cc(r[0], 19u);
+#pragma unroll
+    for (int i = 1; i < 7; i++) q[i] = addc_cc(r[i], 0u);
+    q[7] = addc(r[7], 0u);
+    u32 ge = 0u - (q[7] >> 31);  // all-ones: take r - p = (r + 19) - 2^255
+    q[7] &= 0x7fffffffu;
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = (q[i] & ge) | (r[i] & ~ge);
 }
 
-// Little-endian 8 x u32 words -> limbs; bit 255 is ignored (dalek FieldElement::from_bytes behaviour).
+// Little-endian 8 x u32 words -> field element; bit 255 is ignored (dalek FieldElement::from_bytes behaviour).
 QQ_HD void fe_fromwords(fe& h, const u32 w[8]) {
-    h.v[0] = w[0] & QQ_M26;
-    h.v[1] = ((w[0] >> 26) | (w[1] << 6)) & QQ_M25;
-    h.v[2] = ((w[1] >> 19) | (w[2] << 13)) & QQ_M26;
-    h.v[3] = ((w[2] >> 13) | (w[3] << 19)) & QQ_M25;
-    h.v[4] = (w[3] >> 6) & QQ_M26;
-    h.v[5] = w[4] & QQ_M25;
-    h.v[6] = ((w[4] >> 25) | (w[5] << 7)) & QQ_M26;
-    h.v[7] = ((w[5] >> 19) | (w[6] << 13)) & QQ_M25;
-    h.v[8] = ((w[6] >> 12) | (w[7] << 20)) & QQ_M26;
-    h.v[9] = (w[7] >> 6) & QQ_M25;
+#pragma unroll
+    for (int i = 0; i < 7; i++) h.v[i] = w[i];
+    h.v[7] = w[7] & 0x7fffffffu;
 }
 
 QQ_HD u32 fe_isnegative(const fe& f) {
@@ -346,16 +368,16 @@ QQ_HD u32 fe_iszero(const fe& f) {
 }
 QQ_HD u32 fe_eq(const fe& f, const fe& g) {
     fe d;
-    fe_sub(d, f, g);  // requires g tight
+    fe_sub(d, f, g);
     return fe_iszero(d);
 }
 // h = b ? g : h     (b in {0,1}; branch-free)
 QQ_HD void fe_cmov(fe& h, const fe& g, u32 b) {
     u32 m = 0u - b;
 #pragma unroll
-    for (int i = 0; i < 10; i++) h.v[i] ^= m & (h.v[i] ^ g.v[i]);
+    for (int i = 0; i < 8; i++) h.v[i] ^= m & (h.v[i] ^ g.v[i]);
 }
-// h = b ? -h : h  (h tight)
+// h = b ? -h : h
 QQ_HD void fe_cneg(fe& h, u32 b) {
     fe n;
     fe_neg(n, h);
@@ -364,15 +386,15 @@ QQ_HD void fe_cneg(fe& h, u32 b) {
 QQ_HD void fe_abs(fe& h) { fe_cneg(h, fe_isnegative(h)); }
 
 // ---- constants (generated by tools/gen_consts.py; checked numerically by tests/test_host_arith.py) ----
-#define QQ_FE_CONST(name, a0, a1, a2, a3, a4, a5, a6, a7, a8, a9) \
-    QQ_HD fe name() {                                             \
-        fe r = {{a0, a1, a2, a3, a4, a5, a6, a7, a8, a9}};        \
-        return r;                                                 \
+#define QQ_FE_CONST(name, a0, a1, a2, a3, a4, a5, a6, a7) \
+    QQ_HD fe name() {                                     \
+        fe r = {{a0, a1, a2, a3, a4, a5, a6, a7}};        \
+        return r;                                         \
     }
 #include "fe25519_consts.inc"
 
 // sqrt_ratio_i (RFC 9496 4.2; dalek field.rs sqrt_ratio_i): returns was_square, r = sqrt(u/v) or sqrt(i*u/v), r >= 0.
-// Branch-free (constant-time as written).  u, v tight or loose (<= 2T).
+// Branch-free (constant-time as written).
 QQ_HD u32 fe_sqrt_ratio_i(fe& r, const fe& u, const fe& v) {
     fe v3, v7, t, check, uneg, unegi;
     fe_sq(v3, v);
@@ -385,12 +407,9 @@ QQ_HD u32 fe_sqrt_ratio_i(fe& r, const fe& u, const fe& v) {
     fe_mul(r, r, t);        // r = u v^3 (u v^7)^((p-5)/8)
     fe_sq(check, r);
     fe_mul(check, v, check);  // v r^2
-    fe uc;
-    fe_carry(uc, u);
-    fe_neg(uneg, uc);
+    fe_neg(uneg, u);
     fe_mul(unegi, uneg, fe_sqrt_m1());
-    u32 correct = fe_eq(check, uc);
-    fe_carry(uneg, uneg);
+    u32 correct = fe_eq(check, u);
     u32 flipped = fe_eq(check, uneg);
     u32 flipped_i = fe_eq(check, unegi);
     fe ri;

@@ -5,19 +5,20 @@
 // site reaches through `&Scalar * &RistrettoPoint`, point `+`/`-` and `multiscalar_mul`
 // (reference src/ristretto/keys.rs:277-281, src/elgamal/elgamal.rs:47-52,66-68).  Formulas: HWCD-2008 (RFC 8032 5.1.4).
 //
-// Bound annotations use T = tight limb bound (see fe25519.cuh).  fe_mul(f, g) needs g <= 3.3T and f*g <= ~30 T^2.
+// Field elements are saturated 8 x 32-bit values in [0, 2^256) (fe25519.cuh): every fe_* accepts the full range, so no
+// magnitude bookkeeping is needed here.
 #pragma once
 #include "fe25519.cuh"
 
 namespace qq {
 
-struct ge_p3 {      // extended (X:Y:Z:T), x = X/Z, y = Y/Z, T = XY/Z; coordinates tight
+struct ge_p3 {      // extended (X:Y:Z:T), x = X/Z, y = Y/Z, T = XY/Z
     fe X, Y, Z, T;
 };
-struct ge_cached {  // projective Niels: (Y+X, Y-X, Z, 2dT)
-    fe YpX, YmX, Z, T2d;
+struct ge_cached {  // projective Niels with the factor 2 of the addition formula folded in: (Y+X, Y-X, 2Z, 2dT)
+    fe YpX, YmX, Z2, T2d;
 };
-struct ge_niels {   // affine Niels (Z = 1): (y+x, y-x, 2dxy); limbs tight (stored reduced)
+struct ge_niels {   // affine Niels (Z = 1): (y+x, y-x, 2dxy)
     fe ypx, ymx, xy2d;
 };
 
@@ -29,18 +30,15 @@ QQ_HD void ge_identity(ge_p3& p) {
 }
 
 QQ_HD void ge_to_cached(ge_cached& c, const ge_p3& p) {
-    fe_add(c.YpX, p.Y, p.X);             // 2T
-    fe_sub(c.YmX, p.Y, p.X);             // 3T
-    c.Z = p.Z;
-    fe_mul(c.T2d, p.T, fe_2d());         // T
+    fe_add(c.YpX, p.Y, p.X);
+    fe_sub(c.YmX, p.Y, p.X);
+    fe_add(c.Z2, p.Z, p.Z);
+    fe_mul(c.T2d, p.T, fe_2d());
 }
 // affine Niels from a point with Z == 1 (e.g. straight out of decompress)
 QQ_HD void ge_to_niels_z1(ge_niels& n, const ge_p3& p) {
-    fe t;
-    fe_add(t, p.Y, p.X);
-    fe_carry(n.ypx, t);
-    fe_sub(t, p.Y, p.X);
-    fe_carry(n.ymx, t);
+    fe_add(n.ypx, p.Y, p.X);
+    fe_sub(n.ymx, p.Y, p.X);
     fe_mul(n.xy2d, p.T, fe_2d());
 }
 
@@ -54,7 +52,7 @@ QQ_HD void ge_neg(ge_p3& r, const ge_p3& p) {
 QQ_HD void ge_cached_cneg(ge_cached& c, u32 b) {
     u32 m = 0u - b;
 #pragma unroll
-    for (int i = 0; i < 10; i++) {
+    for (int i = 0; i < QQ_FE_LIMBS; i++) {
         u32 x = m & (c.YpX.v[i] ^ c.YmX.v[i]);
         c.YpX.v[i] ^= x;
         c.YmX.v[i] ^= x;
@@ -66,7 +64,7 @@ QQ_HD void ge_cached_cneg(ge_cached& c, u32 b) {
 QQ_HD void ge_niels_cneg(ge_niels& c, u32 b) {
     u32 m = 0u - b;
 #pragma unroll
-    for (int i = 0; i < 10; i++) {
+    for (int i = 0; i < QQ_FE_LIMBS; i++) {
         u32 x = m & (c.ypx.v[i] ^ c.ymx.v[i]);
         c.ypx.v[i] ^= x;
         c.ymx.v[i] ^= x;
@@ -76,23 +74,22 @@ QQ_HD void ge_niels_cneg(ge_niels& c, u32 b) {
     fe_cmov(c.xy2d, n, b);
 }
 
-// r = p + q  (8 M).  p coordinates <= 2T each (tight or one fe_neg), q as produced by ge_to_cached / cneg.
+// r = p + q  (8 M)
 QQ_HD void ge_add(ge_p3& r, const ge_p3& p, const ge_cached& q) {
     fe a, b, c, d, e, f, g, h, t;
-    fe_sub(t, p.Y, p.X);            // 3T
-    fe_mul(a, t, q.YmX);            // 3T * 3T
-    fe_add(t, p.Y, p.X);            // 2T
-    fe_mul(b, t, q.YpX);            // 2T * 2T
-    fe_mul(c, p.T, q.T2d);          // 2T * 2T
-    fe_mul(d, p.Z, q.Z);
-    fe_add(d, d, d);                // 2T
-    fe_sub(e, b, a);                // 3T
-    fe_sub(f, d, c);                // 4T
-    fe_add(g, d, c);                // 3T
-    fe_add(h, b, a);                // 2T
-    fe_mul(r.X, f, e);              // f-side 4T, g-side 3T
+    fe_sub(t, p.Y, p.X);
+    fe_mul(a, t, q.YmX);
+    fe_add(t, p.Y, p.X);
+    fe_mul(b, t, q.YpX);
+    fe_mul(c, p.T, q.T2d);
+    fe_mul(d, p.Z, q.Z2);           // 2 Z1 Z2
+    fe_sub(e, b, a);
+    fe_sub(f, d, c);
+    fe_add(g, d, c);
+    fe_add(h, b, a);
+    fe_mul(r.X, f, e);
     fe_mul(r.Y, g, h);
-    fe_mul(r.Z, f, g);              // f-side 4T, g-side 3T
+    fe_mul(r.Z, f, g);
     fe_mul(r.T, e, h);
 }
 // r = p + q, q affine Niels (7 M)
@@ -103,10 +100,10 @@ QQ_HD void ge_madd(ge_p3& r, const ge_p3& p, const ge_niels& q) {
     fe_add(t, p.Y, p.X);
     fe_mul(b, t, q.ypx);
     fe_mul(c, p.T, q.xy2d);
-    fe_add(d, p.Z, p.Z);            // 2T (4T if p.Z came from fe_neg; never the case)
+    fe_add(d, p.Z, p.Z);
     fe_sub(e, b, a);
-    fe_sub(f, d, c);                // 4T
-    fe_add(g, d, c);                // 3T
+    fe_sub(f, d, c);
+    fe_add(g, d, c);
     fe_add(h, b, a);
     fe_mul(r.X, f, e);
     fe_mul(r.Y, g, h);
@@ -114,27 +111,24 @@ QQ_HD void ge_madd(ge_p3& r, const ge_p3& p, const ge_niels& q) {
     fe_mul(r.T, e, h);
 }
 
-// r = 2p.  WITH_T = false skips T3 (4S + 3M) when the next operation is another doubling.
-// p.X, p.Y, p.Z tight.  p.T is not read.
+// r = 2p.  WITH_T = false skips T3 (4S + 3M) when the next operation is another doubling.  p.T is not read.
 template <bool WITH_T>
 QQ_HD void ge_dbl(ge_p3& r, const ge_p3& p) {
     fe xx, yy, zz, s, cx, cy, cz, ct, t;
     fe_sq(xx, p.X);
     fe_sq(yy, p.Y);
     fe_sq(zz, p.Z);
-    fe_add(t, p.X, p.Y);            // 2T
+    fe_add(t, p.X, p.Y);
     fe_sq(s, t);
-    fe_add(cy, yy, xx);             // 2T
-    fe_sub(cz, yy, xx);             // 3T
-    fe_sub4(cx, s, cy);             // 5T   (f-side only)
+    fe_add(cy, yy, xx);
+    fe_sub(cz, yy, xx);
+    fe_sub(cx, s, cy);
     fe_add(t, zz, zz);
-    fe_add(t, t, xx);               // 3T
-    fe_sub(t, t, yy);               // 5T   = 2ZZ - (YY - XX)
-    fe_carry(ct, t);                // T
+    fe_sub(ct, t, cz);              // 2ZZ - (YY - XX)
     fe_mul(r.X, cx, ct);
-    fe_mul(r.Y, cy, cz);            // 2T * 3T (g-side 3T)
+    fe_mul(r.Y, cy, cz);
     fe_mul(r.Z, cz, ct);
-    if (WITH_T) fe_mul(r.T, cx, cy);  // 5T * 2T
+    if (WITH_T) fe_mul(r.T, cx, cy);
 }
 
 // Ristretto equality (dalek RistrettoPoint::ct_eq): X1*Y2 == Y1*X2  or  X1*X2 == Y1*Y2

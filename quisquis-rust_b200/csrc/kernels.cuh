@@ -1,9 +1,9 @@
 // CUDA kernels (sm_100a) for the quisquis hot path.  One thread owns one group element; every kernel is a grid-stride
 // loop so the grid can be sized to a multiple of the SM count (148 on B200).  Points travel between kernels as
-// extended coordinates, 4 x 10 limbs = 160 B, read and written with 128-bit accesses; the compressed API buffers
-// (32 B per point / scalar) are read with two 128-bit loads per thread.
+// extended coordinates, 4 x 8 limbs = 128 B (QQ_PT_Q x 16 B), read and written with 128-bit accesses; the compressed API
+// buffers (32 B per point / scalar) are read with two 128-bit loads per thread.
 //
-// The work is bound by integer-multiply issue (IMAD.WIDE.U32 + 64-bit IADD3 pairs), not by HBM: see DESIGN.md.
+// The work is bound by integer-multiply issue (IMAD.WIDE.U32 carry chains), not by HBM: see DESIGN.md.
 #pragma once
 #include "ristretto.cuh"
 #include "scalarmult.cuh"
@@ -45,14 +45,14 @@ __global__ void __launch_bounds__(256) k_decompress(const u32x4* __restrict__ in
         load_words32(w, in, map_index(map, t));
         ge_p3 p;
         u32 v = ristretto_decompress(p, w);
-        ge_p3_store(pts + 10 * t, p);
+        ge_p3_store(pts + QQ_PT_Q * t, p);
         ok[t] = (uint8_t)v;
     }
 }
 
 // ---- variable-base scalar multiplication ------------------------------------------------------------------------
 // item t: point pts[map(t)], scalars s0[t / sdiv] (and s1[t / sdiv] when NS == 2); out0[t] = s0 * P, out1[t] = s1 * P.
-// The per-thread window table lives in `scratch` (gridDim.x * blockDim.x * 90 x 16 B), so it stays L2-resident
+// The per-thread window table lives in `scratch` (gridDim.x * blockDim.x * 72 x 16 B), so it stays L2-resident
 // while the grid-stride loop walks the batch.
 struct vb_args {
     const u32x4* pts;
@@ -71,19 +71,19 @@ template <int NS>
 __global__ void __launch_bounds__(128, 2) k_varbase(vb_args a) {
     size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
-    u32x4* tbl = a.scratch + gtid * (QQ_VB_ENTRIES * 10);
+    u32x4* tbl = a.scratch + gtid * (QQ_VB_ENTRIES * QQ_PT_Q);
     for (size_t t = gtid; t < a.n; t += stride) {
         ge_p3 p, r;
-        ge_p3_load(p, a.pts + 10 * map_index(a.map, t));
+        ge_p3_load(p, a.pts + QQ_PT_Q * map_index(a.map, t));
         vb_build_table(tbl, p);
         u32 s[8];
         load_words32(s, a.s0, t / (size_t)a.sdiv);
         vb_scalarmult(r, tbl, s);
-        ge_p3_store(a.out0 + 10 * t, r);
+        ge_p3_store(a.out0 + QQ_PT_Q * t, r);
         if (NS == 2) {
             load_words32(s, a.s1, t / (size_t)a.sdiv);
             vb_scalarmult(r, tbl, s);
-            ge_p3_store(a.out1 + 10 * t, r);
+            ge_p3_store(a.out1 + QQ_PT_Q * t, r);
         }
     }
 }
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(512) k_fixedbase(const u32* __restrict__ tbl_g
         load_words32(w, s, t);
         ge_p3 r;
         fb_scalarmult<W>(r, tbl_s, w);
-        ge_p3_store(out + 10 * t, r);
+        ge_p3_store(out + QQ_PT_Q * t, r);
     }
 }
 
@@ -124,7 +124,7 @@ __global__ void k_fb_build(u32* tbl, const u32x4* base_compressed, int W, int nw
 
 // ---- finish kernels: combine + compress -------------------------------------------------------------------------
 // A finish job produces one compressed point per item t:  enc( sum of up to 3 extended points ).
-// Source k of output t is  src[k].base + 10 * map(src[k].map, t)  (null base = absent), optionally negated.
+// Source k of output t is  src[k].base + QQ_PT_Q * map(src[k].map, t)  (null base = absent), optionally negated.
 struct fin_src {
     const u32x4* base;
     idx_map map;
@@ -138,13 +138,13 @@ struct fin_args {
     size_t n;
 };
 __device__ __forceinline__ void fin_eval(ge_p3& q, const fin_args& a, size_t t) {
-    ge_p3_load(q, a.src[0].base + 10 * map_index(a.src[0].map, t));
+    ge_p3_load(q, a.src[0].base + QQ_PT_Q * map_index(a.src[0].map, t));
     if (a.src[0].negate) ge_neg(q, q);
 #pragma unroll 1
     for (int k = 1; k < 3; k++) {
         if (a.src[k].base == nullptr) break;
         ge_p3 p;
-        ge_p3_load(p, a.src[k].base + 10 * map_index(a.src[k].map, t));
+        ge_p3_load(p, a.src[k].base + QQ_PT_Q * map_index(a.src[k].map, t));
         if (a.src[k].negate) ge_neg(p, p);
         ge_cached c;
         ge_to_cached(c, p);
@@ -187,8 +187,8 @@ __global__ void __launch_bounds__(256) k_points_equal(const u32x4* __restrict__ 
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
         ge_p3 p, q;
-        ge_p3_load(p, a + 10 * t);
-        ge_p3_load(q, b + 10 * t);
+        ge_p3_load(p, a + QQ_PT_Q * t);
+        ge_p3_load(q, b + QQ_PT_Q * t);
         flag[t] = (uint8_t)ge_ristretto_eq(p, q);
     }
 }
@@ -290,31 +290,31 @@ __global__ void k_key_to_status(const unsigned long long* key, uint8_t* status) 
 // followed by a shared-memory tree over the block.  Used for the identity check and for MSM fallbacks.
 __global__ void __launch_bounds__(128) k_point_sum(const u32x4* __restrict__ in, idx_map map, size_t n,
                                                    u32x4* __restrict__ out) {
-    __shared__ u32x4 sm[128 * 10];
+    __shared__ u32x4 sm[128 * QQ_PT_Q];
     ge_p3 acc;
     ge_identity(acc);
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
         ge_p3 p;
-        ge_p3_load(p, in + 10 * map_index(map, t));
+        ge_p3_load(p, in + QQ_PT_Q * map_index(map, t));
         ge_cached c;
         ge_to_cached(c, p);
         ge_add(acc, acc, c);
     }
-    ge_p3_store(sm + 10 * threadIdx.x, acc);
+    ge_p3_store(sm + QQ_PT_Q * threadIdx.x, acc);
     __syncthreads();
     for (int s = blockDim.x / 2; s > 0; s >>= 1) {
         if (threadIdx.x < s) {
             ge_p3 p;
-            ge_p3_load(p, sm + 10 * (threadIdx.x + s));
+            ge_p3_load(p, sm + QQ_PT_Q * (threadIdx.x + s));
             ge_cached c;
             ge_to_cached(c, p);
             ge_add(acc, acc, c);
-            ge_p3_store(sm + 10 * threadIdx.x, acc);
+            ge_p3_store(sm + QQ_PT_Q * threadIdx.x, acc);
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) ge_p3_store(out + 10 * blockIdx.x, acc);
+    if (threadIdx.x == 0) ge_p3_store(out + QQ_PT_Q * blockIdx.x, acc);
 }
 // single thread: out_xyzt (4 x 32 canonical bytes), out compressed, identity flag, from one extended point
 __global__ void k_point_export(const u32x4* in, u32x4* xyzt, u32x4* compressed, uint8_t* is_identity) {
@@ -344,7 +344,7 @@ __global__ void k_point_import(const u32x4* xyzt, u32x4* pts, size_t k) {
     load_words32(w, xyzt, 4 * t + 1); fe_fromwords(p.Y, w);
     load_words32(w, xyzt, 4 * t + 2); fe_fromwords(p.Z, w);
     load_words32(w, xyzt, 4 * t + 3); fe_fromwords(p.T, w);
-    ge_p3_store(pts + 10 * t, p);
+    ge_p3_store(pts + QQ_PT_Q * t, p);
 }
 // segmented sum: instance j = sum of terms offsets[j]..offsets[j+1]-1, compressed; bad if any term flag set
 __global__ void __launch_bounds__(256) k_segment_sum_compress(const u32x4* __restrict__ terms,
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(256) k_segment_sum_compress(const u32x4* __res
         uint8_t st = 0;
         for (uint32_t t = offsets[j]; t < offsets[j + 1]; t++) {
             ge_p3 p;
-            ge_p3_load(p, terms + 10 * (size_t)t);
+            ge_p3_load(p, terms + QQ_PT_Q * (size_t)t);
             ge_cached c;
             ge_to_cached(c, p);
             ge_add(acc, acc, c);
@@ -381,10 +381,11 @@ __global__ void __launch_bounds__(256) k_segment_sum_compress(const u32x4* __res
 // One thread per instance: the 2..9 terms of an instance (reference call sites: src/accounts/verifier.rs:165-880,
 // src/shuffle/*.rs) share ONE doubling chain -- 252 doublings + 64 table additions per term instead of
 // 252 doublings per term.  Per-term window tables and recoded scalars live in a per-thread global scratch slab
-// (QQ_STRAUS_KMAX terms x 92 x 16 B); instances with more terms are processed in chunks of QQ_STRAUS_KMAX.
+// (QQ_STRAUS_KMAX terms x 74 x 16 B); instances with more terms are processed in chunks of QQ_STRAUS_KMAX.
 // dalek counterpart: backend/serial/scalar_mul/straus.rs.
 #define QQ_STRAUS_KMAX 10
-#define QQ_STRAUS_TERM_Q 92   // 90 x 16 B table + 2 x 16 B recoded scalar
+#define QQ_STRAUS_TABLE_Q (QQ_VB_ENTRIES * QQ_PT_Q)
+#define QQ_STRAUS_TERM_Q (QQ_STRAUS_TABLE_Q + 2)   // 72 x 16 B table + 2 x 16 B recoded scalar
 struct straus_args {
     const u32x4* pts;          // decompressed terms
     const u32x4* scalars;
@@ -414,13 +415,13 @@ __global__ void __launch_bounds__(128, 2) k_straus(straus_args a) {
             int k = (int)((hi - c0) < QQ_STRAUS_KMAX ? (hi - c0) : QQ_STRAUS_KMAX);
             for (int t = 0; t < k; t++) {
                 ge_p3 p;
-                ge_p3_load(p, a.pts + 10 * (size_t)(c0 + t));
+                ge_p3_load(p, a.pts + QQ_PT_Q * (size_t)(c0 + t));
                 u32x4* tb = slab + (size_t)t * QQ_STRAUS_TERM_Q;
                 vb_build_table(tb, p);
                 u32 s[8], rr[9];
                 load_words32(s, a.scalars, c0 + t);
                 sc_recode_bias<4, 64>(rr, s);
-                store_words32(tb + 90, 0, rr);
+                store_words32(tb + QQ_STRAUS_TABLE_Q, 0, rr);
                 uint8_t ts = a.term_status[c0 + t];
                 st = (ts == 2 || st == 2) ? 2 : (st | ts);
             }
@@ -437,12 +438,12 @@ __global__ void __launch_bounds__(128, 2) k_straus(straus_args a) {
 #pragma unroll 1
                 for (int t = 0; t < k; t++) {
                     const u32x4* tb = slab + (size_t)t * QQ_STRAUS_TERM_Q;
-                    u32 word = reinterpret_cast<const u32*>(tb + 90)[w >> 3];
+                    u32 word = reinterpret_cast<const u32*>(tb + QQ_STRAUS_TABLE_Q)[w >> 3];
                     int d = (int)((word >> ((w & 7) * 4)) & 15u) - 8;
                     u32 neg = d < 0 ? 1u : 0u;
                     u32 idx = (u32)(d < 0 ? -d : d);
                     ge_cached c;
-                    ge_cached_load(c, tb + 10 * idx);
+                    ge_cached_load(c, tb + QQ_PT_Q * idx);
                     ge_cached_cneg(c, neg);
                     ge_add(r, r, c);
                 }

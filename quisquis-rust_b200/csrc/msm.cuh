@@ -6,7 +6,7 @@
 // (the result is a canonical encoding); the `None`-on-bad-point behaviour is kept through per-term status.
 //
 // Pipeline for n terms, signed c-bit windows, K = ceil(256 / c) windows, NB = 2^(c-1) buckets per window:
-//   k_msm_prepare     decompress point -> affine Niels (128 B, Z = 1), status, K signed digits, bucket histogram
+//   k_msm_prepare     decompress point -> affine Niels (96 B, Z = 1), status, K signed digits, bucket histogram
 //   k_scan_*          bucket offsets (tile totals, scan of totals, apply)
 //   k_msm_scatter     counting sort of (term, sign) pairs by (window, bucket)
 //   k_msm_order_*     buckets ordered by population (descending) so the lanes of a warp get equal work
@@ -19,30 +19,23 @@
 
 namespace qq {
 
-#define QQ_NIELS_STRIDE_Q 8  // stored affine-Niels point = 8 x 16 B (30 limbs + 2 pad words)
+#define QQ_NIELS_STRIDE_Q 6  // stored affine-Niels point = 3 field elements = 6 x 16 B
 
 __device__ __forceinline__ void niels_store_padded(u32x4* dst, const ge_niels& n) {
-    uint4* d = reinterpret_cast<uint4*>(dst);
-    d[0] = make_uint4(n.ypx.v[0], n.ypx.v[1], n.ypx.v[2], n.ypx.v[3]);
-    d[1] = make_uint4(n.ypx.v[4], n.ypx.v[5], n.ypx.v[6], n.ypx.v[7]);
-    d[2] = make_uint4(n.ypx.v[8], n.ypx.v[9], n.ymx.v[0], n.ymx.v[1]);
-    d[3] = make_uint4(n.ymx.v[2], n.ymx.v[3], n.ymx.v[4], n.ymx.v[5]);
-    d[4] = make_uint4(n.ymx.v[6], n.ymx.v[7], n.ymx.v[8], n.ymx.v[9]);
-    d[5] = make_uint4(n.xy2d.v[0], n.xy2d.v[1], n.xy2d.v[2], n.xy2d.v[3]);
-    d[6] = make_uint4(n.xy2d.v[4], n.xy2d.v[5], n.xy2d.v[6], n.xy2d.v[7]);
-    d[7] = make_uint4(n.xy2d.v[8], n.xy2d.v[9], 0u, 0u);
+    int o = 0;
+    fe_store(dst, o, n.ypx);
+    fe_store(dst, o, n.ymx);
+    fe_store(dst, o, n.xy2d);
 }
 __device__ __forceinline__ void niels_load_padded(ge_niels& n, const u32x4* src) {
     const uint4* s = reinterpret_cast<const uint4*>(src);
     uint4 q;
     q = __ldg(s + 0); n.ypx.v[0] = q.x; n.ypx.v[1] = q.y; n.ypx.v[2] = q.z; n.ypx.v[3] = q.w;
     q = __ldg(s + 1); n.ypx.v[4] = q.x; n.ypx.v[5] = q.y; n.ypx.v[6] = q.z; n.ypx.v[7] = q.w;
-    q = __ldg(s + 2); n.ypx.v[8] = q.x; n.ypx.v[9] = q.y; n.ymx.v[0] = q.z; n.ymx.v[1] = q.w;
-    q = __ldg(s + 3); n.ymx.v[2] = q.x; n.ymx.v[3] = q.y; n.ymx.v[4] = q.z; n.ymx.v[5] = q.w;
-    q = __ldg(s + 4); n.ymx.v[6] = q.x; n.ymx.v[7] = q.y; n.ymx.v[8] = q.z; n.ymx.v[9] = q.w;
-    q = __ldg(s + 5); n.xy2d.v[0] = q.x; n.xy2d.v[1] = q.y; n.xy2d.v[2] = q.z; n.xy2d.v[3] = q.w;
-    q = __ldg(s + 6); n.xy2d.v[4] = q.x; n.xy2d.v[5] = q.y; n.xy2d.v[6] = q.z; n.xy2d.v[7] = q.w;
-    q = __ldg(s + 7); n.xy2d.v[8] = q.x; n.xy2d.v[9] = q.y;
+    q = __ldg(s + 2); n.ymx.v[0] = q.x; n.ymx.v[1] = q.y; n.ymx.v[2] = q.z; n.ymx.v[3] = q.w;
+    q = __ldg(s + 3); n.ymx.v[4] = q.x; n.ymx.v[5] = q.y; n.ymx.v[6] = q.z; n.ymx.v[7] = q.w;
+    q = __ldg(s + 4); n.xy2d.v[0] = q.x; n.xy2d.v[1] = q.y; n.xy2d.v[2] = q.z; n.xy2d.v[3] = q.w;
+    q = __ldg(s + 5); n.xy2d.v[4] = q.x; n.xy2d.v[5] = q.y; n.xy2d.v[6] = q.z; n.xy2d.v[7] = q.w;
 }
 
 // runtime-width signed recoding (see sc_recode_bias): r = s + sum_k 2^(c k + c - 1)
@@ -247,7 +240,7 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(const u32x4* __restrict_
         ge_niels_cneg(nl, v >> 31);
         ge_madd(acc, acc, nl);
     }
-    ge_p3_store(buckets + 10 * (size_t)b, acc);
+    ge_p3_store(buckets + QQ_PT_Q * (size_t)b, acc);
 }
 
 // ---- bucket reduction ------------------------------------------------------------------------------------------------
@@ -260,13 +253,13 @@ __global__ void __launch_bounds__(128) k_msm_reduce_seg(const u32x4* __restrict_
     if (t >= g.K * nseg) return;
     int k = t / nseg, s = t - k * nseg;
     int base = s * SEG;
-    const u32x4* bk = buckets + 10 * ((size_t)k * g.NB + base);
+    const u32x4* bk = buckets + QQ_PT_Q * ((size_t)k * g.NB + base);
     ge_p3 run, sum;
     ge_identity(run);
     ge_identity(sum);
     for (int j = SEG - 1; j >= 0; j--) {
         ge_p3 p;
-        ge_p3_load(p, bk + 10 * j);
+        ge_p3_load(p, bk + QQ_PT_Q * j);
         ge_cached c;
         ge_to_cached(c, p);
         ge_add(run, run, c);
@@ -287,36 +280,36 @@ __global__ void __launch_bounds__(128) k_msm_reduce_seg(const u32x4* __restrict_
         ge_to_cached(cm, m);
         ge_add(sum, sum, cm);
     }
-    ge_p3_store(seg_out + 10 * (size_t)t, sum);
+    ge_p3_store(seg_out + QQ_PT_Q * (size_t)t, sum);
 }
 // block r sums in[r * row_len .. (r + 1) * row_len) -> out[r]
 __global__ void __launch_bounds__(128) k_point_sum_rows(const u32x4* __restrict__ in, int row_len,
                                                         u32x4* __restrict__ out) {
-    __shared__ u32x4 sm[128 * 10];
+    __shared__ u32x4 sm[128 * QQ_PT_Q];
     ge_p3 acc;
     ge_identity(acc);
-    const u32x4* row = in + 10 * (size_t)blockIdx.x * row_len;
+    const u32x4* row = in + QQ_PT_Q * (size_t)blockIdx.x * row_len;
     for (int t = threadIdx.x; t < row_len; t += blockDim.x) {
         ge_p3 p;
-        ge_p3_load(p, row + 10 * t);
+        ge_p3_load(p, row + QQ_PT_Q * t);
         ge_cached c;
         ge_to_cached(c, p);
         ge_add(acc, acc, c);
     }
-    ge_p3_store(sm + 10 * threadIdx.x, acc);
+    ge_p3_store(sm + QQ_PT_Q * threadIdx.x, acc);
     __syncthreads();
     for (int s = blockDim.x / 2; s > 0; s >>= 1) {
         if (threadIdx.x < s) {
             ge_p3 p;
-            ge_p3_load(p, sm + 10 * (threadIdx.x + s));
+            ge_p3_load(p, sm + QQ_PT_Q * (threadIdx.x + s));
             ge_cached c;
             ge_to_cached(c, p);
             ge_add(acc, acc, c);
-            ge_p3_store(sm + 10 * threadIdx.x, acc);
+            ge_p3_store(sm + QQ_PT_Q * threadIdx.x, acc);
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) ge_p3_store(out + 10 * blockIdx.x, acc);
+    if (threadIdx.x == 0) ge_p3_store(out + QQ_PT_Q * blockIdx.x, acc);
 }
 // result = sum_k 2^(c k) win[k].  A chain of c (K - 1) = 240 dependent doublings: latency, not throughput.  Four lanes of one
 // warp cooperate on every doubling -- lane l squares one of (X, Y, Z, X + Y), the four squares are exchanged through
@@ -329,7 +322,7 @@ __global__ void __launch_bounds__(32) k_msm_horner(const u32x4* __restrict__ win
     if (blockIdx.x != 0 || lane >= 4) return;
     const unsigned mask = 0xfu;
     ge_p3 acc;
-    ge_p3_load(acc, win + 10 * (size_t)(g.K - 1));
+    ge_p3_load(acc, win + QQ_PT_Q * (size_t)(g.K - 1));
     // lane l keeps coordinate l of the running point in `mine` (0: X, 1: Y, 2: Z, 3: T)
     fe mine = lane == 0 ? acc.X : (lane == 1 ? acc.Y : (lane == 2 ? acc.Z : acc.T));
     for (int k = g.K - 2; k >= 0; k--) {
@@ -337,7 +330,7 @@ __global__ void __launch_bounds__(32) k_msm_horner(const u32x4* __restrict__ win
             co_s[lane] = mine;
             __syncwarp(mask);
             fe in;
-            if (lane == 3) fe_add(in, co_s[0], co_s[1]);   // X + Y (2T)
+            if (lane == 3) fe_add(in, co_s[0], co_s[1]);   // X + Y
             else in = mine;
             fe sq;
             fe_sq(sq, in);
@@ -347,11 +340,9 @@ __global__ void __launch_bounds__(32) k_msm_horner(const u32x4* __restrict__ win
             fe cx, cy, cz, ct, t;
             fe_add(cy, yy, xx);
             fe_sub(cz, yy, xx);
-            fe_sub4(cx, s, cy);
+            fe_sub(cx, s, cy);
             fe_add(t, zz, zz);
-            fe_add(t, t, xx);
-            fe_sub(t, t, yy);
-            fe_carry(ct, t);
+            fe_sub(ct, t, cz);
             // X3 = cx ct, Y3 = cy cz, Z3 = cz ct, T3 = cx cy
             fe a = (lane == 0 || lane == 3) ? cx : (lane == 1 ? cy : cz);
             fe b = (lane == 0 || lane == 2) ? ct : (lane == 1 ? cz : cy);
@@ -364,7 +355,7 @@ __global__ void __launch_bounds__(32) k_msm_horner(const u32x4* __restrict__ win
         if (lane == 0) {
             ge_p3 r, p;
             r.X = co_s[0]; r.Y = co_s[1]; r.Z = co_s[2]; r.T = co_s[3];
-            ge_p3_load(p, win + 10 * (size_t)k);
+            ge_p3_load(p, win + QQ_PT_Q * (size_t)k);
             ge_cached c;
             ge_to_cached(c, p);
             ge_add(r, r, c);

@@ -13,7 +13,7 @@
 
 using namespace qq;
 
-#define QQ_FB_W 6  // window width of the shared-memory fixed-base tables (43 windows x 33 entries x 120 B = 166 KB)
+#define QQ_FB_W 6  // window width of the shared-memory fixed-base tables (43 windows x 33 entries x 96 B = 136 KB)
 enum { FAM_DEC = 0, FAM_VB = 1, FAM_FB = 2, FAM_FIN = 3, FAM_MSM_BUCKET = 4, FAM_MSM_REDUCE = 5, FAM_COUNT = 6 };
 
 struct qq_ctx {
@@ -219,7 +219,7 @@ static int launch_status(qq_ctx* ctx, const void* s0, const void* s1, const void
     CK(cudaGetLastError());
     return QQ_OK;
 }
-// sum of n extended points (mapped) -> one extended point at `result` (device, 160 B)
+// sum of n extended points (mapped) -> one extended point at `result` (device, 128 B)
 static int launch_point_sum(qq_ctx* ctx, const u32x4* pts, idx_map map, size_t n, u32x4* partials /*>= sms*2*10*/,
                             u32x4* result) {
     int blocks = grid_for(n, 128, ctx->sms * 2);
@@ -404,9 +404,9 @@ static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 static int core_scale_pairs(qq_ctx* ctx, const uint8_t* pk, const uint8_t* s, uint8_t* out, uint8_t* status, size_t n) {
     for (size_t base = 0; base < n; base += QQ_CHUNK) {
         size_t m = n - base < QQ_CHUNK ? n - base : QQ_CHUNK;
-        CKQ(ws_begin(ctx, ws_need({2 * m * 160, 2 * m * 160, 2 * m, vb_scratch_bytes(ctx, 1)})));
-        u32x4* P = ws_take<u32x4>(ctx, 2 * m * 160);
-        u32x4* R = ws_take<u32x4>(ctx, 2 * m * 160);
+        CKQ(ws_begin(ctx, ws_need({2 * m * QQ_PT_BYTES, 2 * m * QQ_PT_BYTES, 2 * m, vb_scratch_bytes(ctx, 1)})));
+        u32x4* P = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);
+        u32x4* R = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);
         uint8_t* ok = ws_take<uint8_t>(ctx, 2 * m);
         u32x4* scratch = ws_take<u32x4>(ctx, vb_scratch_bytes(ctx, 1));
         const uint8_t* pk_c = pk + base * 64;
@@ -424,10 +424,10 @@ static int core_generate_commitment(qq_ctx* ctx, const uint8_t* pk, const uint8_
                                     uint8_t* status, size_t n) {
     for (size_t base = 0; base < n; base += QQ_CHUNK) {
         size_t m = n - base < QQ_CHUNK ? n - base : QQ_CHUNK;
-        CKQ(ws_begin(ctx, ws_need({2 * m * 160, 2 * m * 160, m * 160, 2 * m, vb_scratch_bytes(ctx, 1)})));
-        u32x4* P = ws_take<u32x4>(ctx, 2 * m * 160);
-        u32x4* R = ws_take<u32x4>(ctx, 2 * m * 160);
-        u32x4* F = ws_take<u32x4>(ctx, m * 160);
+        CKQ(ws_begin(ctx, ws_need({2 * m * QQ_PT_BYTES, 2 * m * QQ_PT_BYTES, m * QQ_PT_BYTES, 2 * m, vb_scratch_bytes(ctx, 1)})));
+        u32x4* P = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);
+        u32x4* R = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);
+        u32x4* F = ws_take<u32x4>(ctx, m * QQ_PT_BYTES);
         uint8_t* ok = ws_take<uint8_t>(ctx, 2 * m);
         u32x4* scratch = ws_take<u32x4>(ctx, vb_scratch_bytes(ctx, 1));
         const uint8_t* pk_c = pk + base * 64;
@@ -448,9 +448,9 @@ static int core_add_commitments(qq_ctx* ctx, const uint8_t* a, const uint8_t* b,
                                 uint8_t* status, size_t n) {
     for (size_t base = 0; base < n; base += QQ_CHUNK) {
         size_t m = n - base < QQ_CHUNK ? n - base : QQ_CHUNK;
-        CKQ(ws_begin(ctx, ws_need({2 * m * 160, 2 * m * 160, 2 * m, 2 * m, m, m})));
-        u32x4* A = ws_take<u32x4>(ctx, 2 * m * 160);
-        u32x4* B = ws_take<u32x4>(ctx, 2 * m * 160);
+        CKQ(ws_begin(ctx, ws_need({2 * m * QQ_PT_BYTES, 2 * m * QQ_PT_BYTES, 2 * m, 2 * m, m, m})));
+        u32x4* A = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);
+        u32x4* B = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);
         uint8_t* oka = ws_take<uint8_t>(ctx, 2 * m);
         uint8_t* okb = ws_take<uint8_t>(ctx, 2 * m);
         uint8_t* sa = ws_take<uint8_t>(ctx, m);
@@ -472,11 +472,11 @@ static int core_update_account(qq_ctx* ctx, const uint8_t* acc, const uint8_t* b
                                uint8_t* out, uint8_t* status, size_t n) {
     for (size_t base = 0; base < n; base += QQ_CHUNK) {
         size_t m = n - base < QQ_CHUNK ? n - base : QQ_CHUNK;
-        CKQ(ws_begin(ctx, ws_need({4 * m * 160, 2 * m * 160, 2 * m * 160, m * 160, 4 * m, vb_scratch_bytes(ctx, 2)})));
-        u32x4* P = ws_take<u32x4>(ctx, 4 * m * 160);   // gr, grsk, c, d of every account
-        u32x4* Ru = ws_take<u32x4>(ctx, 2 * m * 160);  // u*gr, u*grsk
-        u32x4* Rc = ws_take<u32x4>(ctx, 2 * m * 160);  // c*gr, c*grsk
-        u32x4* F = ws_take<u32x4>(ctx, m * 160);       // bl*B
+        CKQ(ws_begin(ctx, ws_need({4 * m * QQ_PT_BYTES, 2 * m * QQ_PT_BYTES, 2 * m * QQ_PT_BYTES, m * QQ_PT_BYTES, 4 * m, vb_scratch_bytes(ctx, 2)})));
+        u32x4* P = ws_take<u32x4>(ctx, 4 * m * QQ_PT_BYTES);   // gr, grsk, c, d of every account
+        u32x4* Ru = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);  // u*gr, u*grsk
+        u32x4* Rc = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);  // c*gr, c*grsk
+        u32x4* F = ws_take<u32x4>(ctx, m * QQ_PT_BYTES);       // bl*B
         uint8_t* ok = ws_take<uint8_t>(ctx, 4 * m);
         u32x4* scratch = ws_take<u32x4>(ctx, vb_scratch_bytes(ctx, 2));
         const uint8_t* acc_c = acc + base * 128;
@@ -503,10 +503,10 @@ static int core_verify_account(qq_ctx* ctx, const uint8_t* acc, const uint8_t* s
                                size_t n) {
     for (size_t base = 0; base < n; base += QQ_CHUNK) {
         size_t m = n - base < QQ_CHUNK ? n - base : QQ_CHUNK;
-        CKQ(ws_begin(ctx, ws_need({2 * m * 160, 2 * m * 160, m * 160, 2 * m, 2 * m, m, vb_scratch_bytes(ctx, 1)})));
-        u32x4* P = ws_take<u32x4>(ctx, 2 * m * 160);  // gr, c
-        u32x4* R = ws_take<u32x4>(ctx, 2 * m * 160);  // sk*gr, sk*c
-        u32x4* F = ws_take<u32x4>(ctx, m * 160);      // bl*B
+        CKQ(ws_begin(ctx, ws_need({2 * m * QQ_PT_BYTES, 2 * m * QQ_PT_BYTES, m * QQ_PT_BYTES, 2 * m, 2 * m, m, vb_scratch_bytes(ctx, 1)})));
+        u32x4* P = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);  // gr, c
+        u32x4* R = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);  // sk*gr, sk*c
+        u32x4* F = ws_take<u32x4>(ctx, m * QQ_PT_BYTES);      // bl*B
         uint8_t* ok = ws_take<uint8_t>(ctx, 2 * m);
         uint8_t* eq = ws_take<uint8_t>(ctx, 2 * m);
         uint8_t* pre = ws_take<uint8_t>(ctx, m);
@@ -531,10 +531,10 @@ static int core_verify_pk_update(qq_ctx* ctx, const uint8_t* upd, const uint8_t*
                                  size_t n) {
     for (size_t base = 0; base < n; base += QQ_CHUNK) {
         size_t m = n - base < QQ_CHUNK ? n - base : QQ_CHUNK;
-        CKQ(ws_begin(ctx, ws_need({2 * m * 160, 2 * m * 160, 2 * m * 160, 4 * m, 2 * m, m, m, vb_scratch_bytes(ctx, 1)})));
-        u32x4* P = ws_take<u32x4>(ctx, 2 * m * 160);
-        u32x4* U = ws_take<u32x4>(ctx, 2 * m * 160);
-        u32x4* R = ws_take<u32x4>(ctx, 2 * m * 160);
+        CKQ(ws_begin(ctx, ws_need({2 * m * QQ_PT_BYTES, 2 * m * QQ_PT_BYTES, 2 * m * QQ_PT_BYTES, 4 * m, 2 * m, m, m, vb_scratch_bytes(ctx, 1)})));
+        u32x4* P = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);
+        u32x4* U = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);
+        u32x4* R = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);
         uint8_t* ok = ws_take<uint8_t>(ctx, 4 * m);
         uint8_t* eq = ws_take<uint8_t>(ctx, 2 * m);
         uint8_t* s1 = ws_take<uint8_t>(ctx, m);
@@ -559,12 +559,12 @@ static int core_delta_epsilon(qq_ctx* ctx, const uint8_t* acc, const uint8_t* bl
                               uint8_t* eps, uint8_t* status, size_t n) {
     for (size_t base = 0; base < n; base += QQ_CHUNK) {
         size_t m = n - base < QQ_CHUNK ? n - base : QQ_CHUNK;
-        CKQ(ws_begin(ctx, ws_need({2 * m * 160, 2 * m * 160, m * 160, m * 160, m * 160, 2 * m, vb_scratch_bytes(ctx, 1)})));
-        u32x4* P = ws_take<u32x4>(ctx, 2 * m * 160);   // gr, grsk
-        u32x4* R = ws_take<u32x4>(ctx, 2 * m * 160);   // r*gr, r*grsk
-        u32x4* FB = ws_take<u32x4>(ctx, m * 160);      // bl*B
-        u32x4* RB = ws_take<u32x4>(ctx, m * 160);      // r*B
-        u32x4* RH = ws_take<u32x4>(ctx, m * 160);      // r*H
+        CKQ(ws_begin(ctx, ws_need({2 * m * QQ_PT_BYTES, 2 * m * QQ_PT_BYTES, m * QQ_PT_BYTES, m * QQ_PT_BYTES, m * QQ_PT_BYTES, 2 * m, vb_scratch_bytes(ctx, 1)})));
+        u32x4* P = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);   // gr, grsk
+        u32x4* R = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);   // r*gr, r*grsk
+        u32x4* FB = ws_take<u32x4>(ctx, m * QQ_PT_BYTES);      // bl*B
+        u32x4* RB = ws_take<u32x4>(ctx, m * QQ_PT_BYTES);      // r*B
+        u32x4* RH = ws_take<u32x4>(ctx, m * QQ_PT_BYTES);      // r*H
         uint8_t* ok = ws_take<uint8_t>(ctx, 2 * m);
         u32x4* scratch = ws_take<u32x4>(ctx, vb_scratch_bytes(ctx, 1));
         const uint8_t* acc_c = acc + base * 128;
@@ -593,8 +593,8 @@ static int core_delta_epsilon(qq_ctx* ctx, const uint8_t* acc, const uint8_t* bl
 static int core_fixed_base(qq_ctx* ctx, int which, const uint8_t* s, uint8_t* out, uint8_t* status, size_t n) {
     for (size_t base = 0; base < n; base += QQ_CHUNK) {
         size_t m = n - base < QQ_CHUNK ? n - base : QQ_CHUNK;
-        CKQ(ws_begin(ctx, ws_need({m * 160})));
-        u32x4* F = ws_take<u32x4>(ctx, m * 160);
+        CKQ(ws_begin(ctx, ws_need({m * QQ_PT_BYTES})));
+        u32x4* F = ws_take<u32x4>(ctx, m * QQ_PT_BYTES);
         CKQ(launch_status(ctx, s + base * 32, nullptr, nullptr, nullptr, 0, status + base, m));
         CKQ(launch_fixedbase(ctx, which, s + base * 32, F, m));
         CKQ(launch_finish(ctx, fsrc(F, IDENT), FNONE, FNONE, out + base * 32, IDENT, status + base, m));
@@ -603,7 +603,7 @@ static int core_fixed_base(qq_ctx* ctx, int which, const uint8_t* s, uint8_t* ou
 }
 
 // ---- MSM ----------------------------------------------------------------------------------------------------------
-// result: extended point (device, 160 B) = sum s_i * P_i ; *dstatus (device byte) = 0 / 1 / 2
+// result: extended point (device, 128 B) = sum s_i * P_i ; *dstatus (device byte) = 0 / 1 / 2
 static int core_msm_to_point(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, u32x4* result,
                              uint8_t* dstatus);
 
@@ -615,7 +615,7 @@ static int core_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* po
     size_t grid = (m + 127) / 128;
     if (grid > (size_t)ctx->sms * occ) grid = (size_t)ctx->sms * occ;
     size_t scratch_bytes = grid * 128 * (size_t)QQ_STRAUS_KMAX * QQ_STRAUS_TERM_Q * 16;
-    CKQ(ws_begin(ctx, ws_need({nterms * 160, nterms, nterms, scratch_bytes, m * 4, m * 4, QQ_ORDER_BINS * 4, QQ_ORDER_BINS * 4,
+    CKQ(ws_begin(ctx, ws_need({nterms * QQ_PT_BYTES, nterms, nterms, scratch_bytes, m * 4, m * 4, QQ_ORDER_BINS * 4, QQ_ORDER_BINS * 4,
                                QQ_ORDER_BINS * 4, 4096 * 4})));
     unsigned int* counts = ws_take<unsigned int>(ctx, m * 4);
     unsigned int* order = ws_take<unsigned int>(ctx, m * 4);
@@ -623,7 +623,7 @@ static int core_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* po
     unsigned int* ooff = ws_take<unsigned int>(ctx, QQ_ORDER_BINS * 4);
     unsigned int* ocur = ws_take<unsigned int>(ctx, QQ_ORDER_BINS * 4);
     unsigned int* scan_tmp = ws_take<unsigned int>(ctx, 4096 * 4);
-    u32x4* P = ws_take<u32x4>(ctx, nterms * 160);
+    u32x4* P = ws_take<u32x4>(ctx, nterms * QQ_PT_BYTES);
     uint8_t* ok = ws_take<uint8_t>(ctx, nterms);
     uint8_t* tst = ws_take<uint8_t>(ctx, nterms);
     u32x4* scratch = ws_take<u32x4>(ctx, scratch_bytes);

@@ -21,9 +21,7 @@ QQ_HD u32 fe_invsqrt(fe& r, const fe& v) {
     fe_mul(check, v, check);
     fe_1(one);
     fe_neg(mone, one);
-    fe_carry(mone, mone);
     fe_neg(monei, fe_sqrt_m1());
-    fe_carry(monei, monei);
     u32 correct = fe_eq(check, one);
     u32 flipped = fe_eq(check, mone);
     u32 flipped_i = fe_eq(check, monei);
@@ -48,13 +46,13 @@ QQ_HD u32 ristretto_decompress(ge_p3& p, const u32 w[8]) {
     fe_sq(ss, s);
     fe one;
     fe_1(one);
-    fe_sub(u1, one, ss);                         // 2T
-    fe_add(u2, one, ss);                         // T+1
+    fe_sub(u1, one, ss);
+    fe_add(u2, one, ss);
     fe_sq(u2s, u2);
     fe_sq(u1s, u1);
     fe_mul(t, u1s, fe_d());
-    fe_neg(v, t);                                // 2T
-    fe_sub(v, v, u2s);                           // 4T  (f-side only below)
+    fe_neg(v, t);
+    fe_sub(v, v, u2s);
     fe_mul(t, v, u2s);
     u32 ok = fe_invsqrt(I, t);
     fe_mul(dx, I, u2);
@@ -63,7 +61,6 @@ QQ_HD u32 ristretto_decompress(ge_p3& p, const u32 w[8]) {
     fe_add(t, s, s);
     fe_mul(p.X, t, dx);
     fe_abs(p.X);
-    fe_carry(p.X, p.X);
     fe_mul(p.Y, u1, dy);
     fe_1(p.Z);
     fe_mul(p.T, p.X, p.Y);
@@ -75,8 +72,8 @@ QQ_HD u32 ristretto_decompress(ge_p3& p, const u32 w[8]) {
 // extended point -> canonical 32-byte encoding (8 words)
 QQ_HD void ristretto_compress(u32 w[8], const ge_p3& p) {
     fe u1, u2, t, inv, i1, i2, zinv, deninv, ix, iy, ed, x, y, zy;
-    fe_add(u1, p.Z, p.Y);                        // 2T
-    fe_sub(t, p.Z, p.Y);                         // 3T
+    fe_add(u1, p.Z, p.Y);
+    fe_sub(t, p.Z, p.Y);
     fe_mul(u1, u1, t);
     fe_mul(u2, p.X, p.Y);
     fe_sq(t, u2);
@@ -98,9 +95,9 @@ QQ_HD void ristretto_compress(u32 w[8], const ge_p3& p) {
     fe_cmov(y, ix, rotate);
     fe_cmov(deninv, ed, rotate);
     fe_mul(t, x, zinv);
-    fe yc = y;                                   // tight (p.Y or a product)
+    fe yc = y;
     fe_cneg(yc, fe_isnegative(t));
-    fe_sub(zy, p.Z, yc);                         // yc <= 2p limb-wise after cneg
+    fe_sub(zy, p.Z, yc);
     fe_mul(t, zy, deninv);
     fe_abs(t);
     fe_towords(w, t);

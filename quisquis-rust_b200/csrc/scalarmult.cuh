@@ -18,35 +18,40 @@ struct alignas(16) u32x4 {
     u32 x, y, z, w;
 };
 
+// Memory layouts (all in 16-byte units, u32x4): an extended or cached point is 4 field elements = 8 x 16 B = 128 B,
+// an affine Niels point is 3 field elements = 96 B.
+#define QQ_PT_Q 8
+#define QQ_PT_BYTES (QQ_PT_Q * 16)
 #define QQ_VB_ENTRIES 9
-#define QQ_VB_TABLE_WORDS (QQ_VB_ENTRIES * 40)
+#define QQ_VB_TABLE_WORDS (QQ_VB_ENTRIES * QQ_PT_Q * 4)
 
-QQ_HD void fe_store4(u32x4* dst, int& o, const fe& a, const fe& b) {
-    // two field elements = 20 words = 5 x 128-bit
+QQ_HD void fe_store(u32x4* dst, int& o, const fe& a) {
     u32x4 q;
     q.x = a.v[0]; q.y = a.v[1]; q.z = a.v[2]; q.w = a.v[3]; dst[o++] = q;
     q.x = a.v[4]; q.y = a.v[5]; q.z = a.v[6]; q.w = a.v[7]; dst[o++] = q;
-    q.x = a.v[8]; q.y = a.v[9]; q.z = b.v[0]; q.w = b.v[1]; dst[o++] = q;
-    q.x = b.v[2]; q.y = b.v[3]; q.z = b.v[4]; q.w = b.v[5]; dst[o++] = q;
-    q.x = b.v[6]; q.y = b.v[7]; q.z = b.v[8]; q.w = b.v[9]; dst[o++] = q;
 }
-QQ_HD void fe_load4(const u32x4* src, int& o, fe& a, fe& b) {
+QQ_HD void fe_load(const u32x4* src, int& o, fe& a) {
     u32x4 q;
     q = src[o++]; a.v[0] = q.x; a.v[1] = q.y; a.v[2] = q.z; a.v[3] = q.w;
     q = src[o++]; a.v[4] = q.x; a.v[5] = q.y; a.v[6] = q.z; a.v[7] = q.w;
-    q = src[o++]; a.v[8] = q.x; a.v[9] = q.y; b.v[0] = q.z; b.v[1] = q.w;
-    q = src[o++]; b.v[2] = q.x; b.v[3] = q.y; b.v[4] = q.z; b.v[5] = q.w;
-    q = src[o++]; b.v[6] = q.x; b.v[7] = q.y; b.v[8] = q.z; b.v[9] = q.w;
+}
+QQ_HD void fe_store4(u32x4* dst, int& o, const fe& a, const fe& b) {
+    fe_store(dst, o, a);
+    fe_store(dst, o, b);
+}
+QQ_HD void fe_load4(const u32x4* src, int& o, fe& a, fe& b) {
+    fe_load(src, o, a);
+    fe_load(src, o, b);
 }
 QQ_HD void ge_cached_store(u32x4* dst, const ge_cached& c) {
     int o = 0;
     fe_store4(dst, o, c.YpX, c.YmX);
-    fe_store4(dst, o, c.Z, c.T2d);
+    fe_store4(dst, o, c.Z2, c.T2d);
 }
 QQ_HD void ge_cached_load(ge_cached& c, const u32x4* src) {
     int o = 0;
     fe_load4(src, o, c.YpX, c.YmX);
-    fe_load4(src, o, c.Z, c.T2d);
+    fe_load4(src, o, c.Z2, c.T2d);
 }
 QQ_HD void ge_p3_store(u32x4* dst, const ge_p3& p) {
     int o = 0;
@@ -59,7 +64,7 @@ QQ_HD void ge_p3_load(ge_p3& p, const u32x4* src) {
     fe_load4(src, o, p.Z, p.T);
 }
 
-// Build the 9-entry table {0P, 1P, ..., 8P} (cached form) into tbl (9 x 10 x u32x4 = 1440 B).
+// Build the 9-entry table {0P, 1P, ..., 8P} (cached form) into tbl (9 x 8 x u32x4 = 1152 B).
 QQ_HD void vb_build_table(u32x4* tbl, const ge_p3& p) {
     ge_cached c0, c;
     ge_p3 id, q;
@@ -67,12 +72,12 @@ QQ_HD void vb_build_table(u32x4* tbl, const ge_p3& p) {
     ge_to_cached(c, id);
     ge_cached_store(tbl, c);
     ge_to_cached(c0, p);
-    ge_cached_store(tbl + 10, c0);
+    ge_cached_store(tbl + QQ_PT_Q, c0);
     q = p;
     for (int i = 2; i <= 8; i++) {
         ge_add(q, q, c0);
         ge_to_cached(c, q);
-        ge_cached_store(tbl + 10 * i, c);
+        ge_cached_store(tbl + QQ_PT_Q * i, c);
     }
 }
 
@@ -107,7 +112,7 @@ QQ_HD void vb_scalarmult_t(ge_p3& r, const u32x4* tbl, const u32 s[8]) {
         u32 neg = d < 0 ? 1u : 0u;
         u32 idx = (u32)(d < 0 ? -d : d);
         ge_cached c;
-        ge_cached_load(c, tbl + 10 * idx);
+        ge_cached_load(c, tbl + QQ_PT_Q * idx);
         ge_cached_cneg(c, neg);
         ge_add(r, r, c);
     }
@@ -115,20 +120,20 @@ QQ_HD void vb_scalarmult_t(ge_p3& r, const u32x4* tbl, const u32 s[8]) {
 QQ_HD void vb_scalarmult(ge_p3& r, const u32x4* tbl, const u32 s[8]) { vb_scalarmult_t<false>(r, tbl, s); }
 
 // ---------------------------------------------------------------------------------------------------------
-// Fixed-base tables.  Layout: entry (k, j) at tbl[(k * (2^(W-1) + 1) + j) * 30 .. +30] words:
-// ypx[10], ymx[10], xy2d[10].  j = 0 is the identity (1, 1, 0).
+// Fixed-base tables.  Layout: entry (k, j) at tbl[(k * (2^(W-1) + 1) + j) * 24 .. +24] words:
+// ypx[8], ymx[8], xy2d[8].  j = 0 is the identity (1, 1, 0).
 // ---------------------------------------------------------------------------------------------------------
-#define QQ_NIELS_WORDS 30
+#define QQ_NIELS_WORDS 24
 
 QQ_HD int fb_num_windows(int w) { return (256 + w - 1) / w; }   // W*NW >= 256 keeps the recoding carry-free
 QQ_HD int fb_entries(int w) { return (1 << (w - 1)) + 1; }
 
 QQ_HD void ge_niels_load(ge_niels& n, const u32* src) {
 #pragma unroll
-    for (int i = 0; i < 10; i++) {
+    for (int i = 0; i < 8; i++) {
         n.ypx.v[i] = src[i];
-        n.ymx.v[i] = src[10 + i];
-        n.xy2d.v[i] = src[20 + i];
+        n.ymx.v[i] = src[8 + i];
+        n.xy2d.v[i] = src[16 + i];
     }
 }
 
@@ -183,17 +188,15 @@ QQ_HD void ge_to_niels_affine(u32* dst, const ge_p3& p) {
     fe_mul(x, p.X, zi);
     fe_mul(y, p.Y, zi);
     fe ypx, ymx, xy2d;
-    fe_add(t, y, x);
-    fe_carry(ypx, t);
-    fe_sub(t, y, x);
-    fe_carry(ymx, t);
+    fe_add(ypx, y, x);
+    fe_sub(ymx, y, x);
     fe_mul(t, x, y);
     fe_mul(xy2d, t, fe_2d());
 #pragma unroll
-    for (int i = 0; i < 10; i++) {
+    for (int i = 0; i < 8; i++) {
         dst[i] = ypx.v[i];
-        dst[10 + i] = ymx.v[i];
-        dst[20 + i] = xy2d.v[i];
+        dst[8 + i] = ymx.v[i];
+        dst[16 + i] = xy2d.v[i];
     }
 }
 

@@ -15,26 +15,38 @@ extern "C" {
 
 void hh_fe_mul_limbs(u32* out, const u32* f, const u32* g) {
     fe a, b, c;
-    memcpy(a.v, f, 40);
-    memcpy(b.v, g, 40);
+    memcpy(a.v, f, 32);
+    memcpy(b.v, g, 32);
     fe_mul(c, a, b);
-    memcpy(out, c.v, 40);
+    memcpy(out, c.v, 32);
 }
 void hh_fe_sq_limbs(u32* out, const u32* f) {
     fe a, c;
-    memcpy(a.v, f, 40);
+    memcpy(a.v, f, 32);
     fe_sq(c, a);
-    memcpy(out, c.v, 40);
+    memcpy(out, c.v, 32);
 }
-void hh_fe_carry_limbs(u32* out, const u32* f) {
-    fe a, c;
-    memcpy(a.v, f, 40);
-    fe_carry(c, a);
-    memcpy(out, c.v, 40);
+void hh_fe_mul_school_limbs(u32* out, const u32* f, const u32* g) {
+    fe a, b, c;
+    memcpy(a.v, f, 32);
+    memcpy(b.v, g, 32);
+    fe_mul_school(c, a, b);
+    memcpy(out, c.v, 32);
+}
+void hh_fe_addsub_limbs(u32* sum, u32* diff, u32* neg, const u32* f, const u32* g) {
+    fe a, b, c;
+    memcpy(a.v, f, 32);
+    memcpy(b.v, g, 32);
+    fe_add(c, a, b);
+    memcpy(sum, c.v, 32);
+    fe_sub(c, a, b);
+    memcpy(diff, c.v, 32);
+    fe_neg(c, a);
+    memcpy(neg, c.v, 32);
 }
 void hh_fe_tobytes_limbs(uint8_t* out, const u32* f) {
     fe a;
-    memcpy(a.v, f, 40);
+    memcpy(a.v, f, 32);
     u32 w[8];
     fe_towords(w, a);
     store_words(out, w);
@@ -44,7 +56,7 @@ void hh_fe_frombytes(u32* out, const uint8_t* in) {
     load_words(w, in);
     fe a;
     fe_fromwords(a, w);
-    memcpy(out, a.v, 40);
+    memcpy(out, a.v, 32);
 }
 void hh_fe_const(int which, uint8_t* out) {
     fe c = which == 0 ? fe_d() : which == 1 ? fe_2d() : which == 2 ? fe_sqrt_m1() : which == 3 ? fe_invsqrt_a_minus_d()
@@ -157,7 +169,7 @@ int hh_scalarmult(uint8_t* out, const uint8_t* scalar, const uint8_t* point) {
     load_words(w, point);
     int ok = (int)ristretto_decompress(p, w);
     load_words(s, scalar);
-    std::vector<u32x4> tbl(QQ_VB_ENTRIES * 10);
+    std::vector<u32x4> tbl(QQ_VB_ENTRIES * QQ_PT_Q);
     vb_build_table(tbl.data(), p);
     vb_scalarmult(r, tbl.data(), s);
     ristretto_compress(w, r);

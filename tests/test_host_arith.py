@@ -1,5 +1,5 @@
 """CPU tests (no GPU): the exact device arithmetic (quisquis-rust_b200/csrc/*.cuh compiled for the host by
-tests/csrc/host_harness.cpp -- test infrastructure only) against the big-int oracle, including limb bounds."""
+tests/csrc/host_harness.cpp -- test infrastructure only) against the big-int oracle, over the full 256-bit range."""
 import ctypes
 import os
 import random
@@ -11,7 +11,6 @@ import ristretto_ref as R
 from qq_testlib import invalid_encodings
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-OFFS = [0, 26, 51, 77, 102, 128, 153, 179, 204, 230]
 
 
 @pytest.fixture(scope="module")
@@ -27,11 +26,37 @@ def hh():
     return lib
 
 
+A8 = ctypes.c_uint32 * 8
+
+
+def limbs(x):
+    return A8(*[(x >> (32 * i)) & 0xFFFFFFFF for i in range(8)])
+
+
 def val(l):
-    return sum(int(x) << o for x, o in zip(l, OFFS)) % R.P
+    return sum(int(l[i]) << (32 * i) for i in range(8))
 
 
-A10 = ctypes.c_uint32 * 10
+EDGES = [0, 1, 2, 18, 19, 20, 37, 38, 39, R.P - 1, R.P, R.P + 1, 2 * R.P - 1, 2 * R.P, 2 * R.P + 1, 2**256 - 1,
+         2**256 - 2, 2**256 - 38, 2**256 - 39, 2**255, 2**255 - 1, 2**255 - 19, 2**255 + 18, 2**128, 2**128 - 1,
+         2**128 + 1, (2**128 - 1) << 128, 2**256 - 2**128, 2**224, 2**32 - 1, (2**32 - 1) << 224]
+
+
+def rand_fe(rnd):
+    """Field elements in the saturated form: ANY value in [0, 2^256), biased towards the carry/borrow corner cases."""
+    r = rnd.random()
+    if r < 0.25:
+        return rnd.choice(EDGES)
+    if r < 0.35:
+        return (2**256 - 1) ^ rnd.getrandbits(rnd.choice([6, 20, 70]))
+    if r < 0.45:
+        return rnd.getrandbits(rnd.choice([6, 40, 130]))
+    if r < 0.6:  # equal / nearly equal 128-bit halves: the |f0 - f1| path of the Karatsuba multiplication
+        h = rnd.getrandbits(128)
+        return h | ((h ^ rnd.getrandbits(rnd.choice([0, 1, 3, 33]))) << 128)
+    if r < 0.7:  # limbs of all-ones / all-zeros
+        return sum((0xFFFFFFFF if rnd.random() < 0.5 else 0) << (32 * i) for i in range(8))
+    return rnd.getrandbits(256)
 
 
 def test_field_constants(hh):
@@ -42,40 +67,33 @@ def test_field_constants(hh):
         assert int.from_bytes(o.raw, "little") == v
 
 
-def test_field_mul_sq_at_the_limb_bounds(hh):
+def test_field_ops_over_the_full_saturated_range(hh):
+    """mul (Karatsuba and schoolbook), sq, add, sub, neg and canonical encoding for arbitrary 256-bit inputs."""
     rnd = random.Random(11)
-
-    def rl(sc):
-        return [rnd.randrange(0, int(sc * (1 << (26 if i % 2 == 0 else 25)))) for i in range(10)]
-
-    def mx(sc):
-        return [int(sc * (1 << (26 if i % 2 == 0 else 25))) - 1 for i in range(10)]
-    for it in range(4000):
-        sf, sg = rnd.choice([1.0, 2.0, 3.0, 4.0, 5.0, 9.0]), rnd.choice([1.0, 2.0, 3.0, 3.3])
-        if sf * sg > 30:
-            sf, sg = 9.0, 3.3
-        f = mx(sf) if it % 5 == 0 else rl(sf)
-        g = mx(sg) if it % 10 == 0 else rl(sg)
-        o = A10()
-        hh.hh_fe_mul_limbs(o, A10(*f), A10(*g))
-        assert val(o) == val(f) * val(g) % R.P
-        for i in range(10):
-            assert o[i] < ((1 << 26) if i % 2 == 0 else (1 << 25) + (1 << 18))
-        ff = mx(3.3) if it % 7 == 0 else rl(min(sf, 3.3))
-        hh.hh_fe_sq_limbs(o, A10(*ff))
-        assert val(o) == val(ff) ** 2 % R.P
+    for it in range(30000):
+        f, g = rand_fe(rnd), rand_fe(rnd)
+        o, o2, o3 = A8(), A8(), A8()
+        hh.hh_fe_mul_limbs(o, limbs(f), limbs(g))
+        assert val(o) % R.P == f * g % R.P, (hex(f), hex(g))
+        hh.hh_fe_mul_school_limbs(o, limbs(f), limbs(g))
+        assert val(o) % R.P == f * g % R.P, (hex(f), hex(g))
+        hh.hh_fe_sq_limbs(o, limbs(f))
+        assert val(o) % R.P == f * f % R.P, hex(f)
+        hh.hh_fe_addsub_limbs(o, o2, o3, limbs(f), limbs(g))
+        assert val(o) % R.P == (f + g) % R.P and val(o2) % R.P == (f - g) % R.P and val(o3) % R.P == -f % R.P
         b = ctypes.create_string_buffer(32)
-        hh.hh_fe_tobytes_limbs(b, A10(*f))
-        assert int.from_bytes(b.raw, "little") == val(f)
+        hh.hh_fe_tobytes_limbs(b, limbs(f))
+        assert int.from_bytes(b.raw, "little") == f % R.P
 
 
 def test_canonical_encoding_edges(hh):
-    for x in [0, 1, R.P - 1, R.P, R.P + 1, 2**255 - 1, 2 * R.P - 1, 2 * R.P, 2 * R.P + 5, 19, 2**255 - 20]:
-        l = [(x >> o) & ((1 << (26 if i % 2 == 0 else 25)) - 1) for i, o in enumerate(OFFS)]
-        l[9] += (x >> 255) << 25
+    for x in EDGES:
         b = ctypes.create_string_buffer(32)
-        hh.hh_fe_tobytes_limbs(b, A10(*l))
+        hh.hh_fe_tobytes_limbs(b, limbs(x))
         assert int.from_bytes(b.raw, "little") == x % R.P
+        o = A8()
+        hh.hh_fe_frombytes(o, x.to_bytes(32, "little"))
+        assert val(o) == x & (2**255 - 1)      # bit 255 ignored, like dalek's FieldElement::from_bytes
 
 
 def test_sqrt_ratio_and_invert(hh):
