@@ -252,7 +252,11 @@ QQ_HD void fe_sq_inl(fe& h, const fe& f) {
 #if defined(__CUDACC__) && !defined(QQ_INLINE_FIELD_OPS)
 static __device__ __noinline__ fe fe_mul_ool(fe f, fe g) {
     fe h;
+#if defined(QQ_FE_MUL_SCHOOLBOOK)
+    fe_mul_school(h, f, g);
+#else
     fe_mul_inl(h, f, g);
+#endif
     return h;
 }
 static __device__ __noinline__ fe fe_sq_ool(fe f) {

@@ -74,62 +74,81 @@ QQ_HD void ge_niels_cneg(ge_niels& c, u32 b) {
     fe_cmov(c.xy2d, n, b);
 }
 
+// Field-multiplication flavour used inside a group operation: INL = true inlines the products (straight-line code
+// whose independent multiplications ptxas interleaves), INL = false calls the out-of-line fe_mul / fe_sq.
+template <bool INL>
+QQ_HD void fe_mul_t(fe& h, const fe& f, const fe& g) {
+    if (INL) fe_mul_inl(h, f, g);
+    else fe_mul(h, f, g);
+}
+template <bool INL>
+QQ_HD void fe_sq_t(fe& h, const fe& f) {
+    if (INL) fe_sq_inl(h, f);
+    else fe_sq(h, f);
+}
+
 // r = p + q  (8 M)
-QQ_HD void ge_add(ge_p3& r, const ge_p3& p, const ge_cached& q) {
+template <bool INL>
+QQ_HD void ge_add_t(ge_p3& r, const ge_p3& p, const ge_cached& q) {
     fe a, b, c, d, e, f, g, h, t;
     fe_sub(t, p.Y, p.X);
-    fe_mul(a, t, q.YmX);
+    fe_mul_t<INL>(a, t, q.YmX);
     fe_add(t, p.Y, p.X);
-    fe_mul(b, t, q.YpX);
-    fe_mul(c, p.T, q.T2d);
-    fe_mul(d, p.Z, q.Z2);           // 2 Z1 Z2
+    fe_mul_t<INL>(b, t, q.YpX);
+    fe_mul_t<INL>(c, p.T, q.T2d);
+    fe_mul_t<INL>(d, p.Z, q.Z2);           // 2 Z1 Z2
     fe_sub(e, b, a);
     fe_sub(f, d, c);
     fe_add(g, d, c);
     fe_add(h, b, a);
-    fe_mul(r.X, f, e);
-    fe_mul(r.Y, g, h);
-    fe_mul(r.Z, f, g);
-    fe_mul(r.T, e, h);
+    fe_mul_t<INL>(r.X, f, e);
+    fe_mul_t<INL>(r.Y, g, h);
+    fe_mul_t<INL>(r.Z, f, g);
+    fe_mul_t<INL>(r.T, e, h);
 }
+QQ_HD void ge_add(ge_p3& r, const ge_p3& p, const ge_cached& q) { ge_add_t<false>(r, p, q); }
 // r = p + q, q affine Niels (7 M)
-QQ_HD void ge_madd(ge_p3& r, const ge_p3& p, const ge_niels& q) {
+template <bool INL>
+QQ_HD void ge_madd_t(ge_p3& r, const ge_p3& p, const ge_niels& q) {
     fe a, b, c, d, e, f, g, h, t;
     fe_sub(t, p.Y, p.X);
-    fe_mul(a, t, q.ymx);
+    fe_mul_t<INL>(a, t, q.ymx);
     fe_add(t, p.Y, p.X);
-    fe_mul(b, t, q.ypx);
-    fe_mul(c, p.T, q.xy2d);
+    fe_mul_t<INL>(b, t, q.ypx);
+    fe_mul_t<INL>(c, p.T, q.xy2d);
     fe_add(d, p.Z, p.Z);
     fe_sub(e, b, a);
     fe_sub(f, d, c);
     fe_add(g, d, c);
     fe_add(h, b, a);
-    fe_mul(r.X, f, e);
-    fe_mul(r.Y, g, h);
-    fe_mul(r.Z, f, g);
-    fe_mul(r.T, e, h);
+    fe_mul_t<INL>(r.X, f, e);
+    fe_mul_t<INL>(r.Y, g, h);
+    fe_mul_t<INL>(r.Z, f, g);
+    fe_mul_t<INL>(r.T, e, h);
 }
+QQ_HD void ge_madd(ge_p3& r, const ge_p3& p, const ge_niels& q) { ge_madd_t<false>(r, p, q); }
 
 // r = 2p.  WITH_T = false skips T3 (4S + 3M) when the next operation is another doubling.  p.T is not read.
-template <bool WITH_T>
-QQ_HD void ge_dbl(ge_p3& r, const ge_p3& p) {
+template <bool WITH_T, bool INL>
+QQ_HD void ge_dbl_t(ge_p3& r, const ge_p3& p) {
     fe xx, yy, zz, s, cx, cy, cz, ct, t;
-    fe_sq(xx, p.X);
-    fe_sq(yy, p.Y);
-    fe_sq(zz, p.Z);
+    fe_sq_t<INL>(xx, p.X);
+    fe_sq_t<INL>(yy, p.Y);
+    fe_sq_t<INL>(zz, p.Z);
     fe_add(t, p.X, p.Y);
-    fe_sq(s, t);
+    fe_sq_t<INL>(s, t);
     fe_add(cy, yy, xx);
     fe_sub(cz, yy, xx);
     fe_sub(cx, s, cy);
     fe_add(t, zz, zz);
     fe_sub(ct, t, cz);              // 2ZZ - (YY - XX)
-    fe_mul(r.X, cx, ct);
-    fe_mul(r.Y, cy, cz);
-    fe_mul(r.Z, cz, ct);
-    if (WITH_T) fe_mul(r.T, cx, cy);
+    fe_mul_t<INL>(r.X, cx, ct);
+    fe_mul_t<INL>(r.Y, cy, cz);
+    fe_mul_t<INL>(r.Z, cz, ct);
+    if (WITH_T) fe_mul_t<INL>(r.T, cx, cy);
 }
+template <bool WITH_T>
+QQ_HD void ge_dbl(ge_p3& r, const ge_p3& p) { ge_dbl_t<WITH_T, false>(r, p); }
 
 // Ristretto equality (dalek RistrettoPoint::ct_eq): X1*Y2 == Y1*X2  or  X1*X2 == Y1*Y2
 QQ_HD u32 ge_ristretto_eq(const ge_p3& p, const ge_p3& q) {

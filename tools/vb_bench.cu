@@ -4,25 +4,28 @@
 #include <cstdlib>
 #include <cuda_runtime.h>
 #include "kernels.cuh"
+#ifndef QQ_BUILD_TAG
+#define QQ_BUILD_TAG "default"
+#endif
 using namespace qq;
 
 template <int NS, int MINB, bool ROLLED>
 __global__ void __launch_bounds__(128, MINB) k_vb(vb_args a) {
     size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
-    u32x4* tbl = a.scratch + gtid * (QQ_VB_ENTRIES * 10);
+    u32x4* tbl = a.scratch + gtid * (QQ_VB_ENTRIES * QQ_PT_Q);
     for (size_t t = gtid; t < a.n; t += stride) {
         ge_p3 p, r;
-        ge_p3_load(p, a.pts + 10 * map_index(a.map, t));
+        ge_p3_load(p, a.pts + QQ_PT_Q * map_index(a.map, t));
         vb_build_table(tbl, p);
         u32 s[8];
         load_words32(s, a.s0, t / (size_t)a.sdiv);
         vb_scalarmult_t<ROLLED>(r, tbl, s);
-        ge_p3_store(a.out0 + 10 * t, r);
+        ge_p3_store(a.out0 + QQ_PT_Q * t, r);
         if (NS == 2) {
             load_words32(s, a.s1, t / (size_t)a.sdiv);
             vb_scalarmult_t<ROLLED>(r, tbl, s);
-            ge_p3_store(a.out1 + 10 * t, r);
+            ge_p3_store(a.out1 + QQ_PT_Q * t, r);
         }
     }
 }
@@ -35,12 +38,12 @@ static void run(size_t n, int sms) {
     cudaFuncGetAttributes(&fa, k_vb<2, MINB, ROLLED>);
     int grid = sms * occ;
     u32x4 *pts, *s0, *s1, *o0, *o1, *scratch;
-    cudaMalloc(&pts, n * 160); cudaMalloc(&s0, n * 32); cudaMalloc(&s1, n * 32);
-    cudaMalloc(&o0, n * 160); cudaMalloc(&o1, n * 160);
+    cudaMalloc(&pts, n * QQ_PT_BYTES); cudaMalloc(&s0, n * 32); cudaMalloc(&s1, n * 32);
+    cudaMalloc(&o0, n * QQ_PT_BYTES); cudaMalloc(&o1, n * QQ_PT_BYTES);
     cudaMalloc(&scratch, (size_t)grid * 128 * QQ_VB_TABLE_WORDS * 4);
-    size_t words = n * 40;
+    size_t words = n * 32;
     u32* h = (u32*)malloc(words * 4);
-    for (size_t i = 0; i < words; i++) h[i] = (u32)(rand()) & 0x1ffffff;
+    for (size_t i = 0; i < words; i++) h[i] = (u32)rand() * 2654435761u;
     cudaMemcpy(pts, h, words * 4, cudaMemcpyHostToDevice);
     for (size_t i = 0; i < n * 8; i++) h[i] = (u32)rand() * 2654435761u;
     for (size_t i = 7; i < n * 8; i += 8) h[i] &= 0x0fffffff;
@@ -59,13 +62,17 @@ static void run(size_t n, int sms) {
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         if (ms < best) best = ms;
     }
-    printf("{\"variant\": \"minb%d_%s\", \"regs\": %d, \"local_bytes\": %zu, \"blocks_per_sm\": %d, \"n_items\": %zu, \"ms\": %.3f, \"scalar_mults_per_s\": %.4e, \"err\": \"%s\"}\n",
+    printf("{\"build\": \"" QQ_BUILD_TAG "\", \"variant\": \"minb%d_%s\", \"regs\": %d, \"local_bytes\": %zu, \"blocks_per_sm\": %d, \"n_items\": %zu, \"ms\": %.3f, \"scalar_mults_per_s\": %.4e, \"err\": \"%s\"}\n",
            MINB, ROLLED ? "rolled" : "unrolled", fa.numRegs, (size_t)fa.localSizeBytes, occ, n, best, 2.0 * n / (best * 1e-3), cudaGetErrorString(cudaGetLastError()));
     cudaFree(pts); cudaFree(s0); cudaFree(s1); cudaFree(o0); cudaFree(o1); cudaFree(scratch); free(h);
 }
 int main() {
     cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
     size_t n = 1 << 18;
+#ifdef QQ_VB_PROFILE_ONLY
+    run<2, false>(1 << 16, p.multiProcessorCount);
+    return 0;
+#endif
     run<2, false>(n, p.multiProcessorCount);
     run<2, true>(n, p.multiProcessorCount);
     run<3, false>(n, p.multiProcessorCount);
