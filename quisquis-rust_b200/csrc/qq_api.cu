@@ -147,7 +147,7 @@ static int launch_decompress(qq_ctx* ctx, const void* in, idx_map map, u32x4* pt
     return QQ_OK;
 }
 static size_t vb_scratch_bytes(qq_ctx* ctx, int ns) {
-    return (size_t)ctx->sms * ctx->vb_blocks_per_sm[ns] * 128 * QQ_VB_TABLE_WORDS * 4;
+    return (size_t)ctx->sms * ctx->vb_blocks_per_sm[ns] * 128 * (ns == 2 ? QQ_VBS_TABLE_WORDS : QQ_VB_TABLE_WORDS) * 4;
 }
 static int launch_varbase(qq_ctx* ctx, int ns, const u32x4* pts, idx_map map, const void* s0, const void* s1, int sdiv,
                           u32x4* out0, u32x4* out1, u32x4* scratch, size_t n) {
@@ -158,7 +158,7 @@ static int launch_varbase(qq_ctx* ctx, int ns, const u32x4* pts, idx_map map, co
     int grid = ctx->sms * ctx->vb_blocks_per_sm[ns];
     span_begin(ctx, FAM_VB);
     if (ns == 1) k_varbase<1><<<grid, 128, 0, ctx->stream>>>(a);
-    else k_varbase<2><<<grid, 128, 0, ctx->stream>>>(a);
+    else k_varbase_split<<<grid, 128, 0, ctx->stream>>>(a);
     span_end(ctx);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -263,7 +263,7 @@ extern "C" int qq_init(qq_ctx** out, int device) {
         int occ = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_varbase<1>, 128, 0));
         ctx->vb_blocks_per_sm[1] = occ > 0 ? occ : 1;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_varbase<2>, 128, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_varbase_split, 128, 0));
         ctx->vb_blocks_per_sm[2] = occ > 0 ? occ : 1;
         // fixed-base tables for B and H, built on the device from their compressed encodings
         static const uint8_t BASE_PK[64] = {

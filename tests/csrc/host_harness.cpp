@@ -176,6 +176,24 @@ int hh_scalarmult(uint8_t* out, const uint8_t* scalar, const uint8_t* point) {
     store_words(out, w);
     return ok | ((int)sc_is_canonical(s) << 1);
 }
+// split variable base (two scalars, one point): out0 = s0 * P, out1 = s1 * P
+int hh_scalarmult_split(uint8_t* out0, uint8_t* out1, const uint8_t* s0, const uint8_t* s1, const uint8_t* point) {
+    u32 w[8], s[8];
+    ge_p3 p, r;
+    load_words(w, point);
+    int ok = (int)ristretto_decompress(p, w);
+    std::vector<u32x4> tbl(QQ_VBS_TABLE_Q);
+    vbs_build_tables(tbl.data(), p);
+    load_words(s, s0);
+    vbs_scalarmult(r, tbl.data(), s);
+    ristretto_compress(w, r);
+    store_words(out0, w);
+    load_words(s, s1);
+    vbs_scalarmult(r, tbl.data(), s);
+    ristretto_compress(w, r);
+    store_words(out1, w);
+    return ok;
+}
 // fixed base: W in {4,5,6,8}; builds the table on each call into caller-provided buffer (words)
 size_t hh_fb_table_words(int W) { return (size_t)fb_num_windows(W) * fb_entries(W) * QQ_NIELS_WORDS; }
 int hh_fb_build(u32* tbl, int W, const uint8_t* base) {

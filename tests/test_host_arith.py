@@ -172,6 +172,20 @@ def test_group_law_and_scalar_mult(hh):
         assert o.raw == R.compress(R.mul(s, R.decompress(p)))
 
 
+def test_split_variable_base(hh):
+    # vbs_*: four 16-digit quarters over P, 2^64 P, 2^128 P, 2^192 P -- same results as the plain window method
+    rnd = random.Random(16)
+    edge = [0, 1, 2, R.L - 1, 8, R.L - 8, 2**64, 2**64 - 1, 2**128 + 2**64, 2**192 - 1, 2**252, 8 * (16**64 - 1) // 15 % R.L]
+    for i in range(40):
+        s0 = edge[i] if i < len(edge) else rnd.randrange(R.L)
+        s1 = edge[-1 - i] if i < len(edge) else rnd.randrange(R.L)
+        p = bytes(32) if i == 3 else R.compress(R.mul(rnd.randrange(R.L), R.BASEPOINT))
+        o0, o1 = ctypes.create_string_buffer(32), ctypes.create_string_buffer(32)
+        assert hh.hh_scalarmult_split(o0, o1, s0.to_bytes(32, "little"), s1.to_bytes(32, "little"), p) == 1
+        assert o0.raw == R.compress(R.mul(s0, R.decompress(p)))
+        assert o1.raw == R.compress(R.mul(s1, R.decompress(p)))
+
+
 @pytest.mark.parametrize("W", [4, 6])
 def test_fixed_base_tables(hh, W):
     rnd = random.Random(15)

@@ -9,38 +9,40 @@
 #endif
 using namespace qq;
 
-template <int NS, int MINB, bool ROLLED>
+// MODE 0: one 9-entry table, 252 doublings per scalar.  MODE 1: split tables (vbs_*), 192 + 60 per scalar.
+template <int MINB, int MODE>
 __global__ void __launch_bounds__(128, MINB) k_vb(vb_args a) {
     size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
-    u32x4* tbl = a.scratch + gtid * (QQ_VB_ENTRIES * QQ_PT_Q);
+    u32x4* tbl = a.scratch + gtid * (MODE ? QQ_VBS_TABLE_Q : QQ_VB_ENTRIES * QQ_PT_Q);
     for (size_t t = gtid; t < a.n; t += stride) {
         ge_p3 p, r;
         ge_p3_load(p, a.pts + QQ_PT_Q * map_index(a.map, t));
-        vb_build_table(tbl, p);
+        if (MODE) vbs_build_tables(tbl, p);
+        else vb_build_table(tbl, p);
         u32 s[8];
         load_words32(s, a.s0, t / (size_t)a.sdiv);
-        vb_scalarmult_t<ROLLED>(r, tbl, s);
+        if (MODE) vbs_scalarmult(r, tbl, s);
+        else vb_scalarmult(r, tbl, s);
         ge_p3_store(a.out0 + QQ_PT_Q * t, r);
-        if (NS == 2) {
-            load_words32(s, a.s1, t / (size_t)a.sdiv);
-            vb_scalarmult_t<ROLLED>(r, tbl, s);
-            ge_p3_store(a.out1 + QQ_PT_Q * t, r);
-        }
+        load_words32(s, a.s1, t / (size_t)a.sdiv);
+        if (MODE) vbs_scalarmult(r, tbl, s);
+        else vb_scalarmult(r, tbl, s);
+        ge_p3_store(a.out1 + QQ_PT_Q * t, r);
     }
 }
 
-template <int MINB, bool ROLLED>
+template <int MINB, int MODE>
 static void run(size_t n, int sms) {
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_vb<2, MINB, ROLLED>, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_vb<MINB, MODE>, 128, 0);
     cudaFuncAttributes fa;
-    cudaFuncGetAttributes(&fa, k_vb<2, MINB, ROLLED>);
+    cudaFuncGetAttributes(&fa, k_vb<MINB, MODE>);
     int grid = sms * occ;
     u32x4 *pts, *s0, *s1, *o0, *o1, *scratch;
     cudaMalloc(&pts, n * QQ_PT_BYTES); cudaMalloc(&s0, n * 32); cudaMalloc(&s1, n * 32);
     cudaMalloc(&o0, n * QQ_PT_BYTES); cudaMalloc(&o1, n * QQ_PT_BYTES);
-    cudaMalloc(&scratch, (size_t)grid * 128 * QQ_VB_TABLE_WORDS * 4);
+    cudaMalloc(&scratch, (size_t)grid * 128 * QQ_VBS_TABLE_WORDS * 4);
     size_t words = n * 32;
     u32* h = (u32*)malloc(words * 4);
     for (size_t i = 0; i < words; i++) h[i] = (u32)rand() * 2654435761u;
@@ -52,32 +54,32 @@ static void run(size_t n, int sms) {
     vb_args a;
     a.pts = pts; a.map = idx_map{1, 1, {0, 0, 0, 0}}; a.s0 = s0; a.s1 = s1; a.sdiv = 1; a.out0 = o0; a.out1 = o1; a.scratch = scratch; a.n = n;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    k_vb<2, MINB, ROLLED><<<grid, 128>>>(a);
+    k_vb<MINB, MODE><<<grid, 128>>>(a);
     cudaDeviceSynchronize();
     float best = 1e30f;
     for (int r = 0; r < 2; r++) {
         cudaEventRecord(e0);
-        k_vb<2, MINB, ROLLED><<<grid, 128>>>(a);
+        k_vb<MINB, MODE><<<grid, 128>>>(a);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         if (ms < best) best = ms;
     }
     printf("{\"build\": \"" QQ_BUILD_TAG "\", \"variant\": \"minb%d_%s\", \"regs\": %d, \"local_bytes\": %zu, \"blocks_per_sm\": %d, \"n_items\": %zu, \"ms\": %.3f, \"scalar_mults_per_s\": %.4e, \"err\": \"%s\"}\n",
-           MINB, ROLLED ? "rolled" : "unrolled", fa.numRegs, (size_t)fa.localSizeBytes, occ, n, best, 2.0 * n / (best * 1e-3), cudaGetErrorString(cudaGetLastError()));
+           MINB, MODE ? "split4" : "plain", fa.numRegs, (size_t)fa.localSizeBytes, occ, n, best, 2.0 * n / (best * 1e-3), cudaGetErrorString(cudaGetLastError()));
     cudaFree(pts); cudaFree(s0); cudaFree(s1); cudaFree(o0); cudaFree(o1); cudaFree(scratch); free(h);
 }
 int main() {
     cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
     size_t n = 1 << 18;
 #ifdef QQ_VB_PROFILE_ONLY
-    run<2, false>(1 << 16, p.multiProcessorCount);
+    run<3, 1>(1 << 16, p.multiProcessorCount);
     return 0;
 #endif
-    run<2, false>(n, p.multiProcessorCount);
-    run<2, true>(n, p.multiProcessorCount);
-    run<3, false>(n, p.multiProcessorCount);
-    run<3, true>(n, p.multiProcessorCount);
-    run<4, false>(n, p.multiProcessorCount);
-    run<4, true>(n, p.multiProcessorCount);
+    run<2, 0>(n, p.multiProcessorCount);
+    run<3, 0>(n, p.multiProcessorCount);
+    run<4, 0>(n, p.multiProcessorCount);
+    run<2, 1>(n, p.multiProcessorCount);
+    run<3, 1>(n, p.multiProcessorCount);
+    run<4, 1>(n, p.multiProcessorCount);
     return 0;
 }
