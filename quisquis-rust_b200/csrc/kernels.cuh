@@ -60,6 +60,7 @@ struct vb_args {
     const u32x4* s0;
     const u32x4* s1;
     int sdiv;
+    int halve0, halve1;   // multiply by s/2 mod l instead of s (outputs feed the double-and-compress encoder)
     u32x4* out0;
     u32x4* out1;
     u32x4* scratch;
@@ -68,7 +69,7 @@ struct vb_args {
 // 2 blocks/SM (<= 255 regs) measured faster than 3 or 4 (tools/vb_bench.cu): the kernel is FMA-pipe bound, not
 // latency bound, and a tighter register cap only adds moves.
 template <int NS>
-__global__ void __launch_bounds__(128, 2) k_varbase(vb_args a) {
+__global__ void __launch_bounds__(128, 4) k_varbase(vb_args a) {
     size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     u32x4* tbl = a.scratch + gtid * (QQ_VB_ENTRIES * QQ_PT_Q);
@@ -78,10 +79,12 @@ __global__ void __launch_bounds__(128, 2) k_varbase(vb_args a) {
         vb_build_table(tbl, p);
         u32 s[8];
         load_words32(s, a.s0, t / (size_t)a.sdiv);
+        if (a.halve0) sc_halve(s, s);
         vb_scalarmult(r, tbl, s);
         ge_p3_store(a.out0 + QQ_PT_Q * t, r);
         if (NS == 2) {
             load_words32(s, a.s1, t / (size_t)a.sdiv);
+            if (a.halve1) sc_halve(s, s);
             vb_scalarmult(r, tbl, s);
             ge_p3_store(a.out1 + QQ_PT_Q * t, r);
         }
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(128, 2) k_varbase(vb_args a) {
 
 // Two scalars per point through the split tables (vbs_*): 312 doublings per point instead of 504.  The four tables of
 // a thread (4.6 KB) are written once and read 128 times; they stream through L2.
-__global__ void __launch_bounds__(128, 2) k_varbase_split(vb_args a) {
+__global__ void __launch_bounds__(128, 4) k_varbase_split(vb_args a) {
     size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     u32x4* tbl = a.scratch + gtid * QQ_VBS_TABLE_Q;
@@ -100,9 +103,11 @@ __global__ void __launch_bounds__(128, 2) k_varbase_split(vb_args a) {
         vbs_build_tables(tbl, p);
         u32 s[8];
         load_words32(s, a.s0, t / (size_t)a.sdiv);
+        if (a.halve0) sc_halve(s, s);
         vbs_scalarmult(r, tbl, s);
         ge_p3_store(a.out0 + QQ_PT_Q * t, r);
         load_words32(s, a.s1, t / (size_t)a.sdiv);
+        if (a.halve1) sc_halve(s, s);
         vbs_scalarmult(r, tbl, s);
         ge_p3_store(a.out1 + QQ_PT_Q * t, r);
     }
@@ -110,7 +115,7 @@ __global__ void __launch_bounds__(128, 2) k_varbase_split(vb_args a) {
 
 // ---- fixed-base scalar multiplication: table staged in shared memory ---------------------------------------------
 template <int W>
-__global__ void __launch_bounds__(512) k_fixedbase(const u32* __restrict__ tbl_g, const u32x4* __restrict__ s,
+__global__ void __launch_bounds__(512) k_fixedbase(const u32* __restrict__ tbl_g, const u32x4* __restrict__ s, int halve,
                                                    u32x4* __restrict__ out, size_t n) {
     extern __shared__ __align__(16) u32 tbl_s[];
     const int words = ((256 + W - 1) / W) * ((1 << (W - 1)) + 1) * QQ_NIELS_WORDS;
@@ -125,6 +130,7 @@ __global__ void __launch_bounds__(512) k_fixedbase(const u32* __restrict__ tbl_g
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
         u32 w[8];
         load_words32(w, s, t);
+        if (halve) sc_halve(w, w);
         ge_p3 r;
         fb_scalarmult<W>(r, tbl_s, w);
         ge_p3_store(out + QQ_PT_Q * t, r);
@@ -154,7 +160,8 @@ struct fin_args {
     fin_src src[3];
     u32x4* out;        // compressed outputs
     idx_map omap;      // where output t is written (index into `out`, in 32-byte units)
-    const uint8_t* bad;  // per-item status (indexed by t): non-zero -> write zeros instead
+    const uint8_t* bad;  // per-element status (indexed by t / bdiv): non-zero -> write zeros instead
+    int bdiv;
     size_t n;
 };
 __device__ __forceinline__ void fin_eval(ge_p3& q, const fin_args& a, size_t t) {
@@ -178,27 +185,11 @@ __global__ void __launch_bounds__(256) k_finish_compress(fin_args a) {
         fin_eval(q, a, t);
         u32 w[8];
         ristretto_compress(w, q);
-        if (a.bad != nullptr && a.bad[t] != 0) {
+        if (a.bad != nullptr && a.bad[t / (size_t)a.bdiv] != 0) {
 #pragma unroll
             for (int i = 0; i < 8; i++) w[i] = 0;
         }
         store_words32(a.out, map_index(a.omap, t), w);
-    }
-}
-// compare enc(sum) against expected compressed bytes: flag[t] = 1 if equal
-__global__ void __launch_bounds__(256) k_finish_compare(fin_args a, const u32x4* __restrict__ expect, idx_map emap,
-                                                        uint8_t* __restrict__ flag) {
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < a.n; t += stride) {
-        ge_p3 q;
-        fin_eval(q, a, t);
-        u32 w[8], e[8];
-        ristretto_compress(w, q);
-        load_words32(e, expect, map_index(emap, t));
-        u32 d = 0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) d |= w[i] ^ e[i];
-        flag[t] = d == 0 ? 1 : 0;
     }
 }
 // projective Ristretto equality of two extended points: flag[t] = 1 if equal

@@ -10,6 +10,7 @@
 #include "../../include/qq_b200.h"
 #include "kernels.cuh"
 #include "msm.cuh"
+#include "compress_batch.cuh"
 
 using namespace qq;
 
@@ -150,10 +151,11 @@ static size_t vb_scratch_bytes(qq_ctx* ctx, int ns) {
     return (size_t)ctx->sms * ctx->vb_blocks_per_sm[ns] * 128 * (ns == 2 ? QQ_VBS_TABLE_WORDS : QQ_VB_TABLE_WORDS) * 4;
 }
 static int launch_varbase(qq_ctx* ctx, int ns, const u32x4* pts, idx_map map, const void* s0, const void* s1, int sdiv,
-                          u32x4* out0, u32x4* out1, u32x4* scratch, size_t n) {
+                          u32x4* out0, u32x4* out1, u32x4* scratch, size_t n, int halve0 = 0, int halve1 = 0) {
     if (n == 0) return QQ_OK;
     vb_args a;
     a.pts = pts; a.map = map; a.s0 = (const u32x4*)s0; a.s1 = (const u32x4*)s1; a.sdiv = sdiv;
+    a.halve0 = halve0; a.halve1 = halve1;
     a.out0 = out0; a.out1 = out1; a.scratch = scratch; a.n = n;
     int grid = ctx->sms * ctx->vb_blocks_per_sm[ns];
     span_begin(ctx, FAM_VB);
@@ -165,13 +167,13 @@ static int launch_varbase(qq_ctx* ctx, int ns, const u32x4* pts, idx_map map, co
     return QQ_OK;
 }
 static size_t fb_table_words() { return (size_t)fb_num_windows(QQ_FB_W) * fb_entries(QQ_FB_W) * QQ_NIELS_WORDS; }
-static int launch_fixedbase(qq_ctx* ctx, int which, const void* s, u32x4* out, size_t n) {
+static int launch_fixedbase(qq_ctx* ctx, int which, const void* s, u32x4* out, size_t n, int halve = 0) {
     if (n == 0) return QQ_OK;
     size_t smem = fb_table_words() * 4;
     int grid = (int)((n + 511) / 512);
     if (grid > ctx->sms) grid = ctx->sms;
     span_begin(ctx, FAM_FB);
-    k_fixedbase<QQ_FB_W><<<grid, 512, smem, ctx->stream>>>(ctx->fb_tbl[which], (const u32x4*)s, out, n);
+    k_fixedbase<QQ_FB_W><<<grid, 512, smem, ctx->stream>>>(ctx->fb_tbl[which], (const u32x4*)s, halve, out, n);
     span_end(ctx);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -188,7 +190,7 @@ static int launch_finish(qq_ctx* ctx, fin_src a, fin_src b, fin_src c, void* out
     if (n == 0) return QQ_OK;
     fin_args f;
     f.src[0] = a; f.src[1] = b; f.src[2] = c;
-    f.out = (u32x4*)out; f.omap = omap; f.bad = bad; f.n = n;
+    f.out = (u32x4*)out; f.omap = omap; f.bad = bad; f.bdiv = 1; f.n = n;
     span_begin(ctx, FAM_FIN);
     k_finish_compress<<<grid_for(n, 256, ctx->sms * 64), 256, 0, ctx->stream>>>(f);
     span_end(ctx);
@@ -196,13 +198,76 @@ static int launch_finish(qq_ctx* ctx, fin_src a, fin_src b, fin_src c, void* out
     CK(cudaGetLastError());
     return QQ_OK;
 }
-static int launch_compare(qq_ctx* ctx, fin_src a, fin_src b, const void* expect, idx_map emap, uint8_t* flag, size_t n) {
+// ---- double-and-compress finish (compress_batch.cuh): enc(2 * sum of sources) with one inversion per launch ------
+#define QQ_BINV_C 64
+struct dc_ws {
+    u32x4 *state, *w, *prefix, *lv_vals, *lv_prefix;
+    uint8_t* zflag;
+};
+static size_t dc_levels_q(size_t n) {  // u32x4 units needed by the upper levels of the inversion tree
+    size_t q = 0;
+    while (n > QQ_BINV_C) {
+        n = (n + QQ_BINV_C - 1) / QQ_BINV_C;
+        q += 2 * n;
+    }
+    return q + 2;
+}
+static size_t dc_scratch_bytes(size_t n) {
+    if (n == 0) n = 1;
+    return ws_need({n * QQ_DC_STATE_Q * 16, n * 32, n * 32, dc_levels_q(n) * 16, dc_levels_q(n) * 16, n});
+}
+static dc_ws dc_take(qq_ctx* ctx, size_t n) {
+    if (n == 0) n = 1;
+    dc_ws d;
+    d.state = ws_take<u32x4>(ctx, n * QQ_DC_STATE_Q * 16);
+    d.w = ws_take<u32x4>(ctx, n * 32);
+    d.prefix = ws_take<u32x4>(ctx, n * 32);
+    d.lv_vals = ws_take<u32x4>(ctx, dc_levels_q(n) * 16);
+    d.lv_prefix = ws_take<u32x4>(ctx, dc_levels_q(n) * 16);
+    d.zflag = ws_take<uint8_t>(ctx, n);
+    return d;
+}
+// inv[i] = 1 / vals[i] for n nonzero field elements; `prefix` (n) receives the inverses
+static int launch_batch_invert(qq_ctx* ctx, const dc_ws& d, size_t n) {
+    const u32x4* vals[12];
+    u32x4* pre[12];
+    size_t cnt[12];
+    vals[0] = d.w; pre[0] = d.prefix; cnt[0] = n;
+    int L = 0;
+    size_t off = 0;
+    while (cnt[L] > QQ_BINV_C) {
+        cnt[L + 1] = (cnt[L] + QQ_BINV_C - 1) / QQ_BINV_C;
+        u32x4* tot = d.lv_vals + off;
+        pre[L + 1] = d.lv_prefix + off;
+        off += 2 * cnt[L + 1];
+        k_binv_up<<<grid_for(cnt[L + 1], 128, ctx->sms * 8), 128, 0, ctx->stream>>>(vals[L], cnt[L], QQ_BINV_C, pre[L], tot);
+        vals[L + 1] = tot;
+        L++;
+        ctx->launches++;
+    }
+    k_binv_top<<<1, 32, 0, ctx->stream>>>(vals[L], cnt[L], pre[L], pre[L]);
+    ctx->launches++;
+    for (int l = L - 1; l >= 0; l--) {
+        k_binv_down<<<grid_for(cnt[l + 1], 128, ctx->sms * 8), 128, 0, ctx->stream>>>(vals[l], pre[l], pre[l + 1], cnt[l], QQ_BINV_C, pre[l]);
+        ctx->launches++;
+    }
+    CK(cudaGetLastError());
+    return QQ_OK;
+}
+// out[omap(t)] = enc(2 * (a + b + c)(t)); with expect != nullptr: flag[t] = (enc == expect[emap(t)]) instead
+static int launch_finish_dbl(qq_ctx* ctx, const dc_ws& d, fin_src a, fin_src b, fin_src c, void* out, idx_map omap,
+                             const uint8_t* bad, int bdiv, size_t n, const void* expect = nullptr,
+                             idx_map emap = {1, 1, {0, 0, 0, 0}}, uint8_t* flag = nullptr) {
     if (n == 0) return QQ_OK;
     fin_args f;
-    f.src[0] = a; f.src[1] = b; f.src[2] = FNONE;
-    f.out = nullptr; f.omap = IDENT; f.bad = nullptr; f.n = n;
+    f.src[0] = a; f.src[1] = b; f.src[2] = c;
+    f.out = (u32x4*)out; f.omap = omap; f.bad = bad; f.bdiv = bdiv; f.n = n;
     span_begin(ctx, FAM_FIN);
-    k_finish_compare<<<grid_for(n, 256, ctx->sms * 64), 256, 0, ctx->stream>>>(f, (const u32x4*)expect, emap, flag);
+    k_dc_prepare<<<grid_for(n, 256, ctx->sms * 64), 256, 0, ctx->stream>>>(f, d.state, d.w, d.zflag);
+    ctx->launches++;
+    CKQ(launch_batch_invert(ctx, d, n));
+    k_dc_finish<<<grid_for(n, 256, ctx->sms * 64), 256, 0, ctx->stream>>>(d.state, d.prefix, d.zflag, bad, bdiv, (u32x4*)out, omap,
+                                                                        (const u32x4*)expect, emap, flag, n);
     span_end(ctx);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -404,18 +469,19 @@ static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 static int core_scale_pairs(qq_ctx* ctx, const uint8_t* pk, const uint8_t* s, uint8_t* out, uint8_t* status, size_t n) {
     for (size_t base = 0; base < n; base += QQ_CHUNK) {
         size_t m = n - base < QQ_CHUNK ? n - base : QQ_CHUNK;
-        CKQ(ws_begin(ctx, ws_need({2 * m * QQ_PT_BYTES, 2 * m * QQ_PT_BYTES, 2 * m, vb_scratch_bytes(ctx, 1)})));
+        CKQ(ws_begin(ctx, ws_need({2 * m * QQ_PT_BYTES, 2 * m * QQ_PT_BYTES, 2 * m, vb_scratch_bytes(ctx, 1)}) + dc_scratch_bytes(2 * m)));
         u32x4* P = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);
         u32x4* R = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);
         uint8_t* ok = ws_take<uint8_t>(ctx, 2 * m);
         u32x4* scratch = ws_take<u32x4>(ctx, vb_scratch_bytes(ctx, 1));
+        dc_ws dc = dc_take(ctx, 2 * m);
         const uint8_t* pk_c = pk + base * 64;
         const uint8_t* s_c = s + base * 32;
         CKQ(launch_decompress(ctx, pk_c, IDENT, P, ok, 2 * m));
         CKQ(launch_status(ctx, s_c, nullptr, nullptr, ok, 2, status + base, m));
-        CKQ(launch_varbase(ctx, 1, P, IDENT, s_c, nullptr, 2, R, nullptr, scratch, 2 * m));
-        for (int j = 0; j < 2; j++)
-            CKQ(launch_finish(ctx, fsrc(R, imap(1, 2, j)), FNONE, FNONE, out + base * 64, imap(1, 2, j), status + base, m));
+        // R = (s/2) * P, encoded as enc(2 R): no square root on the output side (compress_batch.cuh)
+        CKQ(launch_varbase(ctx, 1, P, IDENT, s_c, nullptr, 2, R, nullptr, scratch, 2 * m, 1));
+        CKQ(launch_finish_dbl(ctx, dc, fsrc(R, IDENT), FNONE, FNONE, out + base * 64, IDENT, status + base, 2, 2 * m));
     }
     return QQ_OK;
 }
@@ -424,22 +490,24 @@ static int core_generate_commitment(qq_ctx* ctx, const uint8_t* pk, const uint8_
                                     uint8_t* status, size_t n) {
     for (size_t base = 0; base < n; base += QQ_CHUNK) {
         size_t m = n - base < QQ_CHUNK ? n - base : QQ_CHUNK;
-        CKQ(ws_begin(ctx, ws_need({2 * m * QQ_PT_BYTES, 2 * m * QQ_PT_BYTES, m * QQ_PT_BYTES, 2 * m, vb_scratch_bytes(ctx, 1)})));
+        CKQ(ws_begin(ctx, ws_need({2 * m * QQ_PT_BYTES, 2 * m * QQ_PT_BYTES, m * QQ_PT_BYTES, 2 * m, vb_scratch_bytes(ctx, 1)}) + dc_scratch_bytes(m)));
         u32x4* P = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);
         u32x4* R = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);
         u32x4* F = ws_take<u32x4>(ctx, m * QQ_PT_BYTES);
         uint8_t* ok = ws_take<uint8_t>(ctx, 2 * m);
         u32x4* scratch = ws_take<u32x4>(ctx, vb_scratch_bytes(ctx, 1));
+        dc_ws dc = dc_take(ctx, m);
         const uint8_t* pk_c = pk + base * 64;
         const uint8_t* r_c = r + base * 32;
         const uint8_t* v_c = v + base * 32;
         CKQ(launch_decompress(ctx, pk_c, IDENT, P, ok, 2 * m));
         CKQ(launch_status(ctx, r_c, v_c, nullptr, ok, 2, status + base, m));
-        CKQ(launch_varbase(ctx, 1, P, IDENT, r_c, nullptr, 2, R, nullptr, scratch, 2 * m));
-        CKQ(launch_fixedbase(ctx, QQ_BASE_B, v_c, F, m));
-        CKQ(launch_finish(ctx, fsrc(R, imap(1, 2, 0)), FNONE, FNONE, out + base * 64, imap(1, 2, 0), status + base, m));
-        CKQ(launch_finish(ctx, fsrc(R, imap(1, 2, 1)), fsrc(F, IDENT), FNONE, out + base * 64, imap(1, 2, 1),
-                          status + base, m));
+        // every term carries half its scalar; the outputs are enc(2 * sum)
+        CKQ(launch_varbase(ctx, 1, P, IDENT, r_c, nullptr, 2, R, nullptr, scratch, 2 * m, 1));
+        CKQ(launch_fixedbase(ctx, QQ_BASE_B, v_c, F, m, 1));
+        CKQ(launch_finish_dbl(ctx, dc, fsrc(R, imap(1, 2, 0)), FNONE, FNONE, out + base * 64, imap(1, 2, 0), status + base, 1, m));
+        CKQ(launch_finish_dbl(ctx, dc, fsrc(R, imap(1, 2, 1)), fsrc(F, IDENT), FNONE, out + base * 64, imap(1, 2, 1),
+                              status + base, 1, m));
     }
     return QQ_OK;
 }
@@ -472,24 +540,26 @@ static int core_update_account(qq_ctx* ctx, const uint8_t* acc, const uint8_t* b
                                uint8_t* out, uint8_t* status, size_t n) {
     for (size_t base = 0; base < n; base += QQ_CHUNK) {
         size_t m = n - base < QQ_CHUNK ? n - base : QQ_CHUNK;
-        CKQ(ws_begin(ctx, ws_need({4 * m * QQ_PT_BYTES, 2 * m * QQ_PT_BYTES, 2 * m * QQ_PT_BYTES, m * QQ_PT_BYTES, 4 * m, vb_scratch_bytes(ctx, 2)})));
+        CKQ(ws_begin(ctx, ws_need({4 * m * QQ_PT_BYTES, 2 * m * QQ_PT_BYTES, 2 * m * QQ_PT_BYTES, m * QQ_PT_BYTES, 4 * m, vb_scratch_bytes(ctx, 2)}) + dc_scratch_bytes(2 * m)));
         u32x4* P = ws_take<u32x4>(ctx, 4 * m * QQ_PT_BYTES);   // gr, grsk, c, d of every account
         u32x4* Ru = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);  // u*gr, u*grsk
         u32x4* Rc = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);  // c*gr, c*grsk
         u32x4* F = ws_take<u32x4>(ctx, m * QQ_PT_BYTES);       // bl*B
         uint8_t* ok = ws_take<uint8_t>(ctx, 4 * m);
         u32x4* scratch = ws_take<u32x4>(ctx, vb_scratch_bytes(ctx, 2));
+        dc_ws dc = dc_take(ctx, 2 * m);
         const uint8_t* acc_c = acc + base * 128;
         const uint8_t *bl_c = bl + base * 32, *u_c = u + base * 32, *c_c = c + base * 32;
         uint8_t* out_c = out + base * 128;
         CKQ(launch_decompress(ctx, acc_c, IDENT, P, ok, 4 * m));
         CKQ(launch_status(ctx, bl_c, u_c, c_c, ok, 4, status + base, m));
         // items: (account i, point j in {gr, grsk}); two scalars (u_i, c_i) share one window table
-        CKQ(launch_varbase(ctx, 2, P, imap(2, 4, 0, 1), u_c, c_c, 2, Ru, Rc, scratch, 2 * m));
+        // u is halved: Ru = (u/2) * (gr, grsk) feeds the double-and-compress encoder; c stays whole because the
+        // commitment adds the account's own points, which cannot be halved
+        CKQ(launch_varbase(ctx, 2, P, imap(2, 4, 0, 1), u_c, c_c, 2, Ru, Rc, scratch, 2 * m, 1, 0));
         CKQ(launch_fixedbase(ctx, QQ_BASE_B, bl_c, F, m));
         // pk' = (u*gr, u*grsk)
-        CKQ(launch_finish(ctx, fsrc(Ru, imap(1, 2, 0)), FNONE, FNONE, out_c, imap(1, 4, 0), status + base, m));
-        CKQ(launch_finish(ctx, fsrc(Ru, imap(1, 2, 1)), FNONE, FNONE, out_c, imap(1, 4, 1), status + base, m));
+        CKQ(launch_finish_dbl(ctx, dc, fsrc(Ru, IDENT), FNONE, FNONE, out_c, imap(2, 4, 0, 1), status + base, 2, 2 * m));
         // comm' = (c*gr + a.c, bl*B + c*grsk + a.d)        -- OLD pk, reference src/accounts/accounts.rs:149-152
         CKQ(launch_finish(ctx, fsrc(Rc, imap(1, 2, 0)), fsrc(P, imap(1, 4, 2)), FNONE, out_c, imap(1, 4, 2),
                           status + base, m));
@@ -503,7 +573,7 @@ static int core_verify_account(qq_ctx* ctx, const uint8_t* acc, const uint8_t* s
                                size_t n) {
     for (size_t base = 0; base < n; base += QQ_CHUNK) {
         size_t m = n - base < QQ_CHUNK ? n - base : QQ_CHUNK;
-        CKQ(ws_begin(ctx, ws_need({2 * m * QQ_PT_BYTES, 2 * m * QQ_PT_BYTES, m * QQ_PT_BYTES, 2 * m, 2 * m, m, vb_scratch_bytes(ctx, 1)})));
+        CKQ(ws_begin(ctx, ws_need({2 * m * QQ_PT_BYTES, 2 * m * QQ_PT_BYTES, m * QQ_PT_BYTES, 2 * m, 2 * m, m, vb_scratch_bytes(ctx, 1)}) + dc_scratch_bytes(m)));
         u32x4* P = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);  // gr, c
         u32x4* R = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);  // sk*gr, sk*c
         u32x4* F = ws_take<u32x4>(ctx, m * QQ_PT_BYTES);      // bl*B
@@ -511,16 +581,17 @@ static int core_verify_account(qq_ctx* ctx, const uint8_t* acc, const uint8_t* s
         uint8_t* eq = ws_take<uint8_t>(ctx, 2 * m);
         uint8_t* pre = ws_take<uint8_t>(ctx, m);
         u32x4* scratch = ws_take<u32x4>(ctx, vb_scratch_bytes(ctx, 1));
+        dc_ws dc = dc_take(ctx, m);
         const uint8_t* acc_c = acc + base * 128;
         const uint8_t *sk_c = sk + base * 32, *bl_c = bl + base * 32;
         CKQ(launch_decompress(ctx, acc_c, imap(2, 4, 0, 2), P, ok, 2 * m));
         CKQ(launch_status(ctx, sk_c, bl_c, nullptr, ok, 0, pre, m));
-        CKQ(launch_varbase(ctx, 1, P, IDENT, sk_c, nullptr, 2, R, nullptr, scratch, 2 * m));
-        CKQ(launch_fixedbase(ctx, QQ_BASE_B, bl_c, F, m));
+        CKQ(launch_varbase(ctx, 1, P, IDENT, sk_c, nullptr, 2, R, nullptr, scratch, 2 * m, 1));
+        CKQ(launch_fixedbase(ctx, QQ_BASE_B, bl_c, F, m, 1));
         // grsk == enc(sk*gr)                       reference src/ristretto/keys.rs:187-195
-        CKQ(launch_compare(ctx, fsrc(R, imap(1, 2, 0)), FNONE, acc_c, imap(1, 4, 1), eq, m));
+        CKQ(launch_finish_dbl(ctx, dc, fsrc(R, imap(1, 2, 0)), FNONE, FNONE, nullptr, IDENT, nullptr, 1, m, acc_c, imap(1, 4, 1), eq));
         // d == enc(bl*B + sk*c)                    reference src/elgamal/elgamal.rs:81-95
-        CKQ(launch_compare(ctx, fsrc(R, imap(1, 2, 1)), fsrc(F, IDENT), acc_c, imap(1, 4, 3), eq + m, m));
+        CKQ(launch_finish_dbl(ctx, dc, fsrc(R, imap(1, 2, 1)), fsrc(F, IDENT), FNONE, nullptr, IDENT, nullptr, 1, m, acc_c, imap(1, 4, 3), eq + m));
         k_verify_account_status<<<grid_for(m, 256, ctx->sms * 16), 256, 0, ctx->stream>>>(pre, ok, eq, status + base, m);
         ctx->launches++;
     }
@@ -559,7 +630,7 @@ static int core_delta_epsilon(qq_ctx* ctx, const uint8_t* acc, const uint8_t* bl
                               uint8_t* eps, uint8_t* status, size_t n) {
     for (size_t base = 0; base < n; base += QQ_CHUNK) {
         size_t m = n - base < QQ_CHUNK ? n - base : QQ_CHUNK;
-        CKQ(ws_begin(ctx, ws_need({2 * m * QQ_PT_BYTES, 2 * m * QQ_PT_BYTES, m * QQ_PT_BYTES, m * QQ_PT_BYTES, m * QQ_PT_BYTES, 2 * m, vb_scratch_bytes(ctx, 1)})));
+        CKQ(ws_begin(ctx, ws_need({2 * m * QQ_PT_BYTES, 2 * m * QQ_PT_BYTES, m * QQ_PT_BYTES, m * QQ_PT_BYTES, m * QQ_PT_BYTES, 2 * m, vb_scratch_bytes(ctx, 1)}) + dc_scratch_bytes(m)));
         u32x4* P = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);   // gr, grsk
         u32x4* R = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);   // r*gr, r*grsk
         u32x4* FB = ws_take<u32x4>(ctx, m * QQ_PT_BYTES);      // bl*B
@@ -567,25 +638,27 @@ static int core_delta_epsilon(qq_ctx* ctx, const uint8_t* acc, const uint8_t* bl
         u32x4* RH = ws_take<u32x4>(ctx, m * QQ_PT_BYTES);      // r*H
         uint8_t* ok = ws_take<uint8_t>(ctx, 2 * m);
         u32x4* scratch = ws_take<u32x4>(ctx, vb_scratch_bytes(ctx, 1));
+        dc_ws dc = dc_take(ctx, m);
         const uint8_t* acc_c = acc + base * 128;
         const uint8_t *bl_c = bl + base * 32, *r_c = r + base * 32;
         uint8_t *d_c = delta + base * 128, *e_c = eps + base * 128;
         CKQ(launch_decompress(ctx, acc_c, imap(2, 4, 0, 1), P, ok, 2 * m));
         CKQ(launch_status(ctx, r_c, bl_c, nullptr, ok, 2, status + base, m));
-        CKQ(launch_varbase(ctx, 1, P, IDENT, r_c, nullptr, 2, R, nullptr, scratch, 2 * m));
-        CKQ(launch_fixedbase(ctx, QQ_BASE_B, bl_c, FB, m));
-        CKQ(launch_fixedbase(ctx, QQ_BASE_B, r_c, RB, m));
-        CKQ(launch_fixedbase(ctx, QQ_BASE_H, r_c, RH, m));
+        // all four commitment points are sums of scalar multiples: halve every scalar, encode 2 * sum
+        CKQ(launch_varbase(ctx, 1, P, IDENT, r_c, nullptr, 2, R, nullptr, scratch, 2 * m, 1));
+        CKQ(launch_fixedbase(ctx, QQ_BASE_B, bl_c, FB, m, 1));
+        CKQ(launch_fixedbase(ctx, QQ_BASE_B, r_c, RB, m, 1));
+        CKQ(launch_fixedbase(ctx, QQ_BASE_H, r_c, RH, m, 1));
         // pk halves: delta keeps the account pk, epsilon carries base_pk (zeroed when the element is bad)
         pk_bytes bpk;
         memcpy(&bpk, ctx->base_pk, 64);
         k_copy_pk<<<grid_for(m, 256, ctx->sms * 16), 256, 0, ctx->stream>>>((const u32x4*)acc_c, (u32x4*)d_c, (u32x4*)e_c,
                                                                             bpk, status + base, m);
         ctx->launches++;
-        CKQ(launch_finish(ctx, fsrc(R, imap(1, 2, 0)), FNONE, FNONE, d_c, imap(1, 4, 2), status + base, m));
-        CKQ(launch_finish(ctx, fsrc(R, imap(1, 2, 1)), fsrc(FB, IDENT), FNONE, d_c, imap(1, 4, 3), status + base, m));
-        CKQ(launch_finish(ctx, fsrc(RB, IDENT), FNONE, FNONE, e_c, imap(1, 4, 2), status + base, m));
-        CKQ(launch_finish(ctx, fsrc(RH, IDENT), fsrc(FB, IDENT), FNONE, e_c, imap(1, 4, 3), status + base, m));
+        CKQ(launch_finish_dbl(ctx, dc, fsrc(R, imap(1, 2, 0)), FNONE, FNONE, d_c, imap(1, 4, 2), status + base, 1, m));
+        CKQ(launch_finish_dbl(ctx, dc, fsrc(R, imap(1, 2, 1)), fsrc(FB, IDENT), FNONE, d_c, imap(1, 4, 3), status + base, 1, m));
+        CKQ(launch_finish_dbl(ctx, dc, fsrc(RB, IDENT), FNONE, FNONE, e_c, imap(1, 4, 2), status + base, 1, m));
+        CKQ(launch_finish_dbl(ctx, dc, fsrc(RH, IDENT), fsrc(FB, IDENT), FNONE, e_c, imap(1, 4, 3), status + base, 1, m));
     }
     return QQ_OK;
 }
@@ -593,11 +666,12 @@ static int core_delta_epsilon(qq_ctx* ctx, const uint8_t* acc, const uint8_t* bl
 static int core_fixed_base(qq_ctx* ctx, int which, const uint8_t* s, uint8_t* out, uint8_t* status, size_t n) {
     for (size_t base = 0; base < n; base += QQ_CHUNK) {
         size_t m = n - base < QQ_CHUNK ? n - base : QQ_CHUNK;
-        CKQ(ws_begin(ctx, ws_need({m * QQ_PT_BYTES})));
+        CKQ(ws_begin(ctx, ws_need({m * QQ_PT_BYTES}) + dc_scratch_bytes(m)));
         u32x4* F = ws_take<u32x4>(ctx, m * QQ_PT_BYTES);
+        dc_ws dc = dc_take(ctx, m);
         CKQ(launch_status(ctx, s + base * 32, nullptr, nullptr, nullptr, 0, status + base, m));
-        CKQ(launch_fixedbase(ctx, which, s + base * 32, F, m));
-        CKQ(launch_finish(ctx, fsrc(F, IDENT), FNONE, FNONE, out + base * 32, IDENT, status + base, m));
+        CKQ(launch_fixedbase(ctx, which, s + base * 32, F, m, 1));
+        CKQ(launch_finish_dbl(ctx, dc, fsrc(F, IDENT), FNONE, FNONE, out + base * 32, IDENT, status + base, 1, m));
     }
     return QQ_OK;
 }

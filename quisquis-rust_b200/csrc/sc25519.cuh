@@ -23,6 +23,24 @@ QQ_HD u32 sc_is_canonical(const u32 s[8]) {
     return borrow;
 }
 
+// h = s / 2 mod l for s < l:  s >> 1 when s is even, (s + l) >> 1 when odd.  Used with the double-and-compress encoder
+// (compress_batch.cuh): enc(s P) = enc(2 (h P)).  Non-canonical input gives an unspecified (but bounded) result; the
+// callers zero such outputs through the status byte.
+QQ_HD void sc_halve(u32 h[8], const u32 s[8]) {
+    u32 m = 0u - (s[0] & 1u);
+    u32 t[8];
+    u32 carry = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        u64 a = (u64)s[i] + (sc_l_word(i) & m) + carry;
+        t[i] = (u32)a;
+        carry = (u32)(a >> 32);
+    }
+#pragma unroll
+    for (int i = 0; i < 7; i++) h[i] = (t[i] >> 1) | (t[i + 1] << 31);
+    h[7] = (t[7] >> 1) | (carry << 31);
+}
+
 // Signed radix-2^W recoding without digit storage: r = s + sum_i 2^(W-1) 2^(W i)  (NW windows, NW*W >= 255), then
 // digit_i = ((r >> W i) & (2^W - 1)) - 2^(W-1)  in [-2^(W-1), 2^(W-1)).   s < 2^253.
 // r has 9 words (NW*W may exceed 256).

@@ -5,6 +5,7 @@
 #include <vector>
 #include "../../quisquis-rust_b200/csrc/ristretto.cuh"
 #include "../../quisquis-rust_b200/csrc/scalarmult.cuh"
+#include "../../quisquis-rust_b200/csrc/compress_batch.cuh"
 
 using namespace qq;
 
@@ -193,6 +194,39 @@ int hh_scalarmult_split(uint8_t* out0, uint8_t* out1, const uint8_t* s0, const u
     ristretto_compress(w, r);
     store_words(out1, w);
     return ok;
+}
+// out = enc(s * P) computed as enc(2 * ((s / 2 mod l) * P)) through the batch encoder's per-item functions
+// (the inversion that the GPU shares across a batch is a plain fe_invert here); zscale rescales the projective
+// representative first.  Returns the zero flag (1 when the result is the identity class).
+int hh_halve_dblcompress(uint8_t* out, const uint8_t* scalar, const uint8_t* point, const uint8_t* zscale) {
+    u32 w[8], s[8], h[8];
+    ge_p3 p, r;
+    load_words(w, point);
+    ristretto_decompress(p, w);
+    load_words(s, scalar);
+    sc_halve(h, s);
+    std::vector<u32x4> tbl(QQ_VB_ENTRIES * QQ_PT_Q);
+    vb_build_table(tbl.data(), p);
+    vb_scalarmult(r, tbl.data(), h);
+    fe z;
+    load_words(w, zscale);
+    fe_fromwords(z, w);
+    fe_mul(r.X, r.X, z); fe_mul(r.Y, r.Y, z); fe_mul(r.Z, r.Z, z); fe_mul(r.T, r.T, z);
+    dc_state st;
+    fe wv, inv;
+    dc_prepare(st, wv, r);
+    int zero = (int)fe_iszero(wv);
+    fe_invert(inv, wv);
+    dc_finish(w, st, inv);
+    if (zero) memset(w, 0, 32);
+    store_words(out, w);
+    return zero;
+}
+void hh_sc_halve(uint8_t* out, const uint8_t* scalar) {
+    u32 s[8], h[8];
+    load_words(s, scalar);
+    sc_halve(h, s);
+    store_words(out, h);
 }
 // fixed base: W in {4,5,6,8}; builds the table on each call into caller-provided buffer (words)
 size_t hh_fb_table_words(int W) { return (size_t)fb_num_windows(W) * fb_entries(W) * QQ_NIELS_WORDS; }

@@ -186,6 +186,23 @@ def test_split_variable_base(hh):
         assert o1.raw == R.compress(R.mul(s1, R.decompress(p)))
 
 
+def test_halve_and_double_compress(hh):
+    # enc(s P) == double-and-compress((s / 2 mod l) P): dalek ristretto.rs double_and_compress_batch restated
+    rnd = random.Random(17)
+    inv2 = pow(2, R.L - 2, R.L)
+    for i in range(60):
+        s = [0, 1, 2, R.L - 1, R.L - 2, 3][i] if i < 6 else rnd.randrange(R.L)
+        o = ctypes.create_string_buffer(32)
+        hh.hh_sc_halve(o, s.to_bytes(32, "little"))
+        assert int.from_bytes(o.raw, "little") == s * inv2 % R.L
+        p = bytes(32) if i == 7 else R.compress(R.mul(rnd.randrange(R.L), R.BASEPOINT))
+        z = (1 if i % 3 == 0 else rnd.randrange(1, R.P)).to_bytes(32, "little")
+        zero = hh.hh_halve_dblcompress(o, s.to_bytes(32, "little"), p, z)
+        want = R.compress(R.mul(s, R.decompress(p)))
+        assert o.raw == want
+        assert zero == int(want == bytes(32))
+
+
 @pytest.mark.parametrize("W", [4, 6])
 def test_fixed_base_tables(hh, W):
     rnd = random.Random(15)
