@@ -129,6 +129,14 @@ int qq_delta_identity_check(qq_ctx* ctx, const uint8_t* acc, size_t n, uint8_t* 
 int qq_fixed_base_batch(qq_ctx* ctx, int which, const uint8_t* s, uint8_t* out_points, uint8_t* status, size_t n);
 int qq_fixed_base_batch_dev(qq_ctx* ctx, int which, const uint8_t* s, uint8_t* out_points, uint8_t* status,
                             size_t n);
+/* Window width of the large fixed-base table of base `which` (dalek's counterpart is the fixed radix-16
+ * RistrettoBasepointTable, constants.rs / edwards.rs::EdwardsBasepointTable; the reference uses it through
+ * src/elgamal/elgamal.rs:49).  Tables hold ceil(255 / W) x (2^(W-1) + 1) affine points of 96 bytes in device memory:
+ * W = 16 -> 50 MB (default at qq_init, L2 resident), 22 -> 2.4 GB, 24 -> 8.9 GB, 26 -> 32 GB.  A wider window means
+ * fewer additions per scalar and identical results.  window_bits = 0 frees the table (batches then use the
+ * shared-memory 6-bit table only); otherwise 8 <= window_bits <= 28.  Rebuilds synchronously. */
+int qq_fixed_base_set_window(qq_ctx* ctx, int which, int window_bits);
+int qq_fixed_base_window(const qq_ctx* ctx, int which);
 
 /* ---- multiscalar multiplication --------------------------------------------------------------------------------
  * Verifier::multiscalar_multiplication = RistrettoPoint::optional_multiscalar_mul over compressed points

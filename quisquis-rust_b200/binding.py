@@ -18,7 +18,7 @@ EXPORTS = [
     "qq_generate_commitment_batch", "qq_generate_commitment_batch_dev", "qq_add_commitments_batch",
     "qq_mul_commitment_batch", "qq_update_account_batch", "qq_update_account_batch_dev",
     "qq_verify_account_batch", "qq_verify_account_batch_dev", "qq_delta_epsilon_batch", "qq_delta_identity_check",
-    "qq_fixed_base_batch", "qq_fixed_base_batch_dev", "qq_msm", "qq_msm_dev", "qq_msm_partial", "qq_msm_partial_dev",
+    "qq_fixed_base_batch", "qq_fixed_base_batch_dev", "qq_fixed_base_set_window", "qq_fixed_base_window", "qq_msm", "qq_msm_dev", "qq_msm_partial", "qq_msm_partial_dev",
     "qq_points_sum", "qq_msm_segmented",
 ]
 
@@ -76,6 +76,8 @@ def load_library():
     lib.qq_delta_identity_check.argtypes = [vp, u8p, sz, u8p]
     for name in ("qq_fixed_base_batch", "qq_fixed_base_batch_dev"):
         getattr(lib, name).argtypes = [vp, ctypes.c_int, u8p, u8p, u8p, sz]
+    lib.qq_fixed_base_set_window.argtypes = [vp, ctypes.c_int, ctypes.c_int]
+    lib.qq_fixed_base_window.argtypes = [vp, ctypes.c_int]
     for name in ("qq_msm", "qq_msm_dev", "qq_msm_partial", "qq_msm_partial_dev"):
         getattr(lib, name).argtypes = [vp, u8p, u8p, sz, u8p, u8p]
     lib.qq_points_sum.argtypes = [vp, u8p, sz, u8p, u8p]
@@ -254,6 +256,13 @@ class Engine:
         out, st = np.zeros(n * 32, np.uint8), np.zeros(n, np.uint8)
         self._ck(self.lib.qq_fixed_base_batch(self.h, int(which), _ptr(s), _ptr(out), _ptr(st), n), "qq_fixed_base_batch")
         return out.reshape(n, 32), st
+
+    def fixed_base_set_window(self, which, window_bits):
+        """Rebuild the large fixed-base table of base `which` with `window_bits`-bit windows (0 frees it)."""
+        self._ck(self.lib.qq_fixed_base_set_window(self.h, int(which), int(window_bits)), "qq_fixed_base_set_window")
+
+    def fixed_base_window(self, which):
+        return int(self.lib.qq_fixed_base_window(self.h, int(which)))
 
     def msm(self, scalars, points):
         scalars, points = _u8(scalars), _u8(points)

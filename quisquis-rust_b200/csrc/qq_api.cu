@@ -3,6 +3,7 @@
 // No CPU fallback: every entry point fails with QQ_ERR_NODEVICE / QQ_ERR_CUDA when the GPU path is unavailable.
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -11,9 +12,11 @@
 #include "kernels.cuh"
 #include "msm.cuh"
 #include "compress_batch.cuh"
+#include "fixedbase_big.cuh"
 
 using namespace qq;
 
+#define QQ_FBT_MIN_BATCH 2048  // below this the shared-memory table (cold-start free) is used instead of the big one
 #define QQ_FB_W 6  // window width of the shared-memory fixed-base tables (43 windows x 33 entries x 96 B = 136 KB)
 enum { FAM_DEC = 0, FAM_VB = 1, FAM_FB = 2, FAM_FIN = 3, FAM_MSM_BUCKET = 4, FAM_MSM_REDUCE = 5, FAM_COUNT = 6 };
 
@@ -26,7 +29,9 @@ struct qq_ctx {
     char* io = nullptr;      // staging slab for the host-pointer entry points (grow-only)
     size_t io_cap = 0;
     cudaEvent_t user_ev[8] = {nullptr};
-    u32* fb_tbl[2] = {nullptr, nullptr};
+    u32* fb_tbl[2] = {nullptr, nullptr};      // shared-memory-sized tables (W = QQ_FB_W)
+    u32x4* fbt[2] = {nullptr, nullptr};       // large-window tables in L2 / HBM (fixedbase_big.cuh), optional
+    fbt_geom fbt_g[2] = {{0, 0, 0}, {0, 0, 0}};
     uint8_t base_pk[64];
     uint64_t launches = 0;
     float last_ms = 0.f;
@@ -169,6 +174,15 @@ static int launch_varbase(qq_ctx* ctx, int ns, const u32x4* pts, idx_map map, co
 static size_t fb_table_words() { return (size_t)fb_num_windows(QQ_FB_W) * fb_entries(QQ_FB_W) * QQ_NIELS_WORDS; }
 static int launch_fixedbase(qq_ctx* ctx, int which, const void* s, u32x4* out, size_t n, int halve = 0) {
     if (n == 0) return QQ_OK;
+    if (ctx->fbt[which] != nullptr && n >= QQ_FBT_MIN_BATCH) {
+        span_begin(ctx, FAM_FB);
+        k_fixedbase_big<<<grid_for(n, 128, ctx->sms * 4), 128, 0, ctx->stream>>>(ctx->fbt[which], ctx->fbt_g[which],
+                                                                                (const u32x4*)s, halve, out, n);
+        span_end(ctx);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        return QQ_OK;
+    }
     size_t smem = fb_table_words() * 4;
     int grid = (int)((n + 511) / 512);
     if (grid > ctx->sms) grid = ctx->sms;
@@ -297,6 +311,70 @@ static int launch_point_sum(qq_ctx* ctx, const u32x4* pts, idx_map map, size_t n
     return QQ_OK;
 }
 
+// ---- large-window fixed-base tables (fixedbase_big.cuh) ---------------------------------------------------------------
+static int launch_batch_invert(qq_ctx* ctx, const dc_ws& d, size_t n);
+static const uint8_t QQ_BASE_PK_BYTES[64] = {
+    0xe2, 0xf2, 0xae, 0x0a, 0x6a, 0xbc, 0x4e, 0x71, 0xa8, 0x84, 0xa9, 0x61, 0xc5, 0x00, 0x51, 0x5f,
+    0x58, 0xe3, 0x0b, 0x6a, 0xa5, 0x82, 0xdd, 0x8d, 0xb6, 0xa6, 0x59, 0x45, 0xe0, 0x8d, 0x2d, 0x76,
+    0x8c, 0x92, 0x40, 0xb4, 0x56, 0xa9, 0xe6, 0xdc, 0x65, 0xc3, 0x77, 0xa1, 0x04, 0x8d, 0x74, 0x5f,
+    0x94, 0xa0, 0x8c, 0xdb, 0x7f, 0x44, 0xcb, 0xcd, 0x7b, 0x46, 0xf3, 0x40, 0x48, 0x87, 0x11, 0x34};
+static int fbt_build(qq_ctx* ctx, int which, int W) {
+    if (ctx->fbt[which]) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaFree(ctx->fbt[which]));
+        ctx->fbt[which] = nullptr;
+        ctx->fbt_g[which] = fbt_geom{0, 0, 0};
+    }
+    if (W == 0) return QQ_OK;
+    fbt_geom g;
+    g.W = W;
+    g.NW = (255 + W - 1) / W;
+    g.ENT = (1u << (W - 1)) + 1u;
+    size_t entries = (size_t)g.NW * g.ENT;
+    u32x4* tbl = nullptr;
+    CK(cudaMalloc((void**)&tbl, entries * QQ_NIELS_STRIDE_Q * 16));
+    const unsigned int SLICE = 1u << 22;
+    size_t slice = g.ENT < SLICE ? g.ENT : SLICE;
+    u32x4 *dbase = nullptr, *bases = nullptr, *ext = nullptr;
+    dc_ws d;
+    d.state = nullptr; d.zflag = nullptr;
+    CK(cudaMalloc((void**)&dbase, 64));
+    CK(cudaMalloc((void**)&bases, (size_t)g.NW * QQ_PT_BYTES));
+    CK(cudaMalloc((void**)&ext, slice * QQ_PT_BYTES));
+    CK(cudaMalloc((void**)&d.w, slice * 32));
+    CK(cudaMalloc((void**)&d.prefix, slice * 32));
+    CK(cudaMalloc((void**)&d.lv_vals, dc_levels_q(slice) * 16));
+    CK(cudaMalloc((void**)&d.lv_prefix, dc_levels_q(slice) * 16));
+    CK(cudaMemcpyAsync(dbase, QQ_BASE_PK_BYTES, 64, cudaMemcpyHostToDevice, ctx->stream));
+    k_fbt_window_bases<<<1, 32, 0, ctx->stream>>>(dbase + 2 * which, g, bases);
+    ctx->launches++;
+    for (int k = 0; k < g.NW; k++) {
+        for (size_t j0 = 0; j0 < g.ENT; j0 += slice) {
+            unsigned int cnt = (unsigned int)(g.ENT - j0 < slice ? g.ENT - j0 : slice);
+            unsigned int chunks = (cnt + QQ_FBT_CHUNK - 1) / QQ_FBT_CHUNK;
+            k_fbt_points<<<(chunks + 127) / 128, 128, 0, ctx->stream>>>(bases, k, (unsigned int)j0, cnt, ext, d.w);
+            CKQ(launch_batch_invert(ctx, d, cnt));
+            k_fbt_normalize<<<(cnt + 255) / 256, 256, 0, ctx->stream>>>(ext, d.prefix, cnt,
+                                                                      tbl + ((size_t)k * g.ENT + j0) * QQ_NIELS_STRIDE_Q);
+            ctx->launches += 2;
+        }
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    cudaFree(dbase); cudaFree(bases); cudaFree(ext); cudaFree(d.w); cudaFree(d.prefix); cudaFree(d.lv_vals); cudaFree(d.lv_prefix);
+    ctx->fbt[which] = tbl;
+    ctx->fbt_g[which] = g;
+    return QQ_OK;
+}
+extern "C" int qq_fixed_base_set_window(qq_ctx* ctx, int which, int window_bits) {
+    if (!ctx || (which != 0 && which != 1) || (window_bits != 0 && (window_bits < 8 || window_bits > 28))) return QQ_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    return fbt_build(ctx, which, window_bits);
+}
+extern "C" int qq_fixed_base_window(const qq_ctx* ctx, int which) {
+    return (ctx && (which == 0 || which == 1)) ? ctx->fbt_g[which].W : 0;
+}
+
 // =================================================================================================================
 // context
 // =================================================================================================================
@@ -331,11 +409,7 @@ extern "C" int qq_init(qq_ctx** out, int device) {
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_varbase_split, 128, 0));
         ctx->vb_blocks_per_sm[2] = occ > 0 ? occ : 1;
         // fixed-base tables for B and H, built on the device from their compressed encodings
-        static const uint8_t BASE_PK[64] = {
-            0xe2, 0xf2, 0xae, 0x0a, 0x6a, 0xbc, 0x4e, 0x71, 0xa8, 0x84, 0xa9, 0x61, 0xc5, 0x00, 0x51, 0x5f,
-            0x58, 0xe3, 0x0b, 0x6a, 0xa5, 0x82, 0xdd, 0x8d, 0xb6, 0xa6, 0x59, 0x45, 0xe0, 0x8d, 0x2d, 0x76,
-            0x8c, 0x92, 0x40, 0xb4, 0x56, 0xa9, 0xe6, 0xdc, 0x65, 0xc3, 0x77, 0xa1, 0x04, 0x8d, 0x74, 0x5f,
-            0x94, 0xa0, 0x8c, 0xdb, 0x7f, 0x44, 0xcb, 0xcd, 0x7b, 0x46, 0xf3, 0x40, 0x48, 0x87, 0x11, 0x34};
+        const uint8_t* BASE_PK = QQ_BASE_PK_BYTES;
         memcpy(ctx->base_pk, BASE_PK, 64);
         u32x4* dbase = nullptr;
         CK(cudaMalloc((void**)&dbase, 64));
@@ -349,6 +423,11 @@ extern "C" int qq_init(qq_ctx** out, int device) {
         CK(cudaStreamSynchronize(ctx->stream));
         CK(cudaGetLastError());
         CK(cudaFree(dbase));
+        // large-window tables: 16-bit windows (50 MB per base, L2 resident) unless QQ_FB_WINDOW says otherwise
+        int W = 16;
+        if (const char* e = getenv("QQ_FB_WINDOW")) W = atoi(e);
+        if (W != 0 && (W < 8 || W > 28)) { ctx->err = "QQ_FB_WINDOW must be 0 or in [8, 28]"; return QQ_ERR_ARG; }
+        for (int b = 0; b < 2; b++) CKQ(fbt_build(ctx, b, W));
         return QQ_OK;
     };
     int r = body();
@@ -366,8 +445,10 @@ extern "C" void qq_destroy(qq_ctx* ctx) {
     if (ctx->io) cudaFree(ctx->io);
     for (int i = 0; i < 8; i++)
         if (ctx->user_ev[i]) cudaEventDestroy(ctx->user_ev[i]);
-    for (int b = 0; b < 2; b++)
+    for (int b = 0; b < 2; b++) {
         if (ctx->fb_tbl[b]) cudaFree(ctx->fb_tbl[b]);
+        if (ctx->fbt[b]) cudaFree(ctx->fbt[b]);
+    }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -664,12 +745,32 @@ static int core_delta_epsilon(qq_ctx* ctx, const uint8_t* acc, const uint8_t* bl
 }
 
 static int core_fixed_base(qq_ctx* ctx, int which, const uint8_t* s, uint8_t* out, uint8_t* status, size_t n) {
-    for (size_t base = 0; base < n; base += QQ_CHUNK) {
-        size_t m = n - base < QQ_CHUNK ? n - base : QQ_CHUNK;
+    // larger chunks than the account paths: a fixed-base mult is ~100x cheaper than an account update, so the
+    // latency-bound tail of the batch inversion is amortised over 4x more elements (workspace: 400 B per element)
+    const size_t CH = (size_t)1 << 22;
+    for (size_t base = 0; base < n; base += CH) {
+        size_t m = n - base < CH ? n - base : CH;
         CKQ(ws_begin(ctx, ws_need({m * QQ_PT_BYTES}) + dc_scratch_bytes(m)));
         u32x4* F = ws_take<u32x4>(ctx, m * QQ_PT_BYTES);
         dc_ws dc = dc_take(ctx, m);
         CKQ(launch_status(ctx, s + base * 32, nullptr, nullptr, nullptr, 0, status + base, m));
+        if (ctx->fbt[which] != nullptr && m >= QQ_FBT_MIN_BATCH) {
+            // table walk fused with the first stage of the batch encoder: the extended point never goes to HBM
+            span_begin(ctx, FAM_FB);
+            k_fixedbase_big_dc<<<grid_for(m, 128, ctx->sms * 4), 128, 0, ctx->stream>>>(
+                ctx->fbt[which], ctx->fbt_g[which], (const u32x4*)(s + base * 32), dc.state, dc.w, dc.zflag, m);
+            span_end(ctx);
+            ctx->launches++;
+            span_begin(ctx, FAM_FIN);
+            CKQ(launch_batch_invert(ctx, dc, m));
+            k_dc_finish<<<grid_for(m, 256, ctx->sms * 64), 256, 0, ctx->stream>>>(dc.state, dc.prefix, dc.zflag, status + base, 1,
+                                                                                (u32x4*)(out + base * 32), IDENT, nullptr, IDENT,
+                                                                                nullptr, m);
+            span_end(ctx);
+            ctx->launches++;
+            CK(cudaGetLastError());
+            continue;
+        }
         CKQ(launch_fixedbase(ctx, which, s + base * 32, F, m, 1));
         CKQ(launch_finish_dbl(ctx, dc, fsrc(F, IDENT), FNONE, FNONE, out + base * 32, IDENT, status + base, 1, m));
     }

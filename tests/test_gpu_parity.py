@@ -459,3 +459,34 @@ def test_chunked_batch_boundary(engine):
     out2, _ = engine.fixed_base(1, s2)
     assert (out2 == out2[0]).all()
     assert out2[0].tobytes() == R.compress(R.mul(int.from_bytes(s[0].tobytes(), "little"), R.PEDERSEN_H))
+
+
+@pytest.mark.parametrize("W", [8, 13, 16, 19])
+def test_fixed_base_large_window_tables(engine, W):
+    # fixedbase_big.cuh: tables of any window width give the same bytes as the C oracle (and as the shared-memory path)
+    import c_oracle as C
+    old = [engine.fixed_base_window(0), engine.fixed_base_window(1)]
+    try:
+        rng = np.random.default_rng(W)
+        n = 6000                                  # >= QQ_FBT_MIN_BATCH: the big-table kernels run
+        s = _rand_scalars(rng, n)
+        for i, k in enumerate(EDGE_SCALARS + [R.L - 2, 2**(W - 1), 2**(W - 1) - 1, 2**W, (2**252 // 3)]):
+            s[i] = np.frombuffer(sb(k), np.uint8)
+        s[100] = np.frombuffer(R.L.to_bytes(32, "little"), np.uint8)   # non-canonical -> status 2, zero bytes
+        for which in (0, 1):
+            engine.fixed_base_set_window(which, W)
+            assert engine.fixed_base_window(which) == W
+            out, st = engine.fixed_base(which, s)
+            eo, es = C.fixed_base(which, s)
+            assert (st == es).all() and st[100] == 2
+            assert (out == eo).all()
+        # the in-pipeline use (extended output summed with a variable-base term): generate_commitment on a slice
+        stq = Stream(b"fbt")
+        acc, _, _ = make_account(stq)
+        pk = np.tile(np.frombuffer(acc[:64], np.uint8), (n, 1))
+        out, st = engine.generate_commitment(pk, s, s[::-1].copy())
+        eo, es = C.generate_commitment(pk, s, s[::-1].copy())
+        assert (st == es).all() and (out == eo).all()
+    finally:
+        for which in (0, 1):
+            engine.fixed_base_set_window(which, old[which])
