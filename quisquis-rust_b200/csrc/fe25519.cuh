@@ -7,8 +7,9 @@
 // Why saturated limbs: the multiply pipe is the bound of every kernel here.  On sm_100a a
 // 32x32->64 product is one IMAD.WIDE.U32 (measured 0.7-0.8e13 thread-ops/s per GPU, ~2.6x slower than a plain
 // IMAD), and nothing else on the SM multiplies integers faster.  The radix-2^25.5 form needs 100 products per
-// multiplication; this form needs 64, and one level of subtractive Karatsuba brings that to 48, plus 8 products by
-// the constant 38 for the reduction: 56 IMAD.WIDE per multiplication, 44 per squaring.  Accumulation is free:
+// multiplication; this form needs 64 plus 8 products by the constant 38 for the reduction: 72 IMAD.WIDE per
+// multiplication, 44 per squaring (one level of subtractive Karatsuba, 48 + 8, is kept as fe_mul_inl but measures
+// slower in the kernels because of its carry-chain glue).  Accumulation is free:
 // each product is a (mad.lo.cc, madc.hi.cc) PTX pair that ptxas fuses into one IMAD.WIDE.U32.X with the carry in a
 // predicate register (verified in SASS), see tools/gen_field_ops.py for the even/odd accumulator scheme.
 // Additions, subtractions and the Karatsuba glue are carry chains on the ALU pipe (IADD3.X), which has 5x the
@@ -252,10 +253,12 @@ QQ_HD void fe_sq_inl(fe& h, const fe& f) {
 #if defined(__CUDACC__) && !defined(QQ_INLINE_FIELD_OPS)
 static __device__ __noinline__ fe fe_mul_ool(fe f, fe g) {
     fe h;
-#if defined(QQ_FE_MUL_SCHOOLBOOK)
-    fe_mul_school(h, f, g);
-#else
+#if defined(QQ_FE_MUL_KARATSUBA)
     fe_mul_inl(h, f, g);
+#else
+    // schoolbook (64 + 8 products) measured 4 % faster than Karatsuba (48 + 8) inside k_varbase_split: the Karatsuba
+    // glue is ~40 extra carry-chain instructions that issue beside the multiplies (tools/vb_bench.cu, profiles/)
+    fe_mul_school(h, f, g);
 #endif
     return h;
 }

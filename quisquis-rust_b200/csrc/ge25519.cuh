@@ -106,7 +106,18 @@ QQ_HD void ge_add_t(ge_p3& r, const ge_p3& p, const ge_cached& q) {
     fe_mul_t<INL>(r.Z, f, g);
     fe_mul_t<INL>(r.T, e, h);
 }
+#if defined(__CUDA_ARCH__) && defined(QQ_GE_OOL)
+// Group-level out-of-line variant (experiment, tools/vb_bench.cu): one call per group operation with the field products
+// inlined inside, instead of one call per field product.
+static __device__ __noinline__ ge_p3 ge_add_oolf(ge_p3 p, ge_cached q) {
+    ge_p3 r;
+    ge_add_t<true>(r, p, q);
+    return r;
+}
+QQ_HD void ge_add(ge_p3& r, const ge_p3& p, const ge_cached& q) { r = ge_add_oolf(p, q); }
+#else
 QQ_HD void ge_add(ge_p3& r, const ge_p3& p, const ge_cached& q) { ge_add_t<false>(r, p, q); }
+#endif
 // r = p + q, q affine Niels (7 M)
 template <bool INL>
 QQ_HD void ge_madd_t(ge_p3& r, const ge_p3& p, const ge_niels& q) {
@@ -147,8 +158,38 @@ QQ_HD void ge_dbl_t(ge_p3& r, const ge_p3& p) {
     fe_mul_t<INL>(r.Z, cz, ct);
     if (WITH_T) fe_mul_t<INL>(r.T, cx, cy);
 }
+#if defined(__CUDA_ARCH__) && defined(QQ_GE_OOL)
+struct ge_p2 {
+    fe X, Y, Z;
+};
+static __device__ __noinline__ ge_p3 ge_dbl_oolf_t(ge_p2 p) {
+    ge_p3 q, r;
+    q.X = p.X; q.Y = p.Y; q.Z = p.Z;
+    ge_dbl_t<true, true>(r, q);
+    return r;
+}
+static __device__ __noinline__ ge_p2 ge_dbl_oolf_not(ge_p2 p) {
+    ge_p3 q, r;
+    q.X = p.X; q.Y = p.Y; q.Z = p.Z;
+    ge_dbl_t<false, true>(r, q);
+    ge_p2 o;
+    o.X = r.X; o.Y = r.Y; o.Z = r.Z;
+    return o;
+}
+template <bool WITH_T>
+QQ_HD void ge_dbl(ge_p3& r, const ge_p3& p) {
+    ge_p2 q;
+    q.X = p.X; q.Y = p.Y; q.Z = p.Z;
+    if (WITH_T) r = ge_dbl_oolf_t(q);
+    else {
+        ge_p2 o = ge_dbl_oolf_not(q);
+        r.X = o.X; r.Y = o.Y; r.Z = o.Z;
+    }
+}
+#else
 template <bool WITH_T>
 QQ_HD void ge_dbl(ge_p3& r, const ge_p3& p) { ge_dbl_t<WITH_T, false>(r, p); }
+#endif
 
 // Ristretto equality (dalek RistrettoPoint::ct_eq): X1*Y2 == Y1*X2  or  X1*X2 == Y1*Y2
 QQ_HD u32 ge_ristretto_eq(const ge_p3& p, const ge_p3& q) {

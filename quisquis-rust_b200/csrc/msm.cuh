@@ -9,13 +9,15 @@
 //   k_msm_prepare     decompress point -> affine Niels (96 B, Z = 1), status, K signed digits, bucket histogram
 //   k_scan_*          bucket offsets (tile totals, scan of totals, apply)
 //   k_msm_scatter     counting sort of (term, sign) pairs by (window, bucket)
-//   k_msm_order_*     buckets ordered by population (descending) so the lanes of a warp get equal work
-//   k_msm_accumulate  one thread per bucket: mixed additions (7 M) of its points, 128-bit gathers of Niels points
-//   k_msm_reduce_seg  per (window, 32-bucket segment): running-sum trick, then + base * segment total
-//   k_point_sum_rows  per window: tree sum of the segment results (shared memory)
-//   k_msm_horner      sum_k 2^(c k) W_k
+//   k_msm_vcount/vfill buckets above `cap` entries are cut into virtual buckets (bounded work per thread)
+//   k_msm_order_*     virtual buckets ordered by population (descending) so the lanes of a warp get equal work
+//   k_msm_accumulate  one thread per virtual bucket: mixed additions (7 M), next gather issued before each addition
+//   k_msm_reduce0/_level  recursive running-sum reduction, 8 elements per thread and level, no scalar multiplications
+//   k_msm_sum_levels  tree sums of the per-level W arrays;  k_msm_window_totals  Horner over the levels
+//   k_msm_horner      sum_k 2^(c k) T_k
 #pragma once
 #include "kernels.cuh"
+#include "ge_coop.cuh"
 
 namespace qq {
 
@@ -198,97 +200,249 @@ __global__ void __launch_bounds__(256) k_msm_scatter(const int16_t* __restrict__
 }
 
 // ---- bucket ordering by population (descending), counting sort on min(count, 2047) -----------------------------
+// Populations cluster on a few dozen values, so the histogram and the slot reservation are privatised per block in
+// shared memory (one global atomic per (block, occupied bin) instead of one per bucket).
 #define QQ_ORDER_BINS 2048
-__global__ void k_msm_order_hist(const unsigned int* __restrict__ counts, size_t total, unsigned int* __restrict__ hist) {
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < total; b += stride) {
-        unsigned int c = counts[b];
-        unsigned int key = QQ_ORDER_BINS - 1 - (c < QQ_ORDER_BINS - 1 ? c : QQ_ORDER_BINS - 1);
-        atomicAdd(&hist[key], 1u);
-    }
+#define QQ_ORDER_TILE 4096   // elements per block iteration (256 threads x 16)
+__device__ __forceinline__ unsigned int order_key(unsigned int c) {
+    return QQ_ORDER_BINS - 1 - (c < QQ_ORDER_BINS - 1 ? c : QQ_ORDER_BINS - 1);
 }
-__global__ void k_msm_order_scatter(const unsigned int* __restrict__ counts, size_t total,
-                                    const unsigned int* __restrict__ hist_off, unsigned int* __restrict__ cursor,
-                                    unsigned int* __restrict__ order) {
+__global__ void __launch_bounds__(256) k_msm_order_hist(const unsigned int* __restrict__ counts, size_t total,
+                                                        unsigned int* __restrict__ hist) {
+    __shared__ unsigned int sh[QQ_ORDER_BINS];
+    for (int i = threadIdx.x; i < QQ_ORDER_BINS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
     size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < total; b += stride) {
-        unsigned int c = counts[b];
-        unsigned int key = QQ_ORDER_BINS - 1 - (c < QQ_ORDER_BINS - 1 ? c : QQ_ORDER_BINS - 1);
-        unsigned int slot = atomicAdd(&cursor[key], 1u);
-        order[hist_off[key] + slot] = (unsigned int)b;
+    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < total; b += stride) atomicAdd(&sh[order_key(counts[b])], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < QQ_ORDER_BINS; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+__global__ void __launch_bounds__(256) k_msm_order_scatter(const unsigned int* __restrict__ counts, size_t total,
+                                                           const unsigned int* __restrict__ hist_off,
+                                                           unsigned int* __restrict__ cursor, unsigned int* __restrict__ order) {
+    __shared__ unsigned int sh_cnt[QQ_ORDER_BINS];   // tile histogram, then running local rank
+    __shared__ unsigned int sh_base[QQ_ORDER_BINS];  // global slot of the tile's first element of each bin
+    for (size_t tile = (size_t)blockIdx.x * QQ_ORDER_TILE; tile < total; tile += (size_t)gridDim.x * QQ_ORDER_TILE) {
+        for (int i = threadIdx.x; i < QQ_ORDER_BINS; i += blockDim.x) sh_cnt[i] = 0;
+        __syncthreads();
+        size_t end = tile + QQ_ORDER_TILE < total ? tile + QQ_ORDER_TILE : total;
+        for (size_t b = tile + threadIdx.x; b < end; b += blockDim.x) atomicAdd(&sh_cnt[order_key(counts[b])], 1u);
+        __syncthreads();
+        for (int i = threadIdx.x; i < QQ_ORDER_BINS; i += blockDim.x) {
+            unsigned int c = sh_cnt[i];
+            if (c) sh_base[i] = hist_off[i] + atomicAdd(&cursor[i], c);
+            sh_cnt[i] = 0;
+        }
+        __syncthreads();
+        for (size_t b = tile + threadIdx.x; b < end; b += blockDim.x) {
+            unsigned int key = order_key(counts[b]);
+            unsigned int r = atomicAdd(&sh_cnt[key], 1u);
+            order[sh_base[key] + r] = (unsigned int)b;
+        }
+        __syncthreads();
     }
 }
 
-// ---- bucket accumulation: thread t sums the points of bucket order[t] ---------------------------------------------
+// ---- virtual buckets ---------------------------------------------------------------------------------------------------
+// A bucket with more than `cap` entries is cut into ceil(cnt / cap) virtual buckets, each summed by its own thread, so
+// that skewed digit distributions (the short top window: scalars < 2^253 leave it only 2^(253 - c (K-1)) distinct
+// digits; small balances; repeated scalars) do not serialise on one thread.  nsub[b] = number of parts of bucket b.
+__global__ void k_msm_vcount(const unsigned int* __restrict__ counts, size_t total, unsigned int cap,
+                             unsigned int* __restrict__ nsub) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < total; b += stride)
+        nsub[b] = (counts[b] + cap - 1) / cap;
+}
+__global__ void k_msm_vfill(const unsigned int* __restrict__ counts, const unsigned int* __restrict__ offsets,
+                            const unsigned int* __restrict__ voff, size_t total, unsigned int cap,
+                            unsigned int* __restrict__ vstart, unsigned int* __restrict__ vcnt,
+                            unsigned int* __restrict__ multi, unsigned int* __restrict__ nmulti) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < total; b += stride) {
+        unsigned int c = counts[b], o = offsets[b], v = voff[b];
+        if (c > cap) multi[atomicAdd(nmulti, 1u)] = (unsigned int)b;
+        for (unsigned int done = 0; done < c; done += cap, v++) {
+            vstart[v] = o + done;
+            vcnt[v] = c - done < cap ? c - done : cap;
+        }
+    }
+}
+
+// affine Niels (Z = 1) -> extended with Z = 4: X = 2 (ypx - ymx) = 4x, Y = 2 (ypx + ymx) = 4y, T = (ypx - ymx)(ypx + ymx) = 4xy
+__device__ __forceinline__ void ge_from_niels(ge_p3& r, const ge_niels& n) {
+    fe dx, sy;
+    fe_sub(dx, n.ypx, n.ymx);
+    fe_add(sy, n.ypx, n.ymx);
+    fe_add(r.X, dx, dx);
+    fe_add(r.Y, sy, sy);
+    fe_0(r.Z);
+    r.Z.v[0] = 4;
+    fe_mul(r.T, dx, sy);
+}
+
+// ---- bucket accumulation: thread t sums the entries of virtual bucket order[t] ----------------------------------------
+// The gather of entry e + 1 (index, then 96 B Niels point) is issued before the mixed addition of entry e.
 __global__ void __launch_bounds__(128) k_msm_accumulate(const u32x4* __restrict__ niels,
                                                         const unsigned int* __restrict__ sorted,
-                                                        const unsigned int* __restrict__ offsets,
-                                                        const unsigned int* __restrict__ counts,
-                                                        const unsigned int* __restrict__ order, size_t total,
-                                                        u32x4* __restrict__ buckets) {
+                                                        const unsigned int* __restrict__ vstart,
+                                                        const unsigned int* __restrict__ vcnt,
+                                                        const unsigned int* __restrict__ order, size_t vmax,
+                                                        u32x4* __restrict__ partial) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    unsigned int b = order[t];
-    unsigned int cnt = counts[b];
-    const unsigned int* ent = sorted + offsets[b];
+    if (t >= vmax) return;
+    unsigned int v = order[t];
+    unsigned int cnt = vcnt[v];
+    if (cnt == 0) return;
+    const unsigned int* ent = sorted + vstart[v];
+    unsigned int cur = __ldg(ent);
+    ge_niels nl, nx;
+    niels_load_padded(nl, niels + (size_t)QQ_NIELS_STRIDE_Q * (cur & 0x7fffffffu));
+    ge_niels_cneg(nl, cur >> 31);
     ge_p3 acc;
-    ge_identity(acc);
-    for (unsigned int e = 0; e < cnt; e++) {
-        unsigned int v = __ldg(ent + e);
-        ge_niels nl;
-        niels_load_padded(nl, niels + (size_t)QQ_NIELS_STRIDE_Q * (v & 0x7fffffffu));
-        ge_niels_cneg(nl, v >> 31);
+    ge_from_niels(acc, nl);
+    if (cnt > 1) {
+        cur = __ldg(ent + 1);
+        niels_load_padded(nx, niels + (size_t)QQ_NIELS_STRIDE_Q * (cur & 0x7fffffffu));
+    }
+    for (unsigned int e = 1; e < cnt; e++) {
+        nl = nx;
+        unsigned int sign = cur >> 31;
+        if (e + 1 < cnt) {
+            cur = __ldg(ent + e + 1);
+            niels_load_padded(nx, niels + (size_t)QQ_NIELS_STRIDE_Q * (cur & 0x7fffffffu));
+        }
+        ge_niels_cneg(nl, sign);
         ge_madd(acc, acc, nl);
     }
-    ge_p3_store(buckets + QQ_PT_Q * (size_t)b, acc);
+    ge_p3_store(partial + QQ_PT_Q * (size_t)v, acc);
+}
+
+// Buckets that were cut into several virtual buckets: one warp per such bucket sums its partial sums (lanes stride over
+// the parts, then a shared-memory tree) into the first part, so that the reduction reads exactly one point per bucket.
+// `multi` lists those buckets (appended by k_msm_vfill), *nmulti is their number.
+__global__ void __launch_bounds__(128) k_msm_combine(u32x4* __restrict__ partial, const unsigned int* __restrict__ voff,
+                                                     const unsigned int* __restrict__ nsub,
+                                                     const unsigned int* __restrict__ multi,
+                                                     const unsigned int* __restrict__ nmulti) {
+    __shared__ u32x4 sm[128 * QQ_PT_Q];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    u32x4* my = sm + QQ_PT_Q * (size_t)(wib * 32);
+    unsigned int cnt = *nmulti;
+    for (unsigned int w = blockIdx.x * 4 + wib; w < cnt; w += gridDim.x * 4) {
+        unsigned int b = multi[w];
+        unsigned int v0 = voff[b], np = nsub[b];
+        ge_p3 acc;
+        ge_identity(acc);
+        for (unsigned int q = lane; q < np; q += 32) {
+            ge_p3 p;
+            ge_p3_load(p, partial + QQ_PT_Q * (size_t)(v0 + q));
+            ge_cached c;
+            ge_to_cached(c, p);
+            ge_add(acc, acc, c);
+        }
+        ge_p3_store(my + QQ_PT_Q * lane, acc);
+        __syncwarp();
+        for (int s = 16; s > 0; s >>= 1) {
+            if (lane < s && (unsigned int)(lane + s) < np) {
+                ge_p3 p;
+                ge_p3_load(p, my + QQ_PT_Q * (lane + s));
+                ge_cached c;
+                ge_to_cached(c, p);
+                ge_add(acc, acc, c);
+                ge_p3_store(my + QQ_PT_Q * lane, acc);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) ge_p3_store(partial + QQ_PT_Q * (size_t)v0, acc);
+        __syncwarp();
+    }
 }
 
 // ---- bucket reduction ------------------------------------------------------------------------------------------------
-// thread (k, s): segment of SEG buckets starting at base = s * SEG of window k:
-//   run = sum B_j, W = sum (j - base + 1) B_j  (running-sum trick, high to low), result = W + base * run
-__global__ void __launch_bounds__(128) k_msm_reduce_seg(const u32x4* __restrict__ buckets, msm_geom g, int SEG,
-                                                        u32x4* __restrict__ seg_out) {
-    int nseg = g.NB / SEG;
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= g.K * nseg) return;
-    int k = t / nseg, s = t - k * nseg;
-    int base = s * SEG;
-    const u32x4* bk = buckets + QQ_PT_Q * ((size_t)k * g.NB + base);
-    ge_p3 run, sum;
-    ge_identity(run);
-    ge_identity(sum);
-    for (int j = SEG - 1; j >= 0; j--) {
-        ge_p3 p;
-        ge_p3_load(p, bk + QQ_PT_Q * j);
-        ge_cached c;
-        ge_to_cached(c, p);
-        ge_add(run, run, c);
-        ge_to_cached(c, run);
-        ge_add(sum, sum, c);
+// Window value T = sum_{j=1..NB} j B_j.  With A_i = B_{i+1}:  T = P0(A) + sum A,  P0(A) = sum_i i A_i, and for segments
+// of S elements  P0(A) = sum_s W_s + S * P0(run),  W_s = sum_{i<S} i A_{sS+i},  run_s = sum_{i<S} A_{sS+i}
+// (running-sum trick, 2S - 1 additions per segment).  Applied recursively the element count shrinks by S per level:
+//     T = sum_l S^l SW_l + R,   SW_l = sum_s W^l_s,   R = the single run left at the top.
+// No scalar multiplications by segment bases, and every level is data-parallel over (window, segment).
+#define QQ_MSM_RSEG 8
+// k_msm_reduce0, k_msm_window_totals and k_msm_horner are four-lane cooperative (ge_coop.cuh): group = 4 adjacent lanes.
+// One running-sum step: run += A_i; W += run   (skipped for i = 0).
+__device__ __forceinline__ void coop_runsum_step(fe& run, fe& w, const fe& a, bool add_w, int r) {
+    fe ca = coop_to_cached(a, r);
+    run = coop_add(run, ca, r);
+    if (add_w) {
+        fe cr = coop_to_cached(run, r);
+        w = coop_add(w, cr, r);
     }
-    if (base != 0) {
-        // sum += base * run  (double-and-add over the bits of base, at most 15 bits)
-        ge_cached cr;
-        ge_to_cached(cr, run);
-        ge_p3 m;
-        ge_identity(m);
-        for (int bit = 15; bit >= 0; bit--) {
-            ge_dbl<true>(m, m);
-            if ((base >> bit) & 1) ge_add(m, m, cr);
-        }
-        ge_cached cm;
-        ge_to_cached(cm, m);
-        ge_add(sum, sum, cm);
-    }
-    ge_p3_store(seg_out + QQ_PT_Q * (size_t)t, sum);
 }
-// block r sums in[r * row_len .. (r + 1) * row_len) -> out[r]
-__global__ void __launch_bounds__(128) k_point_sum_rows(const u32x4* __restrict__ in, int row_len,
-                                                        u32x4* __restrict__ out) {
+// level 0: element (k, j) = bucket k * NB + j; after k_msm_combine its sum is the first of its partial sums
+__global__ void __launch_bounds__(128) k_msm_reduce0(const u32x4* __restrict__ partial, const unsigned int* __restrict__ voff,
+                                                     const unsigned int* __restrict__ nsub, msm_geom g, int mout,
+                                                     u32x4* __restrict__ run_out, u32x4* __restrict__ w_out) {
+    int gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 2, r = threadIdx.x & 3;
+    bool act = gid < g.K * mout;
+    int t = act ? gid : 0;
+    int k = t / mout, s = t - k * mout;
+    fe run = coop_identity(r), w = coop_identity(r);
+#pragma unroll
+    for (int i = QQ_MSM_RSEG - 1; i >= 0; i--) {
+        int j = s * QQ_MSM_RSEG + i;
+        fe a = coop_identity(r);
+        if (j < g.NB) {
+            size_t b = (size_t)k * g.NB + j;
+            if (nsub[b] != 0) a = coop_load(partial + QQ_PT_Q * (size_t)voff[b], r);
+        }
+        coop_runsum_step(run, w, a, i > 0, r);
+    }
+    if (act) {
+        coop_store(run_out + QQ_PT_Q * (size_t)t, r, run);
+        coop_store(w_out + QQ_PT_Q * (size_t)t, r, w);
+    }
+}
+// level >= 1: in[k][0..m) -> run_out[k][0..mout), w_out[k][0..mout),  mout = ceil(m / S).  One thread per segment:
+// measured faster than the four-lane form here (55 us vs 70 us per level at K = 16, m = 4096; profiles/).
+__global__ void __launch_bounds__(128) k_msm_reduce_level(const u32x4* __restrict__ in, int K, int m, int mout,
+                                                          u32x4* __restrict__ run_out, u32x4* __restrict__ w_out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= K * mout) return;
+    int k = t / mout, s = t - k * mout;
+    ge_p3 run, w;
+    ge_identity(run);
+    ge_identity(w);
+    for (int i = QQ_MSM_RSEG - 1; i >= 0; i--) {
+        int j = s * QQ_MSM_RSEG + i;
+        if (j < m) {
+            ge_p3 p;
+            ge_p3_load(p, in + QQ_PT_Q * ((size_t)k * m + j));
+            ge_cached c;
+            ge_to_cached(c, p);
+            ge_add(run, run, c);
+        }
+        if (i > 0) {
+            ge_cached c;
+            ge_to_cached(c, run);
+            ge_add(w, w, c);
+        }
+    }
+    ge_p3_store(run_out + QQ_PT_Q * (size_t)t, run);
+    ge_p3_store(w_out + QQ_PT_Q * (size_t)t, w);
+}
+// SW_l for every (level, window): block (l, k) sums row k of level l's W array (w_all + off[l], rows of len[l] points)
+#define QQ_MSM_MAXLEVELS 8
+struct msm_levels {
+    int L;
+    int len[QQ_MSM_MAXLEVELS];
+    unsigned int off[QQ_MSM_MAXLEVELS];
+};
+__global__ void __launch_bounds__(128) k_msm_sum_levels(const u32x4* __restrict__ w_all, msm_levels lv, int K,
+                                                        u32x4* __restrict__ sw) {
     __shared__ u32x4 sm[128 * QQ_PT_Q];
+    int l = blockIdx.x / K, k = blockIdx.x - l * K;
+    int row_len = lv.len[l];
+    const u32x4* row = w_all + QQ_PT_Q * ((size_t)lv.off[l] + (size_t)k * row_len);
     ge_p3 acc;
     ge_identity(acc);
-    const u32x4* row = in + QQ_PT_Q * (size_t)blockIdx.x * row_len;
     for (int t = threadIdx.x; t < row_len; t += blockDim.x) {
         ge_p3 p;
         ge_p3_load(p, row + QQ_PT_Q * t);
@@ -299,7 +453,7 @@ __global__ void __launch_bounds__(128) k_point_sum_rows(const u32x4* __restrict_
     ge_p3_store(sm + QQ_PT_Q * threadIdx.x, acc);
     __syncthreads();
     for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-        if (threadIdx.x < s) {
+        if (threadIdx.x < s && threadIdx.x + s < row_len) {
             ge_p3 p;
             ge_p3_load(p, sm + QQ_PT_Q * (threadIdx.x + s));
             ge_cached c;
@@ -309,69 +463,37 @@ __global__ void __launch_bounds__(128) k_point_sum_rows(const u32x4* __restrict_
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) ge_p3_store(out + QQ_PT_Q * blockIdx.x, acc);
+    if (threadIdx.x == 0) ge_p3_store(sw + QQ_PT_Q * blockIdx.x, acc);
 }
-// result = sum_k 2^(c k) win[k].  A chain of c (K - 1) = 240 dependent doublings: latency, not throughput.  Four lanes of one
-// warp cooperate on every doubling -- lane l squares one of (X, Y, Z, X + Y), the four squares are exchanged through
-// shared memory, every lane forms the completed-point terms and multiplies out one output coordinate -- so a doubling
-// costs one squaring + one multiplication of latency instead of four + four.
+// wins[k] = R_k + sum_l S^l SW_l[k]   (Horner over the levels: log2(S) doublings + one addition per level)
+__global__ void __launch_bounds__(128) k_msm_window_totals(const u32x4* __restrict__ sw, const u32x4* __restrict__ run_top,
+                                                           msm_levels lv, int K, u32x4* __restrict__ wins) {
+    int gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 2, r = threadIdx.x & 3;
+    bool act = gid < K;
+    int k = act ? gid : 0;
+    fe t = coop_load(sw + QQ_PT_Q * ((size_t)(lv.L - 1) * K + k), r);
+    for (int l = lv.L - 2; l >= 0; l--) {
+        t = coop_dbl(t, r);
+        t = coop_dbl(t, r);
+        t = coop_dbl(t, r);
+        fe p = coop_load(sw + QQ_PT_Q * ((size_t)l * K + k), r);
+        t = coop_add(t, coop_to_cached(p, r), r);
+    }
+    fe p = coop_load(run_top + QQ_PT_Q * k, r);
+    t = coop_add(t, coop_to_cached(p, r), r);
+    if (act) coop_store(wins + QQ_PT_Q * k, r, t);
+}
+// result = sum_k 2^(c k) win[k]: a chain of c (K - 1) dependent doublings (240 for c = 16), each one squaring + one
+// multiplication of latency.  One warp; every group of four lanes computes the same chain, group 0 stores it.
 __global__ void __launch_bounds__(32) k_msm_horner(const u32x4* __restrict__ win, msm_geom g, u32x4* __restrict__ result) {
-    __shared__ fe sq_s[4];
-    __shared__ fe co_s[4];
-    const int lane = threadIdx.x;
-    if (blockIdx.x != 0 || lane >= 4) return;
-    const unsigned mask = 0xfu;
-    ge_p3 acc;
-    ge_p3_load(acc, win + QQ_PT_Q * (size_t)(g.K - 1));
-    // lane l keeps coordinate l of the running point in `mine` (0: X, 1: Y, 2: Z, 3: T)
-    fe mine = lane == 0 ? acc.X : (lane == 1 ? acc.Y : (lane == 2 ? acc.Z : acc.T));
+    int r = threadIdx.x & 3;
+    fe acc = coop_load(win + QQ_PT_Q * (size_t)(g.K - 1), r);
     for (int k = g.K - 2; k >= 0; k--) {
-        for (int i = 0; i < g.c; i++) {
-            co_s[lane] = mine;
-            __syncwarp(mask);
-            fe in;
-            if (lane == 3) fe_add(in, co_s[0], co_s[1]);   // X + Y
-            else in = mine;
-            fe sq;
-            fe_sq(sq, in);
-            sq_s[lane] = sq;
-            __syncwarp(mask);
-            fe xx = sq_s[0], yy = sq_s[1], zz = sq_s[2], s = sq_s[3];
-            fe cx, cy, cz, ct, t;
-            fe_add(cy, yy, xx);
-            fe_sub(cz, yy, xx);
-            fe_sub(cx, s, cy);
-            fe_add(t, zz, zz);
-            fe_sub(ct, t, cz);
-            // X3 = cx ct, Y3 = cy cz, Z3 = cz ct, T3 = cx cy
-            fe a = (lane == 0 || lane == 3) ? cx : (lane == 1 ? cy : cz);
-            fe b = (lane == 0 || lane == 2) ? ct : (lane == 1 ? cz : cy);
-            fe_mul(mine, a, b);
-            __syncwarp(mask);
-        }
-        // add window k: lane 0 gathers the point, performs the addition, and redistributes
-        co_s[lane] = mine;
-        __syncwarp(mask);
-        if (lane == 0) {
-            ge_p3 r, p;
-            r.X = co_s[0]; r.Y = co_s[1]; r.Z = co_s[2]; r.T = co_s[3];
-            ge_p3_load(p, win + QQ_PT_Q * (size_t)k);
-            ge_cached c;
-            ge_to_cached(c, p);
-            ge_add(r, r, c);
-            co_s[0] = r.X; co_s[1] = r.Y; co_s[2] = r.Z; co_s[3] = r.T;
-        }
-        __syncwarp(mask);
-        mine = co_s[lane];
-        __syncwarp(mask);
+        for (int i = 0; i < g.c; i++) acc = coop_dbl(acc, r);
+        fe p = coop_load(win + QQ_PT_Q * (size_t)k, r);
+        acc = coop_add(acc, coop_to_cached(p, r), r);
     }
-    co_s[lane] = mine;
-    __syncwarp(mask);
-    if (lane == 0) {
-        ge_p3 r;
-        r.X = co_s[0]; r.Y = co_s[1]; r.Z = co_s[2]; r.T = co_s[3];
-        ge_p3_store(result, r);
-    }
+    if (threadIdx.x < 4) coop_store(result, r, acc);
 }
 
 }  // namespace qq

@@ -30,6 +30,8 @@ struct qq_ctx {
     size_t io_cap = 0;
     cudaEvent_t user_ev[8] = {nullptr};
     u32* fb_tbl[2] = {nullptr, nullptr};      // shared-memory-sized tables (W = QQ_FB_W)
+    u32x4* msm_res = nullptr;                 // per-call MSM result point + export bytes (outside the workspace slab)
+    uint8_t* msm_small = nullptr;
     u32x4* fbt[2] = {nullptr, nullptr};       // large-window tables in L2 / HBM (fixedbase_big.cuh), optional
     fbt_geom fbt_g[2] = {{0, 0, 0}, {0, 0, 0}};
     uint8_t base_pk[64];
@@ -423,6 +425,8 @@ extern "C" int qq_init(qq_ctx** out, int device) {
         CK(cudaStreamSynchronize(ctx->stream));
         CK(cudaGetLastError());
         CK(cudaFree(dbase));
+        CK(cudaMalloc((void**)&ctx->msm_res, QQ_PT_BYTES));
+        CK(cudaMalloc((void**)&ctx->msm_small, 256));
         // large-window tables: 16-bit windows (50 MB per base, L2 resident) unless QQ_FB_WINDOW says otherwise
         int W = 16;
         if (const char* e = getenv("QQ_FB_WINDOW")) W = atoi(e);
@@ -443,6 +447,8 @@ extern "C" void qq_destroy(qq_ctx* ctx) {
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->io) cudaFree(ctx->io);
+    if (ctx->msm_res) cudaFree(ctx->msm_res);
+    if (ctx->msm_small) cudaFree(ctx->msm_small);
     for (int i = 0; i < 8; i++)
         if (ctx->user_ev[i]) cudaEventDestroy(ctx->user_ev[i]);
     for (int b = 0; b < 2; b++) {
