@@ -31,6 +31,7 @@ IMAD_PER_VARBASE = 289_000
 # what k_varbase_split actually executes per account (2 points x 2 scalars through 4 quarter tables, scalarmult.cuh):
 # 2 x (1248 S + 2253 M) with M = 144, S = 88 IMAD units -- 75 % of the 4 x 289 000 the cost model charges
 IMAD_EXECUTED_VARBASE_PER_ACCOUNT = 2 * (1248 * 88 + 2253 * 144)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 31.15e9
 IMAD_PER_FIXED_COMPRESSED = 91_400  # FIXED(4) + ENC
 IMAD_PER_MSM_POINT = 43_900        # compressed input, n = 2^20, c = 16
 BYTES_PER_UPDATE_ACCOUNT = 224 + 128 + 1
@@ -389,7 +390,13 @@ def run_b200(args):
                          "whole_step_frac": step_frac, "kernel_ms_per_launch": vb_avg_ms,
                          "kernel_share_of_step": vb_avg_ms / (dev_ms / args.steps),
                          "breakdown_ms_per_step": {k_: v_ / args.steps for k_, v_ in breakdown.items()},
-                         "traffic": None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one k_varbase_split launch at 2^20 accounts, from
+                         # the ncu --set full capture summarised in profiles/ncu_varbase_split_r01_summary.json (per-thread
+                         # window tables spilling past L2, 6 % of HBM bandwidth; the same capture shows the FMA-heavy
+                         # integer-multiply pipe active 81 % of elapsed cycles)
+                         "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH * (n / (1 << 20)),
+                         "traffic_unit": "bytes per launch (ncu, 2^20-account launch, scaled linearly to this batch)",
+                         "ncu_fmaheavy_pipe_active_pct": 81.2,
                          "hbm": {"algorithmic_bytes_per_step": n * BYTES_PER_UPDATE_ACCOUNT,
                                  "achieved_GBps": n * BYTES_PER_UPDATE_ACCOUNT / (dev_ms / args.steps * 1e-3) / 1e9,
                                  "peak_GBps": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
