@@ -318,6 +318,37 @@ def run_b200(args):
         msm = {"points": m, "ms": msm_ms, "points_per_sec_per_gpu": m / (msm_ms * 1e-3),
                "breakdown_ms": bdm, "matches_known_dlog": msm_ok,
                "imad_frac": m * IMAD_PER_MSM_POINT / (msm_ms * 1e-3) / peak["imad_lo_per_s"]}
+        # ---- ONE MSM of world x m points sharded over the ranks: Pippenger on the local slice, 128-byte partial sums
+        # all-gathered over NCCL, the ranks' points added on every rank (quisquis-rust_b200/distributed.py)
+        if world > 1:
+            part = torch.zeros(256, dtype=torch.uint8, device=dev)
+            gathered = [torch.zeros(132, dtype=torch.uint8, device=dev) for _ in range(world)]
+
+            def sharded_once():
+                eng.call_dev("qq_msm_partial_dev", vp(a_d.data_ptr()), vp(pts_d.data_ptr()), ctypes.c_size_t(m),
+                             vp(part.data_ptr()), vp(part.data_ptr() + 128))
+                dist.all_gather(gathered, part[:132])
+                allb = torch.stack(gathered).cpu().numpy()
+                if allb[:, 128].any():
+                    return None, int(allb[:, 128].max())
+                return eng.points_sum(allb[:, :128].reshape(-1))
+
+            sharded_once()
+            barrier()
+            t0s = time.time()
+            for _ in range(reps):
+                out_s, ident_s = sharded_once()
+            torch.cuda.synchronize(dev)
+            sh_ms = (time.time() - t0s) * 1e3 / reps
+            barrier()
+            # expected: (sum over all ranks of sum a_i h_i) * B
+            tot_t = torch.from_numpy(np.frombuffer((tot % L).to_bytes(32, "little"), np.uint8).copy()).to(dev)
+            tots = [torch.zeros(32, dtype=torch.uint8, device=dev) for _ in range(world)]
+            dist.all_gather(tots, tot_t)
+            gtot = sum(int.from_bytes(t_.cpu().numpy().tobytes(), "little") for t_ in tots) % L
+            exp_s, _ = eng.fixed_base(0, np.frombuffer(gtot.to_bytes(32, "little"), np.uint8))
+            msm["sharded"] = {"points_total": m * world, "ms": sh_ms, "matches_known_dlog": bool((exp_s[0] == out_s).all()),
+                              "exchange": "all_gather of 128-byte partial sums + status over NCCL, then %d point additions" % (world - 1)}
 
     # ---- reduce over ranks ----------------------------------------------------------------------------------------
     def maxr(x):
@@ -329,6 +360,9 @@ def run_b200(args):
 
     dev_ms_max, wall_ms_max, e2e_ms_max = maxr(dev_ms), maxr(wall_ms), maxr(e2e_ms)
     msm_ms_max = maxr(msm["ms"]) if msm else None
+    if msm and "sharded" in msm:
+        msm["sharded"]["ms"] = maxr(msm["sharded"]["ms"])
+        msm["sharded"]["points_per_sec"] = msm["sharded"]["points_total"] / (msm["sharded"]["ms"] * 1e-3)
     total_accounts = n * world * args.steps
     value = total_accounts / (wall_ms_max * 1e-3)
     e2e_value = total_accounts / (e2e_ms_max * 1e-3)
