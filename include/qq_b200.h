@@ -153,6 +153,21 @@ int qq_msm_partial(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* points, s
                    uint8_t* status);
 int qq_msm_partial_dev(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t* out_xyzt,
                        uint8_t* status);
+/* Point sets that are reused across many MSMs -- the Bulletproofs generators G_i, H_i, which the reference rebuilds
+ * with BulletproofGens::new(64, 16) on every range-proof verification (src/accounts/verifier.rs:510,540), the Pedersen
+ * bases of src/pedersen/vectorpedersen.rs:45-75 -- can be decompressed ONCE into the library's device-resident MSM
+ * form (96 bytes per point + validity).  qq_msm_prepared then skips the per-point inverse square root, which is 62 %
+ * of the work of qq_msm.  An invalid point in the set makes every MSM that touches it return QQ_ST_BAD_POINT. */
+typedef struct qq_prepared qq_prepared;
+int qq_msm_points_prepare(qq_ctx* ctx, const uint8_t* points, size_t n, qq_prepared** out);
+int qq_msm_points_prepare_dev(qq_ctx* ctx, const uint8_t* points, size_t n, qq_prepared** out);
+void qq_msm_points_free(qq_ctx* ctx, qq_prepared* p);
+size_t qq_msm_points_count(const qq_prepared* p);
+/* out = sum_{i<n} s_i * P_i over the first n points of the prepared set (n <= qq_msm_points_count) */
+int qq_msm_prepared(qq_ctx* ctx, const uint8_t* scalars, const qq_prepared* points, size_t n, uint8_t* out_point,
+                    uint8_t* status);
+int qq_msm_prepared_dev(qq_ctx* ctx, const uint8_t* scalars, const qq_prepared* points, size_t n, uint8_t* out_point,
+                        uint8_t* status);
 /* sum of k extended points given as k x 128 B (X,Y,Z,T canonical) -> compressed; *is_identity set to 1/0 */
 int qq_points_sum(qq_ctx* ctx, const uint8_t* xyzt, size_t k, uint8_t* out_point, uint8_t* is_identity);
 /* many small MSMs (2..9 terms each in the reference, src/accounts/verifier.rs:165-880, src/shuffle/*):

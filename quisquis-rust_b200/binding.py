@@ -19,7 +19,8 @@ EXPORTS = [
     "qq_mul_commitment_batch", "qq_update_account_batch", "qq_update_account_batch_dev",
     "qq_verify_account_batch", "qq_verify_account_batch_dev", "qq_delta_epsilon_batch", "qq_delta_identity_check",
     "qq_fixed_base_batch", "qq_fixed_base_batch_dev", "qq_fixed_base_set_window", "qq_fixed_base_window", "qq_msm", "qq_msm_dev", "qq_msm_partial", "qq_msm_partial_dev",
-    "qq_points_sum", "qq_msm_segmented",
+    "qq_points_sum", "qq_msm_segmented", "qq_msm_points_prepare", "qq_msm_points_prepare_dev", "qq_msm_points_free",
+    "qq_msm_points_count", "qq_msm_prepared", "qq_msm_prepared_dev",
 ]
 
 
@@ -81,6 +82,14 @@ def load_library():
     for name in ("qq_msm", "qq_msm_dev", "qq_msm_partial", "qq_msm_partial_dev"):
         getattr(lib, name).argtypes = [vp, u8p, u8p, sz, u8p, u8p]
     lib.qq_points_sum.argtypes = [vp, u8p, sz, u8p, u8p]
+    for name in ("qq_msm_points_prepare", "qq_msm_points_prepare_dev"):
+        getattr(lib, name).argtypes = [vp, u8p, sz, ctypes.POINTER(vp)]
+    lib.qq_msm_points_free.argtypes = [vp, vp]
+    lib.qq_msm_points_free.restype = None
+    lib.qq_msm_points_count.argtypes = [vp]
+    lib.qq_msm_points_count.restype = ctypes.c_size_t
+    for name in ("qq_msm_prepared", "qq_msm_prepared_dev"):
+        getattr(lib, name).argtypes = [vp, u8p, vp, sz, u8p, u8p]
     lib.qq_msm_segmented.argtypes = [vp, u8p, u8p, vp, sz, u8p, u8p]
     for name in EXPORTS:
         f = getattr(lib, name)
@@ -278,6 +287,24 @@ class Engine:
         _u8(points, n * 32)
         out, st = np.zeros(128, np.uint8), np.zeros(1, np.uint8)
         self._ck(self.lib.qq_msm_partial(self.h, _ptr(scalars), _ptr(points), n, _ptr(out), _ptr(st)), "qq_msm_partial")
+        return out, int(st[0])
+
+    def msm_points_prepare(self, points):
+        """Decompress a reusable point set once; returns an opaque handle for msm_prepared / msm_points_free."""
+        points = _u8(points)
+        n = points.size // 32
+        h = ctypes.c_void_p()
+        self._ck(self.lib.qq_msm_points_prepare(self.h, _ptr(points), n, ctypes.byref(h)), "qq_msm_points_prepare")
+        return h
+
+    def msm_points_free(self, handle):
+        self.lib.qq_msm_points_free(self.h, handle)
+
+    def msm_prepared(self, scalars, handle):
+        scalars = _u8(scalars)
+        n = scalars.size // 32
+        out, st = np.zeros(32, np.uint8), np.zeros(1, np.uint8)
+        self._ck(self.lib.qq_msm_prepared(self.h, _ptr(scalars), handle, n, _ptr(out), _ptr(st)), "qq_msm_prepared")
         return out, int(st[0])
 
     def points_sum(self, xyzt):

@@ -48,16 +48,28 @@ __device__ __forceinline__ fe coop_identity(int r) {
     return a;
 }
 // distributed (X, Y, Z, T) -> distributed cached form (Y-X, Y+X, 2Z, 2dT): lanes 2 and 3 work on their own coordinate
+template <bool INL>
+__device__ __forceinline__ void coop_mul(fe& h, const fe& f, const fe& g) {
+    if (INL) fe_mul_school(h, f, g);
+    else fe_mul(h, f, g);
+}
+template <bool INL>
+__device__ __forceinline__ void coop_sq(fe& h, const fe& f) {
+    if (INL) fe_sq_inl(h, f);
+    else fe_sq(h, f);
+}
+template <bool INL = true>
 __device__ __forceinline__ fe coop_to_cached(const fe& mine, int r) {
     fe other = fe_shfl_xor1(mine);           // lanes 0/1 swap X and Y
     fe d, s, t, z2;
     fe_sub(d, r == 0 ? other : mine, r == 0 ? mine : other);   // lane 0: Y - X
     fe_add(s, mine, other);                                    // lane 1: Y + X
     fe_add(z2, mine, mine);                                    // lane 2: 2 Z
-    fe_mul_school(t, mine, fe_2d());                           // lane 3: 2d T
+    coop_mul<INL>(t, mine, fe_2d());                           // lane 3: 2d T
     return r == 0 ? d : (r == 1 ? s : (r == 2 ? z2 : t));
 }
 // P (distributed) += Q (distributed cached, from coop_to_cached): two rounds of one multiplication per lane
+template <bool INL = true>
 __device__ __forceinline__ fe coop_add(const fe& mine, const fe& qc, int r) {
     fe other = fe_shfl_xor1(mine);
     fe a, d, s;
@@ -65,7 +77,7 @@ __device__ __forceinline__ fe coop_add(const fe& mine, const fe& qc, int r) {
     fe_add(s, mine, other);                                    // lane 1: Y1 + X1
     a = r == 0 ? d : (r == 1 ? s : mine);                      // lane 2: Z1, lane 3: T1
     fe prod;
-    fe_mul_school(prod, a, qc);                                // lane 0: A, lane 1: B, lane 2: D = 2 Z1 Z2, lane 3: C = 2d T1 T2
+    coop_mul<INL>(prod, a, qc);                                // lane 0: A, lane 1: B, lane 2: D = 2 Z1 Z2, lane 3: C = 2d T1 T2
     fe A = fe_shfl4(prod, 0), B = fe_shfl4(prod, 1), D = fe_shfl4(prod, 2), C = fe_shfl4(prod, 3);
     fe E, F, G, H;
     fe_sub(E, B, A);
@@ -76,17 +88,18 @@ __device__ __forceinline__ fe coop_add(const fe& mine, const fe& qc, int r) {
     fe u = (r == 0 || r == 3) ? E : (r == 1 ? G : F);
     fe v = (r == 0) ? F : ((r == 1 || r == 3) ? H : G);
     fe out;
-    fe_mul_school(out, u, v);
+    coop_mul<INL>(out, u, v);
     return out;
 }
 // P (distributed) = 2 P: one squaring + one multiplication per lane
+template <bool INL = true>
 __device__ __forceinline__ fe coop_dbl(const fe& mine, int r) {
     fe X = fe_shfl4(mine, 0), Y = fe_shfl4(mine, 1);
     fe xy;
     fe_add(xy, X, Y);
     fe in = r == 3 ? xy : mine;                                // lane 3 squares X + Y instead of T
     fe sq;
-    fe_sq_inl(sq, in);
+    coop_sq<INL>(sq, in);
     fe xx = fe_shfl4(sq, 0), yy = fe_shfl4(sq, 1), zz = fe_shfl4(sq, 2), s = fe_shfl4(sq, 3);
     fe cx, cy, cz, ct, t;
     fe_add(cy, yy, xx);
@@ -98,7 +111,7 @@ __device__ __forceinline__ fe coop_dbl(const fe& mine, int r) {
     fe u = (r == 0 || r == 3) ? cx : (r == 1 ? cy : cz);
     fe v = (r == 0 || r == 2) ? ct : (r == 1 ? cz : cy);
     fe out;
-    fe_mul_school(out, u, v);
+    coop_mul<INL>(out, u, v);
     return out;
 }
 

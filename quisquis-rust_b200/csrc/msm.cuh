@@ -76,19 +76,29 @@ struct msm_geom {
     int c, K, NB;  // window bits, windows, buckets per window
 };
 
+// PRE = false: decompress the compressed points into `niels` (and ok into pre_ok-less status).
+// PRE = true : the points were decompressed earlier by k_msm_points_prepare (generator sets reused across MSMs);
+//              only the scalars are recoded.  `pre_ok[i]` is the validity recorded then.
+template <bool PRE>
 __global__ void __launch_bounds__(256) k_msm_prepare(const u32x4* __restrict__ points, const u32x4* __restrict__ scalars,
                                                      size_t n, msm_geom g, u32x4* __restrict__ niels,
+                                                     const uint8_t* __restrict__ pre_ok,
                                                      uint8_t* __restrict__ term_status, int16_t* __restrict__ digits,
                                                      unsigned int* __restrict__ counts) {
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        u32 w[8];
-        load_words32(w, points, i);
-        ge_p3 p;
-        u32 ok = ristretto_decompress(p, w);
-        ge_niels nl;
-        ge_to_niels_z1(nl, p);
-        niels_store_padded(niels + (size_t)QQ_NIELS_STRIDE_Q * i, nl);
+        u32 ok;
+        if (PRE) {
+            ok = pre_ok[i];
+        } else {
+            u32 w[8];
+            load_words32(w, points, i);
+            ge_p3 p;
+            ok = ristretto_decompress(p, w);
+            ge_niels nl;
+            ge_to_niels_z1(nl, p);
+            niels_store_padded(niels + (size_t)QQ_NIELS_STRIDE_Q * i, nl);
+        }
         u32 s[8];
         load_words32(s, scalars, i);
         u32 canon = sc_is_canonical(s);
@@ -101,6 +111,21 @@ __global__ void __launch_bounds__(256) k_msm_prepare(const u32x4* __restrict__ p
             digits[(size_t)k * n + i] = (int16_t)d;
             if (d != 0) atomicAdd(&counts[(size_t)k * g.NB + (size_t)((d < 0 ? -d : d) - 1)], 1u);
         }
+    }
+}
+// compressed points -> the MSM's point form (affine Niels, 96 B) + validity, once, for reuse
+__global__ void __launch_bounds__(256) k_msm_points_prepare(const u32x4* __restrict__ points, size_t n,
+                                                            u32x4* __restrict__ niels, uint8_t* __restrict__ ok_out) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        u32 w[8];
+        load_words32(w, points, i);
+        ge_p3 p;
+        u32 ok = ristretto_decompress(p, w);
+        ge_niels nl;
+        ge_to_niels_z1(nl, p);
+        niels_store_padded(niels + (size_t)QQ_NIELS_STRIDE_Q * i, nl);
+        ok_out[i] = (uint8_t)ok;
     }
 }
 
@@ -366,14 +391,15 @@ __global__ void __launch_bounds__(128) k_msm_combine(u32x4* __restrict__ partial
 //     T = sum_l S^l SW_l + R,   SW_l = sum_s W^l_s,   R = the single run left at the top.
 // No scalar multiplications by segment bases, and every level is data-parallel over (window, segment).
 #define QQ_MSM_RSEG 8
-// k_msm_reduce0, k_msm_window_totals and k_msm_horner are four-lane cooperative (ge_coop.cuh): group = 4 adjacent lanes.
+// k_msm_reduce0/_level, k_msm_window_totals and k_msm_horner are four-lane cooperative (ge_coop.cuh): group = 4 adjacent lanes.
 // One running-sum step: run += A_i; W += run   (skipped for i = 0).
+template <bool INL>
 __device__ __forceinline__ void coop_runsum_step(fe& run, fe& w, const fe& a, bool add_w, int r) {
-    fe ca = coop_to_cached(a, r);
-    run = coop_add(run, ca, r);
+    fe ca = coop_to_cached<INL>(a, r);
+    run = coop_add<INL>(run, ca, r);
     if (add_w) {
-        fe cr = coop_to_cached(run, r);
-        w = coop_add(w, cr, r);
+        fe cr = coop_to_cached<INL>(run, r);
+        w = coop_add<INL>(w, cr, r);
     }
 }
 // level 0: element (k, j) = bucket k * NB + j; after k_msm_combine its sum is the first of its partial sums
@@ -385,7 +411,7 @@ __global__ void __launch_bounds__(128) k_msm_reduce0(const u32x4* __restrict__ p
     int t = act ? gid : 0;
     int k = t / mout, s = t - k * mout;
     fe run = coop_identity(r), w = coop_identity(r);
-#pragma unroll
+#pragma unroll 1
     for (int i = QQ_MSM_RSEG - 1; i >= 0; i--) {
         int j = s * QQ_MSM_RSEG + i;
         fe a = coop_identity(r);
@@ -393,40 +419,35 @@ __global__ void __launch_bounds__(128) k_msm_reduce0(const u32x4* __restrict__ p
             size_t b = (size_t)k * g.NB + j;
             if (nsub[b] != 0) a = coop_load(partial + QQ_PT_Q * (size_t)voff[b], r);
         }
-        coop_runsum_step(run, w, a, i > 0, r);
+        coop_runsum_step<true>(run, w, a, i > 0, r);
     }
     if (act) {
         coop_store(run_out + QQ_PT_Q * (size_t)t, r, run);
         coop_store(w_out + QQ_PT_Q * (size_t)t, r, w);
     }
 }
-// level >= 1: in[k][0..m) -> run_out[k][0..mout), w_out[k][0..mout),  mout = ceil(m / S).  One thread per segment:
-// measured faster than the four-lane form here (55 us vs 70 us per level at K = 16, m = 4096; profiles/).
+// level >= 1: in[k][0..m) -> run_out[k][0..mout), w_out[k][0..mout),  mout = ceil(m / S).  Four lanes per segment,
+// out-of-line field products and a rolled loop: these launches are pure latency (a few thousand threads), and the
+// unrolled, inlined form spends its time fetching instructions (64-77 us per level against 30 us here; one thread per
+// segment: 55 us).
 __global__ void __launch_bounds__(128) k_msm_reduce_level(const u32x4* __restrict__ in, int K, int m, int mout,
-                                                          u32x4* __restrict__ run_out, u32x4* __restrict__ w_out) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= K * mout) return;
+                                                               u32x4* __restrict__ run_out, u32x4* __restrict__ w_out) {
+    int gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 2, r = threadIdx.x & 3;
+    bool act = gid < K * mout;
+    int t = act ? gid : 0;
     int k = t / mout, s = t - k * mout;
-    ge_p3 run, w;
-    ge_identity(run);
-    ge_identity(w);
+    fe run = coop_identity(r), w = coop_identity(r);
+#pragma unroll 1
     for (int i = QQ_MSM_RSEG - 1; i >= 0; i--) {
         int j = s * QQ_MSM_RSEG + i;
-        if (j < m) {
-            ge_p3 p;
-            ge_p3_load(p, in + QQ_PT_Q * ((size_t)k * m + j));
-            ge_cached c;
-            ge_to_cached(c, p);
-            ge_add(run, run, c);
-        }
-        if (i > 0) {
-            ge_cached c;
-            ge_to_cached(c, run);
-            ge_add(w, w, c);
-        }
+        fe a = coop_identity(r);
+        if (j < m) a = coop_load(in + QQ_PT_Q * ((size_t)k * m + j), r);
+        coop_runsum_step<false>(run, w, a, i > 0, r);
     }
-    ge_p3_store(run_out + QQ_PT_Q * (size_t)t, run);
-    ge_p3_store(w_out + QQ_PT_Q * (size_t)t, w);
+    if (act) {
+        coop_store(run_out + QQ_PT_Q * (size_t)t, r, run);
+        coop_store(w_out + QQ_PT_Q * (size_t)t, r, w);
+    }
 }
 // SW_l for every (level, window): block (l, k) sums row k of level l's W array (w_all + off[l], rows of len[l] points)
 #define QQ_MSM_MAXLEVELS 8
@@ -435,9 +456,9 @@ struct msm_levels {
     int len[QQ_MSM_MAXLEVELS];
     unsigned int off[QQ_MSM_MAXLEVELS];
 };
-__global__ void __launch_bounds__(128) k_msm_sum_levels(const u32x4* __restrict__ w_all, msm_levels lv, int K,
+__global__ void __launch_bounds__(512) k_msm_sum_levels(const u32x4* __restrict__ w_all, msm_levels lv, int K,
                                                         u32x4* __restrict__ sw) {
-    __shared__ u32x4 sm[128 * QQ_PT_Q];
+    extern __shared__ __align__(16) u32x4 sm[];   // blockDim.x points
     int l = blockIdx.x / K, k = blockIdx.x - l * K;
     int row_len = lv.len[l];
     const u32x4* row = w_all + QQ_PT_Q * ((size_t)lv.off[l] + (size_t)k * row_len);

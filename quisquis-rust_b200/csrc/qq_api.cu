@@ -403,6 +403,7 @@ extern "C" int qq_init(qq_ctx** out, int device) {
     auto body = [&]() -> int {
         CK(cudaSetDevice(device));
         CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        CK(cudaFuncSetAttribute(k_msm_sum_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * QQ_PT_BYTES));
         CK(cudaFuncSetAttribute(k_fixedbase<QQ_FB_W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(fb_table_words() * 4)));
         int occ = 0;
@@ -785,8 +786,9 @@ static int core_fixed_base(qq_ctx* ctx, int which, const uint8_t* s, uint8_t* ou
 
 // ---- MSM ----------------------------------------------------------------------------------------------------------
 // result: extended point (device, 128 B) = sum s_i * P_i ; *dstatus (device byte) = 0 / 1 / 2
+struct qq_prepared;
 static int core_msm_to_point(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, u32x4* result,
-                             uint8_t* dstatus);
+                             uint8_t* dstatus, const qq_prepared* pre = nullptr);
 
 static int core_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* points, const uint32_t* offsets, size_t m,
                           size_t nterms, uint8_t* out, uint8_t* status) {

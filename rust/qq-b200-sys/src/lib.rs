@@ -7,6 +7,11 @@ pub struct QqCtx {
     _private: [u8; 0],
 }
 
+#[repr(C)]
+pub struct QqPrepared {
+    _private: [u8; 0],
+}
+
 extern "C" {
     pub fn qq_init(ctx: *mut *mut QqCtx, device: c_int) -> c_int;
     pub fn qq_destroy(ctx: *mut QqCtx);
@@ -25,6 +30,10 @@ extern "C" {
     pub fn qq_fixed_base_window(ctx: *const QqCtx, which: c_int) -> c_int;
     pub fn qq_msm(ctx: *mut QqCtx, scalars: *const u8, points: *const u8, n: usize, out: *mut u8, status: *mut u8) -> c_int;
     pub fn qq_msm_partial(ctx: *mut QqCtx, scalars: *const u8, points: *const u8, n: usize, out_xyzt: *mut u8, status: *mut u8) -> c_int;
+    pub fn qq_msm_points_prepare(ctx: *mut QqCtx, points: *const u8, n: usize, out: *mut *mut QqPrepared) -> c_int;
+    pub fn qq_msm_points_free(ctx: *mut QqCtx, p: *mut QqPrepared);
+    pub fn qq_msm_points_count(p: *const QqPrepared) -> usize;
+    pub fn qq_msm_prepared(ctx: *mut QqCtx, scalars: *const u8, points: *const QqPrepared, n: usize, out: *mut u8, status: *mut u8) -> c_int;
     pub fn qq_points_sum(ctx: *mut QqCtx, xyzt: *const u8, k: usize, out: *mut u8, is_identity: *mut u8) -> c_int;
     pub fn qq_msm_segmented(ctx: *mut QqCtx, scalars: *const u8, points: *const u8, offsets: *const u32, m: usize, out: *mut u8, status: *mut u8) -> c_int;
 }

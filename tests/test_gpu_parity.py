@@ -490,3 +490,58 @@ def test_fixed_base_large_window_tables(engine, W):
     finally:
         for which in (0, 1):
             engine.fixed_base_set_window(which, old[which])
+
+
+def test_msm_over_prepared_points(engine):
+    # qq_msm_points_prepare + qq_msm_prepared: same bytes as qq_msm / the C oracle on the same (scalar, point) pairs,
+    # for prefixes of the prepared set, including sizes below the Pippenger threshold and a set holding a bad point
+    import c_oracle as C
+    rng = np.random.default_rng(77)
+    n = 5000
+    pts, _ = engine.fixed_base(0, _rand_scalars(rng, n))
+    sc = _rand_scalars(rng, n)
+    sc[::5, 8:] = 0                                  # balances
+    sc[7] = 0
+    h = engine.msm_points_prepare(pts)
+    try:
+        for m in (1, 2, 9, 255, 256, 1000, n):
+            o, s = engine.msm_prepared(sc[:m], h)
+            eo, es = C.msm(sc[:m], pts[:m])
+            assert s == es == 0 and o.tobytes() == eo.tobytes(), m
+        o, s = engine.msm_prepared(sc[:0], h)
+        assert s == 0 and o.tobytes() == bytes(32)
+        sc2 = sc.copy()
+        sc2[3] = np.frombuffer(R.L.to_bytes(32, "little"), np.uint8)
+        o, s = engine.msm_prepared(sc2, h)
+        assert s == 2 and o.tobytes() == bytes(32)
+    finally:
+        engine.msm_points_free(h)
+    pts2 = pts.copy()
+    pts2[1234] = np.frombuffer(invalid_encodings()[0][1], np.uint8)
+    h2 = engine.msm_points_prepare(pts2)
+    try:
+        o, s = engine.msm_prepared(sc[:1000], h2)      # prefix that does not touch the bad point
+        eo, es = C.msm(sc[:1000], pts2[:1000])
+        assert s == es == 0 and o.tobytes() == eo.tobytes()
+        o, s = engine.msm_prepared(sc, h2)
+        assert s == 1 and o.tobytes() == bytes(32)
+    finally:
+        engine.msm_points_free(h2)
+
+
+def test_msm_skewed_scalar_distributions(engine):
+    # virtual buckets: every scalar a 64-bit balance (upper windows empty), and a two-valued scalar set
+    import c_oracle as C
+    rng = np.random.default_rng(78)
+    n = 30000
+    pts, _ = engine.fixed_base(0, _rand_scalars(rng, n))
+    sc = _rand_scalars(rng, n)
+    sc[:, 8:] = 0
+    o, s = engine.msm(sc, pts)
+    eo, es = C.msm(sc, pts)
+    assert s == es == 0 and o.tobytes() == eo.tobytes()
+    sc2 = np.tile(np.frombuffer(sb(R.L - 3), np.uint8), (n, 1)).copy()
+    sc2[::3] = np.frombuffer(sb(12345678901234567890), np.uint8)
+    o, s = engine.msm(sc2, pts)
+    eo, es = C.msm(sc2, pts)
+    assert s == es == 0 and o.tobytes() == eo.tobytes()
