@@ -318,6 +318,25 @@ def run_b200(args):
         msm = {"points": m, "ms": msm_ms, "points_per_sec_per_gpu": m / (msm_ms * 1e-3),
                "breakdown_ms": bdm, "matches_known_dlog": msm_ok,
                "imad_frac": m * IMAD_PER_MSM_POINT / (msm_ms * 1e-3) / peak["imad_lo_per_s"]}
+        # ---- the same MSM over a point set decompressed once (Bulletproofs generators are fixed and cacheable) --------
+        hprep = ctypes.c_void_p()
+        eng._ck(eng.lib.qq_msm_points_prepare_dev(eng.h, vp(pts_d.data_ptr()), ctypes.c_size_t(m), ctypes.byref(hprep)),
+                "qq_msm_points_prepare_dev")
+        for _ in range(2):
+            eng.call_dev("qq_msm_prepared_dev", vp(a_d.data_ptr()), hprep, ctypes.c_size_t(m), vp(small.data_ptr() + 128),
+                         vp(small.data_ptr() + 192))
+        eng.event_record(4)
+        for _ in range(reps):
+            eng.call_dev("qq_msm_prepared_dev", vp(a_d.data_ptr()), hprep, ctypes.c_size_t(m), vp(small.data_ptr() + 128),
+                         vp(small.data_ptr() + 192))
+        eng.event_record(5)
+        prep_ms = eng.event_elapsed_ms(4, 5) / reps
+        res2 = small.cpu().numpy()
+        eng.lib.qq_msm_points_free(eng.h, hprep)
+        msm["prepared_points"] = {"ms": prep_ms, "points_per_sec_per_gpu": m / (prep_ms * 1e-3),
+                                  "same_result": bool((res2[128:160] == res[:32]).all()) and int(res2[192]) == 0,
+                                  "imad_frac": m * 16_128 / (prep_ms * 1e-3) / peak["imad_lo_per_s"],
+                                  "note": "points decompressed once with qq_msm_points_prepare (not timed), 16 128 IMAD units per point"}
         # ---- ONE MSM of world x m points sharded over the ranks: Pippenger on the local slice, 128-byte partial sums
         # all-gathered over NCCL, the ranks' points added on every rank (quisquis-rust_b200/distributed.py)
         if world > 1:

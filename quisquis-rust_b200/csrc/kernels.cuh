@@ -402,7 +402,8 @@ struct straus_args {
     const u32x4* scalars;
     const uint32_t* offsets;   // m + 1
     const uint8_t* term_status;
-    u32x4* out;                // m compressed points
+    u32x4* out;                // m compressed points (classic encoder), unused when half_out != nullptr
+    u32x4* half_out;           // m extended points = sum (s_i / 2) P_i, for the double-and-compress batch encoder
     uint8_t* status;           // m
     u32x4* scratch;
     const unsigned int* order; // instances sorted by term count (descending) so a warp's lanes do equal work
@@ -431,6 +432,7 @@ __global__ void __launch_bounds__(128, 2) k_straus(straus_args a) {
                 vb_build_table(tb, p);
                 u32 s[8], rr[9];
                 load_words32(s, a.scalars, c0 + t);
+                if (a.half_out != nullptr) sc_halve(s, s);
                 sc_recode_bias<4, 64>(rr, s);
                 store_words32(tb + QQ_STRAUS_TABLE_Q, 0, rr);
                 uint8_t ts = a.term_status[c0 + t];
@@ -463,6 +465,11 @@ __global__ void __launch_bounds__(128, 2) k_straus(straus_args a) {
             ge_to_cached(cr, r);
             ge_add(total, total, cr);
         }
+        a.status[j] = st;
+        if (a.half_out != nullptr) {
+            ge_p3_store(a.half_out + QQ_PT_Q * j, total);
+            continue;
+        }
         u32 wds[8];
         ristretto_compress(wds, total);
         if (st) {
@@ -470,7 +477,6 @@ __global__ void __launch_bounds__(128, 2) k_straus(straus_args a) {
             for (int i = 0; i < 8; i++) wds[i] = 0;
         }
         store_words32(a.out, j, wds);
-        a.status[j] = st;
     }
 }
 

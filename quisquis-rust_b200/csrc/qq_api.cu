@@ -799,7 +799,7 @@ static int core_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* po
     if (grid > (size_t)ctx->sms * occ) grid = (size_t)ctx->sms * occ;
     size_t scratch_bytes = grid * 128 * (size_t)QQ_STRAUS_KMAX * QQ_STRAUS_TERM_Q * 16;
     CKQ(ws_begin(ctx, ws_need({nterms * QQ_PT_BYTES, nterms, nterms, scratch_bytes, m * 4, m * 4, QQ_ORDER_BINS * 4, QQ_ORDER_BINS * 4,
-                               QQ_ORDER_BINS * 4, 4096 * 4})));
+                               QQ_ORDER_BINS * 4, 4096 * 4, m * QQ_PT_BYTES}) + dc_scratch_bytes(m)));
     unsigned int* counts = ws_take<unsigned int>(ctx, m * 4);
     unsigned int* order = ws_take<unsigned int>(ctx, m * 4);
     unsigned int* ohist = ws_take<unsigned int>(ctx, QQ_ORDER_BINS * 4);
@@ -810,6 +810,8 @@ static int core_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* po
     uint8_t* ok = ws_take<uint8_t>(ctx, nterms);
     uint8_t* tst = ws_take<uint8_t>(ctx, nterms);
     u32x4* scratch = ws_take<u32x4>(ctx, scratch_bytes);
+    u32x4* half = ws_take<u32x4>(ctx, m * QQ_PT_BYTES);
+    dc_ws dc = dc_take(ctx, m);
     CKQ(launch_decompress(ctx, points, IDENT, P, ok, nterms));
     CKQ(launch_status(ctx, scalars, nullptr, nullptr, ok, 1, tst, nterms));
     // order the instances by term count so that the 32 instances of a warp have (nearly) equal length
@@ -822,12 +824,14 @@ static int core_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* po
     ctx->launches += 6;
     straus_args a;
     a.pts = P; a.scalars = (const u32x4*)scalars; a.offsets = offsets; a.term_status = tst;
-    a.out = (u32x4*)out; a.status = status; a.scratch = scratch; a.order = order; a.m = m;
+    // every scalar of an instance is halved, the instance sum is encoded as enc(2 * sum) by the batch encoder
+    a.out = (u32x4*)out; a.half_out = half; a.status = status; a.scratch = scratch; a.order = order; a.m = m;
     span_begin(ctx, FAM_VB);
     k_straus<<<(unsigned)grid, 128, 0, ctx->stream>>>(a);
     span_end(ctx);
     ctx->launches++;
     CK(cudaGetLastError());
+    CKQ(launch_finish_dbl(ctx, dc, fsrc(half, IDENT), FNONE, FNONE, out, IDENT, status, 1, m));
     return QQ_OK;
 }
 

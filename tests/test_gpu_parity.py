@@ -545,3 +545,27 @@ def test_msm_skewed_scalar_distributions(engine):
     o, s = engine.msm(sc2, pts)
     eo, es = C.msm(sc2, pts)
     assert s == es == 0 and o.tobytes() == eo.tobytes()
+
+
+def test_shuffle_proof_msm_job_list_64_proofs(engine):
+    # BASELINE.json configs[2] workload shape: per proof 46 small MSMs of 2-9 terms; every MSM output of
+    # a 64-proof batch byte-equal to the C oracle (the Straus kernel + batch encoder path of qq_msm_segmented)
+    import c_oracle as C
+    jobs = [4] * 12 + [2] * 6 + [2] * 2 + [3] * 3 + [3] + [6] * 6 + [7] + [9] * 6 + [2] + [3] + [4] * 3
+    ks = np.array(jobs * 64, dtype=np.uint32)
+    offs = np.zeros(ks.size + 1, np.uint32)
+    offs[1:] = np.cumsum(ks)
+    nt = int(offs[-1])
+    rng = np.random.default_rng(64)
+    pts, _ = engine.fixed_base(0, _rand_scalars(rng, nt))
+    sc = _rand_scalars(rng, nt)
+    sc[::7, 8:] = 0
+    # one instance whose terms cancel (identity result), one with a zero scalar
+    sc[offs[5]:offs[5] + 2] = np.frombuffer(sb(5), np.uint8)
+    pts[offs[5] + 1] = np.frombuffer(R.compress(R.neg(R.decompress(pts[offs[5]].tobytes()))), np.uint8)
+    sc[offs[5] + 2:offs[6]] = 0
+    out, st = engine.msm_segmented(sc, pts, offs)
+    eo, es = C.msm_segmented(sc, pts, offs)
+    assert (st == es).all() and not st.any()
+    assert (out == eo).all()
+    assert out[5].tobytes() == bytes(32)
