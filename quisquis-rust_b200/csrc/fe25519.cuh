@@ -277,6 +277,44 @@ static __device__ __noinline__ fe fe_sqn_ool(fe f, int n) {
     return f;
 }
 #endif
+#if defined(__CUDACC__) && !defined(QQ_INLINE_FIELD_OPS)
+// Several INDEPENDENT products per out-of-line call.  The group law offers them in fours (addition: 4 + 4 products,
+// doubling: 4 squarings + 3..4 products); inside one function body ptxas interleaves the four carry chains, and the
+// call marshalling is paid once per group of products.  Measured in k_varbase_split: 5.17e7 -> 5.48e7 scalar-mults/s
+// against one product per call (tools/vb_bench.cu, profiles/).  Arguments and results travel in registers.
+struct fe2 {
+    fe a, b;
+};
+struct fe3 {
+    fe a, b, c;
+};
+struct fe4 {
+    fe a, b, c, d;
+};
+static __device__ __noinline__ fe3 fe_mul3_ool(fe f0, fe g0, fe f1, fe g1, fe f2, fe g2) {
+    fe3 r;
+    fe_mul_school(r.a, f0, g0);
+    fe_mul_school(r.b, f1, g1);
+    fe_mul_school(r.c, f2, g2);
+    return r;
+}
+static __device__ __noinline__ fe4 fe_mul4_ool(fe f0, fe g0, fe f1, fe g1, fe f2, fe g2, fe f3, fe g3) {
+    fe4 r;
+    fe_mul_school(r.a, f0, g0);
+    fe_mul_school(r.b, f1, g1);
+    fe_mul_school(r.c, f2, g2);
+    fe_mul_school(r.d, f3, g3);
+    return r;
+}
+static __device__ __noinline__ fe4 fe_sq4_ool(fe f0, fe f1, fe f2, fe f3) {
+    fe4 r;
+    fe_sq_inl(r.a, f0);
+    fe_sq_inl(r.b, f1);
+    fe_sq_inl(r.c, f2);
+    fe_sq_inl(r.d, f3);
+    return r;
+}
+#endif
 QQ_HD void fe_mul(fe& h, const fe& f, const fe& g) {
 #if defined(__CUDA_ARCH__) && !defined(QQ_INLINE_FIELD_OPS)
     h = fe_mul_ool(f, g);

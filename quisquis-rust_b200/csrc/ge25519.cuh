@@ -106,15 +106,20 @@ QQ_HD void ge_add_t(ge_p3& r, const ge_p3& p, const ge_cached& q) {
     fe_mul_t<INL>(r.Z, f, g);
     fe_mul_t<INL>(r.T, e, h);
 }
-#if defined(__CUDA_ARCH__) && defined(QQ_GE_OOL)
-// Group-level out-of-line variant (experiment, tools/vb_bench.cu): one call per group operation with the field products
-// inlined inside, instead of one call per field product.
-static __device__ __noinline__ ge_p3 ge_add_oolf(ge_p3 p, ge_cached q) {
-    ge_p3 r;
-    ge_add_t<true>(r, p, q);
-    return r;
+#if defined(__CUDA_ARCH__) && !defined(QQ_INLINE_FIELD_OPS) && !defined(QQ_FE_SINGLE)
+// device build: the two rounds of four independent products go through fe_mul4_ool (fe25519.cuh)
+QQ_HD void ge_add(ge_p3& r, const ge_p3& p, const ge_cached& q) {
+    fe e, f, g, h, t, u;
+    fe_sub(t, p.Y, p.X);
+    fe_add(u, p.Y, p.X);
+    fe4 m = fe_mul4_ool(t, q.YmX, u, q.YpX, p.T, q.T2d, p.Z, q.Z2);
+    fe_sub(e, m.b, m.a);
+    fe_sub(f, m.d, m.c);
+    fe_add(g, m.d, m.c);
+    fe_add(h, m.b, m.a);
+    fe4 o = fe_mul4_ool(f, e, g, h, f, g, e, h);
+    r.X = o.a; r.Y = o.b; r.Z = o.c; r.T = o.d;
 }
-QQ_HD void ge_add(ge_p3& r, const ge_p3& p, const ge_cached& q) { r = ge_add_oolf(p, q); }
 #else
 QQ_HD void ge_add(ge_p3& r, const ge_p3& p, const ge_cached& q) { ge_add_t<false>(r, p, q); }
 #endif
@@ -137,7 +142,23 @@ QQ_HD void ge_madd_t(ge_p3& r, const ge_p3& p, const ge_niels& q) {
     fe_mul_t<INL>(r.Z, f, g);
     fe_mul_t<INL>(r.T, e, h);
 }
+#if defined(__CUDA_ARCH__) && !defined(QQ_INLINE_FIELD_OPS) && !defined(QQ_FE_SINGLE)
+QQ_HD void ge_madd(ge_p3& r, const ge_p3& p, const ge_niels& q) {
+    fe d, e, f, g, h, t, u;
+    fe_sub(t, p.Y, p.X);
+    fe_add(u, p.Y, p.X);
+    fe3 m = fe_mul3_ool(t, q.ymx, u, q.ypx, p.T, q.xy2d);
+    fe_add(d, p.Z, p.Z);
+    fe_sub(e, m.b, m.a);
+    fe_sub(f, d, m.c);
+    fe_add(g, d, m.c);
+    fe_add(h, m.b, m.a);
+    fe4 o = fe_mul4_ool(f, e, g, h, f, g, e, h);
+    r.X = o.a; r.Y = o.b; r.Z = o.c; r.T = o.d;
+}
+#else
 QQ_HD void ge_madd(ge_p3& r, const ge_p3& p, const ge_niels& q) { ge_madd_t<false>(r, p, q); }
+#endif
 
 // r = 2p.  WITH_T = false skips T3 (4S + 3M) when the next operation is another doubling.  p.T is not read.
 template <bool WITH_T, bool INL>
@@ -158,32 +179,23 @@ QQ_HD void ge_dbl_t(ge_p3& r, const ge_p3& p) {
     fe_mul_t<INL>(r.Z, cz, ct);
     if (WITH_T) fe_mul_t<INL>(r.T, cx, cy);
 }
-#if defined(__CUDA_ARCH__) && defined(QQ_GE_OOL)
-struct ge_p2 {
-    fe X, Y, Z;
-};
-static __device__ __noinline__ ge_p3 ge_dbl_oolf_t(ge_p2 p) {
-    ge_p3 q, r;
-    q.X = p.X; q.Y = p.Y; q.Z = p.Z;
-    ge_dbl_t<true, true>(r, q);
-    return r;
-}
-static __device__ __noinline__ ge_p2 ge_dbl_oolf_not(ge_p2 p) {
-    ge_p3 q, r;
-    q.X = p.X; q.Y = p.Y; q.Z = p.Z;
-    ge_dbl_t<false, true>(r, q);
-    ge_p2 o;
-    o.X = r.X; o.Y = r.Y; o.Z = r.Z;
-    return o;
-}
+#if defined(__CUDA_ARCH__) && !defined(QQ_INLINE_FIELD_OPS) && !defined(QQ_FE_SINGLE)
 template <bool WITH_T>
 QQ_HD void ge_dbl(ge_p3& r, const ge_p3& p) {
-    ge_p2 q;
-    q.X = p.X; q.Y = p.Y; q.Z = p.Z;
-    if (WITH_T) r = ge_dbl_oolf_t(q);
-    else {
-        ge_p2 o = ge_dbl_oolf_not(q);
-        r.X = o.X; r.Y = o.Y; r.Z = o.Z;
+    fe cx, cy, cz, ct, t;
+    fe_add(t, p.X, p.Y);
+    fe4 q = fe_sq4_ool(p.X, p.Y, p.Z, t);
+    fe_add(cy, q.b, q.a);
+    fe_sub(cz, q.b, q.a);
+    fe_sub(cx, q.d, cy);
+    fe_add(t, q.c, q.c);
+    fe_sub(ct, t, cz);              // 2ZZ - (YY - XX)
+    if (WITH_T) {
+        fe4 o = fe_mul4_ool(cx, ct, cy, cz, cz, ct, cx, cy);
+        r.X = o.a; r.Y = o.b; r.Z = o.c; r.T = o.d;
+    } else {
+        fe3 o = fe_mul3_ool(cx, ct, cy, cz, cz, ct);
+        r.X = o.a; r.Y = o.b; r.Z = o.c;
     }
 }
 #else

@@ -66,14 +66,25 @@ struct vb_args {
     u32x4* scratch;
     size_t n;
 };
-// 2 blocks/SM (<= 255 regs) measured faster than 3 or 4 (tools/vb_bench.cu): the kernel is FMA-pipe bound, not
-// latency bound, and a tighter register cap only adds moves.
+// One 512-thread block per SM, all of whose warps are kept at the same code position by a barrier per item.
+// The loop body of a scalar multiplication is ~60 KB of SASS, far beyond the per-scheduler instruction cache; warps that
+// drift apart (they do, through table-load latency) each fetch their own copy of it and the kernel stalls on
+// instruction fetch: ncu `no_instruction` 3 % at 7 items per thread, 13 % at 55, with the multiply pipe dropping from
+// 78 % to 71 % active.  With the barrier the rate is independent of the batch size: 5.06e7 -> 6.18e7 scalar-mults/s at
+// 2^21 points (tools/vb_bench.cu, profiles/vb_bench_sync_r01.jsonl).  Every thread runs the same number of rounds;
+// threads past the end redo the last item and do not store.
+#define QQ_VB_BLOCK 512
 template <int NS>
-__global__ void __launch_bounds__(128, 4) k_varbase(vb_args a) {
+__global__ void __launch_bounds__(QQ_VB_BLOCK, 1) k_varbase(vb_args a) {
     size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     u32x4* tbl = a.scratch + gtid * (QQ_VB_ENTRIES * QQ_PT_Q);
-    for (size_t t = gtid; t < a.n; t += stride) {
+    size_t rounds = (a.n + stride - 1) / stride;
+    for (size_t it = 0; it < rounds; it++) {
+        size_t t = gtid + it * stride;
+        bool live = t < a.n;
+        if (!live) t = a.n - 1;
+        __syncthreads();
         ge_p3 p, r;
         ge_p3_load(p, a.pts + QQ_PT_Q * map_index(a.map, t));
         vb_build_table(tbl, p);
@@ -81,23 +92,28 @@ __global__ void __launch_bounds__(128, 4) k_varbase(vb_args a) {
         load_words32(s, a.s0, t / (size_t)a.sdiv);
         if (a.halve0) sc_halve(s, s);
         vb_scalarmult(r, tbl, s);
-        ge_p3_store(a.out0 + QQ_PT_Q * t, r);
+        if (live) ge_p3_store(a.out0 + QQ_PT_Q * t, r);
         if (NS == 2) {
             load_words32(s, a.s1, t / (size_t)a.sdiv);
             if (a.halve1) sc_halve(s, s);
             vb_scalarmult(r, tbl, s);
-            ge_p3_store(a.out1 + QQ_PT_Q * t, r);
+            if (live) ge_p3_store(a.out1 + QQ_PT_Q * t, r);
         }
     }
 }
 
 // Two scalars per point through the split tables (vbs_*): 312 doublings per point instead of 504.  The four tables of
 // a thread (4.6 KB) are written once and read 128 times; they stream through L2.
-__global__ void __launch_bounds__(128, 4) k_varbase_split(vb_args a) {
+__global__ void __launch_bounds__(QQ_VB_BLOCK, 1) k_varbase_split(vb_args a) {
     size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     u32x4* tbl = a.scratch + gtid * QQ_VBS_TABLE_Q;
-    for (size_t t = gtid; t < a.n; t += stride) {
+    size_t rounds = (a.n + stride - 1) / stride;
+    for (size_t it = 0; it < rounds; it++) {
+        size_t t = gtid + it * stride;
+        bool live = t < a.n;
+        if (!live) t = a.n - 1;
+        __syncthreads();
         ge_p3 p, r;
         ge_p3_load(p, a.pts + QQ_PT_Q * map_index(a.map, t));
         vbs_build_tables(tbl, p);
@@ -105,11 +121,11 @@ __global__ void __launch_bounds__(128, 4) k_varbase_split(vb_args a) {
         load_words32(s, a.s0, t / (size_t)a.sdiv);
         if (a.halve0) sc_halve(s, s);
         vbs_scalarmult(r, tbl, s);
-        ge_p3_store(a.out0 + QQ_PT_Q * t, r);
+        if (live) ge_p3_store(a.out0 + QQ_PT_Q * t, r);
         load_words32(s, a.s1, t / (size_t)a.sdiv);
         if (a.halve1) sc_halve(s, s);
         vbs_scalarmult(r, tbl, s);
-        ge_p3_store(a.out1 + QQ_PT_Q * t, r);
+        if (live) ge_p3_store(a.out1 + QQ_PT_Q * t, r);
     }
 }
 
@@ -178,7 +194,7 @@ __device__ __forceinline__ void fin_eval(ge_p3& q, const fin_args& a, size_t t) 
         ge_add(q, q, c);
     }
 }
-__global__ void __launch_bounds__(256) k_finish_compress(fin_args a) {
+__global__ void __launch_bounds__(256, 2) k_finish_compress(fin_args a) {
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < a.n; t += stride) {
         ge_p3 q;
@@ -358,7 +374,7 @@ __global__ void k_point_import(const u32x4* xyzt, u32x4* pts, size_t k) {
     ge_p3_store(pts + QQ_PT_Q * t, p);
 }
 // segmented sum: instance j = sum of terms offsets[j]..offsets[j+1]-1, compressed; bad if any term flag set
-__global__ void __launch_bounds__(256) k_segment_sum_compress(const u32x4* __restrict__ terms,
+__global__ void __launch_bounds__(256, 2) k_segment_sum_compress(const u32x4* __restrict__ terms,
                                                               const uint32_t* __restrict__ offsets,
                                                               const uint8_t* __restrict__ term_status,
                                                               u32x4* __restrict__ out, uint8_t* __restrict__ status,
@@ -413,11 +429,16 @@ __global__ void k_seg_counts(const uint32_t* __restrict__ offsets, size_t m, uns
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) counts[j] = offsets[j + 1] - offsets[j];
 }
-__global__ void __launch_bounds__(128, 2) k_straus(straus_args a) {
+template <int BLOCK, int MINB, bool SYNC>
+__global__ void __launch_bounds__(BLOCK, MINB) k_straus(straus_args a) {
     size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     u32x4* slab = a.scratch + gtid * (size_t)(QQ_STRAUS_KMAX * QQ_STRAUS_TERM_Q);
-    for (size_t jj = gtid; jj < a.m; jj += stride) {
+    size_t rounds = (a.m + stride - 1) / stride;
+    for (size_t it = 0; it < rounds; it++) {
+        size_t jj = gtid + it * stride;
+        if (SYNC) __syncthreads();   // instances are ordered by term count: the warps of a block restart together
+        if (jj >= a.m) continue;
         size_t j = a.order[jj];
         uint32_t lo = a.offsets[j], hi = a.offsets[j + 1];
         ge_p3 total;

@@ -155,7 +155,7 @@ static int launch_decompress(qq_ctx* ctx, const void* in, idx_map map, u32x4* pt
     return QQ_OK;
 }
 static size_t vb_scratch_bytes(qq_ctx* ctx, int ns) {
-    return (size_t)ctx->sms * ctx->vb_blocks_per_sm[ns] * 128 * (ns == 2 ? QQ_VBS_TABLE_WORDS : QQ_VB_TABLE_WORDS) * 4;
+    return (size_t)ctx->sms * ctx->vb_blocks_per_sm[ns] * QQ_VB_BLOCK * (ns == 2 ? QQ_VBS_TABLE_WORDS : QQ_VB_TABLE_WORDS) * 4;
 }
 static int launch_varbase(qq_ctx* ctx, int ns, const u32x4* pts, idx_map map, const void* s0, const void* s1, int sdiv,
                           u32x4* out0, u32x4* out1, u32x4* scratch, size_t n, int halve0 = 0, int halve1 = 0) {
@@ -166,8 +166,9 @@ static int launch_varbase(qq_ctx* ctx, int ns, const u32x4* pts, idx_map map, co
     a.out0 = out0; a.out1 = out1; a.scratch = scratch; a.n = n;
     int grid = ctx->sms * ctx->vb_blocks_per_sm[ns];
     span_begin(ctx, FAM_VB);
-    if (ns == 1) k_varbase<1><<<grid, 128, 0, ctx->stream>>>(a);
-    else k_varbase_split<<<grid, 128, 0, ctx->stream>>>(a);
+    if ((size_t)grid * QQ_VB_BLOCK > n) grid = (int)((n + QQ_VB_BLOCK - 1) / QQ_VB_BLOCK);
+    if (ns == 1) k_varbase<1><<<grid, QQ_VB_BLOCK, 0, ctx->stream>>>(a);
+    else k_varbase_split<<<grid, QQ_VB_BLOCK, 0, ctx->stream>>>(a);
     span_end(ctx);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -178,7 +179,7 @@ static int launch_fixedbase(qq_ctx* ctx, int which, const void* s, u32x4* out, s
     if (n == 0) return QQ_OK;
     if (ctx->fbt[which] != nullptr && n >= QQ_FBT_MIN_BATCH) {
         span_begin(ctx, FAM_FB);
-        k_fixedbase_big<<<grid_for(n, 128, ctx->sms * 4), 128, 0, ctx->stream>>>(ctx->fbt[which], ctx->fbt_g[which],
+        k_fixedbase_big<<<grid_for(n, QQ_FBT_BLOCK, ctx->sms * 4), QQ_FBT_BLOCK, 0, ctx->stream>>>(ctx->fbt[which], ctx->fbt_g[which],
                                                                                 (const u32x4*)s, halve, out, n);
         span_end(ctx);
         ctx->launches++;
@@ -407,9 +408,9 @@ extern "C" int qq_init(qq_ctx** out, int device) {
         CK(cudaFuncSetAttribute(k_fixedbase<QQ_FB_W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(fb_table_words() * 4)));
         int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_varbase<1>, 128, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_varbase<1>, QQ_VB_BLOCK, 0));
         ctx->vb_blocks_per_sm[1] = occ > 0 ? occ : 1;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_varbase_split, 128, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_varbase_split, QQ_VB_BLOCK, 0));
         ctx->vb_blocks_per_sm[2] = occ > 0 ? occ : 1;
         // fixed-base tables for B and H, built on the device from their compressed encodings
         const uint8_t* BASE_PK = QQ_BASE_PK_BYTES;
@@ -764,7 +765,7 @@ static int core_fixed_base(qq_ctx* ctx, int which, const uint8_t* s, uint8_t* ou
         if (ctx->fbt[which] != nullptr && m >= QQ_FBT_MIN_BATCH) {
             // table walk fused with the first stage of the batch encoder: the extended point never goes to HBM
             span_begin(ctx, FAM_FB);
-            k_fixedbase_big_dc<<<grid_for(m, 128, ctx->sms * 4), 128, 0, ctx->stream>>>(
+            k_fixedbase_big_dc<<<grid_for(m, QQ_FBT_BLOCK, ctx->sms * 4), QQ_FBT_BLOCK, 0, ctx->stream>>>(
                 ctx->fbt[which], ctx->fbt_g[which], (const u32x4*)(s + base * 32), dc.state, dc.w, dc.zflag, m);
             span_end(ctx);
             ctx->launches++;
@@ -792,12 +793,15 @@ static int core_msm_to_point(qq_ctx* ctx, const uint8_t* scalars, const uint8_t*
 
 static int core_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* points, const uint32_t* offsets, size_t m,
                           size_t nterms, uint8_t* out, uint8_t* status) {
+    // 128-thread blocks, 2 per SM, no barrier: a batch holds only a few instances per thread, the lockstep forms of
+    // k_varbase (256 x 1, 512 x 1 with a barrier per instance) measured 0-5 % slower here
+    const int sblock = 128;
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_straus, 128, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_straus<128, 2, false>, 128, 0));
     if (occ < 1) occ = 1;
-    size_t grid = (m + 127) / 128;
+    size_t grid = (m + sblock - 1) / sblock;
     if (grid > (size_t)ctx->sms * occ) grid = (size_t)ctx->sms * occ;
-    size_t scratch_bytes = grid * 128 * (size_t)QQ_STRAUS_KMAX * QQ_STRAUS_TERM_Q * 16;
+    size_t scratch_bytes = grid * sblock * (size_t)QQ_STRAUS_KMAX * QQ_STRAUS_TERM_Q * 16;
     CKQ(ws_begin(ctx, ws_need({nterms * QQ_PT_BYTES, nterms, nterms, scratch_bytes, m * 4, m * 4, QQ_ORDER_BINS * 4, QQ_ORDER_BINS * 4,
                                QQ_ORDER_BINS * 4, 4096 * 4, m * QQ_PT_BYTES}) + dc_scratch_bytes(m)));
     unsigned int* counts = ws_take<unsigned int>(ctx, m * 4);
@@ -827,7 +831,7 @@ static int core_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* po
     // every scalar of an instance is halved, the instance sum is encoded as enc(2 * sum) by the batch encoder
     a.out = (u32x4*)out; a.half_out = half; a.status = status; a.scratch = scratch; a.order = order; a.m = m;
     span_begin(ctx, FAM_VB);
-    k_straus<<<(unsigned)grid, 128, 0, ctx->stream>>>(a);
+    k_straus<128, 2, false><<<(unsigned)grid, 128, 0, ctx->stream>>>(a);
     span_end(ctx);
     ctx->launches++;
     CK(cudaGetLastError());
