@@ -31,7 +31,7 @@ IMAD_PER_VARBASE = 289_000
 # what k_varbase_split actually executes per account (2 points x 2 scalars through 4 quarter tables, scalarmult.cuh):
 # 2 x (1248 S + 2253 M) with M = 144, S = 88 IMAD units -- 75 % of the 4 x 289 000 the cost model charges
 IMAD_EXECUTED_VARBASE_PER_ACCOUNT = 2 * (1248 * 88 + 2253 * 144)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 31.15e9
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 37.96e9
 IMAD_PER_FIXED_COMPRESSED = 91_400  # FIXED(4) + ENC
 IMAD_PER_MSM_POINT = 43_900        # compressed input, n = 2^20, c = 16
 BYTES_PER_UPDATE_ACCOUNT = 224 + 128 + 1
@@ -445,11 +445,11 @@ def run_b200(args):
                          "breakdown_ms_per_step": {k_: v_ / args.steps for k_, v_ in breakdown.items()},
                          # dram__bytes_read.sum + dram__bytes_write.sum of one k_varbase_split launch at 2^20 accounts, from
                          # the ncu --set full capture summarised in profiles/ncu_varbase_split_r01_summary.json (per-thread
-                         # window tables spilling past L2, 6 % of HBM bandwidth; the same capture shows the FMA-heavy
-                         # integer-multiply pipe active 81 % of elapsed cycles)
+                         # window tables spilling past L2, 8.5 % of HBM bandwidth; the same capture shows the FMA-heavy
+                         # integer-multiply pipe active 88.9 % of elapsed cycles)
                          "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH * (n / (1 << 20)),
                          "traffic_unit": "bytes per launch (ncu, 2^20-account launch, scaled linearly to this batch)",
-                         "ncu_fmaheavy_pipe_active_pct": 81.2,
+                         "ncu_fmaheavy_pipe_active_pct": 88.9,
                          "hbm": {"algorithmic_bytes_per_step": n * BYTES_PER_UPDATE_ACCOUNT,
                                  "achieved_GBps": n * BYTES_PER_UPDATE_ACCOUNT / (dev_ms / args.steps * 1e-3) / 1e9,
                                  "peak_GBps": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -479,8 +479,8 @@ def main():
     ap.add_argument("--accounts", type=int, default=1 << 20, help="accounts per GPU per step")
     ap.add_argument("--msm-points", type=int, default=1 << 20)
     ap.add_argument("--fixed-points", type=int, default=1 << 22, help="fixed-base batch per GPU (0 = skip)")
-    ap.add_argument("--fixed-window", type=int, default=24,
-                    help="also time the fixed-base batch with this table window (24 bits = 8.9 GB in HBM; 0 = default table only)")
+    ap.add_argument("--fixed-window", type=int, default=22,
+                    help="also time the fixed-base batch with this table window (22 bits = 2.4 GB in HBM; 0 = default table only)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-seconds-per-step", type=float, default=4.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

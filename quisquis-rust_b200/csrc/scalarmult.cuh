@@ -147,11 +147,15 @@ QQ_HD void vbs_build_tables(u32x4* tbl, const ge_p3& p) {
         vb_build_table(tbl + part * (QQ_VB_ENTRIES * QQ_PT_Q), q);
         if (part + 1 < QQ_VBS_PARTS) {
 #pragma unroll 1
+#if defined(QQ_VBS_ROLLED)
+            for (int i = 0; i < 64; i++) ge_dbl<true>(q, q);
+#else
             for (int i = 0; i < 63; i++) {
                 if ((i & 7) == 0) QQ_VBS_STEP_SYNC();
                 ge_dbl<false>(q, q);
             }
             ge_dbl<true>(q, q);
+#endif
         }
     }
 }
@@ -167,10 +171,19 @@ QQ_HD void vbs_scalarmult(ge_p3& r, const u32x4* tbl, const u32 s[8]) {
         for (int j = 7; j >= 0; j--) {
             QQ_VBS_STEP_SYNC();
             if (!(half == 1 && j == 7)) {
+#if defined(QQ_VBS_ROLLED)
+#pragma unroll 1
+                for (int d4 = 0; d4 < 4; d4++) ge_dbl<true>(r, r);
+#elif defined(QQ_VBS_ROLLED2)
+#pragma unroll 1
+                for (int d3 = 0; d3 < 3; d3++) ge_dbl<false>(r, r);
+                ge_dbl<true>(r, r);
+#else
                 ge_dbl<false>(r, r);
                 ge_dbl<false>(r, r);
                 ge_dbl<false>(r, r);
                 ge_dbl<true>(r, r);
+#endif
             }
 #pragma unroll 1
             for (int part = 0; part < QQ_VBS_PARTS; part++) {
