@@ -24,6 +24,9 @@ struct qq_ctx {
     int device = 0;
     int sms = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;   // upload / download streams of the pipelined host entry points
+    cudaEvent_t msm_ev[8] = {nullptr};
+    std::vector<cudaEvent_t> pipe_ev;
     char* ws = nullptr;
     size_t ws_cap = 0, ws_off = 0;
     char* io = nullptr;      // staging slab for the host-pointer entry points (grow-only)
@@ -404,6 +407,9 @@ extern "C" int qq_init(qq_ctx** out, int device) {
     auto body = [&]() -> int {
         CK(cudaSetDevice(device));
         CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 8; i++) CK(cudaEventCreateWithFlags(&ctx->msm_ev[i], cudaEventDisableTiming));
         CK(cudaFuncSetAttribute(k_msm_sum_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * QQ_PT_BYTES));
         CK(cudaFuncSetAttribute(k_fixedbase<QQ_FB_W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(fb_table_words() * 4)));
@@ -457,6 +463,11 @@ extern "C" void qq_destroy(qq_ctx* ctx) {
         if (ctx->fb_tbl[b]) cudaFree(ctx->fb_tbl[b]);
         if (ctx->fbt[b]) cudaFree(ctx->fbt[b]);
     }
+    for (int i = 0; i < 8; i++)
+        if (ctx->msm_ev[i]) cudaEventDestroy(ctx->msm_ev[i]);
+    for (auto e : ctx->pipe_ev) cudaEventDestroy(e);
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -983,22 +994,50 @@ extern "C" int qq_update_account_batch_dev(qq_ctx* ctx, const uint8_t* acc, cons
     CKQ(core_update_account(ctx, acc, bl, u, c, out_acc, status, n));
     return call_end(ctx);
 }
+// Host-pointer entry of the headline path.  The batch is cut into slices of QQ_PIPE_SLICE accounts; the upload of slice
+// i + 1 (copy stream) and the download of slice i - 1 (second copy stream) run under the kernels of slice i, so that with
+// pinned host memory only the first upload and the last download are exposed (352 bytes per account cross PCIe).
+#define QQ_PIPE_SLICE ((size_t)1 << 18)
 extern "C" int qq_update_account_batch(qq_ctx* ctx, const uint8_t* acc, const uint8_t* bl, const uint8_t* u,
                                        const uint8_t* c, uint8_t* out_acc, uint8_t* status, size_t n) {
     ENTER();
     REQUIRE(acc && bl && u && c && out_acc && status);
     stage st(ctx);
     CKQ(st.plan({(size_t)(n * 128), (size_t)(n * 32), (size_t)(n * 32), (size_t)(n * 32), (size_t)(n * 128), (size_t)(n)}));
-    uint8_t *dacc, *dbl, *du, *dc, *dout, *dst;
-    CKQ(st.in(acc, n * 128, &dacc));
-    CKQ(st.in(bl, n * 32, &dbl));
-    CKQ(st.in(u, n * 32, &du));
-    CKQ(st.in(c, n * 32, &dc));
-    CKQ(st.outbuf(n * 128, &dout));
-    CKQ(st.outbuf(n, &dst));
-    CKQ(core_update_account(ctx, dacc, dbl, du, dc, dout, dst, n));
-    CKQ(st.back(out_acc, dout, n * 128));
-    CKQ(st.back(status, dst, n));
+    uint8_t* dacc = st.take(n * 128);
+    uint8_t* dbl = st.take(n * 32);
+    uint8_t* du = st.take(n * 32);
+    uint8_t* dc = st.take(n * 32);
+    uint8_t* dout = st.take(n * 128);
+    uint8_t* dst = st.take(n);
+    size_t nsl = (n + QQ_PIPE_SLICE - 1) / QQ_PIPE_SLICE;
+    while (ctx->pipe_ev.size() < 2 * nsl) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->pipe_ev.push_back(e);
+    }
+    // the staging slab may still be read by the previous call's downloads: order the copy streams after the main stream
+    CK(cudaEventRecord(ctx->msm_ev[7], ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_in, ctx->msm_ev[7], 0));
+    for (size_t i = 0; i < nsl; i++) {
+        size_t lo = i * QQ_PIPE_SLICE, m = n - lo < QQ_PIPE_SLICE ? n - lo : QQ_PIPE_SLICE;
+        CK(cudaMemcpyAsync(dacc + lo * 128, acc + lo * 128, m * 128, cudaMemcpyHostToDevice, ctx->copy_in));
+        CK(cudaMemcpyAsync(dbl + lo * 32, bl + lo * 32, m * 32, cudaMemcpyHostToDevice, ctx->copy_in));
+        CK(cudaMemcpyAsync(du + lo * 32, u + lo * 32, m * 32, cudaMemcpyHostToDevice, ctx->copy_in));
+        CK(cudaMemcpyAsync(dc + lo * 32, c + lo * 32, m * 32, cudaMemcpyHostToDevice, ctx->copy_in));
+        CK(cudaEventRecord(ctx->pipe_ev[2 * i], ctx->copy_in));
+    }
+    for (size_t i = 0; i < nsl; i++) {
+        size_t lo = i * QQ_PIPE_SLICE, m = n - lo < QQ_PIPE_SLICE ? n - lo : QQ_PIPE_SLICE;
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->pipe_ev[2 * i], 0));
+        CKQ(core_update_account(ctx, dacc + lo * 128, dbl + lo * 32, du + lo * 32, dc + lo * 32, dout + lo * 128, dst + lo, m));
+        CK(cudaEventRecord(ctx->pipe_ev[2 * i + 1], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->copy_out, ctx->pipe_ev[2 * i + 1], 0));
+        CK(cudaMemcpyAsync(out_acc + lo * 128, dout + lo * 128, m * 128, cudaMemcpyDeviceToHost, ctx->copy_out));
+        CK(cudaMemcpyAsync(status + lo, dst + lo, m, cudaMemcpyDeviceToHost, ctx->copy_out));
+    }
+    CK(cudaEventRecord(ctx->msm_ev[6], ctx->copy_out));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->msm_ev[6], 0));   // call_end synchronises the main stream
     return call_end(ctx);
 }
 extern "C" int qq_verify_account_batch_dev(qq_ctx* ctx, const uint8_t* acc, const uint8_t* sk, const uint8_t* bl,
