@@ -175,6 +175,18 @@ int qq_points_sum(qq_ctx* ctx, const uint8_t* xyzt, size_t k, uint8_t* out_point
 int qq_msm_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* points, const uint32_t* offsets, size_t m,
                      uint8_t* out_points, uint8_t* status);
 
+/* ---- hash-to-group and generator derivation ---------------------------------------------------------------------
+ * RistrettoPoint::from_uniform_bytes over n blocks of 64 uniform bytes (the tail of hash_from_bytes::<Sha3_512>,
+ * src/pedersen/vectorpedersen.rs:49-51,66-70): out_i = enc(elligator(lo_i) + elligator(hi_i)). */
+int qq_from_uniform_bytes_batch(qq_ctx* ctx, const uint8_t* uniform64, uint8_t* out_points, size_t n);
+/* VectorPedersenGens::new(capacity) (src/pedersen/vectorpedersen.rs:45-75): out_h = H (32 B), out_g = G_vec
+ * ((capacity - 1) x 32 B: B followed by the SHA3-512 hash chain started at H).  capacity >= 2. */
+int qq_vector_pedersen_gens(qq_ctx* ctx, size_t capacity, uint8_t* out_h, uint8_t* out_g);
+/* bulletproofs::BulletproofGens::new(gens_capacity, party_capacity), rebuilt by the reference on every range-proof
+ * verification (src/accounts/verifier.rs:510,540): out_g, out_h = party_capacity x gens_capacity x 32 B, party-major.
+ * Feed them to qq_msm_points_prepare once and reuse the handle. */
+int qq_bulletproof_gens(qq_ctx* ctx, size_t gens_capacity, size_t party_capacity, uint8_t* out_g, uint8_t* out_h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -361,3 +361,30 @@ def delta_identity_check(accounts):
             return ST_BAD_POINT
         sc, sd = add(sc, c), add(sd, d)
     return ST_OK if is_identity(sc) and is_identity(sd) else ST_COMMIT
+
+
+# ---- generator derivation (reference src/pedersen/vectorpedersen.rs:45-75; bulletproofs generators.rs [upstream]) ----
+def hash_to_point_sha3_512(data):
+    """RistrettoPoint::hash_from_bytes::<Sha3_512>."""
+    return from_uniform_bytes(hashlib.sha3_512(data).digest())
+
+
+def vector_pedersen_gens(capacity):
+    """VectorPedersenGens::new(capacity) -> (H compressed, [G_vec compressed]); len(G_vec) = capacity - 1."""
+    h = hash_to_point_sha3_512(BASEPOINT_COMPRESSED)
+    others = [h]
+    for i in range(capacity - 2):
+        others.append(hash_to_point_sha3_512(compress(others[i])))
+    return compress(h), [BASEPOINT_COMPRESSED] + [compress(p) for p in others[1:]]
+
+
+def bulletproof_gens(gens_capacity, party_capacity):
+    """BulletproofGens::new: per party i the chains Shake256("GeneratorsChain" || b"G"/b"H" || LE32(i)), 64 bytes per point."""
+    out = {}
+    for tag in (b"G", b"H"):
+        rows = []
+        for i in range(party_capacity):
+            stream = hashlib.shake_256(b"GeneratorsChain" + tag + i.to_bytes(4, "little")).digest(64 * gens_capacity)
+            rows.append([compress(from_uniform_bytes(stream[64 * j:64 * j + 64])) for j in range(gens_capacity)])
+        out[tag] = rows
+    return out[b"G"], out[b"H"]

@@ -21,6 +21,7 @@ EXPORTS = [
     "qq_fixed_base_batch", "qq_fixed_base_batch_dev", "qq_fixed_base_set_window", "qq_fixed_base_window", "qq_msm", "qq_msm_dev", "qq_msm_partial", "qq_msm_partial_dev",
     "qq_points_sum", "qq_msm_segmented", "qq_msm_points_prepare", "qq_msm_points_prepare_dev", "qq_msm_points_free",
     "qq_msm_points_count", "qq_msm_prepared", "qq_msm_prepared_dev",
+    "qq_from_uniform_bytes_batch", "qq_vector_pedersen_gens", "qq_bulletproof_gens",
 ]
 
 
@@ -84,6 +85,9 @@ def load_library():
     lib.qq_points_sum.argtypes = [vp, u8p, sz, u8p, u8p]
     for name in ("qq_msm_points_prepare", "qq_msm_points_prepare_dev"):
         getattr(lib, name).argtypes = [vp, u8p, sz, ctypes.POINTER(vp)]
+    lib.qq_from_uniform_bytes_batch.argtypes = [vp, u8p, u8p, sz]
+    lib.qq_vector_pedersen_gens.argtypes = [vp, sz, u8p, u8p]
+    lib.qq_bulletproof_gens.argtypes = [vp, sz, sz, u8p, u8p]
     lib.qq_msm_points_free.argtypes = [vp, vp]
     lib.qq_msm_points_free.restype = None
     lib.qq_msm_points_count.argtypes = [vp]
@@ -306,6 +310,25 @@ class Engine:
         out, st = np.zeros(32, np.uint8), np.zeros(1, np.uint8)
         self._ck(self.lib.qq_msm_prepared(self.h, _ptr(scalars), handle, n, _ptr(out), _ptr(st)), "qq_msm_prepared")
         return out, int(st[0])
+
+    def from_uniform_bytes(self, uniform64):
+        u = _u8(uniform64)
+        n = u.size // 64
+        out = np.zeros(n * 32, np.uint8)
+        self._ck(self.lib.qq_from_uniform_bytes_batch(self.h, _ptr(u), _ptr(out), n), "qq_from_uniform_bytes_batch")
+        return out.reshape(n, 32)
+
+    def vector_pedersen_gens(self, capacity):
+        """(H, G_vec) of VectorPedersenGens::new(capacity): 32 bytes and (capacity - 1) x 32 bytes."""
+        h, g = np.zeros(32, np.uint8), np.zeros((capacity - 1) * 32, np.uint8)
+        self._ck(self.lib.qq_vector_pedersen_gens(self.h, capacity, _ptr(h), _ptr(g)), "qq_vector_pedersen_gens")
+        return h, g.reshape(capacity - 1, 32)
+
+    def bulletproof_gens(self, gens_capacity, party_capacity):
+        n = gens_capacity * party_capacity
+        g, h = np.zeros(n * 32, np.uint8), np.zeros(n * 32, np.uint8)
+        self._ck(self.lib.qq_bulletproof_gens(self.h, gens_capacity, party_capacity, _ptr(g), _ptr(h)), "qq_bulletproof_gens")
+        return g.reshape(party_capacity, gens_capacity, 32), h.reshape(party_capacity, gens_capacity, 32)
 
     def points_sum(self, xyzt):
         xyzt = _u8(xyzt)

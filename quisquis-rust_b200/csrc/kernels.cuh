@@ -220,6 +220,21 @@ __global__ void __launch_bounds__(256) k_points_equal(const u32x4* __restrict__ 
     }
 }
 
+// ---- hash-to-group tail: 64 uniform bytes -> compressed point (RistrettoPoint::from_uniform_bytes) ---------------------
+__global__ void __launch_bounds__(256, 2) k_from_uniform(const u32x4* __restrict__ in, u32x4* __restrict__ out, size_t n) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+        u32 w[16];
+        load_words32(w, in, 2 * t);
+        load_words32(w + 8, in, 2 * t + 1);
+        ge_p3 p;
+        ristretto_from_uniform(p, w);
+        u32 o[8];
+        ristretto_compress(o, p);
+        store_words32(out, t, o);
+    }
+}
+
 // ---- status assembly ---------------------------------------------------------------------------------------------
 // status[i] = BAD_SCALAR if any of the (up to 3) scalar arrays holds a non-canonical scalar at i,
 //             else BAD_POINT if any of the `npts` validity flags ok[i * npts + j] is 0, else 0.

@@ -13,6 +13,7 @@
 #include "msm.cuh"
 #include "compress_batch.cuh"
 #include "fixedbase_big.cuh"
+#include "keccak_host.hpp"
 
 using namespace qq;
 

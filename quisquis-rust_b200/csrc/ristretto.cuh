@@ -103,4 +103,53 @@ QQ_HD void ristretto_compress(u32 w[8], const ge_p3& p) {
     fe_towords(w, t);
 }
 
+// Elligator 2 map of RFC 9496 4.3.4 (dalek ristretto.rs elligator_ristretto_flavor): field element -> point.
+// Reached in the reference through RistrettoPoint::hash_from_bytes::<Sha3_512> (src/pedersen/vectorpedersen.rs:49-51,
+// 66-70) and through the Bulletproofs generator chains (src/accounts/verifier.rs:510,540).
+QQ_HD void ristretto_elligator(ge_p3& p, const fe& r0) {
+    fe r, ns, c, dd, t, u, s, sp, nt, w0, w1, w2, w3, one, ss;
+    fe_1(one);
+    fe_sq(t, r0);
+    fe_mul(r, t, fe_sqrt_m1());                 // r = i r0^2
+    fe_add(t, r, one);
+    fe_mul(ns, t, fe_one_minus_d_sq());         // (r + 1)(1 - d^2)
+    fe_neg(c, one);                             // c = -1
+    fe_mul(t, fe_d(), r);
+    fe_sub(t, c, t);                            // c - d r
+    fe_add(u, r, fe_d());
+    fe_mul(dd, t, u);                           // (c - d r)(r + d)
+    u32 was_square = fe_sqrt_ratio_i(s, ns, dd);
+    fe_mul(sp, s, r0);
+    fe_abs(sp);
+    fe_neg(sp, sp);                             // s' = -|s r0|
+    fe_cmov(s, sp, was_square ^ 1u);
+    fe_cmov(c, r, was_square ^ 1u);
+    fe_sub(t, r, one);
+    fe_mul(t, c, t);
+    fe_mul(t, t, fe_d_minus_one_sq());
+    fe_sub(nt, t, dd);                          // c (r - 1)(d - 1)^2 - D
+    fe_sq(ss, s);
+    fe_add(t, s, s);
+    fe_mul(w0, t, dd);                          // 2 s D
+    fe_mul(w1, nt, fe_sqrt_ad_minus_one());
+    fe_sub(w2, one, ss);
+    fe_add(w3, one, ss);
+    fe_mul(p.X, w0, w3);
+    fe_mul(p.Y, w2, w1);
+    fe_mul(p.Z, w1, w3);
+    fe_mul(p.T, w0, w2);
+}
+// RistrettoPoint::from_uniform_bytes: 64 bytes (16 words) -> elligator(lo) + elligator(hi); bit 255 of each half ignored
+QQ_HD void ristretto_from_uniform(ge_p3& p, const u32 w[16]) {
+    fe r0, r1;
+    fe_fromwords(r0, w);
+    fe_fromwords(r1, w + 8);
+    ge_p3 a, b;
+    ristretto_elligator(a, r0);
+    ristretto_elligator(b, r1);
+    ge_cached cb;
+    ge_to_cached(cb, b);
+    ge_add(p, a, cb);
+}
+
 }  // namespace qq

@@ -34,6 +34,9 @@ extern "C" {
     pub fn qq_msm_points_free(ctx: *mut QqCtx, p: *mut QqPrepared);
     pub fn qq_msm_points_count(p: *const QqPrepared) -> usize;
     pub fn qq_msm_prepared(ctx: *mut QqCtx, scalars: *const u8, points: *const QqPrepared, n: usize, out: *mut u8, status: *mut u8) -> c_int;
+    pub fn qq_from_uniform_bytes_batch(ctx: *mut QqCtx, uniform64: *const u8, out: *mut u8, n: usize) -> c_int;
+    pub fn qq_vector_pedersen_gens(ctx: *mut QqCtx, capacity: usize, out_h: *mut u8, out_g: *mut u8) -> c_int;
+    pub fn qq_bulletproof_gens(ctx: *mut QqCtx, gens_capacity: usize, party_capacity: usize, out_g: *mut u8, out_h: *mut u8) -> c_int;
     pub fn qq_points_sum(ctx: *mut QqCtx, xyzt: *const u8, k: usize, out: *mut u8, is_identity: *mut u8) -> c_int;
     pub fn qq_msm_segmented(ctx: *mut QqCtx, scalars: *const u8, points: *const u8, offsets: *const u32, m: usize, out: *mut u8, status: *mut u8) -> c_int;
 }

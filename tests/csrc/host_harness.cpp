@@ -228,6 +228,14 @@ void hh_sc_halve(uint8_t* out, const uint8_t* scalar) {
     sc_halve(h, s);
     store_words(out, h);
 }
+void hh_from_uniform(uint8_t* out, const uint8_t* in64) {
+    u32 w[16], o[8];
+    memcpy(w, in64, 64);
+    ge_p3 p;
+    ristretto_from_uniform(p, w);
+    ristretto_compress(o, p);
+    store_words(out, o);
+}
 // fixed base: W in {4,5,6,8}; builds the table on each call into caller-provided buffer (words)
 size_t hh_fb_table_words(int W) { return (size_t)fb_num_windows(W) * fb_entries(W) * QQ_NIELS_WORDS; }
 int hh_fb_build(u32* tbl, int W, const uint8_t* base) {

@@ -569,3 +569,39 @@ def test_shuffle_proof_msm_job_list_64_proofs(engine):
     assert (st == es).all() and not st.any()
     assert (out == eo).all()
     assert out[5].tobytes() == bytes(32)
+
+
+def test_hash_to_group_and_generator_derivation(engine):
+    # from_uniform_bytes (Elligator x 2 + add), VectorPedersenGens::new and BulletproofGens::new against the oracle;
+    # the reference's own constant pins the map: BASE_PK_BTC_COMPRESSED[1] = hash_from_bytes::<Sha3_512>(enc(B))
+    import hashlib
+    rng = np.random.default_rng(99)
+    u = rng.integers(0, 256, size=(300, 64), dtype=np.uint8)
+    u[0] = 0
+    u[1] = 0xff
+    u[2] = np.frombuffer(hashlib.sha3_512(R.BASEPOINT_COMPRESSED).digest(), np.uint8)
+    out = engine.from_uniform_bytes(u)
+    assert out[2].tobytes() == R.PEDERSEN_H_COMPRESSED
+    for i in range(300):
+        assert out[i].tobytes() == R.compress(R.from_uniform_bytes(u[i].tobytes())), i
+    for cap in (2, 3, 9):
+        h, g = engine.vector_pedersen_gens(cap)
+        eh, eg = R.vector_pedersen_gens(cap)
+        assert h.tobytes() == eh == R.PEDERSEN_H_COMPRESSED
+        assert [x.tobytes() for x in g] == eg
+    G, H = engine.bulletproof_gens(8, 3)
+    eG, eH = R.bulletproof_gens(8, 3)
+    for i in range(3):
+        for j in range(8):
+            assert G[i, j].tobytes() == eG[i][j] and H[i, j].tobytes() == eH[i][j], (i, j)
+    # the derived set as a prepared MSM point set
+    G, H = engine.bulletproof_gens(64, 2)
+    pts = np.concatenate([G.reshape(-1, 32), H.reshape(-1, 32)])
+    sc = _rand_scalars(rng, pts.shape[0])
+    hnd = engine.msm_points_prepare(pts)
+    try:
+        o, s = engine.msm_prepared(sc, hnd)
+    finally:
+        engine.msm_points_free(hnd)
+    eo, es = engine.msm(sc, pts)
+    assert s == es == 0 and o.tobytes() == eo.tobytes()

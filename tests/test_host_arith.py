@@ -203,6 +203,20 @@ def test_halve_and_double_compress(hh):
         assert zero == int(want == bytes(32))
 
 
+def test_from_uniform_bytes_elligator(hh):
+    # RistrettoPoint::from_uniform_bytes restated on the device limbs; pinned by the reference's own constant:
+    # BASE_PK_BTC_COMPRESSED[1] = from_uniform_bytes(SHA3-512(enc(B)))  (src/ristretto/constants.rs:17-20)
+    import hashlib
+    o = ctypes.create_string_buffer(32)
+    hh.hh_from_uniform(o, hashlib.sha3_512(R.BASEPOINT_COMPRESSED).digest())
+    assert o.raw == R.PEDERSEN_H_COMPRESSED
+    rnd = random.Random(18)
+    for i in range(60):
+        b = bytes(64) if i == 0 else (b"\xff" * 64 if i == 1 else rnd.randbytes(64))
+        hh.hh_from_uniform(o, b)
+        assert o.raw == R.compress(R.from_uniform_bytes(b)), i
+
+
 @pytest.mark.parametrize("W", [4, 6])
 def test_fixed_base_tables(hh, W):
     rnd = random.Random(15)
