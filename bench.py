@@ -167,6 +167,9 @@ def run_b200(args):
     import __graft_entry__ as g
     world, rank, local = dist_setup(args.gpus)
     if world > 1:
+        # NCCL_DEBUG=VERSION (the image default) prints "NCCL version ..." on stdout; rank 0's stdout carries one JSON line
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = g.load_package()
