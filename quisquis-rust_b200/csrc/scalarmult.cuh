@@ -129,14 +129,6 @@ QQ_HD void vb_scalarmult(ge_p3& r, const u32x4* tbl, const u32 s[8]) { vb_scalar
 // 2 * 252 = 504 (additions unchanged).  Same digits, same tables, same uniform control flow as vb_scalarmult.
 // ---------------------------------------------------------------------------------------------------------
 #define QQ_VBS_PARTS 4
-// Optional block barrier inside the long loops (device kernels define it as __syncthreads() when every thread of the
-// block runs the same trip counts): warps that drift apart execute different code regions and lose instruction-cache
-// locality, see k_varbase_split.
-#if defined(__CUDA_ARCH__) && defined(QQ_VBS_STEP_SYNC_ON)
-#define QQ_VBS_STEP_SYNC() __syncthreads()
-#else
-#define QQ_VBS_STEP_SYNC() ((void)0)
-#endif
 #define QQ_VBS_TABLE_Q (QQ_VBS_PARTS * QQ_VB_ENTRIES * QQ_PT_Q)
 #define QQ_VBS_TABLE_WORDS (QQ_VBS_TABLE_Q * 4)
 
@@ -147,15 +139,8 @@ QQ_HD void vbs_build_tables(u32x4* tbl, const ge_p3& p) {
         vb_build_table(tbl + part * (QQ_VB_ENTRIES * QQ_PT_Q), q);
         if (part + 1 < QQ_VBS_PARTS) {
 #pragma unroll 1
-#if defined(QQ_VBS_ROLLED)
-            for (int i = 0; i < 64; i++) ge_dbl<true>(q, q);
-#else
-            for (int i = 0; i < 63; i++) {
-                if ((i & 7) == 0) QQ_VBS_STEP_SYNC();
-                ge_dbl<false>(q, q);
-            }
+            for (int i = 0; i < 63; i++) ge_dbl<false>(q, q);
             ge_dbl<true>(q, q);
-#endif
         }
     }
 }
@@ -169,21 +154,11 @@ QQ_HD void vbs_scalarmult(ge_p3& r, const u32x4* tbl, const u32 s[8]) {
         u32 w0 = half ? rr[1] : rr[0], w1 = half ? rr[3] : rr[2], w2 = half ? rr[5] : rr[4], w3 = half ? rr[7] : rr[6];
 #pragma unroll 1
         for (int j = 7; j >= 0; j--) {
-            QQ_VBS_STEP_SYNC();
             if (!(half == 1 && j == 7)) {
-#if defined(QQ_VBS_ROLLED)
-#pragma unroll 1
-                for (int d4 = 0; d4 < 4; d4++) ge_dbl<true>(r, r);
-#elif defined(QQ_VBS_ROLLED2)
-#pragma unroll 1
-                for (int d3 = 0; d3 < 3; d3++) ge_dbl<false>(r, r);
-                ge_dbl<true>(r, r);
-#else
                 ge_dbl<false>(r, r);
                 ge_dbl<false>(r, r);
                 ge_dbl<false>(r, r);
                 ge_dbl<true>(r, r);
-#endif
             }
 #pragma unroll 1
             for (int part = 0; part < QQ_VBS_PARTS; part++) {

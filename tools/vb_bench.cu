@@ -1,4 +1,4 @@
-// Tuning harness for the variable-base kernel: register cap (min blocks per SM) x rolled/unrolled doubling body.
+// Tuning harness for the variable-base kernels: block size x register cap x table scheme x per-item barrier.
 // Arithmetic is data-independent, so random limbs are fine for timing.
 #include <cstdio>
 #include <cstdlib>
@@ -12,7 +12,8 @@ using namespace qq;
 
 // MODE 0: one 9-entry table, 252 doublings per scalar.  MODE 1: split tables (vbs_*), 192 + 60 per scalar.
 // MODE 2: MODE 1 + one block barrier per item (all threads run the same number of rounds; out-of-range threads redo the
-// last item without storing).  Compile with -DQQ_VBS_STEP_SYNC='__syncthreads()' for barriers inside the loops as well.
+// last item without storing).  MODE 3: MODE 0 + the barrier.  Build flags compared in profiles/: -DQQ_FE_SINGLE (one
+// product per out-of-line call), -DQQ_INLINE_FIELD_OPS (everything inlined), -DQQ_FE_MUL_KARATSUBA.
 template <int BLOCK, int MINB, int MODE>
 __global__ void __launch_bounds__(BLOCK, MINB) k_vb(vb_args a) {
     size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
