@@ -42,6 +42,7 @@ extern "C" {
 #define QQ_ST_BAD_SCALAR 2  /* a scalar was not canonical (>= l) */
 #define QQ_ST_KEYPAIR 3     /* Err("Invalid Account::Keypair Verification Failed") / `false` */
 #define QQ_ST_COMMIT 4      /* Err("Invalid Account::Commitment Verification Failed") / identity check failed */
+#define QQ_ST_NOT_FOUND 5   /* decommit_value: no v below 2^search_bits (the reference would keep searching up to 2^64) */
 
 #define QQ_BASE_B 0 /* Ristretto basepoint, BASE_PK_BTC_COMPRESSED[0] (src/ristretto/constants.rs:13-16) */
 #define QQ_BASE_H 1 /* Pedersen H,         BASE_PK_BTC_COMPRESSED[1] (src/ristretto/constants.rs:17-20) */
@@ -174,6 +175,16 @@ int qq_points_sum(qq_ctx* ctx, const uint8_t* xyzt, size_t k, uint8_t* out_point
  * instance j covers terms offsets[j] .. offsets[j+1]-1 ; out m x 32 B ; status m */
 int qq_msm_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* points, const uint32_t* offsets, size_t m,
                      uint8_t* out_points, uint8_t* status);
+
+/* ---- decommit ------------------------------------------------------------------------------------------------------
+ * ElGamalCommitment::decommit(sk) = enc(d - sk*c) = enc(v*B)                    src/elgamal/elgamal.rs:106-108 */
+int qq_decommit_batch(qq_ctx* ctx, const uint8_t* comm, const uint8_t* sk, uint8_t* out_points, uint8_t* status, size_t n);
+/* ElGamalCommitment::decommit_value(sk) (src/elgamal/elgamal.rs:119-122, brute_force_decrypt :169-182; the reference's
+ * tests recover 160000 and 16734, elgamal.rs:293-303, accounts.rs:584-595): the smallest v < 2^search_bits with
+ * v*B = d - sk*c, by baby-step / giant-step on the GPU (1 <= search_bits <= 48).  status 0 and out_values[i] = v, or
+ * QQ_ST_NOT_FOUND / QQ_ST_BAD_POINT / QQ_ST_BAD_SCALAR with out_values[i] = 0. */
+int qq_decommit_value_batch(qq_ctx* ctx, const uint8_t* comm, const uint8_t* sk, int search_bits, uint64_t* out_values,
+                            uint8_t* status, size_t n);
 
 /* ---- hash-to-group and generator derivation ---------------------------------------------------------------------
  * RistrettoPoint::from_uniform_bytes over n blocks of 64 uniform bytes (the tail of hash_from_bytes::<Sha3_512>,

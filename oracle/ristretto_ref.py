@@ -388,3 +388,14 @@ def bulletproof_gens(gens_capacity, party_capacity):
             rows.append([compress(from_uniform_bytes(stream[64 * j:64 * j + 64])) for j in range(gens_capacity)])
         out[tag] = rows
     return out[b"G"], out[b"H"]
+
+
+# ---- decommit (reference src/elgamal/elgamal.rs:106-108) ----
+def decommit(comm, sk):
+    """enc(d - sk*c); (bytes, status) with status 1 on a bad point, 2 on a non-canonical scalar."""
+    if not scalar_is_canonical(sk):
+        return bytes(32), 2
+    c, d = decompress(comm[:32]), decompress(comm[32:64])
+    if c is None or d is None:
+        return bytes(32), 1
+    return compress(sub(d, mul(_scal(sk), c))), 0

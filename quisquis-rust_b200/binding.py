@@ -21,7 +21,7 @@ EXPORTS = [
     "qq_fixed_base_batch", "qq_fixed_base_batch_dev", "qq_fixed_base_set_window", "qq_fixed_base_window", "qq_msm", "qq_msm_dev", "qq_msm_partial", "qq_msm_partial_dev",
     "qq_points_sum", "qq_msm_segmented", "qq_msm_points_prepare", "qq_msm_points_prepare_dev", "qq_msm_points_free",
     "qq_msm_points_count", "qq_msm_prepared", "qq_msm_prepared_dev",
-    "qq_from_uniform_bytes_batch", "qq_vector_pedersen_gens", "qq_bulletproof_gens",
+    "qq_decommit_batch", "qq_decommit_value_batch", "qq_from_uniform_bytes_batch", "qq_vector_pedersen_gens", "qq_bulletproof_gens",
 ]
 
 
@@ -85,6 +85,8 @@ def load_library():
     lib.qq_points_sum.argtypes = [vp, u8p, sz, u8p, u8p]
     for name in ("qq_msm_points_prepare", "qq_msm_points_prepare_dev"):
         getattr(lib, name).argtypes = [vp, u8p, sz, ctypes.POINTER(vp)]
+    lib.qq_decommit_batch.argtypes = [vp, u8p, u8p, u8p, u8p, sz]
+    lib.qq_decommit_value_batch.argtypes = [vp, u8p, u8p, ctypes.c_int, u8p, u8p, sz]
     lib.qq_from_uniform_bytes_batch.argtypes = [vp, u8p, u8p, sz]
     lib.qq_vector_pedersen_gens.argtypes = [vp, sz, u8p, u8p]
     lib.qq_bulletproof_gens.argtypes = [vp, sz, sz, u8p, u8p]
@@ -310,6 +312,23 @@ class Engine:
         out, st = np.zeros(32, np.uint8), np.zeros(1, np.uint8)
         self._ck(self.lib.qq_msm_prepared(self.h, _ptr(scalars), handle, n, _ptr(out), _ptr(st)), "qq_msm_prepared")
         return out, int(st[0])
+
+    def decommit(self, comm, sk):
+        comm, sk = _u8(comm), _u8(sk)
+        n = sk.size // 32
+        _u8(comm, n * 64)
+        out, st = np.zeros(n * 32, np.uint8), np.zeros(n, np.uint8)
+        self._ck(self.lib.qq_decommit_batch(self.h, _ptr(comm), _ptr(sk), _ptr(out), _ptr(st), n), "qq_decommit_batch")
+        return out.reshape(n, 32), st
+
+    def decommit_value(self, comm, sk, search_bits=32):
+        comm, sk = _u8(comm), _u8(sk)
+        n = sk.size // 32
+        _u8(comm, n * 64)
+        vals, st = np.zeros(n, np.uint64), np.zeros(n, np.uint8)
+        self._ck(self.lib.qq_decommit_value_batch(self.h, _ptr(comm), _ptr(sk), int(search_bits),
+                                                   vals.ctypes.data_as(ctypes.c_void_p), _ptr(st), n), "qq_decommit_value_batch")
+        return vals, st
 
     def from_uniform_bytes(self, uniform64):
         u = _u8(uniform64)

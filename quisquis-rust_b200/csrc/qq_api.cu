@@ -14,6 +14,7 @@
 #include "compress_batch.cuh"
 #include "fixedbase_big.cuh"
 #include "keccak_host.hpp"
+#include "decommit.cuh"
 
 using namespace qq;
 
@@ -34,6 +35,8 @@ struct qq_ctx {
     size_t io_cap = 0;
     cudaEvent_t user_ev[8] = {nullptr};
     u32* fb_tbl[2] = {nullptr, nullptr};      // shared-memory-sized tables (W = QQ_FB_W)
+    u32x4* bsgs_enc = nullptr;                // baby-step table of decommit_value: enc(j B), j < 2^20 (built on first use)
+    u32* bsgs_slots = nullptr;
     u32x4* msm_res = nullptr;                 // per-call MSM result point + export bytes (outside the workspace slab)
     uint8_t* msm_small = nullptr;
     u32x4* fbt[2] = {nullptr, nullptr};       // large-window tables in L2 / HBM (fixedbase_big.cuh), optional
@@ -456,6 +459,8 @@ extern "C" void qq_destroy(qq_ctx* ctx) {
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->io) cudaFree(ctx->io);
+    if (ctx->bsgs_enc) cudaFree(ctx->bsgs_enc);
+    if (ctx->bsgs_slots) cudaFree(ctx->bsgs_slots);
     if (ctx->msm_res) cudaFree(ctx->msm_res);
     if (ctx->msm_small) cudaFree(ctx->msm_small);
     for (int i = 0; i < 8; i++)

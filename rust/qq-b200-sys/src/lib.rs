@@ -34,6 +34,8 @@ extern "C" {
     pub fn qq_msm_points_free(ctx: *mut QqCtx, p: *mut QqPrepared);
     pub fn qq_msm_points_count(p: *const QqPrepared) -> usize;
     pub fn qq_msm_prepared(ctx: *mut QqCtx, scalars: *const u8, points: *const QqPrepared, n: usize, out: *mut u8, status: *mut u8) -> c_int;
+    pub fn qq_decommit_batch(ctx: *mut QqCtx, comm: *const u8, sk: *const u8, out: *mut u8, status: *mut u8, n: usize) -> c_int;
+    pub fn qq_decommit_value_batch(ctx: *mut QqCtx, comm: *const u8, sk: *const u8, search_bits: c_int, out_values: *mut u64, status: *mut u8, n: usize) -> c_int;
     pub fn qq_from_uniform_bytes_batch(ctx: *mut QqCtx, uniform64: *const u8, out: *mut u8, n: usize) -> c_int;
     pub fn qq_vector_pedersen_gens(ctx: *mut QqCtx, capacity: usize, out_h: *mut u8, out_g: *mut u8) -> c_int;
     pub fn qq_bulletproof_gens(ctx: *mut QqCtx, gens_capacity: usize, party_capacity: usize, out_g: *mut u8, out_h: *mut u8) -> c_int;

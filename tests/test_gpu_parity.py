@@ -605,3 +605,34 @@ def test_hash_to_group_and_generator_derivation(engine):
         engine.msm_points_free(hnd)
     eo, es = engine.msm(sc, pts)
     assert s == es == 0 and o.tobytes() == eo.tobytes()
+
+
+def test_decommit_and_decommit_value(engine):
+    # ElGamalCommitment::decommit / decommit_value; replays the reference's two known-value tests
+    # (elgamal.rs:293-303: 160000, accounts.rs:584-595: 16734) plus values up to 2^36 through the baby-step/giant-step search
+    st = Stream(b"decommit")
+    vals = [160000, 16734, 0, 1, 2**20 - 1, 2**20, 2**20 + 1, 2**32 - 1, 2**32, 2**36 - 5, 123456789012 % 2**36]
+    comms, sks = [], []
+    for v in vals:
+        sk, rho = st.scalar(), st.scalar()
+        gr = R.mul(rho, R.BASEPOINT)
+        pk = R.compress(gr) + R.compress(R.mul(sk, gr))
+        comm, es = R.generate_commitment(pk, st.scalar_bytes(), sb(v))
+        assert es == 0
+        comms.append(comm)
+        sks.append(sb(sk))
+    out, s = engine.decommit(cat(comms), cat(sks))
+    for i, v in enumerate(vals):
+        eo, es = R.decommit(comms[i], sks[i])
+        assert s[i] == es == 0 and out[i].tobytes() == eo == R.compress(R.mul(v, R.BASEPOINT)), i
+    got, s = engine.decommit_value(cat(comms), cat(sks), 36)
+    assert not s.any() and [int(x) for x in got] == vals
+    # a narrower search does not find the large ones (status 5), a wrong key finds nothing, bad inputs keep their codes
+    got, s = engine.decommit_value(cat(comms), cat(sks), 24)
+    assert [int(x) for x in s] == [0 if v < 2**24 else 5 for v in vals]
+    assert [int(x) for x in got] == [v if v < 2**24 else 0 for v in vals]
+    bad_comm = invalid_encodings()[0][1] + comms[0][32:]
+    got, s = engine.decommit_value(cat([comms[0], bad_comm, comms[1]]), cat([sks[1], sks[0], R.L.to_bytes(32, "little")]), 22)
+    assert [int(x) for x in s] == [5, 1, 2] and not got.any()
+    out, s = engine.decommit(cat([bad_comm, comms[1]]), cat([sks[0], R.L.to_bytes(32, "little")]))
+    assert [int(x) for x in s] == [1, 2] and not out.any()
