@@ -132,6 +132,21 @@ class ElGamalCommitment:
             raise PanicError("called `Option::unwrap()` on a `None` value")
         return ElGamalCommitment(out[0].tobytes())
 
+    def decommit(self, pr):
+        """src/elgamal/elgamal.rs:106-108 -> compressed G*v (32 bytes)."""
+        out, st = default_engine().decommit(_b(self.data, 64), _b(pr, 32))
+        if st[0] == B.ST_BAD_POINT:
+            raise PanicError("called `Option::unwrap()` on a `None` value")
+        return out[0].tobytes()
+
+    def decommit_value(self, pr, search_bits=40):
+        """src/elgamal/elgamal.rs:119-122 -> Some(v) as int, or None.  The reference searches every u64 in ascending order;
+        here the search space is 2^search_bits (baby-step / giant-step on the GPU)."""
+        vals, st = default_engine().decommit_value(_b(self.data, 64), _b(pr, 32), search_bits)
+        if st[0] == B.ST_BAD_POINT:
+            raise PanicError("called `Option::unwrap()` on a `None` value")
+        return int(vals[0]) if st[0] == 0 else None
+
     def __eq__(self, o):
         return self.data == o.data
 
@@ -179,6 +194,19 @@ class Account:
         if st[0]:
             raise ValueError(msg[int(st[0])])
         return None
+
+    def decrypt_account_balance(self, sk, bl):
+        """src/accounts/accounts.rs:103-110."""
+        self.verify_account(sk, bl)
+        return self.comm.decommit(sk)
+
+    def decrypt_account_balance_value(self, sk, search_bits=40):
+        """src/accounts/accounts.rs:119-128."""
+        self.pk.verify_keypair(sk)
+        v = self.comm.decommit_value(sk, search_bits)
+        if v is None:
+            raise ValueError("Decryption value failed.")
+        return v
 
     @staticmethod
     def verify_account_batch(accounts, sks, bls, engine=None):

@@ -167,6 +167,27 @@ struct ElGamalCommitment {
         if (st == QQ_ST_BAD_POINT) throw Panic();
         return from_raw(out);
     }
+    // decommit(&self, pr) -> CompressedRistretto   :106-108
+    CompressedRistretto decommit(const RistrettoSecretKey& pr) const {
+        auto b = to_bytes();
+        CompressedRistretto out;
+        uint8_t st;
+        Gpu& g = Gpu::instance();
+        g.check(qq_decommit_batch(g.ctx(), b.data(), pr.s.data(), out.data(), &st, 1), "decommit");
+        if (st == QQ_ST_BAD_POINT) throw Panic();
+        return out;
+    }
+    // decommit_value(&self, pr) -> Option<Scalar>   :119-122 (search space 2^search_bits instead of the reference's 2^64 walk)
+    std::optional<uint64_t> decommit_value(const RistrettoSecretKey& pr, int search_bits = 40) const {
+        auto b = to_bytes();
+        uint64_t v = 0;
+        uint8_t st;
+        Gpu& g = Gpu::instance();
+        g.check(qq_decommit_value_batch(g.ctx(), b.data(), pr.s.data(), search_bits, &v, &st, 1), "decommit_value");
+        if (st == QQ_ST_BAD_POINT) throw Panic();
+        if (st != QQ_ST_OK) return std::nullopt;
+        return v;
+    }
     bool operator==(const ElGamalCommitment& o) const { return c == o.c && d == o.d; }
 
   private:

@@ -67,6 +67,14 @@ int main(int argc, char** argv) {
     auto c6 = ElGamalCommitment::generate_commitment(accs[0].pk, zero, six);
     CHECK((c10 - c4) == c6);
     CHECK(ElGamalCommitment::add_commitments(c4, c6) == c10);
+    // decommit_value (src/elgamal/elgamal.rs verify_decommit_value: 160000)
+    Scalar big{};
+    big[0] = 0x00; big[1] = 0x71; big[2] = 0x02;   // 160000 = 0x027100
+    auto cbig = ElGamalCommitment::generate_commitment(accs[0].pk, us[1], big);
+    auto got = cbig.decommit_value(RistrettoSecretKey{sks[0]}, 24);
+    CHECK(got.has_value() && *got == 160000);
+    CHECK(!cbig.decommit_value(RistrettoSecretKey{sks[1]}, 21).has_value());
+    CHECK(cbig.decommit(RistrettoSecretKey{sks[0]}) == ElGamalCommitment::generate_commitment(accs[0].pk, zero, big).d);
     // verify_account_update with bl = 0 (exactly-9 quirk)
     std::vector<Scalar> z9(9, zero);
     auto upd0 = Account::update_account_batch(accs, z9, us, cs);

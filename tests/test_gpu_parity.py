@@ -268,6 +268,11 @@ def test_reference_interface_mirror(engine, pkg):
         upd.verify_account(sb(sk), sb(16735))
     with pytest.raises(ValueError, match="Keypair Verification Failed"):
         upd.verify_account(sb(sk + 1), sb(16734))
+    # decrypt_account_balance / _value (src/accounts/accounts.rs:103-128; reference tests :396-406, :584-595)
+    assert upd.decrypt_account_balance(sb(sk), sb(16734)) == R.compress(R.mul(16734, R.BASEPOINT))
+    assert upd.decrypt_account_balance_value(sb(sk), search_bits=24) == 16734
+    with pytest.raises(ValueError, match="Keypair Verification Failed"):
+        upd.decrypt_account_balance_value(sb(sk + 1))
     r = st.scalar_bytes()
     pk2 = pkg.RistrettoPublicKey.update_public_key(acc.pk, r)
     assert pkg.RistrettoPublicKey.verify_public_key_update(pk2, acc.pk, r)
