@@ -279,8 +279,17 @@ def run_b200(args):
                                      "mults_per_sec_per_gpu": nf / (best * 1e-3),
                                      "imad_model_frac": nf * IMAD_PER_FIXED_COMPRESSED / (best * 1e-3) / peak["imad_lo_per_s"],
                                      "same_output_as_default_window": chk == ref_sum})
+        # signed 64-bit values (balances, the `bl` of update_account / generate_commitment): only the low windows are walked
+        fv = torch.from_numpy(rng.integers(-2**63, 2**63 - 1, size=nf, dtype=np.int64)).to(dev)
+        best = 1e30
+        for rep in range(4):
+            eng.call_dev("qq_fixed_base_i64_batch_dev", ctypes.c_int(0), vp(fv.data_ptr()), vp(fo.data_ptr()), ctypes.c_size_t(nf))
+            if rep:
+                best = min(best, eng.last_kernel_ms)
+        fixed["i64_values"] = {"window_bits": eng.fixed_base_window(0), "ms": best, "mults_per_sec_per_gpu": nf / (best * 1e-3),
+                               "scalars": "uniform signed 64-bit values (Scalar::from(u64) balances and their negations)"}
         eng.fixed_base_set_window(0, w_default)
-        del fs, fo, fst
+        del fs, fo, fst, fv
 
     # ---- MSM 2^20 (configs[3]): known-dlog points, last scalar solved so the sum is the identity ------------------
     msm = None
@@ -460,7 +469,7 @@ def run_b200(args):
             "cpu_baseline": cpu,
         }
         if fixed:
-            for w_ in fixed["windows"]:
+            for w_ in fixed["windows"] + [fixed["i64_values"]]:
                 w_["mults_per_sec"] = w_["mults_per_sec_per_gpu"] * world
             line["fixed_base"] = fixed
         if msm:

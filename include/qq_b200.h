@@ -137,6 +137,11 @@ int qq_fixed_base_batch_dev(qq_ctx* ctx, int which, const uint8_t* s, uint8_t* o
  * fewer additions per scalar and identical results.  window_bits = 0 frees the table (batches then use the
  * shared-memory 6-bit table only); otherwise 8 <= window_bits <= 28.  Rebuilds synchronously. */
 int qq_fixed_base_set_window(qq_ctx* ctx, int which, int window_bits);
+/* out_i = enc(v_i * Base) for signed 64-bit values: what `&Scalar::from(v as u64) * &RISTRETTO_BASEPOINT_TABLE` (and its
+ * negation) computes for balances (src/elgamal/elgamal.rs:285-300, src/accounts/accounts.rs:419-429).  Only the windows
+ * that a 64-bit magnitude can touch are walked (3 at W = 22).  Requires a large-window table (window_bits != 0). */
+int qq_fixed_base_i64_batch(qq_ctx* ctx, int which, const int64_t* v, uint8_t* out_points, size_t n);
+int qq_fixed_base_i64_batch_dev(qq_ctx* ctx, int which, const int64_t* v, uint8_t* out_points, size_t n);
 int qq_fixed_base_window(const qq_ctx* ctx, int which);
 
 /* ---- multiscalar multiplication --------------------------------------------------------------------------------

@@ -18,7 +18,8 @@ EXPORTS = [
     "qq_generate_commitment_batch", "qq_generate_commitment_batch_dev", "qq_add_commitments_batch",
     "qq_mul_commitment_batch", "qq_update_account_batch", "qq_update_account_batch_dev",
     "qq_verify_account_batch", "qq_verify_account_batch_dev", "qq_delta_epsilon_batch", "qq_delta_identity_check",
-    "qq_fixed_base_batch", "qq_fixed_base_batch_dev", "qq_fixed_base_set_window", "qq_fixed_base_window", "qq_msm", "qq_msm_dev", "qq_msm_partial", "qq_msm_partial_dev",
+    "qq_fixed_base_batch", "qq_fixed_base_batch_dev", "qq_fixed_base_set_window", "qq_fixed_base_window",
+    "qq_fixed_base_i64_batch", "qq_fixed_base_i64_batch_dev", "qq_msm", "qq_msm_dev", "qq_msm_partial", "qq_msm_partial_dev",
     "qq_points_sum", "qq_msm_segmented", "qq_msm_points_prepare", "qq_msm_points_prepare_dev", "qq_msm_points_free",
     "qq_msm_points_count", "qq_msm_prepared", "qq_msm_prepared_dev",
     "qq_decommit_batch", "qq_decommit_value_batch", "qq_from_uniform_bytes_batch", "qq_vector_pedersen_gens", "qq_bulletproof_gens",
@@ -78,6 +79,8 @@ def load_library():
     lib.qq_delta_identity_check.argtypes = [vp, u8p, sz, u8p]
     for name in ("qq_fixed_base_batch", "qq_fixed_base_batch_dev"):
         getattr(lib, name).argtypes = [vp, ctypes.c_int, u8p, u8p, u8p, sz]
+    for name in ("qq_fixed_base_i64_batch", "qq_fixed_base_i64_batch_dev"):
+        getattr(lib, name).argtypes = [vp, ctypes.c_int, vp, u8p, sz]
     lib.qq_fixed_base_set_window.argtypes = [vp, ctypes.c_int, ctypes.c_int]
     lib.qq_fixed_base_window.argtypes = [vp, ctypes.c_int]
     for name in ("qq_msm", "qq_msm_dev", "qq_msm_partial", "qq_msm_partial_dev"):
@@ -271,6 +274,14 @@ class Engine:
         out, st = np.zeros(n * 32, np.uint8), np.zeros(n, np.uint8)
         self._ck(self.lib.qq_fixed_base_batch(self.h, int(which), _ptr(s), _ptr(out), _ptr(st), n), "qq_fixed_base_batch")
         return out.reshape(n, 32), st
+
+    def fixed_base_i64(self, which, values):
+        """enc(v * Base) for signed 64-bit values (balances)."""
+        v = np.ascontiguousarray(values, dtype=np.int64).reshape(-1)
+        out = np.zeros(v.size * 32, np.uint8)
+        self._ck(self.lib.qq_fixed_base_i64_batch(self.h, int(which), v.ctypes.data_as(ctypes.c_void_p), _ptr(out), v.size),
+                 "qq_fixed_base_i64_batch")
+        return out.reshape(v.size, 32)
 
     def fixed_base_set_window(self, which, window_bits):
         """Rebuild the large fixed-base table of base `which` with `window_bits`-bit windows (0 frees it)."""

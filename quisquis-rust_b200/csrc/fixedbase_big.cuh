@@ -174,4 +174,63 @@ __global__ void __launch_bounds__(QQ_FBT_BLOCK, 4) k_fixedbase_big_dc(const u32x
     }
 }
 
+// ---- 64-bit values (balances) ------------------------------------------------------------------------------------------
+// The reference builds most committed values with Scalar::from(u64) (balances: src/accounts/accounts.rs:419-429,
+// src/elgamal/elgamal.rs:285-300; negative amounts as -Scalar::from(u64)).  A 64-bit magnitude needs ceil(66 / W)
+// windows instead of ceil(255 / W): 3 at W = 22.  The batch encoder wants the HALF point; (v / 2 mod l) of an odd v is a
+// 252-bit scalar, so instead  v B = 2 ((v >> 1) B + (v & 1) B/2)  with the constant B/2 = ((l + 1) / 2) B added by one
+// more mixed addition (identity entry when v is even: uniform control flow).  Negative v: the point is negated.
+// out: the batch encoder's first-stage outputs, as k_fixedbase_big_dc.
+__global__ void __launch_bounds__(QQ_FBT_BLOCK, 4) k_fixedbase_big_i64_dc(const u32x4* __restrict__ tbl, fbt_geom g,
+                                                                          const long long* __restrict__ v,
+                                                                          const u32x4* __restrict__ half_base,
+                                                                          u32x4* __restrict__ state, u32x4* __restrict__ wout,
+                                                                          uint8_t* __restrict__ zflag, size_t n) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    ge_niels hb;
+    niels_load_padded(hb, half_base);
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+        long long sv = v[t];
+        unsigned long long mag = sv < 0 ? 0ull - (unsigned long long)sv : (unsigned long long)sv;
+        u32 odd = (u32)(mag & 1ull);
+        unsigned long long h = mag >> 1;
+        u32 w[8] = {(u32)h, (u32)(h >> 32), 0, 0, 0, 0, 0, 0};
+        ge_p3 r;
+        fbt_scalarmult(r, tbl, g, w);                 // g.NW = windows covering 64 bits
+        ge_niels add;                                 // odd ? B/2 : identity (1, 1, 0)
+        fe one, zero;
+        fe_1(one);
+        fe_0(zero);
+        add.ypx = one; add.ymx = one; add.xy2d = zero;
+        fe_cmov(add.ypx, hb.ypx, odd);
+        fe_cmov(add.ymx, hb.ymx, odd);
+        fe_cmov(add.xy2d, hb.xy2d, odd);
+        ge_madd(r, r, add);
+        if (sv < 0) ge_neg(r, r);
+        dc_state st;
+        fe wv;
+        dc_prepare(st, wv, r);
+        u32 z = fe_iszero(wv);
+        fe_cmov(wv, one, z);
+        zflag[t] = (uint8_t)z;
+        u32x4* sp = state + (size_t)QQ_DC_STATE_Q * t;
+        int o = 0;
+        fe_store4(sp, o, st.e, st.f);
+        fe_store4(sp, o, st.g, st.h);
+        fe_store4(sp, o, st.eg, st.fh);
+        fe_st(wout + 2 * t, wv);
+    }
+}
+// one extended point -> affine Niels (96 B): the constant B/2 above
+__global__ void k_point_to_niels(const u32x4* __restrict__ p_ext, u32x4* __restrict__ out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    ge_p3 p;
+    ge_p3_load(p, p_ext);
+    u32 w[QQ_NIELS_WORDS];
+    ge_to_niels_affine(w, p);
+    ge_niels nl;
+    ge_niels_load(nl, w);
+    niels_store_padded(out, nl);
+}
+
 }  // namespace qq

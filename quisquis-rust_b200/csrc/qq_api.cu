@@ -41,6 +41,7 @@ struct qq_ctx {
     uint8_t* msm_small = nullptr;
     u32x4* fbt[2] = {nullptr, nullptr};       // large-window tables in L2 / HBM (fixedbase_big.cuh), optional
     fbt_geom fbt_g[2] = {{0, 0, 0}, {0, 0, 0}};
+    u32x4* half_base[2] = {nullptr, nullptr};  // ((l + 1) / 2) * Base as affine Niels, for the 64-bit fixed-base path
     uint8_t base_pk[64];
     uint64_t launches = 0;
     float last_ms = 0.f;
@@ -444,6 +445,26 @@ extern "C" int qq_init(qq_ctx** out, int device) {
         if (const char* e = getenv("QQ_FB_WINDOW")) W = atoi(e);
         if (W != 0 && (W < 8 || W > 28)) { ctx->err = "QQ_FB_WINDOW must be 0 or in [8, 28]"; return QQ_ERR_ARG; }
         for (int b = 0; b < 2; b++) CKQ(fbt_build(ctx, b, W));
+        // B/2 and H/2 = ((l + 1) / 2) * Base through the shared-memory table, normalised to affine Niels
+        {
+            static const uint8_t HALF_L1[32] = {0xf7, 0xe9, 0x7a, 0x2e, 0x8d, 0x31, 0x09, 0x2c, 0x6b, 0xce, 0x7b, 0x51, 0xef, 0x7c, 0x6f, 0x0a,
+                                                0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0x08};   // (l + 1) / 2, little endian
+            u32x4 *ds = nullptr, *dp = nullptr;
+            CK(cudaMalloc((void**)&ds, 32));
+            CK(cudaMalloc((void**)&dp, QQ_PT_BYTES));
+            CK(cudaMemcpy(ds, HALF_L1, 32, cudaMemcpyHostToDevice));
+            for (int b = 0; b < 2; b++) {
+                CK(cudaMalloc((void**)&ctx->half_base[b], QQ_NIELS_STRIDE_Q * 16));
+                size_t smem = fb_table_words() * 4;
+                k_fixedbase<QQ_FB_W><<<1, 512, smem, ctx->stream>>>(ctx->fb_tbl[b], ds, 0, dp, 1);
+                k_point_to_niels<<<1, 32, 0, ctx->stream>>>(dp, ctx->half_base[b]);
+                ctx->launches += 2;
+            }
+            CK(cudaStreamSynchronize(ctx->stream));
+            CK(cudaGetLastError());
+            cudaFree(ds);
+            cudaFree(dp);
+        }
         return QQ_OK;
     };
     int r = body();
@@ -468,6 +489,7 @@ extern "C" void qq_destroy(qq_ctx* ctx) {
     for (int b = 0; b < 2; b++) {
         if (ctx->fb_tbl[b]) cudaFree(ctx->fb_tbl[b]);
         if (ctx->fbt[b]) cudaFree(ctx->fbt[b]);
+        if (ctx->half_base[b]) cudaFree(ctx->half_base[b]);
     }
     for (int i = 0; i < 8; i++)
         if (ctx->msm_ev[i]) cudaEventDestroy(ctx->msm_ev[i]);
@@ -1112,6 +1134,53 @@ extern "C" int qq_fixed_base_batch(qq_ctx* ctx, int which, const uint8_t* s, uin
     CKQ(core_fixed_base(ctx, which, ds, dout, dst, n));
     CKQ(st.back(out_points, dout, n * 32));
     CKQ(st.back(status, dst, n));
+    return call_end(ctx);
+}
+
+// 64-bit signed values (balances): out_i = enc(v_i * Base).  Needs a large-window table (qq_fixed_base_set_window != 0).
+static int core_fixed_base_i64(qq_ctx* ctx, int which, const int64_t* v, uint8_t* out, size_t n) {
+    if (ctx->fbt[which] == nullptr) {
+        ctx->err = "qq_fixed_base_i64_batch needs a large-window table (qq_fixed_base_set_window)";
+        return QQ_ERR_ARG;
+    }
+    fbt_geom g = ctx->fbt_g[which];
+    g.NW = (66 + g.W - 1) / g.W;                      // windows covering a 63-bit half magnitude + recoding bias
+    const size_t CH = (size_t)1 << 22;
+    for (size_t base = 0; base < n; base += CH) {
+        size_t m = n - base < CH ? n - base : CH;
+        CKQ(ws_begin(ctx, dc_scratch_bytes(m)));
+        dc_ws dc = dc_take(ctx, m);
+        span_begin(ctx, FAM_FB);
+        k_fixedbase_big_i64_dc<<<grid_for(m, QQ_FBT_BLOCK, ctx->sms * 4), QQ_FBT_BLOCK, 0, ctx->stream>>>(
+            ctx->fbt[which], g, (const long long*)(v + base), ctx->half_base[which], dc.state, dc.w, dc.zflag, m);
+        span_end(ctx);
+        ctx->launches++;
+        span_begin(ctx, FAM_FIN);
+        CKQ(launch_batch_invert(ctx, dc, m));
+        k_dc_finish<<<grid_for(m, 256, ctx->sms * 64), 256, 0, ctx->stream>>>(dc.state, dc.prefix, dc.zflag, nullptr, 1,
+                                                                            (u32x4*)(out + base * 32), IDENT, nullptr, IDENT, nullptr, m);
+        span_end(ctx);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    return QQ_OK;
+}
+extern "C" int qq_fixed_base_i64_batch_dev(qq_ctx* ctx, int which, const int64_t* v, uint8_t* out_points, size_t n) {
+    ENTER();
+    REQUIRE((which == 0 || which == 1) && (((uintptr_t)v & 7) == 0) && aligned16(out_points));
+    CKQ(core_fixed_base_i64(ctx, which, v, out_points, n));
+    return call_end(ctx);
+}
+extern "C" int qq_fixed_base_i64_batch(qq_ctx* ctx, int which, const int64_t* v, uint8_t* out_points, size_t n) {
+    ENTER();
+    REQUIRE((which == 0 || which == 1) && (n == 0 || (v && out_points)));
+    stage st(ctx);
+    CKQ(st.plan({(size_t)(n * 8), (size_t)(n * 32)}));
+    uint8_t *dv, *dout;
+    CKQ(st.in(v, n * 8, &dv));
+    CKQ(st.outbuf(n * 32, &dout));
+    CKQ(core_fixed_base_i64(ctx, which, (const int64_t*)dv, dout, n));
+    CKQ(st.back(out_points, dout, n * 32));
     return call_end(ctx);
 }
 

@@ -26,6 +26,7 @@ extern "C" {
     pub fn qq_delta_epsilon_batch(ctx: *mut QqCtx, acc: *const u8, bl: *const u8, r: *const u8, base_pk: *const u8, delta: *mut u8, eps: *mut u8, status: *mut u8, n: usize) -> c_int;
     pub fn qq_delta_identity_check(ctx: *mut QqCtx, acc: *const u8, n: usize, verdict: *mut u8) -> c_int;
     pub fn qq_fixed_base_batch(ctx: *mut QqCtx, which: c_int, s: *const u8, out: *mut u8, status: *mut u8, n: usize) -> c_int;
+    pub fn qq_fixed_base_i64_batch(ctx: *mut QqCtx, which: c_int, v: *const i64, out: *mut u8, n: usize) -> c_int;
     pub fn qq_fixed_base_set_window(ctx: *mut QqCtx, which: c_int, window_bits: c_int) -> c_int;
     pub fn qq_fixed_base_window(ctx: *const QqCtx, which: c_int) -> c_int;
     pub fn qq_msm(ctx: *mut QqCtx, scalars: *const u8, points: *const u8, n: usize, out: *mut u8, status: *mut u8) -> c_int;

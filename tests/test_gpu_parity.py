@@ -641,3 +641,29 @@ def test_decommit_and_decommit_value(engine):
     assert [int(x) for x in s] == [5, 1, 2] and not got.any()
     out, s = engine.decommit(cat([bad_comm, comms[1]]), cat([sks[0], R.L.to_bytes(32, "little")]))
     assert [int(x) for x in s] == [1, 2] and not out.any()
+
+
+@pytest.mark.parametrize("W", [9, 16, 22])
+def test_fixed_base_signed_64_bit_values(engine, W):
+    # qq_fixed_base_i64_batch: enc(v * Base) for balances; v B = 2 ((|v| >> 1) B + (|v| & 1) B/2), negated for v < 0
+    old = [engine.fixed_base_window(0), engine.fixed_base_window(1)]
+    try:
+        rng = np.random.default_rng(640 + W)
+        vals = [0, 1, -1, 2, -2, 3, 160000, 16734, -5, 5, 2**63 - 1, -(2**63 - 1), -(2**63), 2**62, 2**W, 2**W - 1, -(2**(W - 1))]
+        vals += [int(x) for x in rng.integers(-2**63, 2**63 - 1, size=300, dtype=np.int64)]
+        for which, base in ((0, R.BASEPOINT), (1, R.PEDERSEN_H)):
+            engine.fixed_base_set_window(which, W)
+            out = engine.fixed_base_i64(which, vals)
+            for i, v in enumerate(vals if which == 0 else vals[:40]):
+                assert out[i].tobytes() == R.compress(R.mul(v % R.L, base)), (which, i, v)
+        # against the full-width path on a larger batch
+        big = rng.integers(-2**63, 2**63 - 1, size=5000, dtype=np.int64)
+        sc = np.zeros((big.size, 32), np.uint8)
+        for i, v in enumerate(big):
+            sc[i] = np.frombuffer((int(v) % R.L).to_bytes(32, "little"), np.uint8)
+        a = engine.fixed_base_i64(0, big)
+        b, st = engine.fixed_base(0, sc)
+        assert not st.any() and (a == b).all()
+    finally:
+        for which in (0, 1):
+            engine.fixed_base_set_window(which, old[which])
