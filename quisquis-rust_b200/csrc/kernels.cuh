@@ -376,6 +376,14 @@ __global__ void k_point_export(const u32x4* in, u32x4* xyzt, u32x4* compressed, 
     }
     if (is_identity != nullptr) *is_identity = (uint8_t)ge_ristretto_is_identity(p);
 }
+// device-side delivery of an MSM result: nbytes of `src` (zeros when *status != 0) and the status byte
+__global__ void k_emit_result(const uint8_t* __restrict__ src, int nbytes, const uint8_t* __restrict__ status,
+                              uint8_t* __restrict__ out, uint8_t* __restrict__ status_out) {
+    int t = threadIdx.x;
+    uint8_t st = *status;
+    if (t < nbytes) out[t] = st ? 0 : src[t];
+    if (t == 0) *status_out = st;
+}
 // k points given as canonical X,Y,Z,T bytes -> extended limbs
 __global__ void k_point_import(const u32x4* xyzt, u32x4* pts, size_t k) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) k_msm_prepare(const u32x4* __restrict__ p
                                                      size_t n, msm_geom g, u32x4* __restrict__ niels,
                                                      const uint8_t* __restrict__ pre_ok,
                                                      uint8_t* __restrict__ term_status, int16_t* __restrict__ digits,
-                                                     unsigned int* __restrict__ counts) {
+                                                     unsigned int* __restrict__ slots, unsigned int* __restrict__ counts) {
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         u32 ok;
@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(256) k_msm_prepare(const u32x4* __restrict__ p
         for (int k = 0; k < g.K; k++) {
             int d = st ? 0 : sc_digit_rt(r, g.c, k);
             digits[(size_t)k * n + i] = (int16_t)d;
-            if (d != 0) atomicAdd(&counts[(size_t)k * g.NB + (size_t)((d < 0 ? -d : d) - 1)], 1u);
+            // the histogram increment also hands out this entry's position inside its bucket: the scatter needs no atomics
+            if (d != 0) slots[(size_t)k * n + i] = atomicAdd(&counts[(size_t)k * g.NB + (size_t)((d < 0 ? -d : d) - 1)], 1u);
         }
     }
 }
@@ -210,7 +211,7 @@ static inline void launch_scan_exclusive(const unsigned int* in, unsigned int* o
 
 __global__ void __launch_bounds__(256) k_msm_scatter(const int16_t* __restrict__ digits, size_t n, msm_geom g,
                                                      const unsigned int* __restrict__ offsets,
-                                                     unsigned int* __restrict__ cursor, unsigned int* __restrict__ sorted) {
+                                                     const unsigned int* __restrict__ slots, unsigned int* __restrict__ sorted) {
     size_t total = (size_t)g.K * n;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
@@ -219,8 +220,7 @@ __global__ void __launch_bounds__(256) k_msm_scatter(const int16_t* __restrict__
         size_t k = t / n;
         size_t i = t - k * n;
         size_t key = k * g.NB + (size_t)((d < 0 ? -d : d) - 1);
-        unsigned int slot = atomicAdd(&cursor[key], 1u);
-        sorted[offsets[key] + slot] = (unsigned int)i | (d < 0 ? 0x80000000u : 0u);
+        sorted[offsets[key] + slots[t]] = (unsigned int)i | (d < 0 ? 0x80000000u : 0u);
     }
 }
 
