@@ -255,7 +255,7 @@ def run_b200(args):
 
     # ---- configs[0]: the 9-account anonymity set (3x3 shuffle), latency of one update_account + verify_account call pair
     # through the host API (the reference runs this case on one CPU core; reported for information)
-    small = None
+    anon9 = None
     if rank == 0:
         a9, b9, u9, c9 = acc_h[:9].copy(), bl_h[:9].copy(), u_h[:9].copy(), c_h[:9].copy()
         lat = []
@@ -265,7 +265,7 @@ def run_b200(args):
             eng.verify_account(o9, u9, b9)      # verdict not used: times the call
             lat.append((time.time() - t0_) * 1e3)
         lat.sort()
-        small = {"accounts": 9, "update_plus_verify_ms_median": lat[len(lat) // 2], "ms_min": lat[0],
+        anon9 = {"accounts": 9, "update_plus_verify_ms_median": lat[len(lat) // 2], "ms_min": lat[0],
                  "matches_batch_output": bool((o9.reshape(-1) == out_d.cpu().numpy()[:9 * 128]).all())}
 
     # ---- fixed-base throughput (north-star target: 1e9 / s): scalars resident, 32-byte encodings out ----------------
@@ -483,8 +483,8 @@ def run_b200(args):
                                  if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0}},
             "cpu_baseline": cpu,
         }
-        if small:
-            line["anonymity_set_9"] = small
+        if anon9:
+            line["anonymity_set_9"] = anon9
         if fixed:
             for w_ in fixed["windows"] + [fixed["i64_values"]]:
                 w_["mults_per_sec"] = w_["mults_per_sec_per_gpu"] * world
