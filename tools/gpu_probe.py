@@ -8,7 +8,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import __graft_entry__ as g  # noqa: E402
 
 L = 2**252 + 27742317777372353535851937790883648493
