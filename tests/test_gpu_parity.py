@@ -449,9 +449,9 @@ def test_empty_and_tiny_batches(engine):
 
 
 def test_chunked_batch_boundary(engine):
-    """Batches larger than the library's internal chunk (2^20 elements) cross a chunk boundary correctly."""
+    """Batches larger than the library's internal chunk (2^22 elements for fixed-base batches) cross a chunk boundary correctly."""
     rng = np.random.default_rng(31)
-    n = (1 << 20) + 77
+    n = (1 << 22) + 77
     s = _rand_scalars(rng, n)
     s[:, 4:] = 0                       # 32-bit scalars keep the check cheap: compare against a second call on slices
     out, st = engine.fixed_base(0, s)
@@ -464,6 +464,25 @@ def test_chunked_batch_boundary(engine):
     out2, _ = engine.fixed_base(1, s2)
     assert (out2 == out2[0]).all()
     assert out2[0].tobytes() == R.compress(R.mul(int.from_bytes(s[0].tobytes(), "little"), R.PEDERSEN_H))
+
+
+def test_update_account_across_pipeline_slices_and_chunks(engine):
+    """qq_update_account_batch pipelines 2^18-account slices (upload / kernels / download on three streams) and the
+    core processes 2^20-account chunks: elements around every boundary must equal the C oracle, status stays per element."""
+    import c_oracle as C
+    rng = np.random.default_rng(32)
+    n = (1 << 20) + (1 << 18) + 5
+    base = [engine.fixed_base(0, _rand_scalars(rng, 4096))[0] for _ in range(4)]
+    acc = np.tile(np.concatenate(base, axis=1), ((n + 4095) // 4096, 1))[:n].copy()
+    bl, u, c = _rand_scalars(rng, n), _rand_scalars(rng, n), _rand_scalars(rng, n)
+    bad = (1 << 18) + 1
+    acc[bad, :32] = np.frombuffer(invalid_encodings()[0][1], np.uint8)
+    out, st = engine.update_account(acc, bl, u, c)
+    assert st[bad] == 1 and not out[bad].any() and st.sum() == 1
+    idx = np.concatenate([np.arange(0, 24), np.arange((1 << 18) - 12, (1 << 18) + 12), np.arange((1 << 19) - 12, (1 << 19) + 12),
+                          np.arange((1 << 20) - 12, (1 << 20) + 12), np.arange((1 << 20) + (1 << 18) - 12, n)])
+    eo, es = C.update_account(acc[idx], bl[idx], u[idx], c[idx])
+    assert (st[idx] == es).all() and (out[idx] == eo).all()
 
 
 @pytest.mark.parametrize("W", [8, 13, 16, 19])
