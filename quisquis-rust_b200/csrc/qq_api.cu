@@ -329,6 +329,26 @@ static const uint8_t QQ_BASE_PK_BYTES[64] = {
     0x58, 0xe3, 0x0b, 0x6a, 0xa5, 0x82, 0xdd, 0x8d, 0xb6, 0xa6, 0x59, 0x45, 0xe0, 0x8d, 0x2d, 0x76,
     0x8c, 0x92, 0x40, 0xb4, 0x56, 0xa9, 0xe6, 0xdc, 0x65, 0xc3, 0x77, 0xa1, 0x04, 0x8d, 0x74, 0x5f,
     0x94, 0xa0, 0x8c, 0xdb, 0x7f, 0x44, 0xcb, 0xcd, 0x7b, 0x46, 0xf3, 0x40, 0x48, 0x87, 0x11, 0x34};
+// device buffers released on every exit path of a builder function
+struct dev_bufs {
+    std::vector<void*> p;
+    template <class T>
+    cudaError_t alloc(T** out, size_t bytes) {
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, bytes ? bytes : 16);
+        if (e == cudaSuccess) p.push_back(q);
+        *out = (T*)q;
+        return e;
+    }
+    void release(void* keep) {   // hand one buffer over to the caller
+        for (auto& q : p)
+            if (q == keep) q = nullptr;
+    }
+    ~dev_bufs() {
+        for (void* q : p)
+            if (q) cudaFree(q);
+    }
+};
 static int fbt_build(qq_ctx* ctx, int which, int W) {
     if (ctx->fbt[which]) {
         CK(cudaStreamSynchronize(ctx->stream));
@@ -342,20 +362,21 @@ static int fbt_build(qq_ctx* ctx, int which, int W) {
     g.NW = (255 + W - 1) / W;
     g.ENT = (1u << (W - 1)) + 1u;
     size_t entries = (size_t)g.NW * g.ENT;
+    dev_bufs bufs;
     u32x4* tbl = nullptr;
-    CK(cudaMalloc((void**)&tbl, entries * QQ_NIELS_STRIDE_Q * 16));
+    CK(bufs.alloc(&tbl, entries * QQ_NIELS_STRIDE_Q * 16));
     const unsigned int SLICE = 1u << 22;
     size_t slice = g.ENT < SLICE ? g.ENT : SLICE;
     u32x4 *dbase = nullptr, *bases = nullptr, *ext = nullptr;
     dc_ws d;
     d.state = nullptr; d.zflag = nullptr;
-    CK(cudaMalloc((void**)&dbase, 64));
-    CK(cudaMalloc((void**)&bases, (size_t)g.NW * QQ_PT_BYTES));
-    CK(cudaMalloc((void**)&ext, slice * QQ_PT_BYTES));
-    CK(cudaMalloc((void**)&d.w, slice * 32));
-    CK(cudaMalloc((void**)&d.prefix, slice * 32));
-    CK(cudaMalloc((void**)&d.lv_vals, dc_levels_q(slice) * 16));
-    CK(cudaMalloc((void**)&d.lv_prefix, dc_levels_q(slice) * 16));
+    CK(bufs.alloc(&dbase, 64));
+    CK(bufs.alloc(&bases, (size_t)g.NW * QQ_PT_BYTES));
+    CK(bufs.alloc(&ext, slice * QQ_PT_BYTES));
+    CK(bufs.alloc(&d.w, slice * 32));
+    CK(bufs.alloc(&d.prefix, slice * 32));
+    CK(bufs.alloc(&d.lv_vals, dc_levels_q(slice) * 16));
+    CK(bufs.alloc(&d.lv_prefix, dc_levels_q(slice) * 16));
     CK(cudaMemcpyAsync(dbase, QQ_BASE_PK_BYTES, 64, cudaMemcpyHostToDevice, ctx->stream));
     k_fbt_window_bases<<<1, 32, 0, ctx->stream>>>(dbase + 2 * which, g, bases);
     ctx->launches++;
@@ -372,7 +393,7 @@ static int fbt_build(qq_ctx* ctx, int which, int W) {
     }
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
-    cudaFree(dbase); cudaFree(bases); cudaFree(ext); cudaFree(d.w); cudaFree(d.prefix); cudaFree(d.lv_vals); cudaFree(d.lv_prefix);
+    bufs.release(tbl);
     ctx->fbt[which] = tbl;
     ctx->fbt_g[which] = g;
     return QQ_OK;
