@@ -71,8 +71,9 @@ struct vb_args {
 // drift apart (they do, through table-load latency) each fetch their own copy of it and the kernel stalls on
 // instruction fetch: ncu `no_instruction` 3 % at 7 items per thread, 13 % at 55, with the multiply pipe dropping from
 // 78 % to 71 % active.  With the barrier the rate is independent of the batch size: 5.06e7 -> 6.18e7 scalar-mults/s at
-// 2^21 points (tools/vb_bench.cu, profiles/vb_bench_sync_r01.jsonl).  Every thread runs the same number of rounds;
-// threads past the end redo the last item and do not store.
+// 2^21 points (tools/vb_bench.cu, profiles/vb_bench_sync_r01.jsonl).  Every thread runs the same number of rounds
+// (the barrier sits at the top of the round; threads past the end skip the work, so a 9-account call is not slowed
+// down by 500 idle lanes repeating it).
 #define QQ_VB_BLOCK 512
 template <int NS>
 __global__ void __launch_bounds__(QQ_VB_BLOCK, 1) k_varbase(vb_args a) {
@@ -82,9 +83,8 @@ __global__ void __launch_bounds__(QQ_VB_BLOCK, 1) k_varbase(vb_args a) {
     size_t rounds = (a.n + stride - 1) / stride;
     for (size_t it = 0; it < rounds; it++) {
         size_t t = gtid + it * stride;
-        bool live = t < a.n;
-        if (!live) t = a.n - 1;
         __syncthreads();
+        if (t >= a.n) continue;      // still meets the barrier of every later round
         ge_p3 p, r;
         ge_p3_load(p, a.pts + QQ_PT_Q * map_index(a.map, t));
         vb_build_table(tbl, p);
@@ -92,12 +92,12 @@ __global__ void __launch_bounds__(QQ_VB_BLOCK, 1) k_varbase(vb_args a) {
         load_words32(s, a.s0, t / (size_t)a.sdiv);
         if (a.halve0) sc_halve(s, s);
         vb_scalarmult(r, tbl, s);
-        if (live) ge_p3_store(a.out0 + QQ_PT_Q * t, r);
+        ge_p3_store(a.out0 + QQ_PT_Q * t, r);
         if (NS == 2) {
             load_words32(s, a.s1, t / (size_t)a.sdiv);
             if (a.halve1) sc_halve(s, s);
             vb_scalarmult(r, tbl, s);
-            if (live) ge_p3_store(a.out1 + QQ_PT_Q * t, r);
+            ge_p3_store(a.out1 + QQ_PT_Q * t, r);
         }
     }
 }
@@ -111,9 +111,8 @@ __global__ void __launch_bounds__(QQ_VB_BLOCK, 1) k_varbase_split(vb_args a) {
     size_t rounds = (a.n + stride - 1) / stride;
     for (size_t it = 0; it < rounds; it++) {
         size_t t = gtid + it * stride;
-        bool live = t < a.n;
-        if (!live) t = a.n - 1;
         __syncthreads();
+        if (t >= a.n) continue;      // still meets the barrier of every later round
         ge_p3 p, r;
         ge_p3_load(p, a.pts + QQ_PT_Q * map_index(a.map, t));
         vbs_build_tables(tbl, p);
@@ -121,11 +120,11 @@ __global__ void __launch_bounds__(QQ_VB_BLOCK, 1) k_varbase_split(vb_args a) {
         load_words32(s, a.s0, t / (size_t)a.sdiv);
         if (a.halve0) sc_halve(s, s);
         vbs_scalarmult(r, tbl, s);
-        if (live) ge_p3_store(a.out0 + QQ_PT_Q * t, r);
+        ge_p3_store(a.out0 + QQ_PT_Q * t, r);
         load_words32(s, a.s1, t / (size_t)a.sdiv);
         if (a.halve1) sc_halve(s, s);
         vbs_scalarmult(r, tbl, s);
-        if (live) ge_p3_store(a.out1 + QQ_PT_Q * t, r);
+        ge_p3_store(a.out1 + QQ_PT_Q * t, r);
     }
 }
 

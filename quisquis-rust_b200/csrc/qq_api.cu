@@ -172,11 +172,18 @@ static int launch_varbase(qq_ctx* ctx, int ns, const u32x4* pts, idx_map map, co
     a.pts = pts; a.map = map; a.s0 = (const u32x4*)s0; a.s1 = (const u32x4*)s1; a.sdiv = sdiv;
     a.halve0 = halve0; a.halve1 = halve1;
     a.out0 = out0; a.out1 = out1; a.scratch = scratch; a.n = n;
+    // large batches: one 512-thread block per SM (lockstep, see kernels.cuh).  Small batches are latency-bound chains:
+    // narrower blocks spread the few warps over all schedulers (one warp per scheduler up to 4 * sms warps).
+    int block = QQ_VB_BLOCK;
     int grid = ctx->sms * ctx->vb_blocks_per_sm[ns];
+    if ((size_t)grid * QQ_VB_BLOCK > n) {
+        block = 32;
+        while (block < QQ_VB_BLOCK && (n + block - 1) / block > (size_t)ctx->sms * 4) block *= 2;
+        grid = (int)((n + block - 1) / block);
+    }
     span_begin(ctx, FAM_VB);
-    if ((size_t)grid * QQ_VB_BLOCK > n) grid = (int)((n + QQ_VB_BLOCK - 1) / QQ_VB_BLOCK);
-    if (ns == 1) k_varbase<1><<<grid, QQ_VB_BLOCK, 0, ctx->stream>>>(a);
-    else k_varbase_split<<<grid, QQ_VB_BLOCK, 0, ctx->stream>>>(a);
+    if (ns == 1) k_varbase<1><<<grid, block, 0, ctx->stream>>>(a);
+    else k_varbase_split<<<grid, block, 0, ctx->stream>>>(a);
     span_end(ctx);
     ctx->launches++;
     CK(cudaGetLastError());
