@@ -604,8 +604,14 @@ def test_hash_to_group_and_generator_derivation(engine):
     u[0] = 0
     u[1] = 0xff
     u[2] = np.frombuffer(hashlib.sha3_512(R.BASEPOINT_COMPRESSED).digest(), np.uint8)
+    import json, os
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "rfc9496.json")))["hash_to_group_sha512"]
+    for i, v in enumerate(gold):                  # RFC 9496 Appendix A.3 hash-to-group vectors
+        u[3 + i] = np.frombuffer(hashlib.sha512(v["label"].encode()).digest(), np.uint8)
     out = engine.from_uniform_bytes(u)
     assert out[2].tobytes() == R.PEDERSEN_H_COMPRESSED
+    for i, v in enumerate(gold):
+        assert out[3 + i].tobytes().hex() == v["encoding"]
     for i in range(300):
         assert out[i].tobytes() == R.compress(R.from_uniform_bytes(u[i].tobytes())), i
     for cap in (2, 3, 9):

@@ -210,6 +210,11 @@ def test_from_uniform_bytes_elligator(hh):
     o = ctypes.create_string_buffer(32)
     hh.hh_from_uniform(o, hashlib.sha3_512(R.BASEPOINT_COMPRESSED).digest())
     assert o.raw == R.PEDERSEN_H_COMPRESSED
+    import json, os
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "rfc9496.json")))
+    for v in gold["hash_to_group_sha512"]:      # RFC 9496 Appendix A.3
+        hh.hh_from_uniform(o, hashlib.sha512(v["label"].encode()).digest())
+        assert o.raw.hex() == v["encoding"]
     rnd = random.Random(18)
     for i in range(60):
         b = bytes(64) if i == 0 else (b"\xff" * 64 if i == 1 else rnd.randbytes(64))

@@ -44,6 +44,14 @@ def test_rfc9496_invalid_encodings():
     assert {"non_square", "negative_t", "negative_s", "bit255_set", "non_canonical_p"} <= names
 
 
+def test_rfc9496_hash_to_group_vectors():
+    """RFC 9496 Appendix A.3: enc(from_uniform_bytes(SHA-512(label))) -- pins the Elligator map of the oracle."""
+    import hashlib
+    assert len(GOLD["hash_to_group_sha512"]) == 6
+    for v in GOLD["hash_to_group_sha512"]:
+        assert R.compress(R.from_uniform_bytes(hashlib.sha512(v["label"].encode()).digest())).hex() == v["encoding"]
+
+
 def test_reference_base_pk_constants():
     """src/ristretto/constants.rs:12-21: [0] = enc(B), [1] = from_uniform_bytes(SHA3-512(enc(B))) = Pedersen H."""
     assert R.BASEPOINT_COMPRESSED.hex() == GOLD["base_pk_btc_compressed"][0] == bytes(
