@@ -42,6 +42,7 @@ extern "C" {
 #define QQ_ST_BAD_SCALAR 2  /* a scalar was not canonical (>= l) */
 #define QQ_ST_KEYPAIR 3     /* Err("Invalid Account::Keypair Verification Failed") / `false` */
 #define QQ_ST_COMMIT 4      /* Err("Invalid Account::Commitment Verification Failed") / identity check failed */
+#define QQ_ST_PROOF 6       /* a sigma-protocol challenge did not match: Err("DLOG Proof Verify: Failed") and its siblings */
 #define QQ_ST_NOT_FOUND 5   /* decommit_value: no v below 2^search_bits (the reference would keep searching up to 2^64) */
 
 #define QQ_BASE_B 0 /* Ristretto basepoint, BASE_PK_BTC_COMPRESSED[0] (src/ristretto/constants.rs:13-16) */
@@ -180,6 +181,19 @@ int qq_points_sum(qq_ctx* ctx, const uint8_t* xyzt, size_t k, uint8_t* out_point
  * instance j covers terms offsets[j] .. offsets[j+1]-1 ; out m x 32 B ; status m */
 int qq_msm_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* points, const uint32_t* offsets, size_t m,
                      uint8_t* out_points, uint8_t* status);
+
+/* ---- sigma-protocol verification ----------------------------------------------------------------------------------
+ * Verifier::verify_update_account_verifier (src/accounts/verifier.rs:223-292) for `nproofs` independent proofs over n
+ * accounts each.  input_accounts / delta_accounts: nproofs x n x 128 B (updated_input_accounts, updated_delta_accounts),
+ * z: nproofs x n x 32 B, x: nproofs x 32 B.  Every proof is checked under Transcript::new(transcript_label) followed
+ * by Verifier::new(verifier_label, ..) (the reference's test uses b"UpdateAccount", b"DLOGProof", verifier.rs:1049-1072).
+ * status[p]: QQ_ST_OK = Ok(()), QQ_ST_PROOF = Err("DLOG Proof Verify: Failed"), QQ_ST_BAD_POINT where the reference
+ * panics / returns that Err on an undecodable point, QQ_ST_BAD_SCALAR for a non-canonical z or x.
+ * The 2 n commitments of every proof are computed on the GPU as 3-term MSMs; the Fiat-Shamir transcript (Merlin,
+ * STROBE-128) runs on the host. */
+int qq_verify_update_account_dlog_batch(qq_ctx* ctx, const char* transcript_label, const char* verifier_label,
+                                        const uint8_t* input_accounts, const uint8_t* delta_accounts, const uint8_t* z,
+                                        const uint8_t* x, size_t n, size_t nproofs, uint8_t* status);
 
 /* ---- decommit ------------------------------------------------------------------------------------------------------
  * ElGamalCommitment::decommit(sk) = enc(d - sk*c) = enc(v*B)                    src/elgamal/elgamal.rs:106-108 */

@@ -7,7 +7,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 QQ_OK = 0
-ST_OK, ST_BAD_POINT, ST_BAD_SCALAR, ST_KEYPAIR, ST_COMMIT = 0, 1, 2, 3, 4
+ST_OK, ST_BAD_POINT, ST_BAD_SCALAR, ST_KEYPAIR, ST_COMMIT, ST_NOT_FOUND, ST_PROOF = 0, 1, 2, 3, 4, 5, 6
 BASE_B, BASE_H = 0, 1
 
 EXPORTS = [
@@ -22,7 +22,7 @@ EXPORTS = [
     "qq_fixed_base_i64_batch", "qq_fixed_base_i64_batch_dev", "qq_msm", "qq_msm_dev", "qq_msm_partial", "qq_msm_partial_dev",
     "qq_points_sum", "qq_msm_segmented", "qq_msm_points_prepare", "qq_msm_points_prepare_dev", "qq_msm_points_free",
     "qq_msm_points_count", "qq_msm_prepared", "qq_msm_prepared_dev",
-    "qq_decommit_batch", "qq_decommit_value_batch", "qq_from_uniform_bytes_batch", "qq_vector_pedersen_gens", "qq_bulletproof_gens",
+    "qq_verify_update_account_dlog_batch", "qq_decommit_batch", "qq_decommit_value_batch", "qq_from_uniform_bytes_batch", "qq_vector_pedersen_gens", "qq_bulletproof_gens",
 ]
 
 
@@ -88,6 +88,7 @@ def load_library():
     lib.qq_points_sum.argtypes = [vp, u8p, sz, u8p, u8p]
     for name in ("qq_msm_points_prepare", "qq_msm_points_prepare_dev"):
         getattr(lib, name).argtypes = [vp, u8p, sz, ctypes.POINTER(vp)]
+    lib.qq_verify_update_account_dlog_batch.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, u8p, u8p, u8p, u8p, sz, sz, u8p]
     lib.qq_decommit_batch.argtypes = [vp, u8p, u8p, u8p, u8p, sz]
     lib.qq_decommit_value_batch.argtypes = [vp, u8p, u8p, ctypes.c_int, u8p, u8p, sz]
     lib.qq_from_uniform_bytes_batch.argtypes = [vp, u8p, u8p, sz]
@@ -109,6 +110,8 @@ def load_library():
 
 
 def _u8(a, nbytes=None):
+    if isinstance(a, (bytes, bytearray, memoryview)):
+        a = np.frombuffer(bytes(a), dtype=np.uint8)
     a = np.ascontiguousarray(a, dtype=np.uint8).reshape(-1)
     if nbytes is not None and a.size != nbytes:
         raise ValueError("expected %d bytes, got %d" % (nbytes, a.size))
@@ -323,6 +326,18 @@ class Engine:
         out, st = np.zeros(32, np.uint8), np.zeros(1, np.uint8)
         self._ck(self.lib.qq_msm_prepared(self.h, _ptr(scalars), handle, n, _ptr(out), _ptr(st)), "qq_msm_prepared")
         return out, int(st[0])
+
+    def verify_update_account_dlog(self, input_accounts, delta_accounts, z, x, n, transcript_label=b"UpdateAccount",
+                                   verifier_label=b"DLOGProof"):
+        """Verifier::verify_update_account_verifier for x.size // 32 proofs of n accounts each -> status per proof."""
+        ia, da, z, x = _u8(input_accounts), _u8(delta_accounts), _u8(z), _u8(x)
+        nproofs = x.size // 32
+        _u8(ia, nproofs * n * 128), _u8(da, nproofs * n * 128), _u8(z, nproofs * n * 32)
+        st = np.zeros(nproofs, np.uint8)
+        self._ck(self.lib.qq_verify_update_account_dlog_batch(self.h, transcript_label, verifier_label, _ptr(ia), _ptr(da),
+                                                               _ptr(z), _ptr(x), n, nproofs, _ptr(st)),
+                 "qq_verify_update_account_dlog_batch")
+        return st
 
     def decommit(self, comm, sk):
         comm, sk = _u8(comm), _u8(sk)

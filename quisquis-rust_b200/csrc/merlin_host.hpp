@@ -1,0 +1,171 @@
+// Merlin transcripts on the HOST: STROBE-128 over Keccak-f[1600] (merlin.cool; crate `merlin`, a dependency of the
+// reference: src/accounts/transcript.rs:10) and the reference's TranscriptProtocol extension (transcript.rs:55-82).
+// Fiat-Shamir hashing is a sequential sponge over a few kilobytes per proof: host code.  The group arithmetic that
+// produces the points it absorbs (the sigma-protocol commitments, 2-3-term MSMs) runs on the GPU.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+
+#include "keccak_host.hpp"
+
+namespace qq_merlin {
+
+class strobe128 {
+    static const int R = 166;
+    enum { FLAG_I = 1, FLAG_A = 2, FLAG_C = 4, FLAG_T = 8, FLAG_M = 16, FLAG_K = 32 };
+    uint8_t st[200];
+    uint8_t pos, pos_begin, cur_flags;
+
+    void permute() {
+        uint64_t a[25];
+        memcpy(a, st, 200);   // little-endian host (x86-64 / aarch64 LE)
+        qq_keccak::f1600(a);
+        memcpy(st, a, 200);
+    }
+    void run_f() {
+        st[pos] ^= pos_begin;
+        st[pos + 1] ^= 0x04;
+        st[R + 1] ^= 0x80;
+        permute();
+        pos = 0;
+        pos_begin = 0;
+    }
+    void absorb(const uint8_t* d, size_t n) {
+        for (size_t i = 0; i < n; i++) {
+            st[pos++] ^= d[i];
+            if (pos == R) run_f();
+        }
+    }
+    void squeeze(uint8_t* d, size_t n) {
+        for (size_t i = 0; i < n; i++) {
+            d[i] = st[pos];
+            st[pos++] = 0;
+            if (pos == R) run_f();
+        }
+    }
+    void begin_op(uint8_t flags, bool more) {
+        if (more) return;   // continuation of the current operation (same flags by construction)
+        uint8_t old_begin = pos_begin;
+        pos_begin = (uint8_t)(pos + 1);
+        cur_flags = flags;
+        uint8_t hdr[2] = {old_begin, flags};
+        absorb(hdr, 2);
+        if ((flags & (FLAG_C | FLAG_K)) && pos != 0) run_f();
+    }
+
+  public:
+    explicit strobe128(const char* protocol_label) : pos(0), pos_begin(0), cur_flags(0) {
+        memset(st, 0, sizeof st);
+        const uint8_t init[6] = {1, R + 2, 1, 0, 1, 96};
+        memcpy(st, init, 6);
+        memcpy(st + 6, "STROBEv1.0.2", 12);
+        permute();
+        meta_ad((const uint8_t*)protocol_label, strlen(protocol_label), false);
+    }
+    void meta_ad(const uint8_t* d, size_t n, bool more) {
+        begin_op(FLAG_M | FLAG_A, more);
+        absorb(d, n);
+    }
+    void ad(const uint8_t* d, size_t n, bool more) {
+        begin_op(FLAG_A, more);
+        absorb(d, n);
+    }
+    void prf(uint8_t* d, size_t n, bool more) {
+        begin_op(FLAG_I | FLAG_A | FLAG_C, more);
+        squeeze(d, n);
+    }
+};
+
+// merlin::Transcript + the reference's TranscriptProtocol
+class transcript {
+    strobe128 s;
+
+  public:
+    transcript(const uint8_t* label, size_t n) : s("Merlin v1.0") { append_message("dom-sep", label, n); }
+    void append_message(const char* label, const uint8_t* msg, size_t n) {
+        s.meta_ad((const uint8_t*)label, strlen(label), false);
+        uint8_t len[4] = {(uint8_t)n, (uint8_t)(n >> 8), (uint8_t)(n >> 16), (uint8_t)(n >> 24)};
+        s.meta_ad(len, 4, true);
+        s.ad(msg, n, false);
+    }
+    void challenge_bytes(const char* label, uint8_t* out, size_t n) {
+        s.meta_ad((const uint8_t*)label, strlen(label), false);
+        uint8_t len[4] = {(uint8_t)n, (uint8_t)(n >> 8), (uint8_t)(n >> 16), (uint8_t)(n >> 24)};
+        s.meta_ad(len, 4, true);
+        s.prf(out, n, false);
+    }
+    void domain_sep(const char* label) { append_message("dom-sep", (const uint8_t*)label, strlen(label)); }
+    void append_point_var(const char* label, const uint8_t point[32]) {
+        append_message("ptvar", (const uint8_t*)label, strlen(label));
+        append_message("val", point, 32);
+    }
+    void append_scalar_var(const char* label, const uint8_t scalar[32]) { append_message(label, scalar, 32); }
+    void append_account_var(const char* label, const uint8_t acc[128]) {
+        append_message("acvar", (const uint8_t*)label, strlen(label));
+        append_message("gr", acc, 32);
+        append_message("grsk", acc + 32, 32);
+        append_message("commc", acc + 64, 32);
+        append_message("commd", acc + 96, 32);
+    }
+    // get_challenge: 64 challenge bytes reduced mod l (Scalar::from_bytes_mod_order_wide), canonical 32 bytes out
+    void get_challenge(const char* label, uint8_t out[32]);
+};
+
+// ---- scalars mod l on the host (only what the verifiers need: wide reduction, negation) --------------------------------
+static const uint64_t L_WORDS[4] = {0x5812631a5cf5d3edULL, 0x14def9dea2f79cd6ULL, 0ULL, 0x1000000000000000ULL};
+
+// r = x mod l for a 512-bit little-endian x: binary long division (512 shift-compare-subtract steps; a few hundred ns)
+static inline void sc_reduce_wide(uint8_t out[32], const uint8_t in[64]) {
+    uint64_t r[5] = {0, 0, 0, 0, 0};
+    for (int bit = 511; bit >= 0; bit--) {
+        // r = 2 r + bit
+        for (int i = 4; i > 0; i--) r[i] = (r[i] << 1) | (r[i - 1] >> 63);
+        r[0] = (r[0] << 1) | ((in[bit >> 3] >> (bit & 7)) & 1);
+        // if r >= l: r -= l      (r < 2 l < 2^254 always)
+        bool ge = r[4] != 0;
+        if (!ge) {
+            ge = true;
+            for (int i = 3; i >= 0; i--) {
+                if (r[i] != L_WORDS[i]) {
+                    ge = r[i] > L_WORDS[i];
+                    break;
+                }
+            }
+        }
+        if (ge) {
+            unsigned __int128 borrow = 0;
+            for (int i = 0; i < 4; i++) {
+                unsigned __int128 d = (unsigned __int128)r[i] - L_WORDS[i] - (uint64_t)borrow;
+                r[i] = (uint64_t)d;
+                borrow = (d >> 64) & 1;
+            }
+            r[4] -= (uint64_t)borrow;
+        }
+    }
+    memcpy(out, r, 32);
+}
+// out = -s mod l for canonical s
+static inline void sc_negate(uint8_t out[32], const uint8_t s[32]) {
+    uint64_t a[4];
+    memcpy(a, s, 32);
+    if ((a[0] | a[1] | a[2] | a[3]) == 0) {
+        memset(out, 0, 32);
+        return;
+    }
+    unsigned __int128 borrow = 0;
+    uint64_t r[4];
+    for (int i = 0; i < 4; i++) {
+        unsigned __int128 d = (unsigned __int128)L_WORDS[i] - a[i] - (uint64_t)borrow;
+        r[i] = (uint64_t)d;
+        borrow = (d >> 64) & 1;
+    }
+    memcpy(out, r, 32);
+}
+inline void transcript::get_challenge(const char* label, uint8_t out[32]) {
+    uint8_t wide[64];
+    challenge_bytes(label, wide, 64);
+    sc_reduce_wide(out, wide);
+}
+
+}  // namespace qq_merlin

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/qq_b200.h"
@@ -14,6 +15,7 @@
 #include "compress_batch.cuh"
 #include "fixedbase_big.cuh"
 #include "keccak_host.hpp"
+#include "merlin_host.hpp"
 #include "decommit.cuh"
 
 using namespace qq;

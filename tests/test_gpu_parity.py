@@ -692,3 +692,49 @@ def test_fixed_base_signed_64_bit_values(engine, W):
     finally:
         for which in (0, 1):
             engine.fixed_base_set_window(which, old[which])
+
+
+def test_verify_update_account_dlog_proofs(engine):
+    """Verifier::verify_update_account_verifier, batched.  Replays the reference's scenario (verifier.rs:1006-1072):
+    9 updated accounts, values [-5, 5, 0 x 7], delta accounts, the anonymity-set slice [2..9]; the proofs come from the
+    oracle's restatement of the prover; accept / reject verdicts must match the oracle's verifier, proof by proof."""
+    import sigma_ref as S
+    st = Stream(b"dlog-proof")
+    proofs = []
+    for p in range(6):
+        vals = [R.L - 5, 5] + [0] * 7
+        accs = []
+        for _ in range(9):
+            acc, sk, k = make_account(st, 0)
+            upd, s = R.update_account(acc, sb(0), st.scalar_bytes(), st.scalar_bytes())
+            assert s == 0
+            accs.append(upd)
+        rs = [st.scalar() for _ in range(9)]
+        delta = [R.delta_epsilon(a, sb(v), sb(r))[0] for a, v, r in zip(accs, vals, rs)]
+        upd_delta = S.update_delta_accounts(accs, delta)
+        ia, da, r7 = accs[2:9], upd_delta[2:9], rs[2:9]
+        z, x = S.prove_update_account_dlog(ia, da, r7, st.scalar())
+        assert len(z) == 7 and S.verify_update_account_dlog(ia, da, z, x)
+        proofs.append([ia, da, z, x])
+    # tamper: a response, the challenge, an account key, and a non-anonymity-set account (value != 0) in the set
+    bad_z = [list(proofs[1][0]), list(proofs[1][1]), [proofs[1][2][0] + 1] + proofs[1][2][1:], proofs[1][3]]
+    bad_x = [proofs[2][0], proofs[2][1], proofs[2][2], proofs[2][3] + 1]
+    swapped = [list(proofs[3][0]), list(proofs[3][1]), proofs[3][2], proofs[3][3]]
+    swapped[0][0], swapped[0][1] = swapped[0][1], swapped[0][0]
+    cases = proofs + [bad_z, bad_x, swapped]
+    expect = [S.verify_update_account_dlog(*c) for c in cases]
+    assert expect == [True] * 6 + [False] * 3
+    ia = cat([cat(c[0]) for c in cases])
+    da = cat([cat(c[1]) for c in cases])
+    zz = cat([cat([sb(v % R.L) for v in c[2]]) for c in cases])
+    xx = cat([sb(c[3] % R.L) for c in cases])
+    got = engine.verify_update_account_dlog(ia, da, zz, xx, 7)
+    assert [int(s) for s in got] == [0 if e else 6 for e in expect]
+    # another transcript label -> every proof fails; undecodable point / non-canonical response -> their own codes
+    assert (engine.verify_update_account_dlog(ia, da, zz, xx, 7, transcript_label=b"Other") == 6).all()
+    ia2 = bytearray(ia)
+    ia2[64:96] = invalid_encodings()[0][1]
+    zz2 = bytearray(zz)
+    zz2[7 * 32:8 * 32] = R.L.to_bytes(32, "little")
+    got = engine.verify_update_account_dlog(bytes(ia2), da, bytes(zz2), xx, 7)
+    assert int(got[0]) == 1 and int(got[1]) == 2 and int(got[4]) == 0

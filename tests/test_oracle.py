@@ -52,6 +52,31 @@ def test_rfc9496_hash_to_group_vectors():
         assert R.compress(R.from_uniform_bytes(hashlib.sha512(v["label"].encode()).digest())).hex() == v["encoding"]
 
 
+def test_merlin_conformance_vector_and_sigma_round_trip():
+    """Merlin restatement pinned by the crate's published conformance vector; the DLOG sigma proof restatement
+    (prover.rs:264-343 / verifier.rs:223-292) accepts its own proofs and rejects tampered ones."""
+    import merlin_ref as M
+    import sigma_ref as S
+    t = M.Transcript(b"test protocol")
+    t.append_message(b"some label", b"some data")
+    assert t.challenge_bytes(b"challenge", 32).hex() == "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"
+    st = Stream(b"sigma-cpu")
+    n = 3
+    accs = [make_account(st, 0)[0] for _ in range(n)]
+    rs = [st.scalar() for _ in range(n)]
+    delta = []
+    for a, r in zip(accs, rs):
+        d, e = R.delta_epsilon(a, sb(0), sb(r))[:2]
+        delta.append(d)
+    upd_delta = S.update_delta_accounts(accs, delta)
+    z, x = S.prove_update_account_dlog(accs, upd_delta, rs, st.scalar())
+    assert len(z) == n
+    assert S.verify_update_account_dlog(accs, upd_delta, z, x)
+    assert not S.verify_update_account_dlog(accs, upd_delta, [z[0] + 1] + z[1:], x)
+    assert not S.verify_update_account_dlog(accs, upd_delta, z, x + 1)
+    assert not S.verify_update_account_dlog(accs, upd_delta, z, x, transcript_label=b"SomethingElse")
+
+
 def test_reference_base_pk_constants():
     """src/ristretto/constants.rs:12-21: [0] = enc(B), [1] = from_uniform_bytes(SHA3-512(enc(B))) = Pedersen H."""
     assert R.BASEPOINT_COMPRESSED.hex() == GOLD["base_pk_btc_compressed"][0] == bytes(
