@@ -195,6 +195,16 @@ int qq_verify_update_account_dlog_batch(qq_ctx* ctx, const char* transcript_labe
                                         const uint8_t* input_accounts, const uint8_t* delta_accounts, const uint8_t* z,
                                         const uint8_t* x, size_t n, size_t nproofs, uint8_t* status);
 
+/* Verifier::verify_delta_compact_verifier (src/accounts/verifier.rs:138-209; the reference's test uses the labels
+ * b"DeltaCompact", b"DLEQProof", verifier.rs:978-1002): delta and epsilon accounts commit to the same values.
+ * delta_accounts / epsilon_accounts: nproofs x n x 128 B; zv, zr1, zr2: nproofs x n x 32 B; x: nproofs x 32 B.
+ * status[p]: QQ_ST_OK = Ok(()), QQ_ST_PROOF = Err("Dleq Proof Verify: Failed"), QQ_ST_BAD_POINT =
+ * Err("Delta Compact Proof Verify: Failed"), QQ_ST_BAD_SCALAR for a non-canonical response or challenge. */
+int qq_verify_delta_compact_batch(qq_ctx* ctx, const char* transcript_label, const char* verifier_label,
+                                  const uint8_t* delta_accounts, const uint8_t* epsilon_accounts, const uint8_t* zv,
+                                  const uint8_t* zr1, const uint8_t* zr2, const uint8_t* x, size_t n, size_t nproofs,
+                                  uint8_t* status);
+
 /* ---- decommit ------------------------------------------------------------------------------------------------------
  * ElGamalCommitment::decommit(sk) = enc(d - sk*c) = enc(v*B)                    src/elgamal/elgamal.rs:106-108 */
 int qq_decommit_batch(qq_ctx* ctx, const uint8_t* comm, const uint8_t* sk, uint8_t* out_points, uint8_t* status, size_t n);

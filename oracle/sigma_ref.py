@@ -73,3 +73,58 @@ def verify_update_account_dlog(updated_input, updated_delta, z_vector, x, transc
         tr.append_point_var(b"commitmentgr", a)
         tr.append_point_var(b"commitmentgrsk", b)
     return tr.get_challenge(b"chal") == x % R.L
+
+
+# ---- "delta compact" DLEQ proof: prover src/accounts/prover.rs:120-254, verifier src/accounts/verifier.rs:138-209 ----
+def prove_delta_compact(delta_accounts, epsilon_accounts, rscalar, value_vector, blindings, transcript_label=b"DeltaCompact",
+                        prover_label=b"DLEQProof"):
+    """-> (zv[], zr1[], zr2[], x) as ints.  `blindings`: per account (r1', r2', v'') (the reference draws them from a
+    transcript RNG)."""
+    tr = Transcript(transcript_label)
+    tr.domain_sep(prover_label)
+    tr.domain_sep(b"VerifyDeltaCompact")
+    for d, e in zip(delta_accounts, epsilon_accounts):
+        tr.append_account_var(b"delta_account", d)
+        tr.append_account_var(b"epsilon_account", e)
+    for d, e, (r1, r2, vd) in zip(delta_accounts, epsilon_accounts, blindings):
+        gv = R.mul(vd % R.L, R.BASEPOINT)
+        e_delta = R.mul(r1 % R.L, R.decompress(d[0:32]))
+        f_delta = R.add(gv, R.mul(r1 % R.L, R.decompress(d[32:64])))
+        e_eps = R.mul(r2 % R.L, R.decompress(e[0:32]))
+        f_eps = R.add(gv, R.mul(r2 % R.L, R.decompress(e[32:64])))
+        tr.append_point_var(b"e_delta", R.compress(e_delta))
+        tr.append_point_var(b"f_delta", R.compress(f_delta))
+        tr.append_point_var(b"e_epsilon", R.compress(e_eps))
+        tr.append_point_var(b"f_epsilon", R.compress(f_eps))
+    x = tr.get_challenge(b"challenge")
+    zv = [(b[2] - v * x) % R.L for b, v in zip(blindings, value_vector)]
+    zr1 = [(b[0] - r * x) % R.L for b, r in zip(blindings, rscalar)]
+    zr2 = [(b[1] - r * x) % R.L for b, r in zip(blindings, rscalar)]
+    return zv, zr1, zr2, x
+
+
+def verify_delta_compact(delta_accounts, epsilon_accounts, zv, zr1, zr2, x, transcript_label=b"DeltaCompact",
+                         verifier_label=b"DLEQProof"):
+    tr = Transcript(transcript_label)
+    tr.domain_sep(verifier_label)
+    tr.domain_sep(b"VerifyDeltaCompact")
+    for d, e in zip(delta_accounts, epsilon_accounts):
+        tr.append_account_var(b"delta_account", d)
+        tr.append_account_var(b"epsilon_account", e)
+    xb = _scalar_bytes(x)
+    for d, e, v, r1, r2 in zip(delta_accounts, epsilon_accounts, zv, zr1, zr2):
+        pts = []
+        for acc, zr in ((d, r1), (e, r2)):
+            out, st = R.msm([_scalar_bytes(zr), xb], [acc[0:32], acc[64:96]])
+            if st:
+                return False
+            pts.append(out)
+            out, st = R.msm([_scalar_bytes(zr), xb, _scalar_bytes(v)], [acc[32:64], acc[96:128], R.BASEPOINT_COMPRESSED])
+            if st:
+                return False
+            pts.append(out)
+        tr.append_point_var(b"e_delta", pts[0])
+        tr.append_point_var(b"f_delta", pts[1])
+        tr.append_point_var(b"e_epsilon", pts[2])
+        tr.append_point_var(b"f_epsilon", pts[3])
+    return tr.get_challenge(b"challenge") == x % R.L

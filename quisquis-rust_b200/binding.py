@@ -22,7 +22,7 @@ EXPORTS = [
     "qq_fixed_base_i64_batch", "qq_fixed_base_i64_batch_dev", "qq_msm", "qq_msm_dev", "qq_msm_partial", "qq_msm_partial_dev",
     "qq_points_sum", "qq_msm_segmented", "qq_msm_points_prepare", "qq_msm_points_prepare_dev", "qq_msm_points_free",
     "qq_msm_points_count", "qq_msm_prepared", "qq_msm_prepared_dev",
-    "qq_verify_update_account_dlog_batch", "qq_decommit_batch", "qq_decommit_value_batch", "qq_from_uniform_bytes_batch", "qq_vector_pedersen_gens", "qq_bulletproof_gens",
+    "qq_verify_update_account_dlog_batch", "qq_verify_delta_compact_batch", "qq_decommit_batch", "qq_decommit_value_batch", "qq_from_uniform_bytes_batch", "qq_vector_pedersen_gens", "qq_bulletproof_gens",
 ]
 
 
@@ -89,6 +89,7 @@ def load_library():
     for name in ("qq_msm_points_prepare", "qq_msm_points_prepare_dev"):
         getattr(lib, name).argtypes = [vp, u8p, sz, ctypes.POINTER(vp)]
     lib.qq_verify_update_account_dlog_batch.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, u8p, u8p, u8p, u8p, sz, sz, u8p]
+    lib.qq_verify_delta_compact_batch.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, u8p, u8p, u8p, u8p, u8p, u8p, sz, sz, u8p]
     lib.qq_decommit_batch.argtypes = [vp, u8p, u8p, u8p, u8p, sz]
     lib.qq_decommit_value_batch.argtypes = [vp, u8p, u8p, ctypes.c_int, u8p, u8p, sz]
     lib.qq_from_uniform_bytes_batch.argtypes = [vp, u8p, u8p, sz]
@@ -337,6 +338,20 @@ class Engine:
         self._ck(self.lib.qq_verify_update_account_dlog_batch(self.h, transcript_label, verifier_label, _ptr(ia), _ptr(da),
                                                                _ptr(z), _ptr(x), n, nproofs, _ptr(st)),
                  "qq_verify_update_account_dlog_batch")
+        return st
+
+    def verify_delta_compact(self, delta_accounts, epsilon_accounts, zv, zr1, zr2, x, n, transcript_label=b"DeltaCompact",
+                             verifier_label=b"DLEQProof"):
+        """Verifier::verify_delta_compact_verifier for x.size // 32 proofs of n accounts each -> status per proof."""
+        da, ea, zv, zr1, zr2, x = (_u8(a) for a in (delta_accounts, epsilon_accounts, zv, zr1, zr2, x))
+        nproofs = x.size // 32
+        _u8(da, nproofs * n * 128), _u8(ea, nproofs * n * 128)
+        for a in (zv, zr1, zr2):
+            _u8(a, nproofs * n * 32)
+        st = np.zeros(nproofs, np.uint8)
+        self._ck(self.lib.qq_verify_delta_compact_batch(self.h, transcript_label, verifier_label, _ptr(da), _ptr(ea), _ptr(zv),
+                                                         _ptr(zr1), _ptr(zr2), _ptr(x), n, nproofs, _ptr(st)),
+                 "qq_verify_delta_compact_batch")
         return st
 
     def decommit(self, comm, sk):

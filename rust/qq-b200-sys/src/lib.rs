@@ -36,6 +36,7 @@ extern "C" {
     pub fn qq_msm_points_count(p: *const QqPrepared) -> usize;
     pub fn qq_msm_prepared(ctx: *mut QqCtx, scalars: *const u8, points: *const QqPrepared, n: usize, out: *mut u8, status: *mut u8) -> c_int;
     pub fn qq_verify_update_account_dlog_batch(ctx: *mut QqCtx, transcript_label: *const c_char, verifier_label: *const c_char, input_accounts: *const u8, delta_accounts: *const u8, z: *const u8, x: *const u8, n: usize, nproofs: usize, status: *mut u8) -> c_int;
+    pub fn qq_verify_delta_compact_batch(ctx: *mut QqCtx, transcript_label: *const c_char, verifier_label: *const c_char, delta_accounts: *const u8, epsilon_accounts: *const u8, zv: *const u8, zr1: *const u8, zr2: *const u8, x: *const u8, n: usize, nproofs: usize, status: *mut u8) -> c_int;
     pub fn qq_decommit_batch(ctx: *mut QqCtx, comm: *const u8, sk: *const u8, out: *mut u8, status: *mut u8, n: usize) -> c_int;
     pub fn qq_decommit_value_batch(ctx: *mut QqCtx, comm: *const u8, sk: *const u8, search_bits: c_int, out_values: *mut u64, status: *mut u8, n: usize) -> c_int;
     pub fn qq_from_uniform_bytes_batch(ctx: *mut QqCtx, uniform64: *const u8, out: *mut u8, n: usize) -> c_int;

@@ -738,3 +738,43 @@ def test_verify_update_account_dlog_proofs(engine):
     zz2[7 * 32:8 * 32] = R.L.to_bytes(32, "little")
     got = engine.verify_update_account_dlog(bytes(ia2), da, bytes(zz2), xx, 7)
     assert int(got[0]) == 1 and int(got[1]) == 2 and int(got[4]) == 0
+
+
+def test_verify_delta_compact_proofs(engine):
+    """Verifier::verify_delta_compact_verifier, batched; the reference's scenario (verifier.rs:938-1003): 9 accounts,
+    values [-5, 5, 0 x 7], delta + epsilon accounts from create_delta_and_epsilon_accounts; verdicts equal the oracle's."""
+    import sigma_ref as S
+    st = Stream(b"dleq-proof")
+    cases = []
+    for p in range(4):
+        vals = [R.L - 5, 5] + [0] * 7
+        accs = [make_account(st, 0)[0] for _ in range(9)]
+        rs = [st.scalar() for _ in range(9)]
+        de = [R.delta_epsilon(a, sb(v), sb(r)) for a, v, r in zip(accs, vals, rs)]
+        delta, eps = [d[0] for d in de], [d[1] for d in de]
+        blind = [(st.scalar(), st.scalar(), st.scalar()) for _ in range(9)]
+        zv, zr1, zr2, x = S.prove_delta_compact(delta, eps, rs, vals, blind)
+        assert S.verify_delta_compact(delta, eps, zv, zr1, zr2, x)
+        cases.append([delta, eps, zv, zr1, zr2, x])
+    # tampered: zv, zr2, challenge, and an epsilon account that commits to a different value
+    c = cases[0]
+    cases.append([c[0], c[1], [c[2][0] + 1] + c[2][1:], c[3], c[4], c[5]])
+    cases.append([c[0], c[1], c[2], c[3], c[4][:8] + [c[4][8] + 1], c[5]])
+    cases.append([c[0], c[1], c[2], c[3], c[4], c[5] + 1])
+    other_eps = list(cases[1][1])
+    other_eps[3] = R.delta_epsilon(make_account(st, 0)[0], sb(7), sb(st.scalar()))[1]
+    cases.append([cases[1][0], other_eps] + cases[1][2:])
+    expect = [S.verify_delta_compact(*k) for k in cases]
+    assert expect == [True] * 4 + [False] * 4
+
+    def pack(i):
+        return cat([cat([sb(v % R.L) for v in k[i]]) for k in cases])
+    da = cat([cat(k[0]) for k in cases])
+    ea = cat([cat(k[1]) for k in cases])
+    xx = cat([sb(k[5] % R.L) for k in cases])
+    got = engine.verify_delta_compact(da, ea, pack(2), pack(3), pack(4), xx, 9)
+    assert [int(s) for s in got] == [0 if e else 6 for e in expect]
+    ea2 = bytearray(ea)
+    ea2[32:64] = invalid_encodings()[1][1]
+    got = engine.verify_delta_compact(da, bytes(ea2), pack(2), pack(3), pack(4), xx, 9)
+    assert int(got[0]) == 1 and int(got[1]) == 0
