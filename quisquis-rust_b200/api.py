@@ -261,3 +261,35 @@ class Verifier:
         if v:
             raise ValueError("Identity sum verify: Failed")
         return None
+
+    @staticmethod
+    def verify_update_account_verifier(updated_input_accounts, updated_delta_accounts, z_vector, x,
+                                       transcript_label=b"UpdateAccount", verifier_label=b"DLOGProof"):
+        """src/accounts/verifier.rs:223-292.  The reference receives a `Verifier` carrying a transcript; here the two labels
+        that built it (Transcript::new / Verifier::new) are passed instead.  Returns None or raises ValueError(msg)."""
+        n = len(z_vector)
+        ia = b"".join(a.data for a in updated_input_accounts)
+        da = b"".join(a.data for a in updated_delta_accounts)
+        st = default_engine().verify_update_account_dlog(ia, da, b"".join(bytes(v) for v in z_vector), bytes(x), n,
+                                                          transcript_label, verifier_label)
+        if st[0] == B.ST_BAD_POINT:
+            raise PanicError("called `Option::unwrap()` on a `None` value")
+        if st[0]:
+            raise ValueError("DLOG Proof Verify: Failed")
+        return None
+
+    @staticmethod
+    def verify_delta_compact_verifier(delta_accounts, epsilon_accounts, zv_vector, zr1_vector, zr2_vector, x,
+                                      transcript_label=b"DeltaCompact", verifier_label=b"DLEQProof"):
+        """src/accounts/verifier.rs:138-209.  Returns None or raises ValueError with the reference's message."""
+        n = len(zv_vector)
+        da = b"".join(a.data for a in delta_accounts)
+        ea = b"".join(a.data for a in epsilon_accounts)
+        j = lambda v: b"".join(bytes(s) for s in v)  # noqa: E731
+        st = default_engine().verify_delta_compact(da, ea, j(zv_vector), j(zr1_vector), j(zr2_vector), bytes(x), n,
+                                                    transcript_label, verifier_label)
+        if st[0] == B.ST_BAD_POINT:
+            raise ValueError("Delta Compact Proof Verify: Failed")
+        if st[0]:
+            raise ValueError("Dleq Proof Verify: Failed")
+        return None

@@ -730,6 +730,16 @@ def test_verify_update_account_dlog_proofs(engine):
     xx = cat([sb(c[3] % R.L) for c in cases])
     got = engine.verify_update_account_dlog(ia, da, zz, xx, 7)
     assert [int(s) for s in got] == [0 if e else 6 for e in expect]
+    # the reference-shaped call (one proof, Result<(), &str>)
+    from quisquis_rust_b200 import api
+    api.set_default_engine(engine)
+    c = cases[0]
+    assert api.Verifier.verify_update_account_verifier([api.Account(a) for a in c[0]], [api.Account(a) for a in c[1]],
+                                                       [sb(v % R.L) for v in c[2]], sb(c[3] % R.L)) is None
+    with pytest.raises(ValueError, match="DLOG Proof Verify: Failed"):
+        c = cases[6]
+        api.Verifier.verify_update_account_verifier([api.Account(a) for a in c[0]], [api.Account(a) for a in c[1]],
+                                                    [sb(v % R.L) for v in c[2]], sb(c[3] % R.L))
     # another transcript label -> every proof fails; undecodable point / non-canonical response -> their own codes
     assert (engine.verify_update_account_dlog(ia, da, zz, xx, 7, transcript_label=b"Other") == 6).all()
     ia2 = bytearray(ia)
