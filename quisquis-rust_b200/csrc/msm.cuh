@@ -80,13 +80,41 @@ struct msm_geom {
 // PRE = true : the points were decompressed earlier by k_msm_points_prepare (generator sets reused across MSMs);
 //              only the scalars are recoded.  `pre_ok[i]` is the validity recorded then.
 template <bool PRE>
-__global__ void __launch_bounds__(256) k_msm_prepare(const u32x4* __restrict__ points, const u32x4* __restrict__ scalars,
+__global__ void __launch_bounds__(256, 2) k_msm_prepare(const u32x4* __restrict__ points, const u32x4* __restrict__ scalars,
                                                      size_t n, msm_geom g, u32x4* __restrict__ niels,
                                                      const uint8_t* __restrict__ pre_ok,
                                                      uint8_t* __restrict__ term_status, int16_t* __restrict__ digits,
                                                      unsigned int* __restrict__ slots, unsigned int* __restrict__ counts) {
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        // Scalar side first: the K histogram atomics (which also hand out each entry's position inside its bucket, so
+        // the scatter needs no atomics) are issued before the decompression and collected after it -- their round
+        // trips hide behind the square-root chain.  Digits do not depend on the point's validity: a bad term fails
+        // the whole MSM (status), whatever its bucket.
+        u32 s[8];
+        load_words32(s, scalars, i);
+        u32 canon = sc_is_canonical(s);
+        u32 r[9];
+        sc_recode_bias_rt(r, s, g.c, g.K);
+        unsigned int slot[16];
+        const bool fast = g.K <= 16;
+        if (fast) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                slot[k] = 0;
+                if (k < g.K) {
+                    int d = canon ? sc_digit_rt(r, g.c, k) : 0;
+                    digits[(size_t)k * n + i] = (int16_t)d;
+                    if (d != 0) slot[k] = atomicAdd(&counts[(size_t)k * g.NB + (size_t)((d < 0 ? -d : d) - 1)], 1u);
+                }
+            }
+        } else {
+            for (int k = 0; k < g.K; k++) {
+                int d = canon ? sc_digit_rt(r, g.c, k) : 0;
+                digits[(size_t)k * n + i] = (int16_t)d;
+                if (d != 0) slots[(size_t)k * n + i] = atomicAdd(&counts[(size_t)k * g.NB + (size_t)((d < 0 ? -d : d) - 1)], 1u);
+            }
+        }
         u32 ok;
         if (PRE) {
             ok = pre_ok[i];
@@ -99,18 +127,11 @@ __global__ void __launch_bounds__(256) k_msm_prepare(const u32x4* __restrict__ p
             ge_to_niels_z1(nl, p);
             niels_store_padded(niels + (size_t)QQ_NIELS_STRIDE_Q * i, nl);
         }
-        u32 s[8];
-        load_words32(s, scalars, i);
-        u32 canon = sc_is_canonical(s);
-        uint8_t st = canon ? (ok ? 0 : 1) : 2;
-        term_status[i] = st;
-        u32 r[9];
-        sc_recode_bias_rt(r, s, g.c, g.K);
-        for (int k = 0; k < g.K; k++) {
-            int d = st ? 0 : sc_digit_rt(r, g.c, k);
-            digits[(size_t)k * n + i] = (int16_t)d;
-            // the histogram increment also hands out this entry's position inside its bucket: the scatter needs no atomics
-            if (d != 0) slots[(size_t)k * n + i] = atomicAdd(&counts[(size_t)k * g.NB + (size_t)((d < 0 ? -d : d) - 1)], 1u);
+        term_status[i] = canon ? (ok ? 0 : 1) : 2;
+        if (fast) {
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                if (k < g.K) slots[(size_t)k * n + i] = slot[k];
         }
     }
 }
@@ -336,6 +357,11 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(const u32x4* __restrict_
         if (e + 1 < cnt) {
             cur = __ldg(ent + e + 1);
             niels_load_padded(nx, niels + (size_t)QQ_NIELS_STRIDE_Q * (cur & 0x7fffffffu));
+            if (e + 2 < cnt) {   // pull the point after that towards L2
+                const u32x4* pf = niels + (size_t)QQ_NIELS_STRIDE_Q * (__ldg(ent + e + 2) & 0x7fffffffu);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + 5));
+            }
         }
         ge_niels_cneg(nl, sign);
         ge_madd(acc, acc, nl);
@@ -456,10 +482,10 @@ struct msm_levels {
     int len[QQ_MSM_MAXLEVELS];
     unsigned int off[QQ_MSM_MAXLEVELS];
 };
-__global__ void __launch_bounds__(512) k_msm_sum_levels(const u32x4* __restrict__ w_all, msm_levels lv, int K,
+__global__ void __launch_bounds__(512) k_msm_sum_levels(const u32x4* __restrict__ w_all, msm_levels lv, int K, int l_first,
                                                         u32x4* __restrict__ sw) {
     extern __shared__ __align__(16) u32x4 sm[];   // blockDim.x points
-    int l = blockIdx.x / K, k = blockIdx.x - l * K;
+    int l = l_first + blockIdx.x / K, k = blockIdx.x % K;
     int row_len = lv.len[l];
     const u32x4* row = w_all + QQ_PT_Q * ((size_t)lv.off[l] + (size_t)k * row_len);
     ge_p3 acc;
@@ -484,7 +510,7 @@ __global__ void __launch_bounds__(512) k_msm_sum_levels(const u32x4* __restrict_
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) ge_p3_store(sw + QQ_PT_Q * blockIdx.x, acc);
+    if (threadIdx.x == 0) ge_p3_store(sw + QQ_PT_Q * ((size_t)l * K + k), acc);
 }
 // wins[k] = R_k + sum_l S^l SW_l[k]   (Horner over the levels: log2(S) doublings + one addition per level)
 __global__ void __launch_bounds__(128) k_msm_window_totals(const u32x4* __restrict__ sw, const u32x4* __restrict__ run_top,
