@@ -44,6 +44,7 @@ extern "C" {
 #define QQ_ST_COMMIT 4      /* Err("Invalid Account::Commitment Verification Failed") / identity check failed */
 #define QQ_ST_PROOF 6       /* a sigma-protocol challenge did not match: Err("DLOG Proof Verify: Failed") and its siblings */
 #define QQ_ST_NOT_FOUND 5   /* decommit_value: no v below 2^search_bits (the reference would keep searching up to 2^64) */
+#define QQ_ST_PANIC 7       /* an undecodable point where the reference `unwrap()`s (panics) although a neighbouring check of the same function returns Err */
 
 #define QQ_BASE_B 0 /* Ristretto basepoint, BASE_PK_BTC_COMPRESSED[0] (src/ristretto/constants.rs:13-16) */
 #define QQ_BASE_H 1 /* Pedersen H,         BASE_PK_BTC_COMPRESSED[1] (src/ristretto/constants.rs:17-20) */
@@ -204,6 +205,53 @@ int qq_verify_delta_compact_batch(qq_ctx* ctx, const char* transcript_label, con
                                   const uint8_t* delta_accounts, const uint8_t* epsilon_accounts, const uint8_t* zv,
                                   const uint8_t* zr1, const uint8_t* zr2, const uint8_t* x, size_t n, size_t nproofs,
                                   uint8_t* status);
+
+/* Verifier::verify_account_verifier_bulletproof (src/accounts/verifier.rs:396-470) = the sigma-protocol part of
+ * Verifier::verify_account_verifier (:305-381, whose R1CS range proof is outside this path): the senders know their
+ * secret keys and delta / epsilon accounts hold the same balance.  delta_accounts (updated_delta_account_sender),
+ * epsilon_accounts (account_epsilon_sender): nproofs x n x 128 B; base_pk: 64 B; zv, zsk, zr: nproofs x n x 32 B;
+ * x: nproofs x 32 B.  status[p]: QQ_ST_OK = Ok(()), QQ_ST_PROOF = Err("sender account verification failed"),
+ * QQ_ST_BAD_POINT = Err("Account Verify: Failed"), QQ_ST_BAD_SCALAR for a non-canonical response or challenge. */
+int qq_verify_account_sigma_batch(qq_ctx* ctx, const char* transcript_label, const char* verifier_label,
+                                  const uint8_t* delta_accounts, const uint8_t* epsilon_accounts, const uint8_t* base_pk,
+                                  const uint8_t* zv, const uint8_t* zsk, const uint8_t* zr, const uint8_t* x, size_t n,
+                                  size_t nproofs, uint8_t* status);
+
+/* Verifier::zero_balance_account_vector_verifier (src/accounts/verifier.rs:593-634) when vector_form != 0,
+ * Verifier::zero_balance_account_verifier (:647-680) when vector_form == 0 (n must be 1).  accounts: nproofs x n x 128 B,
+ * z: nproofs x n x 32 B, x: nproofs x 32 B.  The vector form keeps the reference verifier's domain separator
+ * b"ZeroBalanceAccounVectorProof" (:605; the prover writes b"ZeroBalanceAccountVectorProof", prover.rs:613, so the
+ * reference's verifier rejects its own prover's proofs - and so does this one).  status[p]: QQ_ST_OK,
+ * QQ_ST_PROOF = Err("Zero balance account verification failed"), QQ_ST_BAD_POINT = Err("Zero balance Account Verify: Failed"). */
+int qq_verify_zero_balance_batch(qq_ctx* ctx, const char* transcript_label, const char* verifier_label,
+                                 const uint8_t* accounts, const uint8_t* z, const uint8_t* x, size_t n, size_t nproofs,
+                                 int vector_form, uint8_t* status);
+
+/* Verifier::destroy_account_verifier (src/accounts/verifier.rs:693-735).  accounts: nproofs x n x 128 B, z: nproofs x n
+ * x 32 B, x: nproofs x 32 B.  status[p]: QQ_ST_OK, QQ_ST_PROOF = Err("Destroy account verification failed"),
+ * QQ_ST_BAD_POINT = Err("Destroy Account Verify: Failed"). */
+int qq_verify_destroy_account_batch(qq_ctx* ctx, const char* transcript_label, const char* verifier_label,
+                                    const uint8_t* accounts, const uint8_t* z, const uint8_t* x, size_t n, size_t nproofs,
+                                    uint8_t* status);
+
+/* Verifier::verify_same_value_compact_verifier (src/accounts/verifier.rs:747-806), one proof per element: enc_accounts
+ * nproofs x 128 B, commitments (Pedersen, PedersenGens::default()) nproofs x 32 B, zv / zr / x: nproofs x 32 B
+ * (SigmaProof::Dleq(zv[0], zr[0], _, x)).  The transcript labels are fixed inside the reference function.
+ * status[p]: QQ_ST_OK, QQ_ST_PROOF = Err("Same Value Proof Verify: Failed"), QQ_ST_BAD_POINT =
+ * Err("Delta Compact Proof Verify: Failed"). */
+int qq_verify_same_value_compact_batch(qq_ctx* ctx, const uint8_t* enc_accounts, const uint8_t* commitments,
+                                       const uint8_t* zv, const uint8_t* zr, const uint8_t* x, size_t nproofs,
+                                       uint8_t* status);
+
+/* Verifier::verify_update_account_dark_tx_verifier (src/accounts/verifier.rs:818-917; the reference's test uses the
+ * labels b"UpdateAccount", b"DLOGProof", :1075-1111).  delta_accounts (delta_updated_accounts), output_accounts:
+ * nproofs x n x 128 B; z: nproofs x 2 x 32 B (z_vector[0], z_vector[1]); x: nproofs x 32 B.  status[p]: QQ_ST_OK,
+ * QQ_ST_PROOF = Err("Update Output Challenge : DLOG Proof Verify: Failed"), QQ_ST_BAD_POINT = Err("Update Account: DLOG
+ * Proof Verify: Failed") (undecodable key), QQ_ST_PANIC where the reference panics (undecodable commitment in
+ * `d.comm - i.comm`, :862-866). */
+int qq_verify_update_account_dark_tx_batch(qq_ctx* ctx, const char* transcript_label, const char* verifier_label,
+                                           const uint8_t* delta_accounts, const uint8_t* output_accounts, const uint8_t* z,
+                                           const uint8_t* x, size_t n, size_t nproofs, uint8_t* status);
 
 /* ---- decommit ------------------------------------------------------------------------------------------------------
  * ElGamalCommitment::decommit(sk) = enc(d - sk*c) = enc(v*B)                    src/elgamal/elgamal.rs:106-108 */

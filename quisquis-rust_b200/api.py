@@ -293,3 +293,84 @@ class Verifier:
         if st[0]:
             raise ValueError("Dleq Proof Verify: Failed")
         return None
+
+    @staticmethod
+    def verify_account_verifier_bulletproof(updated_delta_account_sender, account_epsilon_sender, base_pk, zv, zsk, zr, x,
+                                            transcript_label=b"SenderAccountProof", verifier_label=b"DLOGProof"):
+        """src/accounts/verifier.rs:396-470 (and the sigma-protocol part of verify_account_verifier, :305-381)."""
+        n = len(zv)
+        j = lambda v: b"".join(bytes(s) for s in v)  # noqa: E731
+        st = default_engine().verify_account_sigma(b"".join(a.data for a in updated_delta_account_sender),
+                                                   b"".join(a.data for a in account_epsilon_sender), base_pk.data, j(zv),
+                                                   j(zsk), j(zr), bytes(x), n, transcript_label, verifier_label)
+        if st[0] == B.ST_BAD_POINT:
+            raise ValueError("Account Verify: Failed")
+        if st[0]:
+            raise ValueError("sender account verification failed")
+        return None
+
+    @staticmethod
+    def zero_balance_account_vector_verifier(anonymity_accounts, z, x, transcript_label=b"ZeroBalanceAccount",
+                                             verifier_label=b"DLOGProof"):
+        """src/accounts/verifier.rs:593-634 (domain separator spelled as the reference's verifier spells it)."""
+        assert len(anonymity_accounts) == len(z)
+        st = default_engine().verify_zero_balance(b"".join(a.data for a in anonymity_accounts),
+                                                  b"".join(bytes(s) for s in z), bytes(x), len(z), True, transcript_label,
+                                                  verifier_label)
+        if st[0] == B.ST_BAD_POINT:
+            raise ValueError("Zero balance Account Verify: Failed")
+        if st[0]:
+            raise ValueError("Zero balance account verification failed")
+        return None
+
+    @staticmethod
+    def zero_balance_account_verifier(account, z, x, transcript_label=b"ZeroBalanceAccount", verifier_label=b"DLOGProof"):
+        """src/accounts/verifier.rs:647-680."""
+        st = default_engine().verify_zero_balance(account.data, bytes(z), bytes(x), 1, False, transcript_label, verifier_label)
+        if st[0] == B.ST_BAD_POINT:
+            raise ValueError("Zero balance Account Verify: Failed")
+        if st[0]:
+            raise ValueError("Zero balance account verification failed")
+        return None
+
+    @staticmethod
+    def destroy_account_verifier(accounts, z, x, transcript_label=b"DestroyAccount", verifier_label=b"DLOGProof"):
+        """src/accounts/verifier.rs:693-735."""
+        assert len(accounts) == len(z)
+        st = default_engine().verify_destroy_account(b"".join(a.data for a in accounts), b"".join(bytes(s) for s in z),
+                                                     bytes(x), len(z), transcript_label, verifier_label)
+        if st[0] == B.ST_BAD_POINT:
+            raise ValueError("Destroy Account Verify: Failed")
+        if st[0]:
+            raise ValueError("Destroy account verification failed")
+        return None
+
+    @staticmethod
+    def verify_same_value_compact_verifier(enc_account, commitment, proof):
+        """src/accounts/verifier.rs:747-806.  proof = SigmaProof::Dleq as the tuple (zv[], zr[], _, x) of get_dleq()."""
+        zv, zr, _, x = proof
+        st = default_engine().verify_same_value_compact(enc_account.data, bytes(commitment), bytes(zv[0]), bytes(zr[0]),
+                                                        bytes(x))
+        if st[0] == B.ST_BAD_POINT:
+            raise ValueError("Delta Compact Proof Verify: Failed")
+        if st[0]:
+            raise ValueError("Same Value Proof Verify: Failed")
+        return None
+
+    @staticmethod
+    def verify_update_account_dark_tx_verifier(delta_updated_accounts, output_accounts, z_vector, x,
+                                               transcript_label=b"UpdateAccount", verifier_label=b"DLOGProof"):
+        """src/accounts/verifier.rs:818-917."""
+        if len(delta_updated_accounts) != len(output_accounts):
+            raise ValueError("Length of delta_updated_accounts and output_accounts is not same")
+        st = default_engine().verify_update_account_dark_tx(b"".join(a.data for a in delta_updated_accounts),
+                                                            b"".join(a.data for a in output_accounts),
+                                                            bytes(z_vector[0]) + bytes(z_vector[1]), bytes(x),
+                                                            len(output_accounts), transcript_label, verifier_label)
+        if st[0] == B.ST_PANIC:
+            raise PanicError("called `Option::unwrap()` on a `None` value")
+        if st[0] == B.ST_BAD_POINT:
+            raise ValueError("Update Account: DLOG Proof Verify: Failed")
+        if st[0]:
+            raise ValueError("Update Output Challenge : DLOG Proof Verify: Failed")
+        return None

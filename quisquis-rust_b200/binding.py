@@ -7,7 +7,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 QQ_OK = 0
-ST_OK, ST_BAD_POINT, ST_BAD_SCALAR, ST_KEYPAIR, ST_COMMIT, ST_NOT_FOUND, ST_PROOF = 0, 1, 2, 3, 4, 5, 6
+ST_OK, ST_BAD_POINT, ST_BAD_SCALAR, ST_KEYPAIR, ST_COMMIT, ST_NOT_FOUND, ST_PROOF, ST_PANIC = 0, 1, 2, 3, 4, 5, 6, 7
 BASE_B, BASE_H = 0, 1
 
 EXPORTS = [
@@ -22,6 +22,8 @@ EXPORTS = [
     "qq_fixed_base_i64_batch", "qq_fixed_base_i64_batch_dev", "qq_msm", "qq_msm_dev", "qq_msm_partial", "qq_msm_partial_dev",
     "qq_points_sum", "qq_msm_segmented", "qq_msm_points_prepare", "qq_msm_points_prepare_dev", "qq_msm_points_free",
     "qq_msm_points_count", "qq_msm_prepared", "qq_msm_prepared_dev",
+    "qq_verify_account_sigma_batch", "qq_verify_zero_balance_batch", "qq_verify_destroy_account_batch",
+    "qq_verify_same_value_compact_batch", "qq_verify_update_account_dark_tx_batch",
     "qq_verify_update_account_dlog_batch", "qq_verify_delta_compact_batch", "qq_decommit_batch", "qq_decommit_value_batch", "qq_from_uniform_bytes_batch", "qq_vector_pedersen_gens", "qq_bulletproof_gens",
 ]
 
@@ -90,6 +92,12 @@ def load_library():
         getattr(lib, name).argtypes = [vp, u8p, sz, ctypes.POINTER(vp)]
     lib.qq_verify_update_account_dlog_batch.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, u8p, u8p, u8p, u8p, sz, sz, u8p]
     lib.qq_verify_delta_compact_batch.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, u8p, u8p, u8p, u8p, u8p, u8p, sz, sz, u8p]
+    cs = ctypes.c_char_p
+    lib.qq_verify_account_sigma_batch.argtypes = [vp, cs, cs, u8p, u8p, u8p, u8p, u8p, u8p, u8p, sz, sz, u8p]
+    lib.qq_verify_zero_balance_batch.argtypes = [vp, cs, cs, u8p, u8p, u8p, sz, sz, ctypes.c_int, u8p]
+    lib.qq_verify_destroy_account_batch.argtypes = [vp, cs, cs, u8p, u8p, u8p, sz, sz, u8p]
+    lib.qq_verify_same_value_compact_batch.argtypes = [vp, u8p, u8p, u8p, u8p, u8p, sz, u8p]
+    lib.qq_verify_update_account_dark_tx_batch.argtypes = [vp, cs, cs, u8p, u8p, u8p, u8p, sz, sz, u8p]
     lib.qq_decommit_batch.argtypes = [vp, u8p, u8p, u8p, u8p, sz]
     lib.qq_decommit_value_batch.argtypes = [vp, u8p, u8p, ctypes.c_int, u8p, u8p, sz]
     lib.qq_from_uniform_bytes_batch.argtypes = [vp, u8p, u8p, sz]
@@ -352,6 +360,65 @@ class Engine:
         self._ck(self.lib.qq_verify_delta_compact_batch(self.h, transcript_label, verifier_label, _ptr(da), _ptr(ea), _ptr(zv),
                                                          _ptr(zr1), _ptr(zr2), _ptr(x), n, nproofs, _ptr(st)),
                  "qq_verify_delta_compact_batch")
+        return st
+
+    def verify_account_sigma(self, delta_accounts, epsilon_accounts, base_pk, zv, zsk, zr, x, n,
+                             transcript_label=b"SenderAccountProof", verifier_label=b"DLOGProof"):
+        """Verifier::verify_account_verifier_bulletproof (= the sigma part of verify_account_verifier) for x.size // 32
+        proofs of n sender accounts each -> status per proof."""
+        da, ea, bp, zv, zsk, zr, x = (_u8(a) for a in (delta_accounts, epsilon_accounts, base_pk, zv, zsk, zr, x))
+        nproofs = x.size // 32
+        _u8(da, nproofs * n * 128), _u8(ea, nproofs * n * 128), _u8(bp, 64)
+        for a in (zv, zsk, zr):
+            _u8(a, nproofs * n * 32)
+        st = np.zeros(nproofs, np.uint8)
+        self._ck(self.lib.qq_verify_account_sigma_batch(self.h, transcript_label, verifier_label, _ptr(da), _ptr(ea), _ptr(bp),
+                                                         _ptr(zv), _ptr(zsk), _ptr(zr), _ptr(x), n, nproofs, _ptr(st)),
+                 "qq_verify_account_sigma_batch")
+        return st
+
+    def verify_zero_balance(self, accounts, z, x, n, vector_form=True, transcript_label=b"ZeroBalanceAccount",
+                            verifier_label=b"DLOGProof"):
+        """Verifier::zero_balance_account_vector_verifier (vector_form) / zero_balance_account_verifier (n = 1)."""
+        ac, z, x = _u8(accounts), _u8(z), _u8(x)
+        nproofs = x.size // 32
+        _u8(ac, nproofs * n * 128), _u8(z, nproofs * n * 32)
+        st = np.zeros(nproofs, np.uint8)
+        self._ck(self.lib.qq_verify_zero_balance_batch(self.h, transcript_label, verifier_label, _ptr(ac), _ptr(z), _ptr(x), n,
+                                                        nproofs, 1 if vector_form else 0, _ptr(st)),
+                 "qq_verify_zero_balance_batch")
+        return st
+
+    def verify_destroy_account(self, accounts, z, x, n, transcript_label=b"DestroyAccount", verifier_label=b"DLOGProof"):
+        """Verifier::destroy_account_verifier for x.size // 32 proofs of n accounts each -> status per proof."""
+        ac, z, x = _u8(accounts), _u8(z), _u8(x)
+        nproofs = x.size // 32
+        _u8(ac, nproofs * n * 128), _u8(z, nproofs * n * 32)
+        st = np.zeros(nproofs, np.uint8)
+        self._ck(self.lib.qq_verify_destroy_account_batch(self.h, transcript_label, verifier_label, _ptr(ac), _ptr(z), _ptr(x),
+                                                           n, nproofs, _ptr(st)), "qq_verify_destroy_account_batch")
+        return st
+
+    def verify_same_value_compact(self, enc_accounts, commitments, zv, zr, x):
+        """Verifier::verify_same_value_compact_verifier, one proof per element -> status per proof."""
+        ac, cm, zv, zr, x = (_u8(a) for a in (enc_accounts, commitments, zv, zr, x))
+        nproofs = x.size // 32
+        _u8(ac, nproofs * 128), _u8(cm, nproofs * 32), _u8(zv, nproofs * 32), _u8(zr, nproofs * 32)
+        st = np.zeros(nproofs, np.uint8)
+        self._ck(self.lib.qq_verify_same_value_compact_batch(self.h, _ptr(ac), _ptr(cm), _ptr(zv), _ptr(zr), _ptr(x), nproofs,
+                                                              _ptr(st)), "qq_verify_same_value_compact_batch")
+        return st
+
+    def verify_update_account_dark_tx(self, delta_accounts, output_accounts, z, x, n, transcript_label=b"UpdateAccount",
+                                      verifier_label=b"DLOGProof"):
+        """Verifier::verify_update_account_dark_tx_verifier; z: two scalars per proof -> status per proof."""
+        da, oa, z, x = (_u8(a) for a in (delta_accounts, output_accounts, z, x))
+        nproofs = x.size // 32
+        _u8(da, nproofs * n * 128), _u8(oa, nproofs * n * 128), _u8(z, nproofs * 64)
+        st = np.zeros(nproofs, np.uint8)
+        self._ck(self.lib.qq_verify_update_account_dark_tx_batch(self.h, transcript_label, verifier_label, _ptr(da), _ptr(oa),
+                                                                  _ptr(z), _ptr(x), n, nproofs, _ptr(st)),
+                 "qq_verify_update_account_dark_tx_batch")
         return st
 
     def decommit(self, comm, sk):

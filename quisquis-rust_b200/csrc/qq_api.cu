@@ -1215,3 +1215,4 @@ extern "C" int qq_fixed_base_i64_batch(qq_ctx* ctx, int which, const int64_t* v,
 }
 
 #include "qq_api_msm.inc"
+#include "qq_api_sigma.inc"

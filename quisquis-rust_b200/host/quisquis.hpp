@@ -2,7 +2,7 @@
 // the C ABI of include/qq_b200.h.  Same type names, method names, argument meaning and error behaviour as
 //   src/keys.rs:33-126 (trait PublicKey), src/ristretto/keys.rs:76-282 (RistrettoPublicKey),
 //   src/elgamal/elgamal.rs:18-236 (ElGamalCommitment), src/accounts/accounts.rs:47-347 (Account),
-//   src/accounts/verifier.rs:91-99,566-581 (Verifier)
+//   src/accounts/verifier.rs:91-99,138-917 (Verifier, every sigma-protocol verifier)
 // plus the *_batch forms the Rust shim adds.  The reference is Rust; Rust is not available in this
 // image, so this is the compiled host language closest to it.  Link with -lqq_b200.  No CPU fallback.
 #pragma once
@@ -323,6 +323,130 @@ struct Verifier {
         g.check(qq_delta_identity_check(g.ctx(), acc.data(), n, &v), "verify_delta_identity_check");
         if (v == QQ_ST_BAD_POINT) throw Panic();
         if (v != QQ_ST_OK) throw Err("Identity sum verify: Failed");
+    }
+    // ---- sigma-protocol verifiers (src/accounts/verifier.rs:138-917).  The reference passes a `Verifier` carrying a Merlin
+    // transcript; here the two labels that built it (Transcript::new(label), Verifier::new(label, ..)) are the trailing
+    // arguments, defaulting to the labels of the reference's own tests.  Ok(()) = return, Err(msg) = throw Err(msg).
+    static std::vector<uint8_t> pack(const std::vector<Account>& v) {
+        std::vector<uint8_t> b(v.size() * 128);
+        for (size_t i = 0; i < v.size(); i++) {
+            auto ab = v[i].to_bytes();
+            std::memcpy(&b[i * 128], ab.data(), 128);
+        }
+        return b;
+    }
+    static std::vector<uint8_t> pack(const std::vector<Scalar>& v) {
+        std::vector<uint8_t> b(v.size() * 32);
+        for (size_t i = 0; i < v.size(); i++) std::memcpy(&b[i * 32], v[i].data(), 32);
+        return b;
+    }
+    static void verdict(uint8_t st, const char* bad_point, const char* mismatch) {
+        if (st == QQ_ST_PANIC) throw Panic();
+        if (st == QQ_ST_BAD_POINT) {
+            if (!bad_point) throw Panic();
+            throw Err(bad_point);
+        }
+        if (st != QQ_ST_OK) throw Err(mismatch);
+    }
+    // verifier.rs:138-209
+    static void verify_delta_compact_verifier(const std::vector<Account>& delta_accounts, const std::vector<Account>& epsilon_accounts,
+                                              const std::vector<Scalar>& zv_vector, const std::vector<Scalar>& zr1_vector,
+                                              const std::vector<Scalar>& zr2_vector, const Scalar& x,
+                                              const char* transcript_label = "DeltaCompact", const char* verifier_label = "DLEQProof") {
+        uint8_t st;
+        Gpu& g = Gpu::instance();
+        g.check(qq_verify_delta_compact_batch(g.ctx(), transcript_label, verifier_label, pack(delta_accounts).data(),
+                                              pack(epsilon_accounts).data(), pack(zv_vector).data(), pack(zr1_vector).data(),
+                                              pack(zr2_vector).data(), x.data(), zv_vector.size(), 1, &st),
+                "verify_delta_compact_verifier");
+        verdict(st, "Delta Compact Proof Verify: Failed", "Dleq Proof Verify: Failed");
+    }
+    // verifier.rs:223-292
+    static void verify_update_account_verifier(const std::vector<Account>& updated_input_accounts,
+                                               const std::vector<Account>& updated_delta_accounts, const std::vector<Scalar>& z_vector,
+                                               const Scalar& x, const char* transcript_label = "UpdateAccount",
+                                               const char* verifier_label = "DLOGProof") {
+        uint8_t st;
+        Gpu& g = Gpu::instance();
+        g.check(qq_verify_update_account_dlog_batch(g.ctx(), transcript_label, verifier_label, pack(updated_input_accounts).data(),
+                                                    pack(updated_delta_accounts).data(), pack(z_vector).data(), x.data(),
+                                                    z_vector.size(), 1, &st),
+                "verify_update_account_verifier");
+        verdict(st, nullptr, "DLOG Proof Verify: Failed");
+    }
+    // verifier.rs:396-470 (and the sigma-protocol part of verify_account_verifier, :305-381)
+    static void verify_account_verifier_bulletproof(const std::vector<Account>& updated_delta_account_sender,
+                                                    const std::vector<Account>& account_epsilon_sender, const RistrettoPublicKey& base_pk,
+                                                    const std::vector<Scalar>& zv, const std::vector<Scalar>& zsk,
+                                                    const std::vector<Scalar>& zr, const Scalar& x,
+                                                    const char* transcript_label = "SenderAccountProof",
+                                                    const char* verifier_label = "DLOGProof") {
+        uint8_t st;
+        Gpu& g = Gpu::instance();
+        g.check(qq_verify_account_sigma_batch(g.ctx(), transcript_label, verifier_label, pack(updated_delta_account_sender).data(),
+                                              pack(account_epsilon_sender).data(), base_pk.as_bytes().data(), pack(zv).data(),
+                                              pack(zsk).data(), pack(zr).data(), x.data(), zv.size(), 1, &st),
+                "verify_account_verifier_bulletproof");
+        verdict(st, "Account Verify: Failed", "sender account verification failed");
+    }
+    // verifier.rs:593-634 (domain separator as the reference's verifier spells it)
+    static void zero_balance_account_vector_verifier(const std::vector<Account>& anonymity_accounts, const std::vector<Scalar>& z,
+                                                     const Scalar& x, const char* transcript_label = "ZeroBalanceAccount",
+                                                     const char* verifier_label = "DLOGProof") {
+        if (anonymity_accounts.size() != z.size()) throw std::logic_error("assertion failed: anonymity_accounts.len() == z.len()");
+        uint8_t st;
+        Gpu& g = Gpu::instance();
+        g.check(qq_verify_zero_balance_batch(g.ctx(), transcript_label, verifier_label, pack(anonymity_accounts).data(),
+                                             pack(z).data(), x.data(), z.size(), 1, 1, &st),
+                "zero_balance_account_vector_verifier");
+        verdict(st, "Zero balance Account Verify: Failed", "Zero balance account verification failed");
+    }
+    // verifier.rs:647-680
+    static void zero_balance_account_verifier(const Account& account, const Scalar& z, const Scalar& x,
+                                              const char* transcript_label = "ZeroBalanceAccount",
+                                              const char* verifier_label = "DLOGProof") {
+        uint8_t st;
+        Gpu& g = Gpu::instance();
+        g.check(qq_verify_zero_balance_batch(g.ctx(), transcript_label, verifier_label, account.to_bytes().data(), z.data(),
+                                             x.data(), 1, 1, 0, &st),
+                "zero_balance_account_verifier");
+        verdict(st, "Zero balance Account Verify: Failed", "Zero balance account verification failed");
+    }
+    // verifier.rs:693-735
+    static void destroy_account_verifier(const std::vector<Account>& accounts, const std::vector<Scalar>& z, const Scalar& x,
+                                         const char* transcript_label = "DestroyAccount", const char* verifier_label = "DLOGProof") {
+        if (accounts.size() != z.size()) throw std::logic_error("assertion failed: accounts.len() == z.len()");
+        uint8_t st;
+        Gpu& g = Gpu::instance();
+        g.check(qq_verify_destroy_account_batch(g.ctx(), transcript_label, verifier_label, pack(accounts).data(), pack(z).data(),
+                                                x.data(), z.size(), 1, &st),
+                "destroy_account_verifier");
+        verdict(st, "Destroy Account Verify: Failed", "Destroy account verification failed");
+    }
+    // verifier.rs:747-806; the proof is SigmaProof::Dleq(zv, zr, _, x) with one response each
+    static void verify_same_value_compact_verifier(const Account& enc_account, const CompressedRistretto& commitment, const Scalar& zv,
+                                                   const Scalar& zr, const Scalar& x) {
+        uint8_t st;
+        Gpu& g = Gpu::instance();
+        g.check(qq_verify_same_value_compact_batch(g.ctx(), enc_account.to_bytes().data(), commitment.data(), zv.data(), zr.data(),
+                                                   x.data(), 1, &st),
+                "verify_same_value_compact_verifier");
+        verdict(st, "Delta Compact Proof Verify: Failed", "Same Value Proof Verify: Failed");
+    }
+    // verifier.rs:818-917
+    static void verify_update_account_dark_tx_verifier(const std::vector<Account>& delta_updated_accounts,
+                                                       const std::vector<Account>& output_accounts, const std::vector<Scalar>& z_vector,
+                                                       const Scalar& x, const char* transcript_label = "UpdateAccount",
+                                                       const char* verifier_label = "DLOGProof") {
+        if (delta_updated_accounts.size() != output_accounts.size())
+            throw Err("Length of delta_updated_accounts and output_accounts is not same");
+        uint8_t st;
+        Gpu& g = Gpu::instance();
+        g.check(qq_verify_update_account_dark_tx_batch(g.ctx(), transcript_label, verifier_label, pack(delta_updated_accounts).data(),
+                                                       pack(output_accounts).data(), pack(z_vector).data(), x.data(),
+                                                       output_accounts.size(), 1, &st),
+                "verify_update_account_dark_tx_verifier");
+        verdict(st, "Update Account: DLOG Proof Verify: Failed", "Update Output Challenge : DLOG Proof Verify: Failed");
     }
 };
 

@@ -93,6 +93,43 @@ int main(int argc, char** argv) {
     CHECK(!Verifier::multiscalar_multiplication({us[0], us[1]}, {accs[0].pk.gr, bad.pk.gr}).has_value());
     CHECK(Verifier::multiscalar_multiplication({us[0], us[1]}, {accs[0].pk.gr, accs[1].pk.gr}).has_value());
     // delta / epsilon with sum-zero randomness is checked from Python (needs scalar arithmetic mod l)
+    // sigma-protocol verifiers (second fixture, proofs made by the oracle's prover restatements):
+    //   destroy account: 4 x account 128 | 4 x z 32 | x 32;   dark tx: 4 x delta 128 | 4 x output 128 | z0 z1 32 | x 32
+    if (argc >= 3) {
+        auto sg = read_all(argv[2]);
+        CHECK(sg.size() == (4 * 128 + 4 * 32 + 32) + (8 * 128 + 64 + 32));
+        const uint8_t* q = sg.data();
+        std::vector<Account> da;
+        std::vector<Scalar> dz;
+        for (int i = 0; i < 4; i++) da.push_back(Account::from_raw(q + 128 * i));
+        for (int i = 0; i < 4; i++) dz.push_back(arr<32>(q + 512 + 32 * i));
+        Scalar dx = arr<32>(q + 640);
+        Verifier::destroy_account_verifier(da, dz, dx);            // Ok(())
+        std::string msg;
+        try { Verifier::destroy_account_verifier(da, {dz[1], dz[0], dz[2], dz[3]}, dx); } catch (const Err& e) { msg = e.what(); }
+        CHECK(msg == "Destroy account verification failed");
+        msg.clear();
+        try { Verifier::destroy_account_verifier(da, dz, dx, "DestroyAccount", "SomethingElse"); } catch (const Err& e) { msg = e.what(); }
+        CHECK(msg == "Destroy account verification failed");
+        q += 672;
+        std::vector<Account> td, to;
+        for (int i = 0; i < 4; i++) td.push_back(Account::from_raw(q + 128 * i));
+        for (int i = 0; i < 4; i++) to.push_back(Account::from_raw(q + 512 + 128 * i));
+        std::vector<Scalar> tz = {arr<32>(q + 1024), arr<32>(q + 1056)};
+        Scalar tx = arr<32>(q + 1088);
+        Verifier::verify_update_account_dark_tx_verifier(td, to, tz, tx);
+        msg.clear();
+        try { Verifier::verify_update_account_dark_tx_verifier(td, to, {tz[1], tz[0]}, tx); } catch (const Err& e) { msg = e.what(); }
+        CHECK(msg == "Update Output Challenge : DLOG Proof Verify: Failed");
+        msg.clear();
+        try { Verifier::verify_update_account_dark_tx_verifier(td, {to[0], to[1], to[2]}, tz, tx); } catch (const Err& e) { msg = e.what(); }
+        CHECK(msg == "Length of delta_updated_accounts and output_accounts is not same");
+        Account badc = to[1];
+        badc.comm.c.fill(0xff);
+        threw = false;
+        try { Verifier::verify_update_account_dark_tx_verifier(td, {to[0], badc, to[2], to[3]}, tz, tx); } catch (const Panic&) { threw = true; }
+        CHECK(threw);
+    }
     std::printf("HOST_API_TEST OK\n");
     return 0;
 }

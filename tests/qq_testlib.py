@@ -76,3 +76,79 @@ def invalid_encodings():
         s += 2
     out.extend(found.items())
     return out
+
+
+# ---- sigma-proof scenarios of the reference's own tests (src/accounts/verifier.rs tests), shared by the oracle round-trip
+# test (CPU) and the batched-verifier parity tests (GPU).  Proofs come from the oracle's prover restatements.
+def random_account_with_value(st, value):
+    """Account::generate_random_account_with_value (src/accounts/accounts.rs:331-347) -> (account, sk)."""
+    acc, sk, _ = make_account(st, 0)
+    upd, s = R.update_account(acc, sb(value), st.scalar_bytes(), st.scalar_bytes())
+    assert s == 0
+    return upd, sk
+
+
+def scenario_dark_tx(st, n=4):
+    """verifier.rs:1075-1111 -> (delta_accounts, output_accounts, z[2], x)."""
+    import sigma_ref as S
+    u, c = st.scalar(), st.scalar()
+    accs = [random_account_with_value(st, 10)[0] for _ in range(n)]
+    outs = []
+    for a in accs:
+        o, s = R.update_account(a, sb(0), sb(u), sb(c))
+        assert s == 0
+        outs.append(o)
+    z, x = S.prove_update_account_dark_tx(accs, outs, u, c, st.scalar(), st.scalar())
+    return accs, outs, z, x
+
+
+def zero_balance_accounts(st, n):
+    """verifier.rs:1386-1393 / :1408-1421: zero-balance accounts on re-keyed base keys -> (accounts, comm_rscalars)."""
+    pk, s = R.update_public_key(R.BASE_PK, st.scalar_bytes())
+    accs, rs = [], []
+    for _ in range(n):
+        k, s = R.update_public_key(pk, st.scalar_bytes())
+        r = st.scalar()
+        comm, s = R.generate_commitment(k, sb(r), sb(0))
+        accs.append(k + comm)
+        rs.append(r)
+        pk, s = R.update_public_key(pk, st.scalar_bytes())
+    return accs, rs
+
+
+def scenario_destroy(st, n=4):
+    """verifier.rs:1455-1479 -> (accounts, z[], x)."""
+    import sigma_ref as S
+    pairs = [random_account_with_value(st, 0) for _ in range(n)]
+    accs, sks = [p[0] for p in pairs], [p[1] for p in pairs]
+    z, x = S.prove_destroy_account(accs, sks, [st.scalar() for _ in range(n)])
+    return accs, z, x
+
+
+def scenario_same_value(st, value=10, committed=None):
+    """verifier.rs:1736-1775 -> (enc_account, pedersen_commitment, zv, zr, x); committed != value is the fail test."""
+    import sigma_ref as S
+    sk, rho, r = st.scalar(), st.scalar(), st.scalar()
+    gr = R.mul(rho, R.BASEPOINT)
+    pk = R.compress(gr) + R.compress(R.mul(sk, gr))
+    comm, s = R.generate_commitment(pk, sb(r), sb(value))
+    acc = pk + comm
+    pc = S.pedersen_commit(value if committed is None else committed, r)
+    zv, zr, x = S.prove_same_value(acc, r, value, pc, st.scalar(), st.scalar())
+    return acc, pc, zv, zr, x
+
+
+def scenario_sender_account(st):
+    """The reference's (commented-out) verify_account_verifier test, verifier.rs:1115-1216: 9 accounts of value 10,
+    transfers [-5, -3, 5, 3, 0 x 5], the two senders prove their remaining balances 5 and 7.
+    -> (updated_delta_sender[2], epsilon[2], base_pk, zv, zsk, zr, x)."""
+    import sigma_ref as S
+    vals = [R.L - 5, R.L - 3, 5, 3, 0, 0, 0, 0, 0]
+    pairs = [random_account_with_value(st, 10) for _ in range(9)]
+    accs, sks = [p[0] for p in pairs], [p[1] for p in pairs]
+    delta = [R.delta_epsilon(a, sb(v), st.scalar_bytes())[0] for a, v in zip(accs, vals)]
+    upd = S.update_delta_accounts(accs, delta)
+    senders, bl = upd[0:2], [5, 7]
+    eps, zv, zsk, zr, x = S.prove_account(senders, bl, sks[0:2], R.BASE_PK, [st.scalar(), st.scalar()],
+                                          [(st.scalar(), st.scalar(), st.scalar()) for _ in range(2)])
+    return senders, eps, R.BASE_PK, zv, zsk, zr, x

@@ -24,9 +24,17 @@ def test_cpp_host_mirror(tmp_path, pkg):
         rec += acc + sb(sk) + sb(v) + bl + u + c + exp
     fx = tmp_path / "fixture.bin"
     fx.write_bytes(rec)
+    # second fixture: a destroy-account proof and a dark-tx proof (reference scenarios verifier.rs:1455-1479, :1075-1111)
+    from qq_testlib import scenario_dark_tx, scenario_destroy
+    accs, z, x = scenario_destroy(st, 4)
+    sg = b"".join(accs) + b"".join(sb(v) for v in z) + sb(x)
+    d, o, z, x = scenario_dark_tx(st, 4)
+    sg += b"".join(d) + b"".join(o) + sb(z[0]) + sb(z[1]) + sb(x)
+    fs = tmp_path / "sigma.bin"
+    fs.write_bytes(sg)
     exe = tmp_path / "host_api_test"
     libdir = os.path.join(ROOT, "quisquis-rust_b200")
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", str(exe), os.path.join(ROOT, "tests", "csrc", "host_api_test.cpp"),
                            "-L" + libdir, "-lqq_b200", "-Wl,-rpath," + libdir])
-    out = subprocess.run([str(exe), str(fx)], capture_output=True, text=True, timeout=300)
+    out = subprocess.run([str(exe), str(fx), str(fs)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "HOST_API_TEST OK" in out.stdout, out.stdout + out.stderr

@@ -174,3 +174,39 @@ def test_quirks_of_the_reference_are_kept():
     # identity encodes as 32 zero bytes (dalek), e.g. a - a
     z, s = R.sub_commitments(acc[64:], acc[64:])
     assert z == bytes(64) and s == 0
+
+
+def test_remaining_sigma_proofs_round_trip():
+    """The oracle's restatements of the other sigma proofs of src/accounts/{prover,verifier}.rs replay the reference's own
+    test scenarios: proofs verify, tampered proofs do not, and the reference's outcomes are reproduced - including
+    zero_balance_account_vector_verifier rejecting the reference prover's proofs (verifier.rs:1407-1452: the two sides
+    spell the domain separator differently, prover.rs:613 / verifier.rs:605)."""
+    import sigma_ref as S
+    from qq_testlib import (scenario_dark_tx, scenario_destroy, scenario_same_value, scenario_sender_account,
+                            zero_balance_accounts)
+    st = Stream(b"sigma-rest-cpu")
+    d, o, z, x = scenario_dark_tx(st, 2)
+    assert S.verify_update_account_dark_tx(d, o, z, x) is True
+    assert S.verify_update_account_dark_tx(d, o, [z[1], z[0]], x) is False
+    assert S.verify_update_account_dark_tx(d, o, z, x + 1) is False
+    accs, z, x = scenario_destroy(st, 2)
+    assert S.verify_destroy_account(accs, z, x) is True
+    assert S.verify_destroy_account(accs[::-1], z, x) is False
+    acc, pc, zv, zr, x = scenario_same_value(st)
+    assert S.verify_same_value(acc, pc, zv, zr, x) is True
+    assert S.verify_same_value(*scenario_same_value(st, 10, committed=0)) is False      # verifier.rs:1755-1775
+    accs, rs = zero_balance_accounts(st, 3)
+    z, x = S.prove_zero_balance(accs[:1], rs[:1], [st.scalar()], vector_form=False)
+    assert S.verify_zero_balance(accs[:1], z, x, vector_form=False) is True               # verifier.rs:1386-1404
+    blind = [st.scalar() for _ in accs]
+    z, x = S.prove_zero_balance(accs, rs, blind, vector_form=True)
+    assert S.verify_zero_balance(accs, z, x, vector_form=True) is False                   # the reference's own outcome
+    z, x = S.prove_zero_balance(accs, rs, blind, vector_form=True, domain=b"ZeroBalanceAccounVectorProof")
+    assert S.verify_zero_balance(accs, z, x, vector_form=True) is True                    # the algebra itself is sound
+    assert S.verify_zero_balance(accs, [z[0], z[2], z[1]], x, vector_form=True) is False
+    snd, eps, bpk, zv, zsk, zr, x = scenario_sender_account(st)
+    assert S.verify_account(snd, eps, bpk, zv, zsk, zr, x) is True
+    assert S.verify_account(snd, eps, bpk, zv, zr, zsk, x) is False
+    bad = bytearray(eps[1])
+    bad[64:96] = (1).to_bytes(32, "little")                                               # negative s: undecodable
+    assert S.verify_account(snd, [eps[0], bytes(bad)], bpk, zv, zsk, zr, x) is None
