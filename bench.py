@@ -434,6 +434,18 @@ def run_b200(args):
                          "curve25519-dalek 3.2.1's algorithms (radix-2^51 field, radix-16 variable-base, table "
                          "fixed-base); dalek itself cannot be built here" % (ms_, cores),
                "gpu_output_matches_cpu_on_sample": same_cpu}
+        if anon9 is not None:
+            # configs[0] as the reference runs it: the same 9 accounts on ONE host core (update_account + verify_account)
+            C.set_threads(1)
+            lat = []
+            for rep in range(7):
+                t = time.time()
+                o9c, _ = C.update_account(acc_h[:9], bl_h[:9], u_h[:9], c_h[:9])
+                C.verify_account(o9c, u_h[:9], bl_h[:9])
+                lat.append((time.time() - t) * 1e3)
+            lat.sort()
+            anon9["cpu_port_one_core_ms_median"] = lat[len(lat) // 2]
+            C.set_threads(cores)
 
     if rank == 0:
         clocks = sampler.summary(t_region0, t_region1)

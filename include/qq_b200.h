@@ -139,6 +139,11 @@ int qq_fixed_base_batch_dev(qq_ctx* ctx, int which, const uint8_t* s, uint8_t* o
  * fewer additions per scalar and identical results.  window_bits = 0 frees the table (batches then use the
  * shared-memory 6-bit table only); otherwise 8 <= window_bits <= 28.  Rebuilds synchronously. */
 int qq_fixed_base_set_window(qq_ctx* ctx, int which, int window_bits);
+/* Tuning: variable-base calls of at most max_scalar_mults scalar multiplications (9-account anonymity sets, a block's
+ * worth of transactions) run four lanes per multiplication (k_varbase_coop: latency of 2 instead of 8 field products
+ * per group operation); larger calls run one thread per point.  < 0 restores the default (160 per SM), 0 disables (and
+ * with it the other small-batch paths, for A/B measurements). */
+int qq_varbase_set_coop_limit(qq_ctx* ctx, long max_scalar_mults);
 /* out_i = enc(v_i * Base) for signed 64-bit values: what `&Scalar::from(v as u64) * &RISTRETTO_BASEPOINT_TABLE` (and its
  * negation) computes for balances (src/elgamal/elgamal.rs:285-300, src/accounts/accounts.rs:419-429).  Only the windows
  * that a 64-bit magnitude can touch are walked (3 at W = 22).  Requires a large-window table (window_bits != 0). */

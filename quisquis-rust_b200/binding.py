@@ -18,7 +18,7 @@ EXPORTS = [
     "qq_generate_commitment_batch", "qq_generate_commitment_batch_dev", "qq_add_commitments_batch",
     "qq_mul_commitment_batch", "qq_update_account_batch", "qq_update_account_batch_dev",
     "qq_verify_account_batch", "qq_verify_account_batch_dev", "qq_delta_epsilon_batch", "qq_delta_identity_check",
-    "qq_fixed_base_batch", "qq_fixed_base_batch_dev", "qq_fixed_base_set_window", "qq_fixed_base_window",
+    "qq_fixed_base_batch", "qq_fixed_base_batch_dev", "qq_fixed_base_set_window", "qq_fixed_base_window", "qq_varbase_set_coop_limit",
     "qq_fixed_base_i64_batch", "qq_fixed_base_i64_batch_dev", "qq_msm", "qq_msm_dev", "qq_msm_partial", "qq_msm_partial_dev",
     "qq_points_sum", "qq_msm_segmented", "qq_msm_points_prepare", "qq_msm_points_prepare_dev", "qq_msm_points_free",
     "qq_msm_points_count", "qq_msm_prepared", "qq_msm_prepared_dev",
@@ -85,6 +85,7 @@ def load_library():
         getattr(lib, name).argtypes = [vp, ctypes.c_int, vp, u8p, sz]
     lib.qq_fixed_base_set_window.argtypes = [vp, ctypes.c_int, ctypes.c_int]
     lib.qq_fixed_base_window.argtypes = [vp, ctypes.c_int]
+    lib.qq_varbase_set_coop_limit.argtypes = [vp, ctypes.c_long]
     for name in ("qq_msm", "qq_msm_dev", "qq_msm_partial", "qq_msm_partial_dev"):
         getattr(lib, name).argtypes = [vp, u8p, u8p, sz, u8p, u8p]
     lib.qq_points_sum.argtypes = [vp, u8p, sz, u8p, u8p]
@@ -298,6 +299,10 @@ class Engine:
     def fixed_base_set_window(self, which, window_bits):
         """Rebuild the large fixed-base table of base `which` with `window_bits`-bit windows (0 frees it)."""
         self._ck(self.lib.qq_fixed_base_set_window(self.h, int(which), int(window_bits)), "qq_fixed_base_set_window")
+
+    def varbase_set_coop_limit(self, max_scalar_mults):
+        """Variable-base calls up to this many scalar mults use four lanes per multiplication (< 0: default, 0: off)."""
+        self._ck(self.lib.qq_varbase_set_coop_limit(self.h, int(max_scalar_mults)), "qq_varbase_set_coop_limit")
 
     def fixed_base_window(self, which):
         return int(self.lib.qq_fixed_base_window(self.h, int(which)))

@@ -204,6 +204,41 @@ __global__ void __launch_bounds__(256) k_dc_finish(const u32x4* __restrict__ sta
         }
     }
 }
+// Small batches: the five dependent launches above are pure latency (one inversion deep each way), so every item
+// inverts its own w -- prepare, fe_invert and finish in ONE kernel, one thread per item, 32-thread blocks spread over
+// the SMs.  Same outputs as k_dc_prepare / k_binv_* / k_dc_finish.
+__global__ void __launch_bounds__(32) k_dc_direct(fin_args a, const uint8_t* __restrict__ bad, int bdiv,
+                                                  u32x4* __restrict__ out, idx_map omap,
+                                                  const u32x4* __restrict__ expect, idx_map emap,
+                                                  uint8_t* __restrict__ flag) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n) return;
+    ge_p3 q;
+    fin_eval(q, a, t);
+    dc_state st;
+    fe wv, one, iv;
+    dc_prepare(st, wv, q);
+    u32 z = fe_iszero(wv);
+    fe_1(one);
+    fe_cmov(wv, one, z);
+    fe_invert(iv, wv);
+    u32 w[8];
+    dc_finish(w, st, iv);
+    if (z != 0 || (bad != nullptr && bad[t / (size_t)bdiv] != 0)) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) w[i] = 0;
+    }
+    if (expect != nullptr) {
+        u32 e[8];
+        load_words32(e, expect, map_index(emap, t));
+        u32 d = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) d |= w[i] ^ e[i];
+        flag[t] = d == 0 ? 1 : 0;
+    } else {
+        store_words32(out, map_index(omap, t), w);
+    }
+}
 #endif
 
 }  // namespace qq

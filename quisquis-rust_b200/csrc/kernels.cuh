@@ -7,6 +7,7 @@
 #pragma once
 #include "ristretto.cuh"
 #include "scalarmult.cuh"
+#include "ge_coop.cuh"
 
 namespace qq {
 
@@ -126,6 +127,70 @@ __global__ void __launch_bounds__(QQ_VB_BLOCK, 1) k_varbase_split(vb_args a) {
         vbs_scalarmult(r, tbl, s);
         ge_p3_store(a.out1 + QQ_PT_Q * t, r);
     }
+}
+
+// Small batches (9-account anonymity sets, a block's worth of transactions): the chain of 316 group operations of one
+// scalar multiplication is pure latency and most of the GPU's lanes are idle, so FOUR adjacent lanes share one
+// (point, scalar) job (ge_coop.cuh: lane r owns coordinate r, every group operation is two rounds of one field
+// multiplication per lane instead of 8 multiplications in a row).  Job j = point j / ns with scalar j % ns; each
+// group builds its own cached table {1..8}P in shared memory (1 KB per group).  Same digits (signed radix 16), same
+// results as k_varbase / k_varbase_split; chosen by launch_varbase while the jobs leave lanes idle.
+#define QQ_VBC_GROUP_Q 64   // 8 entries x 4 lanes x 2 u32x4
+__global__ void __launch_bounds__(128) k_varbase_coop(vb_args a, int ns) {
+    extern __shared__ __align__(16) u32x4 vbc_tbl[];
+    const int r = threadIdx.x & 3;
+    u32x4* tb = vbc_tbl + (threadIdx.x >> 2) * QQ_VBC_GROUP_Q;
+    size_t job = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2, njobs = a.n * (size_t)ns;
+    bool act = job < njobs;
+    size_t j = act ? job : 0;     // idle groups of the last warp repeat job 0 (the shuffles are warp-wide) and store nothing
+    size_t t = j / (size_t)ns;
+    int which = (int)(j - t * (size_t)ns);
+    fe p = coop_load(a.pts + QQ_PT_Q * map_index(a.map, t), r);
+    fe c1 = coop_to_cached(p, r), q = p;
+    {
+        int o = 2 * r;
+        fe_store(tb, o, c1);
+    }
+#pragma unroll 1
+    for (int i = 2; i <= 8; i++) {
+        q = coop_add(q, c1, r);
+        fe c = coop_to_cached(q, r);
+        int o = ((i - 1) * 4 + r) * 2;
+        fe_store(tb, o, c);
+    }
+    __syncwarp();
+    u32 s[8], rr[9], w[8];
+    load_words32(s, which ? a.s1 : a.s0, t / (size_t)a.sdiv);
+    if (which ? a.halve1 : a.halve0) sc_halve(s, s);
+    sc_recode_bias<4, 64>(rr, s);        // rr[8] == 0 for s < 2^253
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = rr[i];
+    fe acc = coop_identity(r);
+#pragma unroll 1
+    for (int k = 63; k >= 0; k--) {
+        if (k != 63) {
+#pragma unroll 1
+            for (int d = 0; d < 4; d++) acc = coop_dbl(acc, r);
+        }
+        int d = (int)(w[7] >> 28) - 8;     // signed digit in [-8, 8); then shift the register left by one nibble
+#pragma unroll
+        for (int i = 7; i > 0; i--) w[i] = (w[i] << 4) | (w[i - 1] >> 28);
+        w[0] <<= 4;
+        u32 neg = d < 0 ? 1u : 0u;
+        int idx = d < 0 ? -d : d;
+        // cached lanes: 0 = Y - X, 1 = Y + X, 2 = 2 Z, 3 = 2d T.  Negation swaps lanes 0 / 1 and negates lane 3.
+        int lane = r < 2 ? (r ^ (int)neg) : r;
+        fe c;
+        int o = ((idx > 0 ? idx - 1 : 0) * 4 + lane) * 2;
+        fe_load(tb, o, c);
+        if (r == 3) fe_cneg(c, neg);
+        fe idc;
+        fe_0(idc);
+        idc.v[0] = r == 2 ? 2u : (r == 3 ? 0u : 1u);
+        c = fe_sel(idx == 0, idc, c);
+        acc = coop_add(acc, c, r);
+    }
+    if (act) coop_store((which ? a.out1 : a.out0) + QQ_PT_Q * t, r, acc);
 }
 
 // ---- fixed-base scalar multiplication: table staged in shared memory ---------------------------------------------
@@ -520,6 +585,101 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_straus(straus_args a) {
             for (int i = 0; i < 8; i++) wds[i] = 0;
         }
         store_words32(a.out, j, wds);
+    }
+}
+
+// Few instances (the 18-36 MSMs of ONE sigma proof, the ~42 of one shuffle proof): four lanes per instance, as in
+// k_varbase_coop.  A 32-thread block holds 8 instances; the per-term tables {1..8}P (cached, lane-sliced) and recoded
+// scalars of a chunk of up to QQ_STC_KC terms live in shared memory.  The shuffles are warp-wide, so the 8 instances of
+// a warp run the term count of the longest one (absent terms add the identity); no ordering pass is needed.
+// Output: half_out (the scalars are halved, the batch encoder doubles), as in k_straus.
+#define QQ_STC_KC 9
+#define QQ_STC_TERM_Q (QQ_VBC_GROUP_Q + 2)                 // table + 8 recoded words
+#define QQ_STC_SMEM_BYTES (8 * QQ_STC_KC * QQ_STC_TERM_Q * 16)
+__global__ void __launch_bounds__(32) k_straus_coop(straus_args a) {
+    extern __shared__ __align__(16) u32x4 stc_smem[];
+    const int r = threadIdx.x & 3, grp = threadIdx.x >> 2;
+    u32x4* slab = stc_smem + (size_t)grp * (QQ_STC_KC * QQ_STC_TERM_Q);
+    size_t inst = (size_t)blockIdx.x * 8 + grp;
+    bool act = inst < a.m;
+    size_t j = act ? inst : 0;
+    uint32_t lo = a.offsets[j], nt = a.offsets[j + 1] - lo;
+    uint32_t ntmax = nt;
+#pragma unroll
+    for (int sft = 4; sft < 32; sft <<= 1) {
+        uint32_t o = __shfl_xor_sync(QQ_COOP_MASK, ntmax, sft);
+        ntmax = o > ntmax ? o : ntmax;
+    }
+    fe total = coop_identity(r);
+    uint8_t st = 0;
+    for (uint32_t c0 = 0; c0 < ntmax; c0 += QQ_STC_KC) {
+        int kw = (int)(ntmax - c0 < QQ_STC_KC ? ntmax - c0 : QQ_STC_KC);               // warp-uniform
+        int k = c0 < nt ? (int)(nt - c0 < QQ_STC_KC ? nt - c0 : QQ_STC_KC) : 0;        // this instance's
+#pragma unroll 1
+        for (int t = 0; t < kw; t++) {
+            bool have = t < k;
+            size_t ti = (size_t)lo + c0 + (have ? t : 0);
+            u32x4* tb = slab + (size_t)t * QQ_STC_TERM_Q;
+            fe p = coop_identity(r);
+            u32 rr[9];
+#pragma unroll
+            for (int i = 0; i < 9; i++) rr[i] = 0x88888888u;     // every digit 0
+            if (have) {
+                p = coop_load(a.pts + QQ_PT_Q * ti, r);
+                u32 sc[8];
+                load_words32(sc, a.scalars, ti);
+                sc_halve(sc, sc);
+                sc_recode_bias<4, 64>(rr, sc);
+                uint8_t ts = a.term_status[ti];
+                st = (ts == 2 || st == 2) ? 2 : (st | ts);
+            }
+            if (r == 0) store_words32(tb + QQ_VBC_GROUP_Q, 0, rr);
+            fe c1 = coop_to_cached(p, r), q = p;
+            {
+                int o = 2 * r;
+                fe_store(tb, o, c1);
+            }
+#pragma unroll 1
+            for (int i = 2; i <= 8; i++) {
+                q = coop_add(q, c1, r);
+                fe c = coop_to_cached(q, r);
+                int o = ((i - 1) * 4 + r) * 2;
+                fe_store(tb, o, c);
+            }
+        }
+        __syncwarp();
+        fe acc = coop_identity(r);
+#pragma unroll 1
+        for (int w = 63; w >= 0; w--) {
+            if (w != 63) {
+#pragma unroll 1
+                for (int d = 0; d < 4; d++) acc = coop_dbl(acc, r);
+            }
+#pragma unroll 1
+            for (int t = 0; t < kw; t++) {
+                const u32x4* tb = slab + (size_t)t * QQ_STC_TERM_Q;
+                u32 word = reinterpret_cast<const u32*>(tb + QQ_VBC_GROUP_Q)[w >> 3];
+                int d = (int)((word >> ((w & 7) * 4)) & 15u) - 8;
+                u32 neg = d < 0 ? 1u : 0u;
+                int idx = d < 0 ? -d : d;
+                int lane = r < 2 ? (r ^ (int)neg) : r;
+                fe c;
+                int o = ((idx > 0 ? idx - 1 : 0) * 4 + lane) * 2;
+                fe_load(tb, o, c);
+                if (r == 3) fe_cneg(c, neg);
+                fe idc;
+                fe_0(idc);
+                idc.v[0] = r == 2 ? 2u : (r == 3 ? 0u : 1u);
+                c = fe_sel(idx == 0, idc, c);
+                acc = coop_add(acc, c, r);
+            }
+        }
+        total = coop_add(total, coop_to_cached(acc, r), r);
+        __syncwarp();
+    }
+    if (act) {
+        coop_store(a.half_out + QQ_PT_Q * j, r, total);
+        if (r == 0) a.status[j] = st;
     }
 }
 

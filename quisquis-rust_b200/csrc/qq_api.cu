@@ -20,7 +20,13 @@
 
 using namespace qq;
 
-#define QQ_FBT_MIN_BATCH 2048  // below this the shared-memory table (cold-start free) is used instead of the big one
+// The large-window table (15 additions at W = 16) is used at every batch size when it exists: measured 0.05 ms against
+// 0.10 (n = 9) ... 0.24 ms (n = 1000) for the shared-memory table, whose 136 KB staging per block is what a small batch
+// pays for (profiles/small_batch_r01.jsonl).  The shared-memory kernel remains for qq_fixed_base_set_window(.., 0).
+#define QQ_FBT_MIN_BATCH 1
+// Batch encoder: up to this many items every thread inverts its own denominator (k_dc_direct, one launch) instead of the
+// multi-level shared inversion (five dependent launches)
+#define QQ_DC_DIRECT_MAX ((size_t)ctx->sms * 128)
 #define QQ_FB_W 6  // window width of the shared-memory fixed-base tables (43 windows x 33 entries x 96 B = 136 KB)
 enum { FAM_DEC = 0, FAM_VB = 1, FAM_FB = 2, FAM_FIN = 3, FAM_MSM_BUCKET = 4, FAM_MSM_REDUCE = 5, FAM_COUNT = 6 };
 
@@ -54,6 +60,8 @@ struct qq_ctx {
     std::vector<span> spans;
     int ev_used = 0;
     int vb_blocks_per_sm[3] = {0, 0, 0};
+    bool stc_ready = false;                    // k_straus_coop's shared-memory opt-in done
+    long vbc_max_jobs = -1;                    // four-lane cooperative variable base up to this many scalar mults (< 0: sms * 160)
 };
 
 #define CK(call)                                                                                   \
@@ -176,6 +184,20 @@ static int launch_varbase(qq_ctx* ctx, int ns, const u32x4* pts, idx_map map, co
     a.out0 = out0; a.out1 = out1; a.scratch = scratch; a.n = n;
     // large batches: one 512-thread block per SM (lockstep, see kernels.cuh).  Small batches are latency-bound chains:
     // narrower blocks spread the few warps over all schedulers (one warp per scheduler up to 4 * sms warps).
+    // While the lanes are not all busy, four lanes per scalar multiplication (k_varbase_coop): measured faster up to
+    // ~19 000 scalar mults (0.66 against 0.98 ms), slower from ~38 000 (1.23 against 1.01 ms); switch at 160 per SM.
+    size_t coop_max = ctx->vbc_max_jobs < 0 ? (size_t)ctx->sms * 160 : (size_t)ctx->vbc_max_jobs;
+    if (n * (size_t)ns <= coop_max) {
+        size_t threads = n * (size_t)ns * 4;
+        int cb = 32;
+        while (cb < 128 && (threads + cb - 1) / cb > (size_t)ctx->sms * 4) cb *= 2;
+        span_begin(ctx, FAM_VB);
+        k_varbase_coop<<<(unsigned)((threads + cb - 1) / cb), cb, (size_t)(cb / 4) * QQ_VBC_GROUP_Q * 16, ctx->stream>>>(a, ns);
+        span_end(ctx);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        return QQ_OK;
+    }
     int block = QQ_VB_BLOCK;
     int grid = ctx->sms * ctx->vb_blocks_per_sm[ns];
     if ((size_t)grid * QQ_VB_BLOCK > n) {
@@ -297,6 +319,13 @@ static int launch_finish_dbl(qq_ctx* ctx, const dc_ws& d, fin_src a, fin_src b, 
     f.src[0] = a; f.src[1] = b; f.src[2] = c;
     f.out = (u32x4*)out; f.omap = omap; f.bad = bad; f.bdiv = bdiv; f.n = n;
     span_begin(ctx, FAM_FIN);
+    if (n <= QQ_DC_DIRECT_MAX && ctx->vbc_max_jobs != 0) {
+        k_dc_direct<<<(unsigned)((n + 31) / 32), 32, 0, ctx->stream>>>(f, bad, bdiv, (u32x4*)out, omap, (const u32x4*)expect, emap, flag);
+        span_end(ctx);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        return QQ_OK;
+    }
     k_dc_prepare<<<grid_for(n, 256, ctx->sms * 64), 256, 0, ctx->stream>>>(f, d.state, d.w, d.zflag);
     ctx->launches++;
     CKQ(launch_batch_invert(ctx, d, n));
@@ -405,6 +434,11 @@ static int fbt_build(qq_ctx* ctx, int which, int W) {
     bufs.release(tbl);
     ctx->fbt[which] = tbl;
     ctx->fbt_g[which] = g;
+    return QQ_OK;
+}
+extern "C" int qq_varbase_set_coop_limit(qq_ctx* ctx, long max_scalar_mults) {
+    if (!ctx) return QQ_ERR_ARG;
+    ctx->vbc_max_jobs = max_scalar_mults;
     return QQ_OK;
 }
 extern "C" int qq_fixed_base_set_window(qq_ctx* ctx, int which, int window_bits) {
@@ -862,6 +896,31 @@ static int core_msm_to_point(qq_ctx* ctx, const uint8_t* scalars, const uint8_t*
 
 static int core_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* points, const uint32_t* offsets, size_t m,
                           size_t nterms, uint8_t* out, uint8_t* status) {
+    // Few instances (one proof's worth): four lanes per instance, no ordering pass, direct encoder -- 4 launches
+    if (ctx->vbc_max_jobs != 0 && m <= (size_t)ctx->sms * 24) {
+        if (!ctx->stc_ready) {
+            CK(cudaFuncSetAttribute(k_straus_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, QQ_STC_SMEM_BYTES));
+            ctx->stc_ready = true;
+        }
+        CKQ(ws_begin(ctx, ws_need({nterms * QQ_PT_BYTES, nterms, nterms, m * QQ_PT_BYTES}) + dc_scratch_bytes(m)));
+        u32x4* P = ws_take<u32x4>(ctx, nterms * QQ_PT_BYTES);
+        uint8_t* ok = ws_take<uint8_t>(ctx, nterms);
+        uint8_t* tst = ws_take<uint8_t>(ctx, nterms);
+        u32x4* half = ws_take<u32x4>(ctx, m * QQ_PT_BYTES);
+        dc_ws dc = dc_take(ctx, m);
+        CKQ(launch_decompress(ctx, points, IDENT, P, ok, nterms));
+        CKQ(launch_status(ctx, scalars, nullptr, nullptr, ok, 1, tst, nterms));
+        straus_args a;
+        a.pts = P; a.scalars = (const u32x4*)scalars; a.offsets = offsets; a.term_status = tst;
+        a.out = (u32x4*)out; a.half_out = half; a.status = status; a.scratch = nullptr; a.order = nullptr; a.m = m;
+        span_begin(ctx, FAM_VB);
+        k_straus_coop<<<(unsigned)((m + 7) / 8), 32, QQ_STC_SMEM_BYTES, ctx->stream>>>(a);
+        span_end(ctx);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        CKQ(launch_finish_dbl(ctx, dc, fsrc(half, IDENT), FNONE, FNONE, out, IDENT, status, 1, m));
+        return QQ_OK;
+    }
     // 128-thread blocks, 2 per SM, no barrier: a batch holds only a few instances per thread, the lockstep forms of
     // k_varbase (256 x 1, 512 x 1 with a barrier per instance) measured 0-5 % slower here
     const int sblock = 128;

@@ -933,3 +933,52 @@ def test_verify_zero_balance_and_sender_account_proofs(engine):
     with pytest.raises(ValueError, match="Account Verify: Failed"):
         api.Verifier.verify_account_verifier_bulletproof(A(k[0]), A(k[1]), api.RistrettoPublicKey(k[2]), S_(k[3]), S_(k[4]),
                                                          S_(k[5]), sb(k[6]))
+
+
+def test_small_batch_paths_equal_regular_paths(engine):
+    """The latency paths taken by small calls (four lanes per scalar multiplication: k_varbase_coop, k_straus_coop; the
+    direct batch encoder k_dc_direct) against the throughput paths (qq_varbase_set_coop_limit(0)) and the oracle, on
+    the same inputs: ragged segmented MSMs of 0..23 terms (chunks of 9), edge scalars, undecodable points."""
+    st = Stream(b"small-paths")
+    scal, pts, offs = [], [], [0]
+    edge = [0, 1, 8, R.L - 1, R.L - 8, 2**252]
+    for j, k in enumerate([2, 3, 0, 9, 10, 1, 19, 23, 2, 3, 3, 2, 18, 5, 7, 2, 3]):
+        for t in range(k):
+            scal.append(sb(edge[(j + t) % len(edge)]) if (j + t) % 4 == 0 else st.scalar_bytes())
+            pts.append(R.compress(R.mul(st.scalar(), R.BASEPOINT)) if (j * 7 + t) % 11 else bytes(32))   # some identities
+        offs.append(len(scal))
+    scal += [st.scalar_bytes(), R.L.to_bytes(32, "little"), st.scalar_bytes()]                           # non-canonical scalar
+    pts += [pts[0], pts[1], pts[3]]
+    offs.append(len(scal))
+    scal += [st.scalar_bytes(), st.scalar_bytes()]
+    pts += [invalid_encodings()[5][1], pts[0]]                                                           # undecodable point
+    offs.append(len(scal))
+    offs = np.array(offs, np.uint32)
+    n = 40
+    accs = cat([make_account(st, v)[0] for v in range(n)])
+    bl = cat([sb(edge[i % len(edge)]) if i % 3 == 0 else st.scalar_bytes() for i in range(n)])
+    u, c = cat([st.scalar_bytes() for _ in range(n)]), cat([sb(edge[i % len(edge)]) if i % 5 == 0 else st.scalar_bytes() for i in range(n)])
+    got = {}
+    try:
+        for name, limit in (("regular", 0), ("small", -1)):
+            engine.varbase_set_coop_limit(limit)
+            got[name] = (engine.msm_segmented(cat(scal), cat(pts), offs), engine.update_account(accs, bl, u, c),
+                         engine.update_public_key(accs.reshape(n, 128)[:, :64].copy(), u),
+                         engine.generate_commitment(accs.reshape(n, 128)[:, :64].copy(), u, bl),
+                         engine.verify_account(accs, u, bl))
+    finally:
+        engine.varbase_set_coop_limit(-1)
+    for a, b in zip(got["regular"], got["small"]):
+        if isinstance(a, tuple):
+            assert all((x == y).all() for x, y in zip(a, b))
+        else:
+            assert (a == b).all()
+    out, status = got["small"][0]
+    for j in range(len(offs) - 1):
+        exp, es = R.msm(scal[offs[j]:offs[j + 1]], pts[offs[j]:offs[j + 1]])
+        assert status[j] == es and out[j].tobytes() == exp, j
+    out, status = got["small"][1]
+    for i in range(0, n, 7):
+        exp, es = R.update_account(accs[128 * i:128 * i + 128].tobytes(), bl[32 * i:32 * i + 32].tobytes(),
+                                   u[32 * i:32 * i + 32].tobytes(), c[32 * i:32 * i + 32].tobytes())
+        assert status[i] == es and out[i].tobytes() == exp, i

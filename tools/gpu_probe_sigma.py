@@ -34,6 +34,18 @@ def main():
     print(json.dumps({"probe": "verify_update_account_dlog", "proofs": B, "accounts_per_proof": n, "msms": 2 * items,
                       "wall_s": dt, "proofs_per_s": B / dt, "kernel_ms": eng.last_kernel_ms,
                       "all_rejected": bool((st == 6).all())}))
+    # one proof at a time (the latency a single verification sees), small-batch paths on / off
+    for name, limit in (("off", 0), ("default", -1)):
+        eng.varbase_set_coop_limit(limit)
+        ts = []
+        for rep in range(12):
+            t = time.perf_counter()
+            st1 = eng.verify_update_account_dlog(ia[:n], da[:n], z[:n], x[:1], n)
+            ts.append((time.perf_counter() - t) * 1e3)
+        print(json.dumps({"probe": "verify_update_account_dlog_single", "small_batch_paths": name, "accounts_per_proof": n,
+                          "msms": 2 * n, "ms_median": float(np.median(ts)), "kernel_ms": eng.last_kernel_ms,
+                          "same_verdict": bool(st1[0] == st[0])}))
+    eng.varbase_set_coop_limit(-1)
     eng.close()
 
 
