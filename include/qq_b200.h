@@ -258,6 +258,32 @@ int qq_verify_update_account_dark_tx_batch(qq_ctx* ctx, const char* transcript_l
                                            const uint8_t* delta_accounts, const uint8_t* output_accounts, const uint8_t* z,
                                            const uint8_t* x, size_t n, size_t nproofs, uint8_t* status);
 
+/* ---- leaf arguments of the Bayer-Groth shuffle proof (src/shuffle, ROWS = COLUMNS = 3) ---------------------------------
+ * Per proof: Merlin transcript and scalar algebra on the host threads, every group equation as one MSM that must be the
+ * identity, all MSMs of all proofs in one GPU batch.  transcript_label / verifier_label: the labels the caller used for
+ * Transcript::new / Verifier::new (the sub-proofs of a ShuffleProof share one running transcript in the reference; these
+ * entry points verify stand-alone arguments, as the reference's own unit tests do).
+ *
+ * DDHProof::verify_ddh_proof (src/shuffle/ddh.rs:109-142): all arrays nproofs x 32 B.  status[p]: QQ_ST_OK, QQ_ST_PROOF or
+ * QQ_ST_BAD_POINT (both Err("DDH Proof Verify: Failed")), QQ_ST_BAD_SCALAR. */
+int qq_verify_ddh_batch(qq_ctx* ctx, const char* transcript_label, const char* verifier_label, const uint8_t* g,
+                        const uint8_t* h, const uint8_t* g_dash, const uint8_t* h_dash, const uint8_t* challenge,
+                        const uint8_t* z, size_t nproofs, uint8_t* status);
+/* SVPProof::verify (src/shuffle/singlevalueproduct.rs:175-257).  commitment_a, b (SVPStatement): nproofs x 32 B; proof:
+ * nproofs x 352 B = commitment_d | commitment_delta_small | commitment_delta_capital | a_twildle[3] | b_twildle[3] |
+ * r_twildle | s_twildle.  status[p]: QQ_ST_OK, QQ_ST_PROOF = Err("SingleValue Product Proof Verify: Failed"),
+ * QQ_ST_BAD_POINT = Err("SingleValue Product Proof Verify: Decompression Failed"), QQ_ST_BAD_SCALAR. */
+int qq_verify_svp_batch(qq_ctx* ctx, const char* transcript_label, const char* verifier_label, const uint8_t* commitment_a,
+                        const uint8_t* b, const uint8_t* proof, size_t nproofs, uint8_t* status);
+/* HadamardProof::verify (src/shuffle/hadamard.rs:249-389).  omega (HadamardStatement), commit_a, commit_b, commit_c:
+ * nproofs x 96 B; proof: nproofs x 640 B = commitment_a_0 | commitment_b_0 | commitment_c_0 | commitment_delta[4] | a_bar[3]
+ * | b_bar[3] | c_bar[3] | r_bar | s_bar | t_bar | rho_bar.  status[p]: QQ_ST_OK, QQ_ST_BAD_POINT = Err("HadamardProof Verify:
+ * Decompression Failed"), QQ_ST_BAD_SCALAR, QQ_ST_PROOF with detail[p] (detail may be NULL): 1 = "Omega values are not
+ * unique", 2 = "A_bar , B_bar, C_bar check failed", 3 = "Delta Commitment check failed". */
+int qq_verify_hadamard_batch(qq_ctx* ctx, const char* transcript_label, const char* verifier_label, const uint8_t* omega,
+                             const uint8_t* commit_a, const uint8_t* commit_b, const uint8_t* commit_c, const uint8_t* proof,
+                             size_t nproofs, uint8_t* status, uint8_t* detail);
+
 /* ---- decommit ------------------------------------------------------------------------------------------------------
  * ElGamalCommitment::decommit(sk) = enc(d - sk*c) = enc(v*B)                    src/elgamal/elgamal.rs:106-108 */
 int qq_decommit_batch(qq_ctx* ctx, const uint8_t* comm, const uint8_t* sk, uint8_t* out_points, uint8_t* status, size_t n);

@@ -1,0 +1,302 @@
+"""TEST INFRASTRUCTURE (oracle): the leaf arguments of the reference's Bayer-Groth shuffle proof, restated for the parity
+tests - prover and verifier of each, following the reference line by line:
+  DDH tuple proof            src/shuffle/ddh.rs:50-142
+  single value product (SVP) src/shuffle/singlevalueproduct.rs:61-257
+  Hadamard product           src/shuffle/hadamard.rs:96-389, polynomials src/shuffle/polynomial.rs:350-515
+Scalars are Python ints mod l, points are 32-byte encodings.  Blinding scalars are arguments (the reference draws them
+from a transcript RNG; any value gives a valid proof).  Never imported by the product."""
+import ristretto_ref as R
+from merlin_ref import Transcript
+
+L = R.L
+ROWS = COLUMNS = 3
+
+
+def sb(k):
+    return (k % L).to_bytes(32, "little")
+
+
+def exp_iter(x, n, skip=0):
+    """vectorutil::exp_iter(x).skip(skip).take(n): 1, x, x^2, ..."""
+    out, cur = [], 1
+    for i in range(skip + n):
+        if i >= skip:
+            out.append(cur)
+        cur = cur * x % L
+    return out
+
+
+class XpcGens:
+    """VectorPedersenGens::new(capacity): commit(values, blinding) = blinding * H + sum values_i * G_i."""
+
+    def __init__(self, capacity):
+        self.h, self.g = R.vector_pedersen_gens(capacity)
+
+    def commit_point(self, values, blinding):
+        acc = R.mul(blinding % L, R.decompress(self.h))
+        for v, g in zip(values, self.g):
+            acc = R.add(acc, R.mul(v % L, R.decompress(g)))
+        return acc
+
+    def commit(self, values, blinding):
+        return R.compress(self.commit_point(values, blinding))
+
+
+def _msm_point(scalars, points):
+    """sum s_i * P_i as a point, or None when a point does not decode."""
+    acc = R.IDENTITY if hasattr(R, "IDENTITY") else R.mul(0, R.BASEPOINT)
+    for s, p in zip(scalars, points):
+        q = R.decompress(p)
+        if q is None:
+            return None
+        acc = R.add(acc, R.mul(s % L, q))
+    return acc
+
+
+def new_transcript(transcript_label, side_label):
+    tr = Transcript(transcript_label)
+    tr.domain_sep(side_label)          # Prover::new / Verifier::new
+    return tr
+
+
+# ---- DDH tuple proof ---------------------------------------------------------------------------------------------------
+def ddh_prove(tr, g_i, h_i, exp_x, G, H, rho, r_scalar):
+    """-> ((challenge, z), (G_dash, H_dash)).  g_i, h_i, G, H: compressed points."""
+    tr.domain_sep(b"DDHTupleProof")
+    exp_x_rho = [x * rho % L for x in exp_x]
+    G_dash = R.compress(_msm_point(exp_x_rho, g_i))
+    H_dash = R.compress(_msm_point(exp_x_rho, h_i))
+    g_r = R.compress(R.mul(r_scalar % L, R.decompress(G)))
+    h_r = R.compress(R.mul(r_scalar % L, R.decompress(H)))
+    for label, p in ((b"g", G), (b"g_dash", G_dash), (b"h", H), (b"h_dash", H_dash), (b"gr", g_r), (b"hr", h_r)):
+        tr.append_point_var(label, p)
+    challenge = tr.get_challenge(b"Challenge")
+    return (challenge, (r_scalar - challenge * rho) % L), (G_dash, H_dash)
+
+
+def ddh_verify(tr, proof, statement, G, H):
+    """-> True, False or None (= Err on an undecodable point; the reference gives the same message for both)."""
+    challenge, z = proof
+    G_dash, H_dash = statement
+    tr.domain_sep(b"DDHTupleProof")
+    for label, p in ((b"g", G), (b"g_dash", G_dash), (b"h", H), (b"h_dash", H_dash)):
+        tr.append_point_var(label, p)
+    g_r = _msm_point([z, challenge], [G, G_dash])
+    if g_r is None:
+        return None
+    h_r = _msm_point([z, challenge], [H, H_dash])
+    if h_r is None:
+        return None
+    tr.append_point_var(b"gr", R.compress(g_r))
+    tr.append_point_var(b"hr", R.compress(h_r))
+    return tr.get_challenge(b"Challenge") == challenge % L
+
+
+# ---- single value product argument ---------------------------------------------------------------------------------------
+def svp_prove(tr, xpc, r, a_vec, d_vec, rd, delta_mid, s_1, s_x):
+    """-> proof dict.  a_vec: COLUMNS scalars committed in c_a = xpc.commit(a_vec, r); d_vec, rd, delta_mid (the random
+    middle entries of delta_vec, COLUMNS - 2 of them), s_1, s_x: the prover's randomness."""
+    tr.domain_sep(b"SingleValueProductProof")
+    bvec, prod = [], 1
+    for a in a_vec:
+        prod = prod * a % L
+        bvec.append(prod)
+    commit_d = xpc.commit(d_vec, rd)
+    delta_vec = [d_vec[0]] + list(delta_mid) + [0]
+    assert len(delta_vec) == COLUMNS
+    delta_lower = [(-delta_vec[i]) * d_vec[i + 1] % L for i in range(COLUMNS - 1)]
+    delta_upper = [(delta_vec[i + 1] - a_vec[i + 1] * delta_vec[i] - bvec[i] * d_vec[i + 1]) % L for i in range(COLUMNS - 1)]
+    trun = XpcGens(len(delta_lower) + 1)
+    c_small, c_cap = trun.commit(delta_lower, s_1), trun.commit(delta_upper, s_x)
+    tr.append_point_var(b"DeltaSmall", c_small)
+    tr.append_point_var(b"DeltaCapital", c_cap)
+    tr.append_point_var(b"d", commit_d)
+    x = tr.get_challenge(b"challenge")
+    return {"commitment_d": commit_d, "commitment_delta_small": c_small, "commitment_delta_capital": c_cap,
+            "a_twildle": [(a * x + d) % L for a, d in zip(a_vec, d_vec)],
+            "b_twildle": [(b * x + d) % L for b, d in zip(bvec, delta_vec)],
+            "r_twildle": (r * x + rd) % L, "s_twildle": (s_x * x + s_1) % L}
+
+
+def svp_verify(tr, proof, commitment_a, b, xpc):
+    """-> True, False ("SingleValue Product Proof Verify: Failed"), None (Decompression Failed), "size" (Size check failed)."""
+    at, bt = proof["a_twildle"], proof["b_twildle"]
+    if len(at) != COLUMNS or len(bt) != COLUMNS:
+        return "size"
+    if at[0] % L != bt[0] % L:
+        return False
+    tr.domain_sep(b"SingleValueProductProof")
+    tr.append_point_var(b"DeltaSmall", proof["commitment_delta_small"])
+    tr.append_point_var(b"DeltaCapital", proof["commitment_delta_capital"])
+    tr.append_point_var(b"d", proof["commitment_d"])
+    x = tr.get_challenge(b"challenge")
+    if b * x % L != bt[COLUMNS - 1] % L:
+        return False
+    comit_a_bar = xpc.commit_point(at, proof["r_twildle"])
+    lhs = _msm_point([x, 1], [commitment_a, proof["commitment_d"]])
+    if lhs is None:
+        return None
+    if not R.eq(lhs, comit_a_bar):
+        return False
+    lhs2 = _msm_point([x, 1], [proof["commitment_delta_capital"], proof["commitment_delta_small"]])
+    if lhs2 is None:
+        return None
+    comvec = [(bt[i + 1] * x - bt[i] * at[i + 1]) % L for i in range(COLUMNS - 1)]
+    trun = XpcGens(len(comvec) + 1)
+    return bool(R.eq(lhs2, trun.commit_point(comvec, proof["s_twildle"])))
+
+
+# ---- polynomials over Z/l (coefficient lists, lowest degree first) ----------------------------------------------------------
+def poly_mul(a, b):
+    out = [0] * (len(a) + len(b) - 1)
+    for i, x in enumerate(a):
+        for j, y in enumerate(b):
+            out[i + j] = (out[i + j] + x * y) % L
+    return out
+
+
+def poly_add(a, b):
+    n = max(len(a), len(b))
+    return [((a[i] if i < len(a) else 0) + (b[i] if i < len(b) else 0)) % L for i in range(n)]
+
+
+def poly_sub(a, b):
+    return poly_add(a, [(-x) % L for x in b])
+
+
+def poly_scale(a, s):
+    return [x * s % L for x in a]
+
+
+def poly_eval(a, x):
+    acc = 0
+    for c in reversed(a):
+        acc = (acc * x + c) % L
+    return acc
+
+
+def poly_divexact(num, den):
+    num = list(num)
+    out = [0] * (len(num) - len(den) + 1)
+    inv_lead = pow(den[-1], -1, L)
+    for k in range(len(out) - 1, -1, -1):
+        q = num[k + len(den) - 1] * inv_lead % L
+        out[k] = q
+        for j, d in enumerate(den):
+            num[k + j] = (num[k + j] - q * d) % L
+    assert all(v == 0 for v in num), "polynomial division left a remainder"
+    return out
+
+
+def l_polys(w):
+    """polynomial::create_l_i_x_polynomial: [l(X) = prod (X - w_j), l_1(X), l_2(X), l_3(X)] (Lagrange basis on w)."""
+    def lx(ws):
+        p = [1]
+        for v in ws:
+            p = poly_mul(p, [(-v) % L, 1])
+        return p
+    out = [lx(w)]
+    for i in range(3):
+        others = [w[j] for j in range(3) if j != i]
+        den = 1
+        for o in others:
+            den = den * (w[i] - o) % L
+        out.append(poly_scale(lx(others), pow(den, -1, L)))
+    return out
+
+
+def l_evals(w, x):
+    """[l(x), l_1(x), l_2(x), l_3(x)] - what the verifier needs."""
+    return [poly_eval(p, x) for p in l_polys(w)]
+
+
+# ---- Hadamard product argument ------------------------------------------------------------------------------------------
+def hadamard_prove(tr, xpc, a, b, c, commit_a, commit_b, commit_c, wr, ws, wt, rnd):
+    """a, b, c: ROWS x COLUMNS matrices as lists of rows with c = a o b; commit_x[i] = xpc.commit(x[i], w_x[i]).
+    rnd: dict with a_0, b_0 (COLUMNS each), r_0, s_0, t_0, omega (3 distinct), rho (ROWS + 1).
+    -> (proof dict, omega)."""
+    tr.domain_sep(b"HadamardProductProof")
+    for pa, pb, pc in zip(commit_a, commit_b, commit_c):
+        tr.append_point_var(b"c_a", pa)
+        tr.append_point_var(b"c_b", pb)
+        tr.append_point_var(b"c_c", pc)
+    a_0, b_0 = rnd["a_0"], rnd["b_0"]
+    c_0 = [x * y % L for x, y in zip(a_0, b_0)]
+    c_a_0, c_b_0, c_c_0 = xpc.commit(a_0, rnd["r_0"]), xpc.commit(b_0, rnd["s_0"]), xpc.commit(c_0, rnd["t_0"])
+    omega = rnd["omega"]
+    lp = l_polys(omega)
+
+    def expression(m, m0):
+        # compute_polynomial_expression: column j -> m0[j] l(X) + sum_i m[i][j] l_{i+1}(X)
+        out = []
+        for j in range(COLUMNS):
+            p = poly_scale(lp[0], m0[j])
+            for i in range(ROWS):
+                p = poly_add(p, poly_scale(lp[i + 1], m[i][j]))
+            out.append(p)
+        return out
+    ae, be, ce = expression(a, a_0), expression(b, b_0), expression(c, c_0)
+    div = [poly_divexact(poly_sub(poly_mul(x, y), z), lp[0]) for x, y, z in zip(ae, be, ce)]
+    delta_vec = [[(div[j][i] if i < len(div[j]) else 0) for j in range(3)] for i in range(4)]
+    rho = rnd["rho"]
+    c_delta = [xpc.commit(row, rho[i]) for i, row in enumerate(delta_vec)]
+    tr.append_point_var(b"c_a_0", c_a_0)
+    tr.append_point_var(b"c_b_0", c_b_0)
+    tr.append_point_var(b"c_c_0", c_c_0)
+    for cd in c_delta:
+        tr.append_point_var(b"c_delta", cd)
+    x = tr.get_challenge(b"challenge")
+    ev = [poly_eval(p, x) for p in lp]
+    r_bar = (rnd["r_0"] * ev[0] + sum(wr[i] * ev[i + 1] for i in range(3))) % L
+    s_bar = (rnd["s_0"] * ev[0] + sum(ws[i] * ev[i + 1] for i in range(3))) % L
+    t_bar = (rnd["t_0"] * ev[0] + sum(wt[i] * ev[i + 1] for i in range(3))) % L
+    xs = exp_iter(x, 4)
+    rho_bar = ev[0] * (sum(p * r for p, r in zip(xs, rho)) % L) % L
+    proof = {"commitment_a_0": c_a_0, "commitment_b_0": c_b_0, "commitment_c_0": c_c_0, "commitment_delta": c_delta,
+             "a_bar": [poly_eval(p, x) for p in ae], "b_bar": [poly_eval(p, x) for p in be],
+             "c_bar": [poly_eval(p, x) for p in ce], "r_bar": r_bar, "s_bar": s_bar, "t_bar": t_bar, "rho_bar": rho_bar}
+    return proof, list(omega)
+
+
+def hadamard_verify(tr, proof, omega, commit_a, commit_b, commit_c, xpc):
+    """-> True, None (Decompression Failed), or the reference's message tail: "omega", "abc", "delta"."""
+    if len({w % L for w in omega}) != 3:
+        return "omega"
+    tr.domain_sep(b"HadamardProductProof")
+    for pa, pb, pc in zip(commit_a, commit_b, commit_c):
+        tr.append_point_var(b"c_a", pa)
+        tr.append_point_var(b"c_b", pb)
+        tr.append_point_var(b"c_c", pc)
+    tr.append_point_var(b"c_a_0", proof["commitment_a_0"])
+    tr.append_point_var(b"c_b_0", proof["commitment_b_0"])
+    tr.append_point_var(b"c_c_0", proof["commitment_c_0"])
+    for cd in proof["commitment_delta"]:
+        tr.append_point_var(b"c_delta", cd)
+    x = tr.get_challenge(b"challenge")
+    ev = l_evals(omega, x)
+    bars = [xpc.commit_point(proof["a_bar"], proof["r_bar"]), xpc.commit_point(proof["b_bar"], proof["s_bar"]),
+            xpc.commit_point(proof["c_bar"], proof["t_bar"])]
+    zeros = [R.decompress(proof[k]) for k in ("commitment_a_0", "commitment_b_0", "commitment_c_0")]
+    if any(z is None for z in zeros):
+        return None
+    sums = [R.mul(ev[0], z) for z in zeros]
+    for i in range(3):
+        for k, cm in enumerate((commit_a, commit_b, commit_c)):
+            p = R.decompress(cm[i])
+            if p is None:
+                return None
+            sums[k] = R.add(sums[k], R.mul(ev[i + 1], p))
+    if not all(R.eq(s, bar) for s, bar in zip(sums, bars)):
+        return "abc"
+    xs = exp_iter(x, 4)
+    acc = R.decompress(proof["commitment_delta"][0])
+    if acc is None:
+        return None
+    for i in range(1, 4):
+        p = R.decompress(proof["commitment_delta"][i])
+        if p is None:
+            return None
+        acc = R.add(acc, R.mul(xs[i], p))
+    lhs = R.mul(ev[0], acc)
+    diff = [(a * b - c) % L for a, b, c in zip(proof["a_bar"], proof["b_bar"], proof["c_bar"])]
+    return True if R.eq(lhs, xpc.commit_point(diff, proof["rho_bar"])) else "delta"

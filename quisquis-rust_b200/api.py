@@ -374,3 +374,68 @@ class Verifier:
         if st[0]:
             raise ValueError("Update Output Challenge : DLOG Proof Verify: Failed")
         return None
+
+
+# ---- leaf arguments of the shuffle proof (src/shuffle/{ddh,singlevalueproduct,hadamard}.rs) ---------------------------------
+# The reference's verify methods receive a `Verifier` carrying the running Merlin transcript; here the two labels that
+# built it are keyword arguments (defaults: the labels of the reference's own unit tests).
+class DDHProof:
+    def __init__(self, challenge, z):
+        self.challenge, self.z = _b(challenge, 32), _b(z, 32)
+
+    def verify_ddh_proof(self, statement, G, H, transcript_label=b"ShuffleProof", verifier_label=b"DDHTuple"):
+        """src/shuffle/ddh.rs:109-142; statement = (G_dash, H_dash).  Returns None or raises ValueError."""
+        st = default_engine().verify_ddh(bytes(G), bytes(H), bytes(statement[0]), bytes(statement[1]), self.challenge, self.z,
+                                         transcript_label, verifier_label)
+        if st[0]:
+            raise ValueError("DDH Proof Verify: Failed")
+        return None
+
+
+class SVPProof:
+    FIELDS = ("commitment_d", "commitment_delta_small", "commitment_delta_capital", "a_twildle", "b_twildle", "r_twildle",
+              "s_twildle")
+
+    def __init__(self, **kw):
+        for f in self.FIELDS:
+            setattr(self, f, kw[f])
+
+    def verify(self, svparg, transcript_label=b"SingleValue", verifier_label=b"Shuffle"):
+        """src/shuffle/singlevalueproduct.rs:175-257; svparg = (commitment_a, b)."""
+        if len(self.a_twildle) != 3 or len(self.b_twildle) != 3:
+            raise ValueError("SingleValue Product Proof Verify: Size check failed")
+        blob = (bytes(self.commitment_d) + bytes(self.commitment_delta_small) + bytes(self.commitment_delta_capital) +
+                b"".join(bytes(s) for s in self.a_twildle) + b"".join(bytes(s) for s in self.b_twildle) +
+                bytes(self.r_twildle) + bytes(self.s_twildle))
+        st = default_engine().verify_svp(bytes(svparg[0]), bytes(svparg[1]), blob, transcript_label, verifier_label)
+        if st[0] == B.ST_BAD_POINT:
+            raise ValueError("SingleValue Product Proof Verify: Decompression Failed")
+        if st[0]:
+            raise ValueError("SingleValue Product Proof Verify: Failed")
+        return None
+
+
+class HadamardProof:
+    FIELDS = ("commitment_a_0", "commitment_b_0", "commitment_c_0", "commitment_delta", "a_bar", "b_bar", "c_bar", "r_bar",
+              "s_bar", "t_bar", "rho_bar")
+    MESSAGES = {1: "Hadamard Proof Verify: Omega values are not unique",
+                2: "Hadamard Proof Verify: A_bar , B_bar, C_bar check failed",
+                3: "Hadamard Proof Verify: Delta Commitment check failed"}
+
+    def __init__(self, **kw):
+        for f in self.FIELDS:
+            setattr(self, f, kw[f])
+
+    def verify(self, hstatement, commit_a, commit_b, commit_c, transcript_label=b"Hadamard", verifier_label=b"Shuffle"):
+        """src/shuffle/hadamard.rs:249-389; hstatement = omega (3 scalars)."""
+        j = lambda v: b"".join(bytes(s) for s in v)  # noqa: E731
+        blob = (bytes(self.commitment_a_0) + bytes(self.commitment_b_0) + bytes(self.commitment_c_0) + j(self.commitment_delta) +
+                j(self.a_bar) + j(self.b_bar) + j(self.c_bar) + bytes(self.r_bar) + bytes(self.s_bar) + bytes(self.t_bar) +
+                bytes(self.rho_bar))
+        st, det = default_engine().verify_hadamard(j(hstatement), j(commit_a), j(commit_b), j(commit_c), blob, transcript_label,
+                                                   verifier_label)
+        if st[0] == B.ST_BAD_POINT:
+            raise ValueError("HadamardProof Verify: Decompression Failed")
+        if st[0]:
+            raise ValueError(self.MESSAGES.get(int(det[0]), "Hadamard Proof Verify: failed"))
+        return None

@@ -22,6 +22,7 @@ EXPORTS = [
     "qq_fixed_base_i64_batch", "qq_fixed_base_i64_batch_dev", "qq_msm", "qq_msm_dev", "qq_msm_partial", "qq_msm_partial_dev",
     "qq_points_sum", "qq_msm_segmented", "qq_msm_points_prepare", "qq_msm_points_prepare_dev", "qq_msm_points_free",
     "qq_msm_points_count", "qq_msm_prepared", "qq_msm_prepared_dev",
+    "qq_verify_ddh_batch", "qq_verify_svp_batch", "qq_verify_hadamard_batch",
     "qq_verify_account_sigma_batch", "qq_verify_zero_balance_batch", "qq_verify_destroy_account_batch",
     "qq_verify_same_value_compact_batch", "qq_verify_update_account_dark_tx_batch",
     "qq_verify_update_account_dlog_batch", "qq_verify_delta_compact_batch", "qq_decommit_batch", "qq_decommit_value_batch", "qq_from_uniform_bytes_batch", "qq_vector_pedersen_gens", "qq_bulletproof_gens",
@@ -99,6 +100,9 @@ def load_library():
     lib.qq_verify_destroy_account_batch.argtypes = [vp, cs, cs, u8p, u8p, u8p, sz, sz, u8p]
     lib.qq_verify_same_value_compact_batch.argtypes = [vp, u8p, u8p, u8p, u8p, u8p, sz, u8p]
     lib.qq_verify_update_account_dark_tx_batch.argtypes = [vp, cs, cs, u8p, u8p, u8p, u8p, sz, sz, u8p]
+    lib.qq_verify_ddh_batch.argtypes = [vp, cs, cs, u8p, u8p, u8p, u8p, u8p, u8p, sz, u8p]
+    lib.qq_verify_svp_batch.argtypes = [vp, cs, cs, u8p, u8p, u8p, sz, u8p]
+    lib.qq_verify_hadamard_batch.argtypes = [vp, cs, cs, u8p, u8p, u8p, u8p, u8p, sz, u8p, u8p]
     lib.qq_decommit_batch.argtypes = [vp, u8p, u8p, u8p, u8p, sz]
     lib.qq_decommit_value_batch.argtypes = [vp, u8p, u8p, ctypes.c_int, u8p, u8p, sz]
     lib.qq_from_uniform_bytes_batch.argtypes = [vp, u8p, u8p, sz]
@@ -425,6 +429,39 @@ class Engine:
                                                                   _ptr(z), _ptr(x), n, nproofs, _ptr(st)),
                  "qq_verify_update_account_dark_tx_batch")
         return st
+
+    def verify_ddh(self, g, h, g_dash, h_dash, challenge, z, transcript_label=b"ShuffleProof", verifier_label=b"DDHTuple"):
+        """DDHProof::verify_ddh_proof, one proof per 32-byte element -> status per proof."""
+        g, h, gd, hd, ch, z = (_u8(a) for a in (g, h, g_dash, h_dash, challenge, z))
+        nproofs = z.size // 32
+        for a in (g, h, gd, hd, ch):
+            _u8(a, nproofs * 32)
+        st = np.zeros(nproofs, np.uint8)
+        self._ck(self.lib.qq_verify_ddh_batch(self.h, transcript_label, verifier_label, _ptr(g), _ptr(h), _ptr(gd), _ptr(hd),
+                                               _ptr(ch), _ptr(z), nproofs, _ptr(st)), "qq_verify_ddh_batch")
+        return st
+
+    def verify_svp(self, commitment_a, b, proof, transcript_label=b"SingleValue", verifier_label=b"Shuffle"):
+        """SVPProof::verify; proof: 352 bytes per proof (see include/qq_b200.h) -> status per proof."""
+        ca, b, pr = _u8(commitment_a), _u8(b), _u8(proof)
+        nproofs = b.size // 32
+        _u8(ca, nproofs * 32), _u8(pr, nproofs * 352)
+        st = np.zeros(nproofs, np.uint8)
+        self._ck(self.lib.qq_verify_svp_batch(self.h, transcript_label, verifier_label, _ptr(ca), _ptr(b), _ptr(pr), nproofs,
+                                               _ptr(st)), "qq_verify_svp_batch")
+        return st
+
+    def verify_hadamard(self, omega, commit_a, commit_b, commit_c, proof, transcript_label=b"Hadamard",
+                        verifier_label=b"Shuffle"):
+        """HadamardProof::verify; proof: 640 bytes per proof -> (status, detail) per proof."""
+        om, ca, cb, cc, pr = (_u8(a) for a in (omega, commit_a, commit_b, commit_c, proof))
+        nproofs = om.size // 96
+        _u8(ca, nproofs * 96), _u8(cb, nproofs * 96), _u8(cc, nproofs * 96), _u8(pr, nproofs * 640)
+        st, det = np.zeros(nproofs, np.uint8), np.zeros(nproofs, np.uint8)
+        self._ck(self.lib.qq_verify_hadamard_batch(self.h, transcript_label, verifier_label, _ptr(om), _ptr(ca), _ptr(cb),
+                                                    _ptr(cc), _ptr(pr), nproofs, _ptr(st), _ptr(det)),
+                 "qq_verify_hadamard_batch")
+        return st, det
 
     def decommit(self, comm, sk):
         comm, sk = _u8(comm), _u8(sk)

@@ -16,6 +16,7 @@
 #include "fixedbase_big.cuh"
 #include "keccak_host.hpp"
 #include "merlin_host.hpp"
+#include "sc_host.hpp"
 #include "decommit.cuh"
 
 using namespace qq;
@@ -60,6 +61,8 @@ struct qq_ctx {
     std::vector<span> spans;
     int ev_used = 0;
     int vb_blocks_per_sm[3] = {0, 0, 0};
+    bool xpc_ready = false;                    // VectorPedersenGens::new(4): H, G_vec (compressed), derived on first use
+    uint8_t xpc_h[32], xpc_g[96];
     bool stc_ready = false;                    // k_straus_coop's shared-memory opt-in done
     long vbc_max_jobs = -1;                    // four-lane cooperative variable base up to this many scalar mults (< 0: sms * 160)
 };
@@ -1275,3 +1278,4 @@ extern "C" int qq_fixed_base_i64_batch(qq_ctx* ctx, int which, const int64_t* v,
 
 #include "qq_api_msm.inc"
 #include "qq_api_sigma.inc"
+#include "qq_api_shuffle.inc"

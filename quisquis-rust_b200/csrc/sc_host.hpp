@@ -1,0 +1,148 @@
+// Host-side arithmetic in Z/l, l = 2^252 + 27742317777372353535851937790883648493 (the Ristretto255 scalar field), for the
+// verifier drivers that run next to the GPU batches: challenge powers, polynomial evaluation, the scalar checks of the
+// Bayer-Groth sub-arguments (reference src/shuffle/*.rs use curve25519_dalek::scalar::Scalar for the same).
+// Four 64-bit limbs, values always canonical (< l); multiplication = 4x4 schoolbook + Barrett reduction (HAC 14.42,
+// b = 2^64, k = 4, mu = floor(2^512 / l)).  No secrets are handled here (verifier side): not constant time.
+#pragma once
+#include <cstdint>
+#include <cstring>
+
+namespace qq_sc {
+
+typedef unsigned __int128 u128;
+
+struct sc {
+    uint64_t v[4];
+    bool operator==(const sc& o) const { return v[0] == o.v[0] && v[1] == o.v[1] && v[2] == o.v[2] && v[3] == o.v[3]; }
+    bool operator!=(const sc& o) const { return !(*this == o); }
+};
+
+static const uint64_t L[4] = {0x5812631a5cf5d3edULL, 0x14def9dea2f79cd6ULL, 0ULL, 0x1000000000000000ULL};
+static const uint64_t MU[5] = {0xed9ce5a30a2c131bULL, 0x2106215d086329a7ULL, 0xffffffffffffffebULL, 0xffffffffffffffffULL, 0xfULL};
+
+static inline sc zero() { return sc{{0, 0, 0, 0}}; }
+static inline sc one() { return sc{{1, 0, 0, 0}}; }
+static inline sc from_u64(uint64_t x) { return sc{{x, 0, 0, 0}}; }
+static inline bool is_zero(const sc& a) { return (a.v[0] | a.v[1] | a.v[2] | a.v[3]) == 0; }
+
+// a >= l ?
+static inline bool geq_l(const uint64_t a[4]) {
+    for (int i = 3; i >= 0; i--) {
+        if (a[i] != L[i]) return a[i] > L[i];
+    }
+    return true;
+}
+// canonical 32 little-endian bytes -> sc; false when the value is >= l
+static inline bool from_bytes(sc& out, const uint8_t b[32]) {
+    memcpy(out.v, b, 32);
+    return !geq_l(out.v);
+}
+static inline void to_bytes(uint8_t b[32], const sc& a) { memcpy(b, a.v, 32); }
+
+static inline sc add(const sc& a, const sc& b) {
+    sc r;
+    u128 c = 0;
+    for (int i = 0; i < 4; i++) {
+        c += (u128)a.v[i] + b.v[i];
+        r.v[i] = (uint64_t)c;
+        c >>= 64;
+    }
+    if (geq_l(r.v)) {   // a + b < 2 l < 2^254: no carry out of limb 3
+        u128 br = 0;
+        for (int i = 0; i < 4; i++) {
+            u128 d = (u128)r.v[i] - L[i] - (uint64_t)br;
+            r.v[i] = (uint64_t)d;
+            br = (d >> 64) & 1;
+        }
+    }
+    return r;
+}
+static inline sc neg(const sc& a) {
+    if (is_zero(a)) return a;
+    sc r;
+    u128 br = 0;
+    for (int i = 0; i < 4; i++) {
+        u128 d = (u128)L[i] - a.v[i] - (uint64_t)br;
+        r.v[i] = (uint64_t)d;
+        br = (d >> 64) & 1;
+    }
+    return r;
+}
+static inline sc sub(const sc& a, const sc& b) { return add(a, neg(b)); }
+
+// x (8 limbs, < 2^512) mod l
+static inline sc reduce512(const uint64_t x[8]) {
+    // q1 = floor(x / b^3): limbs 3..7 (5 limbs); q2 = q1 * mu (10 limbs); q3 = floor(q2 / b^5): limbs 5..9
+    uint64_t q2[10] = {0};
+    for (int i = 0; i < 5; i++) {
+        u128 c = 0;
+        for (int j = 0; j < 5; j++) {
+            c += (u128)x[3 + i] * MU[j] + q2[i + j];
+            q2[i + j] = (uint64_t)c;
+            c >>= 64;
+        }
+        q2[i + 5] = (uint64_t)c;
+    }
+    const uint64_t* q3 = q2 + 5;
+    // r2 = q3 * l mod b^5
+    uint64_t r2[5] = {0};
+    for (int i = 0; i < 5; i++) {
+        u128 c = 0;
+        for (int j = 0; j < 4 && i + j < 5; j++) {
+            c += (u128)q3[i] * L[j] + r2[i + j];
+            r2[i + j] = (uint64_t)c;
+            c >>= 64;
+        }
+        if (i + 4 < 5) r2[i + 4] += (uint64_t)c;
+    }
+    // r = (x mod b^5) - r2 mod b^5   (0 <= r < 3 l)
+    uint64_t r[5];
+    u128 br = 0;
+    for (int i = 0; i < 5; i++) {
+        u128 d = (u128)x[i] - r2[i] - (uint64_t)br;
+        r[i] = (uint64_t)d;
+        br = (d >> 64) & 1;
+    }
+    for (int pass = 0; pass < 2; pass++) {
+        if (r[4] != 0 || geq_l(r)) {
+            u128 b2 = 0;
+            for (int i = 0; i < 5; i++) {
+                u128 d = (u128)r[i] - (i < 4 ? L[i] : 0) - (uint64_t)b2;
+                r[i] = (uint64_t)d;
+                b2 = (d >> 64) & 1;
+            }
+        }
+    }
+    return sc{{r[0], r[1], r[2], r[3]}};
+}
+static inline sc mul(const sc& a, const sc& b) {
+    uint64_t x[8] = {0};
+    for (int i = 0; i < 4; i++) {
+        u128 c = 0;
+        for (int j = 0; j < 4; j++) {
+            c += (u128)a.v[i] * b.v[j] + x[i + j];
+            x[i + j] = (uint64_t)c;
+            c >>= 64;
+        }
+        x[i + 4] = (uint64_t)c;
+    }
+    return reduce512(x);
+}
+// Scalar::from_bytes_mod_order_wide
+static inline sc from_wide(const uint8_t b[64]) {
+    uint64_t x[8];
+    memcpy(x, b, 64);
+    return reduce512(x);
+}
+// a^(l - 2)
+static inline sc invert(const sc& a) {
+    uint64_t e[4] = {L[0] - 2, L[1], L[2], L[3]};
+    sc r = one();
+    for (int bit = 252; bit >= 0; bit--) {
+        r = mul(r, r);
+        if ((e[bit >> 6] >> (bit & 63)) & 1) r = mul(r, a);
+    }
+    return r;
+}
+
+}  // namespace qq_sc

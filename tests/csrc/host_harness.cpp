@@ -6,6 +6,7 @@
 #include "../../quisquis-rust_b200/csrc/ristretto.cuh"
 #include "../../quisquis-rust_b200/csrc/scalarmult.cuh"
 #include "../../quisquis-rust_b200/csrc/compress_batch.cuh"
+#include "../../quisquis-rust_b200/csrc/sc_host.hpp"
 
 using namespace qq;
 
@@ -258,5 +259,20 @@ void hh_fb_mult(uint8_t* out, const u32* tbl, int W, const uint8_t* scalar) {
     else fb_scalarmult<8>(r, tbl, s);
     ristretto_compress(w, r);
     store_words(out, w);
+}
+// host scalar field (sc_host.hpp): op 0 add, 1 sub, 2 mul, 3 invert(a), 4 from_wide(a || b); returns 0 when an input is not canonical
+int hh_sc_op(uint8_t* out, int op, const uint8_t* a, const uint8_t* b) {
+    qq_sc::sc x, y, r;
+    if (op == 4) {
+        uint8_t w[64];
+        memcpy(w, a, 32);
+        memcpy(w + 32, b, 32);
+        r = qq_sc::from_wide(w);
+    } else {
+        if (!qq_sc::from_bytes(x, a) || !qq_sc::from_bytes(y, b)) return 0;
+        r = op == 0 ? qq_sc::add(x, y) : op == 1 ? qq_sc::sub(x, y) : op == 2 ? qq_sc::mul(x, y) : qq_sc::invert(x);
+    }
+    qq_sc::to_bytes(out, r);
+    return 1;
 }
 }

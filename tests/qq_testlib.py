@@ -152,3 +152,57 @@ def scenario_sender_account(st):
     eps, zv, zsk, zr, x = S.prove_account(senders, bl, sks[0:2], R.BASE_PK, [st.scalar(), st.scalar()],
                                           [(st.scalar(), st.scalar(), st.scalar()) for _ in range(2)])
     return senders, eps, R.BASE_PK, zv, zsk, zr, x
+
+
+# ---- leaf arguments of the shuffle proof: the reference's own test scenarios (src/shuffle/{ddh,singlevalueproduct,
+# hadamard}.rs tests) with proofs from the oracle's prover restatements (oracle/shuffle_ref.py)
+def scenario_ddh(st):
+    """ddh.rs:162-194 -> (G, H, G_dash, H_dash, challenge, z); transcript b"ShuffleProof" / b"DDHTuple"."""
+    import shuffle_ref as F
+    pks = [make_account(st, 0)[0][:64] for _ in range(9)]
+    g_i, h_i = [p[:32] for p in pks], [p[32:] for p in pks]
+    x, rho = st.scalar(), st.scalar()
+    exp_x = F.exp_iter(x, 9, skip=1)
+    G, H = R.compress(F._msm_point(exp_x, g_i)), R.compress(F._msm_point(exp_x, h_i))
+    tr = F.new_transcript(b"ShuffleProof", b"DDHTuple")
+    (challenge, z), (G_dash, H_dash) = F.ddh_prove(tr, g_i, h_i, exp_x, G, H, rho, st.scalar())
+    return G, H, G_dash, H_dash, challenge, z
+
+
+def scenario_svp(st, pi=(7, 6, 1, 5, 3, 4, 2, 8, 9)):
+    """singlevalueproduct.rs:269-327 -> (commitment_a, b, proof dict); transcript b"SingleValue" / b"Shuffle"."""
+    import shuffle_ref as F
+    xpc = F.XpcGens(4)
+    rows = [pi[0:3], pi[3:6], pi[6:9]]
+    bvec = [r[0] * r[1] * r[2] % R.L for r in rows]
+    s = st.scalar()
+    cb = xpc.commit(bvec, s)
+    b = bvec[0] * bvec[1] * bvec[2] % R.L
+    tr = F.new_transcript(b"SingleValue", b"Shuffle")
+    proof = F.svp_prove(tr, xpc, s, bvec, [st.scalar() for _ in range(3)], st.scalar(), [st.scalar()], st.scalar(),
+                        st.scalar())
+    return cb, b, proof
+
+
+def scenario_hadamard(st, random_matrices=False):
+    """hadamard.rs:395-470 -> (omega, commit_a, commit_b, commit_c, proof dict); transcript b"Hadamard" / b"Shuffle"."""
+    import shuffle_ref as F
+    xpc = F.XpcGens(4)
+    if random_matrices:
+        a = [[st.scalar() for _ in range(3)] for _ in range(3)]
+        b = [[st.scalar() for _ in range(3)] for _ in range(3)]
+        r, s, t = ([st.scalar() for _ in range(3)] for _ in range(3))
+    else:
+        av, bv = (7, 6, 1, 5, 3, 4, 2, 8, 9), (3, 2, 1, 7, 3, 5, 8, 3, 6)
+        a, b = [list(av[3 * i:3 * i + 3]) for i in range(3)], [list(bv[3 * i:3 * i + 3]) for i in range(3)]
+        r, s, t = [6, 2, 5], [7, 1, 3], [5, 2, 1]
+    c = [[x * y % R.L for x, y in zip(ra, rb)] for ra, rb in zip(a, b)]
+    ca = [xpc.commit(a[i], r[i]) for i in range(3)]
+    cb = [xpc.commit(b[i], s[i]) for i in range(3)]
+    cc = [xpc.commit(c[i], t[i]) for i in range(3)]
+    rnd = {"a_0": [st.scalar() for _ in range(3)], "b_0": [st.scalar() for _ in range(3)], "r_0": st.scalar(),
+           "s_0": st.scalar(), "t_0": st.scalar(), "omega": [st.scalar() for _ in range(3)],
+           "rho": [st.scalar() for _ in range(4)]}
+    tr = F.new_transcript(b"Hadamard", b"Shuffle")
+    proof, omega = F.hadamard_prove(tr, xpc, a, b, c, ca, cb, cc, r, s, t, rnd)
+    return omega, ca, cb, cc, proof

@@ -982,3 +982,109 @@ def test_small_batch_paths_equal_regular_paths(engine):
         exp, es = R.update_account(accs[128 * i:128 * i + 128].tobytes(), bl[32 * i:32 * i + 32].tobytes(),
                                    u[32 * i:32 * i + 32].tobytes(), c[32 * i:32 * i + 32].tobytes())
         assert status[i] == es and out[i].tobytes() == exp, i
+
+
+def _svp_blob(proof):
+    return (proof["commitment_d"] + proof["commitment_delta_small"] + proof["commitment_delta_capital"] +
+            b"".join(sb(v) for v in proof["a_twildle"]) + b"".join(sb(v) for v in proof["b_twildle"]) +
+            sb(proof["r_twildle"]) + sb(proof["s_twildle"]))
+
+
+def _hadamard_blob(proof):
+    return (proof["commitment_a_0"] + proof["commitment_b_0"] + proof["commitment_c_0"] + b"".join(proof["commitment_delta"]) +
+            b"".join(sb(v) for v in proof["a_bar"]) + b"".join(sb(v) for v in proof["b_bar"]) +
+            b"".join(sb(v) for v in proof["c_bar"]) + sb(proof["r_bar"]) + sb(proof["s_bar"]) + sb(proof["t_bar"]) +
+            sb(proof["rho_bar"]))
+
+
+def test_shuffle_leaf_arguments(engine):
+    """DDHProof::verify_ddh_proof, SVPProof::verify, HadamardProof::verify, batched (src/shuffle/{ddh,singlevalueproduct,
+    hadamard}.rs); the reference's own test scenarios with proofs from the oracle's prover restatements; per proof the
+    verdict (and for Hadamard the failing check) equals the oracle verifier's."""
+    import copy
+    import shuffle_ref as F
+    from qq_testlib import scenario_ddh, scenario_hadamard, scenario_svp
+    from quisquis_rust_b200 import api
+    api.set_default_engine(engine)
+    st = Stream(b"leaf-gpu")
+    bad_enc = invalid_encodings()[4][1]
+    # ---- DDH ----
+    cases = [list(scenario_ddh(st)) for _ in range(3)]
+    c = cases[0]
+    cases += [c[:5] + [c[5] + 1], c[:4] + [c[4] + 1, c[5]], [c[1], c[0]] + c[2:], c[:3] + [bad_enc] + c[4:]]
+    expect = [F.ddh_verify(F.new_transcript(b"ShuffleProof", b"DDHTuple"), (k[4], k[5]), (k[2], k[3]), k[0], k[1]) for k in cases]
+    assert expect == [True] * 3 + [False] * 3 + [None]
+    col = lambda i, f=lambda v: v: cat([f(k[i]) for k in cases])  # noqa: E731
+    got = engine.verify_ddh(col(0), col(1), col(2), col(3), col(4, sb), col(5, sb))
+    assert [int(s) for s in got] == [_status_of(e) for e in expect]
+    assert (engine.verify_ddh(col(0), col(1), col(2), col(3), col(4, sb), col(5, sb), verifier_label=b"Other") != 0).all()
+    assert api.DDHProof(sb(c[4]), sb(c[5])).verify_ddh_proof((c[2], c[3]), c[0], c[1]) is None
+    with pytest.raises(ValueError, match="DDH Proof Verify: Failed"):
+        api.DDHProof(sb(c[4]), sb(c[5] + 1)).verify_ddh_proof((c[2], c[3]), c[0], c[1])
+    # ---- single value product ----
+    xpc = F.XpcGens(4)
+    base = [scenario_svp(st), scenario_svp(st, pi=(2, 3, 5, 7, 11, 13, 17, 19, 23))]
+    cases = [[ca, b, pr] for ca, b, pr in base]
+    ca, b, pr = base[0]
+    cases.append([ca, b + 1, pr])
+    for key, idx in (("r_twildle", None), ("s_twildle", None), ("a_twildle", 0), ("a_twildle", 1), ("b_twildle", 2)):
+        bad = copy.deepcopy(pr)
+        if idx is None:
+            bad[key] += 1
+        else:
+            bad[key][idx] += 1
+        cases.append([ca, b, bad])
+    bad = copy.deepcopy(pr)
+    bad["commitment_delta_small"] = base[1][2]["commitment_delta_small"]
+    cases.append([ca, b, bad])
+    cases.append([bad_enc, b, pr])                              # statement commitment undecodable
+    V = lambda: F.new_transcript(b"SingleValue", b"Shuffle")  # noqa: E731
+    expect = [F.svp_verify(V(), k[2], k[0], k[1], xpc) for k in cases]
+    assert expect == [True, True] + [False] * 7 + [None]
+    got = engine.verify_svp(cat([k[0] for k in cases]), cat([sb(k[1]) for k in cases]), cat([_svp_blob(k[2]) for k in cases]))
+    assert [int(s) for s in got] == [_status_of(e) for e in expect]
+    S_ = lambda v: [sb(s) for s in v]  # noqa: E731
+    mk = lambda q: api.SVPProof(commitment_d=q["commitment_d"], commitment_delta_small=q["commitment_delta_small"],  # noqa: E731
+                                commitment_delta_capital=q["commitment_delta_capital"], a_twildle=S_(q["a_twildle"]),
+                                b_twildle=S_(q["b_twildle"]), r_twildle=sb(q["r_twildle"]), s_twildle=sb(q["s_twildle"]))
+    assert mk(pr).verify((ca, sb(b))) is None
+    with pytest.raises(ValueError, match="SingleValue Product Proof Verify: Failed"):
+        mk(cases[3][2]).verify((ca, sb(b)))
+    short = mk(pr)
+    short.a_twildle = short.a_twildle[:2]
+    with pytest.raises(ValueError, match="Size check failed"):
+        short.verify((ca, sb(b)))
+    # ---- Hadamard ----
+    base = [scenario_hadamard(st), scenario_hadamard(st, random_matrices=True)]
+    cases = [list(k) for k in base]
+    om, pa, pb, pc, pr = base[0]
+    cases.append([[om[0], om[0], om[2]], pa, pb, pc, pr])
+    for key, idx in (("b_bar", 1), ("r_bar", None), ("t_bar", None), ("rho_bar", None)):
+        bad = copy.deepcopy(pr)
+        if idx is None:
+            bad[key] += 1
+        else:
+            bad[key][idx] += 1
+        cases.append([om, pa, pb, pc, bad])
+    cases.append([om, pb, pa, pc, pr])
+    bad = copy.deepcopy(pr)
+    bad["commitment_delta"][2] = bad_enc                        # changes the challenge: the A/B/C check fails first
+    cases.append([om, pa, pb, pc, bad])
+    bad = copy.deepcopy(pr)
+    bad["commitment_a_0"] = bad_enc
+    cases.append([om, pa, pb, pc, bad])
+    V = lambda: F.new_transcript(b"Hadamard", b"Shuffle")  # noqa: E731
+    expect = [F.hadamard_verify(V(), k[4], k[0], k[1], k[2], k[3], xpc) for k in cases]
+    assert expect == [True, True, "omega", "abc", "abc", "abc", "delta", "abc", "abc", None]
+    got, det = engine.verify_hadamard(cat([cat(S_(k[0])) for k in cases]), cat([cat(k[1]) for k in cases]),
+                                      cat([cat(k[2]) for k in cases]), cat([cat(k[3]) for k in cases]),
+                                      cat([_hadamard_blob(k[4]) for k in cases]))
+    code = {True: (0, 0), None: (1, 0), "omega": (6, 1), "abc": (6, 2), "delta": (6, 3)}
+    assert [(int(s), int(d)) for s, d in zip(got, det)] == [code[e] for e in expect]
+    mk = lambda q: api.HadamardProof(commitment_a_0=q["commitment_a_0"], commitment_b_0=q["commitment_b_0"],  # noqa: E731
+                                     commitment_c_0=q["commitment_c_0"], commitment_delta=q["commitment_delta"],
+                                     a_bar=S_(q["a_bar"]), b_bar=S_(q["b_bar"]), c_bar=S_(q["c_bar"]), r_bar=sb(q["r_bar"]),
+                                     s_bar=sb(q["s_bar"]), t_bar=sb(q["t_bar"]), rho_bar=sb(q["rho_bar"]))
+    assert mk(pr).verify(S_(om), pa, pb, pc) is None
+    with pytest.raises(ValueError, match="Delta Commitment check failed"):
+        mk(cases[6][4]).verify(S_(om), pa, pb, pc)

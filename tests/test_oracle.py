@@ -210,3 +210,57 @@ def test_remaining_sigma_proofs_round_trip():
     bad = bytearray(eps[1])
     bad[64:96] = (1).to_bytes(32, "little")                                               # negative s: undecodable
     assert S.verify_account(snd, [eps[0], bytes(bad)], bpk, zv, zsk, zr, x) is None
+
+
+def test_shuffle_leaf_arguments_round_trip():
+    """oracle/shuffle_ref.py: DDH, single-value-product and Hadamard arguments on the reference's own test scenarios
+    (ddh.rs:162, singlevalueproduct.rs:269, hadamard.rs:395): proofs verify, tampered ones fail with the reference's
+    error class; polynomial helpers reproduce the reference's known answers (polynomial.rs:988-1046)."""
+    import copy
+    import shuffle_ref as F
+    from qq_testlib import scenario_ddh, scenario_hadamard, scenario_svp
+    L = R.L
+    assert F.l_polys([1, 2, 3])[0] == [(-6) % L, 11, (-6) % L, 1]                       # l_x_polynomial_test
+    assert F.poly_eval([2, 3], 3) == 11 and F.poly_eval([1, 2, 3, 4], 3) == 142          # evaluate_polynomial_test
+    lp = F.l_polys([5, 9, 11])
+    assert [F.poly_eval(lp[1], w) for w in (5, 9, 11)] == [1, 0, 0] and F.poly_eval(lp[0], 9) == 0
+    assert F.exp_iter(3, 4) == [1, 3, 9, 27] and F.exp_iter(3, 2, skip=1) == [3, 9]        # vectorutil.rs:132-143
+    st = Stream(b"leaf-cpu")
+    G, H, Gd, Hd, ch, z = scenario_ddh(st)
+    V = lambda: F.new_transcript(b"ShuffleProof", b"DDHTuple")  # noqa: E731
+    assert F.ddh_verify(V(), (ch, z), (Gd, Hd), G, H) is True
+    assert F.ddh_verify(V(), (ch, z + 1), (Gd, Hd), G, H) is False
+    assert F.ddh_verify(V(), (ch, z), (Hd, Gd), G, H) is False
+    assert F.ddh_verify(V(), (ch, z), (Gd, (1).to_bytes(32, "little")), G, H) is None
+    ca, b, proof = scenario_svp(st)
+    xpc = F.XpcGens(4)
+    V = lambda: F.new_transcript(b"SingleValue", b"Shuffle")  # noqa: E731
+    assert F.svp_verify(V(), proof, ca, b, xpc) is True
+    assert F.svp_verify(V(), proof, ca, b + 1, xpc) is False
+    for key in ("r_twildle", "s_twildle"):
+        bad = copy.deepcopy(proof)
+        bad[key] += 1
+        assert F.svp_verify(V(), bad, ca, b, xpc) is False
+    bad = copy.deepcopy(proof)
+    bad["a_twildle"][0] += 1
+    assert F.svp_verify(V(), bad, ca, b, xpc) is False
+    bad = copy.deepcopy(proof)
+    bad["a_twildle"] = bad["a_twildle"][:2]
+    assert F.svp_verify(V(), bad, ca, b, xpc) == "size"
+    omega, pa, pb, pc, proof = scenario_hadamard(st)
+    V = lambda: F.new_transcript(b"Hadamard", b"Shuffle")  # noqa: E731
+    assert F.hadamard_verify(V(), proof, omega, pa, pb, pc, xpc) is True
+    assert F.hadamard_verify(V(), proof, [omega[0], omega[0], omega[2]], pa, pb, pc, xpc) == "omega"
+    bad = copy.deepcopy(proof)
+    bad["b_bar"][1] += 1
+    assert F.hadamard_verify(V(), bad, omega, pa, pb, pc, xpc) == "abc"
+    bad = copy.deepcopy(proof)
+    bad["rho_bar"] += 1
+    assert F.hadamard_verify(V(), bad, omega, pa, pb, pc, xpc) == "delta"
+    assert F.hadamard_verify(V(), proof, omega, pb, pa, pc, xpc) == "abc"
+    bad = copy.deepcopy(proof)
+    bad["commitment_delta"][2] = (1).to_bytes(32, "little")         # changes the challenge: the first check fails first
+    assert F.hadamard_verify(V(), bad, omega, pa, pb, pc, xpc) == "abc"
+    bad = copy.deepcopy(proof)
+    bad["commitment_a_0"] = (1).to_bytes(32, "little")
+    assert F.hadamard_verify(V(), bad, omega, pa, pb, pc, xpc) is None
