@@ -283,6 +283,16 @@ int qq_verify_svp_batch(qq_ctx* ctx, const char* transcript_label, const char* v
 int qq_verify_hadamard_batch(qq_ctx* ctx, const char* transcript_label, const char* verifier_label, const uint8_t* omega,
                              const uint8_t* commit_a, const uint8_t* commit_b, const uint8_t* commit_c, const uint8_t* proof,
                              size_t nproofs, uint8_t* status, uint8_t* detail);
+/* ProductProof::verify (src/shuffle/product.rs:170-195: MultiHadamardProof::verify :325-389, ZeroProof::verify :508-600,
+ * SVPProof::verify) on one running transcript.  c_prod_A: nproofs x 96 B (the three column commitments); statement: nproofs x
+ * 192 B = c_b | zero_statement.c_A[3] | svp commitment_a | svp b; proof: nproofs x 1024 B = c_B[3] | c_A_0 | c_B_m | c_D[7] |
+ * a_vec[3] | b_vec[3] | r | s | t | SVPProof (352 B).  status[p]: QQ_ST_OK, QQ_ST_BAD_SCALAR, QQ_ST_BAD_POINT (detail 10 =
+ * "Multihadamard Proof Verify: Failed", 11 = "ZeroProof Verify: Decompression Failed" / "ZeroProof Verify: Failed", 12 =
+ * the SVP's), QQ_ST_PROOF with detail 1 = "Multihadamard Product Proof Verify: c_B_1 == c_A_1 Failed", 2 = "... c_B_m == c_b
+ * Failed", 3..6 = "Zero Argument Proof Verify: c_d_(m+1) == com(0,0) / com(a_bar, r) / com(b_bar, s) / com(a_bar * b_bar, t)
+ * ... Failed", 7 = "SingleValue Product Proof Verify: Failed".  detail may be NULL. */
+int qq_verify_product_batch(qq_ctx* ctx, const char* transcript_label, const char* verifier_label, const uint8_t* c_prod_A,
+                            const uint8_t* statement, const uint8_t* proof, size_t nproofs, uint8_t* status, uint8_t* detail);
 
 /* ---- decommit ------------------------------------------------------------------------------------------------------
  * ElGamalCommitment::decommit(sk) = enc(d - sk*c) = enc(v*B)                    src/elgamal/elgamal.rs:106-108 */

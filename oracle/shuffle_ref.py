@@ -300,3 +300,180 @@ def hadamard_verify(tr, proof, omega, commit_a, commit_b, commit_c, xpc):
     lhs = R.mul(ev[0], acc)
     diff = [(a * b - c) % L for a, b, c in zip(proof["a_bar"], proof["b_bar"], proof["c_bar"])]
     return True if R.eq(lhs, xpc.commit_point(diff, proof["rho_bar"])) else "delta"
+
+
+# ---- product argument = multi-Hadamard + zero argument + SVP (reference src/shuffle/product.rs) --------------------------
+def columns(m):
+    return [list(c) for c in zip(*m)]
+
+
+def pc_commit_point(value, blinding):
+    """bulletproofs::PedersenGens::default().commit(value, blinding) = value * B + blinding * B_blinding."""
+    return R.add(R.mul(value % L, R.BASEPOINT), R.mul(blinding % L, R.decompress(R.PEDERSEN_H_COMPRESSED)))
+
+
+def single_bilinearmap(ai, bj, yi):
+    """product.rs single_bilinearmap: sum_t a_t b_t y_t."""
+    assert len(ai) == len(bj) == len(yi)
+    return sum(a * b * y for a, b, y in zip(ai, bj, yi)) % L
+
+
+def bilinearmap(a_cols, b_cols, y):
+    """product.rs bilinearmap over the m + 1 = 4 columns of a and b: d_k = sum_{j = m - k + i} a_i * b_j (k = 0..2m)."""
+    y_i = exp_iter(y, ROWS, skip=1)
+    m = ROWS
+    out = []
+    for k in range(2 * ROWS + 1):
+        s = 0
+        for i in range(m + 1):
+            j = m - k + i
+            if 0 <= j <= m:
+                s = (s + single_bilinearmap(a_cols[i], b_cols[j], y_i)) % L
+        out.append(s)
+    return out
+
+
+def zero_prove(tr, xpc, a_cols3, b_cols3, r_vec, s_vec, y, rnd):
+    """ZeroProof::create_zero_argument_proof.  a_cols3 / b_cols3: the three columns of a_2d / b_2d; r_vec: the blindings of
+    the statement commitments (entries 1, 2 are used); s_vec: three blindings, a fourth (s_m) is appended as in the reference.
+    rnd: a_0, b_m (COLUMNS each), r_0, s_m, t (2 ROWS + 1; entry ROWS + 1 is forced to 0)."""
+    tr.domain_sep(b"ZeroArgumentProof")
+    a_0, b_m, r_0, s_m = rnd["a_0"], rnd["b_m"], rnd["r_0"], rnd["s_m"]
+    c_a_0, c_b_m = xpc.commit(a_0, r_0), xpc.commit(b_m, s_m)
+    a_columns = [list(a_0)] + [list(c) for c in a_cols3]
+    b_columns = [list(c) for c in b_cols3] + [list(b_m)]
+    dv = bilinearmap(a_columns, b_columns, y)
+    t = list(rnd["t"])
+    t[ROWS + 1] = 0
+    c_D = [R.compress(pc_commit_point(d, tt)) for d, tt in zip(dv, t)]
+    tr.append_point_var(b"A0Commitment", c_a_0)
+    tr.append_point_var(b"BmCommitment", c_b_m)
+    for cd in c_D:
+        tr.append_point_var(b"DCommitment", cd)
+    x = tr.get_challenge(b"challenge")
+    x_exp = exp_iter(x, 2 * ROWS + 1)
+    x_exp_m = x_exp[0:ROWS + 1]
+    x_m_j = x_exp_m[::-1]
+    a_bar = [sum(a_columns[i][c] * x_exp_m[i] for i in range(ROWS + 1)) % L for c in range(ROWS)]
+    b_bar = [sum(b_columns[i][c] * x_m_j[i] for i in range(ROWS + 1)) % L for c in range(ROWS)]
+    r_ext = [r_0] + [r_vec[i] for i in range(1, ROWS)] + [0]
+    s_full = list(s_vec) + [s_m]
+    return {"c_A_0": c_a_0, "c_B_m": c_b_m, "c_D": c_D, "a_vec": a_bar, "b_vec": b_bar,
+            "r": sum(p * q for p, q in zip(r_ext, x_exp_m)) % L, "s": sum(p * q for p, q in zip(s_full, x_m_j)) % L,
+            "t": sum(p * q for p, q in zip(t, x_exp)) % L}
+
+
+ZERO_ERRORS = {"size": "Zero Argument Proof Verify: Size check failed",
+               "d": "Zero Argument Proof Verify: c_d_(m+1) == com(0,0) Failed",
+               "a": "Zero Argument Proof Verify: com(a_bar, r) verification check Failed",
+               "b": "Zero Argument Proof Verify: com(b_bar, s) verification check Failed",
+               "ab": "Zero Argument Proof Verify: com(a_bar * b_bar, t) verification check Failed"}
+
+
+def zero_verify(tr, proof, c_A, xpc, c_B_points, chal_y):
+    """ZeroProof::verify.  c_A: 3 compressed points; c_B_points: 3 points (already decompressed by the caller, as in the
+    reference).  -> True, None (an Err that comes from a failed decompression), or a key of ZERO_ERRORS."""
+    if len(proof["c_D"]) != 2 * ROWS + 1 or len(proof["a_vec"]) != COLUMNS or len(proof["b_vec"]) != COLUMNS:
+        return "size"
+    d_m_1 = R.decompress(proof["c_D"][ROWS + 1])
+    if d_m_1 is None:
+        return None
+    if not R.is_identity(d_m_1):
+        return "d"
+    tr.domain_sep(b"ZeroArgumentProof")
+    tr.append_point_var(b"A0Commitment", proof["c_A_0"])
+    tr.append_point_var(b"BmCommitment", proof["c_B_m"])
+    for cd in proof["c_D"]:
+        tr.append_point_var(b"DCommitment", cd)
+    x = tr.get_challenge(b"challenge")
+    x_exp = exp_iter(x, 2 * ROWS + 1)
+    temp_a = _msm_point(x_exp[1:ROWS + 1], c_A)
+    if temp_a is None:
+        return None
+    a0 = R.decompress(proof["c_A_0"])
+    if a0 is None:
+        return None
+    if not R.eq(xpc.commit_point(proof["a_vec"], proof["r"]), R.add(a0, temp_a)):
+        return "a"
+    full = R.mul(0, R.BASEPOINT)
+    for s, p in zip(x_exp[1:ROWS + 1][::-1], c_B_points):
+        full = R.add(full, R.mul(s, p))
+    bm = R.decompress(proof["c_B_m"])
+    if bm is None:
+        return None
+    if not R.eq(xpc.commit_point(proof["b_vec"], proof["s"]), R.add(full, bm)):
+        return "b"
+    y_i = exp_iter(chal_y, ROWS, skip=1)
+    abb = single_bilinearmap(proof["a_vec"], proof["b_vec"], y_i)
+    dxk = _msm_point(x_exp, proof["c_D"])
+    if dxk is None:
+        return None
+    return True if R.eq(pc_commit_point(abb, proof["t"]), dxk) else "ab"
+
+
+def multihadamard_prove(tr, xpc, pi, bvec, comit_a, cb, r, s_3, rnd):
+    """MultiHadamardProof::create_multi_hadamard_product_arg.  pi: 3 x 3 rows; comit_a[i] = xpc.commit(column i, r[i]);
+    cb = xpc.commit(bvec, s_3).  rnd: s_mid (one scalar) and "zero" (the zero argument's randomness).
+    -> (proof {c_B, zero_proof}, statement {c_b, zero_c_A})."""
+    tr.domain_sep(b"MultiHadamardProductProof")
+    cols = columns(pi)
+    b2 = [p * q % L for p, q in zip(cols[0], cols[1])]
+    s_vec_product = [r[0], rnd["s_mid"], s_3]
+    c_B = [comit_a[0], xpc.commit(b2, s_vec_product[1]), cb]
+    for c in c_B:
+        tr.append_point_var(b"BVectorCommitment", c)
+    x = tr.get_challenge(b"XChallenge")
+    y = tr.get_challenge(b"YChallenge")
+    xe = exp_iter(x, ROWS, skip=1)
+    neg_one = [L - 1] * 3
+    d_1 = [v * xe[0] % L for v in cols[0]]
+    d_2 = [v * xe[1] % L for v in b2]
+    d = [(p * xe[0] + q * xe[1]) % L for p, q in zip(b2, bvec)]
+    s = [s_vec_product[0] * xe[0] % L, s_vec_product[1] * xe[1] % L, (xe[0] * s_vec_product[1] + xe[1] * s_vec_product[2]) % L]
+    zero = zero_prove(tr, xpc, [cols[1], cols[2], neg_one], [d_1, d_2, d], r, s, y, rnd["zero"])
+    c_minus_one = xpc.commit(neg_one, 0)
+    return {"c_B": c_B, "zero_proof": zero}, {"c_b": cb, "zero_c_A": [comit_a[1], comit_a[2], c_minus_one]}
+
+
+def multihadamard_verify(tr, proof, statement, c_A, xpc):
+    """MultiHadamardProof::verify.  c_A: 3 compressed points (the reference holds them decompressed and compares their
+    encodings).  -> True, None, "c_B_1", "c_B_m" or a zero_verify result."""
+    cB, zA = proof["c_B"], statement["zero_c_A"]
+    if not (c_A[0] == cB[0] and c_A[1] == zA[0] and c_A[2] == zA[1]):
+        return "c_B_1"
+    if statement["c_b"] != cB[ROWS - 1]:
+        return "c_B_m"
+    tr.domain_sep(b"MultiHadamardProductProof")
+    for c in cB:
+        tr.append_point_var(b"BVectorCommitment", c)
+    x = tr.get_challenge(b"XChallenge")
+    y = tr.get_challenge(b"YChallenge")
+    xe = exp_iter(x, ROWS, skip=1)
+    pts = [R.decompress(c) for c in cB]
+    if any(p is None for p in pts):
+        return None
+    d_vec = [R.mul(xe[0], pts[0]), R.mul(xe[1], pts[1]), R.add(R.mul(xe[0], pts[1]), R.mul(xe[1], pts[2]))]
+    c_zero_A = [zA[0], zA[1], xpc.commit([L - 1] * 3, 0)]
+    return zero_verify(tr, proof["zero_proof"], c_zero_A, xpc, d_vec, y)
+
+
+def product_prove(tr, xpc, pi, witness_r, rnd):
+    """ProductProof::create_product_argument_proof.  rnd: s, "mh" (multihadamard_prove's rnd), "svp" = (d_vec, rd,
+    delta_mid, s_1, s_x).  -> (proof, statement)."""
+    cols = columns(pi)
+    c_prod_A = [xpc.commit(cols[i], witness_r[i]) for i in range(ROWS)]
+    bvec = [row[0] * row[1] * row[2] % L for row in pi]
+    s = rnd["s"]
+    cb = xpc.commit(bvec, s)
+    b = bvec[0] * bvec[1] * bvec[2] % L
+    mh_proof, mh_state = multihadamard_prove(tr, xpc, pi, bvec, c_prod_A, cb, witness_r, s, rnd["mh"])
+    svp = svp_prove(tr, xpc, s, bvec, *rnd["svp"])
+    return {"mh": mh_proof, "svp": svp}, {"mh": mh_state, "svp": (cb, b)}
+
+
+def product_verify(tr, proof, statement, c_prod_A, xpc):
+    res = multihadamard_verify(tr, proof["mh"], statement["mh"], c_prod_A, xpc)
+    if res is not True:
+        return res
+    res = svp_verify(tr, proof["svp"], statement["svp"][0], statement["svp"][1], xpc)
+    return "svp" if res is False else res

@@ -22,7 +22,7 @@ EXPORTS = [
     "qq_fixed_base_i64_batch", "qq_fixed_base_i64_batch_dev", "qq_msm", "qq_msm_dev", "qq_msm_partial", "qq_msm_partial_dev",
     "qq_points_sum", "qq_msm_segmented", "qq_msm_points_prepare", "qq_msm_points_prepare_dev", "qq_msm_points_free",
     "qq_msm_points_count", "qq_msm_prepared", "qq_msm_prepared_dev",
-    "qq_verify_ddh_batch", "qq_verify_svp_batch", "qq_verify_hadamard_batch",
+    "qq_verify_ddh_batch", "qq_verify_svp_batch", "qq_verify_hadamard_batch", "qq_verify_product_batch",
     "qq_verify_account_sigma_batch", "qq_verify_zero_balance_batch", "qq_verify_destroy_account_batch",
     "qq_verify_same_value_compact_batch", "qq_verify_update_account_dark_tx_batch",
     "qq_verify_update_account_dlog_batch", "qq_verify_delta_compact_batch", "qq_decommit_batch", "qq_decommit_value_batch", "qq_from_uniform_bytes_batch", "qq_vector_pedersen_gens", "qq_bulletproof_gens",
@@ -103,6 +103,7 @@ def load_library():
     lib.qq_verify_ddh_batch.argtypes = [vp, cs, cs, u8p, u8p, u8p, u8p, u8p, u8p, sz, u8p]
     lib.qq_verify_svp_batch.argtypes = [vp, cs, cs, u8p, u8p, u8p, sz, u8p]
     lib.qq_verify_hadamard_batch.argtypes = [vp, cs, cs, u8p, u8p, u8p, u8p, u8p, sz, u8p, u8p]
+    lib.qq_verify_product_batch.argtypes = [vp, cs, cs, u8p, u8p, u8p, sz, u8p, u8p]
     lib.qq_decommit_batch.argtypes = [vp, u8p, u8p, u8p, u8p, sz]
     lib.qq_decommit_value_batch.argtypes = [vp, u8p, u8p, ctypes.c_int, u8p, u8p, sz]
     lib.qq_from_uniform_bytes_batch.argtypes = [vp, u8p, u8p, sz]
@@ -461,6 +462,16 @@ class Engine:
         self._ck(self.lib.qq_verify_hadamard_batch(self.h, transcript_label, verifier_label, _ptr(om), _ptr(ca), _ptr(cb),
                                                     _ptr(cc), _ptr(pr), nproofs, _ptr(st), _ptr(det)),
                  "qq_verify_hadamard_batch")
+        return st, det
+
+    def verify_product(self, c_prod_A, statement, proof, transcript_label=b"ShuffleProof", verifier_label=b"Shuffle"):
+        """ProductProof::verify; statement 192 B, proof 1024 B per proof (include/qq_b200.h) -> (status, detail)."""
+        ca, stm, pr = _u8(c_prod_A), _u8(statement), _u8(proof)
+        nproofs = ca.size // 96
+        _u8(stm, nproofs * 192), _u8(pr, nproofs * 1024)
+        st, det = np.zeros(nproofs, np.uint8), np.zeros(nproofs, np.uint8)
+        self._ck(self.lib.qq_verify_product_batch(self.h, transcript_label, verifier_label, _ptr(ca), _ptr(stm), _ptr(pr),
+                                                   nproofs, _ptr(st), _ptr(det)), "qq_verify_product_batch")
         return st, det
 
     def decommit(self, comm, sk):

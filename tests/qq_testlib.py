@@ -206,3 +206,21 @@ def scenario_hadamard(st, random_matrices=False):
     tr = F.new_transcript(b"Hadamard", b"Shuffle")
     proof, omega = F.hadamard_prove(tr, xpc, a, b, c, ca, cb, cc, r, s, t, rnd)
     return omega, ca, cb, cc, proof
+
+
+def scenario_product(st, pi=(7, 6, 1, 5, 3, 4, 2, 8, 9)):
+    """product.rs product_proof_test (:595-640) -> (c_prod_A[3], proof, statement); transcript b"ShuffleProof" / b"Shuffle"."""
+    import shuffle_ref as F
+    xpc = F.XpcGens(4)
+    rows = [list(pi[0:3]), list(pi[3:6]), list(pi[6:9])]
+    r = [st.scalar() for _ in range(3)]
+    cols = F.columns(rows)
+    c_prod_A = [xpc.commit(cols[i], r[i]) for i in range(3)]
+    rnd = {"s": st.scalar(),
+           "mh": {"s_mid": st.scalar(),
+                  "zero": {"a_0": [st.scalar() for _ in range(3)], "b_m": [st.scalar() for _ in range(3)], "r_0": st.scalar(),
+                           "s_m": st.scalar(), "t": [st.scalar() for _ in range(7)]}},
+           "svp": ([st.scalar() for _ in range(3)], st.scalar(), [st.scalar()], st.scalar(), st.scalar())}
+    tr = F.new_transcript(b"ShuffleProof", b"Shuffle")
+    proof, statement = F.product_prove(tr, xpc, rows, r, rnd)
+    return c_prod_A, proof, statement

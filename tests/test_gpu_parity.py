@@ -1088,3 +1088,72 @@ def test_shuffle_leaf_arguments(engine):
     assert mk(pr).verify(S_(om), pa, pb, pc) is None
     with pytest.raises(ValueError, match="Delta Commitment check failed"):
         mk(cases[6][4]).verify(S_(om), pa, pb, pc)
+
+
+def _product_blobs(proof, statement):
+    z = proof["mh"]["zero_proof"]
+    pr = (b"".join(proof["mh"]["c_B"]) + z["c_A_0"] + z["c_B_m"] + b"".join(z["c_D"]) + b"".join(sb(v) for v in z["a_vec"]) +
+          b"".join(sb(v) for v in z["b_vec"]) + sb(z["r"]) + sb(z["s"]) + sb(z["t"]) + _svp_blob(proof["svp"]))
+    stm = statement["mh"]["c_b"] + b"".join(statement["mh"]["zero_c_A"]) + statement["svp"][0] + sb(statement["svp"][1])
+    assert len(pr) == 1024 and len(stm) == 192
+    return pr, stm
+
+
+PRODUCT_CODES = {True: (0, 0), "c_B_1": (6, 1), "c_B_m": (6, 2), "d": (6, 3), "a": (6, 4), "b": (6, 5), "ab": (6, 6), "svp": (6, 7)}
+
+
+def test_product_argument(engine):
+    """ProductProof::verify (multi-Hadamard -> zero argument -> SVP on one transcript, src/shuffle/product.rs), batched; the
+    reference's product_proof_test scenario and a second permutation; verdict and failing check equal the oracle's."""
+    import copy
+    import shuffle_ref as F
+    from qq_testlib import scenario_product
+    st = Stream(b"product-gpu")
+    xpc = F.XpcGens(4)
+    base = [scenario_product(st), scenario_product(st, pi=(9, 1, 4, 3, 8, 2, 6, 5, 7))]
+    cases = [list(k) for k in base]
+    cA, proof, state = base[0]
+    cases.append([[cA[1], cA[0], cA[2]], proof, state])
+    for path in (("mh", "zero_proof", "r"), ("mh", "zero_proof", "s"), ("mh", "zero_proof", "t"), ("svp", "r_twildle"),
+                 ("svp", "s_twildle")):
+        bad = copy.deepcopy(proof)
+        node = bad
+        for k in path[:-1]:
+            node = node[k]
+        node[path[-1]] += 1
+        cases.append([cA, bad, state])
+    for idx in (0, 2):
+        bad = copy.deepcopy(proof)
+        bad["mh"]["zero_proof"]["a_vec"][idx] += 1
+        cases.append([cA, bad, state])
+    bad = copy.deepcopy(proof)
+    bad["svp"]["a_twildle"][0] += 1                                      # a~_1 != b~_1: the SVP's first scalar check
+    cases.append([cA, bad, state])
+    bad = copy.deepcopy(proof)
+    bad["mh"]["zero_proof"]["c_D"][4] = R.BASEPOINT_COMPRESSED
+    cases.append([cA, bad, state])
+    bad_state = copy.deepcopy(state)
+    bad_state["mh"]["c_b"] = cA[0]
+    cases.append([cA, proof, bad_state])
+    bad_state = copy.deepcopy(state)
+    bad_state["svp"] = (state["svp"][0], state["svp"][1] + 1)
+    cases.append([cA, proof, bad_state])
+    bad = copy.deepcopy(proof)
+    bad["mh"]["zero_proof"]["c_D"][6] = invalid_encodings()[4][1]          # decoded last, but it moves the challenge
+    cases.append([cA, bad, state])
+    bad = copy.deepcopy(proof)
+    bad["mh"]["zero_proof"]["c_D"][4] = invalid_encodings()[4][1]
+    cases.append([cA, bad, state])
+    V = lambda: F.new_transcript(b"ShuffleProof", b"Shuffle")  # noqa: E731
+    expect = [F.product_verify(V(), k[1], k[2], k[0], xpc) for k in cases]
+    assert expect == [True, True, "c_B_1", "a", "b", "ab", "svp", "svp", "a", "a", "svp", "d", "c_B_m", "svp", "a", None]
+    blobs = [_product_blobs(k[1], k[2]) for k in cases]
+    got, det = engine.verify_product(cat([cat(k[0]) for k in cases]), cat([b[1] for b in blobs]), cat([b[0] for b in blobs]))
+    for i, e in enumerate(expect):
+        if e is None:
+            assert int(got[i]) == 1 and int(det[i]) == 11, i
+        else:
+            assert (int(got[i]), int(det[i])) == PRODUCT_CODES[e], (i, e, int(got[i]), int(det[i]))
+    got2, _ = engine.verify_product(cat([cat(k[0]) for k in cases]), cat([b[1] for b in blobs]), cat([b[0] for b in blobs]),
+                                    transcript_label=b"Other")
+    assert (got2[:2] != 0).all()

@@ -264,3 +264,36 @@ def test_shuffle_leaf_arguments_round_trip():
     bad = copy.deepcopy(proof)
     bad["commitment_a_0"] = (1).to_bytes(32, "little")
     assert F.hadamard_verify(V(), bad, omega, pa, pb, pc, xpc) is None
+
+
+def test_product_argument_round_trip_and_bilinear_map_vectors():
+    """oracle/shuffle_ref.py product argument (multi-Hadamard + zero argument + SVP, src/shuffle/product.rs): pinned by the
+    reference's known answers for bilinearmap / single_bilinearmap (product.rs single_bilinear_map_test, bilinear_map_test),
+    then the reference's product_proof_test scenario: the proof verifies, tampering fails in the check it belongs to."""
+    import copy
+    import shuffle_ref as F
+    from qq_testlib import scenario_product
+    a, b = [[7, 6, 1], [5, 3, 4], [2, 8, 9]], [[3, 2, 1], [7, 3, 5], [8, 3, 6]]
+    golden = [87 + 8 * 256, 30 + 20 * 256, 106 + 29 * 256, 166 + 64 * 256, 208 + 52 * 256, 12 + 48 * 256, 243 + 37 * 256]
+    assert F.bilinearmap([[6, 2, 5]] + F.columns(a), F.columns(b) + [[7, 1, 3]], 5) == golden
+    assert F.single_bilinearmap([7, 6, 1], [5, 3, 4], F.exp_iter(5, 3, skip=1)) == 1125
+    st = Stream(b"product-cpu")
+    cA, proof, state = scenario_product(st)
+    xpc = F.XpcGens(4)
+    V = lambda: F.new_transcript(b"ShuffleProof", b"Shuffle")  # noqa: E731
+    assert F.product_verify(V(), proof, state, cA, xpc) is True
+    assert F.product_verify(V(), proof, state, [cA[1], cA[0], cA[2]], xpc) == "c_B_1"
+    for path, expect in ((("mh", "zero_proof", "r"), "a"), (("mh", "zero_proof", "s"), "b"), (("mh", "zero_proof", "t"), "ab"),
+                         (("svp", "r_twildle"), "svp")):
+        bad = copy.deepcopy(proof)
+        node = bad
+        for k in path[:-1]:
+            node = node[k]
+        node[path[-1]] += 1
+        assert F.product_verify(V(), bad, state, cA, xpc) == expect, path
+    bad = copy.deepcopy(proof)
+    bad["mh"]["zero_proof"]["c_D"][4] = R.BASEPOINT_COMPRESSED
+    assert F.product_verify(V(), bad, state, cA, xpc) == "d"
+    bad_state = copy.deepcopy(state)
+    bad_state["mh"]["c_b"] = cA[0]
+    assert F.product_verify(V(), proof, bad_state, cA, xpc) == "c_B_m"
