@@ -477,3 +477,289 @@ def product_verify(tr, proof, statement, c_prod_A, xpc):
         return res
     res = svp_verify(tr, proof["svp"], statement["svp"][0], statement["svp"][1], xpc)
     return "svp" if res is False else res
+
+
+# ---- multi-exponentiation arguments (reference src/shuffle/multiexponential.rs) ------------------------------------------
+def _ek_common(C_rows, A_rows):
+    """create_ek_common: C_rows 3 x 3 compressed points, A_rows 4 x 3 scalars -> the 2m = 6 diagonal sums E_0..E_5."""
+    def ms(a_idx, c_idx):
+        sc, pt = [], []
+        for i in a_idx:
+            sc += A_rows[i]
+        for i in c_idx:
+            pt += C_rows[i]
+        return _msm_point(sc, pt)
+    return [ms([0], [2]), ms([0, 1], [1, 2]), ms([0, 1, 2], [0, 1, 2]), ms([1, 2, 3], [0, 1, 2]), ms([2, 3], [0, 1]), ms([3], [0])]
+
+
+def _multiexpo_common(xpc, rnd):
+    a_0, r_0 = rnd["a_0"], rnd["r_0"]
+    b_vec, s_vec = list(rnd["b_vec"]), list(rnd["s_vec"])
+    b_vec[ROWS] = 0
+    s_vec[ROWS] = 0
+    c_A_0 = xpc.commit(a_0, r_0)
+    cb_k = [R.compress(pc_commit_point(b, s)) for b, s in zip(b_vec, s_vec)]
+    return a_0, b_vec, s_vec, c_A_0, cb_k, r_0
+
+
+def _multiexpo_response(a_witness, x_exp, a_0, s_dash, b_vec, s_vec, r_0):
+    cols = columns(a_witness)
+    a_vec = [(sum(cols[i][j] * x_exp[1 + j] for j in range(ROWS)) + a_0[i]) % L for i in range(ROWS)]
+    r = (r_0 + sum(s_dash[j] * x_exp[1 + j] for j in range(ROWS))) % L
+    return a_vec, r, sum(b * x for b, x in zip(b_vec, x_exp)) % L, sum(s * x for s, x in zip(s_vec, x_exp)) % L
+
+
+def _rows3(flat):
+    return [list(flat[0:3]), list(flat[3:6]), list(flat[6:9])]
+
+
+def multiexpo_pubkey_prove(tr, xpc, pks, a_witness, s_dash, base_pk, rnd):
+    """create_multiexponential_pubkey_proof.  pks: 9 x 64 B (updated keys), a_witness: 3 x 3 rows.
+    rnd: a_0 (3), r_0, b_vec (6), s_vec (6)."""
+    tr.domain_sep(b"MultiExponentialPubKeyProof")
+    a_0, b_vec, s_vec, c_A_0, cb_k, r_0 = _multiexpo_common(xpc, rnd)
+    A = [list(a_0)] + [list(r) for r in a_witness]
+    e_g = _ek_common(_rows3([p[0:32] for p in pks]), A)
+    e_h = _ek_common(_rows3([p[32:64] for p in pks]), A)
+    Gb, Hb = R.decompress(base_pk[0:32]), R.decompress(base_pk[32:64])
+    ek_g = [R.compress(R.add(R.mul(b % L, Gb), e)) for b, e in zip(b_vec, e_g)]
+    ek_h = [R.compress(R.add(R.mul(b % L, Hb), e)) for b, e in zip(b_vec, e_h)]
+    tr.append_point_var(b"A0Commitment", c_A_0)
+    for cbk, g, h in zip(cb_k, ek_g, ek_h):
+        tr.append_point_var(b"BKCommitment", cbk)
+        tr.append_point_var(b"EK0Commitment", g)
+        tr.append_point_var(b"EK1Commitment", h)
+    x = tr.get_challenge(b"xchallenege")
+    x_exp = exp_iter(x, 2 * ROWS)
+    a_vec, r, bx, sx = _multiexpo_response(a_witness, x_exp, a_0, s_dash, b_vec, s_vec, r_0)
+    return {"c_A_0": c_A_0, "c_B_k": cb_k, "E_k_0": ek_g, "E_k_1": ek_h, "a_vec": a_vec, "r": r, "b": bx, "s": sx, "t": 0}
+
+
+def multiexpo_commit_prove(tr, xpc, comms, a_witness, s_dash, base_pk, rho, rnd):
+    """create_multiexponential_elgamal_commit_proof.  comms: 9 x 64 B (updated commitments); rnd additionally tau_vec (6)."""
+    tr.domain_sep(b"MultiExponentialElgamalCommmitmentProof")
+    a_0, b_vec, s_vec, c_A_0, cb_k, r_0 = _multiexpo_common(xpc, rnd)
+    tau = list(rnd["tau_vec"])
+    tau[ROWS] = rho % L
+    A = [list(a_0)] + [list(r) for r in a_witness]
+    e_c = _ek_common(_rows3([c[0:32] for c in comms]), A)
+    e_d = _ek_common(_rows3([c[32:64] for c in comms]), A)
+    Gb, Hb = R.decompress(base_pk[0:32]), R.decompress(base_pk[32:64])
+    E_c = [R.compress(R.add(R.mul(t % L, Gb), e)) for t, e in zip(tau, e_c)]
+    E_d = [R.compress(R.add(R.add(R.mul(b % L, R.BASEPOINT), R.mul(t % L, Hb)), e)) for b, t, e in zip(b_vec, tau, e_d)]
+    tr.append_point_var(b"A0Commitment", c_A_0)
+    for cbk, c, d in zip(cb_k, E_c, E_d):
+        tr.append_point_var(b"BKCommitment", cbk)
+        tr.append_point_var(b"EK0Commitment", c)
+        tr.append_point_var(b"EK1Commitment", d)
+    x = tr.get_challenge(b"xchallenege")
+    x_exp = exp_iter(x, 2 * ROWS)
+    a_vec, r, bx, sx = _multiexpo_response(a_witness, x_exp, a_0, s_dash, b_vec, s_vec, r_0)
+    return {"c_A_0": c_A_0, "c_B_k": cb_k, "E_k_0": E_c, "E_k_1": E_d, "a_vec": a_vec, "r": r, "b": bx, "s": sx,
+            "t": sum(t * x for t, x in zip(tau, x_exp)) % L}
+
+
+def _multiexpo_scalars(proof, c_A, x_exp, xpc):
+    """verify_multiexpo_scalars -> True, None, "a", "b"."""
+    lhs = _msm_point(x_exp[1:ROWS + 1], c_A)
+    if lhs is None:
+        return None
+    a0 = R.decompress(proof["c_A_0"])
+    if a0 is None:
+        return None
+    if not R.eq(R.add(lhs, a0), xpc.commit_point(proof["a_vec"], proof["r"])):
+        return "a"
+    bk = _msm_point(x_exp, proof["c_B_k"])
+    if bk is None:
+        return None
+    return True if R.eq(pc_commit_point(proof["b"], proof["s"]), bk) else "b"
+
+
+def _multiexpo_ek(proof, x_exp, c, d):
+    """verify_multiexpo_ek: c, d = 9 decompressed points each -> (E_k_0 sum or None, E_k_1 sum or None, c_c_x, c_d_x)."""
+    sc = ([a * x_exp[2] % L for a in proof["a_vec"]] + [a * x_exp[1] % L for a in proof["a_vec"]] + list(proof["a_vec"]))
+
+    def ms(points):
+        acc = R.mul(0, R.BASEPOINT)
+        for s, p in zip(sc, points):
+            acc = R.add(acc, R.mul(s % L, p))
+        return acc
+    return _msm_point(x_exp, proof["E_k_0"]), _msm_point(x_exp, proof["E_k_1"]), ms(c), ms(d)
+
+
+def _multiexpo_transcript(tr, proof, domain):
+    tr.domain_sep(domain)
+    tr.append_point_var(b"A0Commitment", proof["c_A_0"])
+    for cbk, e0, e1 in zip(proof["c_B_k"], proof["E_k_0"], proof["E_k_1"]):
+        tr.append_point_var(b"BKCommitment", cbk)
+        tr.append_point_var(b"EK0Commitment", e0)
+        tr.append_point_var(b"EK1Commitment", e1)
+    return exp_iter(tr.get_challenge(b"xchallenege"), 2 * ROWS)
+
+
+def multiexpo_pubkey_verify(tr, proof, c_A, updated_accounts, base_pk, pk_GH, xpc):
+    """verify_multiexponential_pubkey_proof -> True, None, "c_B_m", "Em", "a", "b", "E_K"."""
+    if len(proof["a_vec"]) != COLUMNS or proof["c_B_k"][ROWS] != bytes(32):
+        return "c_B_m"
+    if pk_GH != proof["E_k_0"][ROWS] + proof["E_k_1"][ROWS]:
+        return "Em"
+    x_exp = _multiexpo_transcript(tr, proof, b"MultiExponentialPubKeyProof")
+    res = _multiexpo_scalars(proof, c_A, x_exp, xpc)
+    if res is not True:
+        return res
+    g = [R.decompress(a[0:32]) for a in updated_accounts]
+    h = [R.decompress(a[32:64]) for a in updated_accounts]
+    Gb, Hb = R.decompress(base_pk[0:32]), R.decompress(base_pk[32:64])
+    if any(p is None for p in g + h + [Gb, Hb]):
+        return None
+    eg, eh, cg, ch = _multiexpo_ek(proof, x_exp, g, h)
+    if eg is None:
+        return None
+    if not R.eq(eg, R.add(cg, R.mul(proof["b"] % L, Gb))):
+        return "E_K"
+    if eh is None:
+        return None
+    return True if R.eq(eh, R.add(ch, R.mul(proof["b"] % L, Hb))) else "E_K"
+
+
+def multiexpo_commit_verify(tr, proof, c_A, updated_accounts, accounts, base_pk, exp_x, xpc):
+    """verify_multiexponential_elgamal_commit_proof -> True, None, "c_B_m", "Em", "a", "b", "E_K"."""
+    if len(proof["a_vec"]) != COLUMNS or proof["c_B_k"][ROWS] != bytes(32):
+        return "c_B_m"
+    C_c = _msm_point(exp_x, [a[64:96] for a in accounts])
+    if C_c is None:
+        return None
+    C_d = _msm_point(exp_x, [a[96:128] for a in accounts])
+    if C_d is None:
+        return None
+    if R.compress(C_c) != proof["E_k_0"][ROWS] or R.compress(C_d) != proof["E_k_1"][ROWS]:
+        return "Em"
+    x_exp = _multiexpo_transcript(tr, proof, b"MultiExponentialElgamalCommmitmentProof")
+    res = _multiexpo_scalars(proof, c_A, x_exp, xpc)
+    if res is not True:
+        return res
+    c = [R.decompress(a[64:96]) for a in updated_accounts]
+    d = [R.decompress(a[96:128]) for a in updated_accounts]
+    if any(p is None for p in c + d):
+        return None
+    Gb, Hb = R.decompress(base_pk[0:32]), R.decompress(base_pk[32:64])
+    bb_c = R.mul(proof["t"] % L, Gb)
+    bb_d = R.add(R.mul(proof["b"] % L, R.BASEPOINT), R.mul(proof["t"] % L, Hb))
+    ec, ed, cc, cd = _multiexpo_ek(proof, x_exp, c, d)
+    if ec is None:
+        return None
+    if not R.eq(ec, R.add(cc, bb_c)):
+        return "E_K"
+    if ed is None:
+        return None
+    return True if R.eq(ed, R.add(cd, bb_d)) else "E_K"
+
+
+# ---- the shuffle proof (reference src/shuffle/shuffle.rs) -------------------------------------------------------------------
+def input_shuffle(inputs, perm, tau, rho):
+    """Shuffle::input_shuffle with its randomness as arguments: perm = a permutation of 1..9 (row major), tau (9), rho.
+    -> dict(inputs, outputs, tau, rho, pi) as the reference's Shuffle struct holds them (pi already inverted)."""
+    shuffled = [inputs[perm[i] - 1] for i in range(9)]
+    inv = [0] * 9
+    for i in range(9):
+        inv[perm[i] - 1] = i + 1
+    outs = []
+    for acc, t in zip(inputs, tau):
+        o, st = R.update_account(acc, sb(0), sb(t), sb(rho))
+        assert st == 0
+        outs.append(o)
+    return {"inputs": shuffled, "outputs": outs, "tau": list(tau), "rho": rho, "pi": inv}
+
+
+def shuffle_prove(tr, shuffle, xpc, rnd):
+    """ShuffleProof::create_shuffle_proof.  rnd: r, r_dash, s, s_dash (3 each), "hadamard", "product", "ddh_r", "mexp_pk",
+    "mexp_comm" (the sub-provers' randomness).  -> (proof, statement)."""
+    pi, tau, rho = shuffle["pi"], shuffle["tau"], shuffle["rho"]
+    witness = _rows3(pi)
+    r, r_dash, s, s_dash = rnd["r"], rnd["r_dash"], rnd["s"], rnd["s_dash"]
+    c_A = [xpc.commit(witness[i], r[i]) for i in range(ROWS)]
+    tau_rows = _rows3(tau)
+    c_tau = [xpc.commit(tau_rows[i], r_dash[i]) for i in range(COLUMNS)]
+    for a, t in zip(c_A, c_tau):
+        tr.append_point_var(b"ACommitment", a)
+        tr.append_point_var(b"tauCommitment", t)
+    x = tr.get_challenge(b"xChallenge")
+    exp_x = exp_iter(x, 9, skip=1)
+    x_psi = [exp_x[pi[i] - 1] for i in range(9)]
+    b_dash = [x_psi[i] * pow(tau[i], -1, L) % L for i in range(9)]
+    b_rows, b_dash_rows = _rows3(x_psi), _rows3(b_dash)
+    c_B = [xpc.commit(b_rows[i], s[i]) for i in range(ROWS)]
+    c_B_dash = [xpc.commit(b_dash_rows[i], s_dash[i]) for i in range(ROWS)]
+    for cb, cbd in zip(c_B, c_B_dash):
+        tr.append_point_var(b"BCommitment", cb)
+        tr.append_point_var(b"BDashCommitment", cbd)
+    had_proof, omega = hadamard_prove(tr, xpc, b_dash_rows, tau_rows, b_rows, c_B_dash, c_tau, c_B, s_dash, r_dash, s,
+                                      rnd["hadamard"])
+    y = tr.get_challenge(b"yChallenge")
+    z = tr.get_challenge(b"zChallenge")
+    e = [(a * y + b - z) % L for a, b in zip(pi, x_psi)]
+    t = [(ri * y + si) % L for ri, si in zip(r, s)]
+    e_2d_rows = [[e[c * ROWS + rr] for c in range(COLUMNS)] for rr in range(ROWS)]      # Array2D::from_column_major
+    prod_proof, prod_state = product_prove(tr, xpc, e_2d_rows, t, rnd["product"])
+    g_i = [a[0:32] for a in shuffle["inputs"]]
+    h_i = [a[32:64] for a in shuffle["inputs"]]
+    G, H = R.compress(_msm_point(exp_x, g_i)), R.compress(_msm_point(exp_x, h_i))
+    ddh_proof, ddh_state = ddh_prove(tr, g_i, h_i, exp_x, G, H, rho, rnd["ddh_r"])
+    upk = [a[0:64] for a in shuffle["outputs"]]
+    ucomm = [a[64:128] for a in shuffle["outputs"]]
+    mexp_pk = multiexpo_pubkey_prove(tr, xpc, upk, b_dash_rows, s_dash, R.BASE_PK, rnd["mexp_pk"])
+    mexp_comm = multiexpo_commit_prove(tr, xpc, ucomm, b_rows, s, G + H, (-rho) % L, rnd["mexp_comm"])
+    proof = {"c_A": c_A, "c_tau": c_tau, "c_B": c_B, "c_B_dash": c_B_dash, "hadamard": had_proof, "product": prod_proof,
+             "mexp_pk": mexp_pk, "mexp_comm": mexp_comm, "ddh": ddh_proof}
+    return proof, {"omega": omega, "product": prod_state, "ddh": ddh_state}
+
+
+def shuffle_verify(tr, proof, statement, shuffle_input, shuffle_output, xpc):
+    """ShuffleProof::verify -> (True, None) or (False, (stage, reason)): stage in "length", "hadamard", "product_b", "c_F",
+    "product", "pk", "ddh", "mexp_pk", "mexp_comm"; reason = the sub-verifier's result (None = a decompression Err)."""
+    if not all(len(proof[k]) == ROWS for k in ("c_A", "c_B", "c_B_dash", "c_tau")):
+        return False, ("length", None)
+    for ca, ctau in zip(proof["c_A"], proof["c_tau"]):
+        tr.append_point_var(b"ACommitment", ca)
+        tr.append_point_var(b"tauCommitment", ctau)
+    x = tr.get_challenge(b"xChallenge")
+    exp_x = exp_iter(x, 9, skip=1)
+    for b, bd in zip(proof["c_B"], proof["c_B_dash"]):
+        tr.append_point_var(b"BCommitment", b)
+        tr.append_point_var(b"BDashCommitment", bd)
+    res = hadamard_verify(tr, proof["hadamard"], statement["omega"], proof["c_B_dash"], proof["c_tau"], proof["c_B"], xpc)
+    if res is not True:
+        return False, ("hadamard", res)
+    y = tr.get_challenge(b"yChallenge")
+    z = tr.get_challenge(b"zChallenge")
+    product = 1
+    for i, xi in enumerate(exp_x):
+        product = product * (y * (i + 1) + xi - z) % L
+    if product != statement["product"]["svp"][1] % L:
+        return False, ("product_b", False)
+    z_neg = xpc.commit_point([(-z) % L] * 3, 0)
+    c_E = []
+    for ca, cb in zip(proof["c_A"], proof["c_B"]):
+        pa, pb = R.decompress(ca), R.decompress(cb)
+        if pa is None or pb is None:
+            return False, ("c_F", None)
+        c_E.append(R.compress(R.add(R.add(R.mul(y, pa), pb), z_neg)))
+    res = product_verify(tr, proof["product"], statement["product"], c_E, xpc)
+    if res is not True:
+        return False, ("product", res)
+    g_i = [a[0:32] for a in shuffle_input]
+    h_i = [a[32:64] for a in shuffle_input]
+    Gp, Hp = _msm_point(exp_x, g_i), _msm_point(exp_x, h_i)
+    if Gp is None or Hp is None:
+        return False, ("pk", None)
+    G, H = R.compress(Gp), R.compress(Hp)
+    res = ddh_verify(tr, proof["ddh"], statement["ddh"], G, H)
+    if res is not True:
+        return False, ("ddh", res)
+    res = multiexpo_pubkey_verify(tr, proof["mexp_pk"], proof["c_B_dash"], shuffle_output, R.BASE_PK, G + H, xpc)
+    if res is not True:
+        return False, ("mexp_pk", res)
+    res = multiexpo_commit_verify(tr, proof["mexp_comm"], proof["c_B"], shuffle_output, shuffle_input, G + H, exp_x, xpc)
+    if res is not True:
+        return False, ("mexp_comm", res)
+    return True, None

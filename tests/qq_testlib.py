@@ -224,3 +224,32 @@ def scenario_product(st, pi=(7, 6, 1, 5, 3, 4, 2, 8, 9)):
     tr = F.new_transcript(b"ShuffleProof", b"Shuffle")
     proof, statement = F.product_prove(tr, xpc, rows, r, rnd)
     return c_prod_A, proof, statement
+
+
+def scenario_shuffle(st, perm=None):
+    """shuffle.rs shuffle_proof_test (:759-795): 9 zero-balance accounts, Shuffle::input_shuffle, create_shuffle_proof.
+    -> (shuffle_input[9], shuffle_output[9], proof, statement); transcript b"ShuffleProof" / b"Shuffle"."""
+    import shuffle_ref as F
+    xpc = F.XpcGens(4)
+    accounts = [make_account(st, 0)[0] for _ in range(9)]
+    if perm is None:
+        perm = list(range(1, 10))
+        for i in range(8, 0, -1):
+            j = st.scalar() % (i + 1)
+            perm[i], perm[j] = perm[j], perm[i]
+    sh = F.input_shuffle(accounts, perm, [st.scalar() for _ in range(9)], st.scalar())
+    v3 = lambda: [st.scalar() for _ in range(3)]  # noqa: E731
+    mexp = lambda: {"a_0": v3(), "r_0": st.scalar(), "b_vec": [st.scalar() for _ in range(6)],  # noqa: E731
+                    "s_vec": [st.scalar() for _ in range(6)], "tau_vec": [st.scalar() for _ in range(6)]}
+    rnd = {"r": v3(), "r_dash": v3(), "s": v3(), "s_dash": v3(),
+           "hadamard": {"a_0": v3(), "b_0": v3(), "r_0": st.scalar(), "s_0": st.scalar(), "t_0": st.scalar(), "omega": v3(),
+                        "rho": [st.scalar() for _ in range(4)]},
+           "product": {"s": st.scalar(),
+                       "mh": {"s_mid": st.scalar(),
+                              "zero": {"a_0": v3(), "b_m": v3(), "r_0": st.scalar(), "s_m": st.scalar(),
+                                       "t": [st.scalar() for _ in range(7)]}},
+                       "svp": (v3(), st.scalar(), [st.scalar()], st.scalar(), st.scalar())},
+           "ddh_r": st.scalar(), "mexp_pk": mexp(), "mexp_comm": mexp()}
+    tr = F.new_transcript(b"ShuffleProof", b"Shuffle")
+    proof, statement = F.shuffle_prove(tr, sh, xpc, rnd)
+    return sh["inputs"], sh["outputs"], proof, statement

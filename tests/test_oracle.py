@@ -297,3 +297,44 @@ def test_product_argument_round_trip_and_bilinear_map_vectors():
     bad_state = copy.deepcopy(state)
     bad_state["mh"]["c_b"] = cA[0]
     assert F.product_verify(V(), proof, bad_state, cA, xpc) == "c_B_m"
+
+
+def test_shuffle_proof_round_trip():
+    """oracle/shuffle_ref.py: the whole Bayer-Groth shuffle argument on the reference's shuffle_proof_test scenario
+    (src/shuffle/shuffle.rs:759-795): Shuffle::input_shuffle + create_shuffle_proof verifies under ShuffleProof::verify;
+    a tampered proof / statement / account set fails in the stage it belongs to."""
+    import copy
+    import shuffle_ref as F
+    from qq_testlib import scenario_shuffle
+    st = Stream(b"shuffle-cpu")
+    inp, out, proof, state = scenario_shuffle(st)
+    xpc = F.XpcGens(4)
+    V = lambda: F.new_transcript(b"ShuffleProof", b"Shuffle")  # noqa: E731
+    assert F.shuffle_verify(V(), proof, state, inp, out, xpc) == (True, None)
+
+    def tampered(path, delta=1, target="proof"):
+        p, s = copy.deepcopy(proof), copy.deepcopy(state)
+        node = p if target == "proof" else s
+        for k in path[:-1]:
+            node = node[k]
+        if isinstance(node[path[-1]], int):
+            node[path[-1]] += delta
+        else:
+            node[path[-1]] = delta
+        return p, s
+    p, s = tampered(("hadamard", "rho_bar"))
+    assert F.shuffle_verify(V(), p, s, inp, out, xpc) == (False, ("hadamard", "delta"))
+    p, s = tampered(("product", "svp"), (state["product"]["svp"][0], state["product"]["svp"][1] + 1), target="state")
+    assert F.shuffle_verify(V(), p, s, inp, out, xpc) == (False, ("product_b", False))
+    p, s = tampered(("product", "mh", "zero_proof", "t"))
+    assert F.shuffle_verify(V(), p, s, inp, out, xpc) == (False, ("product", "ab"))
+    p, s = tampered(("ddh",), (proof["ddh"][0], proof["ddh"][1] + 1))
+    assert F.shuffle_verify(V(), p, s, inp, out, xpc) == (False, ("ddh", False))
+    p, s = tampered(("mexp_pk", "b"))
+    assert F.shuffle_verify(V(), p, s, inp, out, xpc) == (False, ("mexp_pk", "b"))
+    p, s = tampered(("mexp_comm", "t"))
+    assert F.shuffle_verify(V(), p, s, inp, out, xpc) == (False, ("mexp_comm", "E_K"))
+    swapped = [out[1], out[0]] + out[2:]
+    assert F.shuffle_verify(V(), proof, state, inp, swapped, xpc) == (False, ("mexp_pk", "E_K"))
+    other = [inp[1], inp[0]] + inp[2:]
+    assert F.shuffle_verify(V(), proof, state, other, out, xpc)[1][0] == "ddh"
