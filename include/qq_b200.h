@@ -293,6 +293,22 @@ int qq_verify_hadamard_batch(qq_ctx* ctx, const char* transcript_label, const ch
  * ... Failed", 7 = "SingleValue Product Proof Verify: Failed".  detail may be NULL. */
 int qq_verify_product_batch(qq_ctx* ctx, const char* transcript_label, const char* verifier_label, const uint8_t* c_prod_A,
                             const uint8_t* statement, const uint8_t* proof, size_t nproofs, uint8_t* status, uint8_t* detail);
+/* ShuffleProof::verify (src/shuffle/shuffle.rs:547-712): the whole shuffle argument over 9 accounts, nproofs independent
+ * proofs in two GPU round trips (Hadamard + product arguments + key aggregates, then DDH check + the two multi-exponentiation
+ * arguments).  shuffle_input / shuffle_output: nproofs x 9 x 128 B.  statement: nproofs x 352 B = HadamardStatement omega[3] |
+ * ProductStatement (192 B, as above) | DDHStatement G_dash | H_dash.  proof: nproofs x 3776 B = c_A[3] | c_tau[3] | c_B[3] |
+ * c_B_dash[3] | HadamardProof (640 B) | ProductProof (1024 B) | multi_exponen_pk | multi_exponen_commit (MultiexpoProof, 832 B
+ * each: c_A_0 | c_B_k[6] | E_k_0[6] | E_k_1[6] | a_vec[3] | r | b | s | t) | DDHProof challenge | z - the structs' fields in
+ * declaration order, vectors without their bincode length prefix.  status[p]: QQ_ST_OK = Ok(()), QQ_ST_PROOF (a check
+ * failed), QQ_ST_BAD_POINT (an Err caused by an undecodable point), QQ_ST_BAD_SCALAR.  stage[p] / detail[p] (may be NULL): 1
+ * Hadamard (detail as qq_verify_hadamard_batch), 2 "Shuffle Proof Verify:prod pf i .. N (yi + x^i -z) failed", 3 "ShuffleProof
+ * Verify: Decompression Failed" (c_A / c_B), 4 product argument (detail as qq_verify_product_batch), 5 the same message for an
+ * input key, 6 "DDH Proof Verify: Failed", 7 / 8 "Multi-exponentiation Pubkey / Commitment Argument: ..." with detail 1 "Verify
+ * com(0,0) == c_B_m Failed", 2 "Verify Em == C Failed", 3 "a Scalar vector Verification Failed", 4 "Scalar b Verification Failed",
+ * 5 "E_K Verification Failed". */
+int qq_verify_shuffle_batch(qq_ctx* ctx, const char* transcript_label, const char* verifier_label, const uint8_t* shuffle_input,
+                            const uint8_t* shuffle_output, const uint8_t* statement, const uint8_t* proof, size_t nproofs,
+                            uint8_t* status, uint8_t* stage, uint8_t* detail);
 
 /* ---- decommit ------------------------------------------------------------------------------------------------------
  * ElGamalCommitment::decommit(sk) = enc(d - sk*c) = enc(v*B)                    src/elgamal/elgamal.rs:106-108 */

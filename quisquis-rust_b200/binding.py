@@ -22,7 +22,7 @@ EXPORTS = [
     "qq_fixed_base_i64_batch", "qq_fixed_base_i64_batch_dev", "qq_msm", "qq_msm_dev", "qq_msm_partial", "qq_msm_partial_dev",
     "qq_points_sum", "qq_msm_segmented", "qq_msm_points_prepare", "qq_msm_points_prepare_dev", "qq_msm_points_free",
     "qq_msm_points_count", "qq_msm_prepared", "qq_msm_prepared_dev",
-    "qq_verify_ddh_batch", "qq_verify_svp_batch", "qq_verify_hadamard_batch", "qq_verify_product_batch",
+    "qq_verify_ddh_batch", "qq_verify_svp_batch", "qq_verify_hadamard_batch", "qq_verify_product_batch", "qq_verify_shuffle_batch",
     "qq_verify_account_sigma_batch", "qq_verify_zero_balance_batch", "qq_verify_destroy_account_batch",
     "qq_verify_same_value_compact_batch", "qq_verify_update_account_dark_tx_batch",
     "qq_verify_update_account_dlog_batch", "qq_verify_delta_compact_batch", "qq_decommit_batch", "qq_decommit_value_batch", "qq_from_uniform_bytes_batch", "qq_vector_pedersen_gens", "qq_bulletproof_gens",
@@ -104,6 +104,7 @@ def load_library():
     lib.qq_verify_svp_batch.argtypes = [vp, cs, cs, u8p, u8p, u8p, sz, u8p]
     lib.qq_verify_hadamard_batch.argtypes = [vp, cs, cs, u8p, u8p, u8p, u8p, u8p, sz, u8p, u8p]
     lib.qq_verify_product_batch.argtypes = [vp, cs, cs, u8p, u8p, u8p, sz, u8p, u8p]
+    lib.qq_verify_shuffle_batch.argtypes = [vp, cs, cs, u8p, u8p, u8p, u8p, sz, u8p, u8p, u8p]
     lib.qq_decommit_batch.argtypes = [vp, u8p, u8p, u8p, u8p, sz]
     lib.qq_decommit_value_batch.argtypes = [vp, u8p, u8p, ctypes.c_int, u8p, u8p, sz]
     lib.qq_from_uniform_bytes_batch.argtypes = [vp, u8p, u8p, sz]
@@ -473,6 +474,17 @@ class Engine:
         self._ck(self.lib.qq_verify_product_batch(self.h, transcript_label, verifier_label, _ptr(ca), _ptr(stm), _ptr(pr),
                                                    nproofs, _ptr(st), _ptr(det)), "qq_verify_product_batch")
         return st, det
+
+    def verify_shuffle(self, shuffle_input, shuffle_output, statement, proof, transcript_label=b"ShuffleProof",
+                       verifier_label=b"Shuffle"):
+        """ShuffleProof::verify for proof.size // 3776 proofs over 9 accounts each -> (status, stage, detail) per proof."""
+        si, so, stm, pr = (_u8(a) for a in (shuffle_input, shuffle_output, statement, proof))
+        nproofs = pr.size // 3776
+        _u8(si, nproofs * 9 * 128), _u8(so, nproofs * 9 * 128), _u8(stm, nproofs * 352), _u8(pr, nproofs * 3776)
+        st, sg, det = (np.zeros(nproofs, np.uint8) for _ in range(3))
+        self._ck(self.lib.qq_verify_shuffle_batch(self.h, transcript_label, verifier_label, _ptr(si), _ptr(so), _ptr(stm), _ptr(pr),
+                                                   nproofs, _ptr(st), _ptr(sg), _ptr(det)), "qq_verify_shuffle_batch")
+        return st, sg, det
 
     def decommit(self, comm, sk):
         comm, sk = _u8(comm), _u8(sk)

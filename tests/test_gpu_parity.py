@@ -1157,3 +1157,106 @@ def test_product_argument(engine):
     got2, _ = engine.verify_product(cat([cat(k[0]) for k in cases]), cat([b[1] for b in blobs]), cat([b[0] for b in blobs]),
                                     transcript_label=b"Other")
     assert (got2[:2] != 0).all()
+
+
+def _mexp_blob(m):
+    out = (m["c_A_0"] + b"".join(m["c_B_k"]) + b"".join(m["E_k_0"]) + b"".join(m["E_k_1"]) + b"".join(sb(v) for v in m["a_vec"]) +
+           sb(m["r"]) + sb(m["b"]) + sb(m["s"]) + sb(m["t"]))
+    assert len(out) == 832
+    return out
+
+
+def _shuffle_blobs(proof, statement):
+    ppr, pst = _product_blobs(proof["product"], statement["product"])
+    pr = (b"".join(proof["c_A"]) + b"".join(proof["c_tau"]) + b"".join(proof["c_B"]) + b"".join(proof["c_B_dash"]) +
+          _hadamard_blob(proof["hadamard"]) + ppr + _mexp_blob(proof["mexp_pk"]) + _mexp_blob(proof["mexp_comm"]) +
+          sb(proof["ddh"][0]) + sb(proof["ddh"][1]))
+    stm = b"".join(sb(w) for w in statement["omega"]) + pst + statement["ddh"][0] + statement["ddh"][1]
+    assert len(pr) == 3776 and len(stm) == 352
+    return pr, stm
+
+
+def _shuffle_code(result):
+    """oracle shuffle_verify result -> (status, stage, detail or None when the detail is not pinned)"""
+    ok, why = result
+    if ok:
+        return (0, 0, 0)
+    stage, reason = why
+    num = {"hadamard": 1, "product_b": 2, "c_F": 3, "product": 4, "pk": 5, "ddh": 6, "mexp_pk": 7, "mexp_comm": 8}[stage]
+    if reason is None:
+        return (1, num, None)
+    if stage == "hadamard":
+        return (6, 1, {"omega": 1, "abc": 2, "delta": 3}[reason])
+    if stage == "product":
+        return (6, 4, PRODUCT_CODES[reason][1])
+    if stage in ("mexp_pk", "mexp_comm"):
+        return (6, num, {"c_B_m": 1, "Em": 2, "a": 3, "b": 4, "E_K": 5}[reason])
+    return (6, num, 0)
+
+
+def shuffle_cases(st):
+    """valid proofs over two permutations + one tampering per stage of ShuffleProof::verify"""
+    import copy
+    from qq_testlib import scenario_shuffle
+    base = [scenario_shuffle(st), scenario_shuffle(st, perm=[9, 8, 7, 6, 5, 4, 3, 2, 1])]
+    inp, out, proof, state = base[0]
+    cases = [list(k) for k in base]
+
+    def tampered(path, value=None, target="proof"):
+        p, s = copy.deepcopy(proof), copy.deepcopy(state)
+        node = p if target == "proof" else s
+        for k in path[:-1]:
+            node = node[k]
+        node[path[-1]] = node[path[-1]] + 1 if value is None else value
+        return [inp, out, p, s]
+    cases.append(tampered(("hadamard", "rho_bar")))
+    cases.append(tampered(("hadamard", "a_bar", 1)))
+    cases.append(tampered(("product", "svp"), (state["product"]["svp"][0], state["product"]["svp"][1] + 1), target="state"))
+    cases.append(tampered(("product", "mh", "zero_proof", "t")))
+    cases.append(tampered(("product", "mh", "zero_proof", "r")))
+    cases.append(tampered(("product", "svp", "s_twildle")))
+    cases.append(tampered(("product", "mh", "c_B", 0), proof["c_B"][0]))
+    cases.append(tampered(("ddh",), (proof["ddh"][0], proof["ddh"][1] + 1)))
+    cases.append(tampered(("ddh",), (state["ddh"][1], state["ddh"][0]), target="state"))
+    cases.append(tampered(("mexp_pk", "b")))
+    cases.append(tampered(("mexp_pk", "r")))
+    cases.append(tampered(("mexp_pk", "E_k_0", 3), proof["mexp_pk"]["E_k_1"][3]))
+    cases.append(tampered(("mexp_comm", "t")))
+    cases.append(tampered(("mexp_comm", "s")))
+    cases.append(tampered(("mexp_comm", "c_B_k", 3), R.BASEPOINT_COMPRESSED))
+    cases.append(tampered(("mexp_comm", "E_k_1", 3), proof["mexp_comm"]["E_k_0"][3]))
+    cases.append([inp, [out[1], out[0]] + out[2:], proof, state])              # outputs exchanged
+    cases.append([[inp[1], inp[0]] + inp[2:], out, proof, state])              # inputs exchanged
+    bad_key = bytearray(inp[4])
+    bad_key[32:64] = invalid_encodings()[4][1]
+    cases.append([inp[:4] + [bytes(bad_key)] + inp[5:], out, proof, state])    # undecodable input key
+    bad_out = bytearray(out[8])
+    bad_out[64:96] = invalid_encodings()[1][1]
+    cases.append([inp, out[:8] + [bytes(bad_out)], proof, state])              # undecodable output commitment
+    cases.append(tampered(("c_A", 1), invalid_encodings()[4][1]))              # moves x: the Hadamard argument fails first
+    return cases
+
+
+def test_shuffle_proof_verification(engine):
+    """ShuffleProof::verify, batched in two GPU round trips (src/shuffle/shuffle.rs:547-712); the reference's
+    shuffle_proof_test scenario (:759-795) with proofs from the oracle's restatement of Shuffle::input_shuffle and
+    create_shuffle_proof.  Per proof: accept / reject, the stage that rejected and its check equal the oracle verifier's."""
+    import shuffle_ref as F
+    st = Stream(b"shuffle-gpu")
+    xpc = F.XpcGens(4)
+    cases = shuffle_cases(st)
+    expect = [_shuffle_code(F.shuffle_verify(F.new_transcript(b"ShuffleProof", b"Shuffle"), k[2], k[3], k[0], k[1], xpc))
+              for k in cases]
+    assert [e[0] for e in expect[:2]] == [0, 0] and all(e[0] != 0 for e in expect[2:])
+    assert {e[1] for e in expect} == {0, 1, 2, 4, 5, 6, 7, 8}                  # every stage but the c_F decode is hit
+    blobs = [_shuffle_blobs(k[2], k[3]) for k in cases]
+    got = engine.verify_shuffle(cat([cat(k[0]) for k in cases]), cat([cat(k[1]) for k in cases]), cat([b[1] for b in blobs]),
+                                cat([b[0] for b in blobs]))
+    for i, e in enumerate(expect):
+        g = tuple(int(a[i]) for a in got)
+        assert g[:2] == e[:2] and (e[2] is None or g[2] == e[2]), (i, e, g)
+    # one proof per call and another transcript label
+    one = engine.verify_shuffle(cat(cases[1][0]), cat(cases[1][1]), blobs[1][1], blobs[1][0])
+    assert tuple(int(a[0]) for a in one) == (0, 0, 0)
+    other = engine.verify_shuffle(cat(cases[1][0]), cat(cases[1][1]), blobs[1][1], blobs[1][0], transcript_label=b"Other")
+    assert int(other[0][0]) == 6 and int(other[1][0]) == 1
