@@ -1260,3 +1260,21 @@ def test_shuffle_proof_verification(engine):
     assert tuple(int(a[0]) for a in one) == (0, 0, 0)
     other = engine.verify_shuffle(cat(cases[1][0]), cat(cases[1][1]), blobs[1][1], blobs[1][0], transcript_label=b"Other")
     assert int(other[0][0]) == 6 and int(other[1][0]) == 1
+
+
+def test_golden_shuffle_proofs_accepted(engine):
+    """The committed proofs of tests/golden/shuffle_proofs.bin (made by the oracle's prover restatement) are accepted; the
+    same proofs with one byte of an output account / of a response flipped are rejected."""
+    import os
+    raw = np.fromfile(os.path.join(os.path.dirname(__file__), "golden", "shuffle_proofs.bin"), dtype=np.uint8)
+    rec = raw.reshape(-1, 6432)
+    n = rec.shape[0]
+    si, so, stm, pr = rec[:, :1152].copy(), rec[:, 1152:2304].copy(), rec[:, 2304:2656].copy(), rec[:, 2656:].copy()
+    st, sg, det = engine.verify_shuffle(si, so, stm, pr)
+    assert not st.any() and not sg.any()
+    so2 = so.copy()
+    so2[0, 5] ^= 1
+    pr2 = pr.copy()
+    pr2[1, 3776 - 1 - 32] ^= 1          # top byte of the DDH challenge: still canonical or not, never the right one
+    st, sg, det = engine.verify_shuffle(si, so2, stm, pr2)
+    assert st[0] != 0 and st[1] != 0 and not st[2:].any()

@@ -338,3 +338,19 @@ def test_shuffle_proof_round_trip():
     assert F.shuffle_verify(V(), proof, state, inp, swapped, xpc) == (False, ("mexp_pk", "E_K"))
     other = [inp[1], inp[0]] + inp[2:]
     assert F.shuffle_verify(V(), proof, state, other, out, xpc)[1][0] == "ddh"
+
+
+def test_golden_shuffle_fixture_is_what_the_oracle_prover_makes():
+    """tests/golden/shuffle_proofs.bin (the workload of bench.py's shuffle-verification section) is reproduced byte for
+    byte by its generator: the oracle's prover restatement on seeded inputs, serialised in the C ABI's layout."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    gold = open(os.path.join(here, "golden", "shuffle_proofs.bin"), "rb").read()
+    assert len(gold) % 6432 == 0 and len(gold) >= 6432
+    import shuffle_ref as F
+    import test_gpu_parity as T
+    from qq_testlib import scenario_shuffle
+    st = Stream(b"shuffle-golden")
+    inp, outp, proof, state = scenario_shuffle(st)
+    pr, stm = T._shuffle_blobs(proof, state)
+    assert gold[:6432] == b"".join(inp) + b"".join(outp) + stm + pr
+    assert F.shuffle_verify(F.new_transcript(b"ShuffleProof", b"Shuffle"), proof, state, inp, outp, F.XpcGens(4)) == (True, None)

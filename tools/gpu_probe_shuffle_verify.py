@@ -1,0 +1,41 @@
+"""Throughput of the batched ShuffleProof::verify (qq_verify_shuffle_batch) on the committed valid proofs
+(tests/golden/shuffle_proofs.bin), tiled to N proofs (BASELINE.json configs[2]: 4096).  Every proof must be accepted."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as g  # noqa: E402
+
+
+def load(n):
+    raw = np.fromfile(os.path.join(ROOT, "tests", "golden", "shuffle_proofs.bin"), dtype=np.uint8).reshape(-1, 6432)
+    rec = np.tile(raw, ((n + raw.shape[0] - 1) // raw.shape[0], 1))[:n]
+    return (np.ascontiguousarray(rec[:, :1152]), np.ascontiguousarray(rec[:, 1152:2304]),
+            np.ascontiguousarray(rec[:, 2304:2656]), np.ascontiguousarray(rec[:, 2656:]))
+
+
+def main():
+    pkg = g.load_package()
+    eng = pkg.Engine(0)
+    for n in [int(x) for x in (sys.argv[1:] or ["1", "64", "4096"])]:
+        si, so, stm, pr = load(n)
+        ts = []
+        for rep in range(4):
+            t = time.perf_counter()
+            st, sg, det = eng.verify_shuffle(si, so, stm, pr)
+            ts.append(time.perf_counter() - t)
+        assert not st.any()
+        best = min(ts[1:])
+        print(json.dumps({"probe": "verify_shuffle", "proofs": n, "wall_ms": best * 1e3, "proofs_per_s": n / best,
+                          "last_batch_kernel_ms": eng.last_kernel_ms, "msms": 28 * n, "terms": 239 * n,
+                          "all_accepted": True}), flush=True)
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()
