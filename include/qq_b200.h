@@ -310,6 +310,36 @@ int qq_verify_shuffle_batch(qq_ctx* ctx, const char* transcript_label, const cha
                             const uint8_t* shuffle_output, const uint8_t* statement, const uint8_t* proof, size_t nproofs,
                             uint8_t* status, uint8_t* stage, uint8_t* detail);
 
+/* ---- Bulletproofs range proofs (BASELINE configs[3]) -----------------------------------------------------------------
+ * RangeProof::verify_multiple / verify_single of the `bulletproofs` crate, as called by
+ *   Verifier::verify_non_negative_sender_receiver_bulletproof_batch_verifier   src/accounts/verifier.rs:504-523
+ *       (domain_label "AggregateBulletProof", n_bits 64, m = epsilon_account.len() <= 16 a power of two, chain 1)
+ *   Verifier::verify_non_negative_sender_receiver_bulletproof_vector_verifier  src/accounts/verifier.rs:534-555
+ *       (same label, m = 1, chain = proof_vector.len(): the proofs of one call run on ONE transcript, in order)
+ * for nproofs independent transcripts.  commitments: nproofs x chain x m x 32 B (the reference passes acc.comm.d);
+ * proofs: nproofs x chain x (9 + 2 lg(n_bits m)) x 32 B, each RangeProof::to_bytes() = A | S | T_1 | T_2 | t_x |
+ * t_x_blinding | e_blinding | L_0 | R_0 | .. | a | b.  Generators: PedersenGens::default(), BulletproofGens::new(64, 16).
+ * The transcript of proof p is Transcript::new(transcript_label) + Verifier::new(verifier_label) (verifier_label NULL: a bare
+ * merlin transcript, for RangeProof::verify_multiple outside the reference's Verifier), or - when
+ * transcript_state is not NULL - the qq_transcript_state_bytes() bytes at transcript_state + p * that size (a transcript an
+ * earlier verification on the same Verifier left behind, see qq_transcript_capture); then domain_sep(domain_label) unless
+ * domain_label is NULL.
+ * Host threads run the transcripts; the GPU folds the generator scalars of all proofs with random weights and evaluates ONE
+ * aggregated MSM (2 n m + 2 shared terms + 4 + 2 lg(n m) + m terms per proof); a failing aggregate is bisected, so the
+ * verdict is per transcript.  status[p]: QQ_ST_OK = Ok(()), QQ_ST_PROOF = Err("Bulletproof verification failed"),
+ * QQ_ST_BAD_POINT = the same Err caused by an undecodable point, QQ_ST_BAD_SCALAR = a non-canonical scalar (the crate's
+ * RangeProof::from_bytes FormatError). */
+int qq_verify_range_proof_batch(qq_ctx* ctx, const char* transcript_label, const char* verifier_label,
+                                const uint8_t* transcript_state, const char* domain_label, const uint8_t* commitments,
+                                const uint8_t* proofs, size_t n_bits, size_t m, size_t chain, size_t nproofs, uint8_t* status);
+/* Size of one serialised verifier transcript (opaque: the STROBE-128 state of merlin::Transcript). */
+size_t qq_transcript_state_bytes(void);
+/* The NEXT sigma-proof verification call on this ctx (qq_verify_account_sigma_batch, ..) also writes the transcript of each
+ * proof, as it stands after the challenge, to states_out (nproofs x qq_transcript_state_bytes()): the reference keeps one
+ * running transcript per Verifier across verify_account_verifier_bulletproof and the range proof (verifier.rs:1603-1628).
+ * One-shot; NULL cancels. */
+int qq_transcript_capture(qq_ctx* ctx, uint8_t* states_out);
+
 /* ---- decommit ------------------------------------------------------------------------------------------------------
  * ElGamalCommitment::decommit(sk) = enc(d - sk*c) = enc(v*B)                    src/elgamal/elgamal.rs:106-108 */
 int qq_decommit_batch(qq_ctx* ctx, const uint8_t* comm, const uint8_t* sk, uint8_t* out_points, uint8_t* status, size_t n);

@@ -155,10 +155,12 @@ def create_epsilon_account(base_pk, rscalar, bl):
 
 # ---- sender account proof: prover src/accounts/prover.rs:355-500, verifier src/accounts/verifier.rs:396-470 -------------
 def prove_account(delta_accounts, bl, sk, base_pk, eps_rscalars, blindings, transcript_label=b"SenderAccountProof",
-                  prover_label=b"DLOGProof"):
-    """-> (epsilon_accounts, zv[], zsk[], zr[], x).  blindings: per account (r_v, r_sk, r_dash)."""
-    tr = Transcript(transcript_label)
-    tr.domain_sep(prover_label)
+                  prover_label=b"DLOGProof", tr=None):
+    """-> (epsilon_accounts, zv[], zsk[], zr[], x).  blindings: per account (r_v, r_sk, r_dash).
+    tr: the Prover's running transcript (Transcript::new + Prover::new already applied), continued in place."""
+    if tr is None:
+        tr = Transcript(transcript_label)
+        tr.domain_sep(prover_label)
     tr.domain_sep(b"VerifyAccountProof")
     eps = [create_epsilon_account(base_pk, r, v) for r, v in zip(eps_rscalars, bl)]
     for d, e in zip(delta_accounts, eps):
@@ -182,10 +184,12 @@ def prove_account(delta_accounts, bl, sk, base_pk, eps_rscalars, blindings, tran
 
 
 def verify_account(delta_accounts, epsilon_accounts, base_pk, zv, zsk, zr, x, transcript_label=b"SenderAccountProof",
-                   verifier_label=b"DLOGProof"):
-    """-> True, False ("sender account verification failed") or None ("Account Verify: Failed")."""
-    tr = Transcript(transcript_label)
-    tr.domain_sep(verifier_label)
+                   verifier_label=b"DLOGProof", tr=None):
+    """-> True, False ("sender account verification failed") or None ("Account Verify: Failed").
+    tr: the Verifier's running transcript, continued in place."""
+    if tr is None:
+        tr = Transcript(transcript_label)
+        tr.domain_sep(verifier_label)
     tr.domain_sep(b"VerifyAccountProof")
     for d, e in zip(delta_accounts, epsilon_accounts):
         tr.append_account_var(b"delta_account", d)

@@ -296,10 +296,14 @@ class Verifier:
 
     @staticmethod
     def verify_account_verifier_bulletproof(updated_delta_account_sender, account_epsilon_sender, base_pk, zv, zsk, zr, x,
-                                            transcript_label=b"SenderAccountProof", verifier_label=b"DLOGProof"):
-        """src/accounts/verifier.rs:396-470 (and the sigma-protocol part of verify_account_verifier, :305-381)."""
+                                            transcript_label=b"SenderAccountProof", verifier_label=b"DLOGProof",
+                                            keep_transcript=False):
+        """src/accounts/verifier.rs:396-470 (and the sigma-protocol part of verify_account_verifier, :305-381).
+        keep_transcript: return the verifier's running transcript (opaque bytes) for the range-proof verification that
+        follows on the same Verifier in the reference (verifier.rs:1603-1628)."""
         n = len(zv)
         j = lambda v: b"".join(bytes(s) for s in v)  # noqa: E731
+        state = default_engine().transcript_capture(1) if keep_transcript else None
         st = default_engine().verify_account_sigma(b"".join(a.data for a in updated_delta_account_sender),
                                                    b"".join(a.data for a in account_epsilon_sender), base_pk.data, j(zv),
                                                    j(zsk), j(zr), bytes(x), n, transcript_label, verifier_label)
@@ -307,6 +311,40 @@ class Verifier:
             raise ValueError("Account Verify: Failed")
         if st[0]:
             raise ValueError("sender account verification failed")
+        return state
+
+    @staticmethod
+    def verify_non_negative_sender_receiver_bulletproof_batch_verifier(epsilon_account, proof, transcript_label=b"SenderAccountProof",
+                                                                       verifier_label=b"BulletProof", transcript=None):
+        """src/accounts/verifier.rs:504-523: one aggregated 64-bit range proof over the d components of the epsilon accounts.
+        proof: RangeProof::to_bytes().  transcript: what verify_account_verifier_bulletproof(keep_transcript=True) returned."""
+        eng = default_engine()
+        m = len(epsilon_account)
+        proof = bytes(proof)
+        if m == 0 or m > 16 or m & (m - 1) or len(proof) != eng.range_proof_bytes(m):
+            raise ValueError("Bulletproof verification failed")
+        st = eng.verify_range_proofs(b"".join(a.data[96:128] for a in epsilon_account), proof, m, 1, 64, transcript_label,
+                                     verifier_label, b"AggregateBulletProof", transcript)
+        if st[0]:
+            raise ValueError("Bulletproof verification failed")
+        return None
+
+    @staticmethod
+    def verify_non_negative_sender_receiver_bulletproof_vector_verifier(epsilon_account, proof_vector,
+                                                                        transcript_label=b"SenderAccountProof",
+                                                                        verifier_label=b"BulletProof", transcript=None):
+        """src/accounts/verifier.rs:534-555: one single-value range proof per epsilon account, all on one transcript."""
+        eng = default_engine()
+        k = min(len(epsilon_account), len(proof_vector))          # zip() stops at the shorter one
+        if k == 0:
+            return None
+        proofs = [bytes(p) for p in proof_vector[:k]]
+        if any(len(p) != eng.range_proof_bytes(1) for p in proofs):
+            raise ValueError("Bulletproof verification failed")
+        st = eng.verify_range_proofs(b"".join(a.data[96:128] for a in epsilon_account[:k]), b"".join(proofs), 1, k, 64,
+                                     transcript_label, verifier_label, b"AggregateBulletProof", transcript)
+        if st[0]:
+            raise ValueError("Bulletproof verification failed")
         return None
 
     @staticmethod

@@ -26,6 +26,7 @@ EXPORTS = [
     "qq_verify_account_sigma_batch", "qq_verify_zero_balance_batch", "qq_verify_destroy_account_batch",
     "qq_verify_same_value_compact_batch", "qq_verify_update_account_dark_tx_batch",
     "qq_verify_update_account_dlog_batch", "qq_verify_delta_compact_batch", "qq_decommit_batch", "qq_decommit_value_batch", "qq_from_uniform_bytes_batch", "qq_vector_pedersen_gens", "qq_bulletproof_gens",
+    "qq_verify_range_proof_batch", "qq_transcript_state_bytes", "qq_transcript_capture",
 ]
 
 
@@ -110,6 +111,10 @@ def load_library():
     lib.qq_from_uniform_bytes_batch.argtypes = [vp, u8p, u8p, sz]
     lib.qq_vector_pedersen_gens.argtypes = [vp, sz, u8p, u8p]
     lib.qq_bulletproof_gens.argtypes = [vp, sz, sz, u8p, u8p]
+    lib.qq_verify_range_proof_batch.argtypes = [vp, cs, cs, u8p, cs, u8p, u8p, sz, sz, sz, sz, u8p]
+    lib.qq_transcript_state_bytes.argtypes = []
+    lib.qq_transcript_state_bytes.restype = ctypes.c_size_t
+    lib.qq_transcript_capture.argtypes = [vp, u8p]
     lib.qq_msm_points_free.argtypes = [vp, vp]
     lib.qq_msm_points_free.restype = None
     lib.qq_msm_points_count.argtypes = [vp]
@@ -485,6 +490,34 @@ class Engine:
         self._ck(self.lib.qq_verify_shuffle_batch(self.h, transcript_label, verifier_label, _ptr(si), _ptr(so), _ptr(stm), _ptr(pr),
                                                    nproofs, _ptr(st), _ptr(sg), _ptr(det)), "qq_verify_shuffle_batch")
         return st, sg, det
+
+    def range_proof_bytes(self, m, n_bits=64):
+        """Length of RangeProof::to_bytes() for m aggregated n_bits-bit values."""
+        return (9 + 2 * ((n_bits * m).bit_length() - 1)) * 32
+
+    def verify_range_proofs(self, commitments, proofs, m, chain=1, n_bits=64, transcript_label=b"SenderAccountProof",
+                            verifier_label=b"BulletProof", domain_label=b"AggregateBulletProof", transcript_state=None):
+        """RangeProof::verify_multiple (chain = 1, m values per proof) / a chain of verify_single calls on one transcript (m = 1),
+        batched over independent transcripts -> status per transcript.  transcript_state: the array transcript_capture()
+        filled during an earlier verification on the same transcripts (replaces the two labels)."""
+        cm, pr = _u8(commitments), _u8(proofs)
+        per = self.range_proof_bytes(m, n_bits) * chain
+        nproofs = pr.size // per
+        _u8(pr, nproofs * per), _u8(cm, nproofs * chain * m * 32)
+        ts = None
+        if transcript_state is not None:
+            ts = _u8(transcript_state, nproofs * self.lib.qq_transcript_state_bytes())
+        st = np.zeros(nproofs, np.uint8)
+        self._ck(self.lib.qq_verify_range_proof_batch(self.h, transcript_label, verifier_label, _ptr(ts) if ts is not None else None,
+                                                       domain_label, _ptr(cm), _ptr(pr), n_bits, m, chain, nproofs, _ptr(st)),
+                 "qq_verify_range_proof_batch")
+        return st
+
+    def transcript_capture(self, nproofs):
+        """Arms the one-shot capture: the next sigma verification call leaves its nproofs transcripts in the returned array."""
+        buf = np.zeros(nproofs * self.lib.qq_transcript_state_bytes(), np.uint8)
+        self._ck(self.lib.qq_transcript_capture(self.h, _ptr(buf)), "qq_transcript_capture")
+        return buf
 
     def decommit(self, comm, sk):
         comm, sk = _u8(comm), _u8(sk)

@@ -18,6 +18,7 @@
 #include "merlin_host.hpp"
 #include "sc_host.hpp"
 #include "decommit.cuh"
+#include "rangeproof.cuh"
 
 using namespace qq;
 
@@ -63,6 +64,9 @@ struct qq_ctx {
     int vb_blocks_per_sm[3] = {0, 0, 0};
     bool xpc_ready = false;                    // VectorPedersenGens::new(4): H, G_vec (compressed), derived on first use
     uint8_t xpc_h[32], xpc_g[96];
+    bool bp_ready = false;                     // BulletproofGens::new(64, 16) (compressed, party-major), derived on first use
+    std::vector<uint8_t> bp_g, bp_h;
+    uint8_t* transcript_capture = nullptr;     // qq_transcript_capture: where the next sigma verification leaves its transcripts
     bool stc_ready = false;                    // k_straus_coop's shared-memory opt-in done
     long vbc_max_jobs = -1;                    // four-lane cooperative variable base up to this many scalar mults (< 0: sms * 160)
 };
@@ -1279,3 +1283,4 @@ extern "C" int qq_fixed_base_i64_batch(qq_ctx* ctx, int which, const int64_t* v,
 #include "qq_api_msm.inc"
 #include "qq_api_sigma.inc"
 #include "qq_api_shuffle.inc"
+#include "qq_api_rangeproof.inc"

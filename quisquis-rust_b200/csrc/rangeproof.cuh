@@ -1,0 +1,72 @@
+// Bulletproofs range-proof batch verification: the generator scalars of the verification equation, folded over a batch
+// of proofs ON THE DEVICE.
+//
+// RangeProof::verify_multiple (bulletproofs crate; called by the reference at src/accounts/verifier.rs:517,548) ends in one
+// multiscalar multiplication whose 2 n m generator scalars are, for generator index i of proof p,
+//     g_i = -z - a s_i                        h_i = z + y^-i (z^2 z^(i / n) 2^(i mod n) - b s_(nm-1-i))
+// with s_i = (u_1 .. u_k)^-1 prod_{bit j of i set} u_(k-j)^2.  A batch of proofs shares the generators, so with one random
+// weight rho_p per proof the whole batch needs sum_p rho_p g_(p,i) and sum_p rho_p h_(p,i): nm x proofs small products in
+// Z/l -- data-parallel integer work that the host threads would spend 0.25 ms per proof on.  One thread per generator
+// index walks a chunk of the proofs (records are read as warp-wide broadcasts), partial sums per chunk are added by a
+// second kernel straight into the scalar array of the aggregated MSM.
+#pragma once
+#include "kernels.cuh"
+#include "sc_host.hpp"
+
+namespace qq {
+
+#define QQ_RP_MAX_LG 10      // n m <= 64 x 16 = 1024
+#define QQ_RP_MAX_PARTIES 16
+
+// one record per (sub-)proof, written by the host pass (all scalars canonical, already multiplied by the weight rho)
+struct rp_record {
+    qq_sc::sc neg_rz;                      // -rho z
+    qq_sc::sc rz;                          //  rho z
+    qq_sc::sc ra;                          //  rho a
+    qq_sc::sc rb;                          //  rho b
+    qq_sc::sc allinv;                      // (u_1 .. u_k)^-1
+    qq_sc::sc usq[QQ_RP_MAX_LG];           // u^2 in creation order (the crate's challenges_sq)
+    qq_sc::sc yinv_pow[QQ_RP_MAX_LG];      // y^-(2^j)
+    qq_sc::sc rzz_zj[QQ_RP_MAX_PARTIES];   // rho z^2 z^j
+};
+
+// grid = (ceil(N / block), chunks); partial: chunks x 2N scalars (g sums then h sums)
+__global__ void __launch_bounds__(128) k_rp_fold(const rp_record* __restrict__ rec, unsigned int first, unsigned int count,
+                                                 int n_bits, int N, int lg, qq_sc::sc* __restrict__ partial) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    unsigned int per = (count + gridDim.y - 1) / gridDim.y;
+    unsigned int p0 = blockIdx.y * per, p1 = p0 + per < count ? p0 + per : count;
+    qq_sc::sc sum_g = qq_sc::zero(), sum_h = qq_sc::zero();
+    const int irev = N - 1 - i;
+    qq_sc::sc two_pow = qq_sc::zero();
+    two_pow.v[0] = 1ull << (i % n_bits);
+    const int party = i / n_bits;
+    for (unsigned int p = p0; p < p1; p++) {
+        const rp_record& r = rec[first + p];
+        qq_sc::sc s_i = r.allinv, s_rev = r.allinv, y_i = qq_sc::one();
+        for (int j = 0; j < lg; j++) {
+            const qq_sc::sc u = r.usq[lg - 1 - j];
+            if ((i >> j) & 1) {
+                s_i = qq_sc::mul(s_i, u);
+                y_i = qq_sc::mul(y_i, r.yinv_pow[j]);
+            }
+            if ((irev >> j) & 1) s_rev = qq_sc::mul(s_rev, u);
+        }
+        sum_g = qq_sc::add(sum_g, qq_sc::sub(r.neg_rz, qq_sc::mul(r.ra, s_i)));
+        qq_sc::sc t = qq_sc::sub(qq_sc::mul(r.rzz_zj[party], two_pow), qq_sc::mul(r.rb, s_rev));
+        sum_h = qq_sc::add(sum_h, qq_sc::add(r.rz, qq_sc::mul(y_i, t)));
+    }
+    partial[(size_t)blockIdx.y * 2 * N + i] = sum_g;
+    partial[(size_t)blockIdx.y * 2 * N + N + i] = sum_h;
+}
+// out[t] = sum over chunks of partial[chunk][t], t < 2N, written as the 32-byte scalars of the MSM
+__global__ void k_rp_fold_sum(const qq_sc::sc* __restrict__ partial, int chunks, int twoN, qq_sc::sc* __restrict__ out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= twoN) return;
+    qq_sc::sc s = partial[t];
+    for (int c = 1; c < chunks; c++) s = qq_sc::add(s, partial[(size_t)c * twoN + t]);
+    out[t] = s;
+}
+
+}  // namespace qq

@@ -3,9 +3,18 @@
 // Bayer-Groth sub-arguments (reference src/shuffle/*.rs use curve25519_dalek::scalar::Scalar for the same).
 // Four 64-bit limbs, values always canonical (< l); multiplication = 4x4 schoolbook + Barrett reduction (HAC 14.42,
 // b = 2^64, k = 4, mu = floor(2^512 / l)).  No secrets are handled here (verifier side): not constant time.
+// Every function is also callable from device code (QQ_SC_FN): the range-proof fold kernel (rangeproof.cuh) runs the same
+// arithmetic on the GPU; the constants are function-local there (namespace-scope host arrays are not visible to kernels).
 #pragma once
 #include <cstdint>
 #include <cstring>
+#ifdef __CUDACC__
+#define QQ_SC_FN __host__ __device__ static inline
+#else
+#define QQ_SC_FN static inline
+#endif
+#define QQ_SC_L_WORDS {0x5812631a5cf5d3edULL, 0x14def9dea2f79cd6ULL, 0ULL, 0x1000000000000000ULL}
+#define QQ_SC_MU_WORDS {0xed9ce5a30a2c131bULL, 0x2106215d086329a7ULL, 0xffffffffffffffebULL, 0xffffffffffffffffULL, 0xfULL}
 
 namespace qq_sc {
 
@@ -17,29 +26,31 @@ struct sc {
     bool operator!=(const sc& o) const { return !(*this == o); }
 };
 
-static const uint64_t L[4] = {0x5812631a5cf5d3edULL, 0x14def9dea2f79cd6ULL, 0ULL, 0x1000000000000000ULL};
-static const uint64_t MU[5] = {0xed9ce5a30a2c131bULL, 0x2106215d086329a7ULL, 0xffffffffffffffebULL, 0xffffffffffffffffULL, 0xfULL};
+static const uint64_t L[4] = QQ_SC_L_WORDS;
+static const uint64_t MU[5] = QQ_SC_MU_WORDS;
 
-static inline sc zero() { return sc{{0, 0, 0, 0}}; }
-static inline sc one() { return sc{{1, 0, 0, 0}}; }
-static inline sc from_u64(uint64_t x) { return sc{{x, 0, 0, 0}}; }
-static inline bool is_zero(const sc& a) { return (a.v[0] | a.v[1] | a.v[2] | a.v[3]) == 0; }
+QQ_SC_FN sc zero() { return sc{{0, 0, 0, 0}}; }
+QQ_SC_FN sc one() { return sc{{1, 0, 0, 0}}; }
+QQ_SC_FN sc from_u64(uint64_t x) { return sc{{x, 0, 0, 0}}; }
+QQ_SC_FN bool is_zero(const sc& a) { return (a.v[0] | a.v[1] | a.v[2] | a.v[3]) == 0; }
 
 // a >= l ?
-static inline bool geq_l(const uint64_t a[4]) {
+QQ_SC_FN bool geq_l(const uint64_t a[4]) {
+    const uint64_t L[4] = QQ_SC_L_WORDS;
     for (int i = 3; i >= 0; i--) {
         if (a[i] != L[i]) return a[i] > L[i];
     }
     return true;
 }
 // canonical 32 little-endian bytes -> sc; false when the value is >= l
-static inline bool from_bytes(sc& out, const uint8_t b[32]) {
+QQ_SC_FN bool from_bytes(sc& out, const uint8_t b[32]) {
     memcpy(out.v, b, 32);
     return !geq_l(out.v);
 }
-static inline void to_bytes(uint8_t b[32], const sc& a) { memcpy(b, a.v, 32); }
+QQ_SC_FN void to_bytes(uint8_t b[32], const sc& a) { memcpy(b, a.v, 32); }
 
-static inline sc add(const sc& a, const sc& b) {
+QQ_SC_FN sc add(const sc& a, const sc& b) {
+    const uint64_t L[4] = QQ_SC_L_WORDS;
     sc r;
     u128 c = 0;
     for (int i = 0; i < 4; i++) {
@@ -57,7 +68,8 @@ static inline sc add(const sc& a, const sc& b) {
     }
     return r;
 }
-static inline sc neg(const sc& a) {
+QQ_SC_FN sc neg(const sc& a) {
+    const uint64_t L[4] = QQ_SC_L_WORDS;
     if (is_zero(a)) return a;
     sc r;
     u128 br = 0;
@@ -68,10 +80,12 @@ static inline sc neg(const sc& a) {
     }
     return r;
 }
-static inline sc sub(const sc& a, const sc& b) { return add(a, neg(b)); }
+QQ_SC_FN sc sub(const sc& a, const sc& b) { return add(a, neg(b)); }
 
 // x (8 limbs, < 2^512) mod l
-static inline sc reduce512(const uint64_t x[8]) {
+QQ_SC_FN sc reduce512(const uint64_t x[8]) {
+    const uint64_t L[4] = QQ_SC_L_WORDS;
+    const uint64_t MU[5] = QQ_SC_MU_WORDS;
     // q1 = floor(x / b^3): limbs 3..7 (5 limbs); q2 = q1 * mu (10 limbs); q3 = floor(q2 / b^5): limbs 5..9
     uint64_t q2[10] = {0};
     for (int i = 0; i < 5; i++) {
@@ -115,7 +129,7 @@ static inline sc reduce512(const uint64_t x[8]) {
     }
     return sc{{r[0], r[1], r[2], r[3]}};
 }
-static inline sc mul(const sc& a, const sc& b) {
+QQ_SC_FN sc mul(const sc& a, const sc& b) {
     uint64_t x[8] = {0};
     for (int i = 0; i < 4; i++) {
         u128 c = 0;
@@ -129,13 +143,14 @@ static inline sc mul(const sc& a, const sc& b) {
     return reduce512(x);
 }
 // Scalar::from_bytes_mod_order_wide
-static inline sc from_wide(const uint8_t b[64]) {
+QQ_SC_FN sc from_wide(const uint8_t b[64]) {
     uint64_t x[8];
     memcpy(x, b, 64);
     return reduce512(x);
 }
 // a^(l - 2)
-static inline sc invert(const sc& a) {
+QQ_SC_FN sc invert(const sc& a) {
+    const uint64_t L[4] = QQ_SC_L_WORDS;
     uint64_t e[4] = {L[0] - 2, L[1], L[2], L[3]};
     sc r = one();
     for (int bit = 252; bit >= 0; bit--) {

@@ -154,6 +154,44 @@ def scenario_sender_account(st):
     return senders, eps, R.BASE_PK, zv, zsk, zr, x
 
 
+def scenario_range_batch(st):
+    """verifier.rs verify_non_negative_sender_receiver_bulletproof_batch_verifier_test (:1525-1628): the sender-account proof
+    of the two senders and then, on the SAME transcript (b"SenderAccountProof" / b"BulletProof"), one aggregated range proof
+    over [5, 7, 5, 3] (senders' remaining balances, receivers' amounts).
+    -> (senders[2], eps_sender[2], base_pk, zv, zsk, zr, x, epsilon_accounts_bp[4], proof bytes)."""
+    import rangeproof_ref as RP
+    import sigma_ref as S
+    from merlin_ref import Transcript
+    vals = [R.L - 5, R.L - 3, 5, 3, 0, 0, 0, 0, 0]
+    pairs = [random_account_with_value(st, 10) for _ in range(9)]
+    accs, sks = [p[0] for p in pairs], [p[1] for p in pairs]
+    r_scalars = [st.scalar() for _ in range(9)]
+    de = [R.delta_epsilon(a, sb(v), sb(r)) for a, v, r in zip(accs, vals, r_scalars)]
+    delta, epsilon = [d[0] for d in de], [d[1] for d in de]
+    upd = S.update_delta_accounts(accs, delta)
+    senders, bl = upd[0:2], [5, 7]
+    tr = Transcript(b"SenderAccountProof")
+    tr.domain_sep(b"BulletProof")                      # Prover::new
+    rs_sender = [st.scalar(), st.scalar()]
+    eps, zv, zsk, zr, x = S.prove_account(senders, bl, sks[0:2], R.BASE_PK, rs_sender,
+                                          [(st.scalar(), st.scalar(), st.scalar()) for _ in range(2)], tr=tr)
+    proofs = RP.quisquis_range_prover(tr, [5, 7, 5, 3], [rs_sender[0], rs_sender[1], r_scalars[2], r_scalars[3]], st.scalar)
+    return senders, eps, R.BASE_PK, zv, zsk, zr, x, [eps[0], eps[1], epsilon[2], epsilon[3]], proofs[0]
+
+
+def scenario_range_vector(st, values=(5, 3, 0, 0, 0), label=b"Test_notPower"):
+    """prover.rs verify_non_negative_sender_receiver_prover_test (:965-992), the odd-sized case: one single-value proof per
+    balance on one transcript -> (epsilon accounts, [proof bytes])."""
+    import rangeproof_ref as RP
+    import sigma_ref as S
+    from merlin_ref import Transcript
+    tr = Transcript(label)
+    tr.domain_sep(b"Bulletproof")
+    rs = [st.scalar() for _ in values]
+    eps = [S.create_epsilon_account(R.BASE_PK, r, v) for r, v in zip(rs, values)]
+    return eps, RP.quisquis_range_prover(tr, list(values), rs, st.scalar)
+
+
 # ---- leaf arguments of the shuffle proof: the reference's own test scenarios (src/shuffle/{ddh,singlevalueproduct,
 # hadamard}.rs tests) with proofs from the oracle's prover restatements (oracle/shuffle_ref.py)
 def scenario_ddh(st):

@@ -1278,3 +1278,115 @@ def test_golden_shuffle_proofs_accepted(engine):
     pr2[1, 3776 - 1 - 32] ^= 1          # top byte of the DDH challenge: still canonical or not, never the right one
     st, sg, det = engine.verify_shuffle(si, so2, stm, pr2)
     assert st[0] != 0 and st[1] != 0 and not st[2:].any()
+
+
+def test_range_proof_verification(engine):
+    """Bulletproofs range proofs (qq_verify_range_proof_batch): the reference's batch-verifier scenario (verifier.rs:1525-1628,
+    sender-account proof then the aggregated proof on the same transcript), the vector form (one transcript, five chained
+    single-value proofs), other sizes, and a batch with failures spread through it (bisection of the aggregate).  Verdicts
+    equal the oracle's verifier restatement."""
+    import rangeproof_ref as RP
+    import sigma_ref as S
+    from merlin_ref import Transcript
+    from qq_testlib import scenario_range_batch, scenario_range_vector
+    from quisquis_rust_b200 import api
+    api.set_default_engine(engine)
+    st = Stream(b"range-gpu")
+    scen = [scenario_range_batch(st) for _ in range(3)]
+
+    def oracle_verdict(k, eps_bp, proof):
+        tr = Transcript(b"SenderAccountProof")
+        tr.domain_sep(b"BulletProof")
+        assert S.verify_account(*k[:7], tr=tr) is True
+        return RP.quisquis_range_batch_verifier(tr, eps_bp, proof)
+
+    cases = []      # (scenario, epsilon accounts, proof, expected status)
+    for k in scen:
+        cases.append((k, k[7], k[8], 0))
+    k = scen[0]
+    proof = k[8]
+    cases.append((k, [k[7][1], k[7][0]] + k[7][2:], proof, 6))                  # commitments exchanged
+    for off in (1, 33, 65, 97, 4 * 32 + 3, 5 * 32, 6 * 32 + 7, 7 * 32 + 1, 8 * 32 + 9, len(proof) - 64, len(proof) - 32):
+        bad = bytearray(proof)
+        bad[off] ^= 1
+        expect = 6
+        if off < 128 or 7 * 32 <= off < len(proof) - 64:
+            expect = 6 if R.decompress(bytes(bad[off // 32 * 32:off // 32 * 32 + 32])) is not None else 1
+        cases.append((k, k[7], bytes(bad), expect))
+    cases.append((k, k[7], proof[:128] + b"\xff" * 32 + proof[160:], 2))       # non-canonical t_x
+    cases.append((k, k[7], proof[:-32] + R.L.to_bytes(32, "little"), 2))        # b = l
+    cases.append((k, k[7], bytes(32) + proof[32:], 6))                          # A = identity
+    cases.append((k, k[7], proof[:7 * 32] + invalid_encodings()[1][1] + proof[8 * 32:], 1))     # L_0 does not decode
+    bad_v = bytearray(k[7][2])
+    bad_v[96:128] = invalid_encodings()[0][1]
+    cases.append((k, k[7][:2] + [bytes(bad_v)] + k[7][3:], proof, 1))           # a commitment does not decode
+    for kk, eps_bp, pr, expect in cases:
+        assert oracle_verdict(kk, eps_bp, pr) is (expect == 0)
+    # sender-account proofs first (their transcripts are kept), then the range proofs on those transcripts
+    n = len(cases)
+    states = engine.transcript_capture(n)
+    pack = lambda i: cat([cat([sb(v) for v in c[0][i]]) for c in cases])  # noqa: E731
+    got = engine.verify_account_sigma(cat([cat(c[0][0]) for c in cases]), cat([cat(c[0][1]) for c in cases]), R.BASE_PK, pack(3),
+                                      pack(4), pack(5), cat([sb(c[0][6]) for c in cases]), 2, b"SenderAccountProof", b"BulletProof")
+    assert not got.any()
+    cm = cat([b"".join(a[96:128] for a in c[1]) for c in cases])
+    pr = cat([c[2] for c in cases])
+    got = engine.verify_range_proofs(cm, pr, 4, transcript_state=states)
+    assert [int(s) for s in got] == [c[3] for c in cases]
+    # without the sender-account proof in the transcript nothing verifies
+    got = engine.verify_range_proofs(cm[:3 * 128], pr[:3 * len(proof)], 4, transcript_label=b"SenderAccountProof", verifier_label=b"BulletProof")
+    assert [int(s) for s in got] == [6, 6, 6]
+    # the mirror of the reference interface
+    A = lambda accs: [api.Account(a) for a in accs]  # noqa: E731
+    S_ = lambda v: [sb(s) for s in v]  # noqa: E731
+    tstate = api.Verifier.verify_account_verifier_bulletproof(A(k[0]), A(k[1]), api.RistrettoPublicKey(k[2]), S_(k[3]), S_(k[4]),
+                                                              S_(k[5]), sb(k[6]), verifier_label=b"BulletProof", keep_transcript=True)
+    assert api.Verifier.verify_non_negative_sender_receiver_bulletproof_batch_verifier(A(k[7]), proof, transcript=tstate) is None
+    with pytest.raises(ValueError, match="Bulletproof verification failed"):
+        api.Verifier.verify_non_negative_sender_receiver_bulletproof_batch_verifier(A(k[7]), proof)
+    with pytest.raises(ValueError, match="Bulletproof verification failed"):
+        api.Verifier.verify_non_negative_sender_receiver_bulletproof_batch_verifier(A(k[7][:3]), proof, transcript=tstate)
+
+    # vector form: five single-value proofs chained on one transcript
+    eps_v, proofs = scenario_range_vector(st)
+    eps_w, proofs_w = scenario_range_vector(st, values=(2**64 - 1, 0, 1, 77, 2**63))
+    vcases = [(eps_v, proofs, 0), (eps_w, proofs_w, 0), (eps_v, [proofs[1], proofs[0]] + proofs[2:], 6),
+              (eps_v, proofs[:4] + [proofs_w[4]], 6), (eps_w[:4] + [eps_v[4]], proofs_w, 6)]
+    for e_, p_, expect in vcases:
+        tr = Transcript(b"Test_notPower")
+        tr.domain_sep(b"Bulletproof")
+        assert RP.quisquis_range_vector_verifier(tr, e_, p_) is (expect == 0)
+    got = engine.verify_range_proofs(cat([b"".join(a[96:128] for a in c[0]) for c in vcases]), cat([b"".join(c[1]) for c in vcases]),
+                                     1, chain=5, transcript_label=b"Test_notPower", verifier_label=b"Bulletproof")
+    assert [int(s) for s in got] == [c[2] for c in vcases]
+    assert api.Verifier.verify_non_negative_sender_receiver_bulletproof_vector_verifier(
+        A(eps_v), proofs, transcript_label=b"Test_notPower", verifier_label=b"Bulletproof") is None
+    with pytest.raises(ValueError, match="Bulletproof verification failed"):
+        api.Verifier.verify_non_negative_sender_receiver_bulletproof_vector_verifier(
+            A(eps_v), proofs[::-1], transcript_label=b"Test_notPower", verifier_label=b"Bulletproof")
+
+    # other shapes: 16 aggregated values (the largest the reference's generators allow), and 8-bit ranges over 2 parties
+    for m, nb in ((16, 64), (2, 8), (1, 32)):
+        vals = [int.from_bytes(st.bytes(8), "little") % (1 << nb) for _ in range(m)]
+        bl = [st.scalar() for _ in range(m)]
+        good, V = RP.prove_multiple(Transcript(b"shapes"), vals, bl, nb, st.scalar, RP.BulletproofGens(64, 16))
+        assert len(good) == engine.range_proof_bytes(m, nb)
+        assert RP.verify_multiple(Transcript(b"shapes"), good, V, nb, bp_gens=RP.BulletproofGens(64, 16)) is True
+        # 37 transcripts, failures at the ends and in the middle: the aggregate is bisected down to them
+        nrep, bad_at = 37, {0: 6, 17: 6, 18: 1, 36: 6}
+        prs, cms = [], []
+        for i in range(nrep):
+            p_ = bytearray(good)
+            if bad_at.get(i) == 6:
+                p_[5 * 32 + (i % 31)] ^= 0x10 if i != 36 else 0
+                if i == 36:
+                    p_[-40] ^= 1        # a
+            elif bad_at.get(i) == 1:
+                p_[7 * 32:8 * 32] = invalid_encodings()[2][1]
+            prs.append(bytes(p_))
+            cms.append(b"".join(V))
+        got = engine.verify_range_proofs(cat(cms), cat(prs), m, n_bits=nb, transcript_label=b"shapes", verifier_label=None,
+                                         domain_label=None)
+        exp = [bad_at.get(i, 0) for i in range(nrep)]
+        # a flipped scalar bit may make the scalar non-canonical (status 2) - only the top byte can, and these flips avoid it
+        assert [int(s) for s in got] == exp, (m, nb)

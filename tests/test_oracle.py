@@ -354,3 +354,50 @@ def test_golden_shuffle_fixture_is_what_the_oracle_prover_makes():
     pr, stm = T._shuffle_blobs(proof, state)
     assert gold[:6432] == b"".join(inp) + b"".join(outp) + stm + pr
     assert F.shuffle_verify(F.new_transcript(b"ShuffleProof", b"Shuffle"), proof, state, inp, outp, F.XpcGens(4)) == (True, None)
+
+
+def test_range_proof_round_trip():
+    """Bulletproofs range proof restatement (oracle/rangeproof_ref.py): the reference's batch-verifier scenario (sender account
+    proof and aggregated range proof on one running transcript, verifier.rs:1525-1628) and the vector scenario
+    (prover.rs:965-992) verify; tampering, a wrong transcript and an out-of-range value do not."""
+    import rangeproof_ref as RP
+    import sigma_ref as S
+    from merlin_ref import Transcript
+    from qq_testlib import scenario_range_batch, scenario_range_vector
+    st = Stream(b"range-oracle")
+    senders, eps, base_pk, zv, zsk, zr, x, eps_bp, proof = scenario_range_batch(st)
+    assert len(proof) == (9 + 2 * 8) * 32
+
+    def verifier():
+        tr = Transcript(b"SenderAccountProof")
+        tr.domain_sep(b"BulletProof")
+        assert S.verify_account(senders, eps, base_pk, zv, zsk, zr, x, tr=tr) is True
+        return tr
+    assert RP.quisquis_range_batch_verifier(verifier(), eps_bp, proof) is True
+    assert RP.quisquis_range_batch_verifier(verifier(), eps_bp, proof, c=987654321) is True      # any weight c
+    fresh = Transcript(b"SenderAccountProof")
+    fresh.domain_sep(b"BulletProof")
+    assert RP.quisquis_range_batch_verifier(fresh, eps_bp, proof) is False                        # the sigma proof is part of the transcript
+    assert RP.quisquis_range_batch_verifier(verifier(), [eps_bp[1], eps_bp[0]] + eps_bp[2:], proof) is False
+    for off in (0, 40, 4 * 32 + 3, 7 * 32 + 1, len(proof) - 40):
+        bad = bytearray(proof)
+        bad[off] ^= 1
+        assert RP.quisquis_range_batch_verifier(verifier(), eps_bp, bytes(bad)) is False
+    assert RP.quisquis_range_batch_verifier(verifier(), eps_bp, proof[:128] + b"\xff" * 32 + proof[160:]) is False   # non-canonical t_x
+    assert RP.quisquis_range_batch_verifier(verifier(), eps_bp, bytes(32) + proof[32:]) is False                     # identity A
+    # vector form
+    eps_v, proofs = scenario_range_vector(st)
+    assert len(proofs) == 5 and all(len(p) == (9 + 12) * 32 for p in proofs)
+
+    def vt():
+        tr = Transcript(b"Test_notPower")
+        tr.domain_sep(b"Bulletproof")
+        return tr
+    assert RP.quisquis_range_vector_verifier(vt(), eps_v, proofs) is True
+    assert RP.quisquis_range_vector_verifier(vt(), eps_v, [proofs[1], proofs[0]] + proofs[2:]) is False
+    # a value outside [0, 2^n) has no valid proof: the honest prover's output is rejected
+    tr = Transcript(b"oob")
+    bad_proof, V = RP.prove_multiple(tr, [1 << 8], [st.scalar()], 8, st.scalar)
+    assert RP.verify_multiple(Transcript(b"oob"), bad_proof, V, 8) is False
+    ok_proof, V = RP.prove_multiple(Transcript(b"oob"), [255], [st.scalar()], 8, st.scalar)
+    assert RP.verify_multiple(Transcript(b"oob"), ok_proof, V, 8) is True
