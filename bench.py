@@ -396,6 +396,69 @@ def run_b200(args):
             msm["sharded"] = {"points_total": m * world, "ms": sh_ms, "matches_known_dlog": bool((exp_s[0] == out_s).all()),
                               "exchange": "all_gather of 128-byte partial sums + status over NCCL, then %d point additions" % (world - 1)}
 
+    # ---- configs[2]: 4096 shuffle proofs, sharded over the ranks (independent proofs, no collective) ----------------
+    # ---- configs[3]: Bulletproofs 64-bit range proofs, 16 aggregated values each: ONE aggregated MSM per batch -----------
+    # Workload = the committed valid proofs of tests/golden (made by the oracle's prover restatements), tiled.  Host buffers
+    # in, verdicts out, through the public C ABI (host Merlin transcripts + GPU batches inside the timed region).
+    proofs_sec = None
+    if args.proofs > 0:
+        gold = os.path.join(ROOT, "tests", "golden")
+        per_rank = max(1, args.proofs // world)
+
+        def tiled(path, rec_bytes, count):
+            raw = np.fromfile(path, dtype=np.uint8).reshape(-1, rec_bytes)
+            return np.tile(raw, ((count + raw.shape[0] - 1) // raw.shape[0], 1))[:count]
+
+        def best_of(fn, reps=3):
+            fn()
+            barrier()
+            best = 1e30
+            for _ in range(reps):
+                t_ = time.time()
+                fn()
+                best = min(best, (time.time() - t_) * 1e3)
+            barrier()
+            return best
+        rec = tiled(os.path.join(gold, "shuffle_proofs.bin"), 6432, per_rank)
+        si, so, stm, prf = (np.ascontiguousarray(rec[:, a:b]) for a, b in ((0, 1152), (1152, 2304), (2304, 2656), (2656, 6432)))
+        res = {}
+
+        def run_shuffle():
+            res["st"] = eng.verify_shuffle(si, so, stm, prf)[0]
+        sh_ms = best_of(run_shuffle)
+        sh_ok = not res["st"].any()
+        prf_bad = prf.copy()
+        prf_bad[per_rank // 2, 3776 - 1] ^= 0x01            # top byte of the DDH response: wrong, perhaps not even canonical
+        sh_rej = eng.verify_shuffle(si, so, stm, prf_bad)[0]
+        proofs_sec = {"shuffle": {"proofs_per_gpu": per_rank, "ms": sh_ms, "all_accepted": bool(sh_ok),
+                                  "tampered_proof_rejected_alone": bool(sh_rej[per_rank // 2] != 0 and int(sh_rej.astype(bool).sum()) == 1),
+                                  "msms_per_proof": 28, "terms_per_proof": 239,
+                                  "api": "qq_verify_shuffle_batch (ShuffleProof::verify, 9 accounts, two GPU round trips)"}}
+        m_rp = 16
+        rp_rec = m_rp * 32 + eng.range_proof_bytes(m_rp)
+        rp_list = []
+        for count in sorted(set([max(1, 512 // world), per_rank])):
+            rr = tiled(os.path.join(gold, "range_proofs_m%d.bin" % m_rp), rp_rec, count)
+            cm, rpf = np.ascontiguousarray(rr[:, :m_rp * 32]), np.ascontiguousarray(rr[:, m_rp * 32:])
+
+            def run_range():
+                res["st"] = eng.verify_range_proofs(cm, rpf, m_rp)
+            rp_ms = best_of(run_range)
+            ok_ = not res["st"].any()
+            rej = None
+            if count >= 3:
+                rpf_bad = rpf.copy()
+                rpf_bad[count // 2, 5 * 32 + 1] ^= 1
+                r_ = eng.verify_range_proofs(cm, rpf_bad, m_rp)
+                rej = bool(r_[count // 2] == 6 and int(r_.astype(bool).sum()) == 1)
+            rp_list.append({"proofs_per_gpu": count, "values_per_proof": m_rp, "bits": 64, "ms": rp_ms, "all_accepted": bool(ok_),
+                            "tampered_proof_rejected_alone": rej,
+                            "aggregated_msm_terms": 2 * 64 * m_rp + 2 + count * (4 + 20 + m_rp),
+                            "reference_msm_points": count * (2 * 64 * m_rp + 20 + m_rp + 6)})
+        proofs_sec["range_proofs"] = {"batches": rp_list,
+                                      "api": "qq_verify_range_proof_batch (RangeProof::verify_multiple; the reference verifies "
+                                             "each proof with its own 2090-term MSM, verifier.rs:517)"}
+
     # ---- reduce over ranks ----------------------------------------------------------------------------------------
     def maxr(x):
         if world == 1:
@@ -406,6 +469,16 @@ def run_b200(args):
 
     dev_ms_max, wall_ms_max, e2e_ms_max = maxr(dev_ms), maxr(wall_ms), maxr(e2e_ms)
     msm_ms_max = maxr(msm["ms"]) if msm else None
+    if proofs_sec:
+        sh = proofs_sec["shuffle"]
+        sh["ms"] = maxr(sh["ms"])
+        sh["proofs_total"] = sh["proofs_per_gpu"] * world
+        sh["proofs_per_sec"] = sh["proofs_total"] / (sh["ms"] * 1e-3)
+        for b_ in proofs_sec["range_proofs"]["batches"]:
+            b_["ms"] = maxr(b_["ms"])
+            b_["proofs_per_sec"] = b_["proofs_per_gpu"] * world / (b_["ms"] * 1e-3)
+            b_["values_per_sec"] = b_["proofs_per_sec"] * b_["values_per_proof"]
+            b_["reference_msm_points_per_sec"] = b_["reference_msm_points"] * world / (b_["ms"] * 1e-3)
     if msm and "sharded" in msm:
         msm["sharded"]["ms"] = maxr(msm["sharded"]["ms"])
         msm["sharded"]["points_per_sec"] = msm["sharded"]["points_total"] / (msm["sharded"]["ms"] * 1e-3)
@@ -434,6 +507,25 @@ def run_b200(args):
                          "curve25519-dalek 3.2.1's algorithms (radix-2^51 field, radix-16 variable-base, table "
                          "fixed-base); dalek itself cannot be built here" % (ms_, cores),
                "gpu_output_matches_cpu_on_sample": same_cpu}
+        if proofs_sec:
+            # one aggregated range proof (16 values) through the oracle's verifier restatement: Merlin in Python, the 2090-term
+            # MSM in the C port with all host threads -- what the reference does per proof
+            import rangeproof_ref as RP
+            from merlin_ref import Transcript as OT
+            rr = np.fromfile(os.path.join(ROOT, "tests", "golden", "range_proofs_m16.bin"), dtype=np.uint8).reshape(-1, 16 * 32 + 928)
+            gens16 = RP.BulletproofGens(64, 16)
+            lat = []
+            for i in range(min(3, rr.shape[0])):
+                b_ = rr[i].tobytes()
+                tr_ = OT(b"SenderAccountProof")
+                tr_.domain_sep(b"BulletProof")
+                tr_.domain_sep(b"AggregateBulletProof")
+                t = time.time()
+                okp = RP.verify_multiple(tr_, b_[512:], [b_[32 * j:32 * j + 32] for j in range(16)], 64, bp_gens=gens16)
+                lat.append((time.time() - t) * 1e3)
+                assert okp
+            proofs_sec["range_proofs"]["cpu_port_ms_per_proof"] = sorted(lat)[len(lat) // 2]
+            proofs_sec["range_proofs"]["cpu_port_note"] = "oracle/rangeproof_ref.py verify_multiple, MSM in oracle/qq_oracle.c on %d host threads" % cores
         if anon9 is not None:
             # configs[0] as the reference runs it: the same 9 accounts on ONE host core (update_account + verify_account)
             C.set_threads(1)
@@ -501,6 +593,8 @@ def run_b200(args):
             for w_ in fixed["windows"] + [fixed["i64_values"]]:
                 w_["mults_per_sec"] = w_["mults_per_sec_per_gpu"] * world
             line["fixed_base"] = fixed
+        if proofs_sec:
+            line["proof_verification"] = proofs_sec
         if msm:
             msm["points_per_sec"] = msm["points"] * world / (msm_ms_max * 1e-3)
             msm["note"] = "each GPU runs a full %d-point MSM (weak scaling); compressed input, decompression included" % msm["points"]
@@ -522,6 +616,7 @@ def main():
     ap.add_argument("--fixed-points", type=int, default=1 << 22, help="fixed-base batch per GPU (0 = skip)")
     ap.add_argument("--fixed-window", type=int, default=22,
                     help="also time the fixed-base batch with this table window (22 bits = 2.4 GB in HBM; 0 = default table only)")
+    ap.add_argument("--proofs", type=int, default=4096, help="shuffle / range proofs verified in total over the ranks (0 = skip)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-seconds-per-step", type=float, default=4.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

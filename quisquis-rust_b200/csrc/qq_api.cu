@@ -2,6 +2,7 @@
 // Owns the device workspace, the fixed-base tables and the stream; sequences the kernels of kernels.cuh / msm.cuh.
 // No CPU fallback: every entry point fails with QQ_ERR_NODEVICE / QQ_ERR_CUDA when the GPU path is unavailable.
 #include <cuda_runtime.h>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
