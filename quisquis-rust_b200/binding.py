@@ -26,7 +26,7 @@ EXPORTS = [
     "qq_verify_account_sigma_batch", "qq_verify_zero_balance_batch", "qq_verify_destroy_account_batch",
     "qq_verify_same_value_compact_batch", "qq_verify_update_account_dark_tx_batch",
     "qq_verify_update_account_dlog_batch", "qq_verify_delta_compact_batch", "qq_decommit_batch", "qq_decommit_value_batch", "qq_from_uniform_bytes_batch", "qq_vector_pedersen_gens", "qq_bulletproof_gens",
-    "qq_verify_range_proof_batch", "qq_transcript_state_bytes", "qq_transcript_capture",
+    "qq_verify_range_proof_batch", "qq_transcript_state_bytes", "qq_transcript_capture", "qq_msm_set_overlap",
 ]
 
 
@@ -115,6 +115,7 @@ def load_library():
     lib.qq_transcript_state_bytes.argtypes = []
     lib.qq_transcript_state_bytes.restype = ctypes.c_size_t
     lib.qq_transcript_capture.argtypes = [vp, u8p]
+    lib.qq_msm_set_overlap.argtypes = [vp, ctypes.c_long, ctypes.c_int, ctypes.c_int]
     lib.qq_msm_points_free.argtypes = [vp, vp]
     lib.qq_msm_points_free.restype = None
     lib.qq_msm_points_count.argtypes = [vp]
@@ -490,6 +491,10 @@ class Engine:
         self._ck(self.lib.qq_verify_shuffle_batch(self.h, transcript_label, verifier_label, _ptr(si), _ptr(so), _ptr(stm), _ptr(pr),
                                                    nproofs, _ptr(st), _ptr(sg), _ptr(det)), "qq_verify_shuffle_batch")
         return st, sg, det
+
+    def msm_set_overlap(self, split_min=1 << 17, tail_pct=30, sort_blocks_per_sm=3):
+        """Large-MSM tuning (decompression of the last tail_pct % of the points under the counting sort); tail_pct 0 = off."""
+        self._ck(self.lib.qq_msm_set_overlap(self.h, split_min, tail_pct, sort_blocks_per_sm), "qq_msm_set_overlap")
 
     def range_proof_bytes(self, m, n_bits=64):
         """Length of RangeProof::to_bytes() for m aggregated n_bits-bit values."""

@@ -81,7 +81,7 @@ struct msm_geom {
 //              only the scalars are recoded.  `pre_ok[i]` is the validity recorded then.
 template <bool PRE>
 __global__ void __launch_bounds__(256, 2) k_msm_prepare(const u32x4* __restrict__ points, const u32x4* __restrict__ scalars,
-                                                     size_t n, msm_geom g, u32x4* __restrict__ niels,
+                                                     size_t n, size_t n_dec, msm_geom g, u32x4* __restrict__ niels,
                                                      const uint8_t* __restrict__ pre_ok,
                                                      uint8_t* __restrict__ term_status, int16_t* __restrict__ digits,
                                                      unsigned int* __restrict__ slots, unsigned int* __restrict__ counts) {
@@ -118,6 +118,8 @@ __global__ void __launch_bounds__(256, 2) k_msm_prepare(const u32x4* __restrict_
         u32 ok;
         if (PRE) {
             ok = pre_ok[i];
+        } else if (i >= n_dec) {
+            ok = 1;       // decompressed by k_msm_decompress, which also downgrades the status
         } else {
             u32 w[8];
             load_words32(w, points, i);
@@ -133,6 +135,24 @@ __global__ void __launch_bounds__(256, 2) k_msm_prepare(const u32x4* __restrict_
             for (int k = 0; k < 16; k++)
                 if (k < g.K) slots[(size_t)k * n + i] = slot[k];
         }
+    }
+}
+// The point side alone (decompression to affine Niels) for the terms k_msm_prepare left out (n_dec <= i < n): it runs while
+// the counting sort of the digits proceeds on a second, high-priority stream -- the sort is latency / atomics / DRAM
+// bound, the decompression multiply bound.  (Splitting ALL the decompression off was measured slower: the histogram
+// atomics of a scalar-only kernel are no longer hidden behind the square-root chain.)
+__global__ void __launch_bounds__(256, 2) k_msm_decompress(const u32x4* __restrict__ points, size_t n, u32x4* __restrict__ niels,
+                                                           uint8_t* __restrict__ term_status) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        u32 w[8];
+        load_words32(w, points, i);
+        ge_p3 p;
+        u32 ok = ristretto_decompress(p, w);
+        ge_niels nl;
+        ge_to_niels_z1(nl, p);
+        niels_store_padded(niels + (size_t)QQ_NIELS_STRIDE_Q * i, nl);
+        if (!ok && term_status[i] == 0) term_status[i] = 1;
     }
 }
 // compressed points -> the MSM's point form (affine Niels, 96 B) + validity, once, for reuse

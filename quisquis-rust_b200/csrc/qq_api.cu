@@ -39,6 +39,10 @@ struct qq_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // upload / download streams of the pipelined host entry points
     cudaEvent_t msm_ev[8] = {nullptr};
+    cudaStream_t msm_hi = nullptr;           // high-priority stream: the MSM's counting sort, concurrent with the decompression
+    long msm_split_min = 1 << 17;            // QQ_MSM_SPLIT_MIN / QQ_MSM_TAIL_PCT in the environment override
+    int msm_sort_bpsm = 3;                   // blocks per SM of the sort kernels while they run under the decompression
+    int msm_tail_pct = 30;                   // share of the points decompressed under the counting sort
     std::vector<cudaEvent_t> pipe_ev;
     char* ws = nullptr;
     size_t ws_cap = 0, ws_off = 0;
@@ -486,6 +490,14 @@ extern "C" int qq_init(qq_ctx** out, int device) {
         CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+        {
+            int lo_pr = 0, hi_pr = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&lo_pr, &hi_pr));
+            CK(cudaStreamCreateWithPriority(&ctx->msm_hi, cudaStreamNonBlocking, hi_pr));
+            if (const char* e = getenv("QQ_MSM_SPLIT_MIN")) ctx->msm_split_min = atol(e);
+            if (const char* e = getenv("QQ_MSM_TAIL_PCT")) ctx->msm_tail_pct = atoi(e);
+            if (const char* e = getenv("QQ_MSM_SORT_BPSM")) ctx->msm_sort_bpsm = atoi(e);
+        }
         for (int i = 0; i < 8; i++) CK(cudaEventCreateWithFlags(&ctx->msm_ev[i], cudaEventDisableTiming));
         CK(cudaFuncSetAttribute(k_msm_sum_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * QQ_PT_BYTES));
         CK(cudaFuncSetAttribute(k_fixedbase<QQ_FB_W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -566,6 +578,7 @@ extern "C" void qq_destroy(qq_ctx* ctx) {
     for (int i = 0; i < 8; i++)
         if (ctx->msm_ev[i]) cudaEventDestroy(ctx->msm_ev[i]);
     for (auto e : ctx->pipe_ev) cudaEventDestroy(e);
+    if (ctx->msm_hi) cudaStreamDestroy(ctx->msm_hi);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

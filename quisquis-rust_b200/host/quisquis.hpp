@@ -6,6 +6,7 @@
 // plus the *_batch forms the Rust shim adds.  The reference is Rust; Rust is not available in this
 // image, so this is the compiled host language closest to it.  Link with -lqq_b200.  No CPU fallback.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <cstring>
@@ -388,6 +389,58 @@ struct Verifier {
                                               pack(zsk).data(), pack(zr).data(), x.data(), zv.size(), 1, &st),
                 "verify_account_verifier_bulletproof");
         verdict(st, "Account Verify: Failed", "sender account verification failed");
+    }
+    // The reference keeps ONE running transcript per Verifier: verify_account_verifier_bulletproof and the range proof that
+    // follows share it (verifier.rs:1603-1628).  keep_transcript() before the sigma verification, then pass the state on.
+    using TranscriptState = std::vector<uint8_t>;
+    static TranscriptState keep_transcript() {
+        TranscriptState s(qq_transcript_state_bytes());
+        Gpu& g = Gpu::instance();
+        g.check(qq_transcript_capture(g.ctx(), s.data()), "keep_transcript");
+        return s;
+    }
+    // verifier.rs:504-523: one aggregated 64-bit range proof (RangeProof::to_bytes()) over the d components of the accounts
+    static void verify_non_negative_sender_receiver_bulletproof_batch_verifier(const std::vector<Account>& epsilon_account,
+                                                                               const std::vector<uint8_t>& proof,
+                                                                               const TranscriptState* transcript = nullptr,
+                                                                               const char* transcript_label = "SenderAccountProof",
+                                                                               const char* verifier_label = "BulletProof") {
+        size_t m = epsilon_account.size(), lg = 0;
+        while (((size_t)1 << lg) < 64 * m) lg++;
+        if (m == 0 || m > 16 || (m & (m - 1)) || proof.size() != (9 + 2 * lg) * 32) throw Err("Bulletproof verification failed");
+        std::vector<uint8_t> cm;
+        for (const Account& a : epsilon_account) {
+            auto b = a.to_bytes();
+            cm.insert(cm.end(), b.begin() + 96, b.begin() + 128);
+        }
+        uint8_t st;
+        Gpu& g = Gpu::instance();
+        g.check(qq_verify_range_proof_batch(g.ctx(), transcript_label, verifier_label, transcript ? transcript->data() : nullptr,
+                                            "AggregateBulletProof", cm.data(), proof.data(), 64, m, 1, 1, &st),
+                "verify_non_negative_sender_receiver_bulletproof_batch_verifier");
+        if (st) throw Err("Bulletproof verification failed");
+    }
+    // verifier.rs:534-555: one single-value proof per account, chained on one transcript
+    static void verify_non_negative_sender_receiver_bulletproof_vector_verifier(const std::vector<Account>& epsilon_account,
+                                                                                const std::vector<std::vector<uint8_t>>& proof_vector,
+                                                                                const TranscriptState* transcript = nullptr,
+                                                                                const char* transcript_label = "SenderAccountProof",
+                                                                                const char* verifier_label = "BulletProof") {
+        size_t k = std::min(epsilon_account.size(), proof_vector.size());      // zip() stops at the shorter one
+        if (k == 0) return;
+        std::vector<uint8_t> cm, pr;
+        for (size_t i = 0; i < k; i++) {
+            if (proof_vector[i].size() != (9 + 12) * 32) throw Err("Bulletproof verification failed");
+            auto b = epsilon_account[i].to_bytes();
+            cm.insert(cm.end(), b.begin() + 96, b.begin() + 128);
+            pr.insert(pr.end(), proof_vector[i].begin(), proof_vector[i].end());
+        }
+        uint8_t st;
+        Gpu& g = Gpu::instance();
+        g.check(qq_verify_range_proof_batch(g.ctx(), transcript_label, verifier_label, transcript ? transcript->data() : nullptr,
+                                            "AggregateBulletProof", cm.data(), pr.data(), 64, 1, k, 1, &st),
+                "verify_non_negative_sender_receiver_bulletproof_vector_verifier");
+        if (st) throw Err("Bulletproof verification failed");
     }
     // verifier.rs:593-634 (domain separator as the reference's verifier spells it)
     static void zero_balance_account_vector_verifier(const std::vector<Account>& anonymity_accounts, const std::vector<Scalar>& z,

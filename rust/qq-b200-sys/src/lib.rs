@@ -43,6 +43,21 @@ extern "C" {
     pub fn qq_vector_pedersen_gens(ctx: *mut QqCtx, capacity: usize, out_h: *mut u8, out_g: *mut u8) -> c_int;
     pub fn qq_bulletproof_gens(ctx: *mut QqCtx, gens_capacity: usize, party_capacity: usize, out_g: *mut u8, out_h: *mut u8) -> c_int;
     pub fn qq_points_sum(ctx: *mut QqCtx, xyzt: *const u8, k: usize, out: *mut u8, is_identity: *mut u8) -> c_int;
+    // batched verifiers (host Merlin transcripts + GPU MSM batches); layouts in include/qq_b200.h
+    pub fn qq_verify_account_sigma_batch(ctx: *mut QqCtx, transcript_label: *const c_char, verifier_label: *const c_char, delta_accounts: *const u8, epsilon_accounts: *const u8, base_pk: *const u8, zv: *const u8, zsk: *const u8, zr: *const u8, x: *const u8, n: usize, nproofs: usize, status: *mut u8) -> c_int;
+    pub fn qq_verify_zero_balance_batch(ctx: *mut QqCtx, transcript_label: *const c_char, verifier_label: *const c_char, accounts: *const u8, z: *const u8, x: *const u8, n: usize, nproofs: usize, vector_form: c_int, status: *mut u8) -> c_int;
+    pub fn qq_verify_destroy_account_batch(ctx: *mut QqCtx, transcript_label: *const c_char, verifier_label: *const c_char, accounts: *const u8, z: *const u8, x: *const u8, n: usize, nproofs: usize, status: *mut u8) -> c_int;
+    pub fn qq_verify_same_value_compact_batch(ctx: *mut QqCtx, enc_accounts: *const u8, commitments: *const u8, zv: *const u8, zr: *const u8, x: *const u8, nproofs: usize, status: *mut u8) -> c_int;
+    pub fn qq_verify_update_account_dark_tx_batch(ctx: *mut QqCtx, transcript_label: *const c_char, verifier_label: *const c_char, delta_accounts: *const u8, output_accounts: *const u8, z: *const u8, x: *const u8, n: usize, nproofs: usize, status: *mut u8) -> c_int;
+    pub fn qq_verify_ddh_batch(ctx: *mut QqCtx, transcript_label: *const c_char, verifier_label: *const c_char, g: *const u8, h: *const u8, g_dash: *const u8, h_dash: *const u8, challenge: *const u8, z: *const u8, nproofs: usize, status: *mut u8) -> c_int;
+    pub fn qq_verify_svp_batch(ctx: *mut QqCtx, transcript_label: *const c_char, verifier_label: *const c_char, commitment_a: *const u8, b: *const u8, proof: *const u8, nproofs: usize, status: *mut u8) -> c_int;
+    pub fn qq_verify_hadamard_batch(ctx: *mut QqCtx, transcript_label: *const c_char, verifier_label: *const c_char, omega: *const u8, commit_a: *const u8, commit_b: *const u8, commit_c: *const u8, proof: *const u8, nproofs: usize, status: *mut u8, detail: *mut u8) -> c_int;
+    pub fn qq_verify_product_batch(ctx: *mut QqCtx, transcript_label: *const c_char, verifier_label: *const c_char, c_prod_a: *const u8, statement: *const u8, proof: *const u8, nproofs: usize, status: *mut u8, detail: *mut u8) -> c_int;
+    pub fn qq_verify_shuffle_batch(ctx: *mut QqCtx, transcript_label: *const c_char, verifier_label: *const c_char, shuffle_input: *const u8, shuffle_output: *const u8, statement: *const u8, proof: *const u8, nproofs: usize, status: *mut u8, stage: *mut u8, detail: *mut u8) -> c_int;
+    pub fn qq_verify_range_proof_batch(ctx: *mut QqCtx, transcript_label: *const c_char, verifier_label: *const c_char, transcript_state: *const u8, domain_label: *const c_char, commitments: *const u8, proofs: *const u8, n_bits: usize, m: usize, chain: usize, nproofs: usize, status: *mut u8) -> c_int;
+    pub fn qq_transcript_state_bytes() -> usize;
+    pub fn qq_msm_set_overlap(ctx: *mut QqCtx, split_min: std::os::raw::c_long, tail_pct: c_int, sort_blocks_per_sm: c_int) -> c_int;
+    pub fn qq_transcript_capture(ctx: *mut QqCtx, states_out: *mut u8) -> c_int;
     pub fn qq_msm_segmented(ctx: *mut QqCtx, scalars: *const u8, points: *const u8, offsets: *const u32, m: usize, out: *mut u8, status: *mut u8) -> c_int;
 }
 

@@ -130,6 +130,33 @@ int main(int argc, char** argv) {
         try { Verifier::verify_update_account_dark_tx_verifier(td, {to[0], badc, to[2], to[3]}, tz, tx); } catch (const Panic&) { threw = true; }
         CHECK(threw);
     }
+    // range proof on the running transcript of the sender-account proof (reference scenario verifier.rs:1525-1628; third fixture):
+    //   senders 2 x 128 | epsilon 2 x 128 | base_pk 64 | zv, zsk, zr 2 x 32 each | x 32 | epsilon_bp 4 x 128 | proof 800
+    if (argc >= 4) {
+        auto rg = read_all(argv[3]);
+        CHECK(rg.size() == 512 + 64 + 192 + 32 + 512 + 800);
+        const uint8_t* q = rg.data();
+        std::vector<Account> snd = {Account::from_raw(q), Account::from_raw(q + 128)};
+        std::vector<Account> eps = {Account::from_raw(q + 256), Account::from_raw(q + 384)};
+        RistrettoPublicKey bpk = RistrettoPublicKey::from_bytes(q + 512);
+        q += 576;
+        std::vector<Scalar> zv = {arr<32>(q), arr<32>(q + 32)}, zsk = {arr<32>(q + 64), arr<32>(q + 96)}, zr = {arr<32>(q + 128), arr<32>(q + 160)};
+        Scalar x = arr<32>(q + 192);
+        q += 224;
+        std::vector<Account> eps_bp;
+        for (int i = 0; i < 4; i++) eps_bp.push_back(Account::from_raw(q + 128 * i));
+        std::vector<uint8_t> proof(q + 512, q + 512 + 800);
+        auto state = Verifier::keep_transcript();
+        Verifier::verify_account_verifier_bulletproof(snd, eps, bpk, zv, zsk, zr, x, "SenderAccountProof", "BulletProof");
+        Verifier::verify_non_negative_sender_receiver_bulletproof_batch_verifier(eps_bp, proof, &state);        // Ok(())
+        std::string msg;
+        try { Verifier::verify_non_negative_sender_receiver_bulletproof_batch_verifier(eps_bp, proof); } catch (const Err& e) { msg = e.what(); }
+        CHECK(msg == "Bulletproof verification failed");          // the sigma proof is part of the transcript
+        msg.clear();
+        proof[5 * 32] ^= 1;
+        try { Verifier::verify_non_negative_sender_receiver_bulletproof_batch_verifier(eps_bp, proof, &state); } catch (const Err& e) { msg = e.what(); }
+        CHECK(msg == "Bulletproof verification failed");
+    }
     std::printf("HOST_API_TEST OK\n");
     return 0;
 }

@@ -32,9 +32,15 @@ def test_cpp_host_mirror(tmp_path, pkg):
     sg += b"".join(d) + b"".join(o) + sb(z[0]) + sb(z[1]) + sb(x)
     fs = tmp_path / "sigma.bin"
     fs.write_bytes(sg)
+    # third fixture: sender-account proof + aggregated range proof on one transcript (verifier.rs:1525-1628)
+    from qq_testlib import scenario_range_batch
+    k = scenario_range_batch(st)
+    rg = b"".join(k[0]) + b"".join(k[1]) + k[2] + b"".join(sb(v) for v in k[3] + k[4] + k[5]) + sb(k[6]) + b"".join(k[7]) + k[8]
+    fr = tmp_path / "range.bin"
+    fr.write_bytes(rg)
     exe = tmp_path / "host_api_test"
     libdir = os.path.join(ROOT, "quisquis-rust_b200")
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", str(exe), os.path.join(ROOT, "tests", "csrc", "host_api_test.cpp"),
                            "-L" + libdir, "-lqq_b200", "-Wl,-rpath," + libdir])
-    out = subprocess.run([str(exe), str(fx), str(fs)], capture_output=True, text=True, timeout=300)
+    out = subprocess.run([str(exe), str(fx), str(fs), str(fr)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "HOST_API_TEST OK" in out.stdout, out.stdout + out.stderr

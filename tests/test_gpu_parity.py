@@ -329,6 +329,43 @@ def test_msm_pippenger_vs_c_oracle(engine, n):
     assert s == es == 1 and o.tobytes() == bytes(32)
 
 
+def test_msm_overlapped_tail_decompression(engine):
+    """The large-MSM path that decompresses the last 30 % of the points under the counting sort (second stream) gives the same
+    point and the same first-failure status as the single-stream path and as the C oracle; bad terms in head and tail."""
+    import c_oracle as C
+    rng = np.random.default_rng(417)
+    n = (1 << 17) + 77
+    pts, _ = engine.fixed_base(0, _rand_scalars(rng, n))
+    sc = _rand_scalars(rng, n)
+    sc[::5, 8:] = 0
+    eo, es = C.msm(sc, pts)
+    assert es == 0
+    bad_pt = np.frombuffer(invalid_encodings()[0][1], np.uint8)
+    bad_sc = np.frombuffer(R.L.to_bytes(32, "little"), np.uint8)
+    try:
+        for tail in (30, 0, 55):
+            engine.msm_set_overlap(1 << 16, tail, 3)
+            o, s = engine.msm(sc, pts)
+            assert s == 0 and o.tobytes() == eo.tobytes(), tail
+            for where, what, expect in ((n - 5, "pt", 1), (100, "pt", 1), (n - 9, "sc", 2), (7, "sc", 2)):
+                p2, s2 = pts.copy(), sc.copy()
+                if what == "pt":
+                    p2[where] = bad_pt
+                else:
+                    s2[where] = bad_sc
+                o, s = engine.msm(s2, p2)
+                assert s == expect and o.tobytes() == bytes(32), (tail, where, what)
+            # the earliest bad term decides: scalar at 50 before point at n - 5
+            p2, s2 = pts.copy(), sc.copy()
+            p2[n - 5] = bad_pt
+            s2[50] = bad_sc
+            assert engine.msm(s2, p2)[1] == 2
+            p2[20] = bad_pt
+            assert engine.msm(s2, p2)[1] == 1
+    finally:
+        engine.msm_set_overlap()
+
+
 def test_msm_all_points_in_one_bucket(engine):
     """Adversarial distribution for the bucket kernel: identical scalars."""
     import c_oracle as C
