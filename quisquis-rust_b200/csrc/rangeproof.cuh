@@ -37,28 +37,25 @@ __global__ void __launch_bounds__(128) k_rp_fold(const rp_record* __restrict__ r
     if (i >= N) return;
     unsigned int per = (count + gridDim.y - 1) / gridDim.y;
     unsigned int p0 = blockIdx.y * per, p1 = p0 + per < count ? p0 + per : count;
+    // thread i owns g_i and h_j with j = nm - 1 - i: both need the same s_i
     qq_sc::sc sum_g = qq_sc::zero(), sum_h = qq_sc::zero();
-    const int irev = N - 1 - i;
+    const int j = N - 1 - i;
     qq_sc::sc two_pow = qq_sc::zero();
-    two_pow.v[0] = 1ull << (i % n_bits);
-    const int party = i / n_bits;
+    two_pow.v[0] = 1ull << (j % n_bits);
+    const int party = j / n_bits;
     for (unsigned int p = p0; p < p1; p++) {
         const rp_record& r = rec[first + p];
-        qq_sc::sc s_i = r.allinv, s_rev = r.allinv, y_i = qq_sc::one();
-        for (int j = 0; j < lg; j++) {
-            const qq_sc::sc u = r.usq[lg - 1 - j];
-            if ((i >> j) & 1) {
-                s_i = qq_sc::mul(s_i, u);
-                y_i = qq_sc::mul(y_i, r.yinv_pow[j]);
-            }
-            if ((irev >> j) & 1) s_rev = qq_sc::mul(s_rev, u);
+        qq_sc::sc s_i = r.allinv, y_j = qq_sc::one();
+        for (int k = 0; k < lg; k++) {
+            if ((i >> k) & 1) s_i = qq_sc::mul(s_i, r.usq[lg - 1 - k]);
+            else y_j = qq_sc::mul(y_j, r.yinv_pow[k]);          // bit k of j is the complement of bit k of i
         }
         sum_g = qq_sc::add(sum_g, qq_sc::sub(r.neg_rz, qq_sc::mul(r.ra, s_i)));
-        qq_sc::sc t = qq_sc::sub(qq_sc::mul(r.rzz_zj[party], two_pow), qq_sc::mul(r.rb, s_rev));
-        sum_h = qq_sc::add(sum_h, qq_sc::add(r.rz, qq_sc::mul(y_i, t)));
+        qq_sc::sc t = qq_sc::sub(qq_sc::mul(r.rzz_zj[party], two_pow), qq_sc::mul(r.rb, s_i));
+        sum_h = qq_sc::add(sum_h, qq_sc::add(r.rz, qq_sc::mul(y_j, t)));
     }
     partial[(size_t)blockIdx.y * 2 * N + i] = sum_g;
-    partial[(size_t)blockIdx.y * 2 * N + N + i] = sum_h;
+    partial[(size_t)blockIdx.y * 2 * N + N + j] = sum_h;
 }
 // out[t] = sum over chunks of partial[chunk][t], t < 2N, written as the 32-byte scalars of the MSM
 __global__ void k_rp_fold_sum(const qq_sc::sc* __restrict__ partial, int chunks, int twoN, qq_sc::sc* __restrict__ out) {
