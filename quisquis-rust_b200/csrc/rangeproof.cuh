@@ -57,13 +57,21 @@ __global__ void __launch_bounds__(128) k_rp_fold(const rp_record* __restrict__ r
     partial[(size_t)blockIdx.y * 2 * N + i] = sum_g;
     partial[(size_t)blockIdx.y * 2 * N + N + j] = sum_h;
 }
-// out[t] = sum over chunks of partial[chunk][t], t < 2N, written as the 32-byte scalars of the MSM
-__global__ void k_rp_fold_sum(const qq_sc::sc* __restrict__ partial, int chunks, int twoN, qq_sc::sc* __restrict__ out) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= twoN) return;
-    qq_sc::sc s = partial[t];
-    for (int c = 1; c < chunks; c++) s = qq_sc::add(s, partial[(size_t)c * twoN + t]);
-    out[t] = s;
+// out[t] = sum over chunks of partial[chunk][t], t < 2N, written as the 32-byte scalars of the MSM: one block per t, the
+// chunks strided over its threads, tree sum in shared memory (few generators and thousands of chunks when n m is small)
+__global__ void __launch_bounds__(128) k_rp_fold_sum(const qq_sc::sc* __restrict__ partial, int chunks, int twoN,
+                                                     qq_sc::sc* __restrict__ out) {
+    __shared__ qq_sc::sc sh[128];
+    const int t = blockIdx.x;
+    qq_sc::sc s = qq_sc::zero();
+    for (int c = threadIdx.x; c < chunks; c += blockDim.x) s = qq_sc::add(s, partial[(size_t)c * twoN + t]);
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = 64; w >= 1; w >>= 1) {
+        if ((int)threadIdx.x < w) sh[threadIdx.x] = qq_sc::add(sh[threadIdx.x], sh[threadIdx.x + w]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[t] = sh[0];
 }
 
 }  // namespace qq
