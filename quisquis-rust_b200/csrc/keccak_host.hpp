@@ -9,7 +9,7 @@
 
 namespace qq_keccak {
 
-static inline uint64_t rotl(uint64_t x, int n) { return n ? (x << n) | (x >> (64 - n)) : x; }
+static inline uint64_t rotl(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }   // 0 < n < 64
 
 static inline void f1600(uint64_t a[25]) {
     static const uint64_t RC[24] = {
@@ -18,19 +18,42 @@ static inline void f1600(uint64_t a[25]) {
         0x0000000080008009ULL, 0x000000008000000aULL, 0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL,
         0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
         0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
-    static const int ROT[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+    // one round written out on 25 locals (theta, rho + pi, chi, iota): the Fiat-Shamir transcripts of the batched verifiers
+    // spend most of their host time here
+    uint64_t a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3], a4 = a[4];
+    uint64_t a5 = a[5], a6 = a[6], a7 = a[7], a8 = a[8], a9 = a[9];
+    uint64_t a10 = a[10], a11 = a[11], a12 = a[12], a13 = a[13], a14 = a[14];
+    uint64_t a15 = a[15], a16 = a[16], a17 = a[17], a18 = a[18], a19 = a[19];
+    uint64_t a20 = a[20], a21 = a[21], a22 = a[22], a23 = a[23], a24 = a[24];
     for (int round = 0; round < 24; round++) {
-        uint64_t c[5], d[5], b[25];
-        for (int x = 0; x < 5; x++) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
-        for (int x = 0; x < 5; x++) d[x] = c[(x + 4) % 5] ^ rotl(c[(x + 1) % 5], 1);
-        for (int i = 0; i < 25; i++) a[i] ^= d[i % 5];
-        // rho + pi: B[y][2x + 3y] = rot(A[x][y]);  index = x + 5 y
-        for (int x = 0; x < 5; x++)
-            for (int y = 0; y < 5; y++) b[y + 5 * ((2 * x + 3 * y) % 5)] = rotl(a[x + 5 * y], ROT[x + 5 * y]);
-        for (int y = 0; y < 5; y++)
-            for (int x = 0; x < 5; x++) a[x + 5 * y] = b[x + 5 * y] ^ (~b[(x + 1) % 5 + 5 * y] & b[(x + 2) % 5 + 5 * y]);
-        a[0] ^= RC[round];
+        const uint64_t c0 = a0 ^ a5 ^ a10 ^ a15 ^ a20, c1 = a1 ^ a6 ^ a11 ^ a16 ^ a21, c2 = a2 ^ a7 ^ a12 ^ a17 ^ a22,
+                       c3 = a3 ^ a8 ^ a13 ^ a18 ^ a23, c4 = a4 ^ a9 ^ a14 ^ a19 ^ a24;
+        const uint64_t d0 = c4 ^ rotl(c1, 1), d1 = c0 ^ rotl(c2, 1), d2 = c1 ^ rotl(c3, 1), d3 = c2 ^ rotl(c4, 1), d4 = c3 ^ rotl(c0, 1);
+        const uint64_t b0 = (a0 ^ d0), b1 = rotl(a6 ^ d1, 44);
+        const uint64_t b2 = rotl(a12 ^ d2, 43), b3 = rotl(a18 ^ d3, 21);
+        const uint64_t b4 = rotl(a24 ^ d4, 14), b5 = rotl(a3 ^ d3, 28);
+        const uint64_t b6 = rotl(a9 ^ d4, 20), b7 = rotl(a10 ^ d0, 3);
+        const uint64_t b8 = rotl(a16 ^ d1, 45), b9 = rotl(a22 ^ d2, 61);
+        const uint64_t b10 = rotl(a1 ^ d1, 1), b11 = rotl(a7 ^ d2, 6);
+        const uint64_t b12 = rotl(a13 ^ d3, 25), b13 = rotl(a19 ^ d4, 8);
+        const uint64_t b14 = rotl(a20 ^ d0, 18), b15 = rotl(a4 ^ d4, 27);
+        const uint64_t b16 = rotl(a5 ^ d0, 36), b17 = rotl(a11 ^ d1, 10);
+        const uint64_t b18 = rotl(a17 ^ d2, 15), b19 = rotl(a23 ^ d3, 56);
+        const uint64_t b20 = rotl(a2 ^ d2, 62), b21 = rotl(a8 ^ d3, 55);
+        const uint64_t b22 = rotl(a14 ^ d4, 39), b23 = rotl(a15 ^ d0, 41);
+        const uint64_t b24 = rotl(a21 ^ d1, 2);
+        a0 = b0 ^ (~b1 & b2); a1 = b1 ^ (~b2 & b3); a2 = b2 ^ (~b3 & b4); a3 = b3 ^ (~b4 & b0); a4 = b4 ^ (~b0 & b1);
+        a5 = b5 ^ (~b6 & b7); a6 = b6 ^ (~b7 & b8); a7 = b7 ^ (~b8 & b9); a8 = b8 ^ (~b9 & b5); a9 = b9 ^ (~b5 & b6);
+        a10 = b10 ^ (~b11 & b12); a11 = b11 ^ (~b12 & b13); a12 = b12 ^ (~b13 & b14); a13 = b13 ^ (~b14 & b10); a14 = b14 ^ (~b10 & b11);
+        a15 = b15 ^ (~b16 & b17); a16 = b16 ^ (~b17 & b18); a17 = b17 ^ (~b18 & b19); a18 = b18 ^ (~b19 & b15); a19 = b19 ^ (~b15 & b16);
+        a20 = b20 ^ (~b21 & b22); a21 = b21 ^ (~b22 & b23); a22 = b22 ^ (~b23 & b24); a23 = b23 ^ (~b24 & b20); a24 = b24 ^ (~b20 & b21);
+        a0 ^= RC[round];
     }
+    a[0] = a0; a[1] = a1; a[2] = a2; a[3] = a3; a[4] = a4;
+    a[5] = a5; a[6] = a6; a[7] = a7; a[8] = a8; a[9] = a9;
+    a[10] = a10; a[11] = a11; a[12] = a12; a[13] = a13; a[14] = a14;
+    a[15] = a15; a[16] = a16; a[17] = a17; a[18] = a18; a[19] = a19;
+    a[20] = a20; a[21] = a21; a[22] = a22; a[23] = a23; a[24] = a24;
 }
 
 struct sponge {

@@ -6,6 +6,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <deque>
+#include <condition_variable>
 #include <memory>
 #include <string>
 #include <thread>

@@ -2,11 +2,14 @@
 // host with g++, so that tests/test_host_arith.py can check the exact limb arithmetic the kernels run against
 // the oracle without a GPU.  This object is never linked into libqq_b200.so and is not a CPU fallback.
 #include <cstring>
+#include <string>
 #include <vector>
 #include "../../quisquis-rust_b200/csrc/ristretto.cuh"
 #include "../../quisquis-rust_b200/csrc/scalarmult.cuh"
 #include "../../quisquis-rust_b200/csrc/compress_batch.cuh"
 #include "../../quisquis-rust_b200/csrc/sc_host.hpp"
+#include "../../quisquis-rust_b200/csrc/keccak_host.hpp"
+#include "../../quisquis-rust_b200/csrc/merlin_host.hpp"
 
 using namespace qq;
 
@@ -274,5 +277,33 @@ int hh_sc_op(uint8_t* out, int op, const uint8_t* a, const uint8_t* b) {
     }
     qq_sc::to_bytes(out, r);
     return 1;
+}
+// host Keccak (keccak_host.hpp): SHA3-512 and SHAKE256 of one message
+void hh_sha3_512(uint8_t* out64, const uint8_t* data, size_t len) { qq_keccak::sha3_512(data, len, out64); }
+void hh_shake256(uint8_t* out, size_t outlen, const uint8_t* data, size_t len) {
+    qq_keccak::shake256 x;
+    x.absorb(data, len);
+    x.squeeze(out, outlen);
+}
+// host Merlin (merlin_host.hpp): Transcript::new(label); a script of operations; the last challenge goes to out.
+// script = records of: kind (0 append_message, 1 challenge_bytes) | label length (1 B) | label | data length (2 B LE) | data
+// (for kind 1 the "data length" is the number of challenge bytes and no data follows); out must hold the largest challenge.
+void hh_merlin_script(uint8_t* out, const uint8_t* label, size_t label_len, const uint8_t* script, size_t script_len) {
+    qq_merlin::transcript tr(label, label_len);
+    size_t i = 0;
+    while (i < script_len) {
+        int kind = script[i++];
+        size_t ll = script[i++];
+        std::string lab((const char*)script + i, ll);
+        i += ll;
+        size_t dl = script[i] | ((size_t)script[i + 1] << 8);
+        i += 2;
+        if (kind == 0) {
+            tr.append_message(lab.c_str(), script + i, dl);
+            i += dl;
+        } else {
+            tr.challenge_bytes(lab.c_str(), out, dl);
+        }
+    }
 }
 }

@@ -1427,3 +1427,22 @@ def test_range_proof_verification(engine):
         exp = [bad_at.get(i, 0) for i in range(nrep)]
         # a flipped scalar bit may make the scalar non-canonical (status 2) - only the top byte can, and these flips avoid it
         assert [int(s) for s in got] == exp, (m, nb)
+
+
+def test_shuffle_verification_pipelined_slices(engine):
+    """Batches of 3 072 proofs and more are verified in slices (GPU batches of one slice under the host pass of the next): 3 100
+    tiled golden proofs with tampered ones at the slice boundaries - exactly those are rejected, at the stage a single-slice
+    call reports."""
+    import os
+    raw = np.fromfile(os.path.join(os.path.dirname(__file__), "golden", "shuffle_proofs.bin"), dtype=np.uint8).reshape(-1, 6432)
+    n = 3100
+    rec = np.tile(raw, ((n + raw.shape[0] - 1) // raw.shape[0], 1))[:n].copy()
+    bad = {0: 2656 + 5, 1549: 40, 1550: 1152 + 70, 1551: 2656 + 3776 - 40, 2000: 2656 + 1500, 3099: 2304 + 10}
+    for i, off in bad.items():
+        rec[i, off] ^= 1
+    si, so, stm, pr = (np.ascontiguousarray(rec[:, a:b]) for a, b in ((0, 1152), (1152, 2304), (2304, 2656), (2656, 6432)))
+    st, sg, det = engine.verify_shuffle(si, so, stm, pr)
+    assert sorted(np.nonzero(st)[0].tolist()) == sorted(bad)
+    for i in bad:       # the same proof alone (single slice, no pipeline): same status, stage and detail
+        s1, g1, d1 = engine.verify_shuffle(si[i:i + 1], so[i:i + 1], stm[i:i + 1], pr[i:i + 1])
+        assert (int(s1[0]), int(g1[0]), int(d1[0])) == (int(st[i]), int(sg[i]), int(det[i])), i

@@ -263,3 +263,56 @@ def test_host_scalar_field(hh):
     for wide in (2**512 - 1, (L << 256) + L - 1, (2**256 - 1) << 256, 2**511):
         assert op(4, wide & (2**256 - 1), wide >> 256) == wide % L
     assert op(2, L, 1) is None and op(0, 1, 2**256 - 1) is None
+
+
+def test_host_keccak_and_merlin(hh):
+    """The host side of the batched verifiers (keccak_host.hpp, merlin_host.hpp compiled with g++): SHA3-512 / SHAKE256 equal
+    hashlib on messages around the rate boundaries; Merlin reproduces the merlin crate's conformance vector and equals the
+    oracle's restatement on random scripts of appends and challenges (absorbs crossing the STROBE rate, long challenges)."""
+    import ctypes
+    import hashlib
+    import random
+    from merlin_ref import Transcript
+    h = hh
+    h.hh_sha3_512.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
+    h.hh_shake256.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
+    h.hh_merlin_script.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
+    rnd = random.Random(5)
+    for n in (0, 1, 31, 32, 71, 72, 73, 135, 136, 137, 143, 144, 200, 1000):
+        msg = bytes(rnd.randrange(256) for _ in range(n))
+        o = ctypes.create_string_buffer(64)
+        h.hh_sha3_512(o, msg, n)
+        assert o.raw == hashlib.sha3_512(msg).digest(), n
+        o = ctypes.create_string_buffer(300)
+        h.hh_shake256(o, 300, msg, n)
+        assert o.raw == hashlib.shake_256(msg).digest(300), n
+
+    def run(label, ops):
+        script = b""
+        for kind, lab, data in ops:
+            script += bytes([kind, len(lab)]) + lab
+            script += (len(data) if kind == 0 else data).to_bytes(2, "little") + (data if kind == 0 else b"")
+        o = ctypes.create_string_buffer(max([1] + [d for k, _, d in ops if k == 1]))
+        h.hh_merlin_script(o, label, len(label), script, len(script))
+        return o.raw
+    # merlin crate, transcript.rs test "equivalence_simple"
+    got = run(b"test protocol", [(0, b"some label", b"some data"), (1, b"challenge", 32)])
+    assert got.hex() == "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"
+    for trial in range(40):
+        label = bytes(rnd.randrange(97, 123) for _ in range(rnd.randrange(1, 20)))
+        ops, tr, last = [], Transcript(label), b""
+        for _ in range(rnd.randrange(1, 30)):
+            lab = bytes(rnd.randrange(97, 123) for _ in range(rnd.randrange(1, 16)))
+            if rnd.random() < 0.75:
+                data = bytes(rnd.randrange(256) for _ in range(rnd.choice((0, 1, 8, 32, 32, 32, 64, 128, 165, 166, 167, 400))))
+                ops.append((0, lab, data))
+                tr.append_message(lab, data)
+            else:
+                k = rnd.choice((1, 32, 64, 64, 128, 200))
+                ops.append((1, lab, k))
+                last = tr.challenge_bytes(lab, k)
+        k = 64
+        ops.append((1, b"final", k))
+        last = tr.challenge_bytes(b"final", k)
+        got = run(label, ops)
+        assert got[:k] == last, trial
