@@ -155,7 +155,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "accounts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # =====================================================================================================================
@@ -621,13 +621,35 @@ def run_b200(args):
             msm["points_per_sec"] = msm["points"] * world / (msm_ms_max * 1e-3)
             msm["note"] = "each GPU runs a full %d-point MSM (weak scaling); compressed input, decompression included" % msm["points"]
             line["msm"] = msm
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     eng.close()
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Rank 0's stdout carries exactly one JSON line: file descriptor 1 is pointed at stderr for the whole run (NCCL prints its
+    version banner on fd 1 from C, whatever NCCL_DEBUG says in this image) and the line is written to the saved descriptor."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _JSON_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

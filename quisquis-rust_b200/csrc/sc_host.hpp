@@ -82,52 +82,69 @@ QQ_SC_FN sc neg(const sc& a) {
 }
 QQ_SC_FN sc sub(const sc& a, const sc& b) { return add(a, neg(b)); }
 
-// x (8 limbs, < 2^512) mod l
+// x (8 limbs, < 2^512) mod l, through the special form l = 2^252 + c (c < 2^125, two limbs): 2^252 = -c (mod l), so
+//   x = lo + 2^252 hi  =  lo - c hi;   c hi = ylo + 2^252 yhi  ->  - ylo + c yhi;   c yhi = zlo + 2^252 zhi  ->  zlo - c zhi
+// with hi < 2^260, yhi < 2^133, zhi < 2^6: 18 64-bit products instead of the 39 of a Barrett reduction.
+// r = lo + zlo + 2 l - ylo - c zhi lies in [0, 4 l + 2^253): a few conditional subtractions finish.
+QQ_SC_FN void split252(const uint64_t* v, int limbs, uint64_t lo[4], uint64_t* hi, int hi_limbs) {
+    // lo = v mod 2^252, hi = v >> 252 (v has `limbs` limbs; limbs beyond are zero)
+    for (int i = 0; i < 3; i++) lo[i] = i < limbs ? v[i] : 0;
+    lo[3] = limbs > 3 ? (v[3] & 0x0fffffffffffffffULL) : 0;
+    for (int i = 0; i < hi_limbs; i++) {
+        uint64_t a = 3 + i < limbs ? v[3 + i] : 0, b = 4 + i < limbs ? v[4 + i] : 0;
+        hi[i] = (a >> 60) | (b << 4);
+    }
+}
+// out (n + 2 limbs) = c * v (n limbs)
+QQ_SC_FN void mul_c(const uint64_t* v, int n, uint64_t* out) {
+    const uint64_t C[2] = {0x5812631a5cf5d3edULL, 0x14def9dea2f79cd6ULL};
+    for (int i = 0; i < n + 2; i++) out[i] = 0;
+    for (int j = 0; j < 2; j++) {
+        u128 carry = 0;
+        for (int i = 0; i < n; i++) {
+            carry += (u128)v[i] * C[j] + out[i + j];
+            out[i + j] = (uint64_t)carry;
+            carry >>= 64;
+        }
+        out[n + j] += (uint64_t)carry;      // no overflow: the running product fits n + 2 limbs
+    }
+}
 QQ_SC_FN sc reduce512(const uint64_t x[8]) {
     const uint64_t L[4] = QQ_SC_L_WORDS;
-    const uint64_t MU[5] = QQ_SC_MU_WORDS;
-    // q1 = floor(x / b^3): limbs 3..7 (5 limbs); q2 = q1 * mu (10 limbs); q3 = floor(q2 / b^5): limbs 5..9
-    uint64_t q2[10] = {0};
-    for (int i = 0; i < 5; i++) {
-        u128 c = 0;
-        for (int j = 0; j < 5; j++) {
-            c += (u128)x[3 + i] * MU[j] + q2[i + j];
-            q2[i + j] = (uint64_t)c;
-            c >>= 64;
-        }
-        q2[i + 5] = (uint64_t)c;
+    uint64_t lo[4], hi[5], y[7], ylo[4], yhi[3], z[5], zlo[4], zhi[1], w[3];
+    split252(x, 8, lo, hi, 5);
+    mul_c(hi, 5, y);                   // < 2^385
+    split252(y, 7, ylo, yhi, 3);       // yhi < 2^133
+    mul_c(yhi, 3, z);                  // < 2^258
+    split252(z, 5, zlo, zhi, 1);       // zhi < 2^6
+    mul_c(zhi, 1, w);                  // < 2^131
+    // t = lo + zlo + 2 l - ylo - w  (5 limbs, never negative)
+    uint64_t t[5];
+    u128 acc = 0;
+    for (int i = 0; i < 4; i++) {
+        acc += (u128)lo[i] + zlo[i] + L[i] + L[i];
+        t[i] = (uint64_t)acc;
+        acc >>= 64;
     }
-    const uint64_t* q3 = q2 + 5;
-    // r2 = q3 * l mod b^5
-    uint64_t r2[5] = {0};
-    for (int i = 0; i < 5; i++) {
-        u128 c = 0;
-        for (int j = 0; j < 4 && i + j < 5; j++) {
-            c += (u128)q3[i] * L[j] + r2[i + j];
-            r2[i + j] = (uint64_t)c;
-            c >>= 64;
-        }
-        if (i + 4 < 5) r2[i + 4] += (uint64_t)c;
-    }
-    // r = (x mod b^5) - r2 mod b^5   (0 <= r < 3 l)
-    uint64_t r[5];
+    t[4] = (uint64_t)acc;
     u128 br = 0;
     for (int i = 0; i < 5; i++) {
-        u128 d = (u128)x[i] - r2[i] - (uint64_t)br;
-        r[i] = (uint64_t)d;
-        br = (d >> 64) & 1;
+        u128 sub = (u128)(i < 4 ? ylo[i] : 0) + (i < 3 ? w[i] : 0) + (uint64_t)br;
+        u128 d = (u128)t[i] - sub;
+        t[i] = (uint64_t)d;
+        br = (uint64_t)(0 - (uint64_t)(d >> 64));      // the subtrahend is below 2^66: the borrow (0, 1 or 2) is minus the high half
     }
-    for (int pass = 0; pass < 2; pass++) {
-        if (r[4] != 0 || geq_l(r)) {
+    for (int pass = 0; pass < 6; pass++) {
+        if (t[4] != 0 || geq_l(t)) {
             u128 b2 = 0;
             for (int i = 0; i < 5; i++) {
-                u128 d = (u128)r[i] - (i < 4 ? L[i] : 0) - (uint64_t)b2;
-                r[i] = (uint64_t)d;
+                u128 d = (u128)t[i] - (i < 4 ? L[i] : 0) - (uint64_t)b2;
+                t[i] = (uint64_t)d;
                 b2 = (d >> 64) & 1;
             }
         }
     }
-    return sc{{r[0], r[1], r[2], r[3]}};
+    return sc{{t[0], t[1], t[2], t[3]}};
 }
 QQ_SC_FN sc mul(const sc& a, const sc& b) {
     uint64_t x[8] = {0};
