@@ -77,6 +77,7 @@ struct qq_ctx {
     std::vector<uint8_t> bp_g, bp_h;
     uint8_t* transcript_capture = nullptr;     // qq_transcript_capture: where the next sigma verification leaves its transcripts
     bool stc_ready = false;                    // k_straus_coop's shared-memory opt-in done
+    int stc_per_sm = 64;                       // segmented MSMs: four-lane cooperative kernel up to this many MSMs per SM (QQ_STRAUS_COOP_PER_SM)
     long vbc_max_jobs = -1;                    // four-lane cooperative variable base up to this many scalar mults (< 0: sms * 160)
 };
 
@@ -499,6 +500,7 @@ extern "C" int qq_init(qq_ctx** out, int device) {
             CK(cudaDeviceGetStreamPriorityRange(&lo_pr, &hi_pr));
             CK(cudaStreamCreateWithPriority(&ctx->msm_hi, cudaStreamNonBlocking, hi_pr));
             if (const char* e = getenv("QQ_MSM_SPLIT_MIN")) ctx->msm_split_min = atol(e);
+            if (const char* e = getenv("QQ_STRAUS_COOP_PER_SM")) ctx->stc_per_sm = atoi(e);
             if (const char* e = getenv("QQ_MSM_TAIL_PCT")) ctx->msm_tail_pct = atoi(e);
             if (const char* e = getenv("QQ_MSM_SORT_BPSM")) ctx->msm_sort_bpsm = atoi(e);
         }
@@ -922,7 +924,7 @@ static int core_msm_to_point(qq_ctx* ctx, const uint8_t* scalars, const uint8_t*
 static int core_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* points, const uint32_t* offsets, size_t m,
                           size_t nterms, uint8_t* out, uint8_t* status) {
     // Few instances (one proof's worth): four lanes per instance, no ordering pass, direct encoder -- 4 launches
-    if (ctx->vbc_max_jobs != 0 && m <= (size_t)ctx->sms * 24) {
+    if (ctx->vbc_max_jobs != 0 && m <= (size_t)ctx->sms * ctx->stc_per_sm) {
         if (!ctx->stc_ready) {
             CK(cudaFuncSetAttribute(k_straus_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, QQ_STC_SMEM_BYTES));
             ctx->stc_ready = true;
