@@ -77,6 +77,7 @@ struct qq_ctx {
     std::vector<uint8_t> bp_g, bp_h;
     uint8_t* transcript_capture = nullptr;     // qq_transcript_capture: where the next sigma verification leaves its transcripts
     bool stc_ready = false;                    // k_straus_coop's shared-memory opt-in done
+    int straus_minb = 4;                       // k_straus build for more than one wave of instances (QQ_STRAUS_MINB)
     int stc_per_sm = 64;                       // segmented MSMs: four-lane cooperative kernel up to this many MSMs per SM (QQ_STRAUS_COOP_PER_SM)
     long vbc_max_jobs = -1;                    // four-lane cooperative variable base up to this many scalar mults (< 0: sms * 160)
 };
@@ -501,6 +502,7 @@ extern "C" int qq_init(qq_ctx** out, int device) {
             CK(cudaStreamCreateWithPriority(&ctx->msm_hi, cudaStreamNonBlocking, hi_pr));
             if (const char* e = getenv("QQ_MSM_SPLIT_MIN")) ctx->msm_split_min = atol(e);
             if (const char* e = getenv("QQ_STRAUS_COOP_PER_SM")) ctx->stc_per_sm = atoi(e);
+            if (const char* e = getenv("QQ_STRAUS_MINB")) ctx->straus_minb = atoi(e);
             if (const char* e = getenv("QQ_MSM_TAIL_PCT")) ctx->msm_tail_pct = atoi(e);
             if (const char* e = getenv("QQ_MSM_SORT_BPSM")) ctx->msm_sort_bpsm = atoi(e);
         }
@@ -952,7 +954,11 @@ static int core_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* po
     // k_varbase (256 x 1, 512 x 1 with a barrier per instance) measured 0-5 % slower here
     const int sblock = 128;
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_straus<128, 2, false>, 128, 0));
+    // more than one wave of instances at 2 blocks per SM: the 4-blocks-per-SM build (128 registers) keeps twice as many
+    // instances resident (QQ_STRAUS_MINB = 2 forces the old choice)
+    const bool dense = ctx->straus_minb >= 4 && m > (size_t)ctx->sms * 2 * sblock;
+    if (dense) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_straus<128, 4, false>, 128, 0));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_straus<128, 2, false>, 128, 0));
     if (occ < 1) occ = 1;
     size_t grid = (m + sblock - 1) / sblock;
     if (grid > (size_t)ctx->sms * occ) grid = (size_t)ctx->sms * occ;
@@ -986,7 +992,8 @@ static int core_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* po
     // every scalar of an instance is halved, the instance sum is encoded as enc(2 * sum) by the batch encoder
     a.out = (u32x4*)out; a.half_out = half; a.status = status; a.scratch = scratch; a.order = order; a.m = m;
     span_begin(ctx, FAM_VB);
-    k_straus<128, 2, false><<<(unsigned)grid, 128, 0, ctx->stream>>>(a);
+    if (dense) k_straus<128, 4, false><<<(unsigned)grid, 128, 0, ctx->stream>>>(a);
+    else k_straus<128, 2, false><<<(unsigned)grid, 128, 0, ctx->stream>>>(a);
     span_end(ctx);
     ctx->launches++;
     CK(cudaGetLastError());
