@@ -37,7 +37,41 @@ using namespace qq;
 #define QQ_FB_W 6  // window width of the shared-memory fixed-base tables (43 windows x 33 entries x 96 B = 136 KB)
 enum { FAM_DEC = 0, FAM_VB = 1, FAM_FB = 2, FAM_FIN = 3, FAM_MSM_BUCKET = 4, FAM_MSM_REDUCE = 5, FAM_COUNT = 6 };
 
+// Grow-only pool of page-locked host buffers for the job lists the batched verifiers upload (acquired by the caller's
+// thread, released by the GPU worker thread of the pipelined shuffle verifier: guarded by a mutex).
+struct pinned_pool {
+    struct blk { uint8_t* p; size_t cap; bool used; };
+    std::mutex mu;
+    std::vector<blk> blocks;
+    uint8_t* acquire(size_t bytes) {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto& b : blocks)
+            if (!b.used && b.cap >= bytes) {
+                b.used = true;
+                return b.p;
+            }
+        void* p = nullptr;
+        size_t cap = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+        if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;      // the caller falls back to pageable memory
+        }
+        blocks.push_back({(uint8_t*)p, cap, true});
+        return (uint8_t*)p;
+    }
+    void release(uint8_t* p) {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto& b : blocks)
+            if (b.p == p) b.used = false;
+    }
+    void destroy() {
+        for (auto& b : blocks) cudaFreeHost(b.p);
+        blocks.clear();
+    }
+};
+
 struct qq_ctx {
+    pinned_pool pin;
     int device = 0;
     int sms = 0;
     cudaStream_t stream = nullptr;
@@ -586,6 +620,7 @@ extern "C" void qq_destroy(qq_ctx* ctx) {
     for (int i = 0; i < 8; i++)
         if (ctx->msm_ev[i]) cudaEventDestroy(ctx->msm_ev[i]);
     for (auto e : ctx->pipe_ev) cudaEventDestroy(e);
+    ctx->pin.destroy();
     if (ctx->msm_hi) cudaStreamDestroy(ctx->msm_hi);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
