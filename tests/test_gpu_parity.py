@@ -1446,3 +1446,29 @@ def test_shuffle_verification_pipelined_slices(engine):
     for i in bad:       # the same proof alone (single slice, no pipeline): same status, stage and detail
         s1, g1, d1 = engine.verify_shuffle(si[i:i + 1], so[i:i + 1], stm[i:i + 1], pr[i:i + 1])
         assert (int(s1[0]), int(g1[0]), int(d1[0])) == (int(st[i]), int(sg[i]), int(det[i])), i
+
+
+def test_range_proof_verification_two_halves(engine):
+    """From 2 048 transcripts on the range-proof verifier works in two halves (device part of the first under the host part of
+    the second): 2 500 tiled golden proofs with tampered ones at the ends of both halves - exactly those are rejected."""
+    import os
+    m = 4
+    per = m * 32 + engine.range_proof_bytes(m)
+    raw = np.fromfile(os.path.join(os.path.dirname(__file__), "golden", "range_proofs_m%d.bin" % m), dtype=np.uint8).reshape(-1, per)
+    n = 2500
+    rec = np.tile(raw, ((n + raw.shape[0] - 1) // raw.shape[0], 1))[:n].copy()
+    bad = {0: (m * 32 + 5 * 32 + 3, 6), 1249: (7, 6), 1250: (m * 32 + 6 * 32 + 9, 6), 2499: (per - 40, 6),
+           1800: (m * 32 + 128 + 31, 2)}       # the last one: top byte of t_x -> non-canonical
+    for i, (off, _) in bad.items():
+        rec[i, off] ^= 0x01 if off != m * 32 + 128 + 31 else 0xff
+    # a flipped bit in a commitment may leave it undecodable: status 1 instead of 6 (either way the reference returns Err)
+    if R.decompress(rec[1249, :32].tobytes()) is None:
+        bad[1249] = (7, 1)
+    cm, pr = np.ascontiguousarray(rec[:, :m * 32]), np.ascontiguousarray(rec[:, m * 32:])
+    st = engine.verify_range_proofs(cm, pr, m)
+    assert sorted(np.nonzero(st)[0].tolist()) == sorted(bad)
+    for i, (_, code) in bad.items():
+        assert int(st[i]) == code, i
+        alone = engine.verify_range_proofs(cm[i:i + 1], pr[i:i + 1], m)
+        assert int(alone[0]) == code, i
+    assert not engine.verify_range_proofs(cm[:0], pr[:0], m).size        # empty batch
