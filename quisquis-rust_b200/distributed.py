@@ -51,3 +51,34 @@ def msm_sharded(partial_fn, sum_fn, scalars, points, device=None):
         return np.zeros(32, np.uint8), bad[0]   # lowest rank = earliest slice = first failing term
     out, ident = sum_fn(parts.reshape(-1))
     return out, 0
+
+
+def verify_sharded(verify_fn, arrays, nproofs, device=None):
+    """Independent proofs across ranks (BASELINE configs[2]: 4 096 shuffle proofs over 8 GPUs): every rank verifies its
+    contiguous slice, the status bytes are all-gathered (the only exchange: one byte per proof).
+    `arrays`: per-proof arrays (nproofs x bytes each); `verify_fn(*slices) -> status (uint8 per proof)`.
+    Every rank returns the full nproofs status array."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    arrays = [np.asarray(a, dtype=np.uint8).reshape(nproofs, -1) for a in arrays]
+    lo, hi = shard_range(nproofs, rank, world)
+    local = np.asarray(verify_fn(*[a[lo:hi] for a in arrays]), dtype=np.uint8).reshape(-1)
+    if local.size != hi - lo:
+        raise ValueError("verify_fn returned %d verdicts for %d proofs" % (local.size, hi - lo))
+    if world == 1:
+        return local.copy()
+    width = (nproofs + world - 1) // world          # slices differ by at most one proof: pad to the widest
+    buf = np.zeros(width, np.uint8)
+    buf[:local.size] = local
+    t = torch.from_numpy(buf)
+    if device is not None:
+        t = t.to(device)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    full = np.zeros(nproofs, np.uint8)
+    for r in range(world):
+        a, b = shard_range(nproofs, r, world)
+        full[a:b] = out[r].cpu().numpy()[:b - a]
+    return full

@@ -90,3 +90,56 @@ def test_shard_range_covers_everything():
             cuts = [shard_range(n, r, w) for r in range(w)]
             assert cuts[0][0] == 0 and cuts[-1][1] == n
             assert all(cuts[i][1] == cuts[i + 1][0] for i in range(w - 1))
+
+
+def _verify_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    import rangeproof_ref as RP
+    from merlin_ref import Transcript
+    g.load_package()
+    from quisquis_rust_b200 import distributed as D
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    m = 1
+    per = m * 32 + (9 + 12) * 32
+    raw = np.fromfile(os.path.join(ROOT, "tests", "golden", "range_proofs_m1.bin"), dtype=np.uint8).reshape(-1, per)
+    n = 5                                                   # uneven slices: 2 + 3
+    rec = np.tile(raw, (2, 1))[:n].copy()
+    rec[1, 32 + 5 * 32] ^= 1                                # rank 0's slice
+    rec[4, 32 + 6 * 32] ^= 1                                # rank 1's slice
+    seen = []
+
+    def verify_fn(cm, pr):  # the oracle's verifier stands in for qq_verify_range_proof_batch
+        seen.append(cm.shape[0])
+        out = []
+        for i in range(cm.shape[0]):
+            tr = Transcript(b"SenderAccountProof")
+            tr.domain_sep(b"BulletProof")
+            tr.domain_sep(b"AggregateBulletProof")
+            ok = RP.verify_multiple(tr, pr[i].tobytes(), [cm[i].tobytes()], 64, bp_gens=RP.BulletproofGens(64, 1))
+            out.append(0 if ok else 6)
+        return np.array(out, np.uint8)
+    full = D.verify_sharded(verify_fn, [rec[:, :32], rec[:, 32:]], n)
+    q.put((rank, full.tolist(), seen))
+    dist.destroy_process_group()
+
+
+def test_verify_sharded_gloo_world2():
+    """Proof batches shard into contiguous slices per rank (no data-path collective), the verdicts are all-gathered: both ranks
+    end with the same five verdicts, each having verified only its own slice."""
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_verify_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(60)
+    assert [r[0] for r in res] == [0, 1]
+    assert res[0][1] == res[1][1] == [0, 6, 0, 0, 6]
+    assert res[0][2] == [2] and res[1][2] == [3]
