@@ -59,6 +59,19 @@ def main():
     xyzt[:, 32] = 1
     xyzt[:, 64] = 1
     eng.points_sum(xyzt)
+    # the batched verifiers on the committed golden proofs (odd counts), and the MSM tuning knob
+    gold = os.path.join(ROOT, "tests", "golden")
+    rec = np.fromfile(os.path.join(gold, "shuffle_proofs.bin"), dtype=np.uint8).reshape(-1, 6432)[:3]
+    st = eng.verify_shuffle(rec[:, :1152].copy(), rec[:, 1152:2304].copy(), rec[:, 2304:2656].copy(), rec[:, 2656:].copy())[0]
+    assert not st.any()
+    for m in (1, 4, 16):
+        per = m * 32 + eng.range_proof_bytes(m)
+        rr = np.fromfile(os.path.join(gold, "range_proofs_m%d.bin" % m), dtype=np.uint8).reshape(-1, per)[:3]
+        assert not eng.verify_range_proofs(rr[:, :m * 32].copy(), rr[:, m * 32:].copy(), m).any()
+    eng.msm_set_overlap(1 << 10, 40, 2)
+    pts = eng.fixed_base(0, scal(3000))[0]
+    assert eng.msm(scal(3000), pts)[1] == 0
+    eng.msm_set_overlap()
     eng.close()
     print("exercise pass done: every entry point returned without a CUDA error")
 
