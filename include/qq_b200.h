@@ -20,6 +20,9 @@
  *     Err("Error::Decompression Failed") / None, status[i] = QQ_ST_BAD_POINT and the outputs for element i are zero.
  *   - One qq_ctx per GPU and per calling thread (or external locking).  There is NO CPU fallback: qq_init fails
  *     when no sm_100 device is usable.
+ *   - The batched verifiers (qq_verify_*_batch) run their Fiat-Shamir transcripts on std::thread workers (one per host
+ *     core, created and joined inside the call); qq_verify_shuffle_batch and qq_verify_range_proof_batch also drive the GPU
+ *     from one internal worker thread while the caller's thread prepares the next slice.  The calls stay synchronous.
  */
 #ifndef QQ_B200_H
 #define QQ_B200_H
