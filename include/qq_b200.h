@@ -64,7 +64,7 @@ uint64_t qq_launch_count(const qq_ctx* ctx);
 /* milliseconds spent in kernels during the most recent call, measured with CUDA events on the ctx stream */
 float qq_last_kernel_ms(const qq_ctx* ctx);
 /* per-kernel-family milliseconds of the most recent call: [0] decompress [1] variable-base [2] fixed-base
- * [3] finish/compress [4] msm-bucket [5] msm-reduce; returns number of entries written */
+ * [3] finish/compress [4] msm-bucket [5] msm-reduce [6] transcript kernels; returns number of entries written */
 int qq_last_kernel_breakdown(const qq_ctx* ctx, float* ms, int cap);
 /* CUDA events on the ctx stream (the stream every kernel of this ctx is launched on), so callers can time a
  * sequence of _dev calls on the device: record slot a, run, record slot b, read elapsed.  slots 0..7 */
@@ -317,6 +317,11 @@ int qq_verify_product_batch(qq_ctx* ctx, const char* transcript_label, const cha
 int qq_verify_shuffle_batch(qq_ctx* ctx, const char* transcript_label, const char* verifier_label, const uint8_t* shuffle_input,
                             const uint8_t* shuffle_output, const uint8_t* statement, const uint8_t* proof, size_t nproofs,
                             uint8_t* status, uint8_t* stage, uint8_t* detail);
+/* Where qq_verify_shuffle_batch runs the per-proof Fiat-Shamir transcripts (Merlin, src/accounts/transcript.rs:55-82) and
+ * the Z/l algebra: on_device != 0 (default) in transcript kernels, one GPU thread per proof - the proof bytes are the only
+ * upload, job lists, transcripts and verdicts stay in device memory; on_device == 0 on the host threads, job lists uploaded
+ * per batch (the round-1 arrangement, kept for A/B measurements).  Verdicts are identical. */
+int qq_verify_set_transcripts(qq_ctx* ctx, int on_device);
 
 /* ---- Bulletproofs range proofs (BASELINE configs[3]) -----------------------------------------------------------------
  * RangeProof::verify_multiple / verify_single of the `bulletproofs` crate, as called by
@@ -340,13 +345,18 @@ int qq_verify_shuffle_batch(qq_ctx* ctx, const char* transcript_label, const cha
 int qq_verify_range_proof_batch(qq_ctx* ctx, const char* transcript_label, const char* verifier_label,
                                 const uint8_t* transcript_state, const char* domain_label, const uint8_t* commitments,
                                 const uint8_t* proofs, size_t n_bits, size_t m, size_t chain, size_t nproofs, uint8_t* status);
-/* Size of one serialised verifier transcript (opaque: the STROBE-128 state of merlin::Transcript). */
+/* Size of one serialised verifier transcript: 200 bytes STROBE-128 state | pos | pos_begin | cur_flags | tag 0xa5 | 4 zero
+ * bytes of merlin::Transcript.  qq_verify_range_proof_batch validates tag and positions; an entry that fails (all-zero: the
+ * sigma check of that proof ended before the capture) gets QQ_ST_PROOF. */
 size_t qq_transcript_state_bytes(void);
-/* The NEXT sigma-proof verification call on this ctx (qq_verify_account_sigma_batch, ..) also writes the transcript of each
- * proof, as it stands after the challenge, to states_out (nproofs x qq_transcript_state_bytes()): the reference keeps one
+/* The NEXT entry point called on this ctx, if it is a sigma-proof verification that keeps a transcript
+ * (qq_verify_account_sigma_batch, qq_verify_zero_balance_batch, qq_verify_destroy_account_batch,
+ * qq_verify_same_value_compact_batch, qq_verify_update_account_dark_tx_batch, qq_verify_ddh_batch), also writes the transcript
+ * of each proof, as it stands after the challenge, to states_out: min(capacity_states, nproofs) entries of
+ * qq_transcript_state_bytes(), zero-filled for proofs whose check ended before the challenge.  The reference keeps one
  * running transcript per Verifier across verify_account_verifier_bulletproof and the range proof (verifier.rs:1603-1628).
- * One-shot; NULL cancels. */
-int qq_transcript_capture(qq_ctx* ctx, uint8_t* states_out);
+ * One-shot: ANY next entry point (whatever it returns) disarms it; NULL cancels. */
+int qq_transcript_capture(qq_ctx* ctx, uint8_t* states_out, size_t capacity_states);
 
 /* ---- decommit ------------------------------------------------------------------------------------------------------
  * ElGamalCommitment::decommit(sk) = enc(d - sk*c) = enc(v*B)                    src/elgamal/elgamal.rs:106-108 */

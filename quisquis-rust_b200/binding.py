@@ -27,6 +27,7 @@ EXPORTS = [
     "qq_verify_same_value_compact_batch", "qq_verify_update_account_dark_tx_batch",
     "qq_verify_update_account_dlog_batch", "qq_verify_delta_compact_batch", "qq_decommit_batch", "qq_decommit_value_batch", "qq_from_uniform_bytes_batch", "qq_vector_pedersen_gens", "qq_bulletproof_gens",
     "qq_verify_range_proof_batch", "qq_transcript_state_bytes", "qq_transcript_capture", "qq_msm_set_overlap",
+    "qq_verify_set_transcripts",
 ]
 
 
@@ -114,7 +115,8 @@ def load_library():
     lib.qq_verify_range_proof_batch.argtypes = [vp, cs, cs, u8p, cs, u8p, u8p, sz, sz, sz, sz, u8p]
     lib.qq_transcript_state_bytes.argtypes = []
     lib.qq_transcript_state_bytes.restype = ctypes.c_size_t
-    lib.qq_transcript_capture.argtypes = [vp, u8p]
+    lib.qq_transcript_capture.argtypes = [vp, u8p, ctypes.c_size_t]
+    lib.qq_verify_set_transcripts.argtypes = [vp, ctypes.c_int]
     lib.qq_msm_set_overlap.argtypes = [vp, ctypes.c_long, ctypes.c_int, ctypes.c_int]
     lib.qq_msm_points_free.argtypes = [vp, vp]
     lib.qq_msm_points_free.restype = None
@@ -187,7 +189,7 @@ class Engine:
     def last_kernel_breakdown(self):
         buf = (ctypes.c_float * 8)()
         k = self.lib.qq_last_kernel_breakdown(self.h, buf, 8)
-        names = ["decompress", "varbase", "fixedbase", "finish", "msm_bucket", "msm_reduce"]
+        names = ["decompress", "varbase", "fixedbase", "finish", "msm_bucket", "msm_reduce", "transcripts"]
         return {names[i]: float(buf[i]) for i in range(k)}
 
     def measure_imad_peak(self):
@@ -492,6 +494,10 @@ class Engine:
                                                    nproofs, _ptr(st), _ptr(sg), _ptr(det)), "qq_verify_shuffle_batch")
         return st, sg, det
 
+    def verify_set_transcripts(self, on_device=True):
+        """Shuffle verifier: per-proof transcripts / scalar algebra in GPU transcript kernels (default) or on the host threads."""
+        self._ck(self.lib.qq_verify_set_transcripts(self.h, 1 if on_device else 0), "qq_verify_set_transcripts")
+
     def msm_set_overlap(self, split_min=1 << 17, tail_pct=30, sort_blocks_per_sm=3):
         """Large-MSM tuning (decompression of the last tail_pct % of the points under the counting sort); tail_pct 0 = off."""
         self._ck(self.lib.qq_msm_set_overlap(self.h, split_min, tail_pct, sort_blocks_per_sm), "qq_msm_set_overlap")
@@ -521,7 +527,7 @@ class Engine:
     def transcript_capture(self, nproofs):
         """Arms the one-shot capture: the next sigma verification call leaves its nproofs transcripts in the returned array."""
         buf = np.zeros(nproofs * self.lib.qq_transcript_state_bytes(), np.uint8)
-        self._ck(self.lib.qq_transcript_capture(self.h, _ptr(buf)), "qq_transcript_capture")
+        self._ck(self.lib.qq_transcript_capture(self.h, _ptr(buf), nproofs), "qq_transcript_capture")
         return buf
 
     def decommit(self, comm, sk):

@@ -1,25 +1,42 @@
-// Keccak-f[1600] sponge on the HOST (FIPS 202): SHA3-512 and the SHAKE256 XOF.
-// Only the hashing of a few labels / 32-byte encodings that precedes the hash-to-group map of generator derivation
-// (reference src/pedersen/vectorpedersen.rs:45-75 uses sha3::Sha3_512; the Bulletproofs generator chains use Shake256);
-// the field and curve work of hash-to-group runs on the GPU (k_from_uniform).  A few kilobytes per call: host code.
+// Keccak-f[1600] sponge (FIPS 202), callable from host AND device code: SHA3-512 and the SHAKE256 XOF for generator
+// derivation (reference src/pedersen/vectorpedersen.rs:45-75 uses sha3::Sha3_512; the Bulletproofs generator chains use
+// Shake256: a few kilobytes per call, hashed on the host, the field and curve work of hash-to-group runs in k_from_uniform),
+// and the permutation under the Merlin transcripts (merlin_host.hpp) that the batched verifiers run one-thread-per-proof in
+// their transcript kernels (shuffle_verify.cuh).
 #pragma once
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
 
+#ifdef __CUDACC__
+#define QQ_HOSTDEV __host__ __device__
+#else
+#define QQ_HOSTDEV
+#endif
+#define QQ_KECCAK_RC_WORDS {                                                                                              \
+        0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL, \
+        0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008aULL, 0x0000000000000088ULL, \
+        0x0000000080008009ULL, 0x000000008000000aULL, 0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, \
+        0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL, \
+        0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL}
+
 namespace qq_keccak {
 
-static inline uint64_t rotl(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }   // 0 < n < 64
+static const uint64_t RC_HOST[24] = QQ_KECCAK_RC_WORDS;
+#ifdef __CUDACC__
+static __constant__ uint64_t RC_DEV[24] = QQ_KECCAK_RC_WORDS;     // the same round constants through the constant bank
+#endif
 
-static inline void f1600(uint64_t a[25]) {
-    static const uint64_t RC[24] = {
-        0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL,
-        0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008aULL, 0x0000000000000088ULL,
-        0x0000000080008009ULL, 0x000000008000000aULL, 0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL,
-        0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
-        0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+QQ_HOSTDEV static inline uint64_t rotl(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }   // 0 < n < 64
+
+QQ_HOSTDEV static inline void f1600(uint64_t a[25]) {
+#ifdef __CUDA_ARCH__
+    const uint64_t* RC = RC_DEV;
+#else
+    const uint64_t* RC = RC_HOST;
+#endif
     // one round written out on 25 locals (theta, rho + pi, chi, iota): the Fiat-Shamir transcripts of the batched verifiers
-    // spend most of their host time here
+    // spend most of their time here
     uint64_t a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3], a4 = a[4];
     uint64_t a5 = a[5], a6 = a[6], a7 = a[7], a8 = a[8], a9 = a[9];
     uint64_t a10 = a[10], a11 = a[11], a12 = a[12], a13 = a[13], a14 = a[14];

@@ -1,29 +1,28 @@
-// Merlin transcripts on the HOST: STROBE-128 over Keccak-f[1600] (merlin.cool; crate `merlin`, a dependency of the
+// Merlin transcripts: STROBE-128 over Keccak-f[1600] (merlin.cool; crate `merlin`, a dependency of the
 // reference: src/accounts/transcript.rs:10) and the reference's TranscriptProtocol extension (transcript.rs:55-82).
-// Fiat-Shamir hashing is a sequential sponge over a few kilobytes per proof: host code.  The group arithmetic that
-// produces the points it absorbs (the sigma-protocol commitments, 2-3-term MSMs) runs on the GPU.
+// Callable from host and device code: the sigma verifiers run one transcript per proof on the host threads, the shuffle
+// verifier runs them one-thread-per-proof in its transcript kernels (shuffle_verify.cuh).  The group arithmetic that
+// produces the points a transcript absorbs runs in the MSM kernels either way.
 #pragma once
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
 
 #include "keccak_host.hpp"
+#include "sc_host.hpp"
 
 namespace qq_merlin {
 
 class strobe128 {
     static const int R = 166;
     enum { FLAG_I = 1, FLAG_A = 2, FLAG_C = 4, FLAG_T = 8, FLAG_M = 16, FLAG_K = 32 };
-    uint8_t st[200];
+    alignas(8) uint8_t st[200];
     uint8_t pos, pos_begin, cur_flags;
 
-    void permute() {
-        uint64_t a[25];
-        memcpy(a, st, 200);   // little-endian host (x86-64 / aarch64 LE)
-        qq_keccak::f1600(a);
-        memcpy(st, a, 200);
+    QQ_HOSTDEV void permute() {
+        qq_keccak::f1600(reinterpret_cast<uint64_t*>(st));   // little-endian host (x86-64 / aarch64 LE) and device
     }
-    void run_f() {
+    QQ_HOSTDEV void run_f() {
         st[pos] ^= pos_begin;
         st[pos + 1] ^= 0x04;
         st[R + 1] ^= 0x80;
@@ -31,20 +30,20 @@ class strobe128 {
         pos = 0;
         pos_begin = 0;
     }
-    void absorb(const uint8_t* d, size_t n) {
+    QQ_HOSTDEV void absorb(const uint8_t* d, size_t n) {
         for (size_t i = 0; i < n; i++) {
             st[pos++] ^= d[i];
             if (pos == R) run_f();
         }
     }
-    void squeeze(uint8_t* d, size_t n) {
+    QQ_HOSTDEV void squeeze(uint8_t* d, size_t n) {
         for (size_t i = 0; i < n; i++) {
             d[i] = st[pos];
             st[pos++] = 0;
             if (pos == R) run_f();
         }
     }
-    void begin_op(uint8_t flags, bool more) {
+    QQ_HOSTDEV void begin_op(uint8_t flags, bool more) {
         if (more) return;   // continuation of the current operation (same flags by construction)
         uint8_t old_begin = pos_begin;
         pos_begin = (uint8_t)(pos + 1);
@@ -55,23 +54,44 @@ class strobe128 {
     }
 
   public:
-    explicit strobe128(const char* protocol_label) : pos(0), pos_begin(0), cur_flags(0) {
+    QQ_HOSTDEV explicit strobe128(const char* protocol_label) : pos(0), pos_begin(0), cur_flags(0) {
         memset(st, 0, sizeof st);
         const uint8_t init[6] = {1, R + 2, 1, 0, 1, 96};
         memcpy(st, init, 6);
         memcpy(st + 6, "STROBEv1.0.2", 12);
         permute();
-        meta_ad((const uint8_t*)protocol_label, strlen(protocol_label), false);
+        meta_ad((const uint8_t*)protocol_label, label_len(protocol_label), false);
     }
-    void meta_ad(const uint8_t* d, size_t n, bool more) {
+    QQ_HOSTDEV static size_t label_len(const char* s) {
+        size_t n = 0;
+        while (s[n]) n++;
+        return n;
+    }
+    // serialised form (qq_transcript_state_bytes): 200 state bytes | pos | pos_begin | cur_flags | tag | 4 zero bytes
+    static const int STATE_BYTES = 208;
+    static const uint8_t STATE_TAG = 0xa5;
+    QQ_HOSTDEV void export_state(uint8_t* out) const {
+        memcpy(out, st, 200);
+        out[200] = pos; out[201] = pos_begin; out[202] = cur_flags; out[203] = STATE_TAG;
+        out[204] = out[205] = out[206] = out[207] = 0;
+    }
+    // false (and the object is left untouched) when the bytes are not a state export_state wrote: wrong tag (e.g. the all-zero
+    // entry of a proof whose sigma check ended before the capture) or positions outside the sponge rate
+    QQ_HOSTDEV bool import_state(const uint8_t* in) {
+        if (in[203] != STATE_TAG || in[200] >= R || in[201] > R) return false;
+        memcpy(st, in, 200);
+        pos = in[200]; pos_begin = in[201]; cur_flags = in[202];
+        return true;
+    }
+    QQ_HOSTDEV void meta_ad(const uint8_t* d, size_t n, bool more) {
         begin_op(FLAG_M | FLAG_A, more);
         absorb(d, n);
     }
-    void ad(const uint8_t* d, size_t n, bool more) {
+    QQ_HOSTDEV void ad(const uint8_t* d, size_t n, bool more) {
         begin_op(FLAG_A, more);
         absorb(d, n);
     }
-    void prf(uint8_t* d, size_t n, bool more) {
+    QQ_HOSTDEV void prf(uint8_t* d, size_t n, bool more) {
         begin_op(FLAG_I | FLAG_A | FLAG_C, more);
         squeeze(d, n);
     }
@@ -82,41 +102,45 @@ class transcript {
     strobe128 s;
 
   public:
-    transcript(const uint8_t* label, size_t n) : s("Merlin v1.0") { append_message("dom-sep", label, n); }
-    void append_message(const char* label, const uint8_t* msg, size_t n) {
-        s.meta_ad((const uint8_t*)label, strlen(label), false);
+    static const int STATE_BYTES = strobe128::STATE_BYTES;
+    QQ_HOSTDEV transcript(const uint8_t* label, size_t n) : s("Merlin v1.0") { append_message("dom-sep", label, n); }
+    QQ_HOSTDEV void export_state(uint8_t* out) const { s.export_state(out); }
+    QQ_HOSTDEV bool import_state(const uint8_t* in) { return s.import_state(in); }
+    QQ_HOSTDEV void append_message(const char* label, const uint8_t* msg, size_t n) {
+        s.meta_ad((const uint8_t*)label, strobe128::label_len(label), false);
         uint8_t len[4] = {(uint8_t)n, (uint8_t)(n >> 8), (uint8_t)(n >> 16), (uint8_t)(n >> 24)};
         s.meta_ad(len, 4, true);
         s.ad(msg, n, false);
     }
-    void challenge_bytes(const char* label, uint8_t* out, size_t n) {
-        s.meta_ad((const uint8_t*)label, strlen(label), false);
+    QQ_HOSTDEV void challenge_bytes(const char* label, uint8_t* out, size_t n) {
+        s.meta_ad((const uint8_t*)label, strobe128::label_len(label), false);
         uint8_t len[4] = {(uint8_t)n, (uint8_t)(n >> 8), (uint8_t)(n >> 16), (uint8_t)(n >> 24)};
         s.meta_ad(len, 4, true);
         s.prf(out, n, false);
     }
-    void domain_sep(const char* label) { append_message("dom-sep", (const uint8_t*)label, strlen(label)); }
-    void append_point_var(const char* label, const uint8_t point[32]) {
-        append_message("ptvar", (const uint8_t*)label, strlen(label));
+    QQ_HOSTDEV void domain_sep(const char* label) { append_message("dom-sep", (const uint8_t*)label, strobe128::label_len(label)); }
+    QQ_HOSTDEV void append_point_var(const char* label, const uint8_t point[32]) {
+        append_message("ptvar", (const uint8_t*)label, strobe128::label_len(label));
         append_message("val", point, 32);
     }
-    void append_scalar_var(const char* label, const uint8_t scalar[32]) { append_message(label, scalar, 32); }
-    void append_account_var(const char* label, const uint8_t acc[128]) {
-        append_message("acvar", (const uint8_t*)label, strlen(label));
+    QQ_HOSTDEV void append_scalar_var(const char* label, const uint8_t scalar[32]) { append_message(label, scalar, 32); }
+    QQ_HOSTDEV void append_account_var(const char* label, const uint8_t acc[128]) {
+        append_message("acvar", (const uint8_t*)label, strobe128::label_len(label));
         append_message("gr", acc, 32);
         append_message("grsk", acc + 32, 32);
         append_message("commc", acc + 64, 32);
         append_message("commd", acc + 96, 32);
     }
     // get_challenge: 64 challenge bytes reduced mod l (Scalar::from_bytes_mod_order_wide), canonical 32 bytes out
-    void get_challenge(const char* label, uint8_t out[32]);
+    QQ_HOSTDEV void get_challenge(const char* label, uint8_t out[32]);
 };
 
 // ---- scalars mod l on the host (only what the verifiers need: wide reduction, negation) --------------------------------
 static const uint64_t L_WORDS[4] = {0x5812631a5cf5d3edULL, 0x14def9dea2f79cd6ULL, 0ULL, 0x1000000000000000ULL};
 
 // r = x mod l for a 512-bit little-endian x: binary long division (512 shift-compare-subtract steps; a few hundred ns)
-static inline void sc_reduce_wide(uint8_t out[32], const uint8_t in[64]) {
+QQ_HOSTDEV static inline void sc_reduce_wide(uint8_t out[32], const uint8_t in[64]) {
+    const uint64_t L_WORDS[4] = QQ_SC_L_WORDS;      // function-local: visible to device code too
     uint64_t r[5] = {0, 0, 0, 0, 0};
     for (int bit = 511; bit >= 0; bit--) {
         // r = 2 r + bit
@@ -146,7 +170,8 @@ static inline void sc_reduce_wide(uint8_t out[32], const uint8_t in[64]) {
     memcpy(out, r, 32);
 }
 // out = -s mod l for canonical s
-static inline void sc_negate(uint8_t out[32], const uint8_t s[32]) {
+QQ_HOSTDEV static inline void sc_negate(uint8_t out[32], const uint8_t s[32]) {
+    const uint64_t L_WORDS[4] = QQ_SC_L_WORDS;
     uint64_t a[4];
     memcpy(a, s, 32);
     if ((a[0] | a[1] | a[2] | a[3]) == 0) {
@@ -162,10 +187,10 @@ static inline void sc_negate(uint8_t out[32], const uint8_t s[32]) {
     }
     memcpy(out, r, 32);
 }
-inline void transcript::get_challenge(const char* label, uint8_t out[32]) {
+QQ_HOSTDEV inline void transcript::get_challenge(const char* label, uint8_t out[32]) {
     uint8_t wide[64];
     challenge_bytes(label, wide, 64);
-    sc_reduce_wide(out, wide);
+    qq_sc::to_bytes(out, qq_sc::from_wide(wide));      // special-form reduction (sc_host.hpp); sc_reduce_wide is the slow cross-check
 }
 
 }  // namespace qq_merlin

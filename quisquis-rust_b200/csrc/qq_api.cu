@@ -10,6 +10,7 @@
 #include <deque>
 #include <condition_variable>
 #include <memory>
+#include <functional>
 #include <string>
 #include <thread>
 #include <vector>
@@ -24,6 +25,7 @@
 #include "sc_host.hpp"
 #include "decommit.cuh"
 #include "rangeproof.cuh"
+#include "shuffle_verify.cuh"
 
 using namespace qq;
 
@@ -35,7 +37,7 @@ using namespace qq;
 // multi-level shared inversion (five dependent launches)
 #define QQ_DC_DIRECT_MAX ((size_t)ctx->sms * 128)
 #define QQ_FB_W 6  // window width of the shared-memory fixed-base tables (43 windows x 33 entries x 96 B = 136 KB)
-enum { FAM_DEC = 0, FAM_VB = 1, FAM_FB = 2, FAM_FIN = 3, FAM_MSM_BUCKET = 4, FAM_MSM_REDUCE = 5, FAM_COUNT = 6 };
+enum { FAM_DEC = 0, FAM_VB = 1, FAM_FB = 2, FAM_FIN = 3, FAM_MSM_BUCKET = 4, FAM_MSM_REDUCE = 5, FAM_TRANSCRIPT = 6, FAM_COUNT = 7 };
 
 // Grow-only pool of page-locked host buffers for the job lists the batched verifiers upload (acquired by the caller's
 // thread, released by the GPU worker thread of the pipelined shuffle verifier: guarded by a mutex).
@@ -109,10 +111,18 @@ struct qq_ctx {
     uint8_t xpc_h[32], xpc_g[96];
     bool bp_ready = false;                     // BulletproofGens::new(64, 16) (compressed, party-major), derived on first use
     std::vector<uint8_t> bp_g, bp_h;
-    uint8_t* transcript_capture = nullptr;     // qq_transcript_capture: where the next sigma verification leaves its transcripts
+    // qq_transcript_capture arms (pointer, capacity in states) for the NEXT entry point only: ENTER() of every entry point moves
+    // them to capture_live / capture_cap (and disarms); only sigma_run reads the live pair, so a call that returns early, a
+    // verifier that keeps no transcript or an exception between the two calls can never leave a stale pointer behind
+    uint8_t* transcript_capture = nullptr;
+    size_t transcript_capture_cap = 0;
+    uint8_t* capture_live = nullptr;
+    size_t capture_cap = 0;
     bool stc_ready = false;                    // k_straus_coop's shared-memory opt-in done
     int straus_minb = 4;                       // k_straus build for more than one wave of instances (QQ_STRAUS_MINB)
     int stc_per_sm = 64;                       // segmented MSMs: four-lane cooperative kernel up to this many MSMs per SM (QQ_STRAUS_COOP_PER_SM)
+    bool verify_host_transcripts = false;      // qq_verify_set_transcripts(ctx, 0): per-proof phases of the shuffle verifier on the host threads
+    uint8_t* d_shuffle_gens = nullptr;         // B | B_blinding | H | G[0..3) of VectorPedersenGens::new(4), device copy for the transcript kernels
     long vbc_max_jobs = -1;                    // four-lane cooperative variable base up to this many scalar mults (< 0: sms * 160)
 };
 
@@ -539,6 +549,7 @@ extern "C" int qq_init(qq_ctx** out, int device) {
             if (const char* e = getenv("QQ_STRAUS_MINB")) ctx->straus_minb = atoi(e);
             if (const char* e = getenv("QQ_MSM_TAIL_PCT")) ctx->msm_tail_pct = atoi(e);
             if (const char* e = getenv("QQ_MSM_SORT_BPSM")) ctx->msm_sort_bpsm = atoi(e);
+            if (const char* e = getenv("QQ_VERIFY_HOST_TRANSCRIPTS")) ctx->verify_host_transcripts = atoi(e) != 0;
         }
         for (int i = 0; i < 8; i++) CK(cudaEventCreateWithFlags(&ctx->msm_ev[i], cudaEventDisableTiming));
         CK(cudaFuncSetAttribute(k_msm_sum_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * QQ_PT_BYTES));
@@ -610,6 +621,7 @@ extern "C" void qq_destroy(qq_ctx* ctx) {
     if (ctx->bsgs_slots) cudaFree(ctx->bsgs_slots);
     if (ctx->msm_res) cudaFree(ctx->msm_res);
     if (ctx->msm_small) cudaFree(ctx->msm_small);
+    if (ctx->d_shuffle_gens) cudaFree(ctx->d_shuffle_gens);
     for (int i = 0; i < 8; i++)
         if (ctx->user_ev[i]) cudaEventDestroy(ctx->user_ev[i]);
     for (int b = 0; b < 2; b++) {
@@ -1086,9 +1098,13 @@ struct stage {
     }
 };
 
-#define ENTER()                          \
-    if (!ctx) return QQ_ERR_ARG;         \
-    CK(cudaSetDevice(ctx->device));      \
+#define ENTER()                                          \
+    if (!ctx) return QQ_ERR_ARG;                         \
+    ctx->capture_live = ctx->transcript_capture;         \
+    ctx->capture_cap = ctx->transcript_capture_cap;      \
+    ctx->transcript_capture = nullptr;                   \
+    ctx->transcript_capture_cap = 0;                     \
+    CK(cudaSetDevice(ctx->device));                      \
     call_begin(ctx)
 
 extern "C" int qq_update_public_key_batch_dev(qq_ctx* ctx, const uint8_t* pk, const uint8_t* r, uint8_t* out_pk,

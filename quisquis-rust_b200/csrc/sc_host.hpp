@@ -10,8 +10,10 @@
 #include <cstring>
 #ifdef __CUDACC__
 #define QQ_SC_FN __host__ __device__ static inline
+#define QQ_SC_MEMBER __host__ __device__
 #else
 #define QQ_SC_FN static inline
+#define QQ_SC_MEMBER
 #endif
 #define QQ_SC_L_WORDS {0x5812631a5cf5d3edULL, 0x14def9dea2f79cd6ULL, 0ULL, 0x1000000000000000ULL}
 #define QQ_SC_MU_WORDS {0xed9ce5a30a2c131bULL, 0x2106215d086329a7ULL, 0xffffffffffffffebULL, 0xffffffffffffffffULL, 0xfULL}
@@ -22,8 +24,8 @@ typedef unsigned __int128 u128;
 
 struct sc {
     uint64_t v[4];
-    bool operator==(const sc& o) const { return v[0] == o.v[0] && v[1] == o.v[1] && v[2] == o.v[2] && v[3] == o.v[3]; }
-    bool operator!=(const sc& o) const { return !(*this == o); }
+    QQ_SC_MEMBER bool operator==(const sc& o) const { return v[0] == o.v[0] && v[1] == o.v[1] && v[2] == o.v[2] && v[3] == o.v[3]; }
+    QQ_SC_MEMBER bool operator!=(const sc& o) const { return !(*this == o); }
 };
 
 static const uint64_t L[4] = QQ_SC_L_WORDS;

@@ -396,7 +396,7 @@ struct Verifier {
     static TranscriptState keep_transcript() {
         TranscriptState s(qq_transcript_state_bytes());
         Gpu& g = Gpu::instance();
-        g.check(qq_transcript_capture(g.ctx(), s.data()), "keep_transcript");
+        g.check(qq_transcript_capture(g.ctx(), s.data(), 1), "keep_transcript");
         return s;
     }
     // verifier.rs:504-523: one aggregated 64-bit range proof (RangeProof::to_bytes()) over the d components of the accounts

@@ -10,6 +10,7 @@
 #include "../../quisquis-rust_b200/csrc/sc_host.hpp"
 #include "../../quisquis-rust_b200/csrc/keccak_host.hpp"
 #include "../../quisquis-rust_b200/csrc/merlin_host.hpp"
+#include "../../quisquis-rust_b200/csrc/shuffle_verify.cuh"
 
 using namespace qq;
 
@@ -305,5 +306,98 @@ void hh_merlin_script(uint8_t* out, const uint8_t* label, size_t label_len, cons
             tr.challenge_bytes(lab.c_str(), out, dl);
         }
     }
+}
+// One segmented MSM batch evaluated on the host with the device arithmetic (what decompress + k_straus + the encoder compute):
+// out[m] = enc(sum s_i dec(P_i)), status 2 for a non-canonical scalar, 1 for an undecodable point (output zeroed then).
+static void hh_segmented(const uint8_t* sc, const uint8_t* pt, const uint32_t* first, size_t msms, uint8_t* e, uint8_t* st) {
+    std::vector<u32x4> tbl(QQ_VB_ENTRIES * QQ_PT_Q);
+    for (size_t m = 0; m < msms; m++) {
+        ge_p3 acc;
+        ge_identity(acc);
+        uint8_t s = 0;
+        for (uint32_t t = first[m]; t < first[m + 1]; t++) {
+            u32 w[8], k[8];
+            load_words(w, pt + 32 * t);
+            load_words(k, sc + 32 * t);
+            ge_p3 P, R;
+            u32 ok = ristretto_decompress(P, w);
+            uint8_t ts = !sc_is_canonical(k) ? 2 : (ok ? 0 : 1);
+            s = (ts == 2 || s == 2) ? 2 : (s | ts);
+            if (ts) continue;
+            vb_build_table(tbl.data(), P);
+            vb_scalarmult(R, tbl.data(), k);
+            ge_cached c;
+            ge_to_cached(c, R);
+            ge_add(acc, acc, c);
+        }
+        u32 w[8];
+        ristretto_compress(w, acc);
+        store_words(e + 32 * m, w);
+        if (s) memset(e + 32 * m, 0, 32);
+        st[m] = s;
+    }
+}
+// ShuffleProof::verify through the per-proof phases of shuffle_verify.cuh (the code the transcript kernels run), MSM batches by
+// hh_segmented: checks the shared phase logic without a GPU.  xpc: H | G[0..3) of VectorPedersenGens::new(4); base_pk: B | H_p.
+void hh_shuffle_verify(const char* transcript_label, const char* verifier_label, const uint8_t* in, const uint8_t* out,
+                       const uint8_t* stm, const uint8_t* proof, size_t n, const uint8_t* base_pk, const uint8_t* xpc,
+                       uint8_t* status, uint8_t* stage, uint8_t* detail) {
+    using namespace qq_shuffle;
+    qq_merlin::transcript tr0((const uint8_t*)transcript_label, strlen(transcript_label));
+    tr0.domain_sep(verifier_label);
+    gens g{base_pk, base_pk + 32, xpc, xpc + 32};
+    const uint32_t sz1[QQ_SHUFFLE_MSMS_1] = {8, 8, 8, 8, 5, 5, 5, 3, 1, 7, 8, 9, 6, 5, 9, 9, 10, 10};
+    const uint32_t sz2[QQ_SHUFFLE_MSMS_2] = {8, 8, 8, 8, 8, 8, 9, 9, 8, 8, 8, 8, 8, 9};
+    for (size_t p = 0; p < n; p++) {
+        std::vector<uint8_t> sc1(QQ_SHUFFLE_TERMS_1 * 32, 0), pt1(QQ_SHUFFLE_TERMS_1 * 32), sc2(QQ_SHUFFLE_TERMS_2 * 32, 0), pt2(QQ_SHUFFLE_TERMS_2 * 32);
+        for (size_t t = 0; t < QQ_SHUFFLE_TERMS_1; t++) memcpy(&pt1[32 * t], base_pk, 32);
+        for (size_t t = 0; t < QQ_SHUFFLE_TERMS_2; t++) memcpy(&pt2[32 * t], base_pk, 32);
+        job_sink j1, j2;
+        j1.sc = sc1.data(); j1.pt = pt1.data(); j1.msms_pp = QQ_SHUFFLE_MSMS_1; j1.terms_pp = QQ_SHUFFLE_TERMS_1; j1.base = p;
+        j2.sc = sc2.data(); j2.pt = pt2.data(); j2.msms_pp = QQ_SHUFFLE_MSMS_2; j2.terms_pp = QQ_SHUFFLE_TERMS_2; j2.base = p;
+        uint32_t t = 0;
+        for (int m = 0; m < QQ_SHUFFLE_MSMS_1; m++) { j1.first[m] = t; t += sz1[m]; }
+        j1.first[QQ_SHUFFLE_MSMS_1] = t;
+        t = 0;
+        for (int m = 0; m < QQ_SHUFFLE_MSMS_2; m++) { j2.first[m] = t; t += sz2[m]; }
+        j2.first[QQ_SHUFFLE_MSMS_2] = t;
+        const uint8_t *pr = proof + QQ_SHUFFLE_PROOF_BYTES * p, *sm = stm + QQ_SHUFFLE_STATEMENT_BYTES * p;
+        proof_state S(tr0);
+        pass_a(S, j1, p, pr, sm, in + 1152 * p, g, nullptr);
+        uint8_t e1[QQ_SHUFFLE_MSMS_1 * 32], s1[QQ_SHUFFLE_MSMS_1], e2[QQ_SHUFFLE_MSMS_2 * 32], s2[QQ_SHUFFLE_MSMS_2];
+        hh_segmented(sc1.data(), pt1.data(), j1.first, QQ_SHUFFLE_MSMS_1, e1, s1);
+        pass_b(S, j2, p, pr, sm, in + 1152 * p, out + 1152 * p, e1, s1, g);
+        hh_segmented(sc2.data(), pt2.data(), j2.first, QQ_SHUFFLE_MSMS_2, e2, s2);
+        pass_final(S, pr, e2, s2);
+        status[p] = S.st;
+        stage[p] = S.sg;
+        detail[p] = S.dt;
+    }
+}
+size_t hh_transcript_state_bytes() { return qq_merlin::transcript::STATE_BYTES; }
+// export -> import round trip of a transcript state, then one more challenge from both; returns 1 when they agree and the
+// import rejects a corrupted tag / position
+int hh_transcript_state_roundtrip(const uint8_t* label, size_t label_len, uint8_t* state_out) {
+    qq_merlin::transcript a(label, label_len);
+    a.domain_sep("state-test");
+    uint8_t st[qq_merlin::transcript::STATE_BYTES];
+    a.export_state(st);
+    memcpy(state_out, st, sizeof st);
+    qq_merlin::transcript b((const uint8_t*)"other", 5);
+    if (!b.import_state(st)) return 0;
+    uint8_t ca[32], cb[32];
+    a.get_challenge("c", ca);
+    b.get_challenge("c", cb);
+    if (memcmp(ca, cb, 32)) return 0;
+    uint8_t bad[qq_merlin::transcript::STATE_BYTES];
+    memcpy(bad, st, sizeof st);
+    bad[203] = 0;
+    if (b.import_state(bad)) return 0;
+    memcpy(bad, st, sizeof st);
+    bad[200] = 166;
+    if (b.import_state(bad)) return 0;
+    memset(bad, 0, sizeof bad);
+    if (b.import_state(bad)) return 0;
+    return 1;
 }
 }

@@ -1299,6 +1299,33 @@ def test_shuffle_proof_verification(engine):
     assert int(other[0][0]) == 6 and int(other[1][0]) == 1
 
 
+def test_shuffle_verification_device_and_host_transcripts_agree(engine):
+    """qq_verify_set_transcripts: the per-proof phases in the transcript kernels (default) and on the host threads give the same
+    (status, stage, detail) on the 23 accept / reject cases and on 300 tiled golden proofs with tampered ones among them."""
+    import os
+    import shuffle_ref as F
+    cases = shuffle_cases(Stream(b"shuffle-gpu"))
+    blobs = [_shuffle_blobs(k[2], k[3]) for k in cases]
+    args = (cat([cat(k[0]) for k in cases]), cat([cat(k[1]) for k in cases]), cat([b[1] for b in blobs]), cat([b[0] for b in blobs]))
+    raw = np.fromfile(os.path.join(os.path.dirname(__file__), "golden", "shuffle_proofs.bin"), dtype=np.uint8).reshape(-1, 6432)
+    rec = np.tile(raw, (75, 1)).copy()
+    rng = np.random.default_rng(3)
+    for i in rng.choice(rec.shape[0], 40, replace=False):
+        rec[i, int(rng.integers(0, 6432))] ^= 1 << int(rng.integers(0, 8))
+    big = tuple(np.ascontiguousarray(rec[:, a:b]) for a, b in ((0, 1152), (1152, 2304), (2304, 2656), (2656, 6432)))
+    try:
+        dev = [engine.verify_shuffle(*args), engine.verify_shuffle(*big)]
+        engine.verify_set_transcripts(False)
+        host = [engine.verify_shuffle(*args), engine.verify_shuffle(*big)]
+    finally:
+        engine.verify_set_transcripts(True)
+    for d, h in zip(dev, host):
+        for a, b in zip(d, h):
+            assert a.tolist() == b.tolist()
+    assert dev[0][0][:2].tolist() == [0, 0] and all(dev[0][0][2:])
+    assert 0 < np.count_nonzero(dev[1][0]) <= 40
+
+
 def test_golden_shuffle_proofs_accepted(engine):
     """The committed proofs of tests/golden/shuffle_proofs.bin (made by the oracle's prover restatement) are accepted; the
     same proofs with one byte of an output account / of a response flipped are rejected."""

@@ -316,3 +316,54 @@ def test_host_keccak_and_merlin(hh):
         last = tr.challenge_bytes(b"final", k)
         got = run(label, ops)
         assert got[:k] == last, trial
+
+
+def test_shuffle_phases_shared_with_the_transcript_kernels(hh):
+    """The per-proof phases of the shuffle verifier (quisquis-rust_b200/csrc/shuffle_verify.cuh: pass A, pass B, final verdict
+    - the code k_shuffle_pass_a / _pass_b / _final run one GPU thread per proof) compiled for the host, MSM batches evaluated
+    with the host-compiled device arithmetic: the golden proofs are accepted, tampered ones rejected at the stage the oracle's
+    restatement of ShuffleProof::verify (src/shuffle/shuffle.rs:547-712) names.  Also the serialised transcript state."""
+    import numpy as np
+    import shuffle_ref as F
+    from qq_testlib import Stream, cat
+    from test_gpu_parity import _shuffle_blobs, _shuffle_code, shuffle_cases
+    h = hh
+    u8p = ctypes.c_char_p
+    h.hh_shuffle_verify.argtypes = [u8p, u8p, u8p, u8p, u8p, u8p, ctypes.c_size_t, u8p, u8p, u8p, u8p, u8p]
+    h.hh_transcript_state_bytes.restype = ctypes.c_size_t
+    xpc = F.XpcGens(4)
+    xpc_bytes = xpc.h + b"".join(xpc.g[:3])        # compressed H | G[0..3)
+    base_pk = R.BASEPOINT_COMPRESSED + R.PEDERSEN_H_COMPRESSED
+
+    def run(si, so, stm, pr, n, label=b"ShuffleProof"):
+        st, sg, dt = (ctypes.create_string_buffer(n) for _ in range(3))
+        h.hh_shuffle_verify(label, b"Shuffle", si, so, stm, pr, n, base_pk, xpc_bytes, st, sg, dt)
+        return list(st.raw), list(sg.raw), list(dt.raw)
+    raw = np.fromfile(os.path.join(HERE, "golden", "shuffle_proofs.bin"), dtype=np.uint8).reshape(-1, 6432)
+    n = raw.shape[0]
+    cols = lambda rec: tuple(np.ascontiguousarray(rec[:, a:b]).tobytes() for a, b in ((0, 1152), (1152, 2304), (2304, 2656), (2656, 6432)))  # noqa: E731
+    st, sg, dt = run(*cols(raw), n)
+    assert st == [0] * n and sg == [0] * n
+    bad = raw.copy()
+    bad[0, 1152 + 5] ^= 1                 # an output account
+    bad[1, 2656 + 3776 - 1 - 32] ^= 1     # top byte of the DDH challenge
+    bad[2, 2656 + 384 + 608] ^= 1         # Hadamard rho_bar
+    st, sg, dt = run(*cols(bad), n)
+    assert st[0] != 0 and st[1] != 0 and st[2] != 0 and st[3:] == [0] * (n - 3)
+    assert sg[2] == 1 and sg[1] == 6
+    # other label: the first challenge moves, the Hadamard argument rejects
+    st, sg, dt = run(*cols(raw[:1]), 1, label=b"Other")
+    assert (st[0], sg[0]) == (6, 1)
+    # the 23 accept / reject cases of the GPU parity test, against the oracle's verifier
+    cases = shuffle_cases(Stream(b"shuffle-gpu"))
+    expect = [_shuffle_code(F.shuffle_verify(F.new_transcript(b"ShuffleProof", b"Shuffle"), k[2], k[3], k[0], k[1], xpc)) for k in cases]
+    blobs = [_shuffle_blobs(k[2], k[3]) for k in cases]
+    st, sg, dt = run(b"".join(b"".join(k[0]) for k in cases), b"".join(b"".join(k[1]) for k in cases),
+                     b"".join(b[1] for b in blobs), b"".join(b[0] for b in blobs), len(cases))
+    for i, e in enumerate(expect):
+        assert (st[i], sg[i]) == e[:2] and (e[2] is None or dt[i] == e[2]), (i, e, (st[i], sg[i], dt[i]))
+    # serialised transcript state: round trip, corrupted tag / position refused
+    state = ctypes.create_string_buffer(h.hh_transcript_state_bytes())
+    assert h.hh_transcript_state_bytes() == 208
+    assert h.hh_transcript_state_roundtrip(b"abc", 3, state) == 1
+    assert state.raw[203] == 0xa5

@@ -22,18 +22,23 @@ def load(n):
 def main():
     pkg = g.load_package()
     eng = pkg.Engine(0)
-    for n in [int(x) for x in (sys.argv[1:] or ["1", "64", "4096"])]:
-        si, so, stm, pr = load(n)
-        ts = []
-        for rep in range(4):
-            t = time.perf_counter()
-            st, sg, det = eng.verify_shuffle(si, so, stm, pr)
-            ts.append(time.perf_counter() - t)
-        assert not st.any()
-        best = min(ts[1:])
-        print(json.dumps({"probe": "verify_shuffle", "proofs": n, "wall_ms": best * 1e3, "proofs_per_s": n / best,
-                          "last_batch_kernel_ms": eng.last_kernel_ms, "msms": 28 * n, "terms": 239 * n,
-                          "all_accepted": True}), flush=True)
+    import torch
+    for n in [int(x) for x in (sys.argv[1:] or ["1", "64", "512", "4096", "16384"])]:
+        # page-locked host buffers, as a caller that feeds serialized transactions would hold them
+        arrs = [torch.from_numpy(a).pin_memory().numpy() for a in load(n)]
+        for mode in ("device", "host"):
+            eng.verify_set_transcripts(mode == "device")
+            ts = []
+            for rep in range(5):
+                t = time.perf_counter()
+                st, sg, det = eng.verify_shuffle(*arrs)
+                ts.append(time.perf_counter() - t)
+            assert not st.any()
+            best = min(ts[1:])
+            print(json.dumps({"probe": "verify_shuffle", "transcripts": mode, "proofs": n, "wall_ms": best * 1e3,
+                              "proofs_per_s": n / best, "kernel_ms": eng.last_kernel_ms, "breakdown_ms": eng.last_kernel_breakdown(),
+                              "msms": 32 * n, "terms": 239 * n, "all_accepted": True}), flush=True)
+        eng.verify_set_transcripts(True)
     eng.close()
 
 
