@@ -358,6 +358,28 @@ size_t qq_transcript_state_bytes(void);
  * One-shot: ANY next entry point (whatever it returns) disarms it; NULL cancels. */
 int qq_transcript_capture(qq_ctx* ctx, uint8_t* states_out, size_t capacity_states);
 
+/* ---- wire format ---------------------------------------------------------------------------------
+ * bincode 1.x (Cargo.toml:29; default configuration: little endian, fixed-width integers, Vec = u64 length + elements, enum =
+ * u32 variant index) encodings of the reference's serde-derived types <-> the flattened layouts above, so that batches can be
+ * fed straight from serialised transactions.  Host-only helpers without a context.  QQ_ERR_ARG: truncated input, or a Vec
+ * whose length is not the one ShuffleProof::verify indexes (ROWS = COLUMNS = 3; the reference would panic / return Err).
+ * *consumed / *written (may be NULL) receive the number of bincode bytes read / needed.
+ *   ShuffleProof      src/shuffle/shuffle.rs:164-184 (+ hadamard.rs:34-57, product.rs:39-92, singlevalueproduct.rs:33-48,
+ *                     multiexponential.rs:37-56, ddh.rs:27-32): 3 920 B each -> 3 776 B each
+ *   ShuffleStatement  src/shuffle/shuffle.rs:153-161: 360 B each -> 352 B each */
+int qq_shuffle_proofs_from_bincode(const uint8_t* in, size_t in_len, size_t nproofs, uint8_t* out_proofs, size_t* consumed);
+int qq_shuffle_statements_from_bincode(const uint8_t* in, size_t in_len, size_t nproofs, uint8_t* out_statements, size_t* consumed);
+int qq_shuffle_proofs_to_bincode(const uint8_t* proofs, size_t nproofs, uint8_t* out, size_t out_cap, size_t* written);
+int qq_shuffle_statements_to_bincode(const uint8_t* statements, size_t nproofs, uint8_t* out, size_t out_cap, size_t* written);
+/* Vec<Account> (src/accounts/accounts.rs:47-53; e.g. the shuffle's input / output account lists): u64 length + 128 B per
+ * account.  *n_accounts is set even when cap_accounts is too small (QQ_ERR_ARG then). */
+int qq_accounts_from_bincode(const uint8_t* in, size_t in_len, uint8_t* out_accounts, size_t cap_accounts, size_t* n_accounts,
+                             size_t* consumed);
+/* SigmaProof (src/accounts/prover.rs:20-26): *variant 0 = Dlog(z, x), lens[0] = |z|; 1 = Dleq(zv, zr1, zr2, x), lens[0..3).
+ * out_scalars receives the vectors back to back (at most cap_scalars entries of 32 B), out_x the challenge. */
+int qq_sigma_proof_from_bincode(const uint8_t* in, size_t in_len, int* variant, uint8_t* out_scalars, size_t cap_scalars,
+                                size_t lens[3], uint8_t out_x[32], size_t* consumed);
+
 /* ---- decommit ------------------------------------------------------------------------------------------------------
  * ElGamalCommitment::decommit(sk) = enc(d - sk*c) = enc(v*B)                    src/elgamal/elgamal.rs:106-108 */
 int qq_decommit_batch(qq_ctx* ctx, const uint8_t* comm, const uint8_t* sk, uint8_t* out_points, uint8_t* status, size_t n);

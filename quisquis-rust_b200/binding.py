@@ -28,6 +28,8 @@ EXPORTS = [
     "qq_verify_update_account_dlog_batch", "qq_verify_delta_compact_batch", "qq_decommit_batch", "qq_decommit_value_batch", "qq_from_uniform_bytes_batch", "qq_vector_pedersen_gens", "qq_bulletproof_gens",
     "qq_verify_range_proof_batch", "qq_transcript_state_bytes", "qq_transcript_capture", "qq_msm_set_overlap",
     "qq_verify_set_transcripts",
+    "qq_shuffle_proofs_from_bincode", "qq_shuffle_statements_from_bincode", "qq_shuffle_proofs_to_bincode",
+    "qq_shuffle_statements_to_bincode", "qq_accounts_from_bincode", "qq_sigma_proof_from_bincode",
 ]
 
 
@@ -117,6 +119,13 @@ def load_library():
     lib.qq_transcript_state_bytes.restype = ctypes.c_size_t
     lib.qq_transcript_capture.argtypes = [vp, u8p, ctypes.c_size_t]
     lib.qq_verify_set_transcripts.argtypes = [vp, ctypes.c_int]
+    szp = ctypes.POINTER(ctypes.c_size_t)
+    lib.qq_shuffle_proofs_from_bincode.argtypes = [u8p, sz, sz, u8p, szp]
+    lib.qq_shuffle_statements_from_bincode.argtypes = [u8p, sz, sz, u8p, szp]
+    lib.qq_shuffle_proofs_to_bincode.argtypes = [u8p, sz, u8p, sz, szp]
+    lib.qq_shuffle_statements_to_bincode.argtypes = [u8p, sz, u8p, sz, szp]
+    lib.qq_accounts_from_bincode.argtypes = [u8p, sz, u8p, sz, szp, szp]
+    lib.qq_sigma_proof_from_bincode.argtypes = [u8p, sz, ctypes.POINTER(ctypes.c_int), u8p, sz, szp, u8p, szp]
     lib.qq_msm_set_overlap.argtypes = [vp, ctypes.c_long, ctypes.c_int, ctypes.c_int]
     lib.qq_msm_points_free.argtypes = [vp, vp]
     lib.qq_msm_points_free.restype = None
@@ -144,6 +153,80 @@ def _u8(a, nbytes=None):
 
 def _ptr(a):
     return ctypes.c_void_p(a.ctypes.data)
+
+
+# ---- wire format (host-only helpers of the library; no GPU context) ------------------------------------------------------
+def shuffle_proofs_from_bincode(data, nproofs):
+    """bincode(ShuffleProof) x nproofs, back to back -> (nproofs x 3776 flattened bytes, bytes consumed); ValueError when malformed."""
+    lib = load_library()
+    d = _u8(data)
+    out = np.zeros(nproofs * 3776, np.uint8)
+    used = ctypes.c_size_t()
+    if lib.qq_shuffle_proofs_from_bincode(_ptr(d), d.size, nproofs, _ptr(out), ctypes.byref(used)) != QQ_OK:
+        raise ValueError("malformed bincode ShuffleProof")
+    return out.reshape(nproofs, 3776), used.value
+
+
+def shuffle_statements_from_bincode(data, nproofs):
+    lib = load_library()
+    d = _u8(data)
+    out = np.zeros(nproofs * 352, np.uint8)
+    used = ctypes.c_size_t()
+    if lib.qq_shuffle_statements_from_bincode(_ptr(d), d.size, nproofs, _ptr(out), ctypes.byref(used)) != QQ_OK:
+        raise ValueError("malformed bincode ShuffleStatement")
+    return out.reshape(nproofs, 352), used.value
+
+
+def shuffle_proofs_to_bincode(proofs):
+    lib = load_library()
+    p = _u8(proofs)
+    n = p.size // 3776
+    out = np.zeros(n * 3920, np.uint8)
+    wr = ctypes.c_size_t()
+    if lib.qq_shuffle_proofs_to_bincode(_ptr(p), n, _ptr(out), out.size, ctypes.byref(wr)) != QQ_OK or wr.value != out.size:
+        raise ValueError("qq_shuffle_proofs_to_bincode")
+    return out
+
+
+def shuffle_statements_to_bincode(statements):
+    lib = load_library()
+    p = _u8(statements)
+    n = p.size // 352
+    out = np.zeros(n * 360, np.uint8)
+    wr = ctypes.c_size_t()
+    if lib.qq_shuffle_statements_to_bincode(_ptr(p), n, _ptr(out), out.size, ctypes.byref(wr)) != QQ_OK or wr.value != out.size:
+        raise ValueError("qq_shuffle_statements_to_bincode")
+    return out
+
+
+def accounts_from_bincode(data):
+    """bincode(Vec<Account>) -> (n x 128 bytes, bytes consumed)"""
+    lib = load_library()
+    d = _u8(data)
+    cap = max(d.size // 128, 1)
+    out = np.zeros(cap * 128, np.uint8)
+    n, used = ctypes.c_size_t(), ctypes.c_size_t()
+    if lib.qq_accounts_from_bincode(_ptr(d), d.size, _ptr(out), cap, ctypes.byref(n), ctypes.byref(used)) != QQ_OK:
+        raise ValueError("malformed bincode Vec<Account>")
+    return out[:n.value * 128].reshape(n.value, 128), used.value
+
+
+def sigma_proof_from_bincode(data):
+    """bincode(SigmaProof) -> ("dlog", [z], x) or ("dleq", [zv, zr1, zr2], x) with the vectors as (k x 32) byte arrays."""
+    lib = load_library()
+    d = _u8(data)
+    cap = max(d.size // 32, 1)
+    out = np.zeros(cap * 32, np.uint8)
+    lens = (ctypes.c_size_t * 3)()
+    variant, used = ctypes.c_int(), ctypes.c_size_t()
+    x = np.zeros(32, np.uint8)
+    if lib.qq_sigma_proof_from_bincode(_ptr(d), d.size, ctypes.byref(variant), _ptr(out), cap, lens, _ptr(x), ctypes.byref(used)) != QQ_OK:
+        raise ValueError("malformed bincode SigmaProof")
+    vecs, o = [], 0
+    for k in range(1 if variant.value == 0 else 3):
+        vecs.append(out[32 * o:32 * (o + lens[k])].reshape(lens[k], 32).copy())
+        o += lens[k]
+    return ("dlog" if variant.value == 0 else "dleq"), vecs, x, used.value
 
 
 class Engine:
