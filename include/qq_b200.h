@@ -322,6 +322,13 @@ int qq_verify_shuffle_batch(qq_ctx* ctx, const char* transcript_label, const cha
  * upload, job lists, transcripts and verdicts stay in device memory; on_device == 0 on the host threads, job lists uploaded
  * per batch (the round-1 arrangement, kept for A/B measurements).  Verdicts are identical. */
 int qq_verify_set_transcripts(qq_ctx* ctx, int on_device);
+/* Aggregate form of the device-resident shuffle verifier (default on).  on: per proof only G, H, g_r, h_r (the MSM results
+ * the transcript absorbs) are evaluated on their own; the other 28 group equations of every proof are multiplied by fresh
+ * random 128-bit weights in the transcript kernels and decided together by ONE Pippenger MSM over the whole batch (146 terms
+ * per proof + the six fixed generators).  Proofs that fail a scalar-level check, and the whole batch when the aggregate is
+ * not the identity, are verified in the exact form (on == 0: every equation an MSM of its own), which alone reports
+ * (status, stage, detail); an invalid proof is accepted with probability <= 2^-128.  Verdicts of valid proofs are identical. */
+int qq_verify_set_aggregation(qq_ctx* ctx, int on);
 
 /* ---- Bulletproofs range proofs (BASELINE configs[3]) -----------------------------------------------------------------
  * RangeProof::verify_multiple / verify_single of the `bulletproofs` crate, as called by

@@ -27,7 +27,7 @@ EXPORTS = [
     "qq_verify_same_value_compact_batch", "qq_verify_update_account_dark_tx_batch",
     "qq_verify_update_account_dlog_batch", "qq_verify_delta_compact_batch", "qq_decommit_batch", "qq_decommit_value_batch", "qq_from_uniform_bytes_batch", "qq_vector_pedersen_gens", "qq_bulletproof_gens",
     "qq_verify_range_proof_batch", "qq_transcript_state_bytes", "qq_transcript_capture", "qq_msm_set_overlap",
-    "qq_verify_set_transcripts",
+    "qq_verify_set_transcripts", "qq_verify_set_aggregation",
     "qq_shuffle_proofs_from_bincode", "qq_shuffle_statements_from_bincode", "qq_shuffle_proofs_to_bincode",
     "qq_shuffle_statements_to_bincode", "qq_accounts_from_bincode", "qq_sigma_proof_from_bincode",
 ]
@@ -119,6 +119,7 @@ def load_library():
     lib.qq_transcript_state_bytes.restype = ctypes.c_size_t
     lib.qq_transcript_capture.argtypes = [vp, u8p, ctypes.c_size_t]
     lib.qq_verify_set_transcripts.argtypes = [vp, ctypes.c_int]
+    lib.qq_verify_set_aggregation.argtypes = [vp, ctypes.c_int]
     szp = ctypes.POINTER(ctypes.c_size_t)
     lib.qq_shuffle_proofs_from_bincode.argtypes = [u8p, sz, sz, u8p, szp]
     lib.qq_shuffle_statements_from_bincode.argtypes = [u8p, sz, sz, u8p, szp]
@@ -580,6 +581,10 @@ class Engine:
     def verify_set_transcripts(self, on_device=True):
         """Shuffle verifier: per-proof transcripts / scalar algebra in GPU transcript kernels (default) or on the host threads."""
         self._ck(self.lib.qq_verify_set_transcripts(self.h, 1 if on_device else 0), "qq_verify_set_transcripts")
+
+    def verify_set_aggregation(self, on=True):
+        """Shuffle verifier: identity equations of all proofs in one weighted Pippenger MSM (default) or one MSM per equation."""
+        self._ck(self.lib.qq_verify_set_aggregation(self.h, 1 if on else 0), "qq_verify_set_aggregation")
 
     def msm_set_overlap(self, split_min=1 << 17, tail_pct=30, sort_blocks_per_sm=3):
         """Large-MSM tuning (decompression of the last tail_pct % of the points under the counting sort); tail_pct 0 = off."""

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <random>
 #include <deque>
 #include <condition_variable>
 #include <memory>
@@ -121,6 +122,7 @@ struct qq_ctx {
     bool stc_ready = false;                    // k_straus_coop's shared-memory opt-in done
     int straus_minb = 4;                       // k_straus build for more than one wave of instances (QQ_STRAUS_MINB)
     int stc_per_sm = 64;                       // segmented MSMs: four-lane cooperative kernel up to this many MSMs per SM (QQ_STRAUS_COOP_PER_SM)
+    bool verify_aggregate = true;              // qq_verify_set_aggregation: identity equations of the shuffle proofs in one weighted Pippenger MSM
     bool verify_host_transcripts = false;      // qq_verify_set_transcripts(ctx, 0): per-proof phases of the shuffle verifier on the host threads
     uint8_t* d_shuffle_gens = nullptr;         // B | B_blinding | H | G[0..3) of VectorPedersenGens::new(4), device copy for the transcript kernels
     long vbc_max_jobs = -1;                    // four-lane cooperative variable base up to this many scalar mults (< 0: sms * 160)
@@ -550,6 +552,7 @@ extern "C" int qq_init(qq_ctx** out, int device) {
             if (const char* e = getenv("QQ_MSM_TAIL_PCT")) ctx->msm_tail_pct = atoi(e);
             if (const char* e = getenv("QQ_MSM_SORT_BPSM")) ctx->msm_sort_bpsm = atoi(e);
             if (const char* e = getenv("QQ_VERIFY_HOST_TRANSCRIPTS")) ctx->verify_host_transcripts = atoi(e) != 0;
+            if (const char* e = getenv("QQ_VERIFY_AGGREGATE")) ctx->verify_aggregate = atoi(e) != 0;
         }
         for (int i = 0; i < 8; i++) CK(cudaEventCreateWithFlags(&ctx->msm_ev[i], cudaEventDisableTiming));
         CK(cudaFuncSetAttribute(k_msm_sum_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * QQ_PT_BYTES));

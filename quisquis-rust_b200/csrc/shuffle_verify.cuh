@@ -45,34 +45,101 @@ struct gens {
 
 // Where one batch's MSM jobs go: every proof owns the same slots (MSM m = terms first[m] .. first[m + 1] - 1 of its
 // terms_pp), proof-major; sc / pt are host or device arrays of 32-byte entries.
+//
+// Aggregate mode (agg != nullptr; qq_verify_shuffle_batch's fast path): only the MSMs whose RESULT is needed (G, H, g_r,
+// h_r: they enter the transcript) keep a slot of their own - exact_slot[m] >= 0 names it in the (then smaller) sc / pt list.
+// Every other MSM is an equation "sum == identity": its terms are multiplied by the random 128-bit weight w[m] of that check
+// and appended to the proof's segment of ONE aggregated term list (asc / apt, cap entries per proof) that a single Pippenger
+// MSM over all proofs evaluates; terms on the six fixed generators are summed into fixed[] instead (one term per generator
+// for the whole batch).  Slots in skip_mask are not emitted (decode-only checks: their points occur in other equations).
 #define QQ_JOB_MAX_MSMS 20
+struct agg_ctx {                // per proof, lives in the frame of the phase that emits
+    qq_sc::sc w[QQ_JOB_MAX_MSMS];
+    qq_sc::sc fixed[6];         // B, Hp, H, G[0], G[1], G[2]
+    uint32_t k;                 // next entry of the proof's segment
+    uint32_t skip_mask;
+    bool overflow;
+};
 struct job_sink {
     uint8_t *sc, *pt;
     uint32_t first[QQ_JOB_MAX_MSMS + 1];
     uint32_t msms_pp, terms_pp;
     size_t base;      // global index of the first proof of this batch (slices of a larger call)
-    QQ_HOSTDEV void set(size_t p, size_t m, size_t t, const qq_sc::sc& s, const uint8_t* point) const {
-        size_t i = (p - base) * terms_pp + first[m] + t;
+    // aggregate mode
+    agg_ctx* agg;
+    uint8_t *asc, *apt;
+    uint32_t cap;
+    int8_t exact_slot[QQ_JOB_MAX_MSMS];
+    const uint8_t *fB, *fHp, *fH, *fG;      // the fixed generators' addresses (gens), compared by pointer
+    QQ_HOSTDEV static void put(uint8_t* sc_arr, uint8_t* pt_arr, size_t i, const qq_sc::sc& s, const uint8_t* point) {
 #ifdef __CUDA_ARCH__
         // the job arrays are 32-byte aligned device buffers; so are the points of the uploaded proofs (every struct size
         // is a multiple of 32) - the generators and MSM outputs as well.  16-byte accesses instead of 64 byte moves.
-        uint4* ds = reinterpret_cast<uint4*>(&sc[32 * i]);
+        uint4* ds = reinterpret_cast<uint4*>(&sc_arr[32 * i]);
         ds[0] = make_uint4((uint32_t)s.v[0], (uint32_t)(s.v[0] >> 32), (uint32_t)s.v[1], (uint32_t)(s.v[1] >> 32));
         ds[1] = make_uint4((uint32_t)s.v[2], (uint32_t)(s.v[2] >> 32), (uint32_t)s.v[3], (uint32_t)(s.v[3] >> 32));
-        uint4* dp = reinterpret_cast<uint4*>(&pt[32 * i]);
+        uint4* dp = reinterpret_cast<uint4*>(&pt_arr[32 * i]);
         if ((reinterpret_cast<uintptr_t>(point) & 15) == 0) {
             const uint4* sp = reinterpret_cast<const uint4*>(point);
             dp[0] = sp[0];
             dp[1] = sp[1];
         } else {
-            memcpy(&pt[32 * i], point, 32);
+            memcpy(&pt_arr[32 * i], point, 32);
         }
 #else
-        qq_sc::to_bytes(&sc[32 * i], s);
-        memcpy(&pt[32 * i], point, 32);
+        qq_sc::to_bytes(&sc_arr[32 * i], s);
+        memcpy(&pt_arr[32 * i], point, 32);
 #endif
     }
+    QQ_HOSTDEV void set(size_t p, size_t m, size_t t, const qq_sc::sc& s, const uint8_t* point) const {
+        if (agg == nullptr) {
+            put(sc, pt, (p - base) * terms_pp + first[m] + t, s, point);
+            return;
+        }
+        if (exact_slot[m] >= 0) {
+            put(sc, pt, (p - base) * terms_pp + first[exact_slot[m]] + t, s, point);
+            return;
+        }
+        if ((agg->skip_mask >> m) & 1u) return;
+        qq_sc::sc ws = qq_sc::mul(agg->w[m], s);
+        int f = point == fB ? 0 : point == fHp ? 1 : point == fH ? 2 : (point == fG ? 3 : point == fG + 32 ? 4 : point == fG + 64 ? 5 : -1);
+        if (f >= 0) {
+            agg->fixed[f] = qq_sc::add(agg->fixed[f], ws);
+            return;
+        }
+        if (agg->k >= cap) {
+            agg->overflow = true;
+            return;
+        }
+        put(asc, apt, (p - base) * cap + agg->k, ws, point);
+        agg->k++;
+    }
 };
+#define QQ_SHUFFLE_AGG_CAP_1 44      // aggregated (non-fixed) terms of a proof that passes every scalar check: batch 1
+#define QQ_SHUFFLE_AGG_CAP_2 102     // and batch 2
+
+// 128-bit weights of the aggregated checks: Keccak-f over (fresh 32-byte entropy of this call, proof index, batch tag,
+// counter) - unpredictable to whoever made the proofs, which is all a random linear combination needs.
+QQ_HOSTDEV static inline void agg_weights(qq_sc::sc* w, int n, const uint8_t entropy[32], uint64_t p, uint64_t tag) {
+    int got = 0;
+    for (uint64_t ctr = 0; got < n; ctr++) {
+        uint64_t st[25];
+        for (int i = 0; i < 25; i++) st[i] = 0;
+        memcpy(st, entropy, 32);
+        st[4] = p;
+        st[5] = tag;
+        st[6] = ctr;
+        st[7] = 0x71715f6232303061ULL;      // "qq_b200a": domain tag of this generator
+        qq_keccak::f1600(st);
+        for (int i = 0; i + 1 < 24 && got < n; i += 2) {
+            w[got].v[0] = st[i] | 1ULL;      // never zero
+            w[got].v[1] = st[i + 1];
+            w[got].v[2] = 0;
+            w[got].v[3] = 0;
+            got++;
+        }
+    }
+}
 
 QQ_HOSTDEV static inline bool is_zero32(const uint8_t* p) {
     uint8_t acc = 0;
@@ -352,11 +419,14 @@ struct proof_state {
     sc expx[9];                 // x, x^2, .. x^9
     uint8_t had_pre, had_det, prod_pre, prod_det, svp_pre, b_ok, pk_pre, cm_pre;
     uint8_t st, sg, dt;         // verdict so far: status, stage, detail (sg == 0: undecided)
-    uint8_t pad[5];
+    uint8_t clean;              // aggregate mode: 1 = every scalar check passed and the proof's equations are in the aggregate
+    uint8_t pad[4];
+    sc fixed[6];                // aggregate mode: this proof's scalars on the fixed generators (both batches)
     QQ_HOSTDEV explicit proof_state(const qq_merlin::transcript& t0)
-        : tr(t0), had_pre(0), had_det(0), prod_pre(0), prod_det(0), svp_pre(0), b_ok(0), pk_pre(0), cm_pre(0), st(QQ_ST_OK), sg(0), dt(0) {
+        : tr(t0), had_pre(0), had_det(0), prod_pre(0), prod_det(0), svp_pre(0), b_ok(0), pk_pre(0), cm_pre(0), st(QQ_ST_OK), sg(0), dt(0), clean(0) {
         for (int i = 0; i < 9; i++) expx[i] = qq_sc::zero();
-        for (int i = 0; i < 5; i++) pad[i] = 0;
+        for (int i = 0; i < 4; i++) pad[i] = 0;
+        for (int i = 0; i < 6; i++) fixed[i] = qq_sc::zero();
     }
     QQ_HOSTDEV void fail(uint8_t s, uint8_t stage, uint8_t detail) {
         st = s;
@@ -405,6 +475,9 @@ QQ_HOSTDEV static inline void pass_a(proof_state& S, const job_sink& j1, size_t 
         j1.set(p, 4 + i, 0, y, cA + 32 * i);
         j1.set(p, 4 + i, 1, one(), cB + 32 * i);
         for (int k = 0; k < 3; k++) j1.set(p, 4 + i, 2 + k, nz, g.G + 32 * k);
+        // aggregate mode: c_E_i == the product argument's c_B_1 / zero_statement.c_A (MultiHadamardProof::verify's first check)
+        // as an equation: c_E_i - dec(those bytes) == identity
+        if (j1.agg) j1.set(p, 4 + i, 5, neg(one()), i == 0 ? pr + 1024 : stm + 96 + 32 * i);
     }
     product_phase(tr, pr + 1024, stm + 96, nullptr, g, j1, p, 7, S.prod_pre, S.prod_det, S.svp_pre);
     // G, H = sum x^i pk_i;  g_r = z G + c G_dash, h_r = z H + c H_dash with G, H expanded over the keys
@@ -426,35 +499,49 @@ QQ_HOSTDEV static inline void pass_a(proof_state& S, const job_sink& j1, size_t 
 
 // pass B: verdicts of batch 1 (e: 18 x 32 B encodings, s: 18 status bytes); DDH transcript (absorbs G, H, g_r, h_r) and
 // challenge check; transcripts of the two multi-exponentiation arguments; the 14 MSMs of batch 2.
-QQ_HOSTDEV static inline void pass_b(proof_state& S, const job_sink& j2, size_t p, const uint8_t* pr, const uint8_t* stm,
-                                     const uint8_t* in, const uint8_t* out, const uint8_t* e, const uint8_t* s, const gens& g) {
+// eG / sG: encodings and status bytes of G, H, g_r, h_r (= e + 32 * 14, s + 14 in the exact form).
+// Aggregate mode (j2.agg): e / s are not read (the other 14 MSMs of batch 1 are equations inside the aggregate); the proof
+// is `clean` when every check that does not need a group result passed and both multi-exponentiation arguments were
+// emitted - anything else leaves the verdict to the exact form.  Returns clean (always false in the exact form).
+QQ_HOSTDEV static inline bool pass_b(proof_state& S, const job_sink& j2, size_t p, const uint8_t* pr, const uint8_t* stm,
+                                     const uint8_t* in, const uint8_t* out, const uint8_t* e, const uint8_t* s, const uint8_t* eG,
+                                     const uint8_t* sG, const gens& g) {
     using namespace qq_sc;
+    const bool aggregate = j2.agg != nullptr;
     uint8_t vs, vd;
-    hadamard_verdict(S.had_pre, S.had_det, s, e, vs, vd);
-    if (vs != QQ_ST_OK) return S.fail(vs, 1, vd);
-    if (!S.b_ok) return S.fail(QQ_ST_PROOF, 2, 0);
-    if (s[4] || s[5] || s[6]) return S.fail(QQ_ST_BAD_POINT, 3, 0);
-    {   // MultiHadamardProof::verify's first check against the computed c_E
-        const uint8_t *cBp = pr + 1024, *zA = stm + 96 + 32;
-        if (S.prod_pre != QQ_ST_BAD_SCALAR && (differ32(e + 32 * 4, cBp) || differ32(e + 32 * 5, zA) || differ32(e + 32 * 6, zA + 32)))
-            return S.fail(QQ_ST_PROOF, 4, 1);
+    if (aggregate) {
+        if (S.had_pre != QQ_ST_OK || !S.b_ok || S.prod_pre != QQ_ST_OK || S.svp_pre != QQ_ST_OK) return false;
+        if (sG[0] || sG[1] || sG[2] || sG[3]) return false;
+    } else {
+        hadamard_verdict(S.had_pre, S.had_det, s, e, vs, vd);
+        if (vs != QQ_ST_OK) return S.fail(vs, 1, vd), false;
+        if (!S.b_ok) return S.fail(QQ_ST_PROOF, 2, 0), false;
+        if (s[4] || s[5] || s[6]) return S.fail(QQ_ST_BAD_POINT, 3, 0), false;
+        {   // MultiHadamardProof::verify's first check against the computed c_E
+            const uint8_t *cBp = pr + 1024, *zA = stm + 96 + 32;
+            if (S.prod_pre != QQ_ST_BAD_SCALAR && (differ32(e + 32 * 4, cBp) || differ32(e + 32 * 5, zA) || differ32(e + 32 * 6, zA + 32)))
+                return S.fail(QQ_ST_PROOF, 4, 1), false;
+        }
+        product_verdict(S.prod_pre, S.prod_det, S.svp_pre, s + 7, e + 32 * 7, vs, vd);
+        if (vs != QQ_ST_OK) return S.fail(vs, 4, vd), false;
+        if (sG[0] || sG[1]) return S.fail(QQ_ST_BAD_POINT, 5, 0), false;
+        if (sG[2] || sG[3]) return S.fail(sG[2] == QQ_ST_BAD_SCALAR || sG[3] == QQ_ST_BAD_SCALAR ? QQ_ST_BAD_SCALAR : QQ_ST_BAD_POINT, 6, 0), false;
     }
-    product_verdict(S.prod_pre, S.prod_det, S.svp_pre, s + 7, e + 32 * 7, vs, vd);
-    if (vs != QQ_ST_OK) return S.fail(vs, 4, vd);
-    if (s[14] || s[15]) return S.fail(QQ_ST_BAD_POINT, 5, 0);
-    if (s[16] || s[17]) return S.fail(s[16] == QQ_ST_BAD_SCALAR || s[17] == QQ_ST_BAD_SCALAR ? QQ_ST_BAD_SCALAR : QQ_ST_BAD_POINT, 6, 0);
-    const uint8_t *Gc = e + 32 * 14, *Hc = e + 32 * 15;
+    const uint8_t *Gc = eG, *Hc = eG + 32;
     qq_merlin::transcript& tr = S.tr;
     tr.domain_sep("DDHTupleProof");
     tr.append_point_var("g", Gc);
     tr.append_point_var("g_dash", stm + 288);
     tr.append_point_var("h", Hc);
     tr.append_point_var("h_dash", stm + 320);
-    tr.append_point_var("gr", e + 32 * 16);
-    tr.append_point_var("hr", e + 32 * 17);
+    tr.append_point_var("gr", eG + 64);
+    tr.append_point_var("hr", eG + 96);
     uint8_t chal[32];
     tr.get_challenge("Challenge", chal);
-    if (differ32(chal, pr + 3712)) return S.fail(QQ_ST_PROOF, 6, 0);
+    if (differ32(chal, pr + 3712)) {
+        if (!aggregate) S.fail(QQ_ST_PROOF, 6, 0);
+        return false;
+    }
     // ---- pubkey argument (c_A = c_B_dash, base_pk = (B, H_pedersen), pk_GH = (G, H)), then the commitment argument
     const sc* ex = S.expx;
     for (int which = 0; which < 2; which++) {
@@ -465,15 +552,15 @@ QQ_HOSTDEV static inline void pass_b(proof_state& S, const job_sink& j2, size_t 
         for (int i = 0; i < 3; i++) canon = canon && from_bytes(av[i], mp + 608 + 32 * i);
         if (!canon) {
             pre = 100;      // non-canonical scalar
-            return;
+            return false;
         }
         if (!is_zero32(mp + 32 + 32 * 3)) {
             pre = 1;
-            return;
+            return false;
         }
         if (which == 0 && (differ32(Gc, mp + 224 + 96) || differ32(Hc, mp + 416 + 96))) {
             pre = 2;
-            return;
+            return false;
         }
         sc xe[6];
         size_t m0 = 0;
@@ -481,6 +568,10 @@ QQ_HOSTDEV static inline void pass_b(proof_state& S, const job_sink& j2, size_t 
             for (int i = 0; i < 9; i++) {
                 j2.set(p, 6, i, ex[i], in + 128 * i + 64);
                 j2.set(p, 7, i, ex[i], in + 128 * i + 96);
+            }
+            if (aggregate) {      // C_c == E_k_0[3], C_d == E_k_1[3] ("Verify Em == C") as equations
+                j2.set(p, 6, 9, neg(one()), mp + 224 + 96);
+                j2.set(p, 7, 9, neg(one()), mp + 416 + 96);
             }
             m0 = 8;
         }
@@ -499,6 +590,40 @@ QQ_HOSTDEV static inline void pass_b(proof_state& S, const job_sink& j2, size_t 
             ek_set(j2, p, 12, 16, neg(t), Hc);
         }
     }
+    return aggregate;
+}
+
+// Aggregate mode: sinks and weights of the two passes.  Batch 1: slots 14..17 (G, H, g_r, h_r) are exact MSMs 0..3 of the
+// exact list {9, 9, 10, 10}; slot 7 (c_B decodes) is skipped (the same points carry scalars in slot 10); 13 weights.
+// Batch 2: no exact slots; the right half of an E_K pair carries minus the weight of the left half (ek_set negated its
+// terms for the enc(left) == enc(right) comparison of the exact form); 10 weights.
+QQ_HOSTDEV static inline void agg_begin_a(agg_ctx& a, const uint8_t entropy[32], size_t p) {
+    sc w[13];
+    agg_weights(w, 13, entropy, (uint64_t)p, 1);
+    int k = 0;
+    for (int m = 0; m < QQ_JOB_MAX_MSMS; m++) a.w[m] = qq_sc::zero();
+    for (int m = 0; m < 14; m++)
+        if (m != 7) a.w[m] = w[k++];
+    for (int i = 0; i < 6; i++) a.fixed[i] = qq_sc::zero();
+    a.k = 0;
+    a.skip_mask = 1u << 7;
+    a.overflow = false;
+}
+QQ_HOSTDEV static inline void agg_begin_b(agg_ctx& a, const uint8_t entropy[32], size_t p) {
+    sc w[10];
+    agg_weights(w, 10, entropy, (uint64_t)p, 2);
+    for (int m = 0; m < QQ_JOB_MAX_MSMS; m++) a.w[m] = qq_sc::zero();
+    const int single[6] = {0, 1, 6, 7, 8, 9}, pair[4] = {2, 4, 10, 12};
+    int k = 0;
+    for (int i = 0; i < 6; i++) a.w[single[i]] = w[k++];
+    for (int i = 0; i < 4; i++) {
+        a.w[pair[i]] = w[k++];
+        a.w[pair[i] + 1] = qq_sc::neg(a.w[pair[i]]);
+    }
+    for (int i = 0; i < 6; i++) a.fixed[i] = qq_sc::zero();
+    a.k = 0;
+    a.skip_mask = 0;
+    a.overflow = false;
 }
 
 // final verdict from batch 2 (e: 14 x 32 B encodings, s: 14 status bytes); no-op when an earlier phase decided
@@ -573,8 +698,9 @@ __global__ void __launch_bounds__(32) k_shuffle_pass_b(dev_inputs d, gens g, job
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= d.nproofs) return;
     proof_state S = states[p];
+    const uint8_t *e = e1 + 32 * QQ_SHUFFLE_MSMS_1 * p, *s = s1 + QQ_SHUFFLE_MSMS_1 * p;
     pass_b(S, j2, p, d.proof + QQ_SHUFFLE_PROOF_BYTES * p, d.stm + QQ_SHUFFLE_STATEMENT_BYTES * p, d.in + 9 * 128 * p,
-           d.out + 9 * 128 * p, e1 + 32 * QQ_SHUFFLE_MSMS_1 * p, s1 + QQ_SHUFFLE_MSMS_1 * p, g);
+           d.out + 9 * 128 * p, e, s, e + 32 * 14, s + 14, g);
     states[p] = S;
 }
 // verdict bytes: out3 = status[nproofs] | stage[nproofs] | detail[nproofs]
@@ -587,6 +713,83 @@ __global__ void __launch_bounds__(32) k_shuffle_final(dev_inputs d, proof_state*
     out3[p] = S.st;
     out3[d.nproofs + p] = S.sg;
     out3[2 * d.nproofs + p] = S.dt;
+}
+
+
+// ---- aggregate mode --------------------------------------------------------------------------------------------------
+struct entropy32 {
+    uint8_t b[32];
+};
+// n MSM terms = 0 * B
+__global__ void k_shuffle_terms_clear(uint8_t* __restrict__ sc, uint8_t* __restrict__ pt, size_t n, const uint8_t* __restrict__ B) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    uint4 b0 = reinterpret_cast<const uint4*>(B)[0], b1 = reinterpret_cast<const uint4*>(B)[1];
+    uint4 z = make_uint4(0, 0, 0, 0);
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+        reinterpret_cast<uint4*>(sc)[2 * t] = z;
+        reinterpret_cast<uint4*>(sc)[2 * t + 1] = z;
+        reinterpret_cast<uint4*>(pt)[2 * t] = b0;
+        reinterpret_cast<uint4*>(pt)[2 * t + 1] = b1;
+    }
+}
+__global__ void __launch_bounds__(32) k_shuffle_pass_a_agg(dev_inputs d, gens g, job_sink j1, qq_merlin::transcript tr0, entropy32 ent,
+                                                           proof_state* __restrict__ states) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= d.nproofs) return;
+    agg_ctx A;
+    agg_begin_a(A, ent.b, p);
+    j1.agg = &A;
+    proof_state S(tr0);
+    pass_a(S, j1, p, d.proof + QQ_SHUFFLE_PROOF_BYTES * p, d.stm + QQ_SHUFFLE_STATEMENT_BYTES * p, d.in + 9 * 128 * p, g, nullptr);
+    for (int i = 0; i < 6; i++) S.fixed[i] = A.fixed[i];
+    S.clean = A.overflow ? 0 : 1;
+    states[p] = S;
+}
+// eG / sG: the exact MSMs G, H, g_r, h_r of every proof (4 x 32 B, 4 status bytes per proof).  A proof that is not clean
+// drops out of the aggregate (its scalars are zeroed) and is verified in the exact form afterwards.
+__global__ void __launch_bounds__(32) k_shuffle_pass_b_agg(dev_inputs d, gens g, job_sink j1, job_sink j2, entropy32 ent,
+                                                           proof_state* __restrict__ states, const uint8_t* __restrict__ eG,
+                                                           const uint8_t* __restrict__ sG, uint8_t* __restrict__ clean_out) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= d.nproofs) return;
+    proof_state S = states[p];
+    agg_ctx A;
+    agg_begin_b(A, ent.b, p);
+    j2.agg = &A;
+    bool clean = S.clean != 0;
+    if (clean)
+        clean = pass_b(S, j2, p, d.proof + QQ_SHUFFLE_PROOF_BYTES * p, d.stm + QQ_SHUFFLE_STATEMENT_BYTES * p, d.in + 9 * 128 * p,
+                       d.out + 9 * 128 * p, nullptr, nullptr, eG + 128 * p, sG + 4 * p, g) && !A.overflow;
+    uint4 z = make_uint4(0, 0, 0, 0);
+    if (clean) {
+        for (int i = 0; i < 6; i++) states[p].fixed[i] = qq_sc::add(S.fixed[i], A.fixed[i]);
+    } else {
+        for (int i = 0; i < 6; i++) states[p].fixed[i] = qq_sc::zero();
+        uint4* a1 = reinterpret_cast<uint4*>(j1.asc + (size_t)32 * j1.cap * (p - j1.base));
+        for (uint32_t t = 0; t < 2 * j1.cap; t++) a1[t] = z;
+        uint4* a2 = reinterpret_cast<uint4*>(j2.asc + (size_t)32 * j2.cap * (p - j2.base));
+        for (uint32_t t = 0; t < 2 * j2.cap; t++) a2[t] = z;
+    }
+    states[p].clean = clean ? 1 : 0;
+    clean_out[p] = clean ? 1 : 0;
+}
+// the six fixed-generator terms of the aggregate: scalar i = sum over the proofs of states[p].fixed[i]   (grid = 6 blocks)
+__global__ void __launch_bounds__(256) k_shuffle_fixed_sum(const proof_state* __restrict__ states, size_t nproofs, gens g,
+                                                           uint8_t* __restrict__ out_sc, uint8_t* __restrict__ out_pt) {
+    __shared__ qq_sc::sc part[256];
+    const int i = blockIdx.x;
+    qq_sc::sc acc = qq_sc::zero();
+    for (size_t p = threadIdx.x; p < nproofs; p += blockDim.x) acc = qq_sc::add(acc, states[p].fixed[i]);
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    for (int h = 128; h > 0; h >>= 1) {
+        if ((int)threadIdx.x < h) part[threadIdx.x] = qq_sc::add(part[threadIdx.x], part[threadIdx.x + h]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const uint8_t* pt = i == 0 ? g.B : i == 1 ? g.Hp : i == 2 ? g.H : g.G + 32 * (i - 3);
+        job_sink::put(out_sc, out_pt, (size_t)i, part[0], pt);
+    }
 }
 
 }  // namespace qq_shuffle

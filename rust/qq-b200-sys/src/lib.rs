@@ -57,6 +57,7 @@ extern "C" {
     pub fn qq_verify_range_proof_batch(ctx: *mut QqCtx, transcript_label: *const c_char, verifier_label: *const c_char, transcript_state: *const u8, domain_label: *const c_char, commitments: *const u8, proofs: *const u8, n_bits: usize, m: usize, chain: usize, nproofs: usize, status: *mut u8) -> c_int;
     pub fn qq_transcript_state_bytes() -> usize;
     pub fn qq_verify_set_transcripts(ctx: *mut QqCtx, on_device: c_int) -> c_int;
+    pub fn qq_verify_set_aggregation(ctx: *mut QqCtx, on: c_int) -> c_int;
     pub fn qq_msm_set_overlap(ctx: *mut QqCtx, split_min: std::os::raw::c_long, tail_pct: c_int, sort_blocks_per_sm: c_int) -> c_int;
     pub fn qq_transcript_capture(ctx: *mut QqCtx, states_out: *mut u8, capacity_states: usize) -> c_int;
     pub fn qq_msm_segmented(ctx: *mut QqCtx, scalars: *const u8, points: *const u8, offsets: *const u32, m: usize, out: *mut u8, status: *mut u8) -> c_int;

@@ -353,6 +353,9 @@ void hh_shuffle_verify(const char* transcript_label, const char* verifier_label,
         for (size_t t = 0; t < QQ_SHUFFLE_TERMS_1; t++) memcpy(&pt1[32 * t], base_pk, 32);
         for (size_t t = 0; t < QQ_SHUFFLE_TERMS_2; t++) memcpy(&pt2[32 * t], base_pk, 32);
         job_sink j1, j2;
+        memset((void*)&j1, 0, sizeof j1);
+        memset((void*)&j2, 0, sizeof j2);
+        for (int m = 0; m < QQ_JOB_MAX_MSMS; m++) j1.exact_slot[m] = j2.exact_slot[m] = -1;
         j1.sc = sc1.data(); j1.pt = pt1.data(); j1.msms_pp = QQ_SHUFFLE_MSMS_1; j1.terms_pp = QQ_SHUFFLE_TERMS_1; j1.base = p;
         j2.sc = sc2.data(); j2.pt = pt2.data(); j2.msms_pp = QQ_SHUFFLE_MSMS_2; j2.terms_pp = QQ_SHUFFLE_TERMS_2; j2.base = p;
         uint32_t t = 0;
@@ -366,13 +369,77 @@ void hh_shuffle_verify(const char* transcript_label, const char* verifier_label,
         pass_a(S, j1, p, pr, sm, in + 1152 * p, g, nullptr);
         uint8_t e1[QQ_SHUFFLE_MSMS_1 * 32], s1[QQ_SHUFFLE_MSMS_1], e2[QQ_SHUFFLE_MSMS_2 * 32], s2[QQ_SHUFFLE_MSMS_2];
         hh_segmented(sc1.data(), pt1.data(), j1.first, QQ_SHUFFLE_MSMS_1, e1, s1);
-        pass_b(S, j2, p, pr, sm, in + 1152 * p, out + 1152 * p, e1, s1, g);
+        pass_b(S, j2, p, pr, sm, in + 1152 * p, out + 1152 * p, e1, s1, e1 + 32 * 14, s1 + 14, g);
         hh_segmented(sc2.data(), pt2.data(), j2.first, QQ_SHUFFLE_MSMS_2, e2, s2);
         pass_final(S, pr, e2, s2);
         status[p] = S.st;
         stage[p] = S.sg;
         detail[p] = S.dt;
     }
+}
+// Aggregate form of the same verification (the fast path of qq_verify_shuffle_batch): per proof the exact MSMs G, H, g_r, h_r,
+// every other group equation weighted into ONE sum over all proofs, which must be the identity.  clean[p]: the proof passed
+// every scalar check and is inside the aggregate; *agg_identity: the aggregated MSM (clean proofs only) is the identity;
+// counts[2 p], counts[2 p + 1]: aggregated (non-fixed) terms the proof emitted in batch 1 / 2.
+void hh_shuffle_verify_aggregate(const char* transcript_label, const char* verifier_label, const uint8_t* in, const uint8_t* out,
+                                 const uint8_t* stm, const uint8_t* proof, size_t n, const uint8_t* base_pk, const uint8_t* xpc,
+                                 const uint8_t* entropy, uint8_t* clean, uint8_t* agg_identity, uint32_t* counts) {
+    using namespace qq_shuffle;
+    qq_merlin::transcript tr0((const uint8_t*)transcript_label, strlen(transcript_label));
+    tr0.domain_sep(verifier_label);
+    gens g{base_pk, base_pk + 32, xpc, xpc + 32};
+    const size_t C1 = QQ_SHUFFLE_AGG_CAP_1, C2 = QQ_SHUFFLE_AGG_CAP_2, N = n * (C1 + C2) + 6;
+    std::vector<uint8_t> asc(N * 32, 0), apt(N * 32);
+    for (size_t t = 0; t < N; t++) memcpy(&apt[32 * t], base_pk, 32);
+    qq_sc::sc fixed[6];
+    for (int i = 0; i < 6; i++) fixed[i] = qq_sc::zero();
+    for (size_t p = 0; p < n; p++) {
+        std::vector<uint8_t> xsc(38 * 32, 0), xpt(38 * 32);
+        for (size_t t = 0; t < 38; t++) memcpy(&xpt[32 * t], base_pk, 32);
+        job_sink j1, j2;
+        memset((void*)&j1, 0, sizeof j1);
+        memset((void*)&j2, 0, sizeof j2);
+        for (int m = 0; m < QQ_JOB_MAX_MSMS; m++) j1.exact_slot[m] = j2.exact_slot[m] = -1;
+        const uint32_t xf[5] = {0, 9, 18, 28, 38};
+        for (int m = 0; m < 5; m++) j1.first[m] = xf[m];
+        j1.sc = xsc.data(); j1.pt = xpt.data(); j1.msms_pp = 4; j1.terms_pp = 38; j1.base = p;
+        for (int m = 0; m < 4; m++) j1.exact_slot[14 + m] = (int8_t)m;
+        j1.asc = asc.data() + 32 * C1 * p; j1.apt = apt.data() + 32 * C1 * p; j1.cap = (uint32_t)C1;
+        j2.base = p;
+        j2.asc = asc.data() + 32 * (C1 * n + C2 * p); j2.apt = apt.data() + 32 * (C1 * n + C2 * p); j2.cap = (uint32_t)C2;
+        j1.fB = j2.fB = g.B; j1.fHp = j2.fHp = g.Hp; j1.fH = j2.fH = g.H; j1.fG = j2.fG = g.G;
+        const uint8_t *pr = proof + QQ_SHUFFLE_PROOF_BYTES * p, *sm = stm + QQ_SHUFFLE_STATEMENT_BYTES * p;
+        agg_ctx A;
+        agg_begin_a(A, entropy, p);
+        j1.agg = &A;
+        proof_state S(tr0);
+        pass_a(S, j1, p, pr, sm, in + 1152 * p, g, nullptr);
+        counts[2 * p] = A.k;
+        qq_sc::sc fa[6];
+        for (int i = 0; i < 6; i++) fa[i] = A.fixed[i];
+        bool ok = !A.overflow;
+        uint8_t eG[128], sG[4];
+        hh_segmented(xsc.data(), xpt.data(), j1.first, 4, eG, sG);
+        agg_begin_b(A, entropy, p);
+        j2.agg = &A;
+        if (ok) ok = pass_b(S, j2, p, pr, sm, in + 1152 * p, out + 1152 * p, nullptr, nullptr, eG, sG, g) && !A.overflow;
+        counts[2 * p + 1] = A.k;
+        clean[p] = ok ? 1 : 0;
+        if (ok) {
+            for (int i = 0; i < 6; i++) fixed[i] = qq_sc::add(fixed[i], qq_sc::add(fa[i], A.fixed[i]));
+        } else {
+            memset(j1.asc, 0, 32 * C1);
+            memset(j2.asc, 0, 32 * C2);
+        }
+    }
+    for (int i = 0; i < 6; i++) {
+        const uint8_t* pt = i == 0 ? g.B : i == 1 ? g.Hp : i == 2 ? g.H : g.G + 32 * (i - 3);
+        job_sink::put(asc.data(), apt.data(), n * (C1 + C2) + i, fixed[i], pt);
+    }
+    uint32_t first[2] = {0, (uint32_t)N};
+    uint8_t e[32], st;
+    hh_segmented(asc.data(), apt.data(), first, 1, e, &st);
+    *agg_identity = (st == 0 && is_zero32(e)) ? 1 : 0;
 }
 size_t hh_transcript_state_bytes() { return qq_merlin::transcript::STATE_BYTES; }
 // export -> import round trip of a transcript state, then one more challenge from both; returns 1 when they agree and the

@@ -1300,8 +1300,10 @@ def test_shuffle_proof_verification(engine):
 
 
 def test_shuffle_verification_device_and_host_transcripts_agree(engine):
-    """qq_verify_set_transcripts: the per-proof phases in the transcript kernels (default) and on the host threads give the same
-    (status, stage, detail) on the 23 accept / reject cases and on 300 tiled golden proofs with tampered ones among them."""
+    """qq_verify_set_aggregation / qq_verify_set_transcripts: the aggregate form (default: 4 exact MSMs per proof + one weighted
+    Pippenger MSM over all equations of all proofs), the exact form in the transcript kernels and the exact form with host
+    transcripts give the same (status, stage, detail) on the 23 accept / reject cases, on 300 tiled golden proofs with tampered
+    ones among them, on 300 valid ones and on 300 with one scalar-level failure."""
     import os
     import shuffle_ref as F
     cases = shuffle_cases(Stream(b"shuffle-gpu"))
@@ -1313,17 +1315,25 @@ def test_shuffle_verification_device_and_host_transcripts_agree(engine):
     for i in rng.choice(rec.shape[0], 40, replace=False):
         rec[i, int(rng.integers(0, 6432))] ^= 1 << int(rng.integers(0, 8))
     big = tuple(np.ascontiguousarray(rec[:, a:b]) for a, b in ((0, 1152), (1152, 2304), (2304, 2656), (2656, 6432)))
+    clean = tuple(np.ascontiguousarray(np.tile(raw, (75, 1))[:, a:b]) for a, b in ((0, 1152), (1152, 2304), (2304, 2656), (2656, 6432)))
+    one_scalar_bad = [c.copy() for c in clean]
+    one_scalar_bad[3][17, 3776 - 1 - 32] ^= 1        # a DDH challenge: that proof leaves the aggregate, the rest is accepted by it
     try:
-        dev = [engine.verify_shuffle(*args), engine.verify_shuffle(*big)]
+        dev = [engine.verify_shuffle(*args), engine.verify_shuffle(*big), engine.verify_shuffle(*clean), engine.verify_shuffle(*one_scalar_bad)]
+        engine.verify_set_aggregation(False)
+        exact = [engine.verify_shuffle(*args), engine.verify_shuffle(*big), engine.verify_shuffle(*clean), engine.verify_shuffle(*one_scalar_bad)]
         engine.verify_set_transcripts(False)
-        host = [engine.verify_shuffle(*args), engine.verify_shuffle(*big)]
+        host = [engine.verify_shuffle(*args), engine.verify_shuffle(*big), engine.verify_shuffle(*clean), engine.verify_shuffle(*one_scalar_bad)]
     finally:
         engine.verify_set_transcripts(True)
-    for d, h in zip(dev, host):
-        for a, b in zip(d, h):
-            assert a.tolist() == b.tolist()
+        engine.verify_set_aggregation(True)
+    for d, x, h in zip(dev, exact, host):
+        for a, b, c in zip(d, x, h):
+            assert a.tolist() == b.tolist() == c.tolist()
     assert dev[0][0][:2].tolist() == [0, 0] and all(dev[0][0][2:])
     assert 0 < np.count_nonzero(dev[1][0]) <= 40
+    assert not dev[2][0].any()
+    assert np.nonzero(dev[3][0])[0].tolist() == [17] and int(dev[3][1][17]) == 6
 
 
 def test_golden_shuffle_proofs_accepted(engine):

@@ -362,6 +362,31 @@ def test_shuffle_phases_shared_with_the_transcript_kernels(hh):
                      b"".join(b[1] for b in blobs), b"".join(b[0] for b in blobs), len(cases))
     for i, e in enumerate(expect):
         assert (st[i], sg[i]) == e[:2] and (e[2] is None or dt[i] == e[2]), (i, e, (st[i], sg[i], dt[i]))
+    # ---- aggregate form (fast path): clean proofs, one weighted sum over all proofs == identity
+    h.hh_shuffle_verify_aggregate.argtypes = [u8p, u8p, u8p, u8p, u8p, u8p, ctypes.c_size_t, u8p, u8p, u8p, u8p, u8p,
+                                              ctypes.POINTER(ctypes.c_uint32)]
+
+    def run_agg(si, so, stm, pr, n, entropy=bytes(range(32))):
+        clean, ident = ctypes.create_string_buffer(n), ctypes.create_string_buffer(1)
+        counts = (ctypes.c_uint32 * (2 * n))()
+        h.hh_shuffle_verify_aggregate(b"ShuffleProof", b"Shuffle", si, so, stm, pr, n, base_pk, xpc_bytes, entropy, clean, ident, counts)
+        return list(clean.raw), ident.raw[0], list(counts)
+    clean, ident, counts = run_agg(*cols(raw), n)
+    assert clean == [1] * n and ident == 1
+    assert counts == [44, 102] * n                       # QQ_SHUFFLE_AGG_CAP_1 / _2 are exact for a clean proof
+    clean, ident, counts = run_agg(*cols(raw), n, entropy=bytes(32))
+    assert clean == [1] * n and ident == 1               # other weights, same verdict
+    clean, ident, counts = run_agg(*cols(bad), n)
+    assert clean[1] == 0                                 # DDH challenge: scalar-level, caught before the aggregate
+    assert clean[0] == 1 and clean[2] == 1 and ident == 0    # a flipped output account / rho_bar only show in the group equations
+    only_scalar_bad = raw.copy()
+    only_scalar_bad[1, 2656 + 3776 - 1 - 32] ^= 1
+    clean, ident, counts = run_agg(*cols(only_scalar_bad), n)
+    assert clean == [1, 0] + [1] * (n - 2) and ident == 1    # the dirty proof left the aggregate, the rest still verifies
+    # every group-level tampering of the 23 cases breaks the aggregate when it is the only proof in it
+    for i, k in enumerate(cases):
+        cl, idn, _ = run_agg(b"".join(k[0]), b"".join(k[1]), blobs[i][1], blobs[i][0], 1)
+        assert (cl[0] == 1 and idn == 1) == (expect[i][0] == 0), (i, expect[i], cl, idn)
     # serialised transcript state: round trip, corrupted tag / position refused
     state = ctypes.create_string_buffer(h.hh_transcript_state_bytes())
     assert h.hh_transcript_state_bytes() == 208

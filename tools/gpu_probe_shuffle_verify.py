@@ -26,8 +26,9 @@ def main():
     for n in [int(x) for x in (sys.argv[1:] or ["1", "64", "512", "4096", "16384"])]:
         # page-locked host buffers, as a caller that feeds serialized transactions would hold them
         arrs = [torch.from_numpy(a).pin_memory().numpy() for a in load(n)]
-        for mode in ("device", "host"):
-            eng.verify_set_transcripts(mode == "device")
+        for mode in ("aggregate", "device", "host"):
+            eng.verify_set_transcripts(mode != "host")
+            eng.verify_set_aggregation(mode == "aggregate")
             ts = []
             for rep in range(5):
                 t = time.perf_counter()
@@ -39,6 +40,16 @@ def main():
                               "proofs_per_s": n / best, "kernel_ms": eng.last_kernel_ms, "breakdown_ms": eng.last_kernel_breakdown(),
                               "msms": 32 * n, "terms": 239 * n, "all_accepted": True}), flush=True)
         eng.verify_set_transcripts(True)
+        eng.verify_set_aggregation(True)
+        if n >= 64:      # one tampered proof (an output account): the aggregate fails, the slice is verified in the exact form
+            bad = [a.copy() for a in arrs]
+            bad[1][n // 2, 5] ^= 1
+            t = time.perf_counter()
+            st, sg, det = eng.verify_shuffle(*bad)
+            dt = time.perf_counter() - t
+            assert np.nonzero(st)[0].tolist() == [n // 2]
+            print(json.dumps({"probe": "verify_shuffle", "transcripts": "aggregate, one tampered proof (exact fallback)", "proofs": n,
+                              "wall_ms": dt * 1e3}), flush=True)
     eng.close()
 
 
