@@ -10,8 +10,13 @@
 
 #ifdef __CUDACC__
 #define QQ_HOSTDEV __host__ __device__
+// One copy of the big bodies (the Keccak round function, a Z/l product, one transcript operation) in device code: the
+// transcript kernels run one warp per SM, and with everything inlined pass A alone was 152 000 SASS instructions (2.4 MB) -
+// 37 % of its issue slots waited for instruction fetch (ncu: stall_no_instruction, profiles/ncu_shuffle_pass_a_r02.json).
+#define QQ_NOINLINE __noinline__
 #else
 #define QQ_HOSTDEV
+#define QQ_NOINLINE
 #endif
 #define QQ_KECCAK_RC_WORDS {                                                                                              \
         0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL, \
@@ -29,7 +34,7 @@ static __constant__ uint64_t RC_DEV[24] = QQ_KECCAK_RC_WORDS;     // the same ro
 
 QQ_HOSTDEV static inline uint64_t rotl(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }   // 0 < n < 64
 
-QQ_HOSTDEV static inline void f1600(uint64_t a[25]) {
+QQ_HOSTDEV QQ_NOINLINE static void f1600(uint64_t a[25]) {
 #ifdef __CUDA_ARCH__
     const uint64_t* RC = RC_DEV;
 #else

@@ -30,20 +30,69 @@ class strobe128 {
         pos = 0;
         pos_begin = 0;
     }
-    QQ_HOSTDEV void absorb(const uint8_t* d, size_t n) {
-        for (size_t i = 0; i < n; i++) {
-            st[pos++] ^= d[i];
+    // The state is addressed as 25 little-endian 64-bit words (what Keccak-f permutes): absorbing / squeezing moves up to
+    // eight bytes per step with two shifts instead of one load-xor-store per byte.  On the device the message words of a
+    // block of up to 32 bytes are loaded into registers BEFORE the state is touched: d is a generic pointer the compiler
+    // cannot tell apart from st[], and interleaved it would serialise one global-memory latency per load.
+    QQ_HOSTDEV uint64_t* words() { return reinterpret_cast<uint64_t*>(st); }
+    QQ_HOSTDEV static uint64_t load_le(const uint8_t* d, unsigned c) {      // c <= 8 bytes, little endian
+        if (c == 8 && (reinterpret_cast<uintptr_t>(d) & 7) == 0) return *reinterpret_cast<const uint64_t*>(d);
+        uint64_t v = 0;
+        for (unsigned i = 0; i < c; i++) v |= (uint64_t)d[i] << (8 * i);
+        return v;
+    }
+    QQ_HOSTDEV void xor_at(unsigned at, uint64_t v, unsigned c) {           // c <= 8 bytes of v into st[at .. at + c)
+        const unsigned q = at >> 3, sh = (at & 7) * 8;
+        uint64_t* w = words();
+        w[q] ^= v << sh;
+        if (sh + 8 * c > 64) w[q + 1] ^= v >> (64 - sh);
+    }
+    QQ_HOSTDEV QQ_NOINLINE void absorb(const uint8_t* d, size_t n) {
+        while (n) {
+            const unsigned blk = n < 32 ? (unsigned)n : 32u;
+            uint64_t m[4];
+#pragma unroll
+            for (unsigned k = 0; k < 4; k++) m[k] = 8 * k < blk ? load_le(d + 8 * k, blk - 8 * k < 8 ? blk - 8 * k : 8u) : 0;
+#pragma unroll
+            for (unsigned k = 0; k < 4; k++) {
+                if (8 * k >= blk) break;
+                unsigned c = blk - 8 * k < 8 ? blk - 8 * k : 8u;
+                uint64_t v = m[k];
+                while (c) {                                   // at most two rounds: a word that straddles the rate boundary
+                    unsigned room = (unsigned)(R - pos), t = c < room ? c : room;
+                    xor_at(pos, t == 8 ? v : (v & ((1ULL << (8 * t)) - 1)), t);
+                    pos = (uint8_t)(pos + t);
+                    if (pos == R) run_f();
+                    v = t == 8 ? 0 : v >> (8 * t);
+                    c -= t;
+                }
+            }
+            d += blk;
+            n -= blk;
+        }
+    }
+    QQ_HOSTDEV QQ_NOINLINE void squeeze(uint8_t* d, size_t n) {
+        while (n) {
+            unsigned room = (unsigned)(R - pos), c = n < 8 ? (unsigned)n : 8u;
+            if (c > room) c = room;
+            const unsigned q = pos >> 3, sh = (pos & 7) * 8;
+            uint64_t* w = words();
+            uint64_t v = w[q] >> sh;
+            const uint64_t mask = c == 8 ? ~0ULL : ((1ULL << (8 * c)) - 1);
+            w[q] &= ~(mask << sh);                                          // squeezed bytes are zeroed (STROBE's PRF)
+            if (sh + 8 * c > 64) {
+                v |= w[q + 1] << (64 - sh);
+                w[q + 1] &= ~(mask >> (64 - sh));
+            }
+            v &= mask;
+            for (unsigned i = 0; i < c; i++) d[i] = (uint8_t)(v >> (8 * i));
+            pos = (uint8_t)(pos + c);
+            d += c;
+            n -= c;
             if (pos == R) run_f();
         }
     }
-    QQ_HOSTDEV void squeeze(uint8_t* d, size_t n) {
-        for (size_t i = 0; i < n; i++) {
-            d[i] = st[pos];
-            st[pos++] = 0;
-            if (pos == R) run_f();
-        }
-    }
-    QQ_HOSTDEV void begin_op(uint8_t flags, bool more) {
+    QQ_HOSTDEV QQ_NOINLINE void begin_op(uint8_t flags, bool more) {
         if (more) return;   // continuation of the current operation (same flags by construction)
         uint8_t old_begin = pos_begin;
         pos_begin = (uint8_t)(pos + 1);
@@ -106,13 +155,13 @@ class transcript {
     QQ_HOSTDEV transcript(const uint8_t* label, size_t n) : s("Merlin v1.0") { append_message("dom-sep", label, n); }
     QQ_HOSTDEV void export_state(uint8_t* out) const { s.export_state(out); }
     QQ_HOSTDEV bool import_state(const uint8_t* in) { return s.import_state(in); }
-    QQ_HOSTDEV void append_message(const char* label, const uint8_t* msg, size_t n) {
+    QQ_HOSTDEV QQ_NOINLINE void append_message(const char* label, const uint8_t* msg, size_t n) {
         s.meta_ad((const uint8_t*)label, strobe128::label_len(label), false);
         uint8_t len[4] = {(uint8_t)n, (uint8_t)(n >> 8), (uint8_t)(n >> 16), (uint8_t)(n >> 24)};
         s.meta_ad(len, 4, true);
         s.ad(msg, n, false);
     }
-    QQ_HOSTDEV void challenge_bytes(const char* label, uint8_t* out, size_t n) {
+    QQ_HOSTDEV QQ_NOINLINE void challenge_bytes(const char* label, uint8_t* out, size_t n) {
         s.meta_ad((const uint8_t*)label, strobe128::label_len(label), false);
         uint8_t len[4] = {(uint8_t)n, (uint8_t)(n >> 8), (uint8_t)(n >> 16), (uint8_t)(n >> 24)};
         s.meta_ad(len, 4, true);

@@ -10,9 +10,11 @@
 #include <cstring>
 #ifdef __CUDACC__
 #define QQ_SC_FN __host__ __device__ static inline
+#define QQ_SC_FN_BIG __host__ __device__ __noinline__ static      // one copy of the large bodies in device code (see keccak_host.hpp)
 #define QQ_SC_MEMBER __host__ __device__
 #else
 #define QQ_SC_FN static inline
+#define QQ_SC_FN_BIG static inline
 #define QQ_SC_MEMBER
 #endif
 #define QQ_SC_L_WORDS {0x5812631a5cf5d3edULL, 0x14def9dea2f79cd6ULL, 0ULL, 0x1000000000000000ULL}
@@ -111,7 +113,7 @@ QQ_SC_FN void mul_c(const uint64_t* v, int n, uint64_t* out) {
         out[n + j] += (uint64_t)carry;      // no overflow: the running product fits n + 2 limbs
     }
 }
-QQ_SC_FN sc reduce512(const uint64_t x[8]) {
+QQ_SC_FN_BIG sc reduce512(const uint64_t x[8]) {
     const uint64_t L[4] = QQ_SC_L_WORDS;
     uint64_t lo[4], hi[5], y[7], ylo[4], yhi[3], z[5], zlo[4], zhi[1], w[3];
     split252(x, 8, lo, hi, 5);
@@ -148,7 +150,7 @@ QQ_SC_FN sc reduce512(const uint64_t x[8]) {
     }
     return sc{{t[0], t[1], t[2], t[3]}};
 }
-QQ_SC_FN sc mul(const sc& a, const sc& b) {
+QQ_SC_FN_BIG sc mul(const sc& a, const sc& b) {
     uint64_t x[8] = {0};
     for (int i = 0; i < 4; i++) {
         u128 c = 0;
@@ -168,7 +170,7 @@ QQ_SC_FN sc from_wide(const uint8_t b[64]) {
     return reduce512(x);
 }
 // a^(l - 2)
-QQ_SC_FN sc invert(const sc& a) {
+QQ_SC_FN_BIG sc invert(const sc& a) {
     const uint64_t L[4] = QQ_SC_L_WORDS;
     uint64_t e[4] = {L[0] - 2, L[1], L[2], L[3]};
     sc r = one();

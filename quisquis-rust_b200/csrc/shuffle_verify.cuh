@@ -91,7 +91,7 @@ struct job_sink {
         memcpy(&pt_arr[32 * i], point, 32);
 #endif
     }
-    QQ_HOSTDEV void set(size_t p, size_t m, size_t t, const qq_sc::sc& s, const uint8_t* point) const {
+    QQ_HOSTDEV QQ_NOINLINE void set(size_t p, size_t m, size_t t, const qq_sc::sc& s, const uint8_t* point) const {
         if (agg == nullptr) {
             put(sc, pt, (p - base) * terms_pp + first[m] + t, s, point);
             return;
@@ -189,25 +189,15 @@ QQ_HOSTDEV static inline uint8_t svp_phase(qq_merlin::transcript& tr, const uint
     return QQ_ST_OK;
 }
 
-// prod_i (w_i - w_j)(w_i - w_k) of a HadamardStatement, or zero when the omegas are not canonical / not distinct (the
-// phase stops before it needs the inverse then).  It depends on the statement only, so a host caller with many proofs inverts
-// these products with one inversion per host thread before running the transcripts.
-QQ_HOSTDEV static inline sc hadamard_den_product(const uint8_t* omega) {
-    using namespace qq_sc;
-    sc w[3];
-    for (int i = 0; i < 3; i++)
-        if (!from_bytes(w[i], omega + 32 * i)) return zero();
-    sc prod = one();
-    for (int i = 0; i < 3; i++) prod = mul(prod, mul(sub(w[i], w[(i + 1) % 3]), sub(w[i], w[(i + 2) % 3])));
-    return prod;
-}
 // HadamardProof::verify (reference src/shuffle/hadamard.rs:249-389) on a running transcript; fills slots m0 .. m0 + 3 of
 // proof p.  cm[k]: the three commitments of a / b / c.  With l(X) = prod (X - omega_j) and the Lagrange basis l_i(X):
 //   l(x) c_a0 + sum_i l_i(x) c_a_i == com(a_bar; r_bar)  (and the same for b, c)                 [MSMs m0 .. m0 + 2]
 //   l(x) sum_i x^i c_delta_i == com(a_bar o b_bar - c_bar; rho_bar)                              [MSM m0 + 3]
+// The first three are only ever compared with the identity, so each is emitted multiplied by D = prod_i den_i, den_i =
+// (w_i - w_j)(w_i - w_k): l_i(x) D = num_i(x) prod_{j != i} den_j needs no inversion in Z/l (D != 0: the omegas are distinct).
 QQ_HOSTDEV static inline void hadamard_phase(qq_merlin::transcript& tr, const uint8_t* pr, const uint8_t* omega,
                                              const uint8_t* const cm[3], const gens& g, const job_sink& jobs, size_t p, size_t m0,
-                                             uint8_t& pre, uint8_t& pre_detail, const sc* den_inv = nullptr) {
+                                             uint8_t& pre, uint8_t& pre_detail) {
     using namespace qq_sc;
     pre = QQ_ST_OK;
     pre_detail = 0;
@@ -240,24 +230,25 @@ QQ_HOSTDEV static inline void hadamard_phase(qq_merlin::transcript& tr, const ui
     transcript_challenge(tr, "challenge", x);
     // l(x) and the Lagrange basis at x (polynomial::create_l_i_x_polynomial, src/shuffle/polynomial.rs:367-391)
     sc d[3] = {sub(x, w[0]), sub(x, w[1]), sub(x, w[2])};
-    sc ev[4];
-    ev[0] = mul(mul(d[0], d[1]), d[2]);
-    {   // the three denominators (w_i - w_j)(w_i - w_k) with ONE inversion (Montgomery's trick; they are non-zero: the
-        // omega-uniqueness check ran before)
+    const sc lx = mul(mul(d[0], d[1]), d[2]);      // l(x)
+    sc evD[4], D;                                  // l(x) D and l_i(x) D
+    {
         sc den[3];
         for (int i = 0; i < 3; i++) den[i] = mul(sub(w[i], w[(i + 1) % 3]), sub(w[i], w[(i + 2) % 3]));
         sc p01 = mul(den[0], den[1]);
-        sc inv_all = den_inv ? *den_inv : invert(mul(p01, den[2]));      // the caller may have batch-inverted it across proofs
-        sc dinv[3] = {mul(inv_all, mul(den[1], den[2])), mul(inv_all, mul(den[0], den[2])), mul(inv_all, p01)};
-        for (int i = 0; i < 3; i++) ev[i + 1] = mul(mul(d[(i + 1) % 3], d[(i + 2) % 3]), dinv[i]);
+        D = mul(p01, den[2]);
+        const sc cof[3] = {mul(den[1], den[2]), mul(den[0], den[2]), p01};
+        evD[0] = mul(lx, D);
+        for (int i = 0; i < 3; i++) evD[i + 1] = mul(mul(d[(i + 1) % 3], d[(i + 2) % 3]), cof[i]);
     }
+    const sc nD = neg(D);
     for (int k = 0; k < 3; k++) {
-        jobs.set(p, m0 + k, 0, ev[0], pr + 32 * k);
-        for (int i = 0; i < 3; i++) jobs.set(p, m0 + k, 1 + i, ev[i + 1], cm[k] + 32 * i);
-        jobs.set(p, m0 + k, 4, neg(blind[k]), g.H);
-        for (int i = 0; i < 3; i++) jobs.set(p, m0 + k, 5 + i, neg(bar[k][i]), g.G + 32 * i);
+        jobs.set(p, m0 + k, 0, evD[0], pr + 32 * k);
+        for (int i = 0; i < 3; i++) jobs.set(p, m0 + k, 1 + i, evD[i + 1], cm[k] + 32 * i);
+        jobs.set(p, m0 + k, 4, mul(nD, blind[k]), g.H);
+        for (int i = 0; i < 3; i++) jobs.set(p, m0 + k, 5 + i, mul(nD, bar[k][i]), g.G + 32 * i);
     }
-    sc xi = ev[0];
+    sc xi = lx;
     for (int i = 0; i < 4; i++) {
         jobs.set(p, m0 + 3, i, xi, pr + 96 + 32 * i);
         xi = mul(xi, x);
@@ -439,7 +430,7 @@ struct proof_state {
 // check prod (y i + x^i - z) == b; the 18 MSMs of batch 1.  pr / stm / in: this proof's ShuffleProof, ShuffleStatement and
 // input accounts (9 x 128 B).  S.tr must hold Transcript::new(label) + Verifier::new(label).
 QQ_HOSTDEV static inline void pass_a(proof_state& S, const job_sink& j1, size_t p, const uint8_t* pr, const uint8_t* stm,
-                                     const uint8_t* in, const gens& g, const sc* had_den_inv) {
+                                     const uint8_t* in, const gens& g) {
     using namespace qq_sc;
     const uint8_t *cA = pr, *ctau = pr + 96, *cB = pr + 192, *cBd = pr + 288;
     qq_merlin::transcript& tr = S.tr;
@@ -457,7 +448,7 @@ QQ_HOSTDEV static inline void pass_a(proof_state& S, const job_sink& j1, size_t 
         tr.append_point_var("BDashCommitment", cBd + 32 * i);
     }
     const uint8_t* cm[3] = {cBd, ctau, cB};
-    hadamard_phase(tr, pr + 384, stm, cm, g, j1, p, 0, S.had_pre, S.had_det, had_den_inv);
+    hadamard_phase(tr, pr + 384, stm, cm, g, j1, p, 0, S.had_pre, S.had_det);
     if (S.had_pre != QQ_ST_OK) return;     // the verdict is the Hadamard argument's; nothing later is looked at
     sc y, z;
     transcript_challenge(tr, "yChallenge", y);
@@ -690,7 +681,7 @@ __global__ void __launch_bounds__(32) k_shuffle_pass_a(dev_inputs d, gens g, job
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= d.nproofs) return;
     proof_state S(tr0);
-    pass_a(S, j1, p, d.proof + QQ_SHUFFLE_PROOF_BYTES * p, d.stm + QQ_SHUFFLE_STATEMENT_BYTES * p, d.in + 9 * 128 * p, g, nullptr);
+    pass_a(S, j1, p, d.proof + QQ_SHUFFLE_PROOF_BYTES * p, d.stm + QQ_SHUFFLE_STATEMENT_BYTES * p, d.in + 9 * 128 * p, g);
     states[p] = S;
 }
 __global__ void __launch_bounds__(32) k_shuffle_pass_b(dev_inputs d, gens g, job_sink j2, proof_state* __restrict__ states,
@@ -740,7 +731,7 @@ __global__ void __launch_bounds__(32) k_shuffle_pass_a_agg(dev_inputs d, gens g,
     agg_begin_a(A, ent.b, p);
     j1.agg = &A;
     proof_state S(tr0);
-    pass_a(S, j1, p, d.proof + QQ_SHUFFLE_PROOF_BYTES * p, d.stm + QQ_SHUFFLE_STATEMENT_BYTES * p, d.in + 9 * 128 * p, g, nullptr);
+    pass_a(S, j1, p, d.proof + QQ_SHUFFLE_PROOF_BYTES * p, d.stm + QQ_SHUFFLE_STATEMENT_BYTES * p, d.in + 9 * 128 * p, g);
     for (int i = 0; i < 6; i++) S.fixed[i] = A.fixed[i];
     S.clean = A.overflow ? 0 : 1;
     states[p] = S;

@@ -366,7 +366,7 @@ void hh_shuffle_verify(const char* transcript_label, const char* verifier_label,
         j2.first[QQ_SHUFFLE_MSMS_2] = t;
         const uint8_t *pr = proof + QQ_SHUFFLE_PROOF_BYTES * p, *sm = stm + QQ_SHUFFLE_STATEMENT_BYTES * p;
         proof_state S(tr0);
-        pass_a(S, j1, p, pr, sm, in + 1152 * p, g, nullptr);
+        pass_a(S, j1, p, pr, sm, in + 1152 * p, g);
         uint8_t e1[QQ_SHUFFLE_MSMS_1 * 32], s1[QQ_SHUFFLE_MSMS_1], e2[QQ_SHUFFLE_MSMS_2 * 32], s2[QQ_SHUFFLE_MSMS_2];
         hh_segmented(sc1.data(), pt1.data(), j1.first, QQ_SHUFFLE_MSMS_1, e1, s1);
         pass_b(S, j2, p, pr, sm, in + 1152 * p, out + 1152 * p, e1, s1, e1 + 32 * 14, s1 + 14, g);
@@ -413,7 +413,7 @@ void hh_shuffle_verify_aggregate(const char* transcript_label, const char* verif
         agg_begin_a(A, entropy, p);
         j1.agg = &A;
         proof_state S(tr0);
-        pass_a(S, j1, p, pr, sm, in + 1152 * p, g, nullptr);
+        pass_a(S, j1, p, pr, sm, in + 1152 * p, g);
         counts[2 * p] = A.k;
         qq_sc::sc fa[6];
         for (int i = 0; i < 6; i++) fa[i] = A.fixed[i];
