@@ -512,6 +512,18 @@ struct straus_args {
     const unsigned int* order; // instances sorted by term count (descending) so a warp's lanes do equal work
     size_t m;
 };
+// status of an MSM evaluated in `group` parts: a non-canonical scalar wins over an undecodable point
+__global__ void k_group_status(const uint8_t* __restrict__ part, int group, uint8_t* __restrict__ status, size_t mo) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < mo; j += stride) {
+        uint8_t st = 0;
+        for (int g = 0; g < group; g++) {
+            uint8_t s = part[j * group + g];
+            st = (s == 2 || st == 2) ? 2 : (st | s);
+        }
+        status[j] = st;
+    }
+}
 __global__ void k_seg_counts(const uint32_t* __restrict__ offsets, size_t m, unsigned int* __restrict__ counts) {
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) counts[j] = offsets[j + 1] - offsets[j];

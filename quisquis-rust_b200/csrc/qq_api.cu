@@ -122,6 +122,7 @@ struct qq_ctx {
     bool stc_ready = false;                    // k_straus_coop's shared-memory opt-in done
     int straus_minb = 4;                       // k_straus build for more than one wave of instances (QQ_STRAUS_MINB)
     int stc_per_sm = 64;                       // segmented MSMs: four-lane cooperative kernel up to this many MSMs per SM (QQ_STRAUS_COOP_PER_SM)
+    int shuffle_exact_split = 0;               // parts per exact MSM (G, H, g_r, h_r) of the aggregate form: 1, 2, 3; 0 = by batch size
     bool verify_aggregate = true;              // qq_verify_set_aggregation: identity equations of the shuffle proofs in one weighted Pippenger MSM
     bool verify_host_transcripts = false;      // qq_verify_set_transcripts(ctx, 0): per-proof phases of the shuffle verifier on the host threads
     uint8_t* d_shuffle_gens = nullptr;         // B | B_blinding | H | G[0..3) of VectorPedersenGens::new(4), device copy for the transcript kernels
@@ -553,6 +554,10 @@ extern "C" int qq_init(qq_ctx** out, int device) {
             if (const char* e = getenv("QQ_MSM_SORT_BPSM")) ctx->msm_sort_bpsm = atoi(e);
             if (const char* e = getenv("QQ_VERIFY_HOST_TRANSCRIPTS")) ctx->verify_host_transcripts = atoi(e) != 0;
             if (const char* e = getenv("QQ_VERIFY_AGGREGATE")) ctx->verify_aggregate = atoi(e) != 0;
+            if (const char* e = getenv("QQ_SHUFFLE_EXACT_SPLIT")) {
+                int v = atoi(e);
+                if (v >= 1 && v <= 3) ctx->shuffle_exact_split = v;
+            }
         }
         for (int i = 0; i < 8; i++) CK(cudaEventCreateWithFlags(&ctx->msm_ev[i], cudaEventDisableTiming));
         CK(cudaFuncSetAttribute(k_msm_sum_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * QQ_PT_BYTES));
@@ -973,31 +978,43 @@ struct qq_prepared;
 static int core_msm_to_point(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, u32x4* result,
                              uint8_t* dstatus, const qq_prepared* pre = nullptr);
 
+// group > 1: every `group` consecutive instances are the parts of ONE MSM (its terms split so that more threads share the
+// work: an MSM of 9 terms as 5 + 4 costs 252 doublings twice but halves the chain of additions); out / status then hold
+// m / group entries, the parts being summed by the batch encoder (it adds up to three sources).  group <= 3.
 static int core_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* points, const uint32_t* offsets, size_t m,
-                          size_t nterms, uint8_t* out, uint8_t* status) {
+                          size_t nterms, uint8_t* out, uint8_t* status, int group = 1) {
+    const size_t mo = m / (size_t)group;      // outputs
+    auto finish = [&](const dc_ws& dc, u32x4* half, uint8_t* part_status) -> int {
+        if (group == 1) return launch_finish_dbl(ctx, dc, fsrc(half, IDENT), FNONE, FNONE, out, IDENT, status, 1, m);
+        k_group_status<<<grid_for(mo, 256, ctx->sms * 8), 256, 0, ctx->stream>>>(part_status, group, status, mo);
+        ctx->launches++;
+        return launch_finish_dbl(ctx, dc, fsrc(half, imap(1, group, 0)), fsrc(half, imap(1, group, 1)),
+                                 group == 3 ? fsrc(half, imap(1, group, 2)) : FNONE, out, IDENT, status, 1, mo);
+    };
     // Few instances (one proof's worth): four lanes per instance, no ordering pass, direct encoder -- 4 launches
     if (ctx->vbc_max_jobs != 0 && m <= (size_t)ctx->sms * ctx->stc_per_sm) {
         if (!ctx->stc_ready) {
             CK(cudaFuncSetAttribute(k_straus_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, QQ_STC_SMEM_BYTES));
             ctx->stc_ready = true;
         }
-        CKQ(ws_begin(ctx, ws_need({nterms * QQ_PT_BYTES, nterms, nterms, m * QQ_PT_BYTES}) + dc_scratch_bytes(m)));
+        CKQ(ws_begin(ctx, ws_need({nterms * QQ_PT_BYTES, nterms, nterms, m * QQ_PT_BYTES, m}) + dc_scratch_bytes(m)));
         u32x4* P = ws_take<u32x4>(ctx, nterms * QQ_PT_BYTES);
         uint8_t* ok = ws_take<uint8_t>(ctx, nterms);
         uint8_t* tst = ws_take<uint8_t>(ctx, nterms);
         u32x4* half = ws_take<u32x4>(ctx, m * QQ_PT_BYTES);
+        uint8_t* part_status = ws_take<uint8_t>(ctx, m);
         dc_ws dc = dc_take(ctx, m);
         CKQ(launch_decompress(ctx, points, IDENT, P, ok, nterms));
         CKQ(launch_status(ctx, scalars, nullptr, nullptr, ok, 1, tst, nterms));
         straus_args a;
         a.pts = P; a.scalars = (const u32x4*)scalars; a.offsets = offsets; a.term_status = tst;
-        a.out = (u32x4*)out; a.half_out = half; a.status = status; a.scratch = nullptr; a.order = nullptr; a.m = m;
+        a.out = (u32x4*)out; a.half_out = half; a.status = group == 1 ? status : part_status; a.scratch = nullptr; a.order = nullptr; a.m = m;
         span_begin(ctx, FAM_VB);
         k_straus_coop<<<(unsigned)((m + 7) / 8), 32, QQ_STC_SMEM_BYTES, ctx->stream>>>(a);
         span_end(ctx);
         ctx->launches++;
         CK(cudaGetLastError());
-        CKQ(launch_finish_dbl(ctx, dc, fsrc(half, IDENT), FNONE, FNONE, out, IDENT, status, 1, m));
+        CKQ(finish(dc, half, part_status));
         return QQ_OK;
     }
     // 128-thread blocks, 2 per SM, no barrier: a batch holds only a few instances per thread, the lockstep forms of
@@ -1014,7 +1031,7 @@ static int core_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* po
     if (grid > (size_t)ctx->sms * occ) grid = (size_t)ctx->sms * occ;
     size_t scratch_bytes = grid * sblock * (size_t)QQ_STRAUS_KMAX * QQ_STRAUS_TERM_Q * 16;
     CKQ(ws_begin(ctx, ws_need({nterms * QQ_PT_BYTES, nterms, nterms, scratch_bytes, m * 4, m * 4, QQ_ORDER_BINS * 4, QQ_ORDER_BINS * 4,
-                               QQ_ORDER_BINS * 4, 4096 * 4, m * QQ_PT_BYTES}) + dc_scratch_bytes(m)));
+                               QQ_ORDER_BINS * 4, 4096 * 4, m * QQ_PT_BYTES, m}) + dc_scratch_bytes(m)));
     unsigned int* counts = ws_take<unsigned int>(ctx, m * 4);
     unsigned int* order = ws_take<unsigned int>(ctx, m * 4);
     unsigned int* ohist = ws_take<unsigned int>(ctx, QQ_ORDER_BINS * 4);
@@ -1026,6 +1043,7 @@ static int core_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* po
     uint8_t* tst = ws_take<uint8_t>(ctx, nterms);
     u32x4* scratch = ws_take<u32x4>(ctx, scratch_bytes);
     u32x4* half = ws_take<u32x4>(ctx, m * QQ_PT_BYTES);
+    uint8_t* part_status = ws_take<uint8_t>(ctx, m);
     dc_ws dc = dc_take(ctx, m);
     CKQ(launch_decompress(ctx, points, IDENT, P, ok, nterms));
     CKQ(launch_status(ctx, scalars, nullptr, nullptr, ok, 1, tst, nterms));
@@ -1040,14 +1058,14 @@ static int core_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* po
     straus_args a;
     a.pts = P; a.scalars = (const u32x4*)scalars; a.offsets = offsets; a.term_status = tst;
     // every scalar of an instance is halved, the instance sum is encoded as enc(2 * sum) by the batch encoder
-    a.out = (u32x4*)out; a.half_out = half; a.status = status; a.scratch = scratch; a.order = order; a.m = m;
+    a.out = (u32x4*)out; a.half_out = half; a.status = group == 1 ? status : part_status; a.scratch = scratch; a.order = order; a.m = m;
     span_begin(ctx, FAM_VB);
     if (dense) k_straus<128, 4, false><<<(unsigned)grid, 128, 0, ctx->stream>>>(a);
     else k_straus<128, 2, false><<<(unsigned)grid, 128, 0, ctx->stream>>>(a);
     span_end(ctx);
     ctx->launches++;
     CK(cudaGetLastError());
-    CKQ(launch_finish_dbl(ctx, dc, fsrc(half, IDENT), FNONE, FNONE, out, IDENT, status, 1, m));
+    CKQ(finish(dc, half, part_status));
     return QQ_OK;
 }
 
