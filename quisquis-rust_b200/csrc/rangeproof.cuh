@@ -12,23 +12,11 @@
 #pragma once
 #include "kernels.cuh"
 #include "sc_host.hpp"
+#include "rangeproof_verify.cuh"
 
 namespace qq {
 
-#define QQ_RP_MAX_LG 10      // n m <= 64 x 16 = 1024
-#define QQ_RP_MAX_PARTIES 16
-
-// one record per (sub-)proof, written by the host pass (all scalars canonical, already multiplied by the weight rho)
-struct rp_record {
-    qq_sc::sc neg_rz;                      // -rho z
-    qq_sc::sc rz;                          //  rho z
-    qq_sc::sc ra;                          //  rho a
-    qq_sc::sc rb;                          //  rho b
-    qq_sc::sc allinv;                      // (u_1 .. u_k)^-1
-    qq_sc::sc usq[QQ_RP_MAX_LG];           // u^2 in creation order (the crate's challenges_sq)
-    qq_sc::sc yinv_pow[QQ_RP_MAX_LG];      // y^-(2^j)
-    qq_sc::sc rzz_zj[QQ_RP_MAX_PARTIES];   // rho z^2 z^j
-};
+typedef qq_rp::record rp_record;      // written by the transcript phase (rangeproof_verify.cuh)
 
 // grid = (ceil(N / block), chunks); partial: chunks x 2N scalars (g sums then h sums)
 __global__ void __launch_bounds__(128) k_rp_fold(const rp_record* __restrict__ rec, unsigned int first, unsigned int count,

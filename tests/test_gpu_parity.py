@@ -1485,6 +1485,30 @@ def test_shuffle_verification_pipelined_slices(engine):
         assert (int(s1[0]), int(g1[0]), int(d1[0])) == (int(st[i]), int(sg[i]), int(det[i])), i
 
 
+def test_range_proof_device_and_host_transcripts_agree(engine):
+    """qq_verify_set_transcripts for the range-proof verifier: transcripts in k_rp_transcripts (default) and on the host threads
+    give the same status on 600 tiled golden proofs (m = 4 and m = 16) with tampered bytes spread through them."""
+    import os
+    for m in (4, 16):
+        per = m * 32 + engine.range_proof_bytes(m)
+        raw = np.fromfile(os.path.join(os.path.dirname(__file__), "golden", "range_proofs_m%d.bin" % m), dtype=np.uint8).reshape(-1, per)
+        n = 600
+        rec = np.tile(raw, ((n + raw.shape[0] - 1) // raw.shape[0], 1))[:n].copy()
+        rng = np.random.default_rng(m)
+        hit = sorted(rng.choice(n, 25, replace=False).tolist())
+        for i in hit:
+            rec[i, int(rng.integers(0, per))] ^= 1 << int(rng.integers(0, 8))
+        cm, pr = np.ascontiguousarray(rec[:, :m * 32]), np.ascontiguousarray(rec[:, m * 32:])
+        try:
+            dev = engine.verify_range_proofs(cm, pr, m)
+            engine.verify_set_transcripts(False)
+            host = engine.verify_range_proofs(cm, pr, m)
+        finally:
+            engine.verify_set_transcripts(True)
+        assert dev.tolist() == host.tolist()
+        assert sorted(np.nonzero(dev)[0].tolist()) == hit
+
+
 def test_range_proof_verification_two_halves(engine):
     """From 2 048 transcripts on the range-proof verifier works in two halves (device part of the first under the host part of
     the second): 2 500 tiled golden proofs with tampered ones at the ends of both halves - exactly those are rejected."""
