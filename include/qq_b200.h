@@ -365,6 +365,40 @@ size_t qq_transcript_state_bytes(void);
  * One-shot: ANY next entry point (whatever it returns) disarms it; NULL cancels. */
 int qq_transcript_capture(qq_ctx* ctx, uint8_t* states_out, size_t capacity_states);
 
+/* ---- several GPUs behind one handle -------------------------------------------------------------------
+ * qq_multi owns one qq_ctx and one worker thread per listed device (the first is the root).  Batches of independent units are
+ * cut into contiguous slices, one per device, no data-path exchange (results land in the caller's arrays at their positions).
+ * qq_multi_msm cuts ONE multiscalar multiplication (Verifier::multiscalar_multiplication, src/accounts/verifier.rs:91-99; the
+ * Bulletproofs mega-MSM) into slices of (scalar, point) pairs: every device runs Pippenger on its slice, the 144-byte partial
+ * results are pulled into the root's memory with peer copies (NVLink / NVSwitch) and added and encoded there by one kernel -
+ * they never visit the host.  Same outputs and status codes as the single-device entry points.  One caller thread at a time. */
+typedef struct qq_multi qq_multi;
+int qq_init_multi(qq_multi** out, const int* devices, int ndev);
+void qq_destroy_multi(qq_multi* m);
+int qq_multi_device_count(const qq_multi* m);
+qq_ctx* qq_multi_ctx(qq_multi* m, int index);      /* the per-device context (tuning knobs, qq_dev_alloc for the _dev form) */
+const char* qq_multi_last_error(const qq_multi* m);
+int qq_multi_update_account_batch(qq_multi* m, const uint8_t* acc, const uint8_t* bl, const uint8_t* u, const uint8_t* c,
+                                  uint8_t* out_acc, uint8_t* status, size_t n);
+int qq_multi_generate_commitment_batch(qq_multi* m, const uint8_t* pk, const uint8_t* r, const uint8_t* v, uint8_t* out_comm,
+                                       uint8_t* status, size_t n);
+int qq_multi_verify_shuffle_batch(qq_multi* m, const char* transcript_label, const char* verifier_label, const uint8_t* shuffle_input,
+                                  const uint8_t* shuffle_output, const uint8_t* statement, const uint8_t* proof, size_t nproofs,
+                                  uint8_t* status, uint8_t* stage, uint8_t* detail);
+int qq_multi_verify_range_proof_batch(qq_multi* m, const char* transcript_label, const char* verifier_label,
+                                      const uint8_t* transcript_state, const char* domain_label, const uint8_t* commitments,
+                                      const uint8_t* proofs, size_t n_bits, size_t m_values, size_t chain, size_t nproofs, uint8_t* status);
+int qq_multi_msm(qq_multi* m, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t* out_point, uint8_t* status);
+/* the same with the slices already resident: scalars_per_device[d] / points_per_device[d] are DEVICE pointers on device d
+ * (count_per_device[d] x 32 B each) */
+int qq_multi_msm_dev(qq_multi* m, const uint8_t* const* scalars_per_device, const uint8_t* const* points_per_device,
+                     const size_t* count_per_device, uint8_t* out_point, uint8_t* status);
+/* sum of k partial MSM results that sit in DEVICE memory as records of `stride` bytes (a multiple of 16, >= 128): 128 B canonical
+ * X | Y | Z | T as qq_msm_partial_dev writes them, and - when stride > 128 - the status byte at offset 128 (e.g. the output of an
+ * NCCL all-gather of those records).  out_point: compressed sum (zeros when a status is set); *is_identity, *status may be NULL. */
+int qq_points_sum_dev(qq_ctx* ctx, const uint8_t* records, size_t k, size_t stride, uint8_t* out_point, uint8_t* is_identity,
+                      uint8_t* status);
+
 /* ---- wire format ---------------------------------------------------------------------------------
  * bincode 1.x (Cargo.toml:29; default configuration: little endian, fixed-width integers, Vec = u64 length + elements, enum =
  * u32 variant index) encodings of the reference's serde-derived types <-> the flattened layouts above, so that batches can be

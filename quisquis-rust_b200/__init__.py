@@ -5,8 +5,8 @@ The directory name carries a hyphen (it is the reference's crate name), so impor
 The product is the C-ABI shared library `libqq_b200.so` (include/qq_b200.h); this Python layer is the ctypes
 binding plus a mirror of the reference's operator interface used by tests/ and bench.py.
 """
-from .binding import Engine, QQError, lib_path, load_library  # noqa: F401
+from .binding import Engine, MultiEngine, QQError, lib_path, load_library  # noqa: F401
 from .api import Account, ElGamalCommitment, RistrettoPublicKey, Verifier  # noqa: F401
 
-__all__ = ["Engine", "QQError", "lib_path", "load_library", "Account", "ElGamalCommitment", "RistrettoPublicKey",
+__all__ = ["Engine", "MultiEngine", "QQError", "lib_path", "load_library", "Account", "ElGamalCommitment", "RistrettoPublicKey",
            "Verifier"]

@@ -30,6 +30,9 @@ EXPORTS = [
     "qq_verify_set_transcripts", "qq_verify_set_aggregation",
     "qq_shuffle_proofs_from_bincode", "qq_shuffle_statements_from_bincode", "qq_shuffle_proofs_to_bincode",
     "qq_shuffle_statements_to_bincode", "qq_accounts_from_bincode", "qq_sigma_proof_from_bincode",
+    "qq_init_multi", "qq_destroy_multi", "qq_multi_device_count", "qq_multi_ctx", "qq_multi_last_error",
+    "qq_multi_update_account_batch", "qq_multi_generate_commitment_batch", "qq_multi_verify_shuffle_batch",
+    "qq_multi_verify_range_proof_batch", "qq_multi_msm", "qq_multi_msm_dev", "qq_points_sum_dev",
 ]
 
 
@@ -121,6 +124,21 @@ def load_library():
     lib.qq_verify_set_transcripts.argtypes = [vp, ctypes.c_int]
     lib.qq_verify_set_aggregation.argtypes = [vp, ctypes.c_int]
     szp = ctypes.POINTER(ctypes.c_size_t)
+    lib.qq_init_multi.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+    lib.qq_destroy_multi.argtypes = [vp]
+    lib.qq_destroy_multi.restype = None
+    lib.qq_multi_device_count.argtypes = [vp]
+    lib.qq_multi_ctx.argtypes = [vp, ctypes.c_int]
+    lib.qq_multi_ctx.restype = vp
+    lib.qq_multi_last_error.argtypes = [vp]
+    lib.qq_multi_last_error.restype = ctypes.c_char_p
+    lib.qq_multi_update_account_batch.argtypes = [vp, u8p, u8p, u8p, u8p, u8p, u8p, sz]
+    lib.qq_multi_generate_commitment_batch.argtypes = [vp, u8p, u8p, u8p, u8p, u8p, sz]
+    lib.qq_multi_verify_shuffle_batch.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, u8p, u8p, u8p, u8p, sz, u8p, u8p, u8p]
+    lib.qq_multi_verify_range_proof_batch.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, u8p, ctypes.c_char_p, u8p, u8p, sz, sz, sz, sz, u8p]
+    lib.qq_multi_msm.argtypes = [vp, u8p, u8p, sz, u8p, u8p]
+    lib.qq_multi_msm_dev.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), szp, u8p, u8p]
+    lib.qq_points_sum_dev.argtypes = [vp, u8p, sz, sz, u8p, u8p, u8p]
     lib.qq_shuffle_proofs_from_bincode.argtypes = [u8p, sz, sz, u8p, szp]
     lib.qq_shuffle_statements_from_bincode.argtypes = [u8p, sz, sz, u8p, szp]
     lib.qq_shuffle_proofs_to_bincode.argtypes = [u8p, sz, u8p, sz, szp]
@@ -154,6 +172,73 @@ def _u8(a, nbytes=None):
 
 def _ptr(a):
     return ctypes.c_void_p(a.ctypes.data)
+
+
+class MultiEngine:
+    """qq_multi: several GPUs behind one handle (one context + worker thread per device, device 0 of the list is the root)."""
+
+    def __init__(self, devices):
+        self.lib = load_library()
+        self.h = ctypes.c_void_p()
+        arr = (ctypes.c_int * len(devices))(*devices)
+        rc = self.lib.qq_init_multi(ctypes.byref(self.h), arr, len(devices))
+        if rc != QQ_OK:
+            raise QQError("qq_init_multi failed (%d); there is no CPU fallback" % rc)
+        self.ndev = len(devices)
+
+    def close(self):
+        if self.h:
+            self.lib.qq_destroy_multi(self.h)
+            self.h = ctypes.c_void_p()
+
+    def _ck(self, rc, what):
+        if rc != QQ_OK:
+            raise QQError("%s failed (%d): %s" % (what, rc, (self.lib.qq_multi_last_error(self.h) or b"").decode()))
+
+    def ctx(self, index):
+        return self.lib.qq_multi_ctx(self.h, index)
+
+    def update_account(self, acc, bl, u, c):
+        acc, bl, u, c = _u8(acc), _u8(bl), _u8(u), _u8(c)
+        n = acc.size // 128
+        out, st = np.zeros(n * 128, np.uint8), np.zeros(n, np.uint8)
+        self._ck(self.lib.qq_multi_update_account_batch(self.h, _ptr(acc), _ptr(bl), _ptr(u), _ptr(c), _ptr(out), _ptr(st), n),
+                 "qq_multi_update_account_batch")
+        return out.reshape(n, 128), st
+
+    def msm(self, scalars, points):
+        s, p = _u8(scalars), _u8(points)
+        n = s.size // 32
+        out, st = np.zeros(32, np.uint8), np.zeros(1, np.uint8)
+        self._ck(self.lib.qq_multi_msm(self.h, _ptr(s), _ptr(p), n, _ptr(out), _ptr(st)), "qq_multi_msm")
+        return out, int(st[0])
+
+    def msm_dev(self, scalar_ptrs, point_ptrs, counts):
+        nd = self.ndev
+        sp = (ctypes.c_void_p * nd)(*scalar_ptrs)
+        pp = (ctypes.c_void_p * nd)(*point_ptrs)
+        cn = (ctypes.c_size_t * nd)(*counts)
+        out, st = np.zeros(32, np.uint8), np.zeros(1, np.uint8)
+        self._ck(self.lib.qq_multi_msm_dev(self.h, sp, pp, cn, _ptr(out), _ptr(st)), "qq_multi_msm_dev")
+        return out, int(st[0])
+
+    def verify_shuffle(self, shuffle_input, shuffle_output, statement, proof, transcript_label=b"ShuffleProof", verifier_label=b"Shuffle"):
+        si, so, stm, pr = (_u8(a) for a in (shuffle_input, shuffle_output, statement, proof))
+        nproofs = pr.size // 3776
+        st, sg, det = (np.zeros(nproofs, np.uint8) for _ in range(3))
+        self._ck(self.lib.qq_multi_verify_shuffle_batch(self.h, transcript_label, verifier_label, _ptr(si), _ptr(so), _ptr(stm), _ptr(pr),
+                                                        nproofs, _ptr(st), _ptr(sg), _ptr(det)), "qq_multi_verify_shuffle_batch")
+        return st, sg, det
+
+    def verify_range_proofs(self, commitments, proofs, m, chain=1, n_bits=64, transcript_label=b"SenderAccountProof",
+                            verifier_label=b"BulletProof", domain_label=b"AggregateBulletProof"):
+        cm, pr = _u8(commitments), _u8(proofs)
+        per = (9 + 2 * ((n_bits * m).bit_length() - 1)) * 32 * chain
+        nproofs = pr.size // per
+        st = np.zeros(nproofs, np.uint8)
+        self._ck(self.lib.qq_multi_verify_range_proof_batch(self.h, transcript_label, verifier_label, None, domain_label, _ptr(cm), _ptr(pr),
+                                                            n_bits, m, chain, nproofs, _ptr(st)), "qq_multi_verify_range_proof_batch")
+        return st
 
 
 # ---- wire format (host-only helpers of the library; no GPU context) ------------------------------------------------------
@@ -660,6 +745,13 @@ class Engine:
         out, ident = np.zeros(32, np.uint8), np.zeros(1, np.uint8)
         self._ck(self.lib.qq_points_sum(self.h, _ptr(xyzt), k, _ptr(out), _ptr(ident)), "qq_points_sum")
         return out, bool(ident[0])
+
+    def points_sum_dev(self, records_ptr, k, stride=144):
+        """sum of k partial MSM results resident in device memory (records of `stride` bytes) -> (compressed, identity?, status)"""
+        out, ident, st = np.zeros(32, np.uint8), np.zeros(1, np.uint8), np.zeros(1, np.uint8)
+        self._ck(self.lib.qq_points_sum_dev(self.h, ctypes.c_void_p(records_ptr), k, stride, _ptr(out), _ptr(ident), _ptr(st)),
+                 "qq_points_sum_dev")
+        return out, bool(ident[0]), int(st[0])
 
     def msm_segmented(self, scalars, points, offsets):
         scalars, points = _u8(scalars), _u8(points)

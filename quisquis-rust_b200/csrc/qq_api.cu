@@ -1384,3 +1384,4 @@ extern "C" int qq_fixed_base_i64_batch(qq_ctx* ctx, int which, const int64_t* v,
 #include "qq_api_shuffle.inc"
 #include "qq_api_rangeproof.inc"
 #include "qq_api_wire.inc"
+#include "qq_api_multi.inc"

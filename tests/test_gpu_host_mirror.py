@@ -44,3 +44,14 @@ def test_cpp_host_mirror(tmp_path, pkg):
                            "-L" + libdir, "-lqq_b200", "-Wl,-rpath," + libdir])
     out = subprocess.run([str(exe), str(fx), str(fs), str(fr)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "HOST_API_TEST OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_cpp_multi_device_handle(tmp_path, pkg):
+    """qq_init_multi / qq_multi_* through the C ABI from plain C++ (tests/csrc/multi_api_test.cpp): account batches, commitments
+    and ONE MSM split over every visible GPU equal the single-context results byte for byte."""
+    exe = tmp_path / "multi_api_test"
+    libdir = os.path.join(ROOT, "quisquis-rust_b200")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", str(exe), os.path.join(ROOT, "tests", "csrc", "multi_api_test.cpp"),
+                           "-L" + libdir, "-lqq_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "MULTI_API_TEST OK" in out.stdout, out.stdout + out.stderr
