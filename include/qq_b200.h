@@ -154,6 +154,29 @@ int qq_fixed_base_i64_batch(qq_ctx* ctx, int which, const int64_t* v, uint8_t* o
 int qq_fixed_base_i64_batch_dev(qq_ctx* ctx, int which, const int64_t* v, uint8_t* out_points, size_t n);
 int qq_fixed_base_window(const qq_ctx* ctx, int which);
 
+/* ---- secret scalars ----------------------------------------------------------------------------------
+ * The wallet side of the path handles secrets: u, c, bl of update_account, r of update_public_key / generate_commitment /
+ * create_delta_and_epsilon_accounts, sk of verify_account / decommit, and the blindings of the provers (src/accounts/prover.rs).
+ * curve25519-dalek reads its window tables with LookupTable::select (every entry touched, masked) for them.
+ * qq_set_secret_mode(ctx, 1): the variable-base kernels scan all nine entries of a window table and keep one with masks,
+ * fixed-base batches use the shared-memory 6-bit table with the same masked scan of a window's 33 entries (the large-window
+ * tables in L2 / HBM and the four-lane small-batch kernels, whose reads are addressed by the digit, are not used), 64-bit
+ * values are expanded to scalars first.  Control flow was already independent of the scalars in either mode.  Entry points
+ * covered: qq_update_public_key_batch, qq_mul_commitment_batch, qq_generate_commitment_batch, qq_update_account_batch,
+ * qq_delta_epsilon_batch, qq_verify_account_batch, qq_decommit_batch, qq_fixed_base_batch, qq_fixed_base_i64_batch,
+ * qq_sigma_commit_batch (and their _dev forms).  Outputs are byte-identical in both modes.  The verifiers and the MSMs work on
+ * public data and ignore the mode.  Default off (QQ_SECRET_MODE=1 in the environment turns it on at qq_init). */
+int qq_set_secret_mode(qq_ctx* ctx, int on);
+int qq_secret_mode(const qq_ctx* ctx);
+/* Prover-side sigma-protocol commitments: out_i = enc(r_i * dec(P_i)) when v == NULL, enc(v_i * B + r_i * dec(P_i)) otherwise -
+ * the e / f maps of Prover::verify_delta_compact_prover (src/accounts/prover.rs:164-207), verify_account_prover (:415-454),
+ * zero_balance_account_vector_prover (:629-640), destroy_account_prover (:742-753), verify_update_account_dark_tx_prover
+ * (:885-921).  points, r, v, out_points: n x 32 B.  status as for qq_generate_commitment_batch. */
+int qq_sigma_commit_batch(qq_ctx* ctx, const uint8_t* points, const uint8_t* r, const uint8_t* v, uint8_t* out_points,
+                          uint8_t* status, size_t n);
+int qq_sigma_commit_batch_dev(qq_ctx* ctx, const uint8_t* points, const uint8_t* r, const uint8_t* v, uint8_t* out_points,
+                              uint8_t* status, size_t n);
+
 /* ---- multiscalar multiplication --------------------------------------------------------------------------------
  * Verifier::multiscalar_multiplication = RistrettoPoint::optional_multiscalar_mul over compressed points
  * (src/accounts/verifier.rs:91-99) and the Bulletproofs verification mega-MSM reached from

@@ -30,6 +30,7 @@ EXPORTS = [
     "qq_verify_set_transcripts", "qq_verify_set_aggregation",
     "qq_shuffle_proofs_from_bincode", "qq_shuffle_statements_from_bincode", "qq_shuffle_proofs_to_bincode",
     "qq_shuffle_statements_to_bincode", "qq_accounts_from_bincode", "qq_sigma_proof_from_bincode",
+    "qq_set_secret_mode", "qq_secret_mode", "qq_sigma_commit_batch", "qq_sigma_commit_batch_dev",
     "qq_init_multi", "qq_destroy_multi", "qq_multi_device_count", "qq_multi_ctx", "qq_multi_last_error",
     "qq_multi_update_account_batch", "qq_multi_generate_commitment_batch", "qq_multi_verify_shuffle_batch",
     "qq_multi_verify_range_proof_batch", "qq_multi_msm", "qq_multi_msm_dev", "qq_points_sum_dev",
@@ -124,6 +125,10 @@ def load_library():
     lib.qq_verify_set_transcripts.argtypes = [vp, ctypes.c_int]
     lib.qq_verify_set_aggregation.argtypes = [vp, ctypes.c_int]
     szp = ctypes.POINTER(ctypes.c_size_t)
+    lib.qq_set_secret_mode.argtypes = [vp, ctypes.c_int]
+    lib.qq_secret_mode.argtypes = [vp]
+    for name in ("qq_sigma_commit_batch", "qq_sigma_commit_batch_dev"):
+        getattr(lib, name).argtypes = [vp, u8p, u8p, u8p, u8p, u8p, sz]
     lib.qq_init_multi.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int), ctypes.c_int]
     lib.qq_destroy_multi.argtypes = [vp]
     lib.qq_destroy_multi.restype = None
@@ -666,6 +671,20 @@ class Engine:
     def verify_set_transcripts(self, on_device=True):
         """Shuffle verifier: per-proof transcripts / scalar algebra in GPU transcript kernels (default) or on the host threads."""
         self._ck(self.lib.qq_verify_set_transcripts(self.h, 1 if on_device else 0), "qq_verify_set_transcripts")
+
+    def set_secret_mode(self, on=True):
+        """Constant-time table access for the scalar multiplications of the wallet / prover entry points (see the header)."""
+        self._ck(self.lib.qq_set_secret_mode(self.h, 1 if on else 0), "qq_set_secret_mode")
+
+    def sigma_commit(self, points, r, v=None):
+        """out_i = enc(r_i * P_i [+ v_i * B]): the provers' e / f commitment maps (src/accounts/prover.rs)."""
+        points, r = _u8(points), _u8(r)
+        n = points.size // 32
+        vv = _u8(v) if v is not None else None
+        out, st = np.zeros(n * 32, np.uint8), np.zeros(n, np.uint8)
+        self._ck(self.lib.qq_sigma_commit_batch(self.h, _ptr(points), _ptr(r), _ptr(vv) if vv is not None else None, _ptr(out), _ptr(st), n),
+                 "qq_sigma_commit_batch")
+        return out.reshape(n, 32), st
 
     def verify_set_aggregation(self, on=True):
         """Shuffle verifier: identity equations of all proofs in one weighted Pippenger MSM (default) or one MSM per equation."""

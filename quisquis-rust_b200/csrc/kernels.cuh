@@ -76,7 +76,7 @@ struct vb_args {
 // (the barrier sits at the top of the round; threads past the end skip the work, so a 9-account call is not slowed
 // down by 500 idle lanes repeating it).
 #define QQ_VB_BLOCK 512
-template <int NS>
+template <int NS, bool SECRET = false>
 __global__ void __launch_bounds__(QQ_VB_BLOCK, 1) k_varbase(vb_args a) {
     size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -92,12 +92,12 @@ __global__ void __launch_bounds__(QQ_VB_BLOCK, 1) k_varbase(vb_args a) {
         u32 s[8];
         load_words32(s, a.s0, t / (size_t)a.sdiv);
         if (a.halve0) sc_halve(s, s);
-        vb_scalarmult(r, tbl, s);
+        vb_scalarmult_t<false, SECRET>(r, tbl, s);
         ge_p3_store(a.out0 + QQ_PT_Q * t, r);
         if (NS == 2) {
             load_words32(s, a.s1, t / (size_t)a.sdiv);
             if (a.halve1) sc_halve(s, s);
-            vb_scalarmult(r, tbl, s);
+            vb_scalarmult_t<false, SECRET>(r, tbl, s);
             ge_p3_store(a.out1 + QQ_PT_Q * t, r);
         }
     }
@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(QQ_VB_BLOCK, 1) k_varbase(vb_args a) {
 
 // Two scalars per point through the split tables (vbs_*): 312 doublings per point instead of 504.  The four tables of
 // a thread (4.6 KB) are written once and read 128 times; they stream through L2.
+template <bool SECRET = false>
 __global__ void __launch_bounds__(QQ_VB_BLOCK, 1) k_varbase_split(vb_args a) {
     size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -120,11 +121,11 @@ __global__ void __launch_bounds__(QQ_VB_BLOCK, 1) k_varbase_split(vb_args a) {
         u32 s[8];
         load_words32(s, a.s0, t / (size_t)a.sdiv);
         if (a.halve0) sc_halve(s, s);
-        vbs_scalarmult(r, tbl, s);
+        vbs_scalarmult<SECRET>(r, tbl, s);
         ge_p3_store(a.out0 + QQ_PT_Q * t, r);
         load_words32(s, a.s1, t / (size_t)a.sdiv);
         if (a.halve1) sc_halve(s, s);
-        vbs_scalarmult(r, tbl, s);
+        vbs_scalarmult<SECRET>(r, tbl, s);
         ge_p3_store(a.out1 + QQ_PT_Q * t, r);
     }
 }
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(128) k_varbase_coop(vb_args a, int ns) {
 }
 
 // ---- fixed-base scalar multiplication: table staged in shared memory ---------------------------------------------
-template <int W>
+template <int W, bool SECRET = false>
 __global__ void __launch_bounds__(512) k_fixedbase(const u32* __restrict__ tbl_g, const u32x4* __restrict__ s, int halve,
                                                    u32x4* __restrict__ out, size_t n) {
     extern __shared__ __align__(16) u32 tbl_s[];
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(512) k_fixedbase(const u32* __restrict__ tbl_g
         load_words32(w, s, t);
         if (halve) sc_halve(w, w);
         ge_p3 r;
-        fb_scalarmult<W>(r, tbl_s, w);
+        fb_scalarmult<W, SECRET>(r, tbl_s, w);
         ge_p3_store(out + QQ_PT_Q * t, r);
     }
 }
@@ -512,6 +513,29 @@ struct straus_args {
     const unsigned int* order; // instances sorted by term count (descending) so a warp's lanes do equal work
     size_t m;
 };
+// signed 64-bit values -> canonical scalars (v mod l), branch-free: |v| and l - |v| are both formed, the sign selects
+__global__ void k_i64_to_scalars(const long long* __restrict__ v, u32x4* __restrict__ out, size_t n) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        long long x = v[i];
+        u32 neg = (u32)((unsigned long long)x >> 63);
+        unsigned long long mag = ((unsigned long long)x ^ (0ull - (unsigned long long)neg)) + neg;      // |x| (2^63 for INT64_MIN)
+        u32 a[8] = {(u32)mag, (u32)(mag >> 32), 0, 0, 0, 0, 0, 0}, b[8];
+        u32 borrow = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            u64 d = (u64)sc_l_word(k) - a[k] - borrow;
+            b[k] = (u32)d;
+            borrow = (u32)(d >> 63);
+        }
+        u32 use_b = neg & (u32)(mag != 0);
+        u32 m = 0u - use_b;
+        u32 w[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) w[k] = a[k] ^ (m & (a[k] ^ b[k]));
+        store_words32(out, i, w);
+    }
+}
 // status of an MSM evaluated in `group` parts: a non-canonical scalar wins over an undecodable point
 __global__ void k_group_status(const uint8_t* __restrict__ part, int group, uint8_t* __restrict__ status, size_t mo) {
     size_t stride = (size_t)gridDim.x * blockDim.x;

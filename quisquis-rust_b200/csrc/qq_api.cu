@@ -122,6 +122,8 @@ struct qq_ctx {
     bool stc_ready = false;                    // k_straus_coop's shared-memory opt-in done
     int straus_minb = 4;                       // k_straus build for more than one wave of instances (QQ_STRAUS_MINB)
     int stc_per_sm = 64;                       // segmented MSMs: four-lane cooperative kernel up to this many MSMs per SM (QQ_STRAUS_COOP_PER_SM)
+    bool secret_mode = false;                  // qq_set_secret_mode: constant-time table access for scalars that are secrets
+    int vb_blocks_per_sm_secret[3] = {0, 0, 0};
     int shuffle_exact_split = 0;               // parts per exact MSM (G, H, g_r, h_r) of the aggregate form: 1, 2, 3; 0 = by batch size
     bool verify_aggregate = true;              // qq_verify_set_aggregation: identity equations of the shuffle proofs in one weighted Pippenger MSM
     bool verify_host_transcripts = false;      // qq_verify_set_transcripts(ctx, 0): per-proof phases of the shuffle verifier on the host threads
@@ -238,7 +240,8 @@ static int launch_decompress(qq_ctx* ctx, const void* in, idx_map map, u32x4* pt
     return QQ_OK;
 }
 static size_t vb_scratch_bytes(qq_ctx* ctx, int ns) {
-    return (size_t)ctx->sms * ctx->vb_blocks_per_sm[ns] * QQ_VB_BLOCK * (ns == 2 ? QQ_VBS_TABLE_WORDS : QQ_VB_TABLE_WORDS) * 4;
+    int bps = ctx->vb_blocks_per_sm[ns] > ctx->vb_blocks_per_sm_secret[ns] ? ctx->vb_blocks_per_sm[ns] : ctx->vb_blocks_per_sm_secret[ns];
+    return (size_t)ctx->sms * bps * QQ_VB_BLOCK * (ns == 2 ? QQ_VBS_TABLE_WORDS : QQ_VB_TABLE_WORDS) * 4;
 }
 static int launch_varbase(qq_ctx* ctx, int ns, const u32x4* pts, idx_map map, const void* s0, const void* s1, int sdiv,
                           u32x4* out0, u32x4* out1, u32x4* scratch, size_t n, int halve0 = 0, int halve1 = 0) {
@@ -252,7 +255,9 @@ static int launch_varbase(qq_ctx* ctx, int ns, const u32x4* pts, idx_map map, co
     // While the lanes are not all busy, four lanes per scalar multiplication (k_varbase_coop): measured faster up to
     // ~19 000 scalar mults (0.66 against 0.98 ms), slower from ~38 000 (1.23 against 1.01 ms); switch at 160 per SM.
     size_t coop_max = ctx->vbc_max_jobs < 0 ? (size_t)ctx->sms * 160 : (size_t)ctx->vbc_max_jobs;
-    if (n * (size_t)ns <= coop_max) {
+    // secret mode: only the kernels whose table access is a masked scan of the whole table (the cooperative kernel reads its
+    // shared-memory table by digit)
+    if (!ctx->secret_mode && n * (size_t)ns <= coop_max) {
         size_t threads = n * (size_t)ns * 4;
         int cb = 32;
         while (cb < 128 && (threads + cb - 1) / cb > (size_t)ctx->sms * 4) cb *= 2;
@@ -264,15 +269,20 @@ static int launch_varbase(qq_ctx* ctx, int ns, const u32x4* pts, idx_map map, co
         return QQ_OK;
     }
     int block = QQ_VB_BLOCK;
-    int grid = ctx->sms * ctx->vb_blocks_per_sm[ns];
+    int grid = ctx->sms * (ctx->secret_mode ? ctx->vb_blocks_per_sm_secret[ns] : ctx->vb_blocks_per_sm[ns]);
     if ((size_t)grid * QQ_VB_BLOCK > n) {
         block = 32;
         while (block < QQ_VB_BLOCK && (n + block - 1) / block > (size_t)ctx->sms * 4) block *= 2;
         grid = (int)((n + block - 1) / block);
     }
     span_begin(ctx, FAM_VB);
-    if (ns == 1) k_varbase<1><<<grid, block, 0, ctx->stream>>>(a);
-    else k_varbase_split<<<grid, block, 0, ctx->stream>>>(a);
+    if (ctx->secret_mode) {
+        if (ns == 1) k_varbase<1, true><<<grid, block, 0, ctx->stream>>>(a);
+        else k_varbase_split<true><<<grid, block, 0, ctx->stream>>>(a);
+    } else {
+        if (ns == 1) k_varbase<1><<<grid, block, 0, ctx->stream>>>(a);
+        else k_varbase_split<false><<<grid, block, 0, ctx->stream>>>(a);
+    }
     span_end(ctx);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -281,7 +291,7 @@ static int launch_varbase(qq_ctx* ctx, int ns, const u32x4* pts, idx_map map, co
 static size_t fb_table_words() { return (size_t)fb_num_windows(QQ_FB_W) * fb_entries(QQ_FB_W) * QQ_NIELS_WORDS; }
 static int launch_fixedbase(qq_ctx* ctx, int which, const void* s, u32x4* out, size_t n, int halve = 0) {
     if (n == 0) return QQ_OK;
-    if (ctx->fbt[which] != nullptr && n >= QQ_FBT_MIN_BATCH) {
+    if (!ctx->secret_mode && ctx->fbt[which] != nullptr && n >= QQ_FBT_MIN_BATCH) {
         span_begin(ctx, FAM_FB);
         k_fixedbase_big<<<grid_for(n, QQ_FBT_BLOCK, ctx->sms * 4), QQ_FBT_BLOCK, 0, ctx->stream>>>(ctx->fbt[which], ctx->fbt_g[which],
                                                                                 (const u32x4*)s, halve, out, n);
@@ -294,7 +304,9 @@ static int launch_fixedbase(qq_ctx* ctx, int which, const void* s, u32x4* out, s
     int grid = (int)((n + 511) / 512);
     if (grid > ctx->sms) grid = ctx->sms;
     span_begin(ctx, FAM_FB);
-    k_fixedbase<QQ_FB_W><<<grid, 512, smem, ctx->stream>>>(ctx->fb_tbl[which], (const u32x4*)s, halve, out, n);
+    // secret mode: every entry of a window of the shared-memory table is read and masked (33 entries per window)
+    if (ctx->secret_mode) k_fixedbase<QQ_FB_W, true><<<grid, 512, smem, ctx->stream>>>(ctx->fb_tbl[which], (const u32x4*)s, halve, out, n);
+    else k_fixedbase<QQ_FB_W><<<grid, 512, smem, ctx->stream>>>(ctx->fb_tbl[which], (const u32x4*)s, halve, out, n);
     span_end(ctx);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -501,6 +513,13 @@ static int fbt_build(qq_ctx* ctx, int which, int W) {
     ctx->fbt_g[which] = g;
     return QQ_OK;
 }
+// Secret-scalar mode (the wallet's update / commitment scalars and the provers' blindings are secrets).
+extern "C" int qq_set_secret_mode(qq_ctx* ctx, int on) {
+    if (!ctx) return QQ_ERR_ARG;
+    ctx->secret_mode = on != 0;
+    return QQ_OK;
+}
+extern "C" int qq_secret_mode(const qq_ctx* ctx) { return ctx && ctx->secret_mode ? 1 : 0; }
 extern "C" int qq_varbase_set_coop_limit(qq_ctx* ctx, long max_scalar_mults) {
     if (!ctx) return QQ_ERR_ARG;
     ctx->vbc_max_jobs = max_scalar_mults;
@@ -563,11 +582,18 @@ extern "C" int qq_init(qq_ctx** out, int device) {
         CK(cudaFuncSetAttribute(k_msm_sum_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * QQ_PT_BYTES));
         CK(cudaFuncSetAttribute(k_fixedbase<QQ_FB_W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(fb_table_words() * 4)));
+        CK(cudaFuncSetAttribute(k_fixedbase<QQ_FB_W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(fb_table_words() * 4)));
         int occ = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_varbase<1>, QQ_VB_BLOCK, 0));
         ctx->vb_blocks_per_sm[1] = occ > 0 ? occ : 1;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_varbase_split, QQ_VB_BLOCK, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_varbase_split<false>, QQ_VB_BLOCK, 0));
         ctx->vb_blocks_per_sm[2] = occ > 0 ? occ : 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_varbase<1, true>, QQ_VB_BLOCK, 0));
+        ctx->vb_blocks_per_sm_secret[1] = occ > 0 ? occ : 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_varbase_split<true>, QQ_VB_BLOCK, 0));
+        ctx->vb_blocks_per_sm_secret[2] = occ > 0 ? occ : 1;
+        if (const char* e = getenv("QQ_SECRET_MODE")) ctx->secret_mode = atoi(e) != 0;
         // fixed-base tables for B and H, built on the device from their compressed encodings
         const uint8_t* BASE_PK = QQ_BASE_PK_BYTES;
         memcpy(ctx->base_pk, BASE_PK, 64);
@@ -949,7 +975,7 @@ static int core_fixed_base(qq_ctx* ctx, int which, const uint8_t* s, uint8_t* ou
         u32x4* F = ws_take<u32x4>(ctx, m * QQ_PT_BYTES);
         dc_ws dc = dc_take(ctx, m);
         CKQ(launch_status(ctx, s + base * 32, nullptr, nullptr, nullptr, 0, status + base, m));
-        if (ctx->fbt[which] != nullptr && m >= QQ_FBT_MIN_BATCH) {
+        if (!ctx->secret_mode && ctx->fbt[which] != nullptr && m >= QQ_FBT_MIN_BATCH) {
             // table walk fused with the first stage of the batch encoder: the extended point never goes to HBM
             span_begin(ctx, FAM_FB);
             k_fixedbase_big_dc<<<grid_for(m, QQ_FBT_BLOCK, ctx->sms * 4), QQ_FBT_BLOCK, 0, ctx->stream>>>(
@@ -1334,6 +1360,24 @@ extern "C" int qq_fixed_base_batch(qq_ctx* ctx, int which, const uint8_t* s, uin
 
 // 64-bit signed values (balances): out_i = enc(v_i * Base).  Needs a large-window table (qq_fixed_base_set_window != 0).
 static int core_fixed_base_i64(qq_ctx* ctx, int which, const int64_t* v, uint8_t* out, size_t n) {
+    if (ctx->secret_mode) {
+        // balances are secrets on the wallet side: expanded to canonical scalars and sent through the masked-scan table walk
+        const size_t CH = (size_t)1 << 22;
+        for (size_t base = 0; base < n; base += CH) {
+            size_t m = n - base < CH ? n - base : CH;
+            CKQ(ws_begin(ctx, ws_need({m * QQ_PT_BYTES, m * 32, m}) + dc_scratch_bytes(m)));
+            u32x4* F = ws_take<u32x4>(ctx, m * QQ_PT_BYTES);
+            uint8_t* sc = ws_take<uint8_t>(ctx, m * 32);
+            uint8_t* st = ws_take<uint8_t>(ctx, m);
+            dc_ws dc = dc_take(ctx, m);
+            k_i64_to_scalars<<<grid_for(m, 256, ctx->sms * 8), 256, 0, ctx->stream>>>((const long long*)(v + base), (u32x4*)sc, m);
+            ctx->launches++;
+            CK(cudaMemsetAsync(st, 0, m, ctx->stream));
+            CKQ(launch_fixedbase(ctx, which, sc, F, m, 1));
+            CKQ(launch_finish_dbl(ctx, dc, fsrc(F, IDENT), FNONE, FNONE, out + base * 32, IDENT, st, 1, m));
+        }
+        return QQ_OK;
+    }
     if (ctx->fbt[which] == nullptr) {
         ctx->err = "qq_fixed_base_i64_batch needs a large-window table (qq_fixed_base_set_window)";
         return QQ_ERR_ARG;
@@ -1376,6 +1420,54 @@ extern "C" int qq_fixed_base_i64_batch(qq_ctx* ctx, int which, const int64_t* v,
     CKQ(st.outbuf(n * 32, &dout));
     CKQ(core_fixed_base_i64(ctx, which, (const int64_t*)dv, dout, n));
     CKQ(st.back(out_points, dout, n * 32));
+    return call_end(ctx);
+}
+
+// Prover-side sigma-protocol commitments (reference src/accounts/prover.rs:164-207, 415-454, 629-640,
+// 742-753, 885-921): every e / f the provers compute is  r_i * P_i  (P_i = a key or commitment component of an account) or
+// v_i * B + r_i * P_i.  out_i = enc(r_i * dec(P_i) [+ v_i * B]); v == nullptr: no fixed-base term.  The blindings are
+// secrets: callers switch qq_set_secret_mode on.
+static int core_sigma_commit(qq_ctx* ctx, const uint8_t* points, const uint8_t* r, const uint8_t* v, uint8_t* out, uint8_t* status,
+                             size_t n) {
+    for (size_t base = 0; base < n; base += QQ_CHUNK) {
+        size_t m = n - base < QQ_CHUNK ? n - base : QQ_CHUNK;
+        CKQ(ws_begin(ctx, ws_need({m * QQ_PT_BYTES, m * QQ_PT_BYTES, m * QQ_PT_BYTES, m, vb_scratch_bytes(ctx, 1)}) + dc_scratch_bytes(m)));
+        u32x4* P = ws_take<u32x4>(ctx, m * QQ_PT_BYTES);
+        u32x4* R = ws_take<u32x4>(ctx, m * QQ_PT_BYTES);
+        u32x4* F = ws_take<u32x4>(ctx, m * QQ_PT_BYTES);
+        uint8_t* ok = ws_take<uint8_t>(ctx, m);
+        u32x4* scratch = ws_take<u32x4>(ctx, vb_scratch_bytes(ctx, 1));
+        dc_ws dc = dc_take(ctx, m);
+        CKQ(launch_decompress(ctx, points + base * 32, IDENT, P, ok, m));
+        CKQ(launch_status(ctx, r + base * 32, v ? v + base * 32 : nullptr, nullptr, ok, 1, status + base, m));
+        CKQ(launch_varbase(ctx, 1, P, IDENT, r + base * 32, nullptr, 1, R, nullptr, scratch, m, 1));
+        if (v) CKQ(launch_fixedbase(ctx, QQ_BASE_B, v + base * 32, F, m, 1));
+        CKQ(launch_finish_dbl(ctx, dc, fsrc(R, IDENT), v ? fsrc(F, IDENT) : FNONE, FNONE, out + base * 32, IDENT, status + base, 1, m));
+    }
+    return QQ_OK;
+}
+extern "C" int qq_sigma_commit_batch_dev(qq_ctx* ctx, const uint8_t* points, const uint8_t* r, const uint8_t* v, uint8_t* out_points,
+                                         uint8_t* status, size_t n) {
+    ENTER();
+    REQUIRE(aligned16(points) && aligned16(r) && (v == nullptr || aligned16(v)) && aligned16(out_points) && status);
+    CKQ(core_sigma_commit(ctx, points, r, v, out_points, status, n));
+    return call_end(ctx);
+}
+extern "C" int qq_sigma_commit_batch(qq_ctx* ctx, const uint8_t* points, const uint8_t* r, const uint8_t* v, uint8_t* out_points,
+                                     uint8_t* status, size_t n) {
+    ENTER();
+    REQUIRE(points && r && out_points && status);
+    stage st(ctx);
+    CKQ(st.plan({(size_t)(n * 32), (size_t)(n * 32), (size_t)(n * 32), (size_t)(n * 32), (size_t)n}));
+    uint8_t *dp, *dr, *dv = nullptr, *dout, *dst;
+    CKQ(st.in(points, n * 32, &dp));
+    CKQ(st.in(r, n * 32, &dr));
+    if (v) CKQ(st.in(v, n * 32, &dv));
+    CKQ(st.outbuf(n * 32, &dout));
+    CKQ(st.outbuf(n, &dst));
+    CKQ(core_sigma_commit(ctx, dp, dr, dv, dout, dst, n));
+    CKQ(st.back(out_points, dout, n * 32));
+    CKQ(st.back(status, dst, n));
     return call_end(ctx);
 }
 

@@ -81,9 +81,43 @@ QQ_HD void vb_build_table(u32x4* tbl, const ge_p3& p) {
     }
 }
 
+// Table lookup of entry idx (0 .. nent - 1) in cached form.
+// SECRET = false: the entry is read directly - uniform control flow, but the ADDRESS depends on the digit (verifier side,
+// public scalars).  SECRET = true (qq_set_secret_mode: the wallet's u, c, bl, r, sk and the provers' blindings): every entry is
+// read and the wanted one kept with masks, so the address stream is the same for every scalar - the constant-time table
+// access curve25519-dalek's LookupTable::select gives the reference (window.rs; reached through variable_base::mul).
+template <bool SECRET>
+QQ_HD void vb_lookup(ge_cached& c, const u32x4* tbl, u32 idx, int nent = QQ_VB_ENTRIES) {
+    if constexpr (!SECRET) {
+        ge_cached_load(c, tbl + QQ_PT_Q * idx);
+    } else {
+    u32 acc[32];
+#pragma unroll
+    for (int w = 0; w < 32; w++) acc[w] = 0;
+    for (int i = 0; i < nent; i++) {
+        const u32 m = 0u - (u32)((((u32)i ^ idx) - 1u) >> 31);      // all ones when i == idx
+#pragma unroll
+        for (int q = 0; q < QQ_PT_Q; q++) {
+            const u32x4 v = tbl[QQ_PT_Q * i + q];
+            acc[4 * q + 0] |= v.x & m;
+            acc[4 * q + 1] |= v.y & m;
+            acc[4 * q + 2] |= v.z & m;
+            acc[4 * q + 3] |= v.w & m;
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        c.YpX.v[w] = acc[w];
+        c.YmX.v[w] = acc[8 + w];
+        c.Z2.v[w] = acc[16 + w];
+        c.T2d.v[w] = acc[24 + w];
+    }
+    }
+}
+
 // r = s * P using a table built by vb_build_table.  s: 8 little-endian words, s < 2^253.
 // ROLLED keeps one copy of the doubling body (smaller instruction footprint; T is computed by every doubling).
-template <bool ROLLED>
+template <bool ROLLED, bool SECRET = false>
 QQ_HD void vb_scalarmult_t(ge_p3& r, const u32x4* tbl, const u32 s[8]) {
     u32 rr[9];
     sc_recode_bias<4, 64>(rr, s);        // rr[8] == 0 for s < 2^253
@@ -109,15 +143,16 @@ QQ_HD void vb_scalarmult_t(ge_p3& r, const u32x4* tbl, const u32 s[8]) {
 #pragma unroll
         for (int i = 7; i > 0; i--) w[i] = (w[i] << 4) | (w[i - 1] >> 28);
         w[0] <<= 4;
-        u32 neg = d < 0 ? 1u : 0u;
-        u32 idx = (u32)(d < 0 ? -d : d);
+        u32 neg = (u32)d >> 31;
+        u32 idx = (u32)((d ^ (d >> 31)) - (d >> 31));      // |d| without a branch
         ge_cached c;
-        ge_cached_load(c, tbl + QQ_PT_Q * idx);
+        vb_lookup<SECRET>(c, tbl, idx);
         ge_cached_cneg(c, neg);
         ge_add(r, r, c);
     }
 }
 QQ_HD void vb_scalarmult(ge_p3& r, const u32x4* tbl, const u32 s[8]) { vb_scalarmult_t<false>(r, tbl, s); }
+QQ_HD void vb_scalarmult_secret(ge_p3& r, const u32x4* tbl, const u32 s[8]) { vb_scalarmult_t<false, true>(r, tbl, s); }
 
 // ---------------------------------------------------------------------------------------------------------
 // Split variable base, for a point that is multiplied by SEVERAL scalars (update_account multiplies each of gr, grsk
@@ -144,6 +179,7 @@ QQ_HD void vbs_build_tables(u32x4* tbl, const ge_p3& p) {
         }
     }
 }
+template <bool SECRET = false>
 QQ_HD void vbs_scalarmult(ge_p3& r, const u32x4* tbl, const u32 s[8]) {
     u32 rr[9];
     sc_recode_bias<4, 64>(rr, s);        // rr[8] == 0 for s < 2^253
@@ -166,10 +202,10 @@ QQ_HD void vbs_scalarmult(ge_p3& r, const u32x4* tbl, const u32 s[8]) {
                 w0 = (w0 << 4);
                 // rotate the four quarter registers so that the loop body stays one copy
                 u32 tw = w0; w0 = w1; w1 = w2; w2 = w3; w3 = tw;
-                u32 neg = d < 0 ? 1u : 0u;
-                u32 idx = (u32)(d < 0 ? -d : d);
+                u32 neg = (u32)d >> 31;
+                u32 idx = (u32)((d ^ (d >> 31)) - (d >> 31));
                 ge_cached c;
-                ge_cached_load(c, tbl + QQ_PT_Q * (part * QQ_VB_ENTRIES + idx));
+                vb_lookup<SECRET>(c, tbl + QQ_PT_Q * (part * QQ_VB_ENTRIES), idx);
                 ge_cached_cneg(c, neg);
                 ge_add(r, r, c);
             }
@@ -195,8 +231,9 @@ QQ_HD void ge_niels_load(ge_niels& n, const u32* src) {
     }
 }
 
-// r = s * Base from table (W-bit signed windows).  tbl may point to shared or global memory.
-template <int W>
+// r = s * Base from table (W-bit signed windows).  tbl may point to shared or global memory.  SECRET: see vb_lookup (all
+// 2^(W-1) + 1 entries of the window are read and masked; meant for the shared-memory table).
+template <int W, bool SECRET = false>
 QQ_HD void fb_scalarmult(ge_p3& r, const u32* tbl, const u32 s[8]) {
     const int NW = (256 + W - 1) / W;
     const int ENT = (1 << (W - 1)) + 1;
@@ -216,10 +253,28 @@ QQ_HD void fb_scalarmult(ge_p3& r, const u32* tbl, const u32 s[8]) {
         }
         u64 two = (u64)lo | ((u64)hi << 32);
         int d = (int)((u32)(two >> sh) & ((1u << W) - 1u)) - (1 << (W - 1));
-        u32 neg = d < 0 ? 1u : 0u;
-        u32 idx = (u32)(d < 0 ? -d : d);
+        u32 neg = (u32)d >> 31;
+        u32 idx = (u32)((d ^ (d >> 31)) - (d >> 31));
         ge_niels n;
-        ge_niels_load(n, tbl + (size_t)(k * ENT + idx) * QQ_NIELS_WORDS);
+        if (SECRET) {
+            u32 acc[QQ_NIELS_WORDS];
+#pragma unroll
+            for (int w = 0; w < QQ_NIELS_WORDS; w++) acc[w] = 0;
+            for (int i = 0; i < ENT; i++) {
+                const u32 m = 0u - (u32)((((u32)i ^ idx) - 1u) >> 31);
+                const u32* e = tbl + (size_t)(k * ENT + i) * QQ_NIELS_WORDS;
+#pragma unroll
+                for (int w = 0; w < QQ_NIELS_WORDS; w++) acc[w] |= e[w] & m;
+            }
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                n.ypx.v[w] = acc[w];
+                n.ymx.v[w] = acc[8 + w];
+                n.xy2d.v[w] = acc[16 + w];
+            }
+        } else {
+            ge_niels_load(n, tbl + (size_t)(k * ENT + idx) * QQ_NIELS_WORDS);
+        }
         ge_niels_cneg(n, neg);
         ge_madd(r, r, n);
     }

@@ -972,6 +972,71 @@ def test_verify_zero_balance_and_sender_account_proofs(engine):
                                                          S_(k[5]), sb(k[6]))
 
 
+def test_secret_mode_outputs_are_identical(engine):
+    """qq_set_secret_mode: the masked-scan table walks of the wallet / prover entry points return the same
+    bytes and status codes as the index-addressed ones - update_public_key, generate_commitment, update_account (small and
+    large batch), delta / epsilon accounts, verify_account, decommit, fixed base (scalars and signed 64-bit values) - and
+    qq_sigma_commit_batch equals the oracle: e = r P, f = v B + r P (src/accounts/prover.rs:164-207)."""
+    st = Stream(b"secret-mode")
+    n = 300
+    accs, sks, vals = [], [], []
+    for i in range(n):
+        a, sk, _ = make_account(st, i % 5)
+        accs.append(a)
+        sks.append(sb(sk))
+        vals.append(sb(i % 5))
+    acc = cat(accs)
+    acc_bad = acc.copy()
+    acc_bad[128 * 3 + 31] |= 0x80
+    bl = cat([sb(st.scalar() % 2**40) for _ in range(n)])
+    u, c, r = (cat([st.scalar_bytes() for _ in range(n)]) for _ in range(3))
+    r_bad = r.copy()
+    r_bad[32 * 5:32 * 6] = np.frombuffer(R.L.to_bytes(32, "little"), np.uint8)
+    base_pk = R.BASEPOINT_COMPRESSED + R.PEDERSEN_H_COMPRESSED
+    i64 = np.array([0, 1, -1, 2**62, -2**63, 12345678901234] + [int(st.scalar() % 2**63) - 2**62 for _ in range(n - 6)], dtype=np.int64)
+    rng = np.random.default_rng(9)
+    big_n = 70000       # past the four-lane small-batch kernels
+    big_acc = np.tile(acc.reshape(n, 128), (big_n // n + 1, 1))[:big_n].copy()
+    big_s = [rng.integers(0, 256, size=(big_n, 32), dtype=np.uint8) for _ in range(3)]
+    for s_ in big_s:
+        s_[:, 31] &= 0x0f
+
+    def run_all():
+        out = []
+        out.append(engine.update_public_key(acc.reshape(n, 128)[:, :64].copy(), r_bad))
+        out.append(engine.generate_commitment(acc.reshape(n, 128)[:, :64].copy(), r, bl))
+        out.append(engine.update_account(acc_bad, bl, u, c))
+        out.append(engine.delta_epsilon(acc, bl, r, base_pk))
+        out.append((engine.verify_account(acc, cat(sks), cat(vals)),))
+        out.append(engine.decommit(acc.reshape(n, 128)[:, 64:].copy(), cat(sks)))
+        out.append(engine.fixed_base(0, r_bad))
+        out.append(engine.fixed_base(1, u))
+        out.append((engine.fixed_base_i64(0, i64),))
+        out.append(engine.update_account(big_acc, big_s[0], big_s[1], big_s[2]))
+        return out
+    try:
+        plain = run_all()
+        engine.set_secret_mode(True)
+        secret = run_all()
+        # prover commitments (always checked in secret mode: the blindings are secrets)
+        pts = acc.reshape(n, 128)[:, 32:64].copy()
+        pts[7, 31] |= 0x80
+        e, es = engine.sigma_commit(pts, r)
+        f, fs = engine.sigma_commit(pts, r, bl)
+    finally:
+        engine.set_secret_mode(False)
+    for a, b in zip(plain, secret):
+        for x, y in zip(a, b):
+            assert np.array_equal(np.asarray(x), np.asarray(y))
+    assert not plain[4][0].any() and plain[2][1][3] == 1 and plain[0][1][5] == 2
+    for i in range(0, n, 17):
+        ri, vi = int.from_bytes(r[32 * i:32 * i + 32].tobytes(), "little"), int.from_bytes(bl[32 * i:32 * i + 32].tobytes(), "little")
+        P = R.decompress(pts[i].tobytes())
+        assert e[i].tobytes() == R.compress(R.mul(ri, P)) and es[i] == 0
+        assert f[i].tobytes() == R.compress(R.add(R.mul(vi, R.BASEPOINT), R.mul(ri, P))) and fs[i] == 0
+    assert es[7] == 1 and fs[7] == 1 and not e[7].any()
+
+
 def test_small_batch_paths_equal_regular_paths(engine):
     """The latency paths taken by small calls (four lanes per scalar multiplication: k_varbase_coop, k_straus_coop; the
     direct batch encoder k_dc_direct) against the throughput paths (qq_varbase_set_coop_limit(0)) and the oracle, on
