@@ -140,6 +140,19 @@ def run_reference(args):
     dt = time.time() - t
     assert not st.any()
     value = m * args.steps / dt
+    # the second half of the metric: Ristretto MSM points/s at 2^20 (compressed points in, decompression included), all cores
+    msm_ref = None
+    if args.msm_points > 0:
+        mm = args.msm_points
+        pts = np.concatenate([C.fixed_base(0, rand_scalars(rng, min(1 << 16, mm - lo)))[0] for lo in range(0, mm, 1 << 16)])
+        a = rand_scalars(rng, mm)
+        C.msm(a[:4096], pts[:4096])
+        t = time.time()
+        mo, ms_ = C.msm(a, pts)
+        dtm = time.time() - t
+        assert ms_ == 0
+        msm_ref = {"points": mm, "ms": dtm * 1e3, "points_per_sec": mm / dtm, "cores": cores, "kind": "port",
+                   "sample": "one %d-point MSM (oracle/qq_oracle.c oq_msm: decode + Pippenger per thread slice + sum), %d host threads" % (mm, cores)}
     line = {
         "impl": "reference", "metric": "account_updates_per_sec", "value": value, "unit": "accounts/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
@@ -155,6 +168,8 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "accounts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if msm_ref:
+        line["msm"] = msm_ref
     emit(line)
 
 
@@ -182,6 +197,13 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
+
+    def maxr_early(x):
+        if world == 1:
+            return x
+        t_ = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        return float(t_.item())
 
     # ---- synthetic inputs: valid accounts with known discrete logs, built with the fixed-base kernel ------------
     cols = [eng.fixed_base(0, rand_scalars(rng, n))[0] for _ in range(4)]
@@ -252,6 +274,55 @@ def run_b200(args):
     assert int(st_pin.max().item()) == 0
     same = bool(torch.equal(out_pin, out_d.cpu()))
     sampler.stop()
+    # SHA-256 of this rank's 128 n output bytes.  Rank r always works on block r of the global batch (inputs seeded with
+    # 1000 + r whatever the world size), so block r's digest is the same in every run that has a rank r: the 1 / 2 / 4 / 8-GPU
+    # outputs are compared block by block, and block 0 against the CPU port below.
+    import hashlib
+    my_hash = hashlib.sha256(out_pin.numpy().tobytes()).digest()
+    if world > 1:
+        ht = torch.from_numpy(np.frombuffer(my_hash, np.uint8).copy()).to(dev)
+        hall = [torch.zeros(32, dtype=torch.uint8, device=dev) for _ in range(world)]
+        dist.all_gather(hall, ht)
+        block_hashes = [bytes(h.cpu().numpy().tobytes()).hex() for h in hall]
+    else:
+        block_hashes = [my_hash.hex()]
+
+    # ---- config 2, distribution (B): protocol-like balances, bl in {0 (7 of 9), +v, l - v} with v a uniform u64
+    # (transaction.rs:68-72, accounts.rs:419-429: a transfer is [-v, +v, 0 x 7]); u, c stay uniform.  The balance only feeds
+    # the fixed-base term (1.7 % of the step), so the rate is that of distribution (A).
+    proto = None
+    if n >= 9:
+        v64 = rng.integers(0, 2**63, size=n, dtype=np.int64).astype(object)
+        kind = np.arange(n) % 9
+        blB = np.zeros((n, 32), np.uint8)
+        idx_p, idx_m = np.nonzero(kind == 1)[0], np.nonzero(kind == 0)[0]
+        for i in idx_p[:4096]:
+            blB[i] = np.frombuffer(int(v64[i]).to_bytes(32, "little"), np.uint8)
+        for i in idx_m[:4096]:
+            blB[i] = np.frombuffer((L - int(v64[i])).to_bytes(32, "little"), np.uint8)
+        # beyond the first 4096 of each kind the same values repeat (python big-int conversion is slow; the kernels do not care)
+        if idx_p.size > 4096:
+            blB[idx_p[4096:]] = blB[idx_p[:4096]][np.arange(idx_p.size - 4096) % 4096]
+            blB[idx_m[4096:]] = blB[idx_m[:4096]][np.arange(idx_m.size - 4096) % 4096]
+        blB_d = torch.from_numpy(blB.reshape(-1)).to(dev)
+        outB = torch.empty(n * 128, dtype=torch.uint8, device=dev)
+
+        def step_B():
+            eng.call_dev("qq_update_account_batch_dev", vp(d["acc"].data_ptr()), vp(blB_d.data_ptr()), vp(d["u"].data_ptr()),
+                         vp(d["c"].data_ptr()), vp(outB.data_ptr()), vp(st_d.data_ptr()), ctypes.c_size_t(n))
+        step_B()
+        barrier()
+        eng.event_record(6)
+        for _ in range(max(2, args.steps // 2)):
+            step_B()
+        eng.event_record(7)
+        msB = eng.event_elapsed_ms(6, 7) / max(2, args.steps // 2)
+        assert int(st_d.max().item()) == 0
+        # where bl == 0 the commitment's d differs from (A) only through bl: spot-check pk' unchanged between the two runs
+        pk_same = bool(torch.equal(outB.view(n, 128)[:, :64], out_d.view(n, 128)[:, :64]))
+        proto = {"distribution": "bl in {0 (7/9), +v, l - v}, v uniform u64; u, c uniform 252-bit", "ms_per_step": msB,
+                 "accounts_per_sec_per_gpu": n / (msB * 1e-3), "pk_half_equals_distribution_A": pk_same}
+        del blB_d, outB
 
     # ---- configs[0]: the 9-account anonymity set (3x3 shuffle), latency of one update_account + verify_account call pair
     # through the host API (the reference runs this case on one CPU core; reported for information)
@@ -332,6 +403,7 @@ def run_b200(args):
         msm_ms = eng.event_elapsed_ms(2, 3) / reps
         barrier()
         res = small.cpu().numpy()
+        msm_out32 = res[:32].copy()
         # correctness at full size: sum a_i h_i * B computed on the host with big ints, one fixed-base mult on the GPU
         tot = 0
         ai = [int.from_bytes(a[i].tobytes(), "little") for i in range(0, m)] if m <= (1 << 20) else None
@@ -364,37 +436,84 @@ def run_b200(args):
                                   "same_result": bool((res2[128:160] == res[:32]).all()) and int(res2[192]) == 0,
                                   "imad_frac": m * 16_128 / (prep_ms * 1e-3) / peak["imad_lo_per_s"],
                                   "note": "points decompressed once with qq_msm_points_prepare (not timed), 16 128 IMAD units per point"}
-        # ---- ONE MSM of world x m points sharded over the ranks: Pippenger on the local slice, 128-byte partial sums
-        # all-gathered over NCCL, the ranks' points added on every rank (quisquis-rust_b200/distributed.py)
-        if world > 1:
-            part = torch.zeros(256, dtype=torch.uint8, device=dev)
-            gathered = [torch.zeros(132, dtype=torch.uint8, device=dev) for _ in range(world)]
+        # ---- ONE point set split over the ranks (strong scaling; BASELINE configs[4]: sweep 2^10 .. 2^24 at 1 / 2 / 4 / 8 GPUs).
+        # Every rank derives the same global scalars (seed 77) and builds only its contiguous slice of the points; Pippenger
+        # on the slice (qq_msm_partial_dev), the 144-byte partial records all-gathered over NCCL into DEVICE memory and added
+        # and encoded there by one kernel (qq_points_sum_dev) - no host bounce of the partials.  Timed on the host clock around
+        # the device-synchronous calls, max over ranks; world = 1 is the plain single-GPU MSM of the same set.
+        sweep = []
+        grng = np.random.default_rng(77)
+        rec = torch.zeros(144, dtype=torch.uint8, device=dev)
+        recs = torch.zeros(144 * world, dtype=torch.uint8, device=dev)
+        sizes = [s_ for s_ in (1 << 10, 1 << 12, 1 << 14, 1 << 16, 1 << 18, 1 << 20, 1 << 22, 1 << 24) if s_ <= args.msm_sweep_max]
+        for tot_n in sizes:
+            # global scalars in blocks of 2^16 so that every rank draws the same stream without holding 2^24 x 64 bytes twice
+            lo, hi = tot_n * rank // world, tot_n * (rank + 1) // world
+            hs_l = np.empty((hi - lo, 32), np.uint8)
+            as_l = np.empty((hi - lo, 32), np.uint8)
+            acc_dot = 0
+            for b0 in range(0, tot_n, 1 << 16):
+                b1 = min(tot_n, b0 + (1 << 16))
+                hb, ab = rand_scalars(grng, b1 - b0), rand_scalars(grng, b1 - b0)
+                if tot_n <= (1 << 14):      # expected result from the known discrete logs (big ints on the host; small sets only)
+                    acc_dot += sum(int.from_bytes(hb[k].tobytes(), "little") * int.from_bytes(ab[k].tobytes(), "little") for k in range(b1 - b0))
+                a_, b_ = max(b0, lo), min(b1, hi)
+                if a_ < b_:
+                    hs_l[a_ - lo:b_ - lo] = hb[a_ - b0:b_ - b0]
+                    as_l[a_ - lo:b_ - lo] = ab[a_ - b0:b_ - b0]
+            cnt = hi - lo
+            if cnt:
+                hs_t = torch.from_numpy(hs_l.reshape(-1)).to(dev)
+                pt_t = torch.empty(cnt * 32, dtype=torch.uint8, device=dev)
+                fst_t = torch.empty(cnt, dtype=torch.uint8, device=dev)
+                eng.call_dev("qq_fixed_base_batch_dev", ctypes.c_int(0), vp(hs_t.data_ptr()), vp(pt_t.data_ptr()), vp(fst_t.data_ptr()),
+                             ctypes.c_size_t(cnt))
+                as_t = torch.from_numpy(as_l.reshape(-1)).to(dev)
+                del hs_t, fst_t
+            else:
+                pt_t = torch.zeros(32, dtype=torch.uint8, device=dev)
+                as_t = torch.zeros(32, dtype=torch.uint8, device=dev)
 
-            def sharded_once():
-                eng.call_dev("qq_msm_partial_dev", vp(a_d.data_ptr()), vp(pts_d.data_ptr()), ctypes.c_size_t(m),
-                             vp(part.data_ptr()), vp(part.data_ptr() + 128))
-                dist.all_gather(gathered, part[:132])
-                allb = torch.stack(gathered).cpu().numpy()
-                if allb[:, 128].any():
-                    return None, int(allb[:, 128].max())
-                return eng.points_sum(allb[:, :128].reshape(-1))
-
-            sharded_once()
+            def strong_once():
+                eng.call_dev("qq_msm_partial_dev", vp(as_t.data_ptr()), vp(pt_t.data_ptr()), ctypes.c_size_t(cnt), vp(rec.data_ptr()),
+                             vp(rec.data_ptr() + 128))
+                if world > 1:
+                    dist.all_gather_into_tensor(recs, rec)
+                    return eng.points_sum_dev(recs.data_ptr(), world, 144)
+                return eng.points_sum_dev(rec.data_ptr(), 1, 144)
+            strong_once()
+            strong_once()
             barrier()
             t0s = time.time()
-            for _ in range(reps):
-                out_s, ident_s = sharded_once()
+            nrep = 3 if tot_n >= (1 << 22) else 6
+            for _ in range(nrep):
+                out_s, ident_s, st_s = strong_once()
             torch.cuda.synchronize(dev)
-            sh_ms = (time.time() - t0s) * 1e3 / reps
+            ms_s = maxr_early((time.time() - t0s) * 1e3 / nrep)
+            # exchange alone: gather + device-side sum of records that are already there
             barrier()
-            # expected: (sum over all ranks of sum a_i h_i) * B
-            tot_t = torch.from_numpy(np.frombuffer((tot % L).to_bytes(32, "little"), np.uint8).copy()).to(dev)
-            tots = [torch.zeros(32, dtype=torch.uint8, device=dev) for _ in range(world)]
-            dist.all_gather(tots, tot_t)
-            gtot = sum(int.from_bytes(t_.cpu().numpy().tobytes(), "little") for t_ in tots) % L
-            exp_s, _ = eng.fixed_base(0, np.frombuffer(gtot.to_bytes(32, "little"), np.uint8))
-            msm["sharded"] = {"points_total": m * world, "ms": sh_ms, "matches_known_dlog": bool((exp_s[0] == out_s).all()),
-                              "exchange": "all_gather of 128-byte partial sums + status over NCCL, then %d point additions" % (world - 1)}
+            t0s = time.time()
+            for _ in range(10):
+                if world > 1:
+                    dist.all_gather_into_tensor(recs, rec)
+                    eng.points_sum_dev(recs.data_ptr(), world, 144)
+                else:
+                    eng.points_sum_dev(rec.data_ptr(), 1, 144)
+            torch.cuda.synchronize(dev)
+            ex_ms = maxr_early((time.time() - t0s) * 1e3 / 10)
+            ent = {"points_total": tot_n, "points_per_gpu": cnt, "ms": ms_s, "points_per_sec": tot_n / (ms_s * 1e-3),
+                   "exchange_ms": ex_ms, "status": int(st_s),
+                   "imad_frac_per_gpu": cnt * IMAD_PER_MSM_POINT / (ms_s * 1e-3) / peak["imad_lo_per_s"]}
+            if tot_n <= (1 << 14):
+                exp_s, _ = eng.fixed_base(0, np.frombuffer((acc_dot % L).to_bytes(32, "little"), np.uint8))
+                ent["matches_known_dlog"] = bool((exp_s[0] == out_s).all())
+            ent["result_sha16"] = out_s.tobytes().hex()[:16]      # equal across world sizes: the same global point set
+            sweep.append(ent)
+            del pt_t, as_t
+        msm["strong"] = {"sweep": sweep,
+                         "exchange": "NCCL all_gather_into_tensor of 144-byte partial records into device memory + one kernel that adds "
+                                     "and encodes them (qq_points_sum_dev); no host bounce" if world > 1 else "single GPU",
+                         "note": "one global point set (seed 77) split into contiguous slices, one per rank; ms = max over ranks"}
 
     # ---- configs[2]: 4096 shuffle proofs, sharded over the ranks (independent proofs, no collective) ----------------
     # ---- configs[3]: Bulletproofs 64-bit range proofs, 16 aggregated values each: ONE aggregated MSM per batch -----------
@@ -419,8 +538,12 @@ def run_b200(args):
                 best = min(best, (time.time() - t_) * 1e3)
             barrier()
             return best
-        rec = tiled(os.path.join(gold, "shuffle_proofs.bin"), 6432, per_rank)
-        si, so, stm, prf = (np.ascontiguousarray(rec[:, a:b]) for a, b in ((0, 1152), (1152, 2304), (2304, 2656), (2656, 6432)))
+        def pinned(a):      # page-locked host buffers, as a caller feeding serialised transactions would hold them
+            return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+        rec_all = tiled(os.path.join(gold, "shuffle_proofs.bin"), 6432, per_rank * world)
+        cols_ = ((0, 1152), (1152, 2304), (2304, 2656), (2656, 6432))
+        rec = rec_all[rank * per_rank:(rank + 1) * per_rank]
+        si, so, stm, prf = (pinned(rec[:, a:b]) for a, b in cols_)
         res = {}
 
         def run_shuffle():
@@ -448,17 +571,38 @@ def run_b200(args):
         prf_bad = prf.copy()
         prf_bad[per_rank // 2, 3776 - 1] ^= 0x01            # top byte of the DDH response: wrong, perhaps not even canonical
         sh_rej = eng.verify_shuffle(si, so, stm, prf_bad)[0]
+        # strong scaling inside this run: rank 0 alone verifies the WHOLE batch (the other ranks wait), against the sharded time
+        sh_n1 = None
+        if world > 1:
+            barrier()
+            if rank == 0:
+                full = [pinned(rec_all[:, a:b]) for a, b in cols_]
+                eng.verify_shuffle(*full)
+                t_ = time.time()
+                for _ in range(3):
+                    st_full = eng.verify_shuffle(*full)[0]
+                sh_n1 = (time.time() - t_) * 1e3 / 3
+                assert not st_full.any()
+                del full
+            barrier()
+        # the exact form (every group equation an MSM of its own) on the same batch, for the record
+        eng.verify_set_aggregation(False)
+        sh_exact_ms = best_of(run_shuffle, reps=2)
+        eng.verify_set_aggregation(True)
         proofs_sec = {"shuffle": {"proofs_per_gpu": per_rank, "ms": sh_ms, "all_accepted": bool(sh_ok),
                                   "ms_two_contexts": sh2_ms, "all_accepted_two_contexts": bool(sh2_ok),
+                                  "ms_exact_form": sh_exact_ms, "n1_ms_whole_batch_on_rank0": sh_n1,
                                   "tampered_proof_rejected_alone": bool(sh_rej[per_rank // 2] != 0 and int(sh_rej.astype(bool).sum()) == 1),
-                                  "msms_per_proof": 28, "terms_per_proof": 239,
-                                  "api": "qq_verify_shuffle_batch (ShuffleProof::verify, 9 accounts, two GPU round trips)"}}
+                                  "msms_per_proof": 32, "terms_per_proof": 239, "exact_msms_per_proof": 4, "aggregated_terms_per_proof": 146,
+                                  "api": "qq_verify_shuffle_batch (ShuffleProof::verify, 9 accounts): proof bytes uploaded, Merlin transcripts "
+                                         "and Z/l algebra in transcript kernels, G / H / g_r / h_r as exact MSMs, the other 28 group equations "
+                                         "of all proofs in one weighted Pippenger MSM; pinned host buffers in, verdict bytes out"}}
         m_rp = 16
         rp_rec = m_rp * 32 + eng.range_proof_bytes(m_rp)
         rp_list = []
         for count in sorted(set([max(1, 512 // world), per_rank])):
             rr = tiled(os.path.join(gold, "range_proofs_m%d.bin" % m_rp), rp_rec, count)
-            cm, rpf = np.ascontiguousarray(rr[:, :m_rp * 32]), np.ascontiguousarray(rr[:, m_rp * 32:])
+            cm, rpf = pinned(rr[:, :m_rp * 32]), pinned(rr[:, m_rp * 32:])
 
             def run_range():
                 res["st"] = eng.verify_range_proofs(cm, rpf, m_rp)
@@ -470,13 +614,71 @@ def run_b200(args):
                 rpf_bad[count // 2, 5 * 32 + 1] ^= 1
                 r_ = eng.verify_range_proofs(cm, rpf_bad, m_rp)
                 rej = bool(r_[count // 2] == 6 and int(r_.astype(bool).sum()) == 1)
+            rp_n1 = None
+            if world > 1 and count == per_rank:
+                barrier()
+                if rank == 0:
+                    rr_all = tiled(os.path.join(gold, "range_proofs_m%d.bin" % m_rp), rp_rec, count * world)
+                    cm_a, rp_a = pinned(rr_all[:, :m_rp * 32]), pinned(rr_all[:, m_rp * 32:])
+                    eng.verify_range_proofs(cm_a, rp_a, m_rp)
+                    t_ = time.time()
+                    for _ in range(3):
+                        st_full = eng.verify_range_proofs(cm_a, rp_a, m_rp)
+                    rp_n1 = (time.time() - t_) * 1e3 / 3
+                    assert not st_full.any()
+                    del rr_all, cm_a, rp_a
+                barrier()
             rp_list.append({"proofs_per_gpu": count, "values_per_proof": m_rp, "bits": 64, "ms": rp_ms, "all_accepted": bool(ok_),
+                            "n1_ms_whole_batch_on_rank0": rp_n1,
                             "tampered_proof_rejected_alone": rej,
                             "aggregated_msm_terms": 2 * 64 * m_rp + 2 + count * (4 + 20 + m_rp),
                             "reference_msm_points": count * (2 * 64 * m_rp + 20 + m_rp + 6)})
         proofs_sec["range_proofs"] = {"batches": rp_list,
                                       "api": "qq_verify_range_proof_batch (RangeProof::verify_multiple; the reference verifies "
                                              "each proof with its own 2090-term MSM, verifier.rs:517)"}
+
+    # ---- the in-library multi-device handle (qq_init_multi): ONE process drives every GPU of this run; the other ranks wait.
+    # One 2^20-point MSM split over the devices (slices resident), partial sums pulled to the root by peer copies.
+    multi_leg = None
+    if world > 1 and args.msm_points > 0:
+        barrier()
+        if rank == 0:
+            try:
+                me = pkg.MultiEngine(list(range(world)))
+                tot_n = args.msm_points
+                mrng = np.random.default_rng(78)
+                hs_g, as_g = rand_scalars(mrng, tot_n), rand_scalars(mrng, tot_n)
+                pts_g, _ = eng.fixed_base(0, hs_g)
+                sp, pp, cn = [], [], []
+                for d_ in range(world):
+                    lo, hi = tot_n * d_ // world, tot_n * (d_ + 1) // world
+                    c_ = me.ctx(d_)
+                    ptrs = []
+                    for arr in (as_g[lo:hi], pts_g[lo:hi]):
+                        p_ = ctypes.c_void_p()
+                        assert eng.lib.qq_dev_alloc(c_, ctypes.byref(p_), ctypes.c_size_t(arr.size)) == 0
+                        assert eng.lib.qq_dev_upload(c_, p_, vp(np.ascontiguousarray(arr).ctypes.data), ctypes.c_size_t(arr.size)) == 0
+                        ptrs.append(p_)
+                    sp.append(ptrs[0].value)
+                    pp.append(ptrs[1].value)
+                    cn.append(hi - lo)
+                me.msm_dev(sp, pp, cn)
+                t_ = time.time()
+                for _ in range(5):
+                    mo_, ms__ = me.msm_dev(sp, pp, cn)
+                mm_ms = (time.time() - t_) * 1e3 / 5
+                one_o, one_s = eng.msm(as_g, pts_g)
+                multi_leg = {"devices": world, "msm_points_total": tot_n, "ms": mm_ms, "points_per_sec": tot_n / (mm_ms * 1e-3),
+                             "equals_single_gpu_result": bool(ms__ == 0 and one_s == 0 and (mo_ == one_o).all()),
+                             "api": "qq_multi_msm_dev: one worker thread per GPU, partial sums gathered on the root with "
+                                    "cudaMemcpyPeerAsync and added by one kernel"}
+                for d_ in range(world):
+                    eng.lib.qq_dev_free(me.ctx(d_), ctypes.c_void_p(sp[d_]))
+                    eng.lib.qq_dev_free(me.ctx(d_), ctypes.c_void_p(pp[d_]))
+                me.close()
+            except Exception as ex:      # reported, not fatal: the headline legs are done
+                multi_leg = {"error": repr(ex)}
+        barrier()
 
     # ---- reduce over ranks ----------------------------------------------------------------------------------------
     def maxr(x):
@@ -493,6 +695,10 @@ def run_b200(args):
         sh["ms"] = maxr(sh["ms"])
         sh["proofs_total"] = sh["proofs_per_gpu"] * world
         sh["proofs_per_sec"] = sh["proofs_total"] / (sh["ms"] * 1e-3)
+        if sh.get("n1_ms_whole_batch_on_rank0"):
+            sh["strong_scaling"] = {"gpus": world, "proofs_total": sh["proofs_total"], "ms_1_gpu": sh["n1_ms_whole_batch_on_rank0"],
+                                    "ms": sh["ms"], "speedup": sh["n1_ms_whole_batch_on_rank0"] / sh["ms"],
+                                    "efficiency": sh["n1_ms_whole_batch_on_rank0"] / sh["ms"] / world}
         if sh.get("ms_two_contexts"):
             sh["ms_two_contexts"] = maxr(sh["ms_two_contexts"])
             sh["proofs_per_sec_two_contexts"] = sh["proofs_total"] / (sh["ms_two_contexts"] * 1e-3)
@@ -501,9 +707,10 @@ def run_b200(args):
             b_["proofs_per_sec"] = b_["proofs_per_gpu"] * world / (b_["ms"] * 1e-3)
             b_["values_per_sec"] = b_["proofs_per_sec"] * b_["values_per_proof"]
             b_["reference_msm_points_per_sec"] = b_["reference_msm_points"] * world / (b_["ms"] * 1e-3)
-    if msm and "sharded" in msm:
-        msm["sharded"]["ms"] = maxr(msm["sharded"]["ms"])
-        msm["sharded"]["points_per_sec"] = msm["sharded"]["points_total"] / (msm["sharded"]["ms"] * 1e-3)
+            if b_.get("n1_ms_whole_batch_on_rank0"):
+                b_["strong_scaling"] = {"gpus": world, "proofs_total": b_["proofs_per_gpu"] * world, "ms_1_gpu": b_["n1_ms_whole_batch_on_rank0"],
+                                        "ms": b_["ms"], "speedup": b_["n1_ms_whole_batch_on_rank0"] / b_["ms"],
+                                        "efficiency": b_["n1_ms_whole_batch_on_rank0"] / b_["ms"] / world}
     total_accounts = n * world * args.steps
     value = total_accounts / (wall_ms_max * 1e-3)
     e2e_value = total_accounts / (e2e_ms_max * 1e-3)
@@ -529,6 +736,14 @@ def run_b200(args):
                          "curve25519-dalek 3.2.1's algorithms (radix-2^51 field, radix-16 variable-base, table "
                          "fixed-base); dalek itself cannot be built here" % (ms_, cores),
                "gpu_output_matches_cpu_on_sample": same_cpu}
+        if msm:
+            # the MSM half of the metric on the host cores: the same 2^20 compressed points and scalars through the C port
+            t = time.time()
+            cmo, cms = C.msm(a, pts_h)
+            dtm = time.time() - t
+            msm["cpu_baseline"] = {"value": msm["points"] / dtm, "unit": "points/s", "ms": dtm * 1e3, "cores": cores, "kind": "port",
+                                   "sample": "the same %d-point MSM (oracle/qq_oracle.c oq_msm), %d host threads" % (msm["points"], cores),
+                                   "gpu_output_matches_cpu": bool(cms == 0 and (cmo == msm_out32).all())}
         if proofs_sec:
             # one aggregated range proof (16 values) through the oracle's verifier restatement: Merlin in Python, the 2090-term
             # MSM in the C port with all host threads -- what the reference does per proof
@@ -609,6 +824,13 @@ def run_b200(args):
                                  if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0}},
             "cpu_baseline": cpu,
         }
+        line["output_sha256_per_block"] = block_hashes
+        line["config"]["blocks"] = "rank r processes block r of the global batch (inputs seeded 1000 + r): block digests are comparable across world sizes"
+        if proto:
+            proto["accounts_per_sec"] = proto["accounts_per_sec_per_gpu"] * world
+            line["update_account_protocol_like"] = proto
+        if multi_leg:
+            line["multi_device_handle"] = multi_leg
         if anon9:
             line["anonymity_set_9"] = anon9
         if fixed:
@@ -657,6 +879,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--accounts", type=int, default=1 << 20, help="accounts per GPU per step")
     ap.add_argument("--msm-points", type=int, default=1 << 20)
+    ap.add_argument("--msm-sweep-max", type=int, default=1 << 24, help="largest point set of the strong-scaling MSM sweep (0 = skip)")
     ap.add_argument("--fixed-points", type=int, default=1 << 22, help="fixed-base batch per GPU (0 = skip)")
     ap.add_argument("--fixed-window", type=int, default=22,
                     help="also time the fixed-base batch with this table window (22 bits = 2.4 GB in HBM; 0 = default table only)")
