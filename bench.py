@@ -187,6 +187,9 @@ def run_b200(args):
             os.environ["NCCL_DEBUG"] = "WARN"
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # CPU-side barrier for the legs in which ONE process drives several GPUs: an NCCL barrier parks a spinning kernel of
+        # another process on those GPUs, and two processes time-slice a GPU
+        cpu_group = dist.new_group(backend="gloo")
     pkg = g.load_package()
     eng = pkg.Engine(local)
     dev = torch.device("cuda", local)
@@ -501,8 +504,13 @@ def run_b200(args):
                     eng.points_sum_dev(rec.data_ptr(), 1, 144)
             torch.cuda.synchronize(dev)
             ex_ms = maxr_early((time.time() - t0s) * 1e3 / 10)
+            t0s = time.time()
+            for _ in range(10):
+                eng.points_sum_dev(rec.data_ptr(), 1, 144)
+            enc_ms = maxr_early((time.time() - t0s) * 1e3 / 10)
             ent = {"points_total": tot_n, "points_per_gpu": cnt, "ms": ms_s, "points_per_sec": tot_n / (ms_s * 1e-3),
-                   "exchange_ms": ex_ms, "status": int(st_s),
+                   "exchange_ms": ex_ms, "encode_only_ms": enc_ms, "exchange_over_single_gpu_ms": max(0.0, ex_ms - enc_ms),
+                   "status": int(st_s),
                    "imad_frac_per_gpu": cnt * IMAD_PER_MSM_POINT / (ms_s * 1e-3) / peak["imad_lo_per_s"]}
             if tot_n <= (1 << 14):
                 exp_s, _ = eng.fixed_base(0, np.frombuffer((acc_dot % L).to_bytes(32, "little"), np.uint8))
@@ -642,6 +650,7 @@ def run_b200(args):
     multi_leg = None
     if world > 1 and args.msm_points > 0:
         barrier()
+        dist.barrier(group=cpu_group)
         if rank == 0:
             try:
                 me = pkg.MultiEngine(list(range(world)))
@@ -678,6 +687,7 @@ def run_b200(args):
                 me.close()
             except Exception as ex:      # reported, not fatal: the headline legs are done
                 multi_leg = {"error": repr(ex)}
+        dist.barrier(group=cpu_group)      # the other ranks wait on the CPU: their GPUs are rank 0's for this leg
         barrier()
 
     # ---- reduce over ranks ----------------------------------------------------------------------------------------

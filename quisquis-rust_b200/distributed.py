@@ -82,3 +82,38 @@ def verify_sharded(verify_fn, arrays, nproofs, device=None):
         a, b = shard_range(nproofs, r, world)
         full[a:b] = out[r].cpu().numpy()[:b - a]
     return full
+
+
+def msm_sharded_engine(engine, scalars, points, device):
+    """The same exchange with the CUDA engine on both sides and the partial sums kept in device memory: this rank's slice through
+    qq_msm_partial (result record = 128 B X | Y | Z | T + status byte, 144 B), the records all-gathered into ONE device tensor
+    (NCCL: all_gather_into_tensor, no host bounce; under a gloo group the record travels through host memory) and added and
+    encoded by one kernel on every rank (qq_points_sum_dev).  Returns (32-byte compressed point, status) on every rank."""
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    scalars = np.asarray(scalars, dtype=np.uint8).reshape(-1, 32)
+    points = np.asarray(points, dtype=np.uint8).reshape(-1, 32)
+    lo, hi = shard_range(scalars.shape[0], rank, world)
+    s_d = torch.from_numpy(np.ascontiguousarray(scalars[lo:hi]).reshape(-1).copy()).to(device)
+    p_d = torch.from_numpy(np.ascontiguousarray(points[lo:hi]).reshape(-1).copy()).to(device)
+    if hi == lo:      # empty slice: the kernels still want valid pointers
+        s_d = torch.zeros(32, dtype=torch.uint8, device=device)
+        p_d = torch.zeros(32, dtype=torch.uint8, device=device)
+    rec = torch.zeros(144, dtype=torch.uint8, device=device)
+    vp = ctypes.c_void_p
+    engine.call_dev("qq_msm_partial_dev", vp(s_d.data_ptr()), vp(p_d.data_ptr()), ctypes.c_size_t(hi - lo), vp(rec.data_ptr()),
+                    vp(rec.data_ptr() + 128))
+    if world == 1:
+        recs = rec
+    elif dist.get_backend() == "nccl":
+        recs = torch.zeros(144 * world, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(recs, rec)
+    else:
+        parts = [torch.zeros(144, dtype=torch.uint8) for _ in range(world)]
+        dist.all_gather(parts, rec.cpu())
+        recs = torch.cat(parts).to(device)
+    out, _, st = engine.points_sum_dev(recs.data_ptr(), world, 144)
+    return out, st

@@ -1598,3 +1598,85 @@ def test_range_proof_verification_two_halves(engine):
         alone = engine.verify_range_proofs(cm[i:i + 1], pr[i:i + 1], m)
         assert int(alone[0]) == code, i
     assert not engine.verify_range_proofs(cm[:0], pr[:0], m).size        # empty batch
+
+
+def _sharded_msm_worker(rank, world, port, n, backend, q):
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "oracle"))
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    from quisquis_rust_b200 import distributed as D
+    dev_index = rank if backend == "nccl" else 0
+    torch.cuda.set_device(dev_index)
+    dist.init_process_group(backend, init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    eng = pkg.Engine(dev_index)
+    rng = np.random.default_rng(2024)
+    hs = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    a = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    hs[:, 31] &= 0x0f
+    a[:, 31] &= 0x0f
+    pts, _ = eng.fixed_base(0, hs)
+    out, st = D.msm_sharded_engine(eng, a, pts, torch.device("cuda", dev_index))
+    bad = pts.copy()
+    bad[n - 1, 31] |= 0x80            # an undecodable point in the last rank's slice
+    out_b, st_b = D.msm_sharded_engine(eng, a, bad, torch.device("cuda", dev_index))
+    q.put((rank, out.tobytes(), int(st), out_b.tobytes(), int(st_b), pts.tobytes() if rank == 0 else None, a.tobytes() if rank == 0 else None))
+    dist.barrier()
+    eng.close()
+    dist.destroy_process_group()
+
+
+def test_msm_sharded_over_two_ranks_with_the_engine():
+    """SURVEY 8e with the real kernels on both sides: qq_msm_partial_dev on each rank's slice, the 144-byte records all-gathered
+    (NCCL into device memory when two GPUs are there; through a gloo group with both ranks on GPU 0 otherwise), qq_points_sum_dev
+    on every rank - equal to the C oracle's MSM over the whole set; a bad point in the last slice gives status 1 on every rank."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    import c_oracle as C
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    backend = "nccl" if torch.cuda.device_count() >= 2 else "gloo"
+    n = 5000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_msm_worker, args=(r, 2, port, n, backend, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    res.sort()
+    pts = np.frombuffer(res[0][5], np.uint8).reshape(n, 32)
+    a = np.frombuffer(res[0][6], np.uint8).reshape(n, 32)
+    exp, est = C.msm(a, pts)
+    assert est == 0
+    for r in res:
+        assert r[1] == exp.tobytes() and r[2] == 0
+        assert r[4] == 1 and r[3] == bytes(32)
+
+
+@pytest.mark.parametrize("n", [1 << 20, (1 << 21) + 12345])
+def test_msm_large_vs_c_oracle(engine, n):
+    """The Pippenger path at BASELINE's full size (2^20) and at a non-power-of-two beyond it against the C oracle's independent
+    MSM (oracle/qq_oracle.c: other window sizes, other reduction order): byte-identical result.  Points are generated with
+    the fixed-base kernel (valid encodings with known discrete logs), scalars uniform 252-bit."""
+    import c_oracle as C
+    rng = np.random.default_rng(n)
+    hs = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    a = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    hs[:, 31] &= 0x0f
+    a[:, 31] &= 0x0f
+    pts, st = engine.fixed_base(0, hs)
+    assert not st.any()
+    out, s = engine.msm(a, pts)
+    exp, es = C.msm(a, pts)
+    assert s == 0 and es == 0 and out.tobytes() == exp.tobytes()
