@@ -18,9 +18,44 @@ namespace qq {
 
 typedef qq_rp::record rp_record;      // written by the transcript phase (rangeproof_verify.cuh)
 
+// Per (sub-)proof product tables: s_i and y^-j are products over the set bits of the index, so with the index cut into a low
+// part (LB = min(5, lg) bits) and a high part,  s_i = allinv SHi[hi] SLo[lo]  and  y^-j = YHi[jh] YLo[jl]:  five tables of at
+// most 32 entries per proof (160 short products, built once by k_rp_tables) replace the lg products every (generator, proof)
+// pair paid before - 5 instead of lg + 4 = 14 products of Z/l per pair at n m = 1024.  a and b are folded into the high tables.
+#define QQ_RP_TBL 32
+struct rp_tables {
+    qq_sc::sc sa[QQ_RP_TBL];      // rho a allinv SHi[hi]
+    qq_sc::sc sb[QQ_RP_TBL];      // rho b allinv SHi[hi]
+    qq_sc::sc slo[QQ_RP_TBL];     // SLo[lo]
+    qq_sc::sc yhi[QQ_RP_TBL];     // YHi[jh]
+    qq_sc::sc ylo[QQ_RP_TBL];     // YLo[jl]
+};
+// grid = number of (sub-)proofs, block = 5 x 32 threads: thread (table t, entry e)
+__global__ void __launch_bounds__(160) k_rp_tables(const rp_record* __restrict__ rec, int lg, rp_tables* __restrict__ tbl) {
+    const rp_record& r = rec[blockIdx.x];
+    const int t = threadIdx.x / QQ_RP_TBL, e = threadIdx.x % QQ_RP_TBL;
+    const int LB = lg < 5 ? lg : 5, HB = lg - LB;
+    qq_sc::sc v = qq_sc::one();
+    if (t == 0 || t == 1) {
+        v = qq_sc::mul(t == 0 ? r.ra : r.rb, r.allinv);
+        for (int k = 0; k < HB; k++)
+            if ((e >> k) & 1) v = qq_sc::mul(v, r.usq[lg - 1 - (LB + k)]);
+    } else if (t == 2) {
+        for (int k = 0; k < LB; k++)
+            if ((e >> k) & 1) v = qq_sc::mul(v, r.usq[lg - 1 - k]);
+    } else if (t == 3) {
+        for (int k = 0; k < HB; k++)
+            if ((e >> k) & 1) v = qq_sc::mul(v, r.yinv_pow[LB + k]);
+    } else {
+        for (int k = 0; k < LB; k++)
+            if ((e >> k) & 1) v = qq_sc::mul(v, r.yinv_pow[k]);
+    }
+    rp_tables& o = tbl[blockIdx.x];
+    (t == 0 ? o.sa : t == 1 ? o.sb : t == 2 ? o.slo : t == 3 ? o.yhi : o.ylo)[e] = v;
+}
 // grid = (ceil(N / block), chunks); partial: chunks x 2N scalars (g sums then h sums)
-__global__ void __launch_bounds__(128) k_rp_fold(const rp_record* __restrict__ rec, unsigned int first, unsigned int count,
-                                                 int n_bits, int N, int lg, qq_sc::sc* __restrict__ partial) {
+__global__ void __launch_bounds__(128) k_rp_fold(const rp_record* __restrict__ rec, const rp_tables* __restrict__ tbl, unsigned int first,
+                                                 unsigned int count, int n_bits, int N, int lg, qq_sc::sc* __restrict__ partial) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     unsigned int per = (count + gridDim.y - 1) / gridDim.y;
@@ -31,16 +66,16 @@ __global__ void __launch_bounds__(128) k_rp_fold(const rp_record* __restrict__ r
     qq_sc::sc two_pow = qq_sc::zero();
     two_pow.v[0] = 1ull << (j % n_bits);
     const int party = j / n_bits;
+    const int LB = lg < 5 ? lg : 5, lmask = (1 << LB) - 1;
+    const int lo = i & lmask, hi = i >> LB, jl = j & lmask, jh = j >> LB;
     for (unsigned int p = p0; p < p1; p++) {
         const rp_record& r = rec[first + p];
-        qq_sc::sc s_i = r.allinv, y_j = qq_sc::one();
-        for (int k = 0; k < lg; k++) {
-            if ((i >> k) & 1) s_i = qq_sc::mul(s_i, r.usq[lg - 1 - k]);
-            else y_j = qq_sc::mul(y_j, r.yinv_pow[k]);          // bit k of j is the complement of bit k of i
-        }
-        sum_g = qq_sc::add(sum_g, qq_sc::sub(r.neg_rz, qq_sc::mul(r.ra, s_i)));
-        qq_sc::sc t = qq_sc::sub(qq_sc::mul(r.rzz_zj[party], two_pow), qq_sc::mul(r.rb, s_i));
-        sum_h = qq_sc::add(sum_h, qq_sc::add(r.rz, qq_sc::mul(y_j, t)));
+        const rp_tables& t = tbl[first + p];
+        const qq_sc::sc slo = t.slo[lo];
+        const qq_sc::sc y_j = qq_sc::mul(t.yhi[jh], t.ylo[jl]);
+        sum_g = qq_sc::add(sum_g, qq_sc::sub(r.neg_rz, qq_sc::mul(t.sa[hi], slo)));
+        qq_sc::sc u = qq_sc::sub(qq_sc::mul(r.rzz_zj[party], two_pow), qq_sc::mul(t.sb[hi], slo));
+        sum_h = qq_sc::add(sum_h, qq_sc::add(r.rz, qq_sc::mul(y_j, u)));
     }
     partial[(size_t)blockIdx.y * 2 * N + i] = sum_g;
     partial[(size_t)blockIdx.y * 2 * N + N + j] = sum_h;
