@@ -119,7 +119,7 @@ QQ_HOSTDEV static inline uint8_t transcript_phase(qq_merlin::transcript& tr, con
             sc prefix[QQ_RP_MAX_LG + 2];
             prefix[0] = one();
             for (int k = 0; k <= lg; k++) prefix[k + 1] = mul(prefix[k], u[k]);
-            sc inv_all = invert(prefix[lg + 1]);
+            sc inv_all = invert_vartime(prefix[lg + 1]);      // public challenges: the variable-time inversion is fine
             for (int k = lg; k >= 0; k--) {
                 sc v = u[k];
                 u[k] = mul(inv_all, prefix[k]);

@@ -257,9 +257,11 @@ def test_host_scalar_field(hh):
         assert op(1, a, b) == (a - b) % L
         assert op(2, a, b) == (a * b) % L
         assert op(4, a, b) == (a + (b << 256)) % L
-    for a in edge[1:] + vals[-20:]:
+    for a in edge[1:] + vals[-60:]:
         inv = op(3, a, 0)
         assert inv * a % L == 1
+        assert op(5, a, 0) == inv              # binary extended Euclid (invert_vartime) == a^(l - 2)
+    assert op(5, 0, 0) == 0
     for wide in (2**512 - 1, (L << 256) + L - 1, (2**256 - 1) << 256, 2**511):
         assert op(4, wide & (2**256 - 1), wide >> 256) == wide % L
     assert op(2, L, 1) is None and op(0, 1, 2**256 - 1) is None
