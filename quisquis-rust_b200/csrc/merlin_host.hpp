@@ -13,9 +13,16 @@
 
 namespace qq_merlin {
 
+class transcript;
+
 class strobe128 {
-    static const int R = 166;
+    friend class transcript;
+
+  public:
     enum { FLAG_I = 1, FLAG_A = 2, FLAG_C = 4, FLAG_T = 8, FLAG_M = 16, FLAG_K = 32 };
+
+  private:
+    static const int R = 166;
     alignas(8) uint8_t st[200];
     uint8_t pos, pos_begin, cur_flags;
 
@@ -92,6 +99,87 @@ class strobe128 {
             if (pos == R) run_f();
         }
     }
+    // ---- fused operations: one pass over "operation header | bytes" instead of one absorb call per piece ---------------------
+    // (a Merlin append_message is meta-AD(label) | meta-AD(le32 length, continued) | AD(message): five separate absorbs of 2, |label|,
+    // 4, 2 and n bytes, each a read-modify-write chain on the state in local memory; the transcript kernels spent half their
+    // time there)
+    QQ_HOSTDEV void absorb_word(uint64_t v, unsigned c) {                   // the low c <= 8 bytes of v
+        while (c) {
+            const unsigned room = (unsigned)(R - pos), t = c < room ? c : room;
+            xor_at(pos, t == 8 ? v : (v & ((1ULL << (8 * t)) - 1)), t);
+            pos = (uint8_t)(pos + t);
+            if (pos == R) run_f();
+            v = t == 8 ? 0 : v >> (8 * t);
+            c -= t;
+        }
+    }
+    struct feeder {      // bytes -> little-endian words -> absorb_word
+        strobe128& s;
+        uint64_t acc;
+        unsigned cnt;
+        QQ_HOSTDEV explicit feeder(strobe128& st_) : s(st_), acc(0), cnt(0) {}
+        QQ_HOSTDEV void put(uint8_t b) {
+            acc |= (uint64_t)b << (8 * cnt);
+            if (++cnt == 8) {
+                s.absorb_word(acc, 8);
+                acc = 0;
+                cnt = 0;
+            }
+        }
+        QQ_HOSTDEV void put_word(uint64_t w) {                              // eight bytes at once
+            if (cnt == 0) {
+                s.absorb_word(w, 8);
+            } else {
+                s.absorb_word(acc | (w << (8 * cnt)), 8);
+                acc = w >> (64 - 8 * cnt);
+            }
+        }
+        QQ_HOSTDEV void flush() {
+            if (cnt) s.absorb_word(acc, cnt);
+            acc = 0;
+            cnt = 0;
+        }
+    };
+    // begin_op(flags) | label | le32(n) as a continuation of the same operation   (flags = M | A)
+    QQ_HOSTDEV QQ_NOINLINE void op_label_len(uint8_t flags, const char* label, uint32_t n) {
+        const uint8_t old_begin = pos_begin;
+        pos_begin = (uint8_t)(pos + 1);
+        cur_flags = flags;
+        feeder f(*this);
+        f.put(old_begin);
+        f.put(flags);
+        for (unsigned i = 0; label[i]; i++) f.put((uint8_t)label[i]);
+        f.put((uint8_t)n);
+        f.put((uint8_t)(n >> 8));
+        f.put((uint8_t)(n >> 16));
+        f.put((uint8_t)(n >> 24));
+        f.flush();
+    }
+    // begin_op(flags) | n bytes of data   (flags without C / K: no forced permutation)
+    QQ_HOSTDEV QQ_NOINLINE void op_data(uint8_t flags, const uint8_t* d, size_t n) {
+        const uint8_t old_begin = pos_begin;
+        pos_begin = (uint8_t)(pos + 1);
+        cur_flags = flags;
+        feeder f(*this);
+        if (n <= 64 && (n & 7) == 0 && (reinterpret_cast<uintptr_t>(d) & 7) == 0) {
+            // the common case (points, scalars, wide challenges): all words loaded before the state is touched
+            uint64_t w[8];
+            const unsigned nw = (unsigned)(n >> 3);
+#pragma unroll
+            for (unsigned k = 0; k < 8; k++) w[k] = k < nw ? reinterpret_cast<const uint64_t*>(d)[k] : 0;
+            f.put(old_begin);
+            f.put(flags);
+#pragma unroll
+            for (unsigned k = 0; k < 8; k++)
+                if (k < nw) f.put_word(w[k]);
+            f.flush();
+            return;
+        }
+        f.put(old_begin);
+        f.put(flags);
+        f.flush();
+        absorb(d, n);
+    }
     QQ_HOSTDEV QQ_NOINLINE void begin_op(uint8_t flags, bool more) {
         if (more) return;   // continuation of the current operation (same flags by construction)
         uint8_t old_begin = pos_begin;
@@ -155,16 +243,12 @@ class transcript {
     QQ_HOSTDEV transcript(const uint8_t* label, size_t n) : s("Merlin v1.0") { append_message("dom-sep", label, n); }
     QQ_HOSTDEV void export_state(uint8_t* out) const { s.export_state(out); }
     QQ_HOSTDEV bool import_state(const uint8_t* in) { return s.import_state(in); }
-    QQ_HOSTDEV QQ_NOINLINE void append_message(const char* label, const uint8_t* msg, size_t n) {
-        s.meta_ad((const uint8_t*)label, strobe128::label_len(label), false);
-        uint8_t len[4] = {(uint8_t)n, (uint8_t)(n >> 8), (uint8_t)(n >> 16), (uint8_t)(n >> 24)};
-        s.meta_ad(len, 4, true);
-        s.ad(msg, n, false);
+    QQ_HOSTDEV void append_message(const char* label, const uint8_t* msg, size_t n) {
+        s.op_label_len(strobe128::FLAG_M | strobe128::FLAG_A, label, (uint32_t)n);
+        s.op_data(strobe128::FLAG_A, msg, n);
     }
-    QQ_HOSTDEV QQ_NOINLINE void challenge_bytes(const char* label, uint8_t* out, size_t n) {
-        s.meta_ad((const uint8_t*)label, strobe128::label_len(label), false);
-        uint8_t len[4] = {(uint8_t)n, (uint8_t)(n >> 8), (uint8_t)(n >> 16), (uint8_t)(n >> 24)};
-        s.meta_ad(len, 4, true);
+    QQ_HOSTDEV void challenge_bytes(const char* label, uint8_t* out, size_t n) {
+        s.op_label_len(strobe128::FLAG_M | strobe128::FLAG_A, label, (uint32_t)n);
         s.prf(out, n, false);
     }
     QQ_HOSTDEV void domain_sep(const char* label) { append_message("dom-sep", (const uint8_t*)label, strobe128::label_len(label)); }
