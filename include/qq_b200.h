@@ -207,6 +207,15 @@ int qq_msm_prepared(qq_ctx* ctx, const uint8_t* scalars, const qq_prepared* poin
                     uint8_t* status);
 int qq_msm_prepared_dev(qq_ctx* ctx, const uint8_t* scalars, const qq_prepared* points, size_t n, uint8_t* out_point,
                         uint8_t* status);
+/* Shifted form of prepared point sets: qq_msm_points_prepare also stores 2^(c k) P_i for every window k (c fixed by the size of
+ * the set; ceil(256 / c) x 96 B per point) when that fits budget_bytes (default 112 MB = sets up to 2^16 points, whose shifted
+ * form stays L2-resident; 0 = never; sets below 1 024 points never).  qq_msm_prepared then drops every digit of every scalar
+ * into ONE set of 2^(c-1) buckets: no per-window reductions and no chain of 240 doublings at the end (measured 0.44 against
+ * 0.62 ms for 2^10 .. 2^12 points - the Bulletproofs generator set -, 0.61 against 0.76 ms at 2^16; beyond L2 the larger gather
+ * footprint loses: 3.3 against 2.35 ms at 2^20).  use_it = 0: ignore shifted forms that exist (A/B measurements).  Results
+ * are identical. */
+int qq_msm_set_shifted(qq_ctx* ctx, size_t budget_bytes, int use_it);
+size_t qq_msm_points_shifted_bytes(const qq_prepared* p);
 /* Tuning of the large MSM (compressed points, n >= split_min): the last tail_pct % of the points are decompressed by a
  * second kernel while the counting sort of the digits runs beside it on a high-priority stream with sort_blocks_per_sm
  * blocks per SM.  Defaults 2^17, 30, 3 (measured: 2^20 points 4.18 -> 3.99 ms, 2^24 58.0 -> 54.4 ms); tail_pct 0 turns the

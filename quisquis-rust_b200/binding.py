@@ -30,7 +30,7 @@ EXPORTS = [
     "qq_verify_set_transcripts", "qq_verify_set_aggregation",
     "qq_shuffle_proofs_from_bincode", "qq_shuffle_statements_from_bincode", "qq_shuffle_proofs_to_bincode",
     "qq_shuffle_statements_to_bincode", "qq_accounts_from_bincode", "qq_sigma_proof_from_bincode",
-    "qq_set_secret_mode", "qq_secret_mode", "qq_sigma_commit_batch", "qq_sigma_commit_batch_dev",
+    "qq_msm_set_shifted", "qq_msm_points_shifted_bytes", "qq_set_secret_mode", "qq_secret_mode", "qq_sigma_commit_batch", "qq_sigma_commit_batch_dev",
     "qq_init_multi", "qq_destroy_multi", "qq_multi_device_count", "qq_multi_ctx", "qq_multi_last_error",
     "qq_multi_update_account_batch", "qq_multi_generate_commitment_batch", "qq_multi_verify_shuffle_batch",
     "qq_multi_verify_range_proof_batch", "qq_multi_msm", "qq_multi_msm_dev", "qq_points_sum_dev",
@@ -125,6 +125,9 @@ def load_library():
     lib.qq_verify_set_transcripts.argtypes = [vp, ctypes.c_int]
     lib.qq_verify_set_aggregation.argtypes = [vp, ctypes.c_int]
     szp = ctypes.POINTER(ctypes.c_size_t)
+    lib.qq_msm_set_shifted.argtypes = [vp, ctypes.c_size_t, ctypes.c_int]
+    lib.qq_msm_points_shifted_bytes.argtypes = [vp]
+    lib.qq_msm_points_shifted_bytes.restype = ctypes.c_size_t
     lib.qq_set_secret_mode.argtypes = [vp, ctypes.c_int]
     lib.qq_secret_mode.argtypes = [vp]
     for name in ("qq_sigma_commit_batch", "qq_sigma_commit_batch_dev"):
@@ -671,6 +674,10 @@ class Engine:
     def verify_set_transcripts(self, on_device=True):
         """Shuffle verifier: per-proof transcripts / scalar algebra in GPU transcript kernels (default) or on the host threads."""
         self._ck(self.lib.qq_verify_set_transcripts(self.h, 1 if on_device else 0), "qq_verify_set_transcripts")
+
+    def msm_set_shifted(self, budget_bytes=112 << 20, use_it=True):
+        """Shifted form of prepared point sets (see the header): memory budget per set, and whether qq_msm_prepared uses it."""
+        self._ck(self.lib.qq_msm_set_shifted(self.h, budget_bytes, 1 if use_it else 0), "qq_msm_set_shifted")
 
     def set_secret_mode(self, on=True):
         """Constant-time table access for the scalar multiplications of the wallet / prover entry points (see the header)."""

@@ -84,7 +84,8 @@ __global__ void __launch_bounds__(256, 2) k_msm_prepare(const u32x4* __restrict_
                                                      size_t n, size_t n_dec, msm_geom g, u32x4* __restrict__ niels,
                                                      const uint8_t* __restrict__ pre_ok,
                                                      uint8_t* __restrict__ term_status, int16_t* __restrict__ digits,
-                                                     unsigned int* __restrict__ slots, unsigned int* __restrict__ counts) {
+                                                     unsigned int* __restrict__ slots, unsigned int* __restrict__ counts,
+                                                     unsigned int win_stride) {
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         // Scalar side first: the K histogram atomics (which also hand out each entry's position inside its bucket, so
@@ -105,14 +106,14 @@ __global__ void __launch_bounds__(256, 2) k_msm_prepare(const u32x4* __restrict_
                 if (k < g.K) {
                     int d = canon ? sc_digit_rt(r, g.c, k) : 0;
                     digits[(size_t)k * n + i] = (int16_t)d;
-                    if (d != 0) slot[k] = atomicAdd(&counts[(size_t)k * g.NB + (size_t)((d < 0 ? -d : d) - 1)], 1u);
+                    if (d != 0) slot[k] = atomicAdd(&counts[(size_t)k * win_stride + (size_t)((d < 0 ? -d : d) - 1)], 1u);
                 }
             }
         } else {
             for (int k = 0; k < g.K; k++) {
                 int d = canon ? sc_digit_rt(r, g.c, k) : 0;
                 digits[(size_t)k * n + i] = (int16_t)d;
-                if (d != 0) slots[(size_t)k * n + i] = atomicAdd(&counts[(size_t)k * g.NB + (size_t)((d < 0 ? -d : d) - 1)], 1u);
+                if (d != 0) slots[(size_t)k * n + i] = atomicAdd(&counts[(size_t)k * win_stride + (size_t)((d < 0 ? -d : d) - 1)], 1u);
             }
         }
         u32 ok;
@@ -250,9 +251,12 @@ static inline void launch_scan_exclusive(const unsigned int* in, unsigned int* o
     k_scan_apply<<<tiles, 1024, 0, st>>>(in, total, tile_tmp, out);
 }
 
+// win_stride = NB, idx_stride = 0: one bucket set per window, entries name the point.  win_stride = 0, idx_stride = N (shifted
+// point sets, see k_msm_shift_build): ONE bucket set for all windows, the entry of (window k, point i) names 2^(c k) P_i.
 __global__ void __launch_bounds__(256) k_msm_scatter(const int16_t* __restrict__ digits, size_t n, msm_geom g,
                                                      const unsigned int* __restrict__ offsets,
-                                                     const unsigned int* __restrict__ slots, unsigned int* __restrict__ sorted) {
+                                                     const unsigned int* __restrict__ slots, unsigned int* __restrict__ sorted,
+                                                     unsigned int win_stride, unsigned int idx_stride) {
     size_t total = (size_t)g.K * n;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
@@ -260,11 +264,10 @@ __global__ void __launch_bounds__(256) k_msm_scatter(const int16_t* __restrict__
         if (d == 0) continue;
         size_t k = t / n;
         size_t i = t - k * n;
-        size_t key = k * g.NB + (size_t)((d < 0 ? -d : d) - 1);
-        sorted[offsets[key] + slots[t]] = (unsigned int)i | (d < 0 ? 0x80000000u : 0u);
+        size_t key = k * win_stride + (size_t)((d < 0 ? -d : d) - 1);
+        sorted[offsets[key] + slots[t]] = (unsigned int)(i + k * idx_stride) | (d < 0 ? 0x80000000u : 0u);
     }
 }
-
 // ---- bucket ordering by population (descending), counting sort on min(count, 2047) -----------------------------
 // Populations cluster on a few dozen values, so the histogram and the slot reservation are privatised per block in
 // shared memory (one global atomic per (block, occupied bin) instead of one per bucket).
@@ -345,6 +348,25 @@ __device__ __forceinline__ void ge_from_niels(ge_p3& r, const ge_niels& n) {
     fe_0(r.Z);
     r.Z.v[0] = 4;
     fe_mul(r.T, dx, sy);
+}
+
+// Point sets that are reused (qq_msm_points_prepare): window k of the shifted form holds 2^(c k) P_i, so that every digit of
+// every scalar lands in ONE set of 2^(c-1) buckets and the per-window reductions and the Horner chain of 240 doublings
+// disappear from the MSM.  One step: ext_i = 2^c * prev_i (affine Niels in, extended out + Z for the batch inversion).
+__global__ void __launch_bounds__(256) k_msm_shift_build(const u32x4* __restrict__ prev, size_t n, int c, u32x4* __restrict__ ext,
+                                                         u32x4* __restrict__ zs) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        ge_niels nl;
+        niels_load_padded(nl, prev + (size_t)QQ_NIELS_STRIDE_Q * i);
+        ge_p3 p;
+        ge_from_niels(p, nl);
+        for (int k = 0; k < c; k++) ge_dbl<true>(p, p);
+        ge_p3_store(ext + (size_t)QQ_PT_Q * i, p);
+        u32x4 q;
+        q.x = p.Z.v[0]; q.y = p.Z.v[1]; q.z = p.Z.v[2]; q.w = p.Z.v[3]; zs[2 * i] = q;
+        q.x = p.Z.v[4]; q.y = p.Z.v[5]; q.z = p.Z.v[6]; q.w = p.Z.v[7]; zs[2 * i + 1] = q;
+    }
 }
 
 // ---- bucket accumulation: thread t sums the entries of virtual bucket order[t] ----------------------------------------

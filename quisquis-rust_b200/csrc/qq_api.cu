@@ -122,6 +122,11 @@ struct qq_ctx {
     bool stc_ready = false;                    // k_straus_coop's shared-memory opt-in done
     int straus_minb = 4;                       // k_straus build for more than one wave of instances (QQ_STRAUS_MINB)
     int stc_per_sm = 64;                       // segmented MSMs: four-lane cooperative kernel up to this many MSMs per SM (QQ_STRAUS_COOP_PER_SM)
+    // qq_msm_set_shifted: memory one prepared point set may take for its shifted form.  Default = what stays L2-resident
+    // (126 MB L2): measured, shifted / plain ms: 2^10-2^12 points 0.44 / 0.62, 2^16 0.61 / 0.76, 2^18 (403 MB) 1.19 / 1.14, 2^20 (1.6 GB)
+    // 3.29 / 2.35 - beyond L2 the 16 x larger gather footprint costs more than the reductions and the Horner chain save.
+    size_t msm_shift_budget = (size_t)112 << 20;
+    bool msm_use_shifted = true;
     bool secret_mode = false;                  // qq_set_secret_mode: constant-time table access for scalars that are secrets
     int vb_blocks_per_sm_secret[3] = {0, 0, 0};
     int shuffle_exact_split = 0;               // parts per exact MSM (G, H, g_r, h_r) of the aggregate form: 1, 2, 3; 0 = by batch size
@@ -571,6 +576,7 @@ extern "C" int qq_init(qq_ctx** out, int device) {
             if (const char* e = getenv("QQ_STRAUS_MINB")) ctx->straus_minb = atoi(e);
             if (const char* e = getenv("QQ_MSM_TAIL_PCT")) ctx->msm_tail_pct = atoi(e);
             if (const char* e = getenv("QQ_MSM_SORT_BPSM")) ctx->msm_sort_bpsm = atoi(e);
+            if (const char* e = getenv("QQ_MSM_SHIFT_BUDGET_MB")) ctx->msm_shift_budget = (size_t)atol(e) << 20;
             if (const char* e = getenv("QQ_VERIFY_HOST_TRANSCRIPTS")) ctx->verify_host_transcripts = atoi(e) != 0;
             if (const char* e = getenv("QQ_VERIFY_AGGREGATE")) ctx->verify_aggregate = atoi(e) != 0;
             if (const char* e = getenv("QQ_SHUFFLE_EXACT_SPLIT")) {

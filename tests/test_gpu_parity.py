@@ -590,6 +590,37 @@ def test_msm_over_prepared_points(engine):
         engine.msm_points_free(h2)
 
 
+@pytest.mark.parametrize("n", [1024, 3000, 70000])
+def test_msm_prepared_shifted_form(engine, n):
+    """Prepared point sets of 1 024 points and more also hold 2^(c k) P_i for every window (qq_msm_set_shifted): qq_msm_prepared
+    over the shifted form (one bucket set, no Horner chain), over the plain prepared form and the C oracle give the same bytes -
+    full set, prefixes, skewed scalars, zero scalars."""
+    import c_oracle as C
+    rng = np.random.default_rng(n)
+    pts, _ = engine.fixed_base(0, _rand_scalars(rng, n))
+    sc = _rand_scalars(rng, n)
+    sc[::7, 8:] = 0
+    sc[11] = 0
+    engine.msm_set_shifted(budget_bytes=1 << 30)          # the 70 000-point set is beyond the default (L2-sized) budget
+    h = engine.msm_points_prepare(pts)
+    try:
+        assert engine.lib.qq_msm_points_shifted_bytes(h) > 0
+        for m in (n, n - 1, n // 2 + 3, 300):
+            exp, es = C.msm(sc[:m], pts[:m])
+            engine.msm_set_shifted(budget_bytes=1 << 30, use_it=True)
+            o1, s1 = engine.msm_prepared(sc[:m], h)
+            engine.msm_set_shifted(budget_bytes=1 << 30, use_it=False)
+            o2, s2 = engine.msm_prepared(sc[:m], h)
+            assert es == 0 and s1 == 0 and s2 == 0 and o1.tobytes() == exp.tobytes() == o2.tobytes(), m
+        zero = np.zeros_like(sc)
+        engine.msm_set_shifted(budget_bytes=1 << 30, use_it=True)
+        o, s = engine.msm_prepared(zero, h)
+        assert s == 0 and o.tobytes() == bytes(32)
+    finally:
+        engine.msm_set_shifted()
+        engine.msm_points_free(h)
+
+
 def test_msm_skewed_scalar_distributions(engine):
     # virtual buckets: every scalar a 64-bit balance (upper windows empty), and a two-valued scalar set
     import c_oracle as C
