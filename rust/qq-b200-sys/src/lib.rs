@@ -55,6 +55,25 @@ extern "C" {
     pub fn qq_verify_product_batch(ctx: *mut QqCtx, transcript_label: *const c_char, verifier_label: *const c_char, c_prod_a: *const u8, statement: *const u8, proof: *const u8, nproofs: usize, status: *mut u8, detail: *mut u8) -> c_int;
     pub fn qq_verify_shuffle_batch(ctx: *mut QqCtx, transcript_label: *const c_char, verifier_label: *const c_char, shuffle_input: *const u8, shuffle_output: *const u8, statement: *const u8, proof: *const u8, nproofs: usize, status: *mut u8, stage: *mut u8, detail: *mut u8) -> c_int;
     pub fn qq_verify_range_proof_batch(ctx: *mut QqCtx, transcript_label: *const c_char, verifier_label: *const c_char, transcript_state: *const u8, domain_label: *const c_char, commitments: *const u8, proofs: *const u8, n_bits: usize, m: usize, chain: usize, nproofs: usize, status: *mut u8) -> c_int;
+    // round 2: wire format, secret mode, prover commitments, multi-device handle, device-side combine
+    pub fn qq_shuffle_proofs_from_bincode(input: *const u8, in_len: usize, nproofs: usize, out_proofs: *mut u8, consumed: *mut usize) -> c_int;
+    pub fn qq_shuffle_statements_from_bincode(input: *const u8, in_len: usize, nproofs: usize, out_statements: *mut u8, consumed: *mut usize) -> c_int;
+    pub fn qq_shuffle_proofs_to_bincode(proofs: *const u8, nproofs: usize, out: *mut u8, out_cap: usize, written: *mut usize) -> c_int;
+    pub fn qq_shuffle_statements_to_bincode(statements: *const u8, nproofs: usize, out: *mut u8, out_cap: usize, written: *mut usize) -> c_int;
+    pub fn qq_accounts_from_bincode(input: *const u8, in_len: usize, out_accounts: *mut u8, cap_accounts: usize, n_accounts: *mut usize, consumed: *mut usize) -> c_int;
+    pub fn qq_sigma_proof_from_bincode(input: *const u8, in_len: usize, variant: *mut c_int, out_scalars: *mut u8, cap_scalars: usize, lens: *mut usize, out_x: *mut u8, consumed: *mut usize) -> c_int;
+    pub fn qq_set_secret_mode(ctx: *mut QqCtx, on: c_int) -> c_int;
+    pub fn qq_secret_mode(ctx: *const QqCtx) -> c_int;
+    pub fn qq_sigma_commit_batch(ctx: *mut QqCtx, points: *const u8, r: *const u8, v: *const u8, out_points: *mut u8, status: *mut u8, n: usize) -> c_int;
+    pub fn qq_init_multi(out: *mut *mut QqMulti, devices: *const c_int, ndev: c_int) -> c_int;
+    pub fn qq_destroy_multi(m: *mut QqMulti);
+    pub fn qq_multi_device_count(m: *const QqMulti) -> c_int;
+    pub fn qq_multi_ctx(m: *mut QqMulti, index: c_int) -> *mut QqCtx;
+    pub fn qq_multi_update_account_batch(m: *mut QqMulti, acc: *const u8, bl: *const u8, u: *const u8, c: *const u8, out_acc: *mut u8, status: *mut u8, n: usize) -> c_int;
+    pub fn qq_multi_msm(m: *mut QqMulti, scalars: *const u8, points: *const u8, n: usize, out_point: *mut u8, status: *mut u8) -> c_int;
+    pub fn qq_multi_verify_shuffle_batch(m: *mut QqMulti, transcript_label: *const c_char, verifier_label: *const c_char, shuffle_input: *const u8, shuffle_output: *const u8, statement: *const u8, proof: *const u8, nproofs: usize, status: *mut u8, stage: *mut u8, detail: *mut u8) -> c_int;
+    pub fn qq_points_sum_dev(ctx: *mut QqCtx, records: *const u8, k: usize, stride: usize, out_point: *mut u8, is_identity: *mut u8, status: *mut u8) -> c_int;
+    pub fn qq_msm_set_shifted(ctx: *mut QqCtx, budget_bytes: usize, use_it: c_int) -> c_int;
     pub fn qq_transcript_state_bytes() -> usize;
     pub fn qq_verify_set_transcripts(ctx: *mut QqCtx, on_device: c_int) -> c_int;
     pub fn qq_verify_set_aggregation(ctx: *mut QqCtx, on: c_int) -> c_int;
