@@ -242,6 +242,16 @@ class Account:
         return self.data == o.data
 
 
+def _same_len(*seqs):
+    """The batched verifiers take n accounts and n responses per proof.  The reference zips its vectors (the shortest wins for
+    the commitments while the transcript absorbs every account), so lists of different lengths can only fail there; here they
+    are refused up front instead of silently building a different transcript."""
+    n = len(seqs[0])
+    if any(len(q) != n for q in seqs):
+        raise ValueError("account and response vectors must have the same length (%s)" % ", ".join(str(len(q)) for q in seqs))
+    return n
+
+
 class Verifier:
     @staticmethod
     def multiscalar_multiplication(combined_scalars, point):
@@ -267,7 +277,7 @@ class Verifier:
                                        transcript_label=b"UpdateAccount", verifier_label=b"DLOGProof"):
         """src/accounts/verifier.rs:223-292.  The reference receives a `Verifier` carrying a transcript; here the two labels
         that built it (Transcript::new / Verifier::new) are passed instead.  Returns None or raises ValueError(msg)."""
-        n = len(z_vector)
+        n = _same_len(updated_input_accounts, updated_delta_accounts, z_vector)
         ia = b"".join(a.data for a in updated_input_accounts)
         da = b"".join(a.data for a in updated_delta_accounts)
         st = default_engine().verify_update_account_dlog(ia, da, b"".join(bytes(v) for v in z_vector), bytes(x), n,
@@ -282,7 +292,7 @@ class Verifier:
     def verify_delta_compact_verifier(delta_accounts, epsilon_accounts, zv_vector, zr1_vector, zr2_vector, x,
                                       transcript_label=b"DeltaCompact", verifier_label=b"DLEQProof"):
         """src/accounts/verifier.rs:138-209.  Returns None or raises ValueError with the reference's message."""
-        n = len(zv_vector)
+        n = _same_len(delta_accounts, epsilon_accounts, zv_vector, zr1_vector, zr2_vector)
         da = b"".join(a.data for a in delta_accounts)
         ea = b"".join(a.data for a in epsilon_accounts)
         j = lambda v: b"".join(bytes(s) for s in v)  # noqa: E731

@@ -12,6 +12,11 @@ pub struct QqPrepared {
     _private: [u8; 0],
 }
 
+#[repr(C)]
+pub struct QqMulti {
+    _private: [u8; 0],
+}
+
 extern "C" {
     pub fn qq_init(ctx: *mut *mut QqCtx, device: c_int) -> c_int;
     pub fn qq_destroy(ctx: *mut QqCtx);
@@ -101,7 +106,16 @@ impl Gpu {
         let mut st = vec![0u8; n];
         let rc = unsafe { qq_update_account_batch(self.0, acc.as_ptr(), bl.as_ptr(), u.as_ptr(), c.as_ptr(), out.as_mut_ptr(), st.as_mut_ptr(), n) };
         assert_eq!(rc, 0, "qq_update_account_batch failed");
-        if st.iter().any(|&s| s == ST_BAD_POINT) { panic!("called `Option::unwrap()` on a `None` value"); }
+        // every status is handled: an undecodable point is the reference's `.unwrap()` panic; a non-canonical scalar cannot
+        // be built through dalek's `Scalar` API, so it is a caller bug here - never return partially valid output
+        for &s in &st {
+            match s {
+                0 => {}
+                ST_BAD_POINT => panic!("called `Option::unwrap()` on a `None` value"),
+                ST_BAD_SCALAR => panic!("qq_update_account_batch: non-canonical scalar"),
+                other => panic!("qq_update_account_batch: unexpected status {}", other),
+            }
+        }
         out
     }
     /// `Verifier::multiscalar_multiplication`: None if any point fails to decompress.
@@ -111,7 +125,12 @@ impl Gpu {
         let (mut out, mut st) = ([0u8; 32], 0u8);
         let rc = unsafe { qq_msm(self.0, scalars.as_ptr(), points.as_ptr(), n, out.as_mut_ptr(), &mut st) };
         assert_eq!(rc, 0, "qq_msm failed");
-        if st == 0 { Some(out) } else { None }
+        match st {
+            0 => Some(out),
+            ST_BAD_POINT => None, // optional_multiscalar_mul's None
+            ST_BAD_SCALAR => panic!("qq_msm: non-canonical scalar (the reference never builds one)"),
+            other => panic!("qq_msm: unexpected status {}", other),
+        }
     }
 }
 impl Drop for Gpu {
