@@ -39,6 +39,7 @@ extern "C" {
 #define QQ_ERR_CUDA (-2)
 #define QQ_ERR_NOMEM (-3)
 #define QQ_ERR_NODEVICE (-4)
+#define QQ_ERR_INTERNAL (-5) /* an internal failure (a C++ exception caught at the boundary); qq_last_error has the text */
 
 #define QQ_ST_OK 0
 #define QQ_ST_BAD_POINT 1   /* a compressed point failed RFC 9496 decoding */

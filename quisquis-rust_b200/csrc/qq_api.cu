@@ -1151,6 +1151,24 @@ struct stage {
     }
 };
 
+// No exception may cross the C ABI (the callers are ctypes and Rust): the entry points that allocate with std::vector / new or
+// start threads run their body through this guard.
+template <class F>
+static int qq_guarded(qq_ctx* ctx, F&& body) {
+    try {
+        return body();
+    } catch (const std::bad_alloc&) {
+        if (ctx) ctx->err = "out of host memory";
+        return QQ_ERR_NOMEM;
+    } catch (const std::exception& e) {
+        if (ctx) ctx->err = std::string("internal error: ") + e.what();
+        return QQ_ERR_INTERNAL;
+    } catch (...) {
+        if (ctx) ctx->err = "internal error";
+        return QQ_ERR_INTERNAL;
+    }
+}
+
 #define ENTER()                                          \
     if (!ctx) return QQ_ERR_ARG;                         \
     ctx->capture_live = ctx->transcript_capture;         \
