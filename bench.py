@@ -364,9 +364,20 @@ def run_b200(args):
             if ref_sum is None:
                 ref_sum = chk
             ent = (1 << (W - 1)) + 1
-            fixed["windows"].append({"window_bits": W, "table_bytes": ((255 + W - 1) // W) * ent * 96, "ms": best,
+            # executed work per scalar: (NW - 1) mixed additions of 7 field products + the lift of the first entry (1) + the
+            # double-and-compress encoder (4 squarings + 19 products + 3 for its share of the batch inversion); a product is
+            # 72 32x32->64 multiplies (64 + 8 for the fold), a squaring 44.  Table traffic: NW gathers of 96 bytes.
+            nw_ = (255 + W - 1) // W
+            wide_per_scalar = ((nw_ - 1) * 7 + 1 + 19 + 3) * 72 + 4 * 44
+            hbm_peak = (json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+                        if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0)
+            fixed["windows"].append({"window_bits": W, "table_bytes": nw_ * ent * 96, "ms": best,
                                      "mults_per_sec_per_gpu": nf / (best * 1e-3),
-                                     "imad_model_frac": nf * IMAD_PER_FIXED_COMPRESSED / (best * 1e-3) / peak["imad_lo_per_s"],
+                                     "executed_wide_multiplies_per_scalar": wide_per_scalar,
+                                     "wide_multiply_frac": nf * wide_per_scalar / (best * 1e-3) / peak["imad_wide_per_s"],
+                                     "table_gather_GBps": nf * nw_ * 96 / (best * 1e-3) / 1e9,
+                                     "table_gather_frac_of_hbm_peak": nf * nw_ * 96 / (best * 1e-3) / 1e9 / hbm_peak,
+                                     "table_resident_in": "L2 (126 MB)" if nw_ * ent * 96 <= 100e6 else "HBM",
                                      "same_output_as_default_window": chk == ref_sum})
         # signed 64-bit values (balances, the `bl` of update_account / generate_commitment): only the low windows are walked
         fv = torch.from_numpy(rng.integers(-2**63, 2**63 - 1, size=nf, dtype=np.int64)).to(dev)
