@@ -755,11 +755,22 @@ __global__ void __launch_bounds__(32) k_shuffle_pass_b_agg(dev_inputs d, gens g,
     if (clean) {
         for (int i = 0; i < 6; i++) states[p].fixed[i] = qq_sc::add(S.fixed[i], A.fixed[i]);
     } else {
+        // out of the aggregate: zero scalars on a decodable point (an undecodable point of THIS proof must not send the
+        // whole slice to the exact form)
         for (int i = 0; i < 6; i++) states[p].fixed[i] = qq_sc::zero();
+        const uint4 b0 = reinterpret_cast<const uint4*>(g.B)[0], b1 = reinterpret_cast<const uint4*>(g.B)[1];
         uint4* a1 = reinterpret_cast<uint4*>(j1.asc + (size_t)32 * j1.cap * (p - j1.base));
-        for (uint32_t t = 0; t < 2 * j1.cap; t++) a1[t] = z;
+        uint4* p1 = reinterpret_cast<uint4*>(j1.apt + (size_t)32 * j1.cap * (p - j1.base));
+        for (uint32_t t = 0; t < 2 * j1.cap; t++) {
+            a1[t] = z;
+            p1[t] = (t & 1) ? b1 : b0;
+        }
         uint4* a2 = reinterpret_cast<uint4*>(j2.asc + (size_t)32 * j2.cap * (p - j2.base));
-        for (uint32_t t = 0; t < 2 * j2.cap; t++) a2[t] = z;
+        uint4* p2 = reinterpret_cast<uint4*>(j2.apt + (size_t)32 * j2.cap * (p - j2.base));
+        for (uint32_t t = 0; t < 2 * j2.cap; t++) {
+            a2[t] = z;
+            p2[t] = (t & 1) ? b1 : b0;
+        }
     }
     states[p].clean = clean ? 1 : 0;
     clean_out[p] = clean ? 1 : 0;
