@@ -129,7 +129,6 @@ struct qq_ctx {
     bool msm_use_shifted = true;
     bool secret_mode = false;                  // qq_set_secret_mode: constant-time table access for scalars that are secrets
     int vb_blocks_per_sm_secret[3] = {0, 0, 0};
-    int shuffle_exact_split = 0;               // parts per exact MSM (G, H, g_r, h_r) of the aggregate form: 1, 2, 3; 0 = by batch size
     bool verify_aggregate = true;              // qq_verify_set_aggregation: identity equations of the shuffle proofs in one weighted Pippenger MSM
     bool verify_host_transcripts = false;      // qq_verify_set_transcripts(ctx, 0): per-proof phases of the shuffle verifier on the host threads
     uint8_t* d_shuffle_gens = nullptr;         // B | B_blinding | H | G[0..3) of VectorPedersenGens::new(4), device copy for the transcript kernels
@@ -579,10 +578,6 @@ extern "C" int qq_init(qq_ctx** out, int device) {
             if (const char* e = getenv("QQ_MSM_SHIFT_BUDGET_MB")) ctx->msm_shift_budget = (size_t)atol(e) << 20;
             if (const char* e = getenv("QQ_VERIFY_HOST_TRANSCRIPTS")) ctx->verify_host_transcripts = atoi(e) != 0;
             if (const char* e = getenv("QQ_VERIFY_AGGREGATE")) ctx->verify_aggregate = atoi(e) != 0;
-            if (const char* e = getenv("QQ_SHUFFLE_EXACT_SPLIT")) {
-                int v = atoi(e);
-                if (v >= 1 && v <= 3) ctx->shuffle_exact_split = v;
-            }
         }
         for (int i = 0; i < 8; i++) CK(cudaEventCreateWithFlags(&ctx->msm_ev[i], cudaEventDisableTiming));
         CK(cudaFuncSetAttribute(k_msm_sum_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * QQ_PT_BYTES));

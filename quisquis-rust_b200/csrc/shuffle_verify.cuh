@@ -115,7 +115,7 @@ struct job_sink {
         agg->k++;
     }
 };
-#define QQ_SHUFFLE_AGG_CAP_1 44      // aggregated (non-fixed) terms of a proof that passes every scalar check: batch 1
+#define QQ_SHUFFLE_AGG_CAP_1 64      // aggregated (non-fixed) terms of a proof that passes every scalar check: batch 1
 #define QQ_SHUFFLE_AGG_CAP_2 102     // and batch 2
 
 // 128-bit weights of the aggregated checks: Keccak-f over (fresh 32-byte entropy of this call, proof index, batch tag,
@@ -477,6 +477,24 @@ QQ_HOSTDEV static inline void pass_a(proof_state& S, const job_sink& j1, size_t 
         S.had_pre = QQ_ST_BAD_SCALAR;
         return;
     }
+    if (j1.agg) {
+        // Aggregate mode.  An accepted proof carries the encodings of G and H itself: the pubkey argument checks
+        // E_k_0[3] == enc(G), E_k_1[3] == enc(H) ("Verify Em == C").  So G and H are TAKEN from those bytes - the transcript
+        // absorbs them, g_r = z G + c G_dash and h_r become two-term MSMs on them - and "sum x^i pk_i == dec(E_k[3])" joins the
+        // aggregated equations.  If the claim is false the aggregate fails and the exact form gives the verdict.
+        const uint8_t *Gclaim = pr + 2048 + 224 + 96, *Hclaim = pr + 2048 + 416 + 96;
+        for (int i = 0; i < 9; i++) {
+            j1.set(p, 14, i, ex[i], in + 128 * i);
+            j1.set(p, 15, i, ex[i], in + 128 * i + 32);
+        }
+        j1.set(p, 14, 9, neg(one()), Gclaim);
+        j1.set(p, 15, 9, neg(one()), Hclaim);
+        j1.set(p, 16, 0, dz, Gclaim);
+        j1.set(p, 16, 1, dc, stm + 288);
+        j1.set(p, 17, 0, dz, Hclaim);
+        j1.set(p, 17, 1, dc, stm + 320);
+        return;
+    }
     for (int i = 0; i < 9; i++) {
         j1.set(p, 14, i, ex[i], in + 128 * i);
         j1.set(p, 15, i, ex[i], in + 128 * i + 32);
@@ -584,16 +602,17 @@ QQ_HOSTDEV static inline bool pass_b(proof_state& S, const job_sink& j2, size_t 
     return aggregate;
 }
 
-// Aggregate mode: sinks and weights of the two passes.  Batch 1: slots 14..17 (G, H, g_r, h_r) are exact MSMs 0..3 of the
-// exact list {9, 9, 10, 10}; slot 7 (c_B decodes) is skipped (the same points carry scalars in slot 10); 13 weights.
+// Aggregate mode: sinks and weights of the two passes.  Batch 1: slots 16, 17 (g_r, h_r) are exact MSMs 0, 1 of the exact
+// list {2, 2}; slots 14, 15 (G, H against the proof's own encodings of them) are aggregated equations like the rest; slot 7
+// (c_B decodes) is skipped (the same points carry scalars in slot 10); 15 weights.
 // Batch 2: no exact slots; the right half of an E_K pair carries minus the weight of the left half (ek_set negated its
 // terms for the enc(left) == enc(right) comparison of the exact form); 10 weights.
 QQ_HOSTDEV static inline void agg_begin_a(agg_ctx& a, const uint8_t entropy[32], size_t p) {
-    sc w[13];
-    agg_weights(w, 13, entropy, (uint64_t)p, 1);
+    sc w[15];
+    agg_weights(w, 15, entropy, (uint64_t)p, 1);
     int k = 0;
     for (int m = 0; m < QQ_JOB_MAX_MSMS; m++) a.w[m] = qq_sc::zero();
-    for (int m = 0; m < 14; m++)
+    for (int m = 0; m < 16; m++)
         if (m != 7) a.w[m] = w[k++];
     for (int i = 0; i < 6; i++) a.fixed[i] = qq_sc::zero();
     a.k = 0;
@@ -736,11 +755,12 @@ __global__ void __launch_bounds__(32) k_shuffle_pass_a_agg(dev_inputs d, gens g,
     S.clean = A.overflow ? 0 : 1;
     states[p] = S;
 }
-// eG / sG: the exact MSMs G, H, g_r, h_r of every proof (4 x 32 B, 4 status bytes per proof).  A proof that is not clean
-// drops out of the aggregate (its scalars are zeroed) and is verified in the exact form afterwards.
+// ex / sx: the exact MSMs g_r, h_r of every proof (2 x 32 B, 2 status bytes per proof); G and H are the proof's own encodings
+// of them (see pass_a).  A proof that is not clean drops out of the aggregate (its scalars are zeroed) and is verified in the
+// exact form afterwards.
 __global__ void __launch_bounds__(32) k_shuffle_pass_b_agg(dev_inputs d, gens g, job_sink j1, job_sink j2, entropy32 ent,
-                                                           proof_state* __restrict__ states, const uint8_t* __restrict__ eG,
-                                                           const uint8_t* __restrict__ sG, uint8_t* __restrict__ clean_out) {
+                                                           proof_state* __restrict__ states, const uint8_t* __restrict__ ex,
+                                                           const uint8_t* __restrict__ sx, uint8_t* __restrict__ clean_out) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= d.nproofs) return;
     proof_state S = states[p];
@@ -748,9 +768,16 @@ __global__ void __launch_bounds__(32) k_shuffle_pass_b_agg(dev_inputs d, gens g,
     agg_begin_b(A, ent.b, p);
     j2.agg = &A;
     bool clean = S.clean != 0;
-    if (clean)
-        clean = pass_b(S, j2, p, d.proof + QQ_SHUFFLE_PROOF_BYTES * p, d.stm + QQ_SHUFFLE_STATEMENT_BYTES * p, d.in + 9 * 128 * p,
-                       d.out + 9 * 128 * p, nullptr, nullptr, eG + 128 * p, sG + 4 * p, g) && !A.overflow;
+    if (clean) {
+        const uint8_t* pr = d.proof + QQ_SHUFFLE_PROOF_BYTES * p;
+        alignas(16) uint8_t eG[128];
+        uint8_t sG[4] = {0, 0, sx[2 * p], sx[2 * p + 1]};
+        memcpy(eG, pr + 2048 + 224 + 96, 32);
+        memcpy(eG + 32, pr + 2048 + 416 + 96, 32);
+        memcpy(eG + 64, ex + 64 * p, 64);
+        clean = pass_b(S, j2, p, pr, d.stm + QQ_SHUFFLE_STATEMENT_BYTES * p, d.in + 9 * 128 * p, d.out + 9 * 128 * p, nullptr, nullptr,
+                       eG, sG, g) && !A.overflow;
+    }
     uint4 z = make_uint4(0, 0, 0, 0);
     if (clean) {
         for (int i = 0; i < 6; i++) states[p].fixed[i] = qq_sc::add(S.fixed[i], A.fixed[i]);

@@ -377,7 +377,7 @@ void hh_shuffle_verify(const char* transcript_label, const char* verifier_label,
         detail[p] = S.dt;
     }
 }
-// Aggregate form of the same verification (the fast path of qq_verify_shuffle_batch): per proof the exact MSMs G, H, g_r, h_r,
+// Aggregate form of the same verification (the fast path of qq_verify_shuffle_batch): per proof the exact MSMs g_r, h_r,
 // every other group equation weighted into ONE sum over all proofs, which must be the identity.  clean[p]: the proof passed
 // every scalar check and is inside the aggregate; *agg_identity: the aggregated MSM (clean proofs only) is the identity;
 // counts[2 p], counts[2 p + 1]: aggregated (non-fixed) terms the proof emitted in batch 1 / 2.
@@ -394,16 +394,17 @@ void hh_shuffle_verify_aggregate(const char* transcript_label, const char* verif
     qq_sc::sc fixed[6];
     for (int i = 0; i < 6; i++) fixed[i] = qq_sc::zero();
     for (size_t p = 0; p < n; p++) {
-        std::vector<uint8_t> xsc(38 * 32, 0), xpt(38 * 32);
-        for (size_t t = 0; t < 38; t++) memcpy(&xpt[32 * t], base_pk, 32);
+        std::vector<uint8_t> xsc(4 * 32, 0), xpt(4 * 32);
+        for (size_t t = 0; t < 4; t++) memcpy(&xpt[32 * t], base_pk, 32);
         job_sink j1, j2;
         memset((void*)&j1, 0, sizeof j1);
         memset((void*)&j2, 0, sizeof j2);
         for (int m = 0; m < QQ_JOB_MAX_MSMS; m++) j1.exact_slot[m] = j2.exact_slot[m] = -1;
-        const uint32_t xf[5] = {0, 9, 18, 28, 38};
-        for (int m = 0; m < 5; m++) j1.first[m] = xf[m];
-        j1.sc = xsc.data(); j1.pt = xpt.data(); j1.msms_pp = 4; j1.terms_pp = 38; j1.base = p;
-        for (int m = 0; m < 4; m++) j1.exact_slot[14 + m] = (int8_t)m;
+        const uint32_t xf[3] = {0, 2, 4};
+        for (int m = 0; m < 3; m++) j1.first[m] = xf[m];
+        j1.sc = xsc.data(); j1.pt = xpt.data(); j1.msms_pp = 2; j1.terms_pp = 4; j1.base = p;
+        j1.exact_slot[16] = 0;
+        j1.exact_slot[17] = 1;
         j1.asc = asc.data() + 32 * C1 * p; j1.apt = apt.data() + 32 * C1 * p; j1.cap = (uint32_t)C1;
         j2.base = p;
         j2.asc = asc.data() + 32 * (C1 * n + C2 * p); j2.apt = apt.data() + 32 * (C1 * n + C2 * p); j2.cap = (uint32_t)C2;
@@ -418,8 +419,10 @@ void hh_shuffle_verify_aggregate(const char* transcript_label, const char* verif
         qq_sc::sc fa[6];
         for (int i = 0; i < 6; i++) fa[i] = A.fixed[i];
         bool ok = !A.overflow;
-        uint8_t eG[128], sG[4];
-        hh_segmented(xsc.data(), xpt.data(), j1.first, 4, eG, sG);
+        uint8_t eG[128], sG[4] = {0, 0, 0, 0};
+        memcpy(eG, pr + 2048 + 224 + 96, 32);          // G, H: the proof's own encodings (checked inside the aggregate)
+        memcpy(eG + 32, pr + 2048 + 416 + 96, 32);
+        hh_segmented(xsc.data(), xpt.data(), j1.first, 2, eG + 64, sG + 2);
         agg_begin_b(A, entropy, p);
         j2.agg = &A;
         if (ok) ok = pass_b(S, j2, p, pr, sm, in + 1152 * p, out + 1152 * p, nullptr, nullptr, eG, sG, g) && !A.overflow;

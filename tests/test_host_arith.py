@@ -375,7 +375,7 @@ def test_shuffle_phases_shared_with_the_transcript_kernels(hh):
         return list(clean.raw), ident.raw[0], list(counts)
     clean, ident, counts = run_agg(*cols(raw), n)
     assert clean == [1] * n and ident == 1
-    assert counts == [44, 102] * n                       # QQ_SHUFFLE_AGG_CAP_1 / _2 are exact for a clean proof
+    assert counts == [64, 102] * n                       # QQ_SHUFFLE_AGG_CAP_1 / _2 are exact for a clean proof
     clean, ident, counts = run_agg(*cols(raw), n, entropy=bytes(32))
     assert clean == [1] * n and ident == 1               # other weights, same verdict
     clean, ident, counts = run_agg(*cols(bad), n)
