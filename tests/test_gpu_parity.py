@@ -1711,3 +1711,58 @@ def test_msm_large_vs_c_oracle(engine, n):
     out, s = engine.msm(a, pts)
     exp, es = C.msm(a, pts)
     assert s == 0 and es == 0 and out.tobytes() == exp.tobytes()
+
+
+def test_shuffle_verification_beyond_one_device_slice(engine):
+    """More proofs than one device slice holds (2^15): the call walks the slices, verdicts land at their positions - 32 768 + 37
+    tiled golden proofs with tampered ones on both sides of the slice boundary and at the very end."""
+    import os
+    raw = np.fromfile(os.path.join(os.path.dirname(__file__), "golden", "shuffle_proofs.bin"), dtype=np.uint8).reshape(-1, 6432)
+    n = (1 << 15) + 37
+    rec = np.tile(raw, ((n + raw.shape[0] - 1) // raw.shape[0], 1))[:n].copy()
+    bad = {5: 2656 + 3776 - 40, (1 << 15) - 1: 2656 + 3776 - 40, 1 << 15: 2656 + 3776 - 40, n - 1: 2656 + 3776 - 40}
+    for i, off in bad.items():
+        rec[i, off] ^= 1          # the DDH response z: a scalar-level failure (those proofs leave the aggregate, the rest is accepted by it)
+    si, so, stm, pr = (np.ascontiguousarray(rec[:, a:b]) for a, b in ((0, 1152), (1152, 2304), (2304, 2656), (2656, 6432)))
+    st, sg, det = engine.verify_shuffle(si, so, stm, pr)
+    assert sorted(np.nonzero(st)[0].tolist()) == sorted(bad)
+    assert all(int(sg[i]) == 6 for i in bad)
+
+
+def test_multi_engine_verifiers_equal_single_engine(pkg, engine):
+    """qq_multi_verify_shuffle_batch / qq_multi_verify_range_proof_batch / qq_multi_update_account_batch / qq_multi_msm over every
+    visible GPU (one is enough) give the single-context results, tampered proofs at the slice boundaries included."""
+    import os
+    import torch
+    ndev = max(1, min(8, torch.cuda.device_count()))
+    me = pkg.MultiEngine(list(range(ndev)))
+    try:
+        raw = np.fromfile(os.path.join(os.path.dirname(__file__), "golden", "shuffle_proofs.bin"), dtype=np.uint8).reshape(-1, 6432)
+        n = 203
+        rec = np.tile(raw, ((n + raw.shape[0] - 1) // raw.shape[0], 1))[:n].copy()
+        for i in {0, n // ndev - 1, n // ndev, n - 1}:
+            rec[i % n, 1152 + 11] ^= 2
+        cols = [np.ascontiguousarray(rec[:, a:b]) for a, b in ((0, 1152), (1152, 2304), (2304, 2656), (2656, 6432))]
+        a, b = me.verify_shuffle(*cols), engine.verify_shuffle(*cols)
+        for x, y in zip(a, b):
+            assert x.tolist() == y.tolist()
+        assert np.count_nonzero(a[0]) >= 2
+        m = 4
+        per = m * 32 + engine.range_proof_bytes(m)
+        rr = np.fromfile(os.path.join(os.path.dirname(__file__), "golden", "range_proofs_m%d.bin" % m), dtype=np.uint8).reshape(-1, per)
+        rr = np.tile(rr, (40, 1))[:151].copy()
+        rr[77, m * 32 + 5 * 32 + 3] ^= 1
+        cm, prf = np.ascontiguousarray(rr[:, :m * 32]), np.ascontiguousarray(rr[:, m * 32:])
+        assert me.verify_range_proofs(cm, prf, m).tolist() == engine.verify_range_proofs(cm, prf, m).tolist()
+        rng = np.random.default_rng(12)
+        k = 1001
+        acc = np.concatenate([engine.fixed_base(0, _rand_scalars(rng, k))[0] for _ in range(4)], axis=1).copy()
+        bl, u, c = _rand_scalars(rng, k), _rand_scalars(rng, k), _rand_scalars(rng, k)
+        o1, s1 = me.update_account(acc, bl, u, c)
+        o2, s2 = engine.update_account(acc, bl, u, c)
+        assert np.array_equal(o1, o2) and np.array_equal(s1, s2)
+        pts = acc[:, :32].copy()
+        r1, r2 = me.msm(u, pts), engine.msm(u, pts)
+        assert r1[1] == r2[1] == 0 and r1[0].tobytes() == r2[0].tobytes()
+    finally:
+        me.close()
