@@ -1729,6 +1729,26 @@ def test_shuffle_verification_beyond_one_device_slice(engine):
     assert all(int(sg[i]) == 6 for i in bad)
 
 
+def test_shuffle_aggregate_bisection(engine):
+    """From 8 192 proofs on, a failing aggregate is bisected down to ranges of 64 proofs which then run the exact form: 8 300 tiled
+    golden proofs with three group-level tamperings (an output account byte: only the group equations see it) far apart and one
+    scalar-level tampering - exactly those are rejected, with the stage the exact form alone reports for them."""
+    import os
+    raw = np.fromfile(os.path.join(os.path.dirname(__file__), "golden", "shuffle_proofs.bin"), dtype=np.uint8).reshape(-1, 6432)
+    n = 8300
+    rec = np.tile(raw, ((n + raw.shape[0] - 1) // raw.shape[0], 1))[:n].copy()
+    group_bad = [3, 4100, 8299]
+    for i in group_bad:
+        rec[i, 1152 + 200] ^= 1
+    rec[6000, 2656 + 3776 - 40] ^= 1
+    cols = [np.ascontiguousarray(rec[:, a:b]) for a, b in ((0, 1152), (1152, 2304), (2304, 2656), (2656, 6432))]
+    st, sg, det = engine.verify_shuffle(*cols)
+    assert sorted(np.nonzero(st)[0].tolist()) == sorted(group_bad + [6000])
+    for i in group_bad + [6000]:
+        s1, g1, d1 = engine.verify_shuffle(*[c[i:i + 1] for c in cols])
+        assert (int(s1[0]), int(g1[0]), int(d1[0])) == (int(st[i]), int(sg[i]), int(det[i])), i
+
+
 def test_multi_engine_verifiers_equal_single_engine(pkg, engine):
     """qq_multi_verify_shuffle_batch / qq_multi_verify_range_proof_batch / qq_multi_update_account_batch / qq_multi_msm over every
     visible GPU (one is enough) give the single-context results, tampered proofs at the slice boundaries included."""
