@@ -350,10 +350,12 @@ int qq_verify_product_batch(qq_ctx* ctx, const char* transcript_label, const cha
 int qq_verify_shuffle_batch(qq_ctx* ctx, const char* transcript_label, const char* verifier_label, const uint8_t* shuffle_input,
                             const uint8_t* shuffle_output, const uint8_t* statement, const uint8_t* proof, size_t nproofs,
                             uint8_t* status, uint8_t* stage, uint8_t* detail);
-/* Where qq_verify_shuffle_batch runs the per-proof Fiat-Shamir transcripts (Merlin, src/accounts/transcript.rs:55-82) and
- * the Z/l algebra: on_device != 0 (default) in transcript kernels, one GPU thread per proof - the proof bytes are the only
- * upload, job lists, transcripts and verdicts stay in device memory; on_device == 0 on the host threads, job lists uploaded
- * per batch (the round-1 arrangement, kept for A/B measurements).  Verdicts are identical. */
+/* Where the batched verifiers (qq_verify_shuffle_batch, qq_verify_range_proof_batch, the sigma verifiers qq_verify_*_batch of
+ * src/accounts/verifier.rs and qq_verify_ddh_batch) run the per-proof Fiat-Shamir transcripts (Merlin,
+ * src/accounts/transcript.rs:55-82) and the Z/l algebra: on_device != 0 (default) in transcript kernels, one GPU thread per
+ * proof - the proof bytes are the only upload, job lists, transcripts and verdicts stay in device memory; on_device == 0 on
+ * the host threads, job lists uploaded per batch (the round-1 arrangement, kept for A/B measurements; the sigma verifiers also
+ * take it for batches of at most 4 proofs, where a serial GPU transcript costs more than it saves).  Verdicts are identical. */
 int qq_verify_set_transcripts(qq_ctx* ctx, int on_device);
 /* Aggregate form of the device-resident shuffle verifier (default on).  on: per proof only G, H, g_r, h_r (the MSM results
  * the transcript absorbs) are evaluated on their own; the other 28 group equations of every proof are multiplied by fresh

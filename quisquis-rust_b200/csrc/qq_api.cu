@@ -27,6 +27,7 @@
 #include "decommit.cuh"
 #include "rangeproof.cuh"
 #include "shuffle_verify.cuh"
+#include "sigma_verify.cuh"
 
 using namespace qq;
 
@@ -113,7 +114,7 @@ struct qq_ctx {
     bool bp_ready = false;                     // BulletproofGens::new(64, 16) (compressed, party-major), derived on first use
     std::vector<uint8_t> bp_g, bp_h;
     // qq_transcript_capture arms (pointer, capacity in states) for the NEXT entry point only: ENTER() of every entry point moves
-    // them to capture_live / capture_cap (and disarms); only sigma_run reads the live pair, so a call that returns early, a
+    // them to capture_live / capture_cap (and disarms); only sigma_verify reads the live pair, so a call that returns early, a
     // verifier that keeps no transcript or an exception between the two calls can never leave a stale pointer behind
     uint8_t* transcript_capture = nullptr;
     size_t transcript_capture_cap = 0;

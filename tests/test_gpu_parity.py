@@ -762,7 +762,18 @@ def test_fixed_base_signed_64_bit_values(engine, W):
             engine.fixed_base_set_window(which, old[which])
 
 
-def test_verify_update_account_dlog_proofs(engine):
+@pytest.fixture(params=["device", "host"])
+def transcript_mode(engine, request):
+    """qq_verify_set_transcripts for the sigma verifiers: the per-proof phases of sigma_verify.cuh in k_sigma_emit /
+    k_sigma_finish (default) and on the host threads; every verdict test below runs in both."""
+    engine.verify_set_transcripts(request.param == "device")
+    try:
+        yield request.param
+    finally:
+        engine.verify_set_transcripts(True)
+
+
+def test_verify_update_account_dlog_proofs(engine, transcript_mode):
     """Verifier::verify_update_account_verifier, batched.  Replays the reference's scenario (verifier.rs:1006-1072):
     9 updated accounts, values [-5, 5, 0 x 7], delta accounts, the anonymity-set slice [2..9]; the proofs come from the
     oracle's restatement of the prover; accept / reject verdicts must match the oracle's verifier, proof by proof."""
@@ -818,7 +829,7 @@ def test_verify_update_account_dlog_proofs(engine):
     assert int(got[0]) == 1 and int(got[1]) == 2 and int(got[4]) == 0
 
 
-def test_verify_delta_compact_proofs(engine):
+def test_verify_delta_compact_proofs(engine, transcript_mode):
     """Verifier::verify_delta_compact_verifier, batched; the reference's scenario (verifier.rs:938-1003): 9 accounts,
     values [-5, 5, 0 x 7], delta + epsilon accounts from create_delta_and_epsilon_accounts; verdicts equal the oracle's."""
     import sigma_ref as S
@@ -863,7 +874,7 @@ def _status_of(verdict):
     return {True: 0, False: 6, None: 1}[verdict]
 
 
-def test_verify_dark_tx_destroy_and_same_value_proofs(engine):
+def test_verify_dark_tx_destroy_and_same_value_proofs(engine, transcript_mode):
     """Verifier::verify_update_account_dark_tx_verifier, destroy_account_verifier, verify_same_value_compact_verifier,
     batched; the reference's scenarios (verifier.rs:1075-1111, :1455-1479, :1736-1775) with proofs from the oracle's prover
     restatements.  Verdict per proof equals the oracle's verifier, tampered and undecodable inputs included."""
@@ -939,7 +950,7 @@ def test_verify_dark_tx_destroy_and_same_value_proofs(engine):
         api.Verifier.verify_same_value_compact_verifier(api.Account(k[0]), k[1], ([sb(k[2])], [sb(k[3])], [], sb(k[4])))
 
 
-def test_verify_zero_balance_and_sender_account_proofs(engine):
+def test_verify_zero_balance_and_sender_account_proofs(engine, transcript_mode):
     """Verifier::zero_balance_account_verifier / zero_balance_account_vector_verifier (verifier.rs:1386-1452) and the
     sigma part of verify_account_verifier[_bulletproof] (scenario of the reference's commented-out test, :1115-1216)."""
     import sigma_ref as S
@@ -1760,8 +1771,8 @@ def test_multi_engine_verifiers_equal_single_engine(pkg, engine):
         raw = np.fromfile(os.path.join(os.path.dirname(__file__), "golden", "shuffle_proofs.bin"), dtype=np.uint8).reshape(-1, 6432)
         n = 203
         rec = np.tile(raw, ((n + raw.shape[0] - 1) // raw.shape[0], 1))[:n].copy()
-        for i in {0, n // ndev - 1, n // ndev, n - 1}:
-            rec[i % n, 1152 + 11] ^= 2
+        for i in {0, n // ndev - 1, (n // ndev) % n, n - 1}:
+            rec[i, 1152 + 11] ^= 2
         cols = [np.ascontiguousarray(rec[:, a:b]) for a, b in ((0, 1152), (1152, 2304), (2304, 2656), (2656, 6432))]
         a, b = me.verify_shuffle(*cols), engine.verify_shuffle(*cols)
         for x, y in zip(a, b):
