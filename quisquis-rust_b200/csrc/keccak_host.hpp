@@ -32,7 +32,22 @@ static const uint64_t RC_HOST[24] = QQ_KECCAK_RC_WORDS;
 static __constant__ uint64_t RC_DEV[24] = QQ_KECCAK_RC_WORDS;     // the same round constants through the constant bank
 #endif
 
-QQ_HOSTDEV static inline uint64_t rotl(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }   // 0 < n < 64
+// 0 < n < 64.  Device: two funnel shifts on the 32-bit halves (n is a constant at every call site); written as shifts and an OR
+// ptxas spends 4-5 instructions per rotation (279 instructions per round instead of ~210).
+QQ_HOSTDEV static inline uint64_t rotl(uint64_t x, int n) {
+#ifdef __CUDA_ARCH__
+    uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    if (n & 32) {
+        const uint32_t t = lo;
+        lo = hi;
+        hi = t;
+    }
+    if ((n & 31) == 0) return ((uint64_t)hi << 32) | lo;
+    return ((uint64_t)__funnelshift_l(lo, hi, n & 31) << 32) | __funnelshift_l(hi, lo, n & 31);
+#else
+    return (x << n) | (x >> (64 - n));
+#endif
+}
 
 QQ_HOSTDEV QQ_NOINLINE static void f1600(uint64_t a[25]) {
 #ifdef __CUDA_ARCH__
@@ -47,6 +62,7 @@ QQ_HOSTDEV QQ_NOINLINE static void f1600(uint64_t a[25]) {
     uint64_t a10 = a[10], a11 = a[11], a12 = a[12], a13 = a[13], a14 = a[14];
     uint64_t a15 = a[15], a16 = a[16], a17 = a[17], a18 = a[18], a19 = a[19];
     uint64_t a20 = a[20], a21 = a[21], a22 = a[22], a23 = a[23], a24 = a[24];
+#pragma unroll 2
     for (int round = 0; round < 24; round++) {
         const uint64_t c0 = a0 ^ a5 ^ a10 ^ a15 ^ a20, c1 = a1 ^ a6 ^ a11 ^ a16 ^ a21, c2 = a2 ^ a7 ^ a12 ^ a17 ^ a22,
                        c3 = a3 ^ a8 ^ a13 ^ a18 ^ a23, c4 = a4 ^ a9 ^ a14 ^ a19 ^ a24;
@@ -77,6 +93,53 @@ QQ_HOSTDEV QQ_NOINLINE static void f1600(uint64_t a[25]) {
     a[15] = a15; a[16] = a16; a[17] = a17; a[18] = a18; a[19] = a19;
     a[20] = a20; a[21] = a21; a[22] = a22; a[23] = a23; a[24] = a24;
 }
+
+#ifdef __CUDACC__
+// ---- warp-cooperative form -------------------------------------------------------------------------------------------------
+// Every lane of a fully converged warp holds the SAME state a[25] (the transcript kernels in their warp-per-proof form: 32
+// lanes run one proof's script redundantly).  Lane i < 25 carries word i through the 24 rounds - theta's column parities, the
+// pi permutation and chi's row neighbours are warp shuffles (8 64-bit shuffles per round) - and all lanes receive all 25
+// words at the end.  Lanes 25..31 shadow words 0..6; nothing reads them.  One thread alone needs ~4 600 dependent-ish
+// instructions per permutation; here a round is ~45.
+static __constant__ uint8_t RHO_DEV[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
+    const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src), hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+    return ((uint64_t)hi << 32) | lo;
+}
+__device__ __forceinline__ uint64_t rotl_var(uint64_t v, unsigned n) {      // 0 <= n < 64
+    uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+    if (n & 32) {
+        const uint32_t t = lo;
+        lo = hi;
+        hi = t;
+    }
+    const uint32_t nlo = __funnelshift_l(hi, lo, n), nhi = __funnelshift_l(lo, hi, n);      // shift taken mod 32
+    return ((uint64_t)nhi << 32) | nlo;
+}
+__device__ __noinline__ static void f1600_warp(uint64_t a[25]) {
+    const int lane = threadIdx.x & 31;
+    const int i = lane < 25 ? lane : lane - 25;
+    const int x = i % 5, y = i / 5;
+    const unsigned rho = RHO_DEV[i];
+    const int up1 = i + 5 < 25 ? i + 5 : i - 20, up2 = i + 10 < 25 ? i + 10 : i - 15, up4 = i + 20 < 25 ? i + 20 : i - 5;
+    const int col_m1 = (x + 4) % 5, col_p1 = (x + 1) % 5;                   // any lane of a column holds its parity: row 0
+    const int src_pi = ((x + 3 * y) % 5) + 5 * x;                           // B[x'][y'] = rot(A[x][y]), x' = y, y' = 2x + 3y, as a gather
+    const int row_p1 = 5 * y + (x + 1) % 5, row_p2 = 5 * y + (x + 2) % 5;
+    uint64_t w = a[i];
+#pragma unroll 1
+    for (int round = 0; round < 24; round++) {
+        const uint64_t s1 = w ^ shfl64(w, up1);
+        const uint64_t c = s1 ^ shfl64(s1, up2) ^ shfl64(w, up4);
+        const uint64_t d = shfl64(c, col_m1) ^ rotl_var(shfl64(c, col_p1), 1);
+        const uint64_t b = shfl64(rotl_var(w ^ d, rho), src_pi);
+        const uint64_t b1 = shfl64(b, row_p1), b2 = shfl64(b, row_p2);
+        w = b ^ (~b1 & b2);
+        if (i == 0) w ^= RC_DEV[round];
+    }
+#pragma unroll
+    for (int k = 0; k < 25; k++) a[k] = shfl64(w, k);
+}
+#endif
 
 struct sponge {
     uint64_t st[25];

@@ -99,86 +99,109 @@ class strobe128 {
             if (pos == R) run_f();
         }
     }
-    // ---- fused operations: one pass over "operation header | bytes" instead of one absorb call per piece ---------------------
-    // (a Merlin append_message is meta-AD(label) | meta-AD(le32 length, continued) | AD(message): five separate absorbs of 2, |label|,
-    // 4, 2 and n bytes, each a read-modify-write chain on the state in local memory; the transcript kernels spent half their
-    // time there)
-    QQ_HOSTDEV void absorb_word(uint64_t v, unsigned c) {                   // the low c <= 8 bytes of v
-        while (c) {
-            const unsigned room = (unsigned)(R - pos), t = c < room ? c : room;
-            xor_at(pos, t == 8 ? v : (v & ((1ULL << (8 * t)) - 1)), t);
-            pos = (uint8_t)(pos + t);
-            if (pos == R) run_f();
-            v = t == 8 ? 0 : v >> (8 * t);
-            c -= t;
-        }
-    }
-    struct feeder {      // bytes -> little-endian words -> absorb_word
+    // ---- fused operations: one pass over "operation header | label | length | operation header | bytes" with the cursor in registers --
+    // A Merlin append_message is meta-AD(label) | meta-AD(le32 length, continued) | AD(message): five separate absorbs of 2, |label|,
+    // 4, 2 and n bytes.  Done through the member functions above, every piece reloads pos / pos_begin from the object (local memory
+    // in the transcript kernels), and two neighbouring pieces read-modify-write the same state word through memory: chains of
+    // dependent local-memory round trips (31 % of the transcript kernels' time for 15 % of their instructions, ncu source view).
+    // The cursor keeps pos / pos_begin and the pending bytes of the current state word in registers: every state word is
+    // loaded, xored and stored exactly once per operation, and the accesses of different words are independent.
+    struct cursor {
         strobe128& s;
-        uint64_t acc;
-        unsigned cnt;
-        QQ_HOSTDEV explicit feeder(strobe128& st_) : s(st_), acc(0), cnt(0) {}
-        QQ_HOSTDEV void put(uint8_t b) {
-            acc |= (uint64_t)b << (8 * cnt);
-            if (++cnt == 8) {
-                s.absorb_word(acc, 8);
-                acc = 0;
-                cnt = 0;
-            }
-        }
-        QQ_HOSTDEV void put_word(uint64_t w) {                              // eight bytes at once
-            if (cnt == 0) {
-                s.absorb_word(w, 8);
-            } else {
-                s.absorb_word(acc | (w << (8 * cnt)), 8);
-                acc = w >> (64 - 8 * cnt);
-            }
-        }
-        QQ_HOSTDEV void flush() {
-            if (cnt) s.absorb_word(acc, cnt);
+        uint64_t* w;
+        unsigned pos, pos_begin;
+        uint64_t acc;      // bytes absorbed since the last flush, at their place inside state word (pos >> 3)
+        QQ_HOSTDEV explicit cursor(strobe128& st_) : s(st_), w(st_.words()), pos(st_.pos), pos_begin(st_.pos_begin), acc(0) {}
+        QQ_HOSTDEV void flush_word(unsigned q) {
+            w[q] ^= acc;
             acc = 0;
-            cnt = 0;
+        }
+        QQ_HOSTDEV void run_f() {                     // acc is empty here
+            w[pos >> 3] ^= (uint64_t)pos_begin << (8 * (pos & 7));
+            w[(pos + 1) >> 3] ^= (uint64_t)0x04 << (8 * ((pos + 1) & 7));
+            w[(R + 1) >> 3] ^= (uint64_t)0x80 << (8 * ((R + 1) & 7));
+            s.permute();
+            pos = 0;
+            pos_begin = 0;
+        }
+        // the low c <= 8 bytes of v (the bytes above them must be zero)
+        QQ_HOSTDEV void put(uint64_t v, unsigned c) {
+            while (c) {
+                const unsigned o = pos & 7, room_word = 8 - o, room_rate = (unsigned)R - pos;
+                unsigned t = c < room_word ? c : room_word;
+                if (t > room_rate) t = room_rate;
+                acc |= v << (8 * o);                  // bytes beyond the word (or beyond t) are cut by the shift / re-fed below
+                if (t < 8 && o + t < 8) acc &= ~0ULL >> (8 * (8 - o - t));
+                pos += t;
+                if ((pos & 7) == 0 || pos == (unsigned)R) flush_word((pos - 1) >> 3);
+                if (pos == (unsigned)R) run_f();
+                v = t == 8 ? 0 : v >> (8 * t);
+                c -= t;
+            }
+        }
+        QQ_HOSTDEV void begin(uint8_t flags) {        // begin_op for flags without C / K (no forced permutation)
+            const unsigned old_begin = pos_begin;
+            pos_begin = pos + 1;
+            put((uint64_t)old_begin | ((uint64_t)flags << 8), 2);
+        }
+        QQ_HOSTDEV void label_len(const char* label, uint32_t n) {
+            uint64_t v = 0;
+            unsigned cnt = 0;
+            for (unsigned i = 0; label[i]; i++) {
+                v |= (uint64_t)(uint8_t)label[i] << (8 * cnt);
+                if (++cnt == 8) {
+                    put(v, 8);
+                    v = 0;
+                    cnt = 0;
+                }
+            }
+            if (cnt <= 4) {
+                put(v | ((uint64_t)n << (8 * cnt)), cnt + 4);
+            } else {
+                put(v, cnt);
+                put(n, 4);
+            }
+        }
+        QQ_HOSTDEV void finish(uint8_t flags) {
+            if (pos & 7) flush_word(pos >> 3);
+            s.pos = (uint8_t)pos;
+            s.pos_begin = (uint8_t)pos_begin;
+            s.cur_flags = flags;
         }
     };
-    // begin_op(flags) | label | le32(n) as a continuation of the same operation   (flags = M | A)
+    // meta-AD(label | le32(n)) as one operation
     QQ_HOSTDEV QQ_NOINLINE void op_label_len(uint8_t flags, const char* label, uint32_t n) {
-        const uint8_t old_begin = pos_begin;
-        pos_begin = (uint8_t)(pos + 1);
-        cur_flags = flags;
-        feeder f(*this);
-        f.put(old_begin);
-        f.put(flags);
-        for (unsigned i = 0; label[i]; i++) f.put((uint8_t)label[i]);
-        f.put((uint8_t)n);
-        f.put((uint8_t)(n >> 8));
-        f.put((uint8_t)(n >> 16));
-        f.put((uint8_t)(n >> 24));
-        f.flush();
+        cursor c(*this);
+        c.begin(flags);
+        c.label_len(label, n);
+        c.finish(flags);
     }
-    // begin_op(flags) | n bytes of data   (flags without C / K: no forced permutation)
-    QQ_HOSTDEV QQ_NOINLINE void op_data(uint8_t flags, const uint8_t* d, size_t n) {
-        const uint8_t old_begin = pos_begin;
-        pos_begin = (uint8_t)(pos + 1);
-        cur_flags = flags;
-        feeder f(*this);
-        if (n <= 64 && (n & 7) == 0 && (reinterpret_cast<uintptr_t>(d) & 7) == 0) {
-            // the common case (points, scalars, wide challenges): all words loaded before the state is touched
-            uint64_t w[8];
-            const unsigned nw = (unsigned)(n >> 3);
+    // the whole append_message: meta-AD(label | le32(n)), then AD(msg)
+    QQ_HOSTDEV QQ_NOINLINE void op_append(const char* label, const uint8_t* d, size_t n) {
+        // the common case (points, scalars, wide challenges): the message words are loaded before the state is touched - d is a
+        // generic pointer the compiler cannot tell apart from st[], interleaved it would serialise one memory latency per load
+        const bool words = n <= 64 && (n & 7) == 0 && (reinterpret_cast<uintptr_t>(d) & 7) == 0;
+        uint64_t m[8];
+        const unsigned nw = words ? (unsigned)(n >> 3) : 0;
 #pragma unroll
-            for (unsigned k = 0; k < 8; k++) w[k] = k < nw ? reinterpret_cast<const uint64_t*>(d)[k] : 0;
-            f.put(old_begin);
-            f.put(flags);
+        for (unsigned k = 0; k < 8; k++) m[k] = k < nw ? reinterpret_cast<const uint64_t*>(d)[k] : 0;
+        cursor c(*this);
+        c.begin(FLAG_M | FLAG_A);
+        c.label_len(label, (uint32_t)n);
+        c.begin(FLAG_A);
+        if (words) {
 #pragma unroll
             for (unsigned k = 0; k < 8; k++)
-                if (k < nw) f.put_word(w[k]);
-            f.flush();
-            return;
+                if (k < nw) c.put(m[k], 8);
+        } else {
+            while (n) {
+                const unsigned t = n < 8 ? (unsigned)n : 8u;
+                c.put(load_le(d, t), t);
+                d += t;
+                n -= t;
+            }
         }
-        f.put(old_begin);
-        f.put(flags);
-        f.flush();
-        absorb(d, n);
+        c.finish(FLAG_A);
     }
     QQ_HOSTDEV QQ_NOINLINE void begin_op(uint8_t flags, bool more) {
         if (more) return;   // continuation of the current operation (same flags by construction)
@@ -244,8 +267,7 @@ class transcript {
     QQ_HOSTDEV void export_state(uint8_t* out) const { s.export_state(out); }
     QQ_HOSTDEV bool import_state(const uint8_t* in) { return s.import_state(in); }
     QQ_HOSTDEV void append_message(const char* label, const uint8_t* msg, size_t n) {
-        s.op_label_len(strobe128::FLAG_M | strobe128::FLAG_A, label, (uint32_t)n);
-        s.op_data(strobe128::FLAG_A, msg, n);
+        s.op_append(label, msg, n);
     }
     QQ_HOSTDEV void challenge_bytes(const char* label, uint8_t* out, size_t n) {
         s.op_label_len(strobe128::FLAG_M | strobe128::FLAG_A, label, (uint32_t)n);

@@ -75,15 +75,20 @@ struct job_sink {
 #ifdef __CUDA_ARCH__
         // the job arrays are 32-byte aligned device buffers; so are the points of the uploaded proofs (every struct size
         // is a multiple of 32) - the generators and MSM outputs as well.  16-byte accesses instead of 64 byte moves.
+        // Both halves of the point are loaded before anything is stored: through generic pointers the compiler must keep a
+        // load behind every earlier store, and each load is a trip to L2 / HBM.
         uint4* ds = reinterpret_cast<uint4*>(&sc_arr[32 * i]);
-        ds[0] = make_uint4((uint32_t)s.v[0], (uint32_t)(s.v[0] >> 32), (uint32_t)s.v[1], (uint32_t)(s.v[1] >> 32));
-        ds[1] = make_uint4((uint32_t)s.v[2], (uint32_t)(s.v[2] >> 32), (uint32_t)s.v[3], (uint32_t)(s.v[3] >> 32));
         uint4* dp = reinterpret_cast<uint4*>(&pt_arr[32 * i]);
         if ((reinterpret_cast<uintptr_t>(point) & 15) == 0) {
             const uint4* sp = reinterpret_cast<const uint4*>(point);
-            dp[0] = sp[0];
-            dp[1] = sp[1];
+            const uint4 p0 = sp[0], p1 = sp[1];
+            ds[0] = make_uint4((uint32_t)s.v[0], (uint32_t)(s.v[0] >> 32), (uint32_t)s.v[1], (uint32_t)(s.v[1] >> 32));
+            ds[1] = make_uint4((uint32_t)s.v[2], (uint32_t)(s.v[2] >> 32), (uint32_t)s.v[3], (uint32_t)(s.v[3] >> 32));
+            dp[0] = p0;
+            dp[1] = p1;
         } else {
+            ds[0] = make_uint4((uint32_t)s.v[0], (uint32_t)(s.v[0] >> 32), (uint32_t)s.v[1], (uint32_t)(s.v[1] >> 32));
+            ds[1] = make_uint4((uint32_t)s.v[2], (uint32_t)(s.v[2] >> 32), (uint32_t)s.v[3], (uint32_t)(s.v[3] >> 32));
             memcpy(&pt_arr[32 * i], point, 32);
         }
 #else
