@@ -1263,12 +1263,34 @@ extern "C" int qq_update_account_batch_dev(qq_ctx* ctx, const uint8_t* acc, cons
     CKQ(core_update_account(ctx, acc, bl, u, c, out_acc, status, n));
     return call_end(ctx);
 }
-// Host-pointer entry of the headline path.  The batch is cut into slices of QQ_PIPE_SLICE accounts; the upload of slice
-// i + 1 (copy stream) and the download of slice i - 1 (second copy stream) run under the kernels of slice i, so that with
-// pinned host memory only the first upload and the last download are exposed (352 bytes per account cross PCIe).
-#define QQ_PIPE_SLICE ((size_t)1 << 18)
+// Host-pointer entry of the headline path.  The batch is cut into slices; the upload of slice i + 1 (copy stream) and the
+// download of slice i - 1 (second copy stream) run under the kernels of slice i, so that with pinned host memory only the
+// first upload and the last download are exposed (352 bytes per account cross PCIe).  Those two are kept short - the first
+// slice is two waves of the dominant kernel (k_varbase_split: one 512-thread block per SM, two scalar-mult jobs per account
+// = 256 accounts per SM and wave; 6 ms of kernels, enough to cover the upload of everything behind it up to 2^20 accounts),
+// the last slice one wave - and the slices between them are as large as the chunking allows: every slice pays the latency
+// of its own batch inversions (k_binv_*, ~0.3 ms), so few slices, each a whole number of waves.
+static void pipe_slices(const qq_ctx* ctx, size_t n, std::vector<size_t>& cuts) {
+    const size_t wave = (size_t)ctx->sms * 256;
+    cuts.clear();
+    cuts.push_back(0);
+    if (n <= 4 * wave) {
+        cuts.push_back(n);
+        return;
+    }
+    size_t lo = 2 * wave;
+    cuts.push_back(lo);
+    const size_t big = (((size_t)1 << 20) / wave) * wave;
+    while (n - lo > big + wave) {
+        lo += big;
+        cuts.push_back(lo);
+    }
+    cuts.push_back(n - wave);
+    cuts.push_back(n);
+}
 extern "C" int qq_update_account_batch(qq_ctx* ctx, const uint8_t* acc, const uint8_t* bl, const uint8_t* u,
                                        const uint8_t* c, uint8_t* out_acc, uint8_t* status, size_t n) {
+    return qq_guarded(ctx, [&]() -> int {
     ENTER();
     REQUIRE(acc && bl && u && c && out_acc && status);
     stage st(ctx);
@@ -1279,7 +1301,9 @@ extern "C" int qq_update_account_batch(qq_ctx* ctx, const uint8_t* acc, const ui
     uint8_t* dc = st.take(n * 32);
     uint8_t* dout = st.take(n * 128);
     uint8_t* dst = st.take(n);
-    size_t nsl = (n + QQ_PIPE_SLICE - 1) / QQ_PIPE_SLICE;
+    std::vector<size_t> cuts;
+    pipe_slices(ctx, n, cuts);
+    const size_t nsl = cuts.size() - 1;
     while (ctx->pipe_ev.size() < 2 * nsl) {
         cudaEvent_t e;
         CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1289,7 +1313,7 @@ extern "C" int qq_update_account_batch(qq_ctx* ctx, const uint8_t* acc, const ui
     CK(cudaEventRecord(ctx->msm_ev[7], ctx->stream));
     CK(cudaStreamWaitEvent(ctx->copy_in, ctx->msm_ev[7], 0));
     for (size_t i = 0; i < nsl; i++) {
-        size_t lo = i * QQ_PIPE_SLICE, m = n - lo < QQ_PIPE_SLICE ? n - lo : QQ_PIPE_SLICE;
+        const size_t lo = cuts[i], m = cuts[i + 1] - lo;
         CK(cudaMemcpyAsync(dacc + lo * 128, acc + lo * 128, m * 128, cudaMemcpyHostToDevice, ctx->copy_in));
         CK(cudaMemcpyAsync(dbl + lo * 32, bl + lo * 32, m * 32, cudaMemcpyHostToDevice, ctx->copy_in));
         CK(cudaMemcpyAsync(du + lo * 32, u + lo * 32, m * 32, cudaMemcpyHostToDevice, ctx->copy_in));
@@ -1297,7 +1321,7 @@ extern "C" int qq_update_account_batch(qq_ctx* ctx, const uint8_t* acc, const ui
         CK(cudaEventRecord(ctx->pipe_ev[2 * i], ctx->copy_in));
     }
     for (size_t i = 0; i < nsl; i++) {
-        size_t lo = i * QQ_PIPE_SLICE, m = n - lo < QQ_PIPE_SLICE ? n - lo : QQ_PIPE_SLICE;
+        const size_t lo = cuts[i], m = cuts[i + 1] - lo;
         CK(cudaStreamWaitEvent(ctx->stream, ctx->pipe_ev[2 * i], 0));
         CKQ(core_update_account(ctx, dacc + lo * 128, dbl + lo * 32, du + lo * 32, dc + lo * 32, dout + lo * 128, dst + lo, m));
         CK(cudaEventRecord(ctx->pipe_ev[2 * i + 1], ctx->stream));
@@ -1308,6 +1332,7 @@ extern "C" int qq_update_account_batch(qq_ctx* ctx, const uint8_t* acc, const ui
     CK(cudaEventRecord(ctx->msm_ev[6], ctx->copy_out));
     CK(cudaStreamWaitEvent(ctx->stream, ctx->msm_ev[6], 0));   // call_end synchronises the main stream
     return call_end(ctx);
+    });
 }
 extern "C" int qq_verify_account_batch_dev(qq_ctx* ctx, const uint8_t* acc, const uint8_t* sk, const uint8_t* bl,
                                            uint8_t* status, size_t n) {
