@@ -228,6 +228,15 @@ int qq_points_sum(qq_ctx* ctx, const uint8_t* xyzt, size_t k, uint8_t* out_point
  * instance j covers terms offsets[j] .. offsets[j+1]-1 ; out m x 32 B ; status m */
 int qq_msm_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* points, const uint32_t* offsets, size_t m,
                      uint8_t* out_points, uint8_t* status);
+/* m independent LARGE MSMs (hundreds to millions of terms each; m <= 4096) in ONE Pippenger pass: MSM j covers terms
+ * offsets[j] .. offsets[j+1]-1 (offsets[0] = 0), out m x 32 B, status m (`optional_multiscalar_mul` semantics per MSM: a bad
+ * term fails its own MSM only).  The windows of MSM j are the windows [j K, (j + 1) K) of one bucket array, so sorting, bucket
+ * accumulation and the running-sum reduction are one launch each for all MSMs and the m Horner chains run side by side.
+ * This is the per-proof form of Bulletproofs verification (RangeProof::verify_multiple is ONE MSM per proof,
+ * src/accounts/verifier.rs:517) for a batch of proofs, and what the batched verifiers use to locate the failing proofs when a
+ * randomised aggregate does not verify. */
+int qq_msm_grouped(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* points, const uint32_t* offsets, size_t m,
+                   uint8_t* out_points, uint8_t* status);
 
 /* ---- sigma-protocol verification ----------------------------------------------------------------------------------
  * Verifier::verify_update_account_verifier (src/accounts/verifier.rs:223-292) for `nproofs` independent proofs over n

@@ -20,7 +20,7 @@ EXPORTS = [
     "qq_verify_account_batch", "qq_verify_account_batch_dev", "qq_delta_epsilon_batch", "qq_delta_identity_check",
     "qq_fixed_base_batch", "qq_fixed_base_batch_dev", "qq_fixed_base_set_window", "qq_fixed_base_window", "qq_varbase_set_coop_limit",
     "qq_fixed_base_i64_batch", "qq_fixed_base_i64_batch_dev", "qq_msm", "qq_msm_dev", "qq_msm_partial", "qq_msm_partial_dev",
-    "qq_points_sum", "qq_msm_segmented", "qq_msm_points_prepare", "qq_msm_points_prepare_dev", "qq_msm_points_free",
+    "qq_points_sum", "qq_msm_segmented", "qq_msm_grouped", "qq_msm_points_prepare", "qq_msm_points_prepare_dev", "qq_msm_points_free",
     "qq_msm_points_count", "qq_msm_prepared", "qq_msm_prepared_dev",
     "qq_verify_ddh_batch", "qq_verify_svp_batch", "qq_verify_hadamard_batch", "qq_verify_product_batch", "qq_verify_shuffle_batch",
     "qq_verify_account_sigma_batch", "qq_verify_zero_balance_batch", "qq_verify_destroy_account_batch",
@@ -161,6 +161,7 @@ def load_library():
     for name in ("qq_msm_prepared", "qq_msm_prepared_dev"):
         getattr(lib, name).argtypes = [vp, u8p, vp, sz, u8p, u8p]
     lib.qq_msm_segmented.argtypes = [vp, u8p, u8p, vp, sz, u8p, u8p]
+    lib.qq_msm_grouped.argtypes = [vp, u8p, u8p, vp, sz, u8p, u8p]
     for name in EXPORTS:
         f = getattr(lib, name)
         if f.restype is ctypes.c_int and name not in ("qq_device_sm_count", "qq_last_kernel_breakdown"):
@@ -785,6 +786,15 @@ class Engine:
         m = offsets.size - 1
         out, st = np.zeros(m * 32, np.uint8), np.zeros(m, np.uint8)
         self._ck(self.lib.qq_msm_segmented(self.h, _ptr(scalars), _ptr(points), ctypes.c_void_p(offsets.ctypes.data), m, _ptr(out), _ptr(st)), "qq_msm_segmented")
+        return out.reshape(m, 32), st
+
+    def msm_grouped(self, scalars, points, offsets):
+        """m independent large MSMs in one Pippenger pass (CSR offsets as msm_segmented) -> (m x 32 encodings, m status bytes)"""
+        scalars, points = _u8(scalars), _u8(points)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+        m = offsets.size - 1
+        out, st = np.zeros(m * 32, np.uint8), np.zeros(m, np.uint8)
+        self._ck(self.lib.qq_msm_grouped(self.h, _ptr(scalars), _ptr(points), ctypes.c_void_p(offsets.ctypes.data), m, _ptr(out), _ptr(st)), "qq_msm_grouped")
         return out.reshape(m, 32), st
 
     # ---- device-pointer calls (pointers are ints / c_void_p on this engine's GPU) ---------------------------------

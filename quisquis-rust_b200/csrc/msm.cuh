@@ -85,9 +85,11 @@ __global__ void __launch_bounds__(256, 2) k_msm_prepare(const u32x4* __restrict_
                                                      const uint8_t* __restrict__ pre_ok,
                                                      uint8_t* __restrict__ term_status, int16_t* __restrict__ digits,
                                                      unsigned int* __restrict__ slots, unsigned int* __restrict__ counts,
-                                                     unsigned int win_stride) {
+                                                     unsigned int win_stride, const unsigned int* __restrict__ group_of) {
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        // grouped form (several independent MSMs in one pass): group g owns the windows [g K, (g + 1) K) of the bucket array
+        const size_t kb = group_of != nullptr ? (size_t)group_of[i] * (size_t)g.K : 0;
         // Scalar side first: the K histogram atomics (which also hand out each entry's position inside its bucket, so
         // the scatter needs no atomics) are issued before the decompression and collected after it -- their round
         // trips hide behind the square-root chain.  Digits do not depend on the point's validity: a bad term fails
@@ -106,14 +108,14 @@ __global__ void __launch_bounds__(256, 2) k_msm_prepare(const u32x4* __restrict_
                 if (k < g.K) {
                     int d = canon ? sc_digit_rt(r, g.c, k) : 0;
                     digits[(size_t)k * n + i] = (int16_t)d;
-                    if (d != 0) slot[k] = atomicAdd(&counts[(size_t)k * win_stride + (size_t)((d < 0 ? -d : d) - 1)], 1u);
+                    if (d != 0) slot[k] = atomicAdd(&counts[(kb + k) * win_stride + (size_t)((d < 0 ? -d : d) - 1)], 1u);
                 }
             }
         } else {
             for (int k = 0; k < g.K; k++) {
                 int d = canon ? sc_digit_rt(r, g.c, k) : 0;
                 digits[(size_t)k * n + i] = (int16_t)d;
-                if (d != 0) slots[(size_t)k * n + i] = atomicAdd(&counts[(size_t)k * win_stride + (size_t)((d < 0 ? -d : d) - 1)], 1u);
+                if (d != 0) slots[(size_t)k * n + i] = atomicAdd(&counts[(kb + k) * win_stride + (size_t)((d < 0 ? -d : d) - 1)], 1u);
             }
         }
         u32 ok;
@@ -256,7 +258,8 @@ static inline void launch_scan_exclusive(const unsigned int* in, unsigned int* o
 __global__ void __launch_bounds__(256) k_msm_scatter(const int16_t* __restrict__ digits, size_t n, msm_geom g,
                                                      const unsigned int* __restrict__ offsets,
                                                      const unsigned int* __restrict__ slots, unsigned int* __restrict__ sorted,
-                                                     unsigned int win_stride, unsigned int idx_stride) {
+                                                     unsigned int win_stride, unsigned int idx_stride,
+                                                     const unsigned int* __restrict__ group_of) {
     size_t total = (size_t)g.K * n;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
@@ -264,7 +267,8 @@ __global__ void __launch_bounds__(256) k_msm_scatter(const int16_t* __restrict__
         if (d == 0) continue;
         size_t k = t / n;
         size_t i = t - k * n;
-        size_t key = k * win_stride + (size_t)((d < 0 ? -d : d) - 1);
+        size_t kb = group_of != nullptr ? (size_t)group_of[i] * (size_t)g.K : 0;
+        size_t key = (kb + k) * win_stride + (size_t)((d < 0 ? -d : d) - 1);
         sorted[offsets[key] + slots[t]] = (unsigned int)(i + k * idx_stride) | (d < 0 ? 0x80000000u : 0u);
     }
 }
@@ -573,9 +577,12 @@ __global__ void __launch_bounds__(128) k_msm_window_totals(const u32x4* __restri
     if (act) coop_store(wins + QQ_PT_Q * k, r, t);
 }
 // result = sum_k 2^(c k) win[k]: a chain of c (K - 1) dependent doublings (240 for c = 16), each one squaring + one
-// multiplication of latency.  One warp; every group of four lanes computes the same chain, group 0 stores it.
+// multiplication of latency.  One warp per MSM (block b: the windows [b K, (b + 1) K) of the grouped form); every group of four
+// lanes computes the same chain, the first one stores it.
 __global__ void __launch_bounds__(32) k_msm_horner(const u32x4* __restrict__ win, msm_geom g, u32x4* __restrict__ result) {
     int r = threadIdx.x & 3;
+    win += QQ_PT_Q * (size_t)blockIdx.x * g.K;
+    result += QQ_PT_Q * (size_t)blockIdx.x;
     fe acc = coop_load(win + QQ_PT_Q * (size_t)(g.K - 1), r);
     for (int k = g.K - 2; k >= 0; k--) {
         for (int i = 0; i < g.c; i++) acc = coop_dbl(acc, r);
@@ -583,6 +590,47 @@ __global__ void __launch_bounds__(32) k_msm_horner(const u32x4* __restrict__ win
         acc = coop_add(acc, coop_to_cached(p, r), r);
     }
     if (threadIdx.x < 4) coop_store(result, r, acc);
+}
+
+// ---- grouped form: G independent MSMs in one pass ---------------------------------------------------------------------------
+// group_of[i] for terms given as CSR segments (offsets[G + 1]): one thread per term, binary search
+__global__ void k_msm_group_of(const unsigned int* __restrict__ offsets, unsigned int G, size_t n, unsigned int* __restrict__ group_of) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        unsigned int lo = 0, hi = G;      // offsets[lo] <= i < offsets[hi]
+        while (hi - lo > 1) {
+            unsigned int mid = (lo + hi) >> 1;
+            if (offsets[mid] <= i) lo = mid;
+            else hi = mid;
+        }
+        group_of[i] = lo;
+    }
+}
+// per group: the status of its first failing term (keys preset to ~0), then one status byte and one "is the identity" flag
+__global__ void k_msm_group_first_bad(const uint8_t* __restrict__ term_status, const unsigned int* __restrict__ group_of, size_t n,
+                                      unsigned long long* __restrict__ keys) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint8_t s = term_status[i];
+        if (s) atomicMin(&keys[group_of[i]], (unsigned long long)i * 4 + s);
+    }
+}
+__global__ void k_msm_group_verdicts(const u32x4* __restrict__ results, const unsigned long long* __restrict__ keys, unsigned int G,
+                                     u32x4* __restrict__ compressed, uint8_t* __restrict__ status, uint8_t* __restrict__ is_identity) {
+    unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= G) return;
+    ge_p3 p;
+    ge_p3_load(p, results + QQ_PT_Q * (size_t)t);
+    const uint8_t st = keys[t] == ~0ull ? 0 : (uint8_t)(keys[t] & 3);
+    u32 w[8];
+    ristretto_compress(w, p);
+    if (st) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) w[i] = 0;
+    }
+    if (compressed != nullptr) store_words32(compressed, t, w);
+    status[t] = st;
+    is_identity[t] = (uint8_t)(st == 0 && ge_ristretto_is_identity(p));
 }
 
 }  // namespace qq

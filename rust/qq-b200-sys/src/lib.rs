@@ -85,6 +85,7 @@ extern "C" {
     pub fn qq_msm_set_overlap(ctx: *mut QqCtx, split_min: std::os::raw::c_long, tail_pct: c_int, sort_blocks_per_sm: c_int) -> c_int;
     pub fn qq_transcript_capture(ctx: *mut QqCtx, states_out: *mut u8, capacity_states: usize) -> c_int;
     pub fn qq_msm_segmented(ctx: *mut QqCtx, scalars: *const u8, points: *const u8, offsets: *const u32, m: usize, out: *mut u8, status: *mut u8) -> c_int;
+    pub fn qq_msm_grouped(ctx: *mut QqCtx, scalars: *const u8, points: *const u8, offsets: *const u32, m: usize, out: *mut u8, status: *mut u8) -> c_int;
 }
 
 pub const ST_BAD_POINT: u8 = 1;

@@ -329,6 +329,48 @@ def test_msm_pippenger_vs_c_oracle(engine, n):
     assert s == es == 1 and o.tobytes() == bytes(32)
 
 
+def test_msm_grouped_vs_c_oracle(engine):
+    """qq_msm_grouped: independent large MSMs in one Pippenger pass.  Ragged segments (empty, one term, hundreds, thousands), a bad
+    point and a non-canonical scalar in two of them: every MSM equals the C oracle's MSM over its own terms, a failure stays
+    inside its segment; and one segment alone equals qq_msm."""
+    import c_oracle as C
+    rng = np.random.default_rng(2024)
+    sizes = [700, 0, 1, 2049, 333, 5000, 64, 1200, 0, 257]
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint32)
+    n = int(offs[-1])
+    pts, _ = engine.fixed_base(0, _rand_scalars(rng, n))
+    sc = _rand_scalars(rng, n)
+    sc[::5, 8:] = 0
+    sc[int(offs[3]) + 7] = 0
+    pts[int(offs[4]) + 100] = np.frombuffer(invalid_encodings()[0][1], np.uint8)
+    sc[int(offs[7]) + 5] = np.frombuffer(R.L.to_bytes(32, "little"), np.uint8)
+    out, st = engine.msm_grouped(sc, pts, offs)
+    for j, m in enumerate(sizes):
+        lo, hi = int(offs[j]), int(offs[j + 1])
+        if m == 0:
+            assert st[j] == 0 and out[j].tobytes() == bytes(32), j
+            continue
+        eo, es = C.msm(sc[lo:hi], pts[lo:hi])
+        assert int(st[j]) == es, j
+        assert out[j].tobytes() == (eo.tobytes() if es == 0 else bytes(32)), j
+    assert [int(x) for x in st] == [0, 0, 0, 0, 1, 0, 0, 2, 0, 0]
+    o1, s1 = engine.msm(sc[int(offs[5]):int(offs[6])], pts[int(offs[5]):int(offs[6])])
+    assert s1 == 0 and o1.tobytes() == out[5].tobytes()
+    # many equal segments (the shape the verifiers use: 64 groups), and a single group
+    m = 64
+    per = 900
+    offs = (np.arange(m + 1) * per).astype(np.uint32)
+    pts, _ = engine.fixed_base(1, _rand_scalars(rng, m * per))
+    sc = _rand_scalars(rng, m * per)
+    out, st = engine.msm_grouped(sc, pts, offs)
+    assert not st.any()
+    for j in (0, 17, 63):
+        eo, es = C.msm(sc[j * per:(j + 1) * per], pts[j * per:(j + 1) * per])
+        assert es == 0 and eo.tobytes() == out[j].tobytes(), j
+    out1, st1 = engine.msm_grouped(sc[:per], pts[:per], offs[:2])
+    assert st1[0] == 0 and out1[0].tobytes() == out[0].tobytes()
+
+
 def test_msm_overlapped_tail_decompression(engine):
     """The large-MSM path that decompresses the last 30 % of the points under the counting sort (second stream) gives the same
     point and the same first-failure status as the single-stream path and as the C oracle; bad terms in head and tail."""
