@@ -96,6 +96,8 @@ struct qq_ctx {
     u32* bsgs_slots = nullptr;
     u32x4* msm_res = nullptr;                 // per-call MSM result point + export bytes (outside the workspace slab)
     uint8_t* msm_small = nullptr;
+    uint8_t* fb = nullptr;                    // scratch of the verifiers' failure paths (grouped checks), grown on demand
+    size_t fb_cap = 0;
     u32x4* fbt[2] = {nullptr, nullptr};       // large-window tables in L2 / HBM (fixedbase_big.cuh), optional
     fbt_geom fbt_g[2] = {{0, 0, 0}, {0, 0, 0}};
     u32x4* half_base[2] = {nullptr, nullptr};  // ((l + 1) / 2) * Base as affine Niels, for the 64-bit fixed-base path
@@ -657,6 +659,7 @@ extern "C" void qq_destroy(qq_ctx* ctx) {
     if (ctx->bsgs_slots) cudaFree(ctx->bsgs_slots);
     if (ctx->msm_res) cudaFree(ctx->msm_res);
     if (ctx->msm_small) cudaFree(ctx->msm_small);
+    if (ctx->fb) cudaFree(ctx->fb);
     if (ctx->d_shuffle_gens) cudaFree(ctx->d_shuffle_gens);
     for (int i = 0; i < 8; i++)
         if (ctx->user_ev[i]) cudaEventDestroy(ctx->user_ev[i]);

@@ -54,12 +54,25 @@ __global__ void __launch_bounds__(160) k_rp_tables(const rp_record* __restrict__
     (t == 0 ? o.sa : t == 1 ? o.sb : t == 2 ? o.slo : t == 3 ? o.yhi : o.ylo)[e] = v;
 }
 // grid = (ceil(N / block), chunks); partial: chunks x 2N scalars (g sums then h sums)
+// chunk_first == nullptr: the count (sub-)proofs from `first` on are split evenly over the chunks.  Otherwise (the grouped form:
+// one chunk per group, its partial sums are the group's generator scalars) chunk y covers the per_chunk (sub-)proofs from
+// chunk_first[y] on, cut at first + count.
 __global__ void __launch_bounds__(128) k_rp_fold(const rp_record* __restrict__ rec, const rp_tables* __restrict__ tbl, unsigned int first,
-                                                 unsigned int count, int n_bits, int N, int lg, qq_sc::sc* __restrict__ partial) {
+                                                 unsigned int count, int n_bits, int N, int lg, qq_sc::sc* __restrict__ partial,
+                                                 unsigned int per_chunk, const unsigned int* __restrict__ chunk_first) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
-    unsigned int per = (count + gridDim.y - 1) / gridDim.y;
-    unsigned int p0 = blockIdx.y * per, p1 = p0 + per < count ? p0 + per : count;
+    unsigned int p0, p1;
+    if (chunk_first != nullptr) {
+        const unsigned int base = chunk_first[blockIdx.y], end = first + count;
+        p0 = 0;
+        p1 = base >= end ? 0 : (end - base < per_chunk ? end - base : per_chunk);
+        first = base;
+    } else {
+        unsigned int per = (count + gridDim.y - 1) / gridDim.y;
+        p0 = blockIdx.y * per;
+        p1 = p0 + per < count ? p0 + per : count;
+    }
     // thread i owns g_i and h_j with j = nm - 1 - i: both need the same s_i
     qq_sc::sc sum_g = qq_sc::zero(), sum_h = qq_sc::zero();
     const int j = N - 1 - i;
@@ -95,6 +108,45 @@ __global__ void __launch_bounds__(128) k_rp_fold_sum(const qq_sc::sc* __restrict
         __syncthreads();
     }
     if (threadIdx.x == 0) out[t] = sh[0];
+}
+
+// Grouped form of the aggregate (the failure path: which groups of transcripts do not verify?): the term list
+// [groups x (2N + 2) shared terms | groups x terms_per_group proof terms] with the group of every term.  partial: groups x 2N
+// generator scalars (k_rp_fold, one chunk per group), shared: groups x 2 (B_blinding, B), gen: the 2N + 2 shared points.  The
+// proof terms of group g are gathered from src_sc / src_pt (T terms per (sub-)proof) starting at (sub-)proof chunk_first[g];
+// slots beyond `end_sub` (a short last group) are padded with 0 * B.
+__global__ void k_rp_group_terms(const qq_sc::sc* __restrict__ partial, const qq_sc::sc* __restrict__ shared, const uint8_t* __restrict__ gen,
+                                 unsigned int groups, unsigned int twoN, const unsigned int* __restrict__ chunk_first, unsigned int end_sub,
+                                 unsigned int T, size_t terms_per_group, const uint8_t* __restrict__ src_sc, const uint8_t* __restrict__ src_pt,
+                                 uint8_t* __restrict__ sc, uint8_t* __restrict__ pt, unsigned int* __restrict__ group_of) {
+    const size_t G = (size_t)twoN + 2, nshared = (size_t)groups * G, total = nshared + (size_t)groups * terms_per_group;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        uint4* ds = reinterpret_cast<uint4*>(sc + 32 * t);
+        uint4* dp = reinterpret_cast<uint4*>(pt + 32 * t);
+        if (t < nshared) {
+            const size_t g = t / G, j = t - g * G;
+            reinterpret_cast<qq_sc::sc*>(sc)[t] = j < twoN ? partial[g * twoN + j] : shared[2 * g + (j - twoN)];
+            const uint4* src = reinterpret_cast<const uint4*>(gen + 32 * j);
+            const uint4 p0 = src[0], p1 = src[1];
+            dp[0] = p0;
+            dp[1] = p1;
+            group_of[t] = (unsigned int)g;
+        } else {
+            const size_t u = t - nshared, g = u / terms_per_group, within = u - g * terms_per_group;
+            const size_t st = (size_t)chunk_first[g] * T + within;
+            const bool live = st < (size_t)end_sub * T;
+            const uint4* ss = reinterpret_cast<const uint4*>(src_sc + 32 * st);
+            const uint4* sp = reinterpret_cast<const uint4*>((live ? src_pt + 32 * st : gen + 32 * ((size_t)twoN + 1)));
+            const uint4 s0 = live ? ss[0] : z, s1 = live ? ss[1] : z, p0 = sp[0], p1 = sp[1];
+            ds[0] = s0;
+            ds[1] = s1;
+            dp[0] = p0;
+            dp[1] = p1;
+            group_of[t] = (unsigned int)g;
+        }
+    }
 }
 
 }  // namespace qq

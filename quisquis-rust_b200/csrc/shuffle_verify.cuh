@@ -807,13 +807,16 @@ __global__ void __launch_bounds__(32) k_shuffle_pass_b_agg(dev_inputs d, gens g,
     states[p].clean = clean ? 1 : 0;
     clean_out[p] = clean ? 1 : 0;
 }
-// the six fixed-generator terms of the aggregate: scalar i = sum over the proofs of states[p].fixed[i]   (grid = 6 blocks)
-__global__ void __launch_bounds__(256) k_shuffle_fixed_sum(const proof_state* __restrict__ states, size_t nproofs, gens g,
+// the six fixed-generator terms of the aggregate: scalar i = sum over the proofs of states[p].fixed[i].  grid = 6 blocks for
+// the whole batch (group_size >= nproofs), 6 G blocks for the grouped form: block 6 grp + i sums the proofs
+// [grp * group_size, (grp + 1) * group_size) into term 6 grp + i.
+__global__ void __launch_bounds__(256) k_shuffle_fixed_sum(const proof_state* __restrict__ states, size_t nproofs, size_t group_size, gens g,
                                                            uint8_t* __restrict__ out_sc, uint8_t* __restrict__ out_pt) {
     __shared__ qq_sc::sc part[256];
-    const int i = blockIdx.x;
+    const int i = blockIdx.x % 6;
+    const size_t grp = blockIdx.x / 6, lo = grp * group_size, hi = lo + group_size < nproofs ? lo + group_size : nproofs;
     qq_sc::sc acc = qq_sc::zero();
-    for (size_t p = threadIdx.x; p < nproofs; p += blockDim.x) acc = qq_sc::add(acc, states[p].fixed[i]);
+    for (size_t p = lo + threadIdx.x; p < hi; p += blockDim.x) acc = qq_sc::add(acc, states[p].fixed[i]);
     part[threadIdx.x] = acc;
     __syncthreads();
     for (int h = 128; h > 0; h >>= 1) {
@@ -822,8 +825,15 @@ __global__ void __launch_bounds__(256) k_shuffle_fixed_sum(const proof_state* __
     }
     if (threadIdx.x == 0) {
         const uint8_t* pt = i == 0 ? g.B : i == 1 ? g.Hp : i == 2 ? g.H : g.G + 32 * (i - 3);
-        job_sink::put(out_sc, out_pt, (size_t)i, part[0], pt);
+        job_sink::put(out_sc, out_pt, 6 * grp + (size_t)i, part[0], pt);
     }
+}
+// group of every term of the aggregated list [nproofs x cap1 | nproofs x cap2 | 6 per group] (grouped form, qq_msm_grouped's layout)
+__global__ void k_shuffle_group_of(size_t nproofs, size_t cap1, size_t cap2, size_t group_size, size_t groups, unsigned int* __restrict__ group_of) {
+    const size_t n1 = nproofs * cap1, n2 = nproofs * cap2, total = n1 + n2 + 6 * groups;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride)
+        group_of[t] = (unsigned int)(t < n1 ? (t / cap1) / group_size : t < n1 + n2 ? ((t - n1) / cap2) / group_size : (t - n1 - n2) / 6);
 }
 
 }  // namespace qq_shuffle

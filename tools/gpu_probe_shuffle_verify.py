@@ -42,14 +42,27 @@ def main():
         eng.verify_set_transcripts(True)
         eng.verify_set_aggregation(True)
         if n >= 64:      # one tampered proof (an output account): the aggregate fails, the slice is verified in the exact form
-            bad = [a.copy() for a in arrs]
+            bad = [torch.from_numpy(a.copy()).pin_memory().numpy() for a in arrs]
             bad[1][n // 2, 5] ^= 1
-            t = time.perf_counter()
-            st, sg, det = eng.verify_shuffle(*bad)
-            dt = time.perf_counter() - t
+            ts = []
+            for rep in range(3):      # the first repetition grows the workspace (cudaMalloc)
+                t = time.perf_counter()
+                st, sg, det = eng.verify_shuffle(*bad)
+                ts.append(time.perf_counter() - t)
             assert np.nonzero(st)[0].tolist() == [n // 2]
-            print(json.dumps({"probe": "verify_shuffle", "transcripts": "aggregate, one tampered proof (exact fallback)", "proofs": n,
-                              "wall_ms": dt * 1e3}), flush=True)
+            print(json.dumps({"probe": "verify_shuffle", "transcripts": "aggregate, one tampered proof (grouped check + exact form for its group)",
+                              "proofs": n, "wall_ms": min(ts) * 1e3, "first_call_ms": ts[0] * 1e3}), flush=True)
+            if n >= 1024:             # sixteen tampered proofs spread over the batch
+                for k in range(16):
+                    bad[1][(n // 16) * k + 3, 5] ^= 1
+                ts = []
+                for rep in range(2):
+                    t = time.perf_counter()
+                    st, sg, det = eng.verify_shuffle(*bad)
+                    ts.append(time.perf_counter() - t)
+                assert int(np.count_nonzero(st)) == 17
+                print(json.dumps({"probe": "verify_shuffle", "transcripts": "aggregate, 17 tampered proofs", "proofs": n, "wall_ms": min(ts) * 1e3}),
+                      flush=True)
     eng.close()
 
 
