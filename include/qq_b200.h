@@ -371,7 +371,12 @@ int qq_verify_set_transcripts(qq_ctx* ctx, int on_device);
  * random 128-bit weights in the transcript kernels and decided together by ONE Pippenger MSM over the whole batch (146 terms
  * per proof + the six fixed generators).  Proofs that fail a scalar-level check, and the whole batch when the aggregate is
  * not the identity, are verified in the exact form (on == 0: every equation an MSM of its own), which alone reports
- * (status, stage, detail); an invalid proof is accepted with probability <= 2^-128.  Verdicts of valid proofs are identical. */
+ * (status, stage, detail); an invalid proof is accepted with probability <= 2^-128.  Verdicts of valid proofs are identical.
+ * When the aggregate is not the identity, the weighted sums of groups of 64 proofs are evaluated by one grouped MSM
+ * (qq_msm_grouped's machinery) and only the proofs of failing groups go to the exact form.
+ * qq_verify_range_proof_batch follows the same switch: on (default) one weighted MSM over the whole batch, narrowed by grouped
+ * MSMs (64 groups, failing groups cut in eight, ...) when it fails; off: every transcript's own verification MSM (the
+ * reference's per-proof form, 2 n m + 2 + T terms each) as one group of a grouped MSM, 1 024 transcripts per pass. */
 int qq_verify_set_aggregation(qq_ctx* ctx, int on);
 
 /* ---- Bulletproofs range proofs (BASELINE configs[3]) -----------------------------------------------------------------

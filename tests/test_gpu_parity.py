@@ -1652,9 +1652,13 @@ def test_range_proof_device_and_host_transcripts_agree(engine):
             dev = engine.verify_range_proofs(cm, pr, m)
             engine.verify_set_transcripts(False)
             host = engine.verify_range_proofs(cm, pr, m)
+            engine.verify_set_transcripts(True)
+            engine.verify_set_aggregation(False)      # every transcript's own MSM (grouped form), no weighted sum over the batch
+            exact = engine.verify_range_proofs(cm, pr, m)
         finally:
             engine.verify_set_transcripts(True)
-        assert dev.tolist() == host.tolist()
+            engine.verify_set_aggregation(True)
+        assert dev.tolist() == host.tolist() == exact.tolist()
         assert sorted(np.nonzero(dev)[0].tolist()) == hit
 
 

@@ -48,6 +48,15 @@ def main():
                     "values_per_s": n * m / best, "last_call_kernel_ms": eng.last_kernel_ms,
                     "breakdown_ms": eng.last_kernel_breakdown(), "wall_ms_host_transcripts": host_ms, "aggregate_msm_terms": terms,
                     "per_proof_msm_terms_in_the_reference": 2 * 64 * m + 2 * ((64 * m).bit_length() - 1) + m + 6, "all_accepted": True}
+            eng.verify_set_aggregation(False)      # every transcript's own MSM (the reference's per-proof form) through the grouped MSM
+            ts = []
+            for rep in range(3):
+                t = time.perf_counter()
+                st = eng.verify_range_proofs(cm, pr, m)
+                ts.append(time.perf_counter() - t)
+            eng.verify_set_aggregation(True)
+            assert not st.any()
+            line["wall_ms_per_transcript_form"] = min(ts[1:]) * 1e3
             if n >= 3:
                 pr2 = torch.from_numpy(pr.copy()).pin_memory().numpy()
                 pr2[n // 2, 5 * 32 + 1] ^= 1
