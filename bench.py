@@ -590,6 +590,15 @@ def run_b200(args):
         prf_bad = prf.copy()
         prf_bad[per_rank // 2, 3776 - 1] ^= 0x01            # top byte of the DDH response: wrong, perhaps not even canonical
         sh_rej = eng.verify_shuffle(si, so, stm, prf_bad)[0]
+        # one proof with a tampered output account (only the group equations see it): the aggregate fails, grouped MSMs locate the
+        # failing group of 64 proofs, the exact form names the proof
+        so_bad = pinned(so)
+        so_bad[per_rank // 2, 5] ^= 1
+
+        def run_shuffle_bad():
+            res["st_bad"] = eng.verify_shuffle(si, so_bad, stm, prf)[0]
+        sh_bad_ms = best_of(run_shuffle_bad, reps=2)
+        sh_bad_ok = np.nonzero(res["st_bad"])[0].tolist() == [per_rank // 2]
         # strong scaling inside this run: rank 0 alone verifies the WHOLE batch (the other ranks wait), against the sharded time
         sh_n1 = None
         if world > 1:
@@ -611,6 +620,7 @@ def run_b200(args):
         proofs_sec = {"shuffle": {"proofs_per_gpu": per_rank, "ms": sh_ms, "all_accepted": bool(sh_ok),
                                   "ms_two_contexts": sh2_ms, "all_accepted_two_contexts": bool(sh2_ok),
                                   "ms_exact_form": sh_exact_ms, "n1_ms_whole_batch_on_rank0": sh_n1,
+                                  "ms_one_tampered_proof": sh_bad_ms, "one_tampered_proof_isolated": bool(sh_bad_ok),
                                   "tampered_proof_rejected_alone": bool(sh_rej[per_rank // 2] != 0 and int(sh_rej.astype(bool).sum()) == 1),
                                   "msms_per_proof": 32, "terms_per_proof": 239, "exact_msms_per_proof": 4, "aggregated_terms_per_proof": 146,
                                   "api": "qq_verify_shuffle_batch (ShuffleProof::verify, 9 accounts): proof bytes uploaded, Merlin transcripts "
@@ -627,11 +637,15 @@ def run_b200(args):
                 res["st"] = eng.verify_range_proofs(cm, rpf, m_rp)
             rp_ms = best_of(run_range)
             ok_ = not res["st"].any()
-            rej = None
+            rej, rp_bad_ms = None, None
             if count >= 3:
-                rpf_bad = rpf.copy()
+                rpf_bad = pinned(rpf)
                 rpf_bad[count // 2, 5 * 32 + 1] ^= 1
-                r_ = eng.verify_range_proofs(cm, rpf_bad, m_rp)
+
+                def run_range_bad():
+                    res["st_bad"] = eng.verify_range_proofs(cm, rpf_bad, m_rp)
+                rp_bad_ms = best_of(run_range_bad, reps=2)
+                r_ = res["st_bad"]
                 rej = bool(r_[count // 2] == 6 and int(r_.astype(bool).sum()) == 1)
             rp_n1 = None
             if world > 1 and count == per_rank:
@@ -649,9 +663,24 @@ def run_b200(args):
                 barrier()
             rp_list.append({"proofs_per_gpu": count, "values_per_proof": m_rp, "bits": 64, "ms": rp_ms, "all_accepted": bool(ok_),
                             "n1_ms_whole_batch_on_rank0": rp_n1,
-                            "tampered_proof_rejected_alone": rej,
+                            "tampered_proof_rejected_alone": rej, "ms_one_tampered_proof": rp_bad_ms,
                             "aggregated_msm_terms": 2 * 64 * m_rp + 2 + count * (4 + 20 + m_rp),
                             "reference_msm_points": count * (2 * 64 * m_rp + 20 + m_rp + 6)})
+        # sigma verifier (Verifier::verify_update_account_verifier): per_rank DLOG proofs over 9 accounts each, random valid points
+        # (every proof is rejected by its challenge; the work is that of valid proofs)
+        srng = np.random.default_rng(4 + rank)
+        sitems = per_rank * 9
+        s_ia = np.concatenate([eng.fixed_base(0, rand_scalars(srng, sitems))[0] for _ in range(4)], axis=1).copy()
+        s_da = np.concatenate([eng.fixed_base(0, rand_scalars(srng, sitems))[0] for _ in range(4)], axis=1).copy()
+        s_ia, s_da, s_z, s_x = pinned(s_ia), pinned(s_da), pinned(rand_scalars(srng, sitems)), pinned(rand_scalars(srng, per_rank))
+
+        def run_sigma():
+            res["sg"] = eng.verify_update_account_dlog(s_ia, s_da, s_z, s_x, 9)
+        sg_ms = best_of(run_sigma)
+        proofs_sec["sigma_dlog"] = {"proofs_per_gpu": per_rank, "accounts_per_proof": 9, "ms": sg_ms, "msms": 2 * sitems,
+                                    "all_rejected_by_challenge": bool((res["sg"] == 6).all()),
+                                    "api": "qq_verify_update_account_dlog_batch (Verifier::verify_update_account_verifier): accounts, responses "
+                                           "and challenges uploaded, 3-term MSMs + Merlin transcripts on the device, one status byte per proof back"}
         proofs_sec["range_proofs"] = {"batches": rp_list,
                                       "api": "qq_verify_range_proof_batch (RangeProof::verify_multiple; the reference verifies "
                                              "each proof with its own 2090-term MSM, verifier.rs:517)"}
