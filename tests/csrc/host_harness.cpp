@@ -11,6 +11,7 @@
 #include "../../quisquis-rust_b200/csrc/keccak_host.hpp"
 #include "../../quisquis-rust_b200/csrc/merlin_host.hpp"
 #include "../../quisquis-rust_b200/csrc/shuffle_verify.cuh"
+#include "../../tools/fe64/fe64.cuh"
 
 using namespace qq;
 
@@ -469,5 +470,61 @@ int hh_transcript_state_roundtrip(const uint8_t* label, size_t label_len, uint8_
     memset(bad, 0, sizeof bad);
     if (b.import_state(bad)) return 0;
     return 1;
+}
+
+// ---- FP64-pipe field / group arithmetic (fe64.cuh) ---------------------------------------------------------------------
+// raw limbs: x_i = q_i * 2^o_i (signed integers q_i chosen by the test, so worst-case magnitudes can be driven);
+// op 0: a * b, 1: a^2, 2: 2 a^2.  The result comes back in the saturated integer form.
+void hh_fe64_op_raw(u32* out, const long long* qa, const long long* qb, int op) {
+    fe64 a, b, h;
+    for (int i = 0; i < QQ_F64_LIMBS; i++) {
+        a.v[i] = (double)qa[i] * f64_p2(f64_off(i));
+        b.v[i] = (double)qb[i] * f64_p2(f64_off(i));
+    }
+    if (op == 0) fe64_mul(h, a, b);
+    else if (op == 1) fe64_sq<false>(h, a);
+    else fe64_sq<true>(h, a);
+    // the product must come out carried: |x_i| <= 2^(o_(i+1) - 1) (+ the tiny second-lap excess on limb 2)
+    for (int i = 0; i < QQ_F64_LIMBS; i++) {
+        double lim = f64_p2(f64_off(i + 1) - 1) * (i == 2 ? 1.001 : 1.0);
+        if (!(h.v[i] <= lim && h.v[i] >= -lim)) { memset(out, 0xff, 32); return; }
+    }
+    fe r;
+    fe64_to_fe(r, h);
+    memcpy(out, r.v, 32);
+}
+// saturated form -> fe64 -> (sum of `terms` copies, alternating nothing) -> saturated form
+void hh_fe64_roundtrip(u32* out, const u32* in, int terms) {
+    fe f, r;
+    memcpy(f.v, in, 32);
+    fe64 x, acc;
+    fe64_from_fe(x, f);
+    acc = x;
+    for (int i = 1; i < terms; i++) fe64_add(acc, acc, x);
+    fe64_to_fe(r, acc);
+    memcpy(out, r.v, 32);
+}
+int hh_scalarmult_split64(uint8_t* out0, uint8_t* out1, const uint8_t* s0, const uint8_t* s1, const uint8_t* point) {
+    u32 w[8], s[8];
+    ge_p3 p, r;
+    load_words(w, point);
+    int ok = (int)ristretto_decompress(p, w);
+    std::vector<double> tbl(QQ_VBS64_TABLE_D);
+    ge64_p3 p64, r64;
+    fe64 d2;
+    fe64_from_fe(d2, fe_2d());
+    ge64_from_p3(p64, p);
+    vbs64_build_tables(tbl.data(), p64, d2);
+    load_words(s, s0);
+    vbs64_scalarmult(r64, tbl.data(), s);
+    ge64_to_p3(r, r64);
+    ristretto_compress(w, r);
+    store_words(out0, w);
+    load_words(s, s1);
+    vbs64_scalarmult(r64, tbl.data(), s);
+    ge64_to_p3(r, r64);
+    ristretto_compress(w, r);
+    store_words(out1, w);
+    return ok;
 }
 }

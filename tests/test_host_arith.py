@@ -394,3 +394,75 @@ def test_shuffle_phases_shared_with_the_transcript_kernels(hh):
     assert h.hh_transcript_state_bytes() == 208
     assert h.hh_transcript_state_roundtrip(b"abc", 3, state) == 1
     assert state.raw[203] == 0xa5
+
+
+# ---- FP64-pipe arithmetic (csrc/fe64.cuh): exact by construction; checked here against big integers ------------------
+F64_OFF = [(85 * i + 3) // 4 for i in range(13)]
+Q12 = ctypes.c_longlong * 12
+
+
+def test_fe64_column_bound_interval_arithmetic():
+    # the claim in the header of fe64.cuh: a column of products of operands with ta and tb carried terms stays below
+    # 2^(o_k + 53) whenever ta * tb <= 16 (the group law uses at most 3 x 3 = 9, 12 with the doubled squaring)
+    assert F64_OFF == [0, 22, 43, 64, 85, 107, 128, 149, 170, 192, 213, 234, 255]
+    from fractions import Fraction
+    N = [Fraction(2) ** (F64_OFF[i + 1] - 1) for i in range(12)]
+    N[2] = N[2] * (1 + Fraction(1, 2**19))           # second-lap excess of the carry
+    for k in range(12):
+        tot = Fraction(0)
+        for i in range(12):
+            j = k - i
+            tot += N[i] * N[j] if j >= 0 else N[i] * N[j + 12] * 19 / Fraction(2) ** 255
+        assert 16 * tot < Fraction(2) ** (F64_OFF[k] + 53), k
+        for i in range(12):                            # every product is a multiple of the column's unit
+            j = k - i
+            assert F64_OFF[i] + F64_OFF[j if j >= 0 else j + 12] - (0 if j >= 0 else 255) >= F64_OFF[k]
+
+
+def test_fe64_products_and_conversions(hh):
+    rnd = random.Random(64)
+    out = A8()
+    for x in EDGES + [rand_fe(rnd) for _ in range(300)]:
+        for terms in (1, 2, 5, 12):
+            hh.hh_fe64_roundtrip(out, limbs(x), terms)
+            assert val(out) % R.P == terms * x % R.P and val(out) < 2**256
+
+    def raw_val(q):
+        return sum(int(q[i]) << F64_OFF[i] for i in range(12))
+
+    def carried(scale):
+        # signed limbs with |q_i| <= scale * 2^(s_i - 1), biased towards the extremes
+        q = []
+        for i in range(12):
+            m = scale << (F64_OFF[i + 1] - F64_OFF[i] - 1)
+            r = rnd.random()
+            q.append(m if r < 0.2 else -m if r < 0.4 else rnd.randint(-m, m))
+        return q
+    for ta, tb in [(1, 1), (2, 2), (3, 3), (4, 4), (4, 3), (2, 8), (16, 1), (1, 16)]:
+        for _ in range(60):
+            qa, qb = carried(ta), carried(tb)
+            if rnd.random() < 0.15:
+                qa = [s * (ta << (F64_OFF[i + 1] - F64_OFF[i] - 1)) for i, s in enumerate([rnd.choice([1, -1])] * 12)]
+                qb = [s * (tb << (F64_OFF[i + 1] - F64_OFF[i] - 1)) for i, s in enumerate([rnd.choice([1, -1])] * 12)]
+            hh.hh_fe64_op_raw(out, Q12(*qa), Q12(*qb), 0)
+            assert val(out) != 2**256 - 1 and val(out) % R.P == raw_val(qa) * raw_val(qb) % R.P, (ta, tb)
+            if ta * ta <= 16:
+                hh.hh_fe64_op_raw(out, Q12(*qa), Q12(*qb), 1)
+                assert val(out) % R.P == raw_val(qa) ** 2 % R.P
+            if 2 * ta * ta <= 16:
+                hh.hh_fe64_op_raw(out, Q12(*qa), Q12(*qb), 2)
+                assert val(out) % R.P == 2 * raw_val(qa) ** 2 % R.P
+
+
+def test_fe64_split_variable_base(hh):
+    # the FP64 warps' scalar multiplication (vbs64_*) gives the encodings of the integer path
+    rnd = random.Random(65)
+    edge = [0, 1, 2, R.L - 1, 8, R.L - 8, 2**64, 2**64 - 1, 2**128 + 2**64, 2**192 - 1, 2**252, 8 * (16**64 - 1) // 15 % R.L]
+    for i in range(30):
+        s0 = edge[i] if i < len(edge) else rnd.randrange(R.L)
+        s1 = edge[-1 - i] if i < len(edge) else rnd.randrange(R.L)
+        p = bytes(32) if i == 3 else R.compress(R.mul(rnd.randrange(R.L), R.BASEPOINT))
+        o0, o1 = ctypes.create_string_buffer(32), ctypes.create_string_buffer(32)
+        assert hh.hh_scalarmult_split64(o0, o1, s0.to_bytes(32, "little"), s1.to_bytes(32, "little"), p) == 1
+        assert o0.raw == R.compress(R.mul(s0, R.decompress(p)))
+        assert o1.raw == R.compress(R.mul(s1, R.decompress(p)))
