@@ -224,6 +224,13 @@ size_t qq_msm_points_shifted_bytes(const qq_prepared* p);
 int qq_msm_set_overlap(qq_ctx* ctx, long split_min, int tail_pct, int sort_blocks_per_sm);
 /* sum of k extended points given as k x 128 B (X,Y,Z,T canonical) -> compressed; *is_identity set to 1/0 */
 int qq_points_sum(qq_ctx* ctx, const uint8_t* xyzt, size_t k, uint8_t* out_point, uint8_t* is_identity);
+/* Parity hook for the warp-cooperative group operations (csrc/ge_warp.cuh: one point per warp, one 32-bit limb per lane; used
+ * by the window Horner chain of the large MSM): item j = two extended points as 4 x 8 little-endian 32-bit limbs each (ANY
+ * limb values, i.e. field elements in the saturated form, not necessarily points of the curve - the formulas are polynomial);
+ * out_dbl[j] = the doubling formula applied to p[j], out_add[j] = the addition formula applied to p[j], q[j], as 128 B of
+ * limbs (values mod p).  Follows the same formulas as curve25519-dalek's curve_models (ProjectivePoint::double,
+ * EdwardsPoint + ProjectiveNielsPoint), which the reference reaches through every point operation (src/ristretto/keys.rs:277-281). */
+int qq_warp_ops_selftest(qq_ctx* ctx, const uint8_t* p_xyzt, const uint8_t* q_xyzt, size_t n, uint8_t* out_dbl, uint8_t* out_add);
 /* many small MSMs (2..9 terms each in the reference, src/accounts/verifier.rs:165-880, src/shuffle/*):
  * instance j covers terms offsets[j] .. offsets[j+1]-1 ; out m x 32 B ; status m */
 int qq_msm_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* points, const uint32_t* offsets, size_t m,

@@ -33,7 +33,7 @@ EXPORTS = [
     "qq_msm_set_shifted", "qq_msm_points_shifted_bytes", "qq_set_secret_mode", "qq_secret_mode", "qq_sigma_commit_batch", "qq_sigma_commit_batch_dev",
     "qq_init_multi", "qq_destroy_multi", "qq_multi_device_count", "qq_multi_ctx", "qq_multi_last_error",
     "qq_multi_update_account_batch", "qq_multi_generate_commitment_batch", "qq_multi_verify_shuffle_batch",
-    "qq_multi_verify_range_proof_batch", "qq_multi_msm", "qq_multi_msm_dev", "qq_points_sum_dev",
+    "qq_multi_verify_range_proof_batch", "qq_multi_msm", "qq_multi_msm_dev", "qq_points_sum_dev", "qq_warp_ops_selftest",
 ]
 
 
@@ -98,6 +98,7 @@ def load_library():
     for name in ("qq_msm", "qq_msm_dev", "qq_msm_partial", "qq_msm_partial_dev"):
         getattr(lib, name).argtypes = [vp, u8p, u8p, sz, u8p, u8p]
     lib.qq_points_sum.argtypes = [vp, u8p, sz, u8p, u8p]
+    lib.qq_warp_ops_selftest.argtypes = [vp, u8p, u8p, sz, u8p, u8p]
     for name in ("qq_msm_points_prepare", "qq_msm_points_prepare_dev"):
         getattr(lib, name).argtypes = [vp, u8p, sz, ctypes.POINTER(vp)]
     lib.qq_verify_update_account_dlog_batch.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, u8p, u8p, u8p, u8p, sz, sz, u8p]
@@ -772,6 +773,16 @@ class Engine:
         out, ident = np.zeros(32, np.uint8), np.zeros(1, np.uint8)
         self._ck(self.lib.qq_points_sum(self.h, _ptr(xyzt), k, _ptr(out), _ptr(ident)), "qq_points_sum")
         return out, bool(ident[0])
+
+    def warp_ops_selftest(self, p_limbs, q_limbs):
+        """parity hook of the warp-cooperative group operations: (doubling formula of p, addition formula of p and q), raw limbs"""
+        p_limbs, q_limbs = _u8(p_limbs), _u8(q_limbs)
+        n = p_limbs.size // 128
+        if q_limbs.size != p_limbs.size or p_limbs.size % 128:
+            raise ValueError("p and q must hold the same number of 128-byte points")
+        d, a = np.zeros(n * 128, np.uint8), np.zeros(n * 128, np.uint8)
+        self._ck(self.lib.qq_warp_ops_selftest(self.h, _ptr(p_limbs), _ptr(q_limbs), n, _ptr(d), _ptr(a)), "qq_warp_ops_selftest")
+        return d.reshape(n, 128), a.reshape(n, 128)
 
     def points_sum_dev(self, records_ptr, k, stride=144):
         """sum of k partial MSM results resident in device memory (records of `stride` bytes) -> (compressed, identity?, status)"""

@@ -18,6 +18,7 @@
 #pragma once
 #include "kernels.cuh"
 #include "ge_coop.cuh"
+#include "ge_warp.cuh"
 
 namespace qq {
 
@@ -590,6 +591,33 @@ __global__ void __launch_bounds__(32) k_msm_horner(const u32x4* __restrict__ win
         acc = coop_add(acc, coop_to_cached(p, r), r);
     }
     if (threadIdx.x < 4) coop_store(result, r, acc);
+}
+
+// The same chain with one limb per lane (ge_warp.cuh): a doubling is two rounds of 8 products per lane and two carry
+// normalisations instead of two 72-product carry chains per lane.
+__global__ void __launch_bounds__(32) k_msm_horner_warp(const u32x4* __restrict__ win, msm_geom g, u32x4* __restrict__ result) {
+    const int q = (threadIdx.x >> 3) & 3, k = threadIdx.x & 7;
+    win += QQ_PT_Q * (size_t)blockIdx.x * g.K;
+    result += QQ_PT_Q * (size_t)blockIdx.x;
+    u32 acc = warp_point_load(win + QQ_PT_Q * (size_t)(g.K - 1));
+    for (int w = g.K - 2; w >= 0; w--) {
+        u32 p = warp_point_load(win + QQ_PT_Q * (size_t)w);      // issued ahead of the doublings
+        u32 pc = warp_to_cached(p, q, k);
+#pragma unroll 1
+        for (int i = 0; i < g.c; i++) acc = warp_dbl(acc, q, k);
+        acc = warp_add(acc, pc, q, k);
+    }
+    warp_point_store(result, acc);
+}
+// parity hook for the warp-cooperative operations (qq_warp_ops_selftest): warp j computes 2 P_j and P_j + Q_j
+__global__ void __launch_bounds__(128) k_warp_selftest(const u32x4* __restrict__ P, const u32x4* __restrict__ Q, size_t n,
+                                                       u32x4* __restrict__ dbl_out, u32x4* __restrict__ add_out) {
+    const int q = (threadIdx.x >> 3) & 3, k = threadIdx.x & 7;
+    size_t j = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (j >= n) return;      // whole warps
+    u32 p = warp_point_load(P + QQ_PT_Q * j), qq_ = warp_point_load(Q + QQ_PT_Q * j);
+    warp_point_store(dbl_out + QQ_PT_Q * j, warp_dbl(p, q, k));
+    warp_point_store(add_out + QQ_PT_Q * j, warp_add(p, warp_to_cached(qq_, q, k), q, k));
 }
 
 // ---- grouped form: G independent MSMs in one pass ---------------------------------------------------------------------------

@@ -130,6 +130,7 @@ struct qq_ctx {
     // 3.29 / 2.35 - beyond L2 the 16 x larger gather footprint costs more than the reductions and the Horner chain save.
     size_t msm_shift_budget = (size_t)112 << 20;
     bool msm_use_shifted = true;
+    bool msm_horner_warp = true;     // window Horner with one limb per lane (ge_warp.cuh); false: the four-lane form (A/B knob)
     bool secret_mode = false;                  // qq_set_secret_mode: constant-time table access for scalars that are secrets
     int vb_blocks_per_sm_secret[3] = {0, 0, 0};
     bool verify_aggregate = true;              // qq_verify_set_aggregation: identity equations of the shuffle proofs in one weighted Pippenger MSM
@@ -579,6 +580,7 @@ extern "C" int qq_init(qq_ctx** out, int device) {
             if (const char* e = getenv("QQ_MSM_TAIL_PCT")) ctx->msm_tail_pct = atoi(e);
             if (const char* e = getenv("QQ_MSM_SORT_BPSM")) ctx->msm_sort_bpsm = atoi(e);
             if (const char* e = getenv("QQ_MSM_SHIFT_BUDGET_MB")) ctx->msm_shift_budget = (size_t)atol(e) << 20;
+            if (const char* e = getenv("QQ_MSM_HORNER_WARP")) ctx->msm_horner_warp = atoi(e) != 0;
             if (const char* e = getenv("QQ_VERIFY_HOST_TRANSCRIPTS")) ctx->verify_host_transcripts = atoi(e) != 0;
             if (const char* e = getenv("QQ_VERIFY_AGGREGATE")) ctx->verify_aggregate = atoi(e) != 0;
         }

@@ -78,6 +78,7 @@ extern "C" {
     pub fn qq_multi_msm(m: *mut QqMulti, scalars: *const u8, points: *const u8, n: usize, out_point: *mut u8, status: *mut u8) -> c_int;
     pub fn qq_multi_verify_shuffle_batch(m: *mut QqMulti, transcript_label: *const c_char, verifier_label: *const c_char, shuffle_input: *const u8, shuffle_output: *const u8, statement: *const u8, proof: *const u8, nproofs: usize, status: *mut u8, stage: *mut u8, detail: *mut u8) -> c_int;
     pub fn qq_points_sum_dev(ctx: *mut QqCtx, records: *const u8, k: usize, stride: usize, out_point: *mut u8, is_identity: *mut u8, status: *mut u8) -> c_int;
+    pub fn qq_warp_ops_selftest(ctx: *mut QqCtx, p_xyzt: *const u8, q_xyzt: *const u8, n: usize, out_dbl: *mut u8, out_add: *mut u8) -> c_int;
     pub fn qq_msm_set_shifted(ctx: *mut QqCtx, budget_bytes: usize, use_it: c_int) -> c_int;
     pub fn qq_transcript_state_bytes() -> usize;
     pub fn qq_verify_set_transcripts(ctx: *mut QqCtx, on_device: c_int) -> c_int;

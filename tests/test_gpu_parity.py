@@ -1843,3 +1843,90 @@ def test_multi_engine_verifiers_equal_single_engine(pkg, engine):
         assert r1[1] == r2[1] == 0 and r1[0].tobytes() == r2[0].tobytes()
     finally:
         me.close()
+
+
+@pytest.mark.gpu
+def test_warp_cooperative_group_operations(engine):
+    """csrc/ge_warp.cuh (one point per warp, one 32-bit limb per lane; the window Horner chain of the large MSM): the doubling
+    and the addition formula on 4 x 8 raw limbs against the same formulas over big integers - field elements in the saturated
+    form over their whole range, biased to the corners of the carry logic (all-ones limbs that must propagate a carry through
+    the ballot pass, values next to 2^255, 2^256, p, 2p, zero limbs)."""
+    import random
+    rnd = random.Random(77)
+    P, D2 = R.P, 2 * R.D % R.P
+    edges = [0, 1, 2, 18, 19, 37, 38, P - 1, P, P + 1, 2 * P - 1, 2 * P, 2 * P + 1, 2**256 - 1, 2**256 - 2, 2**256 - 38, 2**255,
+             2**255 - 1, 2**255 - 19, 2**128, 2**128 - 1, (2**128 - 1) << 128, 2**224, 2**32 - 1, (2**32 - 1) << 224,
+             2**256 - 2**32, 2**256 - 2**224, (2**224 - 1) << 32, 2**255 + 2**247 - 1]
+
+    def fe():
+        r = rnd.random()
+        if r < 0.3:
+            return rnd.choice(edges)
+        if r < 0.45:
+            return (2**256 - 1) ^ rnd.getrandbits(rnd.choice([5, 20, 33, 70]))
+        if r < 0.55:
+            return rnd.getrandbits(rnd.choice([6, 40, 130]))
+        if r < 0.7:
+            return sum((0xFFFFFFFF if rnd.random() < 0.6 else rnd.choice([0, 1, 0xFFFFFFFE, 0x80000000])) << (32 * i) for i in range(8))
+        return rnd.getrandbits(256)
+
+    n = 3000
+    pts = [[fe() for _ in range(4)] for _ in range(n)]
+    qts = [[fe() for _ in range(4)] for _ in range(n)]
+    # a run of true curve points as well (the chain the Horner kernel really sees)
+    for j in range(40):
+        for arr in (pts, qts):
+            x, y, z, t = R.mul(rnd.randrange(1, R.L), R.BASEPOINT)
+            lam = rnd.randrange(1, P)
+            arr[j] = [x * lam % P, y * lam % P, z * lam % P, t * lam % P]
+    raw = lambda arr: np.frombuffer(b"".join(v.to_bytes(32, "little") for p in arr for v in p), np.uint8)
+    d, a = engine.warp_ops_selftest(raw(pts), raw(qts))
+    val = lambda row, c: int.from_bytes(row[32 * c:32 * c + 32].tobytes(), "little")
+    for j in range(n):
+        X, Y, Z, T = pts[j]
+        X2, Y2, Z2, T2 = qts[j]
+        xx, yy, zz = X * X, Y * Y, Z * Z
+        cx, cy, cz = 2 * X * Y, yy + xx, yy - xx
+        ct = 2 * zz - cz
+        exp_d = [cx * ct, cy * cz, cz * ct, cx * cy]
+        A, B, C, Dd = (Y - X) * (Y2 - X2), (Y + X) * (Y2 + X2), T * D2 * T2, Z * 2 * Z2
+        E, F, G, H = B - A, Dd - C, Dd + C, B + A
+        exp_a = [E * F, G * H, F * G, E * H]
+        for c in range(4):
+            assert val(d[j], c) % P == exp_d[c] % P, (j, c, "dbl")
+            assert val(a[j], c) % P == exp_a[c] % P, (j, c, "add")
+            assert val(d[j], c) < 2**255 + 2**247 and val(a[j], c) < 2**255 + 2**247
+    # the 40 curve points: the results are the group elements the oracle computes
+    for j in range(40):
+        got = tuple(val(d[j], c) % P for c in range(4))
+        assert R.compress(got) == R.compress(R.add(tuple(pts[j]), tuple(pts[j])))
+        got = tuple(val(a[j], c) % P for c in range(4))
+        assert R.compress(got) == R.compress(R.add(tuple(pts[j]), tuple(qts[j])))
+
+
+@pytest.mark.gpu
+def test_msm_horner_forms_agree(pkg):
+    """QQ_MSM_HORNER_WARP=0 (four-lane Horner chain) and the default (one limb per lane) give the same bytes, small and large sets."""
+    import os
+    rng = np.random.default_rng(5)
+    outs = []
+    for knob in ("0", "1"):
+        os.environ["QQ_MSM_HORNER_WARP"] = knob
+        try:
+            e = pkg.Engine(0)
+        finally:
+            del os.environ["QQ_MSM_HORNER_WARP"]
+        res = []
+        for n in (300, 5000, 70000):
+            r2 = np.random.default_rng(n)
+            hs = r2.integers(0, 256, size=(n, 32), dtype=np.uint8)
+            a = r2.integers(0, 256, size=(n, 32), dtype=np.uint8)
+            hs[:, 31] &= 0x0f
+            a[:, 31] &= 0x0f
+            pts, st = e.fixed_base(0, hs)
+            out, s = e.msm(a, pts)
+            assert s == 0
+            res.append(out.tobytes())
+        outs.append(res)
+        e.close()
+    assert outs[0] == outs[1]
