@@ -318,6 +318,66 @@ __global__ void __launch_bounds__(256) k_msm_order_scatter(const unsigned int* _
     }
 }
 
+// ---- pipelined tail: the windows are cut into `ng` ranks (rank 0 = the top windows) whose buckets are accumulated by separate
+// launches, so that the depth-bound reduction / Horner chain of one rank runs (on the high-priority stream) under the
+// accumulation of the next.  Virtual buckets are laid out in bucket order, so a rank is a contiguous range of them:
+// vb[0] = virtual buckets in use, vb[r] (1 <= r < ng) = end of rank r's range = first virtual bucket of window kw[r].
+struct msm_ranks {
+    int ng;
+    unsigned int W;          // ordering bins per rank (ng * W == QQ_ORDER_BINS)
+    int kw[5];               // rank r covers windows [kw[r + 1], kw[r]); kw[0] = K, kw[ng] = 0
+};
+__global__ void k_msm_rank_bounds(const unsigned int* __restrict__ voff, const unsigned int* __restrict__ nsub, size_t total, int NB,
+                                  msm_ranks rk, unsigned int* __restrict__ vb) {
+    int r = threadIdx.x;
+    if (r == 0) vb[0] = voff[total - 1] + nsub[total - 1];
+    else if (r < rk.ng) vb[r] = voff[(size_t)rk.kw[r] * NB];
+}
+__device__ __forceinline__ unsigned int order_key_g(unsigned int c, unsigned int v, const unsigned int* vb, const msm_ranks& rk) {
+    unsigned int r = 0;
+    for (int i = 1; i < rk.ng; i++) r = v < vb[i] ? (unsigned int)i : r;
+    return r * rk.W + (rk.W - 1 - (c < rk.W - 1 ? c : rk.W - 1));
+}
+__global__ void __launch_bounds__(256) k_msm_order_hist_g(const unsigned int* __restrict__ counts, const unsigned int* __restrict__ vb,
+                                                          msm_ranks rk, unsigned int* __restrict__ hist) {
+    __shared__ unsigned int sh[QQ_ORDER_BINS];
+    for (int i = threadIdx.x; i < QQ_ORDER_BINS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const size_t total = vb[0];
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < total; b += stride)
+        atomicAdd(&sh[order_key_g(counts[b], (unsigned int)b, vb, rk)], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < QQ_ORDER_BINS; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+__global__ void __launch_bounds__(256) k_msm_order_scatter_g(const unsigned int* __restrict__ counts, const unsigned int* __restrict__ vb,
+                                                             msm_ranks rk, const unsigned int* __restrict__ hist_off,
+                                                             unsigned int* __restrict__ cursor, unsigned int* __restrict__ order) {
+    __shared__ unsigned int sh_cnt[QQ_ORDER_BINS];
+    __shared__ unsigned int sh_base[QQ_ORDER_BINS];
+    const size_t total = vb[0];
+    for (size_t tile = (size_t)blockIdx.x * QQ_ORDER_TILE; tile < total; tile += (size_t)gridDim.x * QQ_ORDER_TILE) {
+        for (int i = threadIdx.x; i < QQ_ORDER_BINS; i += blockDim.x) sh_cnt[i] = 0;
+        __syncthreads();
+        size_t end = tile + QQ_ORDER_TILE < total ? tile + QQ_ORDER_TILE : total;
+        for (size_t b = tile + threadIdx.x; b < end; b += blockDim.x) atomicAdd(&sh_cnt[order_key_g(counts[b], (unsigned int)b, vb, rk)], 1u);
+        __syncthreads();
+        for (int i = threadIdx.x; i < QQ_ORDER_BINS; i += blockDim.x) {
+            unsigned int c = sh_cnt[i];
+            if (c) sh_base[i] = hist_off[i] + atomicAdd(&cursor[i], c);
+            sh_cnt[i] = 0;
+        }
+        __syncthreads();
+        for (size_t b = tile + threadIdx.x; b < end; b += blockDim.x) {
+            unsigned int key = order_key_g(counts[b], (unsigned int)b, vb, rk);
+            unsigned int r = atomicAdd(&sh_cnt[key], 1u);
+            order[sh_base[key] + r] = (unsigned int)b;
+        }
+        __syncthreads();
+    }
+}
+
 // ---- virtual buckets ---------------------------------------------------------------------------------------------------
 // A bucket with more than `cap` entries is cut into ceil(cnt / cap) virtual buckets, each summed by its own thread, so
 // that skewed digit distributions (the short top window: scalars < 2^253 leave it only 2^(253 - c (K-1)) distinct
@@ -376,15 +436,9 @@ __global__ void __launch_bounds__(256) k_msm_shift_build(const u32x4* __restrict
 
 // ---- bucket accumulation: thread t sums the entries of virtual bucket order[t] ----------------------------------------
 // The gather of entry e + 1 (index, then 96 B Niels point) is issued before the mixed addition of entry e.
-__global__ void __launch_bounds__(128) k_msm_accumulate(const u32x4* __restrict__ niels,
-                                                        const unsigned int* __restrict__ sorted,
-                                                        const unsigned int* __restrict__ vstart,
-                                                        const unsigned int* __restrict__ vcnt,
-                                                        const unsigned int* __restrict__ order, size_t vmax,
-                                                        u32x4* __restrict__ partial) {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= vmax) return;
-    unsigned int v = order[t];
+__device__ __forceinline__ void msm_accumulate_one(const u32x4* __restrict__ niels, const unsigned int* __restrict__ sorted,
+                                                   const unsigned int* __restrict__ vstart, const unsigned int* __restrict__ vcnt,
+                                                   unsigned int v, u32x4* __restrict__ partial) {
     unsigned int cnt = vcnt[v];
     if (cnt == 0) return;
     const unsigned int* ent = sorted + vstart[v];
@@ -415,6 +469,28 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(const u32x4* __restrict_
     }
     ge_p3_store(partial + QQ_PT_Q * (size_t)v, acc);
 }
+__global__ void __launch_bounds__(128) k_msm_accumulate(const u32x4* __restrict__ niels,
+                                                        const unsigned int* __restrict__ sorted,
+                                                        const unsigned int* __restrict__ vstart,
+                                                        const unsigned int* __restrict__ vcnt,
+                                                        const unsigned int* __restrict__ order, size_t vmax,
+                                                        u32x4* __restrict__ partial) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= vmax) return;
+    msm_accumulate_one(niels, sorted, vstart, vcnt, order[t], partial);
+}
+// one rank of the pipelined form: entries [*lo, *hi) of `order` (bounds known on the device only; hi == nullptr: *lo + count)
+__global__ void __launch_bounds__(128) k_msm_accumulate_rank(const u32x4* __restrict__ niels,
+                                                             const unsigned int* __restrict__ sorted,
+                                                             const unsigned int* __restrict__ vstart,
+                                                             const unsigned int* __restrict__ vcnt,
+                                                             const unsigned int* __restrict__ order,
+                                                             const unsigned int* __restrict__ lo, const unsigned int* __restrict__ hi,
+                                                             u32x4* __restrict__ partial) {
+    size_t t = (size_t)*lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)*hi) return;
+    msm_accumulate_one(niels, sorted, vstart, vcnt, order[t], partial);
+}
 
 // Buckets that were cut into several virtual buckets: one warp per such bucket sums its partial sums (lanes stride over
 // the parts, then a shared-memory tree) into the first part, so that the reduction reads exactly one point per bucket.
@@ -422,13 +498,14 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(const u32x4* __restrict_
 __global__ void __launch_bounds__(128) k_msm_combine(u32x4* __restrict__ partial, const unsigned int* __restrict__ voff,
                                                      const unsigned int* __restrict__ nsub,
                                                      const unsigned int* __restrict__ multi,
-                                                     const unsigned int* __restrict__ nmulti) {
+                                                     const unsigned int* __restrict__ nmulti, unsigned int b_lo, unsigned int b_hi) {
     __shared__ u32x4 sm[128 * QQ_PT_Q];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     u32x4* my = sm + QQ_PT_Q * (size_t)(wib * 32);
     unsigned int cnt = *nmulti;
     for (unsigned int w = blockIdx.x * 4 + wib; w < cnt; w += gridDim.x * 4) {
         unsigned int b = multi[w];
+        if (b < b_lo || b >= b_hi) continue;      // warp-uniform: another rank's bucket
         unsigned int v0 = voff[b], np = nsub[b];
         ge_p3 acc;
         ge_identity(acc);
@@ -478,7 +555,7 @@ __device__ __forceinline__ void coop_runsum_step(fe& run, fe& w, const fe& a, bo
 // level 0: element (k, j) = bucket k * NB + j; after k_msm_combine its sum is the first of its partial sums
 __global__ void __launch_bounds__(128) k_msm_reduce0(const u32x4* __restrict__ partial, const unsigned int* __restrict__ voff,
                                                      const unsigned int* __restrict__ nsub, msm_geom g, int mout,
-                                                     u32x4* __restrict__ run_out, u32x4* __restrict__ w_out) {
+                                                     u32x4* __restrict__ run_out, u32x4* __restrict__ w_out, int k0) {
     int gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 2, r = threadIdx.x & 3;
     bool act = gid < g.K * mout;
     int t = act ? gid : 0;
@@ -489,7 +566,7 @@ __global__ void __launch_bounds__(128) k_msm_reduce0(const u32x4* __restrict__ p
         int j = s * QQ_MSM_RSEG + i;
         fe a = coop_identity(r);
         if (j < g.NB) {
-            size_t b = (size_t)k * g.NB + j;
+            size_t b = (size_t)(k0 + k) * g.NB + j;       // g.K = windows of this launch, k0 = its first window
             if (nsub[b] != 0) a = coop_load(partial + QQ_PT_Q * (size_t)voff[b], r);
         }
         coop_runsum_step<true>(run, w, a, i > 0, r);
@@ -530,9 +607,9 @@ struct msm_levels {
     unsigned int off[QQ_MSM_MAXLEVELS];
 };
 __global__ void __launch_bounds__(512) k_msm_sum_levels(const u32x4* __restrict__ w_all, msm_levels lv, int K, int l_first,
-                                                        u32x4* __restrict__ sw) {
+                                                        u32x4* __restrict__ sw, int Kg, int k0) {
     extern __shared__ __align__(16) u32x4 sm[];   // blockDim.x points
-    int l = l_first + blockIdx.x / K, k = blockIdx.x % K;
+    int l = l_first + blockIdx.x / Kg, k = k0 + blockIdx.x % Kg;      // windows [k0, k0 + Kg) of K
     int row_len = lv.len[l];
     const u32x4* row = w_all + QQ_PT_Q * ((size_t)lv.off[l] + (size_t)k * row_len);
     ge_p3 acc;
@@ -561,10 +638,10 @@ __global__ void __launch_bounds__(512) k_msm_sum_levels(const u32x4* __restrict_
 }
 // wins[k] = R_k + sum_l S^l SW_l[k]   (Horner over the levels: log2(S) doublings + one addition per level)
 __global__ void __launch_bounds__(128) k_msm_window_totals(const u32x4* __restrict__ sw, const u32x4* __restrict__ run_top,
-                                                           msm_levels lv, int K, u32x4* __restrict__ wins) {
+                                                           msm_levels lv, int K, u32x4* __restrict__ wins, int Kg, int k0) {
     int gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 2, r = threadIdx.x & 3;
-    bool act = gid < K;
-    int k = act ? gid : 0;
+    bool act = gid < Kg;
+    int k = k0 + (act ? gid : 0);
     fe t = coop_load(sw + QQ_PT_Q * ((size_t)(lv.L - 1) * K + k), r);
     for (int l = lv.L - 2; l >= 0; l--) {
         t = coop_dbl(t, r);
@@ -605,6 +682,24 @@ __global__ void __launch_bounds__(32) k_msm_horner_warp(const u32x4* __restrict_
         u32 pc = warp_to_cached(p, q, k);
 #pragma unroll 1
         for (int i = 0; i < g.c; i++) acc = warp_dbl(acc, q, k);
+        acc = warp_add(acc, pc, q, k);
+    }
+    warp_point_store(result, acc);
+}
+// A segment of the chain for the pipelined tail: windows k_hi - 1 .. k_lo; first: start from win[k_hi - 1], else continue from
+// the value in `result` (the ranks above).
+__global__ void __launch_bounds__(32) k_msm_horner_warp_seg(const u32x4* __restrict__ win, int c, int k_hi, int k_lo, int first,
+                                                            u32x4* __restrict__ result) {
+    const int q = (threadIdx.x >> 3) & 3, k = threadIdx.x & 7;
+    int w = k_hi - 1;
+    u32 acc;
+    if (first) acc = warp_point_load(win + QQ_PT_Q * (size_t)w--);
+    else acc = warp_point_load(result);
+    for (; w >= k_lo; w--) {
+        u32 p = warp_point_load(win + QQ_PT_Q * (size_t)w);
+        u32 pc = warp_to_cached(p, q, k);
+#pragma unroll 1
+        for (int i = 0; i < c; i++) acc = warp_dbl(acc, q, k);
         acc = warp_add(acc, pc, q, k);
     }
     warp_point_store(result, acc);

@@ -80,7 +80,7 @@ struct qq_ctx {
     int sms = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // upload / download streams of the pipelined host entry points
-    cudaEvent_t msm_ev[8] = {nullptr};
+    cudaEvent_t msm_ev[12] = {nullptr};
     cudaStream_t msm_hi = nullptr;           // high-priority stream: the MSM's counting sort, concurrent with the decompression
     long msm_split_min = 1 << 17;            // QQ_MSM_SPLIT_MIN / QQ_MSM_TAIL_PCT in the environment override
     int msm_sort_bpsm = 3;                   // blocks per SM of the sort kernels while they run under the decompression
@@ -130,6 +130,11 @@ struct qq_ctx {
     // 3.29 / 2.35 - beyond L2 the 16 x larger gather footprint costs more than the reductions and the Horner chain save.
     size_t msm_shift_budget = (size_t)112 << 20;
     bool msm_use_shifted = true;
+    // pipelined tail of the large MSM: ranks of windows (QQ_MSM_PIPE_RANKS = 2..4), from msm_pipe_min terms on.  Off by default:
+    // measured 3.94 against 3.97 ms at 2^20 and 55.2 against 54.4 ms at 2^24 (the reductions it hides are real multiply work that
+    // then competes with the accumulation; profiles/msm_pipelined_tail_r02.jsonl)
+    int msm_pipe_ranks = 1;
+    long msm_pipe_min = 1 << 17;
     bool msm_horner_warp = true;     // window Horner with one limb per lane (ge_warp.cuh); false: the four-lane form (A/B knob)
     bool secret_mode = false;                  // qq_set_secret_mode: constant-time table access for scalars that are secrets
     int vb_blocks_per_sm_secret[3] = {0, 0, 0};
@@ -581,10 +586,12 @@ extern "C" int qq_init(qq_ctx** out, int device) {
             if (const char* e = getenv("QQ_MSM_SORT_BPSM")) ctx->msm_sort_bpsm = atoi(e);
             if (const char* e = getenv("QQ_MSM_SHIFT_BUDGET_MB")) ctx->msm_shift_budget = (size_t)atol(e) << 20;
             if (const char* e = getenv("QQ_MSM_HORNER_WARP")) ctx->msm_horner_warp = atoi(e) != 0;
+            if (const char* e = getenv("QQ_MSM_PIPE_RANKS")) { int v = atoi(e); if (v >= 1 && v <= 4) ctx->msm_pipe_ranks = v; }
+            if (const char* e = getenv("QQ_MSM_PIPE_MIN")) { long v = atol(e); if (v >= 1) ctx->msm_pipe_min = v; }
             if (const char* e = getenv("QQ_VERIFY_HOST_TRANSCRIPTS")) ctx->verify_host_transcripts = atoi(e) != 0;
             if (const char* e = getenv("QQ_VERIFY_AGGREGATE")) ctx->verify_aggregate = atoi(e) != 0;
         }
-        for (int i = 0; i < 8; i++) CK(cudaEventCreateWithFlags(&ctx->msm_ev[i], cudaEventDisableTiming));
+        for (int i = 0; i < 12; i++) CK(cudaEventCreateWithFlags(&ctx->msm_ev[i], cudaEventDisableTiming));
         CK(cudaFuncSetAttribute(k_msm_sum_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * QQ_PT_BYTES));
         CK(cudaFuncSetAttribute(k_fixedbase<QQ_FB_W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(fb_table_words() * 4)));
@@ -670,7 +677,7 @@ extern "C" void qq_destroy(qq_ctx* ctx) {
         if (ctx->fbt[b]) cudaFree(ctx->fbt[b]);
         if (ctx->half_base[b]) cudaFree(ctx->half_base[b]);
     }
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < 12; i++)
         if (ctx->msm_ev[i]) cudaEventDestroy(ctx->msm_ev[i]);
     for (auto e : ctx->pipe_ev) cudaEventDestroy(e);
     ctx->pin.destroy();

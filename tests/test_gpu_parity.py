@@ -1930,3 +1930,45 @@ def test_msm_horner_forms_agree(pkg):
         outs.append(res)
         e.close()
     assert outs[0] == outs[1]
+
+
+@pytest.mark.gpu
+def test_msm_pipelined_tail_forms_agree(pkg):
+    """The pipelined tail of the large MSM (QQ_MSM_PIPE_RANKS = 2, 3: ranks of windows accumulated by separate launches, the upper
+    ranks reduced on the high-priority stream under the accumulation of the lower ones) against the single-launch form and the C
+    oracle: uniform scalars, and scalars that leave the top windows empty / put every term of a window into one bucket."""
+    import os
+    import c_oracle as C
+    cases = []
+    for n, kind in ((140000, "uniform"), ((1 << 18) + 5, "small"), (150001, "same")):
+        r2 = np.random.default_rng(n)
+        hs = r2.integers(0, 256, size=(n, 32), dtype=np.uint8)
+        hs[:, 31] &= 0x0f
+        a = r2.integers(0, 256, size=(n, 32), dtype=np.uint8)
+        a[:, 31] &= 0x0f
+        if kind == "small":
+            a[:, 9:] = 0                      # 72-bit scalars: the upper ranks hold empty buckets only
+        if kind == "same":
+            a[:] = a[0]                       # one bucket per window, cut into virtual buckets
+        cases.append((hs, a))
+    outs = []
+    for ranks in ("1", "2", "3"):
+        os.environ["QQ_MSM_PIPE_RANKS"] = ranks
+        try:
+            e = pkg.Engine(0)
+        finally:
+            del os.environ["QQ_MSM_PIPE_RANKS"]
+        res = []
+        for hs, a in cases:
+            pts, st = e.fixed_base(0, hs)
+            for _ in range(2):                # twice: the second call reuses the workspace while nothing of the first may linger
+                out, s = e.msm(a, pts)
+                assert s == 0
+            res.append((out.tobytes(), pts))
+        outs.append([r[0] for r in res])
+        if ranks == "1":
+            for (hs, a), (o, pts) in zip(cases, res):
+                exp, es = C.msm(a, pts)
+                assert es == 0 and exp.tobytes() == o
+        e.close()
+    assert outs[0] == outs[1] == outs[2]
