@@ -8,6 +8,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include "fe25519.cuh"      // mp_mul8 / mp_mul4 and the carry-flag primitives (host: emulated) for the 32-bit limb form below
 #ifdef __CUDACC__
 #define QQ_SC_FN __host__ __device__ static inline
 #define QQ_SC_FN_BIG __host__ __device__ __noinline__ static      // one copy of the large bodies in device code (see keccak_host.hpp)
@@ -161,7 +162,105 @@ QQ_SC_FN_BIG sc reduce512(const uint64_t x[8]) {
     }
     return sc{{r[0], r[1], r[2], r[3]}};
 }
+// ---- the same product with 32-bit limbs ----------------------------------------------------------------------------------
+// Device code has no 64 x 64 -> 128 multiply: every (u128)a * b above becomes four 32-bit multiplies plus carry glue, ~650
+// instructions per product in the one-thread-per-proof transcript kernels, whose running time IS their instruction count.
+// Here the 8 x 8 product is fe25519's mp_mul8 (64 IMAD.WIDE with the carries in the flag) and the special-form reduction
+// (l = 2^252 + c, c = 4 limbs) uses 4 x 4 blocks: c * hi (9 limbs), c * yhi (5 limbs), c * zhi (1 limb).  Same steps as
+// reduce512, same canonical result; compiled for the host too (emulated carry flag) so tests/test_host_arith.py checks it.
+QQ_SC_FN void w32_mul_c1(uint32_t out[5], uint32_t h) {      // out = c * h, h one limb
+    const uint32_t C[4] = {0x5cf5d3edu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu};
+    uint64_t carry = 0;
+    for (int j = 0; j < 4; j++) {
+        uint64_t t = (uint64_t)C[j] * h + carry;
+        out[j] = (uint32_t)t;
+        carry = t >> 32;
+    }
+    out[4] = (uint32_t)carry;
+}
+QQ_SC_FN_BIG sc reduce512_w32(const uint32_t x[16]) {
+    using namespace qq;
+    const uint32_t C[4] = {0x5cf5d3edu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu};
+    const uint32_t L2[8] = {0xb9eba7dau, 0xb024c634u, 0x45ef39acu, 0x29bdf3bdu, 0u, 0u, 0u, 0x20000000u};      // 2 l
+    const uint32_t Lw[8] = {0x5cf5d3edu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu, 0u, 0u, 0u, 0x10000000u};
+    uint32_t hi[9], p0[8], p1[8], p2[5], y[14], yhi[5], q0[8], q1[5], z[10], w[5], t[8];
+    for (int i = 0; i < 9; i++) hi[i] = (x[7 + i] >> 28) | (i < 8 ? x[8 + i] << 4 : 0u);
+    // y = c * hi  (< 2^385: 13 limbs)
+    mp_mul4(p0, C, hi);
+    mp_mul4(p1, C, hi + 4);
+    w32_mul_c1(p2, hi[8]);
+    for (int i = 0; i < 4; i++) y[i] = p0[i];
+    y[4] = add_cc(p0[4], p1[0]);
+    y[5] = addc_cc(p0[5], p1[1]);
+    y[6] = addc_cc(p0[6], p1[2]);
+    y[7] = addc_cc(p0[7], p1[3]);
+    y[8] = addc_cc(p1[4], 0u);
+    y[9] = addc_cc(p1[5], 0u);
+    y[10] = addc_cc(p1[6], 0u);
+    y[11] = addc_cc(p1[7], 0u);
+    y[12] = addc(0u, 0u);
+    y[8] = add_cc(y[8], p2[0]);
+    y[9] = addc_cc(y[9], p2[1]);
+    y[10] = addc_cc(y[10], p2[2]);
+    y[11] = addc_cc(y[11], p2[3]);
+    y[12] = addc(y[12], p2[4]);
+    y[13] = 0;
+    for (int i = 0; i < 5; i++) yhi[i] = (y[7 + i] >> 28) | (y[8 + i] << 4);      // < 2^133
+    // z = c * yhi  (< 2^258: 9 limbs)
+    mp_mul4(q0, C, yhi);
+    w32_mul_c1(q1, yhi[4]);
+    for (int i = 0; i < 4; i++) z[i] = q0[i];
+    z[4] = add_cc(q0[4], q1[0]);
+    z[5] = addc_cc(q0[5], q1[1]);
+    z[6] = addc_cc(q0[6], q1[2]);
+    z[7] = addc_cc(q0[7], q1[3]);
+    z[8] = addc(q1[4], 0u);
+    const uint32_t zhi = (z[7] >> 28) | (z[8] << 4);      // < 2^6
+    w32_mul_c1(w, zhi);                                    // < 2^131
+    // t = lo + zlo + 2 l - ylo - w: in [0, 2^255)
+    t[0] = add_cc(x[0], z[0]);
+    for (int i = 1; i < 7; i++) t[i] = addc_cc(x[i], z[i]);
+    t[7] = addc(x[7] & 0x0fffffffu, z[7] & 0x0fffffffu);
+    t[0] = add_cc(t[0], L2[0]);
+    for (int i = 1; i < 7; i++) t[i] = addc_cc(t[i], L2[i]);
+    t[7] = addc(t[7], L2[7]);
+    t[0] = sub_cc(t[0], y[0]);
+    for (int i = 1; i < 7; i++) t[i] = subc_cc(t[i], y[i]);
+    t[7] = subc(t[7], y[7] & 0x0fffffffu);
+    t[0] = sub_cc(t[0], w[0]);
+    for (int i = 1; i < 5; i++) t[i] = subc_cc(t[i], w[i]);
+    for (int i = 5; i < 7; i++) t[i] = subc_cc(t[i], 0u);
+    t[7] = subc(t[7], 0u);
+    // t = q 2^252 + r, q < 8: r - q c in (-2^128, 2^252); one conditional addition of l finishes
+    const uint32_t q = t[7] >> 28;
+    t[7] &= 0x0fffffffu;
+    uint32_t qc[5];
+    w32_mul_c1(qc, q);
+    t[0] = sub_cc(t[0], qc[0]);
+    for (int i = 1; i < 5; i++) t[i] = subc_cc(t[i], qc[i]);
+    for (int i = 5; i < 8; i++) t[i] = subc_cc(t[i], 0u);
+    const uint32_t m = subc(0u, 0u);      // all ones when negative
+    t[0] = add_cc(t[0], Lw[0] & m);
+    for (int i = 1; i < 7; i++) t[i] = addc_cc(t[i], Lw[i] & m);
+    t[7] = addc(t[7], Lw[7] & m);
+    sc r;
+    for (int i = 0; i < 4; i++) r.v[i] = (uint64_t)t[2 * i] | ((uint64_t)t[2 * i + 1] << 32);
+    return r;
+}
+QQ_SC_FN_BIG sc mul_w32(const sc& a, const sc& b) {
+    uint32_t A[8], B[8], x[16];
+    for (int i = 0; i < 4; i++) {
+        A[2 * i] = (uint32_t)a.v[i]; A[2 * i + 1] = (uint32_t)(a.v[i] >> 32);
+        B[2 * i] = (uint32_t)b.v[i]; B[2 * i + 1] = (uint32_t)(b.v[i] >> 32);
+    }
+    qq::mp_mul8(x, A, B);
+    return reduce512_w32(x);
+}
+
 QQ_SC_FN_BIG sc mul(const sc& a, const sc& b) {
+#if defined(__CUDA_ARCH__)
+    return mul_w32(a, b);
+#else
     uint64_t x[8] = {0};
     for (int i = 0; i < 4; i++) {
         u128 c = 0;
@@ -173,12 +272,19 @@ QQ_SC_FN_BIG sc mul(const sc& a, const sc& b) {
         x[i + 4] = (uint64_t)c;
     }
     return reduce512(x);
+#endif
 }
 // Scalar::from_bytes_mod_order_wide
 QQ_SC_FN sc from_wide(const uint8_t b[64]) {
+#if defined(__CUDA_ARCH__)
+    uint32_t x[16];
+    memcpy(x, b, 64);
+    return reduce512_w32(x);
+#else
     uint64_t x[8];
     memcpy(x, b, 64);
     return reduce512(x);
+#endif
 }
 // a^(l - 2)
 QQ_SC_FN_BIG sc invert(const sc& a) {

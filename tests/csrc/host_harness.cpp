@@ -265,17 +265,25 @@ void hh_fb_mult(uint8_t* out, const u32* tbl, int W, const uint8_t* scalar) {
     ristretto_compress(w, r);
     store_words(out, w);
 }
-// host scalar field (sc_host.hpp): op 0 add, 1 sub, 2 mul, 3 invert(a), 4 from_wide(a || b); returns 0 when an input is not canonical
+// host scalar field (sc_host.hpp): op 0 add, 1 sub, 2 mul, 3 invert(a), 4 from_wide(a || b), 5 invert_vartime, 6 mul in the
+// 32-bit limb form of the device code, 7 its wide reduction; returns 0 when an input is not canonical
 int hh_sc_op(uint8_t* out, int op, const uint8_t* a, const uint8_t* b) {
     qq_sc::sc x, y, r;
-    if (op == 4) {
+    if (op == 4 || op == 7) {
         uint8_t w[64];
         memcpy(w, a, 32);
         memcpy(w + 32, b, 32);
-        r = qq_sc::from_wide(w);
+        if (op == 4) {
+            r = qq_sc::from_wide(w);
+        } else {                      // the 32-bit limb reduction the device code runs
+            uint32_t x32[16];
+            memcpy(x32, w, 64);
+            r = qq_sc::reduce512_w32(x32);
+        }
     } else {
         if (!qq_sc::from_bytes(x, a) || !qq_sc::from_bytes(y, b)) return 0;
-        r = op == 0 ? qq_sc::add(x, y) : op == 1 ? qq_sc::sub(x, y) : op == 2 ? qq_sc::mul(x, y) : op == 3 ? qq_sc::invert(x) : qq_sc::invert_vartime(x);
+        r = op == 0 ? qq_sc::add(x, y) : op == 1 ? qq_sc::sub(x, y) : op == 2 ? qq_sc::mul(x, y) : op == 3 ? qq_sc::invert(x)
+          : op == 6 ? qq_sc::mul_w32(x, y) : qq_sc::invert_vartime(x);
     }
     qq_sc::to_bytes(out, r);
     return 1;

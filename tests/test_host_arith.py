@@ -257,13 +257,20 @@ def test_host_scalar_field(hh):
         assert op(1, a, b) == (a - b) % L
         assert op(2, a, b) == (a * b) % L
         assert op(4, a, b) == (a + (b << 256)) % L
+        assert op(6, a, b) == (a * b) % L                  # the device code's 32-bit limb product (mul_w32)
+        assert op(7, a, b) == (a + (b << 256)) % L         # and its wide reduction (reduce512_w32)
     for a in edge[1:] + vals[-60:]:
         inv = op(3, a, 0)
         assert inv * a % L == 1
         assert op(5, a, 0) == inv              # binary extended Euclid (invert_vartime) == a^(l - 2)
     assert op(5, 0, 0) == 0
-    for wide in (2**512 - 1, (L << 256) + L - 1, (2**256 - 1) << 256, 2**511):
+    wides = [2**512 - 1, (L << 256) + L - 1, (2**256 - 1) << 256, 2**511, (L - 1) ** 2, L * L, L * L - 1, 2**252, 2**252 - 1, L, L - 1,
+             2 * L, (2**252) * (2**260 - 1), 2**504 + 2**252 - 1, (1 << 512) - (1 << 252)]
+    wides += [rnd.getrandbits(512) for _ in range(400)] + [rnd.getrandbits(512) | ((2**260 - 1) << 252) for _ in range(50)]
+    wides += [rnd.getrandbits(rnd.choice([10, 100, 250, 253, 300, 385, 400])) for _ in range(200)]
+    for wide in wides:
         assert op(4, wide & (2**256 - 1), wide >> 256) == wide % L
+        assert op(7, wide & (2**256 - 1), wide >> 256) == wide % L
     assert op(2, L, 1) is None and op(0, 1, 2**256 - 1) is None
 
 
