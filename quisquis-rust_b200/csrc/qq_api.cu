@@ -135,6 +135,7 @@ struct qq_ctx {
     // then competes with the accumulation; profiles/msm_pipelined_tail_r02.jsonl)
     int msm_pipe_ranks = 1;
     long msm_pipe_min = 1 << 17;
+    bool small_fanout = true;        // small batches: independent launches of one call on the copy streams (QQ_SMALL_FANOUT)
     bool msm_horner_warp = true;     // window Horner with one limb per lane (ge_warp.cuh); false: the four-lane form (A/B knob)
     bool secret_mode = false;                  // qq_set_secret_mode: constant-time table access for scalars that are secrets
     int vb_blocks_per_sm_secret[3] = {0, 0, 0};
@@ -586,6 +587,7 @@ extern "C" int qq_init(qq_ctx** out, int device) {
             if (const char* e = getenv("QQ_MSM_SORT_BPSM")) ctx->msm_sort_bpsm = atoi(e);
             if (const char* e = getenv("QQ_MSM_SHIFT_BUDGET_MB")) ctx->msm_shift_budget = (size_t)atol(e) << 20;
             if (const char* e = getenv("QQ_MSM_HORNER_WARP")) ctx->msm_horner_warp = atoi(e) != 0;
+            if (const char* e = getenv("QQ_SMALL_FANOUT")) ctx->small_fanout = atoi(e) != 0;
             if (const char* e = getenv("QQ_MSM_PIPE_RANKS")) { int v = atoi(e); if (v >= 1 && v <= 4) ctx->msm_pipe_ranks = v; }
             if (const char* e = getenv("QQ_MSM_PIPE_MIN")) { long v = atol(e); if (v >= 1) ctx->msm_pipe_min = v; }
             if (const char* e = getenv("QQ_VERIFY_HOST_TRANSCRIPTS")) ctx->verify_host_transcripts = atoi(e) != 0;
@@ -852,6 +854,19 @@ static int core_add_commitments(qq_ctx* ctx, const uint8_t* a, const uint8_t* b,
     return QQ_OK;
 }
 
+// run a launch helper on another stream of the context (the helpers launch on ctx->stream)
+template <class F>
+static int on_stream(qq_ctx* ctx, cudaStream_t s, F&& f) {
+    cudaStream_t keep = ctx->stream;
+    ctx->stream = s;
+    int rc = f();
+    ctx->stream = keep;
+    return rc;
+}
+// small batches: independent launches of one call fan out over the copy streams (QQ_SMALL_FANOUT=0 keeps one stream)
+static bool small_fanout(qq_ctx* ctx, size_t m) {
+    return ctx->small_fanout && ctx->copy_in != nullptr && ctx->copy_out != nullptr && m <= (size_t)ctx->sms * 16;
+}
 static int core_update_account(qq_ctx* ctx, const uint8_t* acc, const uint8_t* bl, const uint8_t* u, const uint8_t* c,
                                uint8_t* out, uint8_t* status, size_t n) {
     for (size_t base = 0; base < n; base += QQ_CHUNK) {
@@ -867,20 +882,43 @@ static int core_update_account(qq_ctx* ctx, const uint8_t* acc, const uint8_t* b
         const uint8_t* acc_c = acc + base * 128;
         const uint8_t *bl_c = bl + base * 32, *u_c = u + base * 32, *c_c = c + base * 32;
         uint8_t* out_c = out + base * 128;
+        // Small batches (a 9-account anonymity set, a block's worth of transactions) are chains of latency-bound launches: the
+        // fixed-base walk runs beside the decompression and the scalar multiplications, and the three encoders (each ends in
+        // one inverse-square-root or inversion chain, ~60 us) run side by side on the two copy streams.
+        const bool fan = small_fanout(ctx, m);
+        if (fan) {
+            CK(cudaEventRecord(ctx->msm_ev[8], ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->copy_in, ctx->msm_ev[8], 0));
+            CK(cudaStreamWaitEvent(ctx->copy_out, ctx->msm_ev[8], 0));
+            CKQ(on_stream(ctx, ctx->copy_in, [&] { return launch_fixedbase(ctx, QQ_BASE_B, bl_c, F, m); }));
+        }
         CKQ(launch_decompress(ctx, acc_c, IDENT, P, ok, 4 * m));
         CKQ(launch_status(ctx, bl_c, u_c, c_c, ok, 4, status + base, m));
         // items: (account i, point j in {gr, grsk}); two scalars (u_i, c_i) share one window table
         // u is halved: Ru = (u/2) * (gr, grsk) feeds the double-and-compress encoder; c stays whole because the
         // commitment adds the account's own points, which cannot be halved
         CKQ(launch_varbase(ctx, 2, P, imap(2, 4, 0, 1), u_c, c_c, 2, Ru, Rc, scratch, 2 * m, 1, 0));
-        CKQ(launch_fixedbase(ctx, QQ_BASE_B, bl_c, F, m));
+        if (!fan) CKQ(launch_fixedbase(ctx, QQ_BASE_B, bl_c, F, m));
+        if (fan) {
+            CK(cudaEventRecord(ctx->msm_ev[9], ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->copy_in, ctx->msm_ev[9], 0));
+            CK(cudaStreamWaitEvent(ctx->copy_out, ctx->msm_ev[9], 0));
+        }
         // pk' = (u*gr, u*grsk)
         CKQ(launch_finish_dbl(ctx, dc, fsrc(Ru, IDENT), FNONE, FNONE, out_c, imap(2, 4, 0, 1), status + base, 2, 2 * m));
         // comm' = (c*gr + a.c, bl*B + c*grsk + a.d)        -- OLD pk, reference src/accounts/accounts.rs:149-152
-        CKQ(launch_finish(ctx, fsrc(Rc, imap(1, 2, 0)), fsrc(P, imap(1, 4, 2)), FNONE, out_c, imap(1, 4, 2),
-                          status + base, m));
-        CKQ(launch_finish(ctx, fsrc(Rc, imap(1, 2, 1)), fsrc(F, IDENT), fsrc(P, imap(1, 4, 3)), out_c, imap(1, 4, 3),
-                          status + base, m));
+        CKQ(on_stream(ctx, fan ? ctx->copy_out : ctx->stream, [&] {
+            return launch_finish(ctx, fsrc(Rc, imap(1, 2, 0)), fsrc(P, imap(1, 4, 2)), FNONE, out_c, imap(1, 4, 2), status + base, m);
+        }));
+        CKQ(on_stream(ctx, fan ? ctx->copy_in : ctx->stream, [&] {
+            return launch_finish(ctx, fsrc(Rc, imap(1, 2, 1)), fsrc(F, IDENT), fsrc(P, imap(1, 4, 3)), out_c, imap(1, 4, 3), status + base, m);
+        }));
+        if (fan) {
+            CK(cudaEventRecord(ctx->msm_ev[10], ctx->copy_in));
+            CK(cudaEventRecord(ctx->msm_ev[11], ctx->copy_out));
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->msm_ev[10], 0));
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->msm_ev[11], 0));
+        }
     }
     return QQ_OK;
 }
@@ -900,14 +938,30 @@ static int core_verify_account(qq_ctx* ctx, const uint8_t* acc, const uint8_t* s
         dc_ws dc = dc_take(ctx, m);
         const uint8_t* acc_c = acc + base * 128;
         const uint8_t *sk_c = sk + base * 32, *bl_c = bl + base * 32;
+        const bool fan = small_fanout(ctx, m) && m <= QQ_DC_DIRECT_MAX && ctx->vbc_max_jobs != 0;   // the direct encoder needs no shared scratch
+        if (fan) {
+            CK(cudaEventRecord(ctx->msm_ev[8], ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->copy_in, ctx->msm_ev[8], 0));
+            CKQ(on_stream(ctx, ctx->copy_in, [&] { return launch_fixedbase(ctx, QQ_BASE_B, bl_c, F, m, 1); }));
+        }
         CKQ(launch_decompress(ctx, acc_c, imap(2, 4, 0, 2), P, ok, 2 * m));
         CKQ(launch_status(ctx, sk_c, bl_c, nullptr, ok, 0, pre, m));
         CKQ(launch_varbase(ctx, 1, P, IDENT, sk_c, nullptr, 2, R, nullptr, scratch, 2 * m, 1));
-        CKQ(launch_fixedbase(ctx, QQ_BASE_B, bl_c, F, m, 1));
+        if (!fan) CKQ(launch_fixedbase(ctx, QQ_BASE_B, bl_c, F, m, 1));
+        if (fan) {
+            CK(cudaEventRecord(ctx->msm_ev[9], ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->copy_in, ctx->msm_ev[9], 0));
+        }
         // grsk == enc(sk*gr)                       reference src/ristretto/keys.rs:187-195
         CKQ(launch_finish_dbl(ctx, dc, fsrc(R, imap(1, 2, 0)), FNONE, FNONE, nullptr, IDENT, nullptr, 1, m, acc_c, imap(1, 4, 1), eq));
         // d == enc(bl*B + sk*c)                    reference src/elgamal/elgamal.rs:81-95
-        CKQ(launch_finish_dbl(ctx, dc, fsrc(R, imap(1, 2, 1)), fsrc(F, IDENT), FNONE, nullptr, IDENT, nullptr, 1, m, acc_c, imap(1, 4, 3), eq + m));
+        CKQ(on_stream(ctx, fan ? ctx->copy_in : ctx->stream, [&] {
+            return launch_finish_dbl(ctx, dc, fsrc(R, imap(1, 2, 1)), fsrc(F, IDENT), FNONE, nullptr, IDENT, nullptr, 1, m, acc_c, imap(1, 4, 3), eq + m);
+        }));
+        if (fan) {
+            CK(cudaEventRecord(ctx->msm_ev[10], ctx->copy_in));
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->msm_ev[10], 0));
+        }
         k_verify_account_status<<<grid_for(m, 256, ctx->sms * 16), 256, 0, ctx->stream>>>(pre, ok, eq, status + base, m);
         ctx->launches++;
     }
