@@ -804,6 +804,19 @@ static int core_scale_pairs(qq_ctx* ctx, const uint8_t* pk, const uint8_t* s, ui
     return QQ_OK;
 }
 
+// run a launch helper on another stream of the context (the helpers launch on ctx->stream)
+template <class F>
+static int on_stream(qq_ctx* ctx, cudaStream_t s, F&& f) {
+    cudaStream_t keep = ctx->stream;
+    ctx->stream = s;
+    int rc = f();
+    ctx->stream = keep;
+    return rc;
+}
+// small batches: independent launches of one call fan out over the copy streams (QQ_SMALL_FANOUT=0 keeps one stream)
+static bool small_fanout(qq_ctx* ctx, size_t m) {
+    return ctx->small_fanout && ctx->copy_in != nullptr && ctx->copy_out != nullptr && m <= (size_t)ctx->sms * 16;
+}
 static int core_generate_commitment(qq_ctx* ctx, const uint8_t* pk, const uint8_t* r, const uint8_t* v, uint8_t* out,
                                     uint8_t* status, size_t n) {
     for (size_t base = 0; base < n; base += QQ_CHUNK) {
@@ -818,14 +831,30 @@ static int core_generate_commitment(qq_ctx* ctx, const uint8_t* pk, const uint8_
         const uint8_t* pk_c = pk + base * 64;
         const uint8_t* r_c = r + base * 32;
         const uint8_t* v_c = v + base * 32;
+        // small batches: the fixed-base walk and the second encoder run on a copy stream (see core_update_account)
+        const bool fan = small_fanout(ctx, m) && m <= QQ_DC_DIRECT_MAX && ctx->vbc_max_jobs != 0;   // the direct encoder needs no shared scratch
+        if (fan) {
+            CK(cudaEventRecord(ctx->msm_ev[8], ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->copy_in, ctx->msm_ev[8], 0));
+            CKQ(on_stream(ctx, ctx->copy_in, [&] { return launch_fixedbase(ctx, QQ_BASE_B, v_c, F, m, 1); }));
+        }
         CKQ(launch_decompress(ctx, pk_c, IDENT, P, ok, 2 * m));
         CKQ(launch_status(ctx, r_c, v_c, nullptr, ok, 2, status + base, m));
         // every term carries half its scalar; the outputs are enc(2 * sum)
         CKQ(launch_varbase(ctx, 1, P, IDENT, r_c, nullptr, 2, R, nullptr, scratch, 2 * m, 1));
-        CKQ(launch_fixedbase(ctx, QQ_BASE_B, v_c, F, m, 1));
+        if (!fan) CKQ(launch_fixedbase(ctx, QQ_BASE_B, v_c, F, m, 1));
+        if (fan) {
+            CK(cudaEventRecord(ctx->msm_ev[9], ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->copy_in, ctx->msm_ev[9], 0));
+        }
         CKQ(launch_finish_dbl(ctx, dc, fsrc(R, imap(1, 2, 0)), FNONE, FNONE, out + base * 64, imap(1, 2, 0), status + base, 1, m));
-        CKQ(launch_finish_dbl(ctx, dc, fsrc(R, imap(1, 2, 1)), fsrc(F, IDENT), FNONE, out + base * 64, imap(1, 2, 1),
-                              status + base, 1, m));
+        CKQ(on_stream(ctx, fan ? ctx->copy_in : ctx->stream, [&] {
+            return launch_finish_dbl(ctx, dc, fsrc(R, imap(1, 2, 1)), fsrc(F, IDENT), FNONE, out + base * 64, imap(1, 2, 1), status + base, 1, m);
+        }));
+        if (fan) {
+            CK(cudaEventRecord(ctx->msm_ev[10], ctx->copy_in));
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->msm_ev[10], 0));
+        }
     }
     return QQ_OK;
 }
@@ -854,19 +883,6 @@ static int core_add_commitments(qq_ctx* ctx, const uint8_t* a, const uint8_t* b,
     return QQ_OK;
 }
 
-// run a launch helper on another stream of the context (the helpers launch on ctx->stream)
-template <class F>
-static int on_stream(qq_ctx* ctx, cudaStream_t s, F&& f) {
-    cudaStream_t keep = ctx->stream;
-    ctx->stream = s;
-    int rc = f();
-    ctx->stream = keep;
-    return rc;
-}
-// small batches: independent launches of one call fan out over the copy streams (QQ_SMALL_FANOUT=0 keeps one stream)
-static bool small_fanout(qq_ctx* ctx, size_t m) {
-    return ctx->small_fanout && ctx->copy_in != nullptr && ctx->copy_out != nullptr && m <= (size_t)ctx->sms * 16;
-}
 static int core_update_account(qq_ctx* ctx, const uint8_t* acc, const uint8_t* bl, const uint8_t* u, const uint8_t* c,
                                uint8_t* out, uint8_t* status, size_t n) {
     for (size_t base = 0; base < n; base += QQ_CHUNK) {

@@ -45,9 +45,11 @@ def main():
             bd = eng.last_kernel_breakdown()
             ms_v = median_ms(lambda: eng.verify_account(acc, u, bl), reps)
             ms_k = median_ms(lambda: eng.update_public_key(acc[:, :64].copy(), u), reps)
+            pk = acc[:, :64].copy()
+            ms_g = median_ms(lambda: eng.generate_commitment(pk, c, bl), reps)
             print(json.dumps({"probe": "small_batch", "n": n, "coop": name, "update_account_ms": ms,
                               "breakdown_ms": bd, "verify_account_ms": ms_v, "update_public_key_ms": ms_k,
-                              "same_output": same}), flush=True)
+                              "generate_commitment_ms": ms_g, "same_output": same}), flush=True)
         eng.varbase_set_coop_limit(-1)
 
 
