@@ -327,6 +327,44 @@ def run_b200(args):
                  "accounts_per_sec_per_gpu": n / (msB * 1e-3), "pk_half_equals_distribution_A": pk_same}
         del blB_d, outB
 
+    # ---- the other three functions the north star names, at the same batch size (inputs resident in HBM; 32-byte encodings
+    # out): RistrettoPublicKey::update_public_key, ElGamalCommitment::generate_commitment (fixed base + two variable-base
+    # multiplications per commitment) and Account::create_delta_and_epsilon_accounts (host API, r supplied by the caller)
+    named = None
+    if n >= 1024 and not args.no_named_functions:
+        pk_d = d["acc"].view(n, 128)[:, :64].contiguous()
+        out64 = torch.empty(n * 64, dtype=torch.uint8, device=dev)
+        reps_n = max(2, args.steps // 2)
+
+        def timed(fn):
+            fn()
+            barrier()
+            eng.event_record(6)
+            for _ in range(reps_n):
+                fn()
+            eng.event_record(7)
+            return eng.event_elapsed_ms(6, 7) / reps_n
+        ms_pk = timed(lambda: eng.call_dev("qq_update_public_key_batch_dev", vp(pk_d.data_ptr()), vp(d["u"].data_ptr()),
+                                           vp(out64.data_ptr()), vp(st_d.data_ptr()), ctypes.c_size_t(n)))
+        assert int(st_d.max().item()) == 0
+        pk_same = bool(torch.equal(out64.view(n, 64), out_d.view(n, 128)[:, :64]))      # update_account's pk half is update_public_key(pk, u)
+        ms_gc = timed(lambda: eng.call_dev("qq_generate_commitment_batch_dev", vp(pk_d.data_ptr()), vp(d["c"].data_ptr()),
+                                           vp(d["bl"].data_ptr()), vp(out64.data_ptr()), vp(st_d.data_ptr()), ctypes.c_size_t(n)))
+        assert int(st_d.max().item()) == 0
+        nde = min(n, 1 << 18)
+        t_de = time.time()
+        # BASE_PK_BTC_COMPRESSED (reference src/ristretto/constants.rs:12-21)
+        base_pk = np.frombuffer(bytes.fromhex("e2f2ae0a6abc4e71a884a961c500515f58e30b6aa582dd8db6a65945e08d2d76"
+                                              "8c9240b456a9e6dc65c377a1048d745f94a08cdb7f44cbcd7b46f34048871134"), np.uint8)
+        dl, ep, st_de = eng.delta_epsilon(acc_h[:nde], bl_h[:nde], c_h[:nde], base_pk)
+        ms_de = (time.time() - t_de) * 1e3
+        assert not st_de.any()
+        named = {"update_public_key": {"n": n, "ms": ms_pk, "per_sec_per_gpu": n / (ms_pk * 1e-3), "equals_pk_half_of_update_account": pk_same},
+                 "generate_commitment": {"n": n, "ms": ms_gc, "per_sec_per_gpu": n / (ms_gc * 1e-3)},
+                 "create_delta_and_epsilon_accounts": {"n": nde, "ms_host_api": ms_de, "per_sec_per_gpu": nde / (ms_de * 1e-3),
+                                                       "note": "host buffers in and out (pageable), one call"}}
+        del pk_d, out64
+
     # ---- configs[0]: the 9-account anonymity set (3x3 shuffle), latency of one update_account + verify_account call pair
     # through the host API (the reference runs this case on one CPU core; reported for information)
     anon9 = None
@@ -879,6 +917,8 @@ def run_b200(args):
         if proto:
             proto["accounts_per_sec"] = proto["accounts_per_sec_per_gpu"] * world
             line["update_account_protocol_like"] = proto
+        if named is not None:
+            line["named_functions"] = named
         if multi_leg:
             line["multi_device_handle"] = multi_leg
         if anon9:
@@ -937,6 +977,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-seconds-per-step", type=float, default=4.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-named-functions", action="store_true", help="skip the update_public_key / generate_commitment / delta-epsilon timings")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
