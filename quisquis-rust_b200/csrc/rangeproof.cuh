@@ -76,20 +76,31 @@ __global__ void __launch_bounds__(128) k_rp_fold(const rp_record* __restrict__ r
     // thread i owns g_i and h_j with j = nm - 1 - i: both need the same s_i
     qq_sc::sc sum_g = qq_sc::zero(), sum_h = qq_sc::zero();
     const int j = N - 1 - i;
-    qq_sc::sc two_pow = qq_sc::zero();
-    two_pow.v[0] = 1ull << (j % n_bits);
     const int party = j / n_bits;
     const int LB = lg < 5 ? lg : 5, lmask = (1 << LB) - 1;
     const int lo = i & lmask, hi = i >> LB, jl = j & lmask, jh = j >> LB;
+    // sum_g = sum_p (neg_rz - sa slo),  sum_h = sum_p (rz + y_j (rzz_zj 2^k - sb slo)): the products sa slo and y_j u are added
+    // up unreduced (17 limbs) and reduced once per thread; u itself needs one reduction (it is a factor of the next product),
+    // y_j one - two reductions per (generator, proof) pair instead of five
+    uint32_t accg[17], acch[17], x[16];
+    for (int q = 0; q < 17; q++) accg[q] = acch[q] = 0;
+    const int kbit = j % n_bits;
     for (unsigned int p = p0; p < p1; p++) {
         const rp_record& r = rec[first + p];
         const rp_tables& t = tbl[first + p];
         const qq_sc::sc slo = t.slo[lo];
         const qq_sc::sc y_j = qq_sc::mul(t.yhi[jh], t.ylo[jl]);
-        sum_g = qq_sc::add(sum_g, qq_sc::sub(r.neg_rz, qq_sc::mul(t.sa[hi], slo)));
-        qq_sc::sc u = qq_sc::sub(qq_sc::mul(r.rzz_zj[party], two_pow), qq_sc::mul(t.sb[hi], slo));
-        sum_h = qq_sc::add(sum_h, qq_sc::add(r.rz, qq_sc::mul(y_j, u)));
+        sum_g = qq_sc::add(sum_g, r.neg_rz);
+        qq_sc::mul_wide_w32(x, t.sa[hi], slo);
+        qq_sc::acc17_add(accg, x);
+        qq_sc::mul_wide_w32(x, t.sb[hi], slo);
+        const qq_sc::sc u = qq_sc::shl_minus_wide(r.rzz_zj[party], kbit, x);
+        sum_h = qq_sc::add(sum_h, r.rz);
+        qq_sc::mul_wide_w32(x, y_j, u);
+        qq_sc::acc17_add(acch, x);
     }
+    sum_g = qq_sc::sub(sum_g, qq_sc::acc17_reduce(accg));
+    sum_h = qq_sc::add(sum_h, qq_sc::acc17_reduce(acch));
     partial[(size_t)blockIdx.y * 2 * N + i] = sum_g;
     partial[(size_t)blockIdx.y * 2 * N + N + j] = sum_h;
 }

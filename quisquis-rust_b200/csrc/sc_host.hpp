@@ -257,6 +257,55 @@ QQ_SC_FN_BIG sc mul_w32(const sc& a, const sc& b) {
     return reduce512_w32(x);
 }
 
+// ---- lazy sums of products (the range-proof fold: sum over the proofs of a_p b_p) -----------------------------------------
+// The 512-bit products are added up unreduced in 17 limbs (room for 2^38 products) and reduced once: the reduction is two
+// thirds of a product's cost.
+QQ_SC_FN void mul_wide_w32(uint32_t x[16], const sc& a, const sc& b) {
+    uint32_t A[8], B[8];
+    for (int i = 0; i < 4; i++) {
+        A[2 * i] = (uint32_t)a.v[i]; A[2 * i + 1] = (uint32_t)(a.v[i] >> 32);
+        B[2 * i] = (uint32_t)b.v[i]; B[2 * i + 1] = (uint32_t)(b.v[i] >> 32);
+    }
+    qq::mp_mul8(x, A, B);
+}
+QQ_SC_FN void acc17_add(uint32_t acc[17], const uint32_t x[16]) {
+    using namespace qq;
+    acc[0] = add_cc(acc[0], x[0]);
+    for (int i = 1; i < 16; i++) acc[i] = addc_cc(acc[i], x[i]);
+    acc[16] = addc(acc[16], 0u);
+}
+// acc (17 limbs) mod l: the low 512 bits through reduce512_w32, the top limb times 2^512 mod l
+QQ_SC_FN sc acc17_reduce(const uint32_t acc[17]) {
+    const sc R512 = sc{{0xa40611e3449c0f01ULL, 0xd00e1ba768859347ULL, 0xceec73d217f5be65ULL, 0x399411b7c309a3dULL}};      // 2^512 mod l
+    sc lo = reduce512_w32(acc);
+    if (acc[16] == 0) return lo;
+    return add(lo, mul_w32(from_u64(acc[16]), R512));
+}
+// (a 2^k + 2^254 l - x) mod l for a canonical a, k < 64 and a 512-bit product x of canonical factors (x < 2^506 < 2^254 l):
+// the difference a 2^k - x with ONE reduction
+QQ_SC_FN_BIG sc shl_minus_wide(const sc& a, int k, const uint32_t x[16]) {
+    using namespace qq;
+    const uint32_t ML[16] = {0x0u, 0x0u, 0x0u, 0x0u, 0x0u, 0x0u, 0x0u, 0x40000000u, 0x973d74fbu, 0x960498c6u, 0xa8bde735u, 0x537be77u,
+                             0x0u, 0x0u, 0x0u, 0x4000000u};      // 2^254 l
+    uint32_t w[16];
+    // w = a << k  (at most 317 bits)
+    uint32_t A[8];
+    for (int i = 0; i < 4; i++) { A[2 * i] = (uint32_t)a.v[i]; A[2 * i + 1] = (uint32_t)(a.v[i] >> 32); }
+    const int ws = k >> 5, bs = k & 31;
+    for (int i = 0; i < 16; i++) {
+        const int s0 = i - ws, s1 = i - ws - 1;
+        uint32_t lo = (s0 >= 0 && s0 < 8) ? A[s0] : 0u, below = (s1 >= 0 && s1 < 8) ? A[s1] : 0u;
+        w[i] = bs ? ((lo << bs) | (below >> (32 - bs))) : lo;
+    }
+    w[0] = add_cc(w[0], ML[0]);
+    for (int i = 1; i < 15; i++) w[i] = addc_cc(w[i], ML[i]);
+    w[15] = addc(w[15], ML[15]);
+    w[0] = sub_cc(w[0], x[0]);
+    for (int i = 1; i < 15; i++) w[i] = subc_cc(w[i], x[i]);
+    w[15] = subc(w[15], x[15]);
+    return reduce512_w32(w);
+}
+
 QQ_SC_FN_BIG sc mul(const sc& a, const sc& b) {
 #if defined(__CUDA_ARCH__)
     return mul_w32(a, b);

@@ -535,4 +535,26 @@ int hh_scalarmult_split64(uint8_t* out0, uint8_t* out1, const uint8_t* s0, const
     store_words(out1, w);
     return ok;
 }
+
+// lazy sums of products (sc_host.hpp: mul_wide_w32 / acc17_add / acc17_reduce) and the one-reduction difference shl_minus_wide:
+// out_sum = sum_p a_p b_p mod l over n pairs of canonical 32-byte scalars (each pair added `repeat` times, to drive the 17th limb);
+// out_u = (rzz 2^k - sb slo) mod l
+void hh_sc_lazy(uint8_t* out_sum, uint8_t* out_u, const uint8_t* a, const uint8_t* b, size_t n, unsigned repeat, const uint8_t* rzz, int k,
+                const uint8_t* sb, const uint8_t* slo) {
+    uint32_t acc[17] = {0}, x[16];
+    for (size_t p = 0; p < n; p++) {
+        qq_sc::sc x1, x2;
+        qq_sc::from_bytes(x1, a + 32 * p);
+        qq_sc::from_bytes(x2, b + 32 * p);
+        qq_sc::mul_wide_w32(x, x1, x2);
+        for (unsigned r = 0; r < repeat; r++) qq_sc::acc17_add(acc, x);
+    }
+    qq_sc::to_bytes(out_sum, qq_sc::acc17_reduce(acc));
+    qq_sc::sc r1, s1, s2;
+    qq_sc::from_bytes(r1, rzz);
+    qq_sc::from_bytes(s1, sb);
+    qq_sc::from_bytes(s2, slo);
+    qq_sc::mul_wide_w32(x, s1, s2);
+    qq_sc::to_bytes(out_u, qq_sc::shl_minus_wide(r1, k, x));
+}
 }

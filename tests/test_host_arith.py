@@ -473,3 +473,24 @@ def test_fe64_split_variable_base(hh):
         assert hh.hh_scalarmult_split64(o0, o1, s0.to_bytes(32, "little"), s1.to_bytes(32, "little"), p) == 1
         assert o0.raw == R.compress(R.mul(s0, R.decompress(p)))
         assert o1.raw == R.compress(R.mul(s1, R.decompress(p)))
+
+
+def test_host_scalar_field_lazy_sums(hh):
+    """The range-proof fold's lazy arithmetic (sc_host.hpp): products added up unreduced in 17 limbs and reduced once (including
+    sums that spill into the 17th limb), and (a 2^k - x) mod l with one reduction, against Python integers."""
+    import random
+    L = R.L
+    rnd = random.Random(12)
+    edge = [0, 1, L - 1, L - 2, 2**252, 2**252 - 1, (L - 1) // 2]
+    s32 = lambda v: v.to_bytes(32, "little")
+    osum, ou = (ctypes.c_uint8 * 32)(), (ctypes.c_uint8 * 32)()
+    for trial in range(60):
+        n = rnd.choice([1, 2, 7, 40])
+        a = [rnd.choice(edge) if rnd.random() < 0.4 else rnd.randrange(L) for _ in range(n)]
+        b = [rnd.choice(edge) if rnd.random() < 0.4 else rnd.randrange(L) for _ in range(n)]
+        repeat = rnd.choice([1, 1, 3, 200, 5000])          # (L - 1)^2 * 40 * 5000 > 2^512: the top limb is used
+        rzz, sb, slo = (rnd.choice(edge) if rnd.random() < 0.4 else rnd.randrange(L) for _ in range(3))
+        k = rnd.choice([0, 1, 31, 32, 33, 63, rnd.randrange(64)])
+        hh.hh_sc_lazy(osum, ou, b"".join(map(s32, a)), b"".join(map(s32, b)), n, repeat, s32(rzz), k, s32(sb), s32(slo))
+        assert int.from_bytes(bytes(osum), "little") == repeat * sum(x * y for x, y in zip(a, b)) % L
+        assert int.from_bytes(bytes(ou), "little") == (rzz * 2**k - sb * slo) % L
