@@ -512,6 +512,7 @@ struct straus_args {
     u32x4* scratch;
     const unsigned int* order; // instances sorted by term count (descending) so a warp's lanes do equal work
     size_t m;
+    int kc;                    // k_straus_coop: terms per pass (1 .. QQ_STC_KC); its shared memory is 8 x kc term slots per warp
 };
 // signed 64-bit values -> canonical scalars (v mod l), branch-free: |v| and l - |v| are both formed, the sign selects
 __global__ void k_i64_to_scalars(const long long* __restrict__ v, u32x4* __restrict__ out, size_t n) {
@@ -632,10 +633,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_straus(straus_args a) {
 #define QQ_STC_KC 9
 #define QQ_STC_TERM_Q (QQ_VBC_GROUP_Q + 2)                 // table + 8 recoded words
 #define QQ_STC_SMEM_BYTES (8 * QQ_STC_KC * QQ_STC_TERM_Q * 16)
+// a.kc terms per pass: an instance with more terms takes several passes (each pays the 252 doublings).  The caller sizes kc to the
+// largest instance when it knows it: with the full 9 slots a block needs 76 KB of shared memory and only two warps fit an SM -
+// 8 192 two-term instances (the exact MSMs of 4 096 shuffle proofs) then run in four waves, 1.09 ms; with kc = 2 (17 KB) in one.
 __global__ void __launch_bounds__(32) k_straus_coop(straus_args a) {
     extern __shared__ __align__(16) u32x4 stc_smem[];
     const int r = threadIdx.x & 3, grp = threadIdx.x >> 2;
-    u32x4* slab = stc_smem + (size_t)grp * (QQ_STC_KC * QQ_STC_TERM_Q);
+    const int KC = a.kc;
+    u32x4* slab = stc_smem + (size_t)grp * ((size_t)KC * QQ_STC_TERM_Q);
     size_t inst = (size_t)blockIdx.x * 8 + grp;
     bool act = inst < a.m;
     size_t j = act ? inst : 0;
@@ -648,9 +653,9 @@ __global__ void __launch_bounds__(32) k_straus_coop(straus_args a) {
     }
     fe total = coop_identity(r);
     uint8_t st = 0;
-    for (uint32_t c0 = 0; c0 < ntmax; c0 += QQ_STC_KC) {
-        int kw = (int)(ntmax - c0 < QQ_STC_KC ? ntmax - c0 : QQ_STC_KC);               // warp-uniform
-        int k = c0 < nt ? (int)(nt - c0 < QQ_STC_KC ? nt - c0 : QQ_STC_KC) : 0;        // this instance's
+    for (uint32_t c0 = 0; c0 < ntmax; c0 += (uint32_t)KC) {
+        int kw = (int)(ntmax - c0 < (uint32_t)KC ? ntmax - c0 : (uint32_t)KC);               // warp-uniform
+        int k = c0 < nt ? (int)(nt - c0 < (uint32_t)KC ? nt - c0 : (uint32_t)KC) : 0;        // this instance's
 #pragma unroll 1
         for (int t = 0; t < kw; t++) {
             bool have = t < k;

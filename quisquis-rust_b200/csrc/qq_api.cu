@@ -1091,8 +1091,9 @@ static int core_msm_to_point(qq_ctx* ctx, const uint8_t* scalars, const uint8_t*
 // group > 1: every `group` consecutive instances are the parts of ONE MSM (its terms split so that more threads share the
 // work: an MSM of 9 terms as 5 + 4 costs 252 doublings twice but halves the chain of additions); out / status then hold
 // m / group entries, the parts being summed by the batch encoder (it adds up to three sources).  group <= 3.
+// max_terms: the largest instance when the caller knows it (0: unknown) - sizes the cooperative kernel's shared memory
 static int core_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* points, const uint32_t* offsets, size_t m,
-                          size_t nterms, uint8_t* out, uint8_t* status, int group = 1) {
+                          size_t nterms, uint8_t* out, uint8_t* status, int group = 1, int max_terms = 0) {
     const size_t mo = m / (size_t)group;      // outputs
     auto finish = [&](const dc_ws& dc, u32x4* half, uint8_t* part_status) -> int {
         if (group == 1) return launch_finish_dbl(ctx, dc, fsrc(half, IDENT), FNONE, FNONE, out, IDENT, status, 1, m);
@@ -1119,8 +1120,9 @@ static int core_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* po
         straus_args a;
         a.pts = P; a.scalars = (const u32x4*)scalars; a.offsets = offsets; a.term_status = tst;
         a.out = (u32x4*)out; a.half_out = half; a.status = group == 1 ? status : part_status; a.scratch = nullptr; a.order = nullptr; a.m = m;
+        a.kc = max_terms > 0 && max_terms < QQ_STC_KC ? max_terms : QQ_STC_KC;
         span_begin(ctx, FAM_VB);
-        k_straus_coop<<<(unsigned)((m + 7) / 8), 32, QQ_STC_SMEM_BYTES, ctx->stream>>>(a);
+        k_straus_coop<<<(unsigned)((m + 7) / 8), 32, (size_t)8 * a.kc * QQ_STC_TERM_Q * 16, ctx->stream>>>(a);
         span_end(ctx);
         ctx->launches++;
         CK(cudaGetLastError());
@@ -1169,6 +1171,7 @@ static int core_segmented(qq_ctx* ctx, const uint8_t* scalars, const uint8_t* po
     a.pts = P; a.scalars = (const u32x4*)scalars; a.offsets = offsets; a.term_status = tst;
     // every scalar of an instance is halved, the instance sum is encoded as enc(2 * sum) by the batch encoder
     a.out = (u32x4*)out; a.half_out = half; a.status = group == 1 ? status : part_status; a.scratch = scratch; a.order = order; a.m = m;
+    a.kc = QQ_STC_KC;
     span_begin(ctx, FAM_VB);
     if (dense) k_straus<128, 4, false><<<(unsigned)grid, 128, 0, ctx->stream>>>(a);
     else k_straus<128, 2, false><<<(unsigned)grid, 128, 0, ctx->stream>>>(a);
