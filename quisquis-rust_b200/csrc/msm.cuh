@@ -277,6 +277,7 @@ __global__ void __launch_bounds__(256) k_msm_scatter(const int16_t* __restrict__
 // Populations cluster on a few dozen values, so the histogram and the slot reservation are privatised per block in
 // shared memory (one global atomic per (block, occupied bin) instead of one per bucket).
 #define QQ_ORDER_BINS 2048
+#define QQ_COMBINE_HEAVY 64   // parts of one bucket beyond which a whole block sums it (k_msm_combine)
 #define QQ_ORDER_TILE 4096   // elements per block iteration (256 threads x 16)
 __device__ __forceinline__ unsigned int order_key(unsigned int c) {
     return QQ_ORDER_BINS - 1 - (c < QQ_ORDER_BINS - 1 ? c : QQ_ORDER_BINS - 1);
@@ -396,6 +397,7 @@ __global__ void k_msm_vfill(const unsigned int* __restrict__ counts, const unsig
     for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < total; b += stride) {
         unsigned int c = counts[b], o = offsets[b], v = voff[b];
         if (c > cap) multi[atomicAdd(nmulti, 1u)] = (unsigned int)b;
+        if (c > cap * QQ_COMBINE_HEAVY) nmulti[1] = 1u;      // some bucket has more than QQ_COMBINE_HEAVY parts (k_msm_combine's second pass)
         for (unsigned int done = 0; done < c; done += cap, v++) {
             vstart[v] = o + done;
             vcnt[v] = c - done < cap ? c - done : cap;
@@ -507,6 +509,7 @@ __global__ void __launch_bounds__(128) k_msm_combine(u32x4* __restrict__ partial
         unsigned int b = multi[w];
         if (b < b_lo || b >= b_hi) continue;      // warp-uniform: another rank's bucket
         unsigned int v0 = voff[b], np = nsub[b];
+        if (np > QQ_COMBINE_HEAVY) continue;      // the second pass below
         ge_p3 acc;
         ge_identity(acc);
         for (unsigned int q = lane; q < np; q += 32) {
@@ -531,6 +534,41 @@ __global__ void __launch_bounds__(128) k_msm_combine(u32x4* __restrict__ partial
         }
         if (lane == 0) ge_p3_store(partial + QQ_PT_Q * (size_t)v0, acc);
         __syncwarp();
+    }
+    // Heavy buckets (more than QQ_COMBINE_HEAVY parts: the digit that the top bit or the recoding carry of a class of scalars
+    // lands in - 128-bit weights put half of their terms into ONE bucket of window 8): the whole block sums one, np / 128 + 7
+    // dependent additions instead of np / 32 + 5 on a warp (2 400 parts: 175 -> 60 us).
+    if (nmulti[1] == 0) return;      // no heavy bucket in this MSM (block-uniform)
+    __syncthreads();
+    for (unsigned int w = blockIdx.x; w < cnt; w += gridDim.x) {
+        unsigned int b = multi[w];
+        if (b < b_lo || b >= b_hi) continue;      // block-uniform
+        unsigned int v0 = voff[b], np = nsub[b];
+        if (np <= QQ_COMBINE_HEAVY) continue;
+        ge_p3 acc;
+        ge_identity(acc);
+        for (unsigned int q = threadIdx.x; q < np; q += blockDim.x) {
+            ge_p3 p;
+            ge_p3_load(p, partial + QQ_PT_Q * (size_t)(v0 + q));
+            ge_cached c;
+            ge_to_cached(c, p);
+            ge_add(acc, acc, c);
+        }
+        ge_p3_store(sm + QQ_PT_Q * threadIdx.x, acc);
+        __syncthreads();
+        for (int s2 = 64; s2 > 0; s2 >>= 1) {
+            if ((int)threadIdx.x < s2) {
+                ge_p3 p;
+                ge_p3_load(p, sm + QQ_PT_Q * (threadIdx.x + s2));
+                ge_cached c;
+                ge_to_cached(c, p);
+                ge_add(acc, acc, c);
+                ge_p3_store(sm + QQ_PT_Q * threadIdx.x, acc);
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) ge_p3_store(partial + QQ_PT_Q * (size_t)v0, acc);
+        __syncthreads();
     }
 }
 
