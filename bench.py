@@ -660,7 +660,7 @@ def run_b200(args):
                                   "ms_exact_form": sh_exact_ms, "n1_ms_whole_batch_on_rank0": sh_n1,
                                   "ms_one_tampered_proof": sh_bad_ms, "one_tampered_proof_isolated": bool(sh_bad_ok),
                                   "tampered_proof_rejected_alone": bool(sh_rej[per_rank // 2] != 0 and int(sh_rej.astype(bool).sum()) == 1),
-                                  "msms_per_proof": 32, "terms_per_proof": 239, "exact_msms_per_proof": 4, "aggregated_terms_per_proof": 146,
+                                  "msms_per_proof": 32, "terms_per_proof": 239, "exact_msms_per_proof": 4, "aggregated_terms_per_proof": 166,
                                   "api": "qq_verify_shuffle_batch (ShuffleProof::verify, 9 accounts): proof bytes uploaded, Merlin transcripts "
                                          "and Z/l algebra in transcript kernels, G / H / g_r / h_r as exact MSMs, the other 28 group equations "
                                          "of all proofs in one weighted Pippenger MSM; pinned host buffers in, verdict bytes out"}}
