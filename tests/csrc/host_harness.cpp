@@ -390,6 +390,8 @@ void hh_shuffle_verify(const char* transcript_label, const char* verifier_label,
 // every other group equation weighted into ONE sum over all proofs, which must be the identity.  clean[p]: the proof passed
 // every scalar check and is inside the aggregate; *agg_identity: the aggregated MSM (clean proofs only) is the identity;
 // counts[2 p], counts[2 p + 1]: aggregated (non-fixed) terms the proof emitted in batch 1 / 2.
+static uint8_t* g_apt_dump = nullptr;      // test hook: the aggregated MSM's point list of the next hh_shuffle_verify_aggregate call
+void hh_set_apt_dump(uint8_t* p) { g_apt_dump = p; }
 void hh_shuffle_verify_aggregate(const char* transcript_label, const char* verifier_label, const uint8_t* in, const uint8_t* out,
                                  const uint8_t* stm, const uint8_t* proof, size_t n, const uint8_t* base_pk, const uint8_t* xpc,
                                  const uint8_t* entropy, uint8_t* clean, uint8_t* agg_identity, uint32_t* counts) {
@@ -448,6 +450,7 @@ void hh_shuffle_verify_aggregate(const char* transcript_label, const char* verif
         const uint8_t* pt = i == 0 ? g.B : i == 1 ? g.Hp : i == 2 ? g.H : g.G + 32 * (i - 3);
         job_sink::put(asc.data(), apt.data(), n * (C1 + C2) + i, fixed[i], pt);
     }
+    if (g_apt_dump) memcpy(g_apt_dump, apt.data(), N * 32);
     uint32_t first[2] = {0, (uint32_t)N};
     uint8_t e[32], st;
     hh_segmented(asc.data(), apt.data(), first, 1, e, &st);
