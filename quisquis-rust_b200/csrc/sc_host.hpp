@@ -178,7 +178,7 @@ QQ_SC_FN void w32_mul_c1(uint32_t out[5], uint32_t h) {      // out = c * h, h o
     }
     out[4] = (uint32_t)carry;
 }
-QQ_SC_FN_BIG sc reduce512_w32(const uint32_t x[16]) {
+QQ_SC_FN sc reduce512_w32_inl(const uint32_t x[16]) {
     using namespace qq;
     const uint32_t C[4] = {0x5cf5d3edu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu};
     const uint32_t L2[8] = {0xb9eba7dau, 0xb024c634u, 0x45ef39acu, 0x29bdf3bdu, 0u, 0u, 0u, 0x20000000u};      // 2 l
@@ -247,14 +247,17 @@ QQ_SC_FN_BIG sc reduce512_w32(const uint32_t x[16]) {
     for (int i = 0; i < 4; i++) r.v[i] = (uint64_t)t[2 * i] | ((uint64_t)t[2 * i + 1] << 32);
     return r;
 }
-QQ_SC_FN_BIG sc mul_w32(const sc& a, const sc& b) {
+QQ_SC_FN_BIG sc reduce512_w32(const uint32_t x[16]) { return reduce512_w32_inl(x); }
+// One out-of-line function per product on the device: the factors travel by value (registers), the 512-bit product stays in
+// registers through the reduction (no generic loads / local stores between a caller, the product and the reduction).
+QQ_SC_FN_BIG sc mul_w32(sc a, sc b) {
     uint32_t A[8], B[8], x[16];
     for (int i = 0; i < 4; i++) {
         A[2 * i] = (uint32_t)a.v[i]; A[2 * i + 1] = (uint32_t)(a.v[i] >> 32);
         B[2 * i] = (uint32_t)b.v[i]; B[2 * i + 1] = (uint32_t)(b.v[i] >> 32);
     }
     qq::mp_mul8(x, A, B);
-    return reduce512_w32(x);
+    return reduce512_w32_inl(x);
 }
 
 // ---- lazy sums of products (the range-proof fold: sum over the proofs of a_p b_p) -----------------------------------------
@@ -306,7 +309,7 @@ QQ_SC_FN_BIG sc shl_minus_wide(const sc& a, int k, const uint32_t x[16]) {
     return reduce512_w32(w);
 }
 
-QQ_SC_FN_BIG sc mul(const sc& a, const sc& b) {
+QQ_SC_FN sc mul(const sc& a, const sc& b) {
 #if defined(__CUDA_ARCH__)
     return mul_w32(a, b);
 #else
