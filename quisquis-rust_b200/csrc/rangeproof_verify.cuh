@@ -173,12 +173,12 @@ QQ_HOSTDEV static inline uint8_t transcript_phase(qq_merlin::transcript& tr, con
         sBt = add(sBt, mul(rho, neg(add(e_b, mul(c, t_xb)))));
         // the proof's own points
         uint8_t* po = p_out + (size_t)32 * sh.T * q;
-        memcpy(po, pr, 128);                                            // A, S, T_1, T_2
+        qq_sc::copy_aligned16(po, pr, 128);                                            // A, S, T_1, T_2
         for (int k = 0; k < lg; k++) {
-            memcpy(po + 32 * (4 + k), pr + 224 + 64 * k, 32);           // L_k
-            memcpy(po + 32 * (4 + lg + k), pr + 224 + 64 * k + 32, 32);  // R_k
+            qq_sc::copy_aligned16(po + 32 * (4 + k), pr + 224 + 64 * k, 32);           // L_k
+            qq_sc::copy_aligned16(po + 32 * (4 + lg + k), pr + 224 + 64 * k + 32, 32);  // R_k
         }
-        memcpy(po + 32 * (4 + 2 * lg), V, (size_t)32 * sh.m);
+        qq_sc::copy_aligned16(po + 32 * (4 + 2 * lg), V, (size_t)32 * sh.m);
     }
     if (pre != QQ_ST_OK) {      // left out of the aggregate: zero scalars on a decodable point
         memset((void*)rec, 0, sh.chain * sizeof(record));

@@ -49,10 +49,40 @@ QQ_SC_FN bool geq_l(const uint64_t a[4]) {
 }
 // canonical 32 little-endian bytes -> sc; false when the value is >= l
 QQ_SC_FN bool from_bytes(sc& out, const uint8_t b[32]) {
+#if defined(__CUDA_ARCH__)
+    if ((reinterpret_cast<uintptr_t>(b) & 15) == 0) {      // two 16-byte loads instead of 32 byte loads
+        const uint4 lo = reinterpret_cast<const uint4*>(b)[0], hi = reinterpret_cast<const uint4*>(b)[1];
+        out.v[0] = (uint64_t)lo.x | ((uint64_t)lo.y << 32);
+        out.v[1] = (uint64_t)lo.z | ((uint64_t)lo.w << 32);
+        out.v[2] = (uint64_t)hi.x | ((uint64_t)hi.y << 32);
+        out.v[3] = (uint64_t)hi.z | ((uint64_t)hi.w << 32);
+        return !geq_l(out.v);
+    }
+#endif
     memcpy(out.v, b, 32);
     return !geq_l(out.v);
 }
-QQ_SC_FN void to_bytes(uint8_t b[32], const sc& a) { memcpy(b, a.v, 32); }
+QQ_SC_FN void to_bytes(uint8_t b[32], const sc& a) {
+#if defined(__CUDA_ARCH__)
+    // device: two 16-byte stores when the destination allows it (a memcpy to a byte pointer is 32 byte stores)
+    if ((reinterpret_cast<uintptr_t>(b) & 15) == 0) {
+        reinterpret_cast<uint4*>(b)[0] = make_uint4((uint32_t)a.v[0], (uint32_t)(a.v[0] >> 32), (uint32_t)a.v[1], (uint32_t)(a.v[1] >> 32));
+        reinterpret_cast<uint4*>(b)[1] = make_uint4((uint32_t)a.v[2], (uint32_t)(a.v[2] >> 32), (uint32_t)a.v[3], (uint32_t)(a.v[3] >> 32));
+        return;
+    }
+#endif
+    memcpy(b, a.v, 32);
+}
+// n bytes (a multiple of 16), 16 at a time when both ends are 16-byte aligned (device); the plain memcpy otherwise
+QQ_SC_FN void copy_aligned16(uint8_t* d, const uint8_t* s, size_t n) {
+#if defined(__CUDA_ARCH__)
+    if (((reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(s) | n) & 15) == 0) {
+        for (size_t i = 0; i < n / 16; i++) reinterpret_cast<uint4*>(d)[i] = reinterpret_cast<const uint4*>(s)[i];
+        return;
+    }
+#endif
+    memcpy(d, s, n);
+}
 
 QQ_SC_FN sc add(const sc& a, const sc& b) {
     const uint64_t L[4] = QQ_SC_L_WORDS;
