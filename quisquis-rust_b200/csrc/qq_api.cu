@@ -823,18 +823,22 @@ static int core_generate_commitment(qq_ctx* ctx, const uint8_t* pk, const uint8_
                                     uint8_t* status, size_t n) {
     for (size_t base = 0; base < n; base += QQ_CHUNK) {
         size_t m = n - base < QQ_CHUNK ? n - base : QQ_CHUNK;
-        CKQ(ws_begin(ctx, ws_need({2 * m * QQ_PT_BYTES, 2 * m * QQ_PT_BYTES, m * QQ_PT_BYTES, 2 * m, vb_scratch_bytes(ctx, 1)}) + dc_scratch_bytes(m)));
+        CKQ(ws_begin(ctx, ws_need({2 * m * QQ_PT_BYTES, 2 * m * QQ_PT_BYTES, m * QQ_PT_BYTES, 2 * m, vb_scratch_bytes(ctx, 1)}) + 2 * dc_scratch_bytes(m)));
         u32x4* P = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);
         u32x4* R = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);
         u32x4* F = ws_take<u32x4>(ctx, m * QQ_PT_BYTES);
         uint8_t* ok = ws_take<uint8_t>(ctx, 2 * m);
         u32x4* scratch = ws_take<u32x4>(ctx, vb_scratch_bytes(ctx, 1));
         dc_ws dc = dc_take(ctx, m);
+        dc_ws dc2 = dc_take(ctx, m);      // the second encoder's own inversion tree: the two run side by side
         const uint8_t* pk_c = pk + base * 64;
         const uint8_t* r_c = r + base * 32;
         const uint8_t* v_c = v + base * 32;
         // small batches: the fixed-base walk and the second encoder run on a copy stream (see core_update_account)
-        const bool fan = small_fanout(ctx, m) && m <= QQ_DC_DIRECT_MAX && ctx->vbc_max_jobs != 0;   // the direct encoder needs no shared scratch
+        // small batches: the fixed-base walk and the second encoder run on a copy stream (see core_update_account); large ones: the
+        // second encoder only (its batch inversion is a chain of one-block launches, 0.4 ms during which the GPU is idle)
+        const bool fan = small_fanout(ctx, m);
+        const bool side = ctx->small_fanout && ctx->copy_in != nullptr;
         if (fan) {
             CK(cudaEventRecord(ctx->msm_ev[8], ctx->stream));
             CK(cudaStreamWaitEvent(ctx->copy_in, ctx->msm_ev[8], 0));
@@ -845,15 +849,15 @@ static int core_generate_commitment(qq_ctx* ctx, const uint8_t* pk, const uint8_
         // every term carries half its scalar; the outputs are enc(2 * sum)
         CKQ(launch_varbase(ctx, 1, P, IDENT, r_c, nullptr, 2, R, nullptr, scratch, 2 * m, 1));
         if (!fan) CKQ(launch_fixedbase(ctx, QQ_BASE_B, v_c, F, m, 1));
-        if (fan) {
+        if (side) {
             CK(cudaEventRecord(ctx->msm_ev[9], ctx->stream));
             CK(cudaStreamWaitEvent(ctx->copy_in, ctx->msm_ev[9], 0));
         }
         CKQ(launch_finish_dbl(ctx, dc, fsrc(R, imap(1, 2, 0)), FNONE, FNONE, out + base * 64, imap(1, 2, 0), status + base, 1, m));
-        CKQ(on_stream(ctx, fan ? ctx->copy_in : ctx->stream, [&] {
-            return launch_finish_dbl(ctx, dc, fsrc(R, imap(1, 2, 1)), fsrc(F, IDENT), FNONE, out + base * 64, imap(1, 2, 1), status + base, 1, m);
+        CKQ(on_stream(ctx, side ? ctx->copy_in : ctx->stream, [&] {
+            return launch_finish_dbl(ctx, dc2, fsrc(R, imap(1, 2, 1)), fsrc(F, IDENT), FNONE, out + base * 64, imap(1, 2, 1), status + base, 1, m);
         }));
-        if (fan) {
+        if (side) {
             CK(cudaEventRecord(ctx->msm_ev[10], ctx->copy_in));
             CK(cudaStreamWaitEvent(ctx->stream, ctx->msm_ev[10], 0));
         }
@@ -945,7 +949,7 @@ static int core_verify_account(qq_ctx* ctx, const uint8_t* acc, const uint8_t* s
                                size_t n) {
     for (size_t base = 0; base < n; base += QQ_CHUNK) {
         size_t m = n - base < QQ_CHUNK ? n - base : QQ_CHUNK;
-        CKQ(ws_begin(ctx, ws_need({2 * m * QQ_PT_BYTES, 2 * m * QQ_PT_BYTES, m * QQ_PT_BYTES, 2 * m, 2 * m, m, vb_scratch_bytes(ctx, 1)}) + dc_scratch_bytes(m)));
+        CKQ(ws_begin(ctx, ws_need({2 * m * QQ_PT_BYTES, 2 * m * QQ_PT_BYTES, m * QQ_PT_BYTES, 2 * m, 2 * m, m, vb_scratch_bytes(ctx, 1)}) + 2 * dc_scratch_bytes(m)));
         u32x4* P = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);  // gr, c
         u32x4* R = ws_take<u32x4>(ctx, 2 * m * QQ_PT_BYTES);  // sk*gr, sk*c
         u32x4* F = ws_take<u32x4>(ctx, m * QQ_PT_BYTES);      // bl*B
@@ -954,9 +958,11 @@ static int core_verify_account(qq_ctx* ctx, const uint8_t* acc, const uint8_t* s
         uint8_t* pre = ws_take<uint8_t>(ctx, m);
         u32x4* scratch = ws_take<u32x4>(ctx, vb_scratch_bytes(ctx, 1));
         dc_ws dc = dc_take(ctx, m);
+        dc_ws dc2 = dc_take(ctx, m);      // the second encoder's own inversion tree (they run side by side)
         const uint8_t* acc_c = acc + base * 128;
         const uint8_t *sk_c = sk + base * 32, *bl_c = bl + base * 32;
-        const bool fan = small_fanout(ctx, m) && m <= QQ_DC_DIRECT_MAX && ctx->vbc_max_jobs != 0;   // the direct encoder needs no shared scratch
+        const bool fan = small_fanout(ctx, m);
+        const bool side = ctx->small_fanout && ctx->copy_in != nullptr;      // large batches too: the second encoder beside the first
         if (fan) {
             CK(cudaEventRecord(ctx->msm_ev[8], ctx->stream));
             CK(cudaStreamWaitEvent(ctx->copy_in, ctx->msm_ev[8], 0));
@@ -966,17 +972,17 @@ static int core_verify_account(qq_ctx* ctx, const uint8_t* acc, const uint8_t* s
         CKQ(launch_status(ctx, sk_c, bl_c, nullptr, ok, 0, pre, m));
         CKQ(launch_varbase(ctx, 1, P, IDENT, sk_c, nullptr, 2, R, nullptr, scratch, 2 * m, 1));
         if (!fan) CKQ(launch_fixedbase(ctx, QQ_BASE_B, bl_c, F, m, 1));
-        if (fan) {
+        if (side) {
             CK(cudaEventRecord(ctx->msm_ev[9], ctx->stream));
             CK(cudaStreamWaitEvent(ctx->copy_in, ctx->msm_ev[9], 0));
         }
         // grsk == enc(sk*gr)                       reference src/ristretto/keys.rs:187-195
         CKQ(launch_finish_dbl(ctx, dc, fsrc(R, imap(1, 2, 0)), FNONE, FNONE, nullptr, IDENT, nullptr, 1, m, acc_c, imap(1, 4, 1), eq));
         // d == enc(bl*B + sk*c)                    reference src/elgamal/elgamal.rs:81-95
-        CKQ(on_stream(ctx, fan ? ctx->copy_in : ctx->stream, [&] {
-            return launch_finish_dbl(ctx, dc, fsrc(R, imap(1, 2, 1)), fsrc(F, IDENT), FNONE, nullptr, IDENT, nullptr, 1, m, acc_c, imap(1, 4, 3), eq + m);
+        CKQ(on_stream(ctx, side ? ctx->copy_in : ctx->stream, [&] {
+            return launch_finish_dbl(ctx, dc2, fsrc(R, imap(1, 2, 1)), fsrc(F, IDENT), FNONE, nullptr, IDENT, nullptr, 1, m, acc_c, imap(1, 4, 3), eq + m);
         }));
-        if (fan) {
+        if (side) {
             CK(cudaEventRecord(ctx->msm_ev[10], ctx->copy_in));
             CK(cudaStreamWaitEvent(ctx->stream, ctx->msm_ev[10], 0));
         }
