@@ -926,8 +926,17 @@ static int core_update_account(qq_ctx* ctx, const uint8_t* acc, const uint8_t* b
             CK(cudaStreamWaitEvent(ctx->copy_in, ctx->msm_ev[9], 0));
             CK(cudaStreamWaitEvent(ctx->copy_out, ctx->msm_ev[9], 0));
         }
-        // pk' = (u*gr, u*grsk)
-        CKQ(launch_finish_dbl(ctx, dc, fsrc(Ru, IDENT), FNONE, FNONE, out_c, imap(2, 4, 0, 1), status + base, 2, 2 * m));
+        // pk' = (u*gr, u*grsk).  Large batches: the batch encoder's inversion tree is a chain of one-block launches (0.4 ms per
+        // 2^18 accounts with the GPU idle); it runs on the high-priority stream while the two classic encoders below fill the SMs.
+        const bool side_big = !fan && ctx->small_fanout && ctx->msm_hi != nullptr && m >= 4096;
+        if (side_big) {
+            CK(cudaEventRecord(ctx->msm_ev[9], ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->msm_hi, ctx->msm_ev[9], 0));
+        }
+        CKQ(on_stream(ctx, side_big ? ctx->msm_hi : ctx->stream, [&] {
+            return launch_finish_dbl(ctx, dc, fsrc(Ru, IDENT), FNONE, FNONE, out_c, imap(2, 4, 0, 1), status + base, 2, 2 * m);
+        }));
+        if (side_big) CK(cudaEventRecord(ctx->msm_ev[10], ctx->msm_hi));
         // comm' = (c*gr + a.c, bl*B + c*grsk + a.d)        -- OLD pk, reference src/accounts/accounts.rs:149-152
         CKQ(on_stream(ctx, fan ? ctx->copy_out : ctx->stream, [&] {
             return launch_finish(ctx, fsrc(Rc, imap(1, 2, 0)), fsrc(P, imap(1, 4, 2)), FNONE, out_c, imap(1, 4, 2), status + base, m);
@@ -941,6 +950,7 @@ static int core_update_account(qq_ctx* ctx, const uint8_t* acc, const uint8_t* b
             CK(cudaStreamWaitEvent(ctx->stream, ctx->msm_ev[10], 0));
             CK(cudaStreamWaitEvent(ctx->stream, ctx->msm_ev[11], 0));
         }
+        if (side_big) CK(cudaStreamWaitEvent(ctx->stream, ctx->msm_ev[10], 0));
     }
     return QQ_OK;
 }
