@@ -175,6 +175,27 @@ __global__ void __launch_bounds__(256) k_msm_points_prepare(const u32x4* __restr
     }
 }
 
+// the same for slots that were rewritten after an early k_msm_points_prepare: slot i belongs to owner i / cap; owners whose flag
+// says "unchanged" (flag == 0 when keep_is_zero, flag != 0 otherwise) are left alone (batched verifiers: a proof that left
+// the aggregate got its points replaced)
+__global__ void __launch_bounds__(256) k_msm_points_reprepare(const u32x4* __restrict__ points, size_t n, unsigned int cap,
+                                                              const uint8_t* __restrict__ flag, int keep_is_zero,
+                                                              u32x4* __restrict__ niels, uint8_t* __restrict__ ok_out) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const bool unchanged = keep_is_zero ? flag[i / cap] == 0 : flag[i / cap] != 0;
+        if (unchanged) continue;
+        u32 w[8];
+        load_words32(w, points, i);
+        ge_p3 p;
+        u32 ok = ristretto_decompress(p, w);
+        ge_niels nl;
+        ge_to_niels_z1(nl, p);
+        niels_store_padded(niels + (size_t)QQ_NIELS_STRIDE_Q * i, nl);
+        ok_out[i] = (uint8_t)ok;
+    }
+}
+
 // ---- exclusive scan of `total` counters -----------------------------------------------------------------------------
 // Tile = 4096 counters per 1024-thread block (4 per thread, warp-shuffle scan).  PASS 0 writes each tile's total,
 // PASS 1 (one block) scans the tile totals in place, PASS 2 rescans every tile and adds its tile offset.

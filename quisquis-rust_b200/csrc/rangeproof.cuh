@@ -53,6 +53,25 @@ __global__ void __launch_bounds__(160) k_rp_tables(const rp_record* __restrict__
     rp_tables& o = tbl[blockIdx.x];
     (t == 0 ? o.sa : t == 1 ? o.sb : t == 2 ? o.slo : t == 3 ? o.yhi : o.ylo)[e] = v;
 }
+// The points of every (sub-)proof's T MSM terms, straight from the proof and commitment bytes (the layout transcript_phase
+// writes: A, S, T_1, T_2 | L_k | R_k | V_j): done before the transcripts so that their decompression can run beside them.
+__global__ void __launch_bounds__(256) k_rp_points(const uint8_t* __restrict__ proofs, const uint8_t* __restrict__ commitments, size_t nsub,
+                                                   unsigned int T, unsigned int lg, unsigned int m, unsigned int proof_bytes,
+                                                   uint8_t* __restrict__ p_out) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < nsub * T; t += stride) {
+        const size_t q = t / T;
+        const unsigned int s = (unsigned int)(t - q * T);
+        const uint8_t* pr = proofs + q * proof_bytes;
+        const uint8_t* src = s < 4 ? pr + 32 * s
+                           : s < 4 + lg ? pr + 224 + 64 * (s - 4)
+                           : s < 4 + 2 * lg ? pr + 224 + 64 * (s - 4 - lg) + 32
+                           : commitments + 32 * ((size_t)m * q + (s - 4 - 2 * lg));
+        const uint4 a = reinterpret_cast<const uint4*>(src)[0], b = reinterpret_cast<const uint4*>(src)[1];
+        reinterpret_cast<uint4*>(p_out + 32 * t)[0] = a;
+        reinterpret_cast<uint4*>(p_out + 32 * t)[1] = b;
+    }
+}
 // grid = (ceil(N / block), chunks); partial: chunks x 2N scalars (g sums then h sums)
 // chunk_first == nullptr: the count (sub-)proofs from `first` on are split evenly over the chunks.  Otherwise (the grouped form:
 // one chunk per group, its partial sums are the group's generator scalars) chunk y covers the per_chunk (sub-)proofs from

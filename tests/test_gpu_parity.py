@@ -1972,3 +1972,34 @@ def test_msm_pipelined_tail_forms_agree(pkg):
                 assert es == 0 and exp.tobytes() == o
         e.close()
     assert outs[0] == outs[1] == outs[2]
+
+
+@pytest.mark.gpu
+def test_range_proofs_with_early_decompression(pkg):
+    """QQ_VERIFY_EARLY_DECOMPRESS=1 (the aggregated MSM's points decompressed on a copy stream beside the transcript kernel, proof points
+    placed by k_rp_points, slots of rejected transcripts prepared again): the same verdicts as the default path on tiled golden proofs
+    with tampered ones (a scalar-level failure that leaves the aggregate, a point-level failure that fails it)."""
+    import os
+    m = 4
+    per = m * 32 + (9 + 2 * ((64 * m).bit_length() - 1)) * 32
+    raw = np.fromfile(os.path.join(os.path.dirname(__file__), "golden", "range_proofs_m%d.bin" % m), dtype=np.uint8).reshape(-1, per)
+    n = 700
+    rec = np.tile(raw, ((n + raw.shape[0] - 1) // raw.shape[0], 1))[:n].copy()
+    rec[5, m * 32 + 32 * 4 + 3] ^= 1          # t_x: a scalar of proof 5
+    rec[77, m * 32 + 7] ^= 0x40               # A of proof 77: another point (or an undecodable one)
+    rec[n - 1, 3] ^= 1                        # a commitment of the last proof
+    cm, pr = np.ascontiguousarray(rec[:, :m * 32]), np.ascontiguousarray(rec[:, m * 32:])
+    out = []
+    for knob in ("0", "1"):
+        os.environ["QQ_VERIFY_EARLY_DECOMPRESS"] = knob
+        try:
+            e = pkg.Engine(0)
+        finally:
+            del os.environ["QQ_VERIFY_EARLY_DECOMPRESS"]
+        st = e.verify_range_proofs(cm, pr, m)
+        clean = e.verify_range_proofs(np.ascontiguousarray(np.tile(raw, (40, 1))[:, :m * 32]), np.ascontiguousarray(np.tile(raw, (40, 1))[:, m * 32:]), m)
+        assert not clean.any()
+        out.append(st.tolist())
+        e.close()
+    assert out[0] == out[1]
+    assert sorted(i for i, v in enumerate(out[0]) if v) == [5, 77, n - 1]
