@@ -136,11 +136,11 @@ struct qq_ctx {
     int msm_pipe_ranks = 1;
     long msm_pipe_min = 1 << 17;
     unsigned transcript_lanes = 32;  // threads per block of the one-thread-per-proof transcript kernels (QQ_TRANSCRIPT_LANES: 8, 16, 32)
-    // range-proof verifier: the MSM's points decompressed on a copy stream beside the transcripts (QQ_VERIFY_EARLY_DECOMPRESS=1).  Off by
-    // default: 4 096 x 16 values 2.84 -> 2.62 ms and 4 096 x 4 values 2.08 -> 1.98 ms, but 4 096 single-value proofs 1.78 -> 2.64 ms
-    // (the decompression kernel takes the SMs' register files first and the one-warp-per-SM transcript kernel runs 1.55 instead of
-    // 0.56 ms)
-    bool verify_early_decompress = false;
+    // range-proof verifier: the MSM's points decompressed on a copy stream beside the transcripts.  -1 (default): for batches of up to
+    // 1 024 transcripts (1 / 64 / 512 proofs: -0.07 ms, 5 %); 1: always (4 096 x 16 values 2.85 -> 2.68 ms, but 4 096 single-value proofs
+    // 1.79 -> 2.65 ms: with a transcript warp on every SM the decompression slows the transcript kernel down by more than it hides);
+    // 0: never.  QQ_VERIFY_EARLY_DECOMPRESS.
+    int verify_early_decompress = -1;
     bool small_fanout = true;        // small batches: independent launches of one call on the copy streams (QQ_SMALL_FANOUT)
     bool msm_horner_warp = true;     // window Horner with one limb per lane (ge_warp.cuh); false: the four-lane form (A/B knob)
     bool secret_mode = false;                  // qq_set_secret_mode: constant-time table access for scalars that are secrets
@@ -594,7 +594,7 @@ extern "C" int qq_init(qq_ctx** out, int device) {
             if (const char* e = getenv("QQ_MSM_SHIFT_BUDGET_MB")) ctx->msm_shift_budget = (size_t)atol(e) << 20;
             if (const char* e = getenv("QQ_MSM_HORNER_WARP")) ctx->msm_horner_warp = atoi(e) != 0;
             if (const char* e = getenv("QQ_SMALL_FANOUT")) ctx->small_fanout = atoi(e) != 0;
-            if (const char* e = getenv("QQ_VERIFY_EARLY_DECOMPRESS")) ctx->verify_early_decompress = atoi(e) != 0;
+            if (const char* e = getenv("QQ_VERIFY_EARLY_DECOMPRESS")) ctx->verify_early_decompress = atoi(e);
             if (const char* e = getenv("QQ_TRANSCRIPT_LANES")) { int v = atoi(e); if (v == 4 || v == 8 || v == 16 || v == 32) ctx->transcript_lanes = (unsigned)v; }
             if (const char* e = getenv("QQ_MSM_PIPE_RANKS")) { int v = atoi(e); if (v >= 1 && v <= 4) ctx->msm_pipe_ranks = v; }
             if (const char* e = getenv("QQ_MSM_PIPE_MIN")) { long v = atol(e); if (v >= 1) ctx->msm_pipe_min = v; }
