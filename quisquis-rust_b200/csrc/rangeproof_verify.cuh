@@ -119,7 +119,11 @@ QQ_HOSTDEV static inline uint8_t transcript_phase(qq_merlin::transcript& tr, con
             sc prefix[QQ_RP_MAX_LG + 2];
             prefix[0] = one();
             for (int k = 0; k <= lg; k++) prefix[k + 1] = mul(prefix[k], u[k]);
+#ifdef __CUDA_ARCH__
+            sc inv_all = invert_fixed(prefix[lg + 1]);        // no divergent branches, operands in registers (sc_host.hpp)
+#else
             sc inv_all = invert_vartime(prefix[lg + 1]);      // public challenges: the variable-time inversion is fine
+#endif
             for (int k = lg; k >= 0; k--) {
                 sc v = u[k];
                 u[k] = mul(inv_all, prefix[k]);

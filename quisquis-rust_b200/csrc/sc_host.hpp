@@ -448,4 +448,62 @@ QQ_SC_FN_BIG sc invert_vartime(const sc& a) {
     return r;
 }
 
+// a^-1 without data-dependent branches or addressing: the binary extended Euclid with the subtraction and the halving merged,
+// 508 fixed rounds (bit lengths of u and v sum to at most 506 and every round takes one off), every choice a mask.  For the GPU:
+// invert_vartime's three-way branch diverges inside a warp and its pointer-selected operands live in local memory - it was 36 % of
+// the range-proof transcript kernel (profiles/ncu_segments_*).  Same result; invert_fixed(0) = 0.
+//   u even:          u /= 2,            x1 /= 2
+//   u odd (u >= v after a swap):  u = (u - v) / 2,  x1 = (x1 - x2) / 2        (mod l; v stays odd)
+QQ_SC_FN_BIG sc invert_fixed(const sc& a) {
+    const uint64_t L[4] = QQ_SC_L_WORDS;
+    const uint64_t L2[4] = {0xb024c634b9eba7daULL, 0x29bdf3bd45ef39acULL, 0ULL, 0x2000000000000000ULL};      // 2 l
+    uint64_t u[4] = {a.v[0], a.v[1], a.v[2], a.v[3]}, v[4] = {L[0], L[1], L[2], L[3]};
+    uint64_t x1[4] = {1, 0, 0, 0}, x2[4] = {0, 0, 0, 0};
+    for (int it = 0; it < 508; it++) {
+        const uint64_t odd = 0 - (u[0] & 1);
+        u128 br = 0;
+        for (int i = 0; i < 4; i++) {
+            u128 d = (u128)u[i] - v[i] - (uint64_t)br;
+            br = (d >> 64) & 1;
+        }
+        const uint64_t sw = odd & (0 - (uint64_t)br);      // u odd and u < v: swap the pairs
+        for (int i = 0; i < 4; i++) {
+            uint64_t t = (u[i] ^ v[i]) & sw;
+            u[i] ^= t;
+            v[i] ^= t;
+            t = (x1[i] ^ x2[i]) & sw;
+            x1[i] ^= t;
+            x2[i] ^= t;
+        }
+        br = 0;
+        for (int i = 0; i < 4; i++) {
+            u128 d = (u128)u[i] - (v[i] & odd) - (uint64_t)br;
+            u[i] = (uint64_t)d;
+            br = (d >> 64) & 1;
+        }
+        for (int i = 0; i < 3; i++) u[i] = (u[i] >> 1) | (u[i + 1] << 63);
+        u[3] >>= 1;
+        // t = x1 - (x2 & odd) in (-l, l); + k l with k in {0, 1, 2} making it non-negative and even (l is odd), then halved: < l
+        uint64_t t[4];
+        br = 0;
+        for (int i = 0; i < 4; i++) {
+            u128 d = (u128)x1[i] - (x2[i] & odd) - (uint64_t)br;
+            t[i] = (uint64_t)d;
+            br = (d >> 64) & 1;
+        }
+        const uint64_t neg = 0 - (uint64_t)br, par = 0 - (t[0] & 1);
+        const uint64_t m1 = (neg & par) | (~neg & par);      // k == 1: parity odd (negative or not)
+        const uint64_t m2 = neg & ~par;                     // k == 2: negative and even
+        u128 c = 0;
+        for (int i = 0; i < 4; i++) {
+            c += (u128)t[i] + ((L[i] & m1) | (L2[i] & m2));
+            t[i] = (uint64_t)c;
+            c >>= 64;
+        }
+        for (int i = 0; i < 3; i++) x1[i] = (t[i] >> 1) | (t[i + 1] << 63);
+        x1[3] = t[3] >> 1;
+    }
+    return sc{{x2[0], x2[1], x2[2], x2[3]}};
+}
+
 }  // namespace qq_sc

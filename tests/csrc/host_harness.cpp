@@ -283,7 +283,7 @@ int hh_sc_op(uint8_t* out, int op, const uint8_t* a, const uint8_t* b) {
     } else {
         if (!qq_sc::from_bytes(x, a) || !qq_sc::from_bytes(y, b)) return 0;
         r = op == 0 ? qq_sc::add(x, y) : op == 1 ? qq_sc::sub(x, y) : op == 2 ? qq_sc::mul(x, y) : op == 3 ? qq_sc::invert(x)
-          : op == 6 ? qq_sc::mul_w32(x, y) : qq_sc::invert_vartime(x);
+          : op == 6 ? qq_sc::mul_w32(x, y) : op == 8 ? qq_sc::invert_fixed(x) : qq_sc::invert_vartime(x);
     }
     qq_sc::to_bytes(out, r);
     return 1;

@@ -263,7 +263,10 @@ def test_host_scalar_field(hh):
         inv = op(3, a, 0)
         assert inv * a % L == 1
         assert op(5, a, 0) == inv              # binary extended Euclid (invert_vartime) == a^(l - 2)
-    assert op(5, 0, 0) == 0
+        assert op(8, a, 0) == inv              # the branch-free fixed-round form the GPU runs (invert_fixed)
+    assert op(5, 0, 0) == 0 and op(8, 0, 0) == 0
+    for a in [2**k for k in range(1, 252, 7)] + [L - 2**k for k in range(1, 252, 7)] + [rnd.randrange(1, L) for _ in range(300)]:
+        assert op(8, a, 0) * a % L == 1
     wides = [2**512 - 1, (L << 256) + L - 1, (2**256 - 1) << 256, 2**511, (L - 1) ** 2, L * L, L * L - 1, 2**252, 2**252 - 1, L, L - 1,
              2 * L, (2**252) * (2**260 - 1), 2**504 + 2**252 - 1, (1 << 512) - (1 << 252)]
     wides += [rnd.getrandbits(512) for _ in range(400)] + [rnd.getrandbits(512) | ((2**260 - 1) << 252) for _ in range(50)]
